@@ -1,0 +1,164 @@
+/* include/wfsa_dev.h -- C ABI of the B200 evaluation backend for w-fsa.
+ *
+ * This is the drop-in boundary.  The reference has no FFI layer: the
+ * hot path sits behind C++ member functions of `Learner` that share protected vectors
+ * (/root/reference/inc/Learner.h:24,54,56,65,83,89-102,143-168).  Each entry point below
+ * names the reference member(s) it replaces.  Plain pointers and sizes only; no C++ or torch
+ * types cross this line; nothing throws; every call returns a wfsa_status.
+ *
+ * Data contracts (same as the reference):
+ *   - x holds natural-log weights of the TRIMMED parameters (src/Learner.cpp:350-436);
+ *   - p is normalised over the WHOLE corpus, unrecognised strings included (src/main.cpp:154);
+ *   - per-string outputs are in the caller's string order (corpus order of this shard).
+ * Ownership: the caller owns every host buffer; descriptors are copied at create time;
+ * the backend owns all device memory.  Calls are synchronous unless named *_launch and a
+ * handle is not re-entrant.
+ */
+#ifndef WFSA_DEV_H
+#define WFSA_DEV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    WFSA_OK = 0,
+    WFSA_ERR_INVALID = 1,      /* bad argument / inconsistent descriptor                     */
+    WFSA_ERR_CUDA = 2,         /* CUDA runtime error (message via wfsa_dev_last_error)       */
+    WFSA_ERR_NO_DEVICE = 3,    /* no usable sm_100 device: there is NO CPU fallback          */
+    WFSA_ERR_EPS_CYCLE = 4,    /* empty-emission cycle: path sum diverges (reference loops)  */
+    WFSA_ERR_STATE = 5,        /* call order violated (e.g. eval before set_param_map)       */
+    WFSA_ERR_LIMIT = 6,        /* automaton exceeds a compiled limit                         */
+    WFSA_ERR_NCCL = 7,         /* NCCL unavailable or failed                                 */
+    WFSA_ERR_NOMEM = 8
+} wfsa_status;
+
+/* Lowered automaton: what replaces Fsa::State / NamedProb / NextState
+ * (inc/Fsa.h:26-66).  States are dense ids; an emission is a sequence of 0..L tokens
+ * (the reference's emission strings, possibly empty); the emission consumed on a step is the
+ * one of the TARGET state (inc/Recognize.h:49-57).  Edge parameter ids follow
+ * Fsa::AssignIndices (src/Fsa.cpp:207-238): -1 for the single emission / single transition
+ * of a state, otherwise a raw parameter id in [0, n_raw_params). */
+typedef struct {
+    int32_t n_states;            /* including start and end                                  */
+    int32_t start_state;
+    int32_t end_state;
+    int32_t n_symbols;           /* tokens are in [0, n_symbols); <0 in a corpus = unknown   */
+    int32_t n_raw_params;
+    const int32_t* emis_row;     /* [n_states+1] CSR of emission edges by state              */
+    const int32_t* emis_tok_off; /* [n_emis+1]   token range of each emission edge           */
+    const int32_t* emis_tok;     /* [emis_tok_off[n_emis]]                                   */
+    const int32_t* emis_param;   /* [n_emis]     raw parameter id or -1                      */
+    const int32_t* trans_row;    /* [n_states+1] CSR of transition edges by source state     */
+    const int32_t* trans_dst;    /* [n_trans]                                                */
+    const int32_t* trans_param;  /* [n_trans]    raw parameter id or -1                      */
+} wfsa_fsa_desc;
+
+/* Packed corpus shard: replaces Corpus = vector<pair<string,double>> (inc/Corpus.h:16). */
+typedef struct {
+    int64_t n_strings;
+    const int64_t* offsets;      /* [n_strings+1] */
+    const int32_t* tokens;       /* [offsets[n_strings]] */
+    const double*  p;            /* [n_strings] normalised over the whole corpus */
+} wfsa_corpus_desc;
+
+typedef struct {
+    int32_t device;              /* CUDA device ordinal                                       */
+    int32_t force_kernel;        /* 0 auto, 1 warp-per-string, 2 CTA-per-string, 3 generic    */
+    int32_t accum_mode;          /* 0 auto, 1 shared-memory accumulators, 2 global (L2) REDs  */
+    int32_t reserved;
+} wfsa_dev_options;
+
+typedef struct wfsa_dev wfsa_dev;
+
+/* Builds the device layout (combined arcs in CSR by (state, symbol), packed int32 tokens in
+ * length buckets) and uploads it.  Replaces the data side of Learner::BuildFrom
+ * (src/Learner.cpp:269-274) and Learner::Finalize's MKL handle creation (:483-485). */
+int wfsa_dev_create(const wfsa_fsa_desc* fsa, const wfsa_corpus_desc* corpus,
+                    const wfsa_dev_options* opt, wfsa_dev** out);
+
+/* Structural pass: replaces Learner::BuildPaths' recognition loop
+ * (src/Learner.cpp:276-348 driving inc/Recognize.h:62-96).  recognised[s] = 1 iff the string
+ * has an accepting path; path_count[s] = number of accepting paths (a double; the DP counts,
+ * it does not enumerate); param_used[i] = 1 iff raw parameter i lies on an accepting path of
+ * some string of this shard (feeds Learner::Trim, :350-425).  Any pointer may be NULL. */
+int wfsa_dev_structure(wfsa_dev* h, uint8_t* recognised, double* path_count, uint8_t* param_used);
+
+/* trimmed[i] for every raw parameter: -2 unused (weight exp(-inf)=0), -1 pinned (weight 1),
+ * otherwise index into x (src/Learner.cpp:427-436).  n = number of trimmed parameters.
+ * recognised (or NULL = all) selects the strings that take part in evaluations; with several
+ * ranks it must be called after the used-flags were combined across ranks. */
+int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32_t n, const uint8_t* recognised);
+
+/* One evaluation = Learner::ComputeModeledProbs + ComputeObjective (src/Learner.cpp:515-553)
+ * + {QuasiNewton,Hessian}Learner::ComputeGrad (src/QuasiNewtonLearner.cpp:93-125,
+ * src/HessianLearner.cpp:565-597):
+ *   loglik = sum_s p_s log q_s   (KL = plogp - loglik),   grad_i = -sum_s p_s E_s[count_i].
+ * With a communicator attached both are the sums over ALL ranks.  logq (may be NULL) receives
+ * log q_s of this shard's strings, -inf/NaN-free only for recognised strings (others: -inf). */
+int wfsa_dev_eval(wfsa_dev* h, const double* x, double* loglik, double* logq, double* grad);
+
+/* Same evaluation with x already resident (last uploaded x); results stay on the device.
+ * Used for kernel-only timing and by callers that pipeline their own copies. */
+int wfsa_dev_upload_x(wfsa_dev* h, const double* x);
+int wfsa_dev_eval_launch(wfsa_dev* h);           /* asynchronous on the handle's stream */
+int wfsa_dev_eval_fetch(wfsa_dev* h, double* loglik, double* logq, double* grad);
+int wfsa_dev_sync(wfsa_dev* h);
+
+/* H_f block of HessianLearner::ComputeHf (src/HessianLearner.cpp:498-547):
+ *   Hf[j*n+k] = sum_s p_s ( g_j g_k - sum_pi r_pi P_pij P_pik ),  full symmetric n x n, row major.
+ * Paths of ambiguous strings are supplied as dense count blocks: for block b,
+ * rows = paths, cols = the block's parameter list.  */
+typedef struct {
+    int64_t n_blocks;
+    const int64_t* path_off;     /* [n_blocks+1] paths of block b: path_off[b]..path_off[b+1]   */
+    const int64_t* col_off;      /* [n_blocks+1] parameter list of block b                       */
+    const int32_t* cols;         /* [col_off[n_blocks]] trimmed parameter ids                    */
+    const int64_t* val_off;      /* [n_blocks+1] start of block b's row-major (paths x cols) data */
+    const double*  counts;       /* [val_off[n_blocks]]                                          */
+    const double*  p;            /* [n_blocks] p_s of the block's string                         */
+} wfsa_path_blocks;
+int wfsa_dev_set_path_blocks(wfsa_dev* h, const wfsa_path_blocks* blocks);
+int wfsa_dev_hessian(wfsa_dev* h, const double* x, double* Hf /* n*n */, double* rmin /* or NULL */);
+
+/* Multi-GPU: one handle per process/GPU; results of eval/structure/hessian are all-reduced
+ * (ncclAllReduce, exact integer sums, so any rank count gives bitwise identical results). */
+#define WFSA_UNIQUE_ID_BYTES 128
+int wfsa_dev_comm_unique_id(void* id_out /* WFSA_UNIQUE_ID_BYTES */);
+int wfsa_dev_comm_init(wfsa_dev* h, const void* id, int rank, int nranks);
+
+/* Sum (op 0) or max (op 1) of n host doubles over all ranks, in place; a no-op without a
+ * communicator.  For the O(1) host scalars of Learner (common support, plogp, counts). */
+int wfsa_dev_allreduce_f64(wfsa_dev* h, double* values, int n, int op);
+
+/* Timing on the handle's own stream with CUDA events (torch events cannot see this stream). */
+int wfsa_dev_timer_begin(wfsa_dev* h);
+int wfsa_dev_timer_end(wfsa_dev* h, float* ms);
+/* ms spent in the dominant kernel (forward-backward) over the launches since timer_begin. */
+int wfsa_dev_timer_kernel_ms(wfsa_dev* h, float* ms, int64_t* launches);
+
+/* Introspection */
+typedef struct {
+    int32_t kernel;              /* 1 warp-per-string, 2 CTA-per-string, 3 generic              */
+    int32_t accum_mode;          /* 1 shared, 2 global                                          */
+    int32_t n_trans, n_emis, n_arcs, n_slots;
+    int32_t max_candidates;      /* max over symbols of states emitting it                      */
+    int32_t sm_count, grid, block;
+    int64_t n_strings, n_active_strings, n_tokens, n_active_tokens;
+    int64_t smem_bytes, table_bytes;
+    int64_t kernels_launched;    /* total kernels this handle has launched                      */
+    double  fixed_point_scale_log2;
+} wfsa_dev_info;
+int wfsa_dev_get_info(wfsa_dev* h, wfsa_dev_info* info);
+
+void wfsa_dev_destroy(wfsa_dev* h);
+const char* wfsa_dev_last_error(const wfsa_dev* h);   /* h may be NULL: last create() error */
+const char* wfsa_dev_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WFSA_DEV_H */

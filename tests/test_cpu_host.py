@@ -1,0 +1,113 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports what include/*.h declares, the host
+parsers reproduce the reference's counts and error behaviour on every golden case, and the
+device entry point fails loudly (no CPU fallback) when there is no GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import wfsa_b200 as W
+from helpers import all_cases, fnum, key
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(wfsa_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = W.lib()
+    names = declared("wfsa_dev.h") + declared("wfsa_host.h")
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), "libwfsa_b200.so does not export %s" % n
+    assert set(W.DEV_SYMBOLS) <= set(names) and set(W.HOST_SYMBOLS) <= set(names)
+    assert b"sm_100a" in lib.wfsa_dev_version()
+
+
+@pytest.mark.parametrize("case", all_cases(), ids=lambda c: c["name"])
+def test_parsers_match_reference_counts(case):
+    if "reference_error" in case:
+        with pytest.raises(W.WfsaError) as ei:
+            W.parse(case["fsa_text"], case["corpus_text"])
+        assert ei.value.code == 100 and "Invalid FSA format" in ei.value.message
+        return
+    d = W.parse(case["fsa_text"], case["corpus_text"])
+    for k in ("corpus_size", "states", "transitions", "emissions", "raw_parameters", "raw_constraints"):
+        assert d[k] == case[k], k
+    assert abs(fnum(d["corpus_sum"]) - fnum(case["corpus_sum"])) < 1e-12
+    assert [w["word"] for w in d["corpus"]] == [w["word"] for w in case["corpus"]]
+    s = sum(fnum(w["weight"]) for w in d["corpus"])
+    for mine, ref in zip(d["corpus"], case["corpus"]):
+        assert abs(fnum(mine["weight"]) / s - fnum(ref["p"])) < 1e-15
+    mine = {key(e): e for e in d["edges"]}
+    assert set(mine) == {key(e) for e in case["edges"]}
+    for e in case["edges"]:
+        assert (mine[key(e)]["raw"] >= 0) == (e["raw"] >= 0)
+        assert fnum(mine[key(e)]["file_logprob"]) == fnum(e["file_logprob"])
+
+
+def test_parser_error_behaviour():
+    ok_corpus = "\na 1\n"
+    bad = {
+        "start emits": "\n^\n$\n^ x 0\n^ a 0\na a 0\na $ 0\n",
+        "duplicate emission": "\n^\n$\n^  0\n^ a 0\na a 0 a 1\na $ 0\n",
+        "duplicate transition": "\n^\n$\n^  0\n^ a 0 a 1\na a 0\na $ 0\n",
+        "into start": "\n^\n$\n^  0\n^ a 0\na a 0\na ^ 0 $ 0\n",
+        "missing transitions": "\n^\n$\n^  0\n^ a 0\na a 0\nb b 0\n",
+        "start == end": "\n^\n^\n^  0\n^ a 0\n",
+    }
+    for what, text in bad.items():
+        with pytest.raises(W.WfsaError) as ei:
+            W.parse(text, ok_corpus)
+        assert ei.value.code == 100, what
+    with pytest.raises(W.WfsaError) as ei:
+        W.parse("\n^\n$\n^  0\n^ a 0\na a 0\na $ 0\n", "\na 1\na 2\n")
+    assert "duplicate" in ei.value.message
+    with pytest.raises(W.WfsaError):
+        W.parse("\n^\n$\n^  0\n^ a 0\na a 0\na $ 0\n", "\na 0\n")          # weight must be normal
+    with pytest.raises(W.WfsaError):
+        W.parse("\n^\n$\n^  0\n^ a 0\na a 0\na $ 0\n", "\na -1\n")
+    # a trailing separator is tolerated, a multi-character separator works, tokens are concatenated
+    d = W.parse("::\n^\n$\n^::::0\n^::a::0\na::a::0::bb::1\na::$::0\n", "::\na::b::b::2::\nx::1\n")
+    assert [w["word"] for w in d["corpus"]] == ["abb", "x"] and d["raw_parameters"] == 2
+
+
+def test_lowering_descriptor_shapes():
+    case = [c for c in all_cases() if c["name"] == "talk.wfsa+talk.corpus"][0]
+    low = W.Lowered(W.parse(case["fsa_text"], case["corpus_text"]))
+    assert low.n_states == 6 and low.n_trans == 6 and low.n_emis == 8 and low.n_raw == 7
+    assert low.emis_row[-1] == 8 and low.trans_row[-1] == 6
+    lens = np.diff(low.emis_tok_off)
+    assert sorted(lens.tolist()) == [0, 0, 0, 1, 1, 2, 4, 4]          # "", "", "", s, s, ed, talk, talk
+    assert low.offsets[-1] == sum(len(w) for w in low.words)
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a CUDA device the product must fail loudly, not compute somewhere else."""
+    case = [c for c in all_cases() if c["name"] == "talk.wfsa+talk.corpus"][0]
+    low = W.Lowered(W.parse(case["fsa_text"], case["corpus_text"]))
+    try:
+        dev = W.Device(low)
+    except W.WfsaError as e:
+        assert e.code == 3 and "no CPU fallback" in e.message
+        with pytest.raises(W.WfsaError):
+            W.Session(case["fsa_text"], case["corpus_text"])
+    else:
+        dev.close()
+        pytest.skip("a GPU is present")
+
+
+def test_descriptor_validation():
+    case = [c for c in all_cases() if c["name"] == "talk.wfsa+talk.corpus"][0]
+    low = W.Lowered(W.parse(case["fsa_text"], case["corpus_text"]))
+    low.trans_dst = low.trans_dst.copy()
+    low.trans_dst[0] = 99
+    with pytest.raises(W.WfsaError) as ei:
+        W.Device(low)
+    assert ei.value.code == 1                                          # WFSA_ERR_INVALID before any CUDA call

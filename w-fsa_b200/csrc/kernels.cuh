@@ -1,0 +1,865 @@
+// w-fsa_b200/csrc/kernels.cuh -- sm_100a kernels of the w-fsa evaluation backend.
+//
+// What they compute (the reference obtains the same numbers by path
+// enumeration + sparse algebra, /root/reference/src/Learner.cpp:515-553,
+// src/QuasiNewtonLearner.cpp:93-125):
+//   alpha_t[v] = b(v,c_t) * sum_u a(u,v) alpha_{t-1}[u]          forward
+//   q          = sum_u alpha_{T-1}[u] a(u,end)
+//   beta~_t[u] = b(u,c_t) * sum_v a(u,v) beta~_{t+1}[v]           backward (beta~ carries b)
+//   gamma(u->v at t) = alpha_t[u] a(u,v) beta~_{t+1}[v] / q       posterior of a combined arc
+//   acc[arc] += p_s * gamma          (64-bit fixed point => order independent, bitwise
+//                                     reproducible for any grid size and any number of GPUs)
+// All arithmetic is FP64 in the linear domain with lazy power-of-two rescaling (exact),
+// so results equal the unscaled computation bit for bit whenever that would not under/overflow.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wfsa {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int kSlotBitsD = 10;
+constexpr int kRowCntBitsD = 8;
+constexpr int kRescaleEvery = 4;       // positions between exponent checks
+constexpr int kRescaleBand = 300;      // rescale when the largest entry leaves 2^(+-300)
+
+enum { MODE_EVAL = 0, MODE_STRUCT = 1 };
+enum { ACC_SMEM_CAS = 0, ACC_SMEM_SPLIT = 1, ACC_GLOBAL = 2 };
+
+struct FastTablesD {
+    const uint32_t* __restrict__ cand_off;    // [n_sym+2]
+    const uint32_t* __restrict__ slot_state;  // [n_slots]
+    const uint32_t* __restrict__ frow;        // [n_states*(n_sym+1)]
+    const uint32_t* __restrict__ fent;
+    const uint32_t* __restrict__ brow;        // [n_states*n_sym]
+    const uint32_t* __restrict__ bent;
+    int n_sym, n_states, n_arcs, n_slots, start_state, start_final_tid;
+};
+
+struct EvalWeightsD {
+    const double* __restrict__ tw;   // [n_trans] transition weights
+    const double* __restrict__ sw;   // [n_slots] emission weight of the slot
+    const double* __restrict__ fw;   // [n_slots] weight of slot-state -> end (0 if none)
+};
+
+struct CorpusD {
+    const int32_t* __restrict__ tokens;
+    const int64_t* __restrict__ offs;     // [n_strings+1]
+    const double* __restrict__ p;         // [n_strings]
+    const int32_t* __restrict__ order;    // [n_order] string ids, longest first
+    int64_t n_order;
+};
+
+struct EvalOutD {
+    double* logq;                    // [n_strings] (string id order) or nullptr
+    double* path_count;              // MODE_STRUCT: [n_strings]
+    unsigned long long* acc_global;  // [n_arcs + n_slots] combined-arc / final-transition accumulators
+    unsigned long long* red;         // red[0] = fixed-point loglik, red[1] = non-finite strings,
+                                     // red[2 + e] = per-edge accumulators
+    double fx_scale;                 // 2^k fixed-point scale of the accumulators
+    double ll_scale;                 // fixed-point scale of loglik
+};
+
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ int biased_exp(double a) { return (__double2hiint(a) >> 20) & 0x7ff; }
+
+template <int ACC>
+__device__ __forceinline__ void acc_add(unsigned long long* acc_s, unsigned long long* acc_g, int idx, long long v)
+{
+    if (v == 0) return;
+    if (ACC == ACC_GLOBAL) {
+        atomicAdd(acc_g + idx, (unsigned long long)v);                       // REDG.E.ADD.64
+    } else if (ACC == ACC_SMEM_CAS) {
+        atomicAdd(acc_s + idx, (unsigned long long)v);                       // ATOMS.CAS.64 loop
+    } else {
+        // exact 64-bit add out of two native 32-bit shared atomics (carry from the returned word)
+        unsigned* w = reinterpret_cast<unsigned*>(acc_s + idx);
+        const unsigned lo = (unsigned)v, hi = (unsigned)((unsigned long long)v >> 32);
+        const unsigned old = atomicAdd(w, lo);
+        const unsigned add_hi = hi + ((old + lo < old) ? 1u : 0u);
+        if (add_hi) atomicAdd(w + 1, add_hi);
+    }
+}
+
+__device__ __forceinline__ void stack_st(unsigned long long* s, unsigned long long* g, int cap, int i, unsigned long long v)
+{
+    if (i < cap) s[i] = v; else g[i - cap] = v;
+}
+__device__ __forceinline__ unsigned long long stack_ld(const unsigned long long* s, const unsigned long long* g, int cap, int i)
+{
+    return (i < cap) ? s[i] : g[i - cap];
+}
+
+struct K2Params {
+    FastTablesD T;
+    EvalWeightsD W;
+    CorpusD C;
+    EvalOutD O;
+    int n_acc_smem;                  // accumulators kept in shared memory (0 => ACC_GLOBAL)
+    int stack_cap;                   // lattice stack words per warp in shared memory
+    unsigned long long* gl_stack;    // overflow of the lattice stacks
+    size_t gl_stack_words;           // per warp
+};
+
+// ------------------------------------------------------------------------------------------
+// K2: one warp per string, candidates of the current symbol across lanes (<= 32 of them),
+// alpha/beta in registers, gathers through warp shuffles, lattice on a per-warp stack.
+// ------------------------------------------------------------------------------------------
+template <int MODE, int ACC>
+__global__ void __launch_bounds__(1024, 1) k2_fwdbwd(const K2Params P)
+{
+    extern __shared__ unsigned long long smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    unsigned long long* acc_s = smem;
+    unsigned long long* stack = smem + P.n_acc_smem + (size_t)warp * P.stack_cap;
+    const long long gw = (long long)blockIdx.x * nwarps + warp, GW = (long long)gridDim.x * nwarps;
+    unsigned long long* gstack = P.gl_stack + (size_t)gw * P.gl_stack_words;
+    const int cap = P.stack_cap;
+    for (int i = threadIdx.x; i < P.n_acc_smem; i += blockDim.x) acc_s[i] = 0ull;
+    __syncthreads();
+
+    const FastTablesD& T = P.T;
+    const int A = T.n_sym;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    long long ll_fx = 0;
+    unsigned long long bad = 0;
+
+    for (long long it = gw; it < P.C.n_order; it += GW) {
+        const int sid = P.C.order[it];
+        const long long off = P.C.offs[sid];
+        const int len = (int)(P.C.offs[sid + 1] - off);
+        const double ps = P.C.p[sid];
+        const int32_t* tok = P.C.tokens + off;
+
+        if (len == 0) {   // the empty string is accepted iff start -> end exists
+            if (lane == 0) {
+                const double q = T.start_final_tid >= 0 ? P.W.tw[T.start_final_tid] : 0.0;
+                if (MODE == MODE_STRUCT) {
+                    P.O.path_count[sid] = q;
+                    if (q != 0.0) atomicAdd(P.O.red + 2 + T.start_final_tid, 1ull);
+                } else {
+                    const double lq = log(q);
+                    if (P.O.logq) P.O.logq[sid] = lq;
+                    if (q > 0.0 && isfinite(lq)) {
+                        ll_fx += __double2ll_rn(ps * lq * P.O.ll_scale);
+                        atomicAdd(P.O.red + 2 + T.start_final_tid, (unsigned long long)__double2ll_rn(ps * P.O.fx_scale));
+                    } else bad++;
+                }
+            }
+            continue;
+        }
+
+        // ---------------- forward ----------------
+        double alpha = (lane == 0) ? 1.0 : 0.0;   // START pseudo position: only the start state
+        int E = 0, sp = 0, cprev = A, tokreg = 0;
+        bool dead = false;
+        uint32_t slot = 0;
+        for (int t = 0; t < len; ++t) {
+            if ((t & 31) == 0) tokreg = (t + lane < len) ? __ldcs(tok + t + lane) : -1;
+            const int c = __shfl_sync(FULL, tokreg, t & 31);
+            if ((unsigned)c >= (unsigned)A) { dead = true; break; }
+            const uint32_t c0 = T.cand_off[c], ncand = T.cand_off[c + 1] - c0;
+            const bool valid = (uint32_t)lane < ncand;
+            slot = c0 + lane;
+            uint32_t row = 0;
+            if (valid) row = T.frow[(size_t)T.slot_state[slot] * (A + 1) + cprev];
+            const int cnt = row & ((1u << kRowCntBitsD) - 1);
+            const uint32_t st = row >> kRowCntBitsD;
+            const int maxcnt = __reduce_max_sync(FULL, cnt);
+            double a_new = 0.0;
+            for (int k = 0; k < maxcnt; ++k) {
+                uint32_t ent = 0; double a = 0.0;
+                if (k < cnt) { ent = T.fent[st + k]; a = P.W.tw[ent >> kSlotBitsD]; }
+                const double au = __shfl_sync(FULL, alpha, ent & 31);
+                a_new = fma(a, au, a_new);
+            }
+            alpha = valid ? a_new * P.W.sw[slot] : 0.0;
+            const unsigned mask = __ballot_sync(FULL, alpha != 0.0);
+            if (mask == 0) { dead = true; break; }
+            if ((t & (kRescaleEvery - 1)) == kRescaleEvery - 1) {
+                const int emax = __reduce_max_sync(FULL, alpha != 0.0 ? biased_exp(alpha) : -1);
+                if (emax < 1023 - kRescaleBand || emax > 1023 + kRescaleBand) {
+                    const int shift = 1023 - emax;
+                    alpha = scalbn(alpha, shift);
+                    E -= shift;
+                }
+            }
+            // push [values..., meta] on the lattice stack
+            const int n = __popc(mask);
+            if (alpha != 0.0) stack_st(stack, gstack, cap, sp + __popc(mask & lt_mask), (unsigned long long)__double_as_longlong(alpha));
+            if (lane == 0) stack_st(stack, gstack, cap, sp + n, (unsigned long long)mask | ((unsigned long long)(unsigned)E << 32));
+            sp += n + 1;
+            cprev = c;
+        }
+        double qh = 0.0, fin = 0.0;
+        if (!dead) {
+            fin = (alpha != 0.0) ? P.W.fw[slot] : 0.0;   // slot of the last position
+            qh = warp_sum(alpha * fin);
+        }
+        if (dead || !(qh > 0.0) || !isfinite(qh)) {
+            if (lane == 0) {
+                if (MODE == MODE_STRUCT) P.O.path_count[sid] = 0.0;
+                else { if (P.O.logq) P.O.logq[sid] = -INFINITY; bad++; }
+            }
+            continue;
+        }
+        const int EQ = E;
+        if (lane == 0) {
+            if (MODE == MODE_STRUCT) P.O.path_count[sid] = scalbn(qh, EQ);
+            else {
+                const double lq = log(qh) + (double)EQ * 0.69314718055994530942;
+                if (P.O.logq) P.O.logq[sid] = lq;
+                ll_fx += __double2ll_rn(ps * lq * P.O.ll_scale);
+            }
+        }
+        __syncwarp();
+
+        // ---------------- backward ----------------
+        const double invq = 1.0 / qh;
+        double bt;            // beta~ of the position processed last
+        int F = 0, cnext;
+        {   // position len-1: beta = a(v,end); posterior of the final transition
+            const unsigned long long meta = stack_ld(stack, gstack, cap, sp - 1);
+            const unsigned mask = (unsigned)meta;
+            const int n = __popc(mask);
+            sp -= n + 1;
+            const bool on = (mask >> lane) & 1u;
+            // alpha (registers) still holds position len-1
+            if (on && fin != 0.0) {
+                if (MODE == MODE_STRUCT) acc_add<ACC>(acc_s, P.O.acc_global, T.n_arcs + (int)slot, 1);
+                else acc_add<ACC>(acc_s, P.O.acc_global, T.n_arcs + (int)slot,
+                                  __double2ll_rn(alpha * fin * invq * ps * P.O.fx_scale));
+            }
+            bt = on ? fin * P.W.sw[slot] : 0.0;
+            const int t = len - 1;
+            cnext = __shfl_sync(FULL, tokreg, t & 31);   // tokreg holds the last chunk
+        }
+        for (int t = len - 2; t >= 0; --t) {
+            if ((t & 31) == 31) tokreg = __ldg(tok + (t - 31) + lane);
+            const int c = __shfl_sync(FULL, tokreg, t & 31);
+            const uint32_t c0 = T.cand_off[c];
+            const unsigned long long meta = stack_ld(stack, gstack, cap, sp - 1);
+            const unsigned mask = (unsigned)meta;
+            const int Et = (int)(meta >> 32);
+            const int n = __popc(mask);
+            sp -= n + 1;
+            const bool on = (mask >> lane) & 1u;
+            slot = c0 + lane;
+            double al = 0.0;
+            uint32_t row = 0;
+            if (on) {
+                al = __longlong_as_double((long long)stack_ld(stack, gstack, cap, sp + __popc(mask & lt_mask)));
+                row = T.brow[(size_t)T.slot_state[slot] * A + cnext];
+            }
+            const int cnt = row & ((1u << kRowCntBitsD) - 1);
+            const uint32_t st = row >> kRowCntBitsD;
+            const int maxcnt = __reduce_max_sync(FULL, cnt);
+            const int d = Et + F - EQ;
+            double sc = invq * ps * P.O.fx_scale;
+            if (d != 0) sc = scalbn(sc, d);
+            double b = 0.0;
+            for (int k = 0; k < maxcnt; ++k) {
+                uint32_t ent = 0; double a = 0.0;
+                if (k < cnt) { ent = T.bent[st + k]; a = P.W.tw[ent >> kSlotBitsD]; }
+                const double term = a * __shfl_sync(FULL, bt, ent & 31);
+                b += term;
+                if (k < cnt && term != 0.0) {
+                    if (MODE == MODE_STRUCT) acc_add<ACC>(acc_s, P.O.acc_global, (int)(st + k), 1);
+                    else acc_add<ACC>(acc_s, P.O.acc_global, (int)(st + k), __double2ll_rn(al * term * sc));
+                }
+            }
+            bt = on ? b * P.W.sw[slot] : 0.0;
+            if ((t & (kRescaleEvery - 1)) == 0) {
+                const int emax = __reduce_max_sync(FULL, bt != 0.0 ? biased_exp(bt) : -1);
+                if (emax >= 0 && (emax < 1023 - kRescaleBand || emax > 1023 + kRescaleBand)) {
+                    const int shift = 1023 - emax;
+                    bt = scalbn(bt, shift);
+                    F -= shift;
+                }
+            }
+            cnext = c;
+        }
+        {   // arcs out of the start state: lane k handles entry k of row (start, c_0)
+            const uint32_t row = T.brow[(size_t)T.start_state * A + cnext];
+            const int cnt = row & ((1u << kRowCntBitsD) - 1);
+            const uint32_t st = row >> kRowCntBitsD;
+            uint32_t ent = 0; double a = 0.0;
+            if (lane < cnt) { ent = T.bent[st + lane]; a = P.W.tw[ent >> kSlotBitsD]; }
+            const double term = a * __shfl_sync(FULL, bt, ent & 31);
+            const int d = F - EQ;
+            double sc = invq * ps * P.O.fx_scale;
+            if (d != 0) sc = scalbn(sc, d);
+            if (lane < cnt && term != 0.0) {
+                if (MODE == MODE_STRUCT) acc_add<ACC>(acc_s, P.O.acc_global, (int)(st + lane), 1);
+                else acc_add<ACC>(acc_s, P.O.acc_global, (int)(st + lane), __double2ll_rn(term * sc));
+            }
+        }
+        __syncwarp();
+    }
+
+    if (lane == 0) {
+        if (ll_fx) atomicAdd(P.O.red, (unsigned long long)ll_fx);
+        if (bad) atomicAdd(P.O.red + 1, bad);
+    }
+    if (ACC != ACC_GLOBAL) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < P.n_acc_smem; i += blockDim.x) {
+            const unsigned long long v = acc_s[i];
+            if (v) atomicAdd(P.O.acc_global + i, v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: one CTA per string for automata where more than 32 states emit one symbol.
+// Thread i <-> candidate slot i of the current symbol; alpha / beta~ vectors double-buffered in
+// shared memory; the lattice (dense over candidates) goes to a per-CTA slab in global memory
+// (L2 resident: 148 x 2 slabs); accumulators are 64-bit REDs into L2.
+// ------------------------------------------------------------------------------------------
+struct K3Params {
+    FastTablesD T;
+    EvalWeightsD W;
+    CorpusD C;
+    EvalOutD O;
+    double* lattice;           // [grid][max_len][nt]
+    int* lat_exp;              // [grid][max_len]
+    int max_len;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(1024, 1) k3_fwdbwd(const K3Params P)
+{
+    extern __shared__ unsigned long long smem[];
+    const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    double* va = reinterpret_cast<double*>(smem);        // [2][nt] alpha or beta~
+    double* red = va + 2 * nt;                           // [32]
+    int* ired = reinterpret_cast<int*>(red + 32);        // [34]
+    const FastTablesD& T = P.T;
+    const int A = T.n_sym;
+    double* lat = P.lattice + (size_t)blockIdx.x * P.max_len * nt;
+    int* lexp = P.lat_exp + (size_t)blockIdx.x * P.max_len;
+    long long ll_fx = 0;
+    unsigned long long bad = 0;
+
+    for (long long it = blockIdx.x; it < P.C.n_order; it += gridDim.x) {
+        const int sid = P.C.order[it];
+        const long long off = P.C.offs[sid];
+        const int len = (int)(P.C.offs[sid + 1] - off);
+        const double ps = P.C.p[sid];
+        const int32_t* tok = P.C.tokens + off;
+        __syncthreads();
+        if (len == 0) {
+            if (tid == 0) {
+                const double q = T.start_final_tid >= 0 ? P.W.tw[T.start_final_tid] : 0.0;
+                if (MODE == MODE_STRUCT) {
+                    P.O.path_count[sid] = q;
+                    if (q != 0.0) atomicAdd(P.O.red + 2 + T.start_final_tid, 1ull);
+                } else {
+                    const double lq = log(q);
+                    if (P.O.logq) P.O.logq[sid] = lq;
+                    if (q > 0.0 && isfinite(lq)) {
+                        ll_fx += __double2ll_rn(ps * lq * P.O.ll_scale);
+                        atomicAdd(P.O.red + 2 + T.start_final_tid, (unsigned long long)__double2ll_rn(ps * P.O.fx_scale));
+                    } else bad++;
+                }
+            }
+            continue;
+        }
+        // ---------------- forward ----------------
+        int cur = 0, E = 0, cprev = A;
+        bool dead = false;
+        va[tid] = (tid == 0) ? 1.0 : 0.0;
+        __syncthreads();
+        uint32_t slot = 0;
+        double alpha = 0.0;
+        for (int t = 0; t < len; ++t) {
+            const int c = tok[t];
+            if ((unsigned)c >= (unsigned)A) { dead = true; break; }
+            const uint32_t c0 = T.cand_off[c], ncand = T.cand_off[c + 1] - c0;
+            const bool valid = (uint32_t)tid < ncand;
+            slot = c0 + tid;
+            alpha = 0.0;
+            if (valid) {
+                const uint32_t row = T.frow[(size_t)T.slot_state[slot] * (A + 1) + cprev];
+                const int cnt = row & ((1u << kRowCntBitsD) - 1);
+                const uint32_t st = row >> kRowCntBitsD;
+                const double* src = va + cur * nt;
+                double s = 0.0;
+                for (int k = 0; k < cnt; ++k) {
+                    const uint32_t ent = T.fent[st + k];
+                    s = fma(P.W.tw[ent >> kSlotBitsD], src[ent & ((1u << kSlotBitsD) - 1)], s);
+                }
+                alpha = s * P.W.sw[slot];
+            }
+            // any nonzero? (and the exponent of the largest entry every few positions)
+            const bool chk = (t & (kRescaleEvery - 1)) == kRescaleEvery - 1;
+            const int e = alpha != 0.0 ? biased_exp(alpha) : -1;
+            const int wmax = __reduce_max_sync(FULL, e);
+            if (lane == 0) ired[warp] = wmax;
+            __syncthreads();
+            int emax = -1;
+            for (int w = 0; w < nwarps; ++w) emax = max(emax, ired[w]);
+            if (emax < 0) { dead = true; break; }
+            if (chk && (emax < 1023 - kRescaleBand || emax > 1023 + kRescaleBand)) {
+                const int shift = 1023 - emax;
+                alpha = scalbn(alpha, shift);
+                E -= shift;
+            }
+            va[(cur ^ 1) * nt + tid] = alpha;
+            lat[(size_t)t * nt + tid] = alpha;
+            if (tid == 0) lexp[t] = E;
+            cur ^= 1;
+            cprev = c;
+            __syncthreads();
+        }
+        double qh = 0.0, fin = 0.0;
+        if (!dead) {
+            fin = (alpha != 0.0) ? P.W.fw[slot] : 0.0;
+            const double part = warp_sum(alpha * fin);
+            if (lane == 0) red[warp] = part;
+            __syncthreads();
+            for (int w = 0; w < nwarps; ++w) qh += red[w];    // fixed order
+        }
+        if (dead || !(qh > 0.0) || !isfinite(qh)) {
+            if (tid == 0) {
+                if (MODE == MODE_STRUCT) P.O.path_count[sid] = 0.0;
+                else { if (P.O.logq) P.O.logq[sid] = -INFINITY; bad++; }
+            }
+            continue;
+        }
+        const int EQ = E;
+        if (tid == 0) {
+            if (MODE == MODE_STRUCT) P.O.path_count[sid] = scalbn(qh, EQ);
+            else {
+                const double lq = log(qh) + (double)EQ * 0.69314718055994530942;
+                if (P.O.logq) P.O.logq[sid] = lq;
+                ll_fx += __double2ll_rn(ps * lq * P.O.ll_scale);
+            }
+        }
+        // ---------------- backward ----------------
+        const double invq = 1.0 / qh;
+        int F = 0, cnext = tok[len - 1];
+        if (alpha != 0.0 && fin != 0.0) {
+            if (MODE == MODE_STRUCT) atomicAdd(P.O.acc_global + T.n_arcs + slot, 1ull);
+            else atomicAdd(P.O.acc_global + T.n_arcs + slot, (unsigned long long)__double2ll_rn(alpha * fin * invq * ps * P.O.fx_scale));
+        }
+        __syncthreads();
+        cur = 0;
+        va[tid] = (alpha != 0.0) ? fin * P.W.sw[slot] : 0.0;
+        __syncthreads();
+        for (int t = len - 2; t >= 0; --t) {
+            const int c = tok[t];
+            const uint32_t c0 = T.cand_off[c];
+            slot = c0 + tid;
+            const double al = lat[(size_t)t * nt + tid];
+            const int Et = lexp[t];
+            const int d = Et + F - EQ;
+            double sc = invq * ps * P.O.fx_scale;
+            if (d != 0) sc = scalbn(sc, d);
+            double bt = 0.0;
+            if (al != 0.0) {
+                const uint32_t row = T.brow[(size_t)T.slot_state[slot] * A + cnext];
+                const int cnt = row & ((1u << kRowCntBitsD) - 1);
+                const uint32_t st = row >> kRowCntBitsD;
+                const double* src = va + cur * nt;
+                double b = 0.0;
+                for (int k = 0; k < cnt; ++k) {
+                    const uint32_t ent = T.bent[st + k];
+                    const double term = P.W.tw[ent >> kSlotBitsD] * src[ent & ((1u << kSlotBitsD) - 1)];
+                    b += term;
+                    if (term != 0.0) {
+                        if (MODE == MODE_STRUCT) atomicAdd(P.O.acc_global + st + k, 1ull);
+                        else {
+                            const long long v = __double2ll_rn(al * term * sc);
+                            if (v) atomicAdd(P.O.acc_global + st + k, (unsigned long long)v);
+                        }
+                    }
+                }
+                bt = b * P.W.sw[slot];
+            }
+            if ((t & (kRescaleEvery - 1)) == 0) {
+                const int wmax = __reduce_max_sync(FULL, bt != 0.0 ? biased_exp(bt) : -1);
+                if (lane == 0) ired[warp] = wmax;
+                __syncthreads();
+                int emax = -1;
+                for (int w = 0; w < nwarps; ++w) emax = max(emax, ired[w]);
+                if (emax >= 0 && (emax < 1023 - kRescaleBand || emax > 1023 + kRescaleBand)) {
+                    const int shift = 1023 - emax;
+                    bt = scalbn(bt, shift);
+                    F -= shift;
+                }
+            }
+            va[(cur ^ 1) * nt + tid] = bt;
+            cur ^= 1;
+            cnext = c;
+            __syncthreads();
+        }
+        {   // arcs out of the start state
+            const uint32_t row = T.brow[(size_t)T.start_state * A + cnext];
+            const int cnt = row & ((1u << kRowCntBitsD) - 1);
+            const uint32_t st = row >> kRowCntBitsD;
+            const int d = F - EQ;
+            double sc = invq * ps * P.O.fx_scale;
+            if (d != 0) sc = scalbn(sc, d);
+            const double* src = va + cur * nt;
+            for (int k = tid; k < cnt; k += nt) {
+                const uint32_t ent = T.bent[st + k];
+                const double term = P.W.tw[ent >> kSlotBitsD] * src[ent & ((1u << kSlotBitsD) - 1)];
+                if (term != 0.0) {
+                    if (MODE == MODE_STRUCT) atomicAdd(P.O.acc_global + st + k, 1ull);
+                    else {
+                        const long long v = __double2ll_rn(term * sc);
+                        if (v) atomicAdd(P.O.acc_global + st + k, (unsigned long long)v);
+                    }
+                }
+            }
+        }
+    }
+    if (tid == 0) {
+        if (ll_fx) atomicAdd(P.O.red, (unsigned long long)ll_fx);
+        if (bad) atomicAdd(P.O.red + 1, bad);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic path: emissions of any length (0, 1, 2, ... tokens), one thread per string, dense
+// log-domain lattice (len+1) x n_states in global scratch.  Correct for every automaton the
+// reference accepts (no empty-emission cycles); not tuned.
+// ------------------------------------------------------------------------------------------
+struct GenericTablesD {
+    const int32_t* __restrict__ emis_row;
+    const int32_t* __restrict__ emis_tok_off;
+    const int32_t* __restrict__ emis_tok;
+    const int32_t* __restrict__ trans_row;
+    const int32_t* __restrict__ trans_dst;
+    const int32_t* __restrict__ eps_order;
+    int n_states, n_trans, start_state, end_state;
+};
+struct GenericParams {
+    GenericTablesD G;
+    const double* __restrict__ ltw;    // log transition weights
+    const double* __restrict__ lew;    // log emission weights
+    CorpusD C;
+    EvalOutD O;
+    double* scratch;                   // [n_threads][2][(max_len+1)*n_states]
+    int max_len;
+    long long first, count;            // slice of C.order handled by this launch
+};
+
+__device__ __forceinline__ double logaddexp_d(double a, double b)
+{
+    if (a == -INFINITY) return b;
+    if (b == -INFINITY) return a;
+    const double m = fmax(a, b);
+    return m + log1p(exp(-fabs(a - b)));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) kg_fwdbwd(const GenericParams P)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.count) return;
+    const GenericTablesD& G = P.G;
+    const int S = G.n_states;
+    const int sid = P.C.order[P.first + i];
+    const long long off = P.C.offs[sid];
+    const int len = (int)(P.C.offs[sid + 1] - off);
+    const double ps = P.C.p[sid];
+    const int32_t* tok = P.C.tokens + off;
+    const size_t lat_sz = (size_t)(P.max_len + 1) * S;
+    double* la = P.scratch + (size_t)i * 2 * lat_sz;
+    double* lb = la + lat_sz;
+    for (size_t k = 0; k < (size_t)(len + 1) * S; ++k) { la[k] = -INFINITY; lb[k] = -INFINITY; }
+    la[G.start_state] = 0.0;
+    double lq = -INFINITY;
+    // forward
+    for (int pos = 0; pos <= len; ++pos) {
+        for (int oi = 0; oi < S; ++oi) {
+            const int u = G.eps_order[oi];
+            const double au = la[(size_t)pos * S + u];
+            if (au == -INFINITY || u == G.end_state) continue;
+            for (int t = G.trans_row[u]; t < G.trans_row[u + 1]; ++t) {
+                const int v = G.trans_dst[t];
+                const double w = au + P.ltw[t];
+                if (w == -INFINITY) continue;
+                if (v == G.end_state) {
+                    if (pos == len) lq = logaddexp_d(lq, w);
+                    continue;
+                }
+                for (int e = G.emis_row[v]; e < G.emis_row[v + 1]; ++e) {
+                    const int e0 = G.emis_tok_off[e], el = G.emis_tok_off[e + 1] - e0;
+                    if (pos + el > len) continue;
+                    bool m = true;
+                    for (int k = 0; k < el; ++k) if (tok[pos + k] != G.emis_tok[e0 + k]) { m = false; break; }
+                    if (!m) continue;
+                    double* dst = la + (size_t)(pos + el) * S + v;
+                    *dst = logaddexp_d(*dst, w + P.lew[e]);
+                }
+            }
+        }
+    }
+    if (!(lq > -INFINITY) || !isfinite(lq)) {
+        if (MODE == MODE_STRUCT) P.O.path_count[sid] = 0.0;
+        else { if (P.O.logq) P.O.logq[sid] = -INFINITY; atomicAdd(P.O.red + 1, 1ull); }
+        return;
+    }
+    if (MODE == MODE_STRUCT) P.O.path_count[sid] = exp(lq);
+    else {
+        if (P.O.logq) P.O.logq[sid] = lq;
+        atomicAdd(P.O.red, (unsigned long long)__double2ll_rn(ps * lq * P.O.ll_scale));
+    }
+    // backward: lb[pos][u] = log sum over continuations of (pos,u); posteriors on the way
+    unsigned long long* eacc = P.O.red + 2;
+    for (int pos = len; pos >= 0; --pos) {
+        for (int oi = S - 1; oi >= 0; --oi) {
+            const int u = G.eps_order[oi];
+            const double au = la[(size_t)pos * S + u];
+            if (au == -INFINITY || u == G.end_state) continue;
+            double bu = -INFINITY;
+            for (int t = G.trans_row[u]; t < G.trans_row[u + 1]; ++t) {
+                const int v = G.trans_dst[t];
+                const double w = P.ltw[t];
+                if (w == -INFINITY) continue;
+                if (v == G.end_state) {
+                    if (pos == len) {
+                        bu = logaddexp_d(bu, w);
+                        const double g = exp(au + w - lq);
+                        if (MODE == MODE_STRUCT) atomicAdd(eacc + t, 1ull);
+                        else { const long long fx = __double2ll_rn(g * ps * P.O.fx_scale); if (fx) atomicAdd(eacc + t, (unsigned long long)fx); }
+                    }
+                    continue;
+                }
+                for (int e = G.emis_row[v]; e < G.emis_row[v + 1]; ++e) {
+                    const int e0 = G.emis_tok_off[e], el = G.emis_tok_off[e + 1] - e0;
+                    if (pos + el > len) continue;
+                    bool m = true;
+                    for (int k = 0; k < el; ++k) if (tok[pos + k] != G.emis_tok[e0 + k]) { m = false; break; }
+                    if (!m) continue;
+                    const double bv = lb[(size_t)(pos + el) * S + v];
+                    if (bv == -INFINITY) continue;
+                    const double term = w + P.lew[e] + bv;
+                    if (term == -INFINITY) continue;
+                    bu = logaddexp_d(bu, term);
+                    if (MODE == MODE_STRUCT) { atomicAdd(eacc + t, 1ull); atomicAdd(eacc + G.n_trans + e, 1ull); }
+                    else {
+                        const long long fx = __double2ll_rn(exp(au + term - lq) * ps * P.O.fx_scale);
+                        if (fx) { atomicAdd(eacc + t, (unsigned long long)fx); atomicAdd(eacc + G.n_trans + e, (unsigned long long)fx); }
+                    }
+                }
+            }
+            lb[(size_t)pos * S + u] = bu;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// small kernels around the dominant one
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double weight_of(int tp, const double* x, int unit)
+{
+    if (unit || tp == -1) return 1.0;
+    if (tp < -1) return 0.0;
+    return exp(x[tp]);
+}
+__device__ __forceinline__ double logweight_of(int tp, const double* x, int unit)
+{
+    if (unit || tp == -1) return 0.0;
+    if (tp < -1) return -INFINITY;
+    return x[tp];
+}
+
+// edge weights from x: replaces the exp(P.x) of src/Learner.cpp:530-533 (per edge, not per path)
+__global__ void k_weights(int n_trans, int n_emis, int n_slots, const int32_t* __restrict__ trans_tp,
+                          const int32_t* __restrict__ emis_tp, const int32_t* __restrict__ slot_emis,
+                          const int32_t* __restrict__ slot_final, const double* __restrict__ x, int unit,
+                          double* tw, double* sw, double* fw, double* ltw, double* lew)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_trans) {
+        tw[i] = weight_of(trans_tp[i], x, unit);
+        ltw[i] = logweight_of(trans_tp[i], x, unit);
+    } else if (i < n_trans + n_emis) {
+        const int e = i - n_trans;
+        lew[e] = logweight_of(emis_tp[e], x, unit);
+    } else if (i < n_trans + n_emis + n_slots) {
+        const int s = i - n_trans - n_emis;
+        sw[s] = slot_emis[s] < 0 ? 1.0 : weight_of(emis_tp[slot_emis[s]], x, unit);
+        fw[s] = slot_final[s] < 0 ? 0.0 : weight_of(trans_tp[slot_final[s]], x, unit);
+    }
+}
+
+// combined-arc / final accumulators -> per-edge accumulators (integer adds: order independent)
+__global__ void k_arcs_to_edges(int n_arcs, int n_slots, int n_trans, const unsigned long long* __restrict__ acc,
+                                const int32_t* __restrict__ arc_tid, const int32_t* __restrict__ arc_eid,
+                                const int32_t* __restrict__ slot_final, unsigned long long* edge_acc)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_arcs) {
+        const unsigned long long v = acc[i];
+        if (v) {
+            atomicAdd(edge_acc + arc_tid[i], v);
+            if (arc_eid[i] >= 0) atomicAdd(edge_acc + n_trans + arc_eid[i], v);
+        }
+    } else if (i < n_arcs + n_slots) {
+        const unsigned long long v = acc[i];
+        const int f = slot_final[i - n_arcs];
+        if (v && f >= 0) atomicAdd(edge_acc + f, v);
+    }
+}
+
+// out[0] = loglik, out[1] = #non-finite strings, out[2+i] = grad_i = -sum_s p_s E_s[count_i]
+__global__ void k_finish_eval(int n_edges, int n, const unsigned long long* __restrict__ red,
+                              const int32_t* __restrict__ edge_tp, double inv_fx, double inv_ll, double* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        const double bad = (double)red[1];
+        out[0] = bad > 0 ? -INFINITY : (double)(long long)red[0] * inv_ll;
+        out[1] = bad;
+    }
+    if (i < n_edges) {
+        const int tp = edge_tp[i];
+        if (tp >= 0 && tp < n) out[2 + tp] = -(double)(long long)red[2 + i] * inv_fx;
+    }
+}
+
+__global__ void k_finish_struct(int n_edges, const unsigned long long* __restrict__ red,
+                                const int32_t* __restrict__ edge_raw, uint8_t* used)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_edges) {
+        const int r = edge_raw[i];
+        if (r >= 0) used[r] = red[2 + i] ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: H_f block, one warp per ambiguous string (block of paths x cols counts).
+//   r = softmax_l( sum_j P_lj x_j ),  g = P^T r,  H_s = p_s ( g g^T - P^T diag(r) P )
+// The contraction P^T diag(r) P runs on the FP64 tensor cores (mma.sync m8n8k4 DMMA):
+// tiles of 8x8 outputs, k = paths in chunks of 4.  Results are scattered into the dense n x n
+// H with fixed-point REDs (order independent).
+// ------------------------------------------------------------------------------------------
+struct HessParams {
+    int64_t n_blocks;
+    const int64_t* __restrict__ path_off;
+    const int64_t* __restrict__ col_off;
+    const int32_t* __restrict__ cols;
+    const int64_t* __restrict__ val_off;
+    const double* __restrict__ counts;
+    const double* __restrict__ p;
+    const double* __restrict__ x;
+    double* r_scratch;               // [total paths] posterior of every path
+    unsigned long long* H_fx;        // [n*n] fixed point
+    double* rmin;                    // [1] smallest path posterior (atomicMin on bits)
+    int n;
+    double fx_scale;
+};
+
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256) k5_hessian(const HessParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long GW = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long b = gw; b < P.n_blocks; b += GW) {
+        const long long p0 = P.path_off[b];
+        const int L = (int)(P.path_off[b + 1] - p0);
+        const long long c0 = P.col_off[b];
+        const int D = (int)(P.col_off[b + 1] - c0);
+        const double* M = P.counts + P.val_off[b];    // L x D row major
+        const int32_t* cols = P.cols + c0;
+        const double ps = P.p[b];
+        double* r = P.r_scratch + p0;
+        // path log-weights, softmax in a fixed order
+        double mx = -INFINITY;
+        for (int l = lane; l < L; l += 32) {
+            double s = 0.0;
+            for (int j = 0; j < D; ++j) s = fma(M[(size_t)l * D + j], P.x[cols[j]], s);
+            r[l] = s;
+            mx = fmax(mx, s);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
+        __syncwarp();
+        double z = 0.0;
+        for (int l = lane; l < L; l += 32) { const double e = exp(r[l] - mx); r[l] = e; z += e; }
+        z = warp_sum(z);
+        __syncwarp();
+        double rm = INFINITY;
+        for (int l = lane; l < L; l += 32) { const double v = r[l] / z; r[l] = v; rm = fmin(rm, v); }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) rm = fmin(rm, __shfl_xor_sync(FULL, rm, o));
+        if (lane == 0 && P.rmin) atomicMin(reinterpret_cast<unsigned long long*>(P.rmin), (unsigned long long)__double_as_longlong(rm));
+        __syncwarp();
+        // 8x8 output tiles; DMMA fragment layout (m8n8k4): A[row=lane/4][k=lane%4],
+        // B[k=lane%4][col=lane/4], C[row=lane/4][col=2*(lane%4)+{0,1}]
+        const int gi = lane >> 2, ti = lane & 3;
+        for (int jt = 0; jt < D; jt += 8) {
+            for (int kt = jt; kt < D; kt += 8) {
+                double c0v = 0.0, c1v = 0.0, g_a = 0.0, g_b0 = 0.0, g_b1 = 0.0;
+                for (int l0 = 0; l0 < L; l0 += 4) {
+                    const int l = l0 + ti;
+                    double a = 0.0, bb = 0.0;
+                    if (l < L) {
+                        const double rl = r[l];
+                        if (jt + gi < D) a = M[(size_t)l * D + jt + gi] * rl;    // (P^T diag r)[j][l]
+                        if (kt + gi < D) bb = M[(size_t)l * D + kt + gi];        // P[l][k]
+                    }
+                    dmma_m8n8k4(c0v, c1v, a, bb);
+                }
+                // g_j for the tile rows / cols: g = P^T r (tiny; recomputed per tile)
+                {
+                    const int jr = jt + gi;
+                    const int k0 = kt + 2 * ti, k1 = k0 + 1;
+                    for (int l = 0; l < L; ++l) {
+                        const double rl = r[l];
+                        if (jr < D) g_a = fma(M[(size_t)l * D + jr], rl, g_a);
+                        if (k0 < D) g_b0 = fma(M[(size_t)l * D + k0], rl, g_b0);
+                        if (k1 < D) g_b1 = fma(M[(size_t)l * D + k1], rl, g_b1);
+                    }
+                    const int row = jr;
+                    if (row < D) {
+                        const int pj = cols[row];
+                        if (k0 < D) {
+                            const long long v = __double2ll_rn(ps * (g_a * g_b0 - c0v) * P.fx_scale);
+                            const int pk = cols[k0];
+                            if (v) {
+                                atomicAdd(P.H_fx + (size_t)pj * P.n + pk, (unsigned long long)v);
+                                if (kt != jt) atomicAdd(P.H_fx + (size_t)pk * P.n + pj, (unsigned long long)v);
+                            }
+                        }
+                        if (k1 < D) {
+                            const long long v = __double2ll_rn(ps * (g_a * g_b1 - c1v) * P.fx_scale);
+                            const int pk = cols[k1];
+                            if (v) {
+                                atomicAdd(P.H_fx + (size_t)pj * P.n + pk, (unsigned long long)v);
+                                if (kt != jt) atomicAdd(P.H_fx + (size_t)pk * P.n + pj, (unsigned long long)v);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void k_fx_to_double(size_t n, const unsigned long long* __restrict__ in, double inv, double* out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)(long long)in[i] * inv;
+}
+
+}  // namespace wfsa

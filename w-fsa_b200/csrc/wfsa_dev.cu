@@ -1,0 +1,746 @@
+// w-fsa_b200/csrc/wfsa_dev.cu -- C ABI of the B200 evaluation backend (include/wfsa_dev.h).
+//
+// Host side of the device path: copies the lowered automaton and the packed corpus shard to
+// HBM once, then every evaluation is   H2D x  ->  k_weights -> forward-backward kernel
+// (K2 warp-per-string | K3 CTA-per-string | generic) -> arc->edge fold -> [ncclAllReduce]
+// -> k_finish_eval -> D2H [loglik, grad].   There is no CPU fallback: every entry point fails
+// with WFSA_ERR_NO_DEVICE / WFSA_ERR_CUDA when the GPU path cannot run.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/wfsa_dev.h"
+#include "kernels.cuh"
+#include "layout.hpp"
+
+using namespace wfsa;
+
+static thread_local std::string g_create_error;
+
+// ---- minimal NCCL binding, resolved at run time (libnccl.so.2 is only needed for n_ranks > 1)
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclInt64 = 4, ncclUint64 = 5, ncclInt32 = 2 };
+enum { ncclSum = 0, ncclMax = 2 };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load(std::string& err)
+    {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "libnccl lacks required symbols"; return false; }
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+template <class T> struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    cudaError_t alloc(size_t count) { release(); n = count; return count ? cudaMalloc(&p, count * sizeof(T)) : cudaSuccess; }
+    cudaError_t upload(const std::vector<T>& v, cudaStream_t s)
+    {
+        cudaError_t e = alloc(v.size());
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+}  // namespace
+
+struct wfsa_dev {
+    std::string err;
+    int device = 0, sm_count = 0, kernel = 0, accum = 0;
+    wfsa_dev_options opt{};
+    cudaStream_t stream = nullptr;
+    HostFsa fsa;
+    FastLayout fast;
+    GenericLayout gen;
+    // corpus shard
+    int64_t n_strings = 0, n_tokens = 0, n_active = 0, n_active_tokens = 0;
+    int max_len = 0;
+    std::vector<int64_t> h_offs;
+    std::vector<int32_t> h_order_all;          // all strings, longest first
+    DevBuf<int32_t> d_tokens, d_order;
+    DevBuf<int64_t> d_offs;
+    DevBuf<double> d_p;
+    // automaton tables
+    DevBuf<uint32_t> d_cand_off, d_slot_state, d_frow, d_fent, d_brow, d_bent;
+    DevBuf<int32_t> d_slot_emis, d_slot_final, d_arc_tid, d_arc_eid;
+    DevBuf<int32_t> d_emis_row, d_emis_tok_off, d_emis_tok, d_trans_row, d_trans_dst, d_eps_order;
+    DevBuf<int32_t> d_trans_tp, d_emis_tp, d_edge_tp, d_edge_raw;
+    // per evaluation
+    int n = -1;                                // trimmed parameters (-1: map not set)
+    int n_edges = 0;
+    DevBuf<double> d_x, d_tw, d_sw, d_fw, d_ltw, d_lew, d_logq, d_pathcnt, d_out;
+    DevBuf<unsigned long long> d_acc, d_red, d_glstack;
+    DevBuf<uint8_t> d_used;
+    DevBuf<double> d_k3lat; DevBuf<int> d_k3exp;
+    DevBuf<double> d_gscratch;
+    long long g_batch = 0;
+    double* h_out = nullptr;                   // pinned [2 + n]
+    double* h_x = nullptr;                     // pinned [n]
+    double fx_log2 = 0, ll_log2 = 44;
+    int grid = 0, block = 0, stack_cap = 0, n_acc_smem = 0;
+    size_t smem_bytes = 0, glstack_words = 0, table_bytes = 0;
+    int64_t launches = 0;
+    bool structure_done = false;
+    std::vector<uint8_t> h_recognised;
+    // Hessian
+    DevBuf<int64_t> d_hb_path_off, d_hb_col_off, d_hb_val_off;
+    DevBuf<int32_t> d_hb_cols;
+    DevBuf<double> d_hb_counts, d_hb_p, d_hb_r, d_H, d_rmin;
+    DevBuf<unsigned long long> d_Hfx;
+    int64_t hb_blocks = -1, hb_paths = 0;
+    // comm
+    ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
+    // timing
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kev;
+    size_t kev_used = 0; bool timing = false;
+};
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+            return WFSA_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+static int set_err(wfsa_dev* h, int code, const std::string& m) { if (h) h->err = m; return code; }
+
+static int nccl_allreduce(wfsa_dev* h, void* buf, size_t count, int dtype, int op)
+{
+    if (!h->comm) return WFSA_OK;
+    const int r = g_nccl.AllReduce(buf, buf, count, dtype, op, h->comm, h->stream);
+    if (r != ncclSuccess)
+        return set_err(h, WFSA_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+    return WFSA_OK;
+}
+
+extern "C" const char* wfsa_dev_version(void) { return "wfsa_b200 0.1 (sm_100a)"; }
+
+extern "C" const char* wfsa_dev_last_error(const wfsa_dev* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" void wfsa_dev_destroy(wfsa_dev* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    DevBuf<int32_t>* i32[] = {&h->d_tokens, &h->d_order, &h->d_slot_emis, &h->d_slot_final, &h->d_arc_tid, &h->d_arc_eid,
+                              &h->d_emis_row, &h->d_emis_tok_off, &h->d_emis_tok, &h->d_trans_row, &h->d_trans_dst,
+                              &h->d_eps_order, &h->d_trans_tp, &h->d_emis_tp, &h->d_edge_tp, &h->d_edge_raw, &h->d_hb_cols};
+    for (auto* b : i32) b->release();
+    DevBuf<uint32_t>* u32[] = {&h->d_cand_off, &h->d_slot_state, &h->d_frow, &h->d_fent, &h->d_brow, &h->d_bent};
+    for (auto* b : u32) b->release();
+    DevBuf<double>* f64[] = {&h->d_p, &h->d_x, &h->d_tw, &h->d_sw, &h->d_fw, &h->d_ltw, &h->d_lew, &h->d_logq, &h->d_pathcnt,
+                             &h->d_out, &h->d_k3lat, &h->d_gscratch, &h->d_hb_counts, &h->d_hb_p, &h->d_hb_r, &h->d_H, &h->d_rmin};
+    for (auto* b : f64) b->release();
+    DevBuf<int64_t>* i64[] = {&h->d_offs, &h->d_hb_path_off, &h->d_hb_col_off, &h->d_hb_val_off};
+    for (auto* b : i64) b->release();
+    h->d_acc.release(); h->d_red.release(); h->d_glstack.release(); h->d_Hfx.release(); h->d_used.release(); h->d_k3exp.release();
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_x) cudaFreeHost(h->h_x);
+    if (h->ev_begin) cudaEventDestroy(h->ev_begin);
+    if (h->ev_end) cudaEventDestroy(h->ev_end);
+    for (auto& e : h->kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int choose_launch(wfsa_dev* h)
+{
+    const FastLayout& L = h->fast;
+    if (h->kernel == 1) {
+        // K2: 1 CTA per SM, as many warps as shared memory allows next to the accumulators
+        const size_t max_smem = 227 * 1024;
+        const size_t n_acc = (size_t)L.n_arcs + L.n_slots;
+        int accum = h->opt.accum_mode;
+        const bool fits = n_acc * 8 <= 120 * 1024;
+        if (accum == 0) accum = fits ? 1 : 2;
+        if (accum == 1 && !fits) accum = 2;
+        h->accum = accum;
+        h->n_acc_smem = accum == 1 ? (int)n_acc : 0;
+        int warps = 32;
+        size_t avail = max_smem - (size_t)h->n_acc_smem * 8;
+        int cap = (int)std::min<size_t>(avail / 8 / warps, 640);
+        if (cap < 96) { warps = 16; cap = (int)std::min<size_t>(avail / 8 / warps, 640); }
+        h->stack_cap = std::max(cap, 8);
+        h->block = warps * 32;
+        h->grid = h->sm_count;
+        h->smem_bytes = ((size_t)h->n_acc_smem + (size_t)warps * h->stack_cap) * 8;
+        h->glstack_words = (size_t)(h->max_len + 1) * 33 + 8;
+        const size_t total = (size_t)h->grid * warps * h->glstack_words;
+        CK(h->d_glstack.alloc(total));
+    } else if (h->kernel == 2) {
+        h->accum = 2;
+        int nt = ((L.max_cand + 31) / 32) * 32;
+        nt = std::max(nt, 64);
+        h->block = nt;
+        h->grid = h->sm_count * std::max(1, std::min(4, 1024 / nt));
+        h->smem_bytes = (size_t)(2 * nt + 32) * 8 + 40 * 4;
+        CK(h->d_k3lat.alloc((size_t)h->grid * std::max(h->max_len, 1) * nt));
+        CK(h->d_k3exp.alloc((size_t)h->grid * std::max(h->max_len, 1)));
+    } else {
+        h->accum = 2;
+        h->block = 128;
+        const size_t per = (size_t)2 * (h->max_len + 1) * h->fsa.n_states;
+        const size_t budget = (size_t)1 << 28;   // 2 GiB of doubles at most
+        long long batch = (long long)std::max<size_t>(1, budget / std::max<size_t>(per, 1));
+        batch = std::min<long long>(batch, std::max<int64_t>(h->n_strings, 1));
+        batch = std::min<long long>(batch, 1 << 20);
+        h->g_batch = batch;
+        h->grid = (int)((batch + h->block - 1) / h->block);
+        h->smem_bytes = 0;
+        CK(h->d_gscratch.alloc((size_t)batch * per));
+    }
+    return WFSA_OK;
+}
+
+extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* cd, const wfsa_dev_options* opt, wfsa_dev** out)
+{
+    g_create_error.clear();
+    if (!out) { g_create_error = "out is NULL"; return WFSA_ERR_INVALID; }
+    *out = nullptr;
+    wfsa_dev* h = new wfsa_dev();
+    auto bail = [&](int code) { g_create_error = h->err; wfsa_dev_destroy(h); return code; };
+    if (opt) h->opt = *opt;
+    int status = WFSA_OK;
+    std::string msg = copy_and_validate(fd, h->fsa, status);
+    if (status != WFSA_OK) { h->err = msg; return bail(status); }
+    if (!cd || cd->n_strings < 0 || (cd->n_strings && (!cd->offsets || !cd->p))) { h->err = "corpus descriptor invalid"; return bail(WFSA_ERR_INVALID); }
+    if (cd->n_strings > 0x7fffffff) { h->err = "more than 2^31 strings in one shard"; return bail(WFSA_ERR_LIMIT); }
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        h->err = "no CUDA device visible: the w-fsa B200 backend has no CPU fallback";
+        return bail(WFSA_ERR_NO_DEVICE);
+    }
+    h->device = h->opt.device;
+    if (h->device < 0 || h->device >= ndev) { h->err = "device ordinal out of range"; return bail(WFSA_ERR_INVALID); }
+    cudaDeviceProp prop;
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) {
+        h->err = "cudaSetDevice failed"; return bail(WFSA_ERR_NO_DEVICE);
+    }
+    if (prop.major != 10) {
+        h->err = std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                 "; this library contains sm_100a code only";
+        return bail(WFSA_ERR_NO_DEVICE);
+    }
+    h->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(WFSA_ERR_CUDA); }
+    cudaEventCreate(&h->ev_begin); cudaEventCreate(&h->ev_end);
+
+    // ---- layout
+    msg = build_fast_layout(h->fsa, h->fast, status);
+    if (status != WFSA_OK) { h->err = msg; return bail(status); }
+    msg = build_generic_layout(h->fsa, h->gen, status);
+    if (status != WFSA_OK) { h->err = msg; return bail(status); }
+    int kernel = h->opt.force_kernel;
+    if (kernel == 0) kernel = !h->fast.ok ? 3 : (h->fast.max_cand <= 32 ? 1 : 2);
+    if ((kernel == 1 || kernel == 2) && !h->fast.ok) { h->err = "forced fast kernel but emissions are not all one token long"; return bail(WFSA_ERR_INVALID); }
+    if (kernel == 1 && h->fast.max_cand > 32) { h->err = "forced warp-per-string kernel but more than 32 states emit one symbol"; return bail(WFSA_ERR_INVALID); }
+    if (kernel < 1 || kernel > 3) { h->err = "force_kernel out of range"; return bail(WFSA_ERR_INVALID); }
+    h->kernel = kernel;
+
+    // ---- corpus shard
+    h->n_strings = cd->n_strings;
+    h->h_offs.assign(cd->offsets ? cd->offsets : nullptr, cd->offsets ? cd->offsets + cd->n_strings + 1 : nullptr);
+    if (h->h_offs.empty()) h->h_offs.push_back(0);
+    if (h->h_offs[0] != 0) { h->err = "offsets must start at 0"; return bail(WFSA_ERR_INVALID); }
+    for (int64_t s = 0; s < h->n_strings; ++s) {
+        const int64_t len = h->h_offs[s + 1] - h->h_offs[s];
+        if (len < 0 || len > (1 << 24)) { h->err = "string length out of range"; return bail(WFSA_ERR_INVALID); }
+        h->max_len = std::max<int>(h->max_len, (int)len);
+    }
+    h->n_tokens = h->h_offs.back();
+    if (h->n_tokens && !cd->tokens) { h->err = "tokens is NULL"; return bail(WFSA_ERR_INVALID); }
+    h->h_order_all.resize(h->n_strings);
+    std::iota(h->h_order_all.begin(), h->h_order_all.end(), 0);
+    std::stable_sort(h->h_order_all.begin(), h->h_order_all.end(), [&](int32_t a, int32_t b) {
+        return (h->h_offs[a + 1] - h->h_offs[a]) > (h->h_offs[b + 1] - h->h_offs[b]);
+    });
+    cudaStream_t st = h->stream;
+#define CKB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(e_ == cudaErrorMemoryAllocation ? WFSA_ERR_NOMEM : WFSA_ERR_CUDA); } } while (0)
+    CKB(h->d_tokens.alloc(std::max<int64_t>(h->n_tokens, 1) + 32));
+    if (h->n_tokens) CKB(cudaMemcpyAsync(h->d_tokens.p, cd->tokens, (size_t)h->n_tokens * 4, cudaMemcpyHostToDevice, st));
+    CKB(h->d_offs.upload(h->h_offs, st));
+    CKB(h->d_p.alloc(std::max<int64_t>(h->n_strings, 1)));
+    if (h->n_strings) CKB(cudaMemcpyAsync(h->d_p.p, cd->p, (size_t)h->n_strings * 8, cudaMemcpyHostToDevice, st));
+    CKB(h->d_order.alloc(std::max<int64_t>(h->n_strings, 1)));
+    CKB(h->d_logq.alloc(std::max<int64_t>(h->n_strings, 1)));
+    CKB(h->d_pathcnt.alloc(std::max<int64_t>(h->n_strings, 1)));
+
+    // ---- tables
+    const HostFsa& F = h->fsa;
+    h->n_edges = F.n_trans() + F.n_emis();
+    if (h->fast.ok) {
+        const FastLayout& L = h->fast;
+        CKB(h->d_cand_off.upload(L.cand_off, st)); CKB(h->d_slot_state.upload(L.slot_state, st));
+        CKB(h->d_frow.upload(L.frow, st)); CKB(h->d_fent.upload(L.fent, st));
+        CKB(h->d_brow.upload(L.brow, st)); CKB(h->d_bent.upload(L.bent, st));
+        CKB(h->d_slot_emis.upload(L.slot_emis, st)); CKB(h->d_slot_final.upload(L.slot_final, st));
+        CKB(h->d_arc_tid.upload(L.arc_tid, st)); CKB(h->d_arc_eid.upload(L.arc_eid, st));
+        CKB(h->d_acc.alloc((size_t)L.n_arcs + L.n_slots));
+        CKB(h->d_sw.alloc(L.n_slots)); CKB(h->d_fw.alloc(L.n_slots));
+        h->table_bytes = 4 * (L.cand_off.size() + L.slot_state.size() + L.frow.size() + L.fent.size() + L.brow.size() + L.bent.size()) +
+                         8 * ((size_t)F.n_trans() + 2 * L.n_slots);
+    }
+    CKB(h->d_emis_row.upload(F.emis_row, st)); CKB(h->d_emis_tok_off.upload(F.emis_tok_off, st));
+    CKB(h->d_emis_tok.upload(F.emis_tok, st)); CKB(h->d_trans_row.upload(F.trans_row, st));
+    CKB(h->d_trans_dst.upload(F.trans_dst, st)); CKB(h->d_eps_order.upload(h->gen.eps_order, st));
+    CKB(h->d_tw.alloc(std::max(F.n_trans(), 1))); CKB(h->d_ltw.alloc(std::max(F.n_trans(), 1)));
+    CKB(h->d_lew.alloc(std::max(F.n_emis(), 1)));
+    CKB(h->d_trans_tp.alloc(std::max(F.n_trans(), 1))); CKB(h->d_emis_tp.alloc(std::max(F.n_emis(), 1)));
+    CKB(h->d_edge_tp.alloc(std::max(h->n_edges, 1)));
+    {
+        std::vector<int32_t> raw(F.trans_param);
+        raw.insert(raw.end(), F.emis_param.begin(), F.emis_param.end());
+        CKB(h->d_edge_raw.upload(raw, st));
+    }
+    CKB(h->d_red.alloc((size_t)h->n_edges + 2));
+    CKB(h->d_used.alloc(std::max(F.n_raw, 1)));
+    if (choose_launch(h) != WFSA_OK) return bail(WFSA_ERR_CUDA);
+    if (h->kernel == 1) {
+        cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_SMEM_CAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_SMEM_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    }
+    CKB(cudaStreamSynchronize(st));
+#undef CKB
+    *out = h;
+    return WFSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static FastTablesD fast_tables(const wfsa_dev* h)
+{
+    FastTablesD T{};
+    T.cand_off = h->d_cand_off.p; T.slot_state = h->d_slot_state.p;
+    T.frow = h->d_frow.p; T.fent = h->d_fent.p; T.brow = h->d_brow.p; T.bent = h->d_bent.p;
+    T.n_sym = h->fsa.n_sym; T.n_states = h->fsa.n_states; T.n_arcs = h->fast.n_arcs; T.n_slots = h->fast.n_slots;
+    T.start_state = h->fsa.start; T.start_final_tid = h->fast.start_final_tid;
+    return T;
+}
+
+// launches weights + dominant kernel + arc fold on the handle's stream
+static int launch_pipeline(wfsa_dev* h, int mode, const int32_t* d_order, int64_t n_order)
+{
+    const HostFsa& F = h->fsa;
+    cudaStream_t st = h->stream;
+    const int unit = (mode == MODE_STRUCT) ? 1 : 0;
+    CK(cudaMemsetAsync(h->d_red.p, 0, h->d_red.n * 8, st));
+    if (h->fast.ok) CK(cudaMemsetAsync(h->d_acc.p, 0, h->d_acc.n * 8, st));
+    const int n_slots = h->fast.ok ? h->fast.n_slots : 0;
+    {
+        const int total = F.n_trans() + F.n_emis() + n_slots;
+        if (total > 0) {
+            k_weights<<<(total + 255) / 256, 256, 0, st>>>(F.n_trans(), F.n_emis(), n_slots, h->d_trans_tp.p, h->d_emis_tp.p,
+                                                          h->d_slot_emis.p, h->d_slot_final.p, h->d_x.p, unit, h->d_tw.p,
+                                                          h->d_sw.p, h->d_fw.p, h->d_ltw.p, h->d_lew.p);
+            h->launches++;
+        }
+    }
+    CorpusD C{h->d_tokens.p, h->d_offs.p, h->d_p.p, d_order, n_order};
+    EvalOutD O{};
+    O.logq = h->d_logq.p; O.path_count = h->d_pathcnt.p; O.acc_global = h->d_acc.p; O.red = h->d_red.p;
+    O.fx_scale = (mode == MODE_STRUCT) ? 1.0 : std::ldexp(1.0, (int)h->fx_log2);
+    O.ll_scale = std::ldexp(1.0, (int)h->ll_log2);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->timing && mode == MODE_EVAL) {
+        if (h->kev_used == h->kev.size() && h->kev.size() < 8192) {
+            cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); h->kev.push_back({a, b});
+        }
+        if (h->kev_used < h->kev.size()) { e0 = h->kev[h->kev_used].first; e1 = h->kev[h->kev_used].second; h->kev_used++; }
+    }
+    if (e0) cudaEventRecord(e0, st);
+    if (n_order > 0) {
+        if (h->kernel == 1) {
+            K2Params P{};
+            P.T = fast_tables(h); P.W = EvalWeightsD{h->d_tw.p, h->d_sw.p, h->d_fw.p}; P.C = C; P.O = O;
+            P.stack_cap = h->stack_cap; P.gl_stack = h->d_glstack.p; P.gl_stack_words = h->glstack_words;
+            if (mode == MODE_STRUCT) {
+                P.n_acc_smem = 0;
+                const size_t smem = (size_t)(h->block / 32) * h->stack_cap * 8;
+                k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL><<<h->grid, h->block, smem, st>>>(P);
+            } else if (h->accum == 1) {
+                P.n_acc_smem = h->n_acc_smem;
+                if (h->opt.reserved == 1) k2_fwdbwd<MODE_EVAL, ACC_SMEM_CAS><<<h->grid, h->block, h->smem_bytes, st>>>(P);
+                else k2_fwdbwd<MODE_EVAL, ACC_SMEM_SPLIT><<<h->grid, h->block, h->smem_bytes, st>>>(P);
+            } else {
+                P.n_acc_smem = 0;
+                const size_t smem = (size_t)(h->block / 32) * h->stack_cap * 8;
+                k2_fwdbwd<MODE_EVAL, ACC_GLOBAL><<<h->grid, h->block, smem, st>>>(P);
+            }
+            h->launches++;
+        } else if (h->kernel == 2) {
+            K3Params P{};
+            P.T = fast_tables(h); P.W = EvalWeightsD{h->d_tw.p, h->d_sw.p, h->d_fw.p}; P.C = C; P.O = O;
+            P.lattice = h->d_k3lat.p; P.lat_exp = h->d_k3exp.p; P.max_len = std::max(h->max_len, 1);
+            if (mode == MODE_STRUCT) k3_fwdbwd<MODE_STRUCT><<<h->grid, h->block, h->smem_bytes, st>>>(P);
+            else k3_fwdbwd<MODE_EVAL><<<h->grid, h->block, h->smem_bytes, st>>>(P);
+            h->launches++;
+        } else {
+            GenericParams P{};
+            P.G = GenericTablesD{h->d_emis_row.p, h->d_emis_tok_off.p, h->d_emis_tok.p, h->d_trans_row.p, h->d_trans_dst.p,
+                                 h->d_eps_order.p, F.n_states, F.n_trans(), F.start, F.end};
+            P.ltw = h->d_ltw.p; P.lew = h->d_lew.p; P.C = C; P.O = O; P.scratch = h->d_gscratch.p; P.max_len = h->max_len;
+            for (long long first = 0; first < n_order; first += h->g_batch) {
+                P.first = first; P.count = std::min<long long>(h->g_batch, n_order - first);
+                const int grid = (int)((P.count + h->block - 1) / h->block);
+                if (mode == MODE_STRUCT) kg_fwdbwd<MODE_STRUCT><<<grid, h->block, 0, st>>>(P);
+                else kg_fwdbwd<MODE_EVAL><<<grid, h->block, 0, st>>>(P);
+                h->launches++;
+            }
+        }
+    }
+    if (e1) cudaEventRecord(e1, st);
+    CK(cudaGetLastError());
+    if (h->fast.ok && h->kernel != 3) {
+        const int total = h->fast.n_arcs + h->fast.n_slots;
+        k_arcs_to_edges<<<(total + 255) / 256, 256, 0, st>>>(h->fast.n_arcs, h->fast.n_slots, F.n_trans(), h->d_acc.p,
+                                                            h->d_arc_tid.p, h->d_arc_eid.p, h->d_slot_final.p, h->d_red.p + 2);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    return WFSA_OK;
+}
+
+extern "C" int wfsa_dev_structure(wfsa_dev* h, uint8_t* recognised, double* path_count, uint8_t* param_used)
+{
+    if (!h) return WFSA_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d_order.p, h->h_order_all.data(), (size_t)h->n_strings * 4, cudaMemcpyHostToDevice, h->stream));
+    int rc = launch_pipeline(h, MODE_STRUCT, h->d_order.p, h->n_strings);
+    if (rc != WFSA_OK) return rc;
+    // used flags are per-edge instance counts; combine across ranks before thresholding
+    rc = nccl_allreduce(h, h->d_red.p, h->d_red.n, ncclUint64, ncclSum);
+    if (rc != WFSA_OK) return rc;
+    CK(cudaMemsetAsync(h->d_used.p, 0, h->d_used.n, h->stream));
+    if (h->n_edges) {
+        k_finish_struct<<<(h->n_edges + 255) / 256, 256, 0, h->stream>>>(h->n_edges, h->d_red.p, h->d_edge_raw.p, h->d_used.p);
+        h->launches++;
+    }
+    std::vector<double> pc((size_t)h->n_strings);
+    if (h->n_strings) CK(cudaMemcpyAsync(pc.data(), h->d_pathcnt.p, (size_t)h->n_strings * 8, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<uint8_t> used((size_t)h->fsa.n_raw);
+    if (h->fsa.n_raw) CK(cudaMemcpyAsync(used.data(), h->d_used.p, (size_t)h->fsa.n_raw, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    h->h_recognised.resize((size_t)h->n_strings);
+    for (int64_t s = 0; s < h->n_strings; ++s) {
+        h->h_recognised[s] = pc[s] > 0.0 ? 1 : 0;
+        if (recognised) recognised[s] = h->h_recognised[s];
+        if (path_count) path_count[s] = pc[s];
+    }
+    if (param_used) std::copy(used.begin(), used.end(), param_used);
+    h->structure_done = true;
+    return WFSA_OK;
+}
+
+extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32_t n, const uint8_t* recognised)
+{
+    if (!h || n < 0 || (!trimmed && h->fsa.n_raw > 0)) return set_err(h, WFSA_ERR_INVALID, "set_param_map: bad arguments");
+    CK(cudaSetDevice(h->device));
+    const HostFsa& F = h->fsa;
+    std::vector<char> seen((size_t)n, 0);
+    for (int i = 0; i < F.n_raw; ++i) {
+        const int t = trimmed[i];
+        if (t < -2 || t >= n) return set_err(h, WFSA_ERR_INVALID, "set_param_map: trimmed index out of range");
+        if (t >= 0) { if (seen[t]) return set_err(h, WFSA_ERR_INVALID, "set_param_map: trimmed index used twice"); seen[t] = 1; }
+    }
+    for (int i = 0; i < n; ++i) if (!seen[i]) return set_err(h, WFSA_ERR_INVALID, "set_param_map: a trimmed index has no parameter");
+    std::vector<int32_t> ttp(F.n_trans()), etp(F.n_emis());
+    for (int t = 0; t < F.n_trans(); ++t) ttp[t] = F.trans_param[t] < 0 ? -1 : trimmed[F.trans_param[t]];
+    for (int e = 0; e < F.n_emis(); ++e) etp[e] = F.emis_param[e] < 0 ? -1 : trimmed[F.emis_param[e]];
+    std::vector<int32_t> edge_tp(ttp);
+    edge_tp.insert(edge_tp.end(), etp.begin(), etp.end());
+    // pinned (-1) and unused (-2) edges produce no gradient entry
+    if (!ttp.empty()) CK(cudaMemcpyAsync(h->d_trans_tp.p, ttp.data(), ttp.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    if (!etp.empty()) CK(cudaMemcpyAsync(h->d_emis_tp.p, etp.data(), etp.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    if (!edge_tp.empty()) CK(cudaMemcpyAsync(h->d_edge_tp.p, edge_tp.data(), edge_tp.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    // strings that take part: recognised ones, longest first
+    std::vector<int32_t> order;
+    order.reserve((size_t)h->n_strings);
+    const uint8_t* rec = recognised ? recognised : (h->structure_done ? h->h_recognised.data() : nullptr);
+    int64_t tokens = 0; int max_len = 0;
+    for (int32_t s : h->h_order_all)
+        if (!rec || rec[s]) {
+            order.push_back(s);
+            const int64_t len = h->h_offs[s + 1] - h->h_offs[s];
+            tokens += len; max_len = std::max<int>(max_len, (int)len);
+        }
+    h->n_active = (int64_t)order.size(); h->n_active_tokens = tokens;
+    if (!order.empty()) CK(cudaMemcpyAsync(h->d_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    // every logq defaults to -inf (unrecognised strings are never touched by an evaluation)
+    {
+        std::vector<double> minf((size_t)h->n_strings, -INFINITY);
+        if (h->n_strings) CK(cudaMemcpyAsync(h->d_logq.p, minf.data(), minf.size() * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    // fixed-point scale: an accumulator is bounded by sum_s p_s * (steps of a path) <= max steps
+    long long bound = ((long long)h->max_len + 2) * (h->gen.n_eps_states + 1);
+    if (h->comm) {
+        long long* d = reinterpret_cast<long long*>(h->d_red.p);
+        CK(cudaMemcpyAsync(d, &bound, 8, cudaMemcpyHostToDevice, h->stream));
+        int rc = nccl_allreduce(h, d, 1, ncclInt64, ncclMax);
+        if (rc != WFSA_OK) return rc;
+        CK(cudaMemcpyAsync(&bound, d, 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    int bits = 1;
+    while ((1ll << bits) <= bound && bits < 40) ++bits;
+    h->fx_log2 = 62 - bits;
+    if (h->n != n) {
+        if (h->h_out) cudaFreeHost(h->h_out);
+        if (h->h_x) cudaFreeHost(h->h_x);
+        h->h_out = nullptr; h->h_x = nullptr;
+        CK(cudaMallocHost(&h->h_out, ((size_t)n + 2) * 8));
+        CK(cudaMallocHost(&h->h_x, std::max<size_t>(n, 1) * 8));
+        CK(h->d_x.alloc(std::max(n, 1)));
+        CK(h->d_out.alloc((size_t)n + 2));
+    }
+    h->n = n;
+    CK(cudaStreamSynchronize(h->stream));
+    return WFSA_OK;
+}
+
+extern "C" int wfsa_dev_upload_x(wfsa_dev* h, const double* x)
+{
+    if (!h || (!x && h->n > 0)) return set_err(h, WFSA_ERR_INVALID, "upload_x: bad arguments");
+    if (h->n < 0) return set_err(h, WFSA_ERR_STATE, "upload_x before set_param_map");
+    CK(cudaSetDevice(h->device));
+    if (h->n) {
+        std::memcpy(h->h_x, x, (size_t)h->n * 8);
+        CK(cudaMemcpyAsync(h->d_x.p, h->h_x, (size_t)h->n * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    return WFSA_OK;
+}
+
+extern "C" int wfsa_dev_eval_launch(wfsa_dev* h)
+{
+    if (!h) return WFSA_ERR_INVALID;
+    if (h->n < 0) return set_err(h, WFSA_ERR_STATE, "eval before set_param_map");
+    CK(cudaSetDevice(h->device));
+    int rc = launch_pipeline(h, MODE_EVAL, h->d_order.p, h->n_active);
+    if (rc != WFSA_OK) return rc;
+    rc = nccl_allreduce(h, h->d_red.p, h->d_red.n, ncclUint64, ncclSum);
+    if (rc != WFSA_OK) return rc;
+    CK(cudaMemsetAsync(h->d_out.p, 0, h->d_out.n * 8, h->stream));
+    const int total = std::max(h->n_edges, 1);
+    k_finish_eval<<<(total + 255) / 256, 256, 0, h->stream>>>(h->n_edges, h->n, h->d_red.p, h->d_edge_tp.p,
+                                                             std::ldexp(1.0, -(int)h->fx_log2), std::ldexp(1.0, -(int)h->ll_log2), h->d_out.p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return WFSA_OK;
+}
+
+extern "C" int wfsa_dev_sync(wfsa_dev* h)
+{
+    if (!h) return WFSA_ERR_INVALID;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return WFSA_OK;
+}
+
+extern "C" int wfsa_dev_eval_fetch(wfsa_dev* h, double* loglik, double* logq, double* grad)
+{
+    if (!h) return WFSA_ERR_INVALID;
+    if (h->n < 0) return set_err(h, WFSA_ERR_STATE, "fetch before set_param_map");
+    CK(cudaMemcpyAsync(h->h_out, h->d_out.p, ((size_t)h->n + 2) * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (logq && h->n_strings) CK(cudaMemcpyAsync(logq, h->d_logq.p, (size_t)h->n_strings * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    if (loglik) *loglik = h->h_out[0];
+    if (grad) std::memcpy(grad, h->h_out + 2, (size_t)h->n * 8);
+    return WFSA_OK;
+}
+
+extern "C" int wfsa_dev_eval(wfsa_dev* h, const double* x, double* loglik, double* logq, double* grad)
+{
+    int rc = wfsa_dev_upload_x(h, x);
+    if (rc != WFSA_OK) return rc;
+    rc = wfsa_dev_eval_launch(h);
+    if (rc != WFSA_OK) return rc;
+    return wfsa_dev_eval_fetch(h, loglik, logq, grad);
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int wfsa_dev_set_path_blocks(wfsa_dev* h, const wfsa_path_blocks* b)
+{
+    if (!h || !b || b->n_blocks < 0) return set_err(h, WFSA_ERR_INVALID, "set_path_blocks: bad arguments");
+    if (h->n < 0) return set_err(h, WFSA_ERR_STATE, "set_path_blocks before set_param_map");
+    CK(cudaSetDevice(h->device));
+    const int64_t nb = b->n_blocks;
+    std::vector<int64_t> po(b->path_off, b->path_off + nb + 1), co(b->col_off, b->col_off + nb + 1), vo(b->val_off, b->val_off + nb + 1);
+    for (int64_t i = 0; i < nb; ++i) {
+        const int64_t L = po[i + 1] - po[i], D = co[i + 1] - co[i];
+        if (L < 0 || D < 0 || vo[i + 1] - vo[i] != L * D) return set_err(h, WFSA_ERR_INVALID, "set_path_blocks: inconsistent block sizes");
+    }
+    std::vector<int32_t> cols(b->cols, b->cols + co[nb]);
+    for (int32_t c : cols) if (c < 0 || c >= h->n) return set_err(h, WFSA_ERR_INVALID, "set_path_blocks: column out of range");
+    std::vector<double> counts(b->counts, b->counts + vo[nb]), p(b->p, b->p + nb);
+    CK(h->d_hb_path_off.upload(po, h->stream)); CK(h->d_hb_col_off.upload(co, h->stream)); CK(h->d_hb_val_off.upload(vo, h->stream));
+    CK(h->d_hb_cols.upload(cols, h->stream)); CK(h->d_hb_counts.upload(counts, h->stream)); CK(h->d_hb_p.upload(p, h->stream));
+    CK(h->d_hb_r.alloc(std::max<int64_t>(po[nb], 1)));
+    CK(h->d_Hfx.alloc(std::max<size_t>((size_t)h->n * h->n, 1)));
+    CK(h->d_H.alloc(std::max<size_t>((size_t)h->n * h->n, 1)));
+    CK(h->d_rmin.alloc(1));
+    CK(cudaStreamSynchronize(h->stream));
+    h->hb_blocks = nb; h->hb_paths = po[nb];
+    return WFSA_OK;
+}
+
+extern "C" int wfsa_dev_hessian(wfsa_dev* h, const double* x, double* Hf, double* rmin)
+{
+    if (!h || !Hf) return set_err(h, WFSA_ERR_INVALID, "hessian: bad arguments");
+    if (h->hb_blocks < 0) return set_err(h, WFSA_ERR_STATE, "hessian before set_path_blocks");
+    int rc = wfsa_dev_upload_x(h, x);
+    if (rc != WFSA_OK) return rc;
+    const size_t nn = (size_t)h->n * h->n;
+    CK(cudaMemsetAsync(h->d_Hfx.p, 0, std::max<size_t>(nn, 1) * 8, h->stream));
+    const double inf = INFINITY;
+    CK(cudaMemcpyAsync(h->d_rmin.p, &inf, 8, cudaMemcpyHostToDevice, h->stream));
+    // |H_jk| <= p_s * (max count)^2 summed over strings; 2^40 head room is ample for counts < 2^10
+    const double fx = std::ldexp(1.0, 40);
+    if (h->hb_blocks > 0) {
+        HessParams P{};
+        P.n_blocks = h->hb_blocks; P.path_off = h->d_hb_path_off.p; P.col_off = h->d_hb_col_off.p; P.cols = h->d_hb_cols.p;
+        P.val_off = h->d_hb_val_off.p; P.counts = h->d_hb_counts.p; P.p = h->d_hb_p.p; P.x = h->d_x.p; P.r_scratch = h->d_hb_r.p;
+        P.H_fx = h->d_Hfx.p; P.rmin = h->d_rmin.p; P.n = h->n; P.fx_scale = fx;
+        const int warps_per_block = 8;
+        const int64_t blocks = std::min<int64_t>((h->hb_blocks + warps_per_block - 1) / warps_per_block, (int64_t)h->sm_count * 8);
+        k5_hessian<<<(int)std::max<int64_t>(blocks, 1), warps_per_block * 32, 0, h->stream>>>(P);
+        h->launches++;
+    }
+    rc = nccl_allreduce(h, h->d_Hfx.p, nn, ncclUint64, ncclSum);
+    if (rc != WFSA_OK) return rc;
+    if (nn) {
+        k_fx_to_double<<<(unsigned)((nn + 255) / 256), 256, 0, h->stream>>>(nn, h->d_Hfx.p, 1.0 / fx, h->d_H.p);
+        h->launches++;
+        CK(cudaMemcpyAsync(Hf, h->d_H.p, nn * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    double rm = INFINITY;
+    CK(cudaMemcpyAsync(&rm, h->d_rmin.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    if (rmin) *rmin = rm;
+    return WFSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int wfsa_dev_comm_unique_id(void* id_out)
+{
+    std::string err;
+    if (!id_out) return WFSA_ERR_INVALID;
+    if (!g_nccl.load(err)) { g_create_error = err; return WFSA_ERR_NCCL; }
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return WFSA_ERR_NCCL; }
+    static_assert(sizeof(ncclUniqueId) == WFSA_UNIQUE_ID_BYTES, "unique id size");
+    std::memcpy(id_out, &id, sizeof(id));
+    return WFSA_OK;
+}
+
+extern "C" int wfsa_dev_comm_init(wfsa_dev* h, const void* id, int rank, int nranks)
+{
+    if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return set_err(h, WFSA_ERR_INVALID, "comm_init: bad arguments");
+    if (nranks == 1) return WFSA_OK;
+    std::string err;
+    if (!g_nccl.load(err)) return set_err(h, WFSA_ERR_NCCL, err);
+    CK(cudaSetDevice(h->device));
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, sizeof(uid));
+    const int r = g_nccl.CommInitRank(&h->comm, nranks, uid, rank);
+    if (r != ncclSuccess) { h->comm = nullptr; return set_err(h, WFSA_ERR_NCCL, "ncclCommInitRank failed"); }
+    h->rank = rank; h->nranks = nranks;
+    return WFSA_OK;
+}
+
+extern "C" int wfsa_dev_allreduce_f64(wfsa_dev* h, double* values, int n, int op)
+{
+    if (!h || n < 0 || (n && !values)) return set_err(h, WFSA_ERR_INVALID, "allreduce_f64: bad arguments");
+    if (!h->comm || n == 0) return WFSA_OK;
+    CK(cudaSetDevice(h->device));
+    DevBuf<double> tmp;
+    CK(tmp.alloc(n));
+    CK(cudaMemcpyAsync(tmp.p, values, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    const int rc = nccl_allreduce(h, tmp.p, n, 8 /* ncclFloat64 */, op == 1 ? ncclMax : ncclSum);
+    if (rc != WFSA_OK) { tmp.release(); return rc; }
+    CK(cudaMemcpyAsync(values, tmp.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    tmp.release();
+    return WFSA_OK;
+}
+
+extern "C" int wfsa_dev_timer_begin(wfsa_dev* h)
+{
+    if (!h) return WFSA_ERR_INVALID;
+    h->timing = true; h->kev_used = 0;
+    CK(cudaEventRecord(h->ev_begin, h->stream));
+    return WFSA_OK;
+}
+
+extern "C" int wfsa_dev_timer_end(wfsa_dev* h, float* ms)
+{
+    if (!h) return WFSA_ERR_INVALID;
+    CK(cudaEventRecord(h->ev_end, h->stream));
+    CK(cudaEventSynchronize(h->ev_end));
+    h->timing = false;
+    if (ms) CK(cudaEventElapsedTime(ms, h->ev_begin, h->ev_end));
+    return WFSA_OK;
+}
+
+extern "C" int wfsa_dev_timer_kernel_ms(wfsa_dev* h, float* ms, int64_t* launches)
+{
+    if (!h) return WFSA_ERR_INVALID;
+    float total = 0.f;
+    for (size_t i = 0; i < h->kev_used; ++i) {
+        float t = 0.f;
+        CK(cudaEventSynchronize(h->kev[i].second));
+        CK(cudaEventElapsedTime(&t, h->kev[i].first, h->kev[i].second));
+        total += t;
+    }
+    if (ms) *ms = total;
+    if (launches) *launches = (int64_t)h->kev_used;
+    return WFSA_OK;
+}
+
+extern "C" int wfsa_dev_get_info(wfsa_dev* h, wfsa_dev_info* info)
+{
+    if (!h || !info) return WFSA_ERR_INVALID;
+    std::memset(info, 0, sizeof(*info));
+    info->kernel = h->kernel; info->accum_mode = h->accum;
+    info->n_trans = h->fsa.n_trans(); info->n_emis = h->fsa.n_emis();
+    info->n_arcs = h->fast.ok ? h->fast.n_arcs : 0; info->n_slots = h->fast.ok ? h->fast.n_slots : 0;
+    info->max_candidates = h->fast.ok ? h->fast.max_cand : 0;
+    info->sm_count = h->sm_count; info->grid = h->grid; info->block = h->block;
+    info->n_strings = h->n_strings; info->n_active_strings = h->n_active; info->n_tokens = h->n_tokens;
+    info->n_active_tokens = h->n_active_tokens; info->smem_bytes = (int64_t)h->smem_bytes; info->table_bytes = (int64_t)h->table_bytes;
+    info->kernels_launched = h->launches; info->fixed_point_scale_log2 = h->fx_log2;
+    return WFSA_OK;
+}

@@ -1,0 +1,170 @@
+// w-fsa_b200/host/main.cpp -- the `wfsa` command line over the B200 backend.
+//
+// Same options, same stderr/stdout protocol and exit codes as the reference executable
+// (/root/reference/src/main.cpp:68-106 options, :121-347 flow).  Not carried over: the MKL
+// micro-benchmarks (-testt/-testn), -t (MKL threads) and the -m path-matrix cache -- a DP
+// backend has no P/M matrices to cache.  -r is accepted and ignored (BFS/DFS only differ in
+// enumeration order).  Added: --device N, --full (dump weights with 17 digits).
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "fsa.hpp"
+#include "learner.hpp"
+
+using namespace wfsa;
+
+static void PrintFixedWidth(FILE* out, double x, int width)      // src/Utils.cpp:82-97
+{
+    const int magnitude = (x == 0) ? 0 : (int)std::floor(std::log10(std::fabs(x)));
+    if (magnitude <= width - 2 && magnitude >= 0) {
+        if (std::floor(x) == x) fprintf(out, "%*.0f", width, x);
+        else fprintf(out, "%*.*f", width, std::max(0, width - 3 - magnitude), x);
+    } else if (-4 < magnitude && magnitude < 0) fprintf(out, "%*.*f", width, width - 3, x);
+    else fprintf(out, "%*.*e", width, width - 7, x);
+}
+
+static void usage()
+{
+    std::cout <<
+        "\n --- Put the W in FSA (B200 evaluation backend) --- \n\n"
+        "Learning weights of a finite state automaton\n\n"
+        "  -c, --corpus FILE          corpus to load\n"
+        "  -a, --automaton, --load FILE  FSA to load\n"
+        "  -o, --output FILE          write learned WFSA in this file, or stdout if empty\n"
+        "  -e, --epoch, --epochs N    number of maximum optimization epochs (20)\n"
+        "  -l, --learning, --eta X    learning rate (1)\n"
+        "  -tol, --tol, --tolerance X tolerance when to stop (1e-6)\n"
+        "  -eval, --eval, --evaluate  evaluate model after optimization\n"
+        "  -n, --normalize            normalize the automaton after optimization\n"
+        "  -p, --print                prints extra info to stderr\n"
+        "  -s, --suppress             suppresses printing of learned FSA to stdout\n"
+        "  -r, --recognize N          accepted for compatibility (0 BFS, 1 DFS); the DP needs neither\n"
+        "  -opt, --optimizer NAME     Hessian | QuasiNewton\n"
+        "  -x, --initx, --initial     reads initial x vector from stdin\n"
+        "  -i, --init FLAGS           1 uniform, 2 normalize, 4 init multipliers, 8 use H_f,\n"
+        "                             16 reorder (no-op: dense solve), 32 exponential multipliers\n"
+        "  --device N                 CUDA device ordinal (0)\n"
+        "  --full                     dump weights with 17 significant digits\n";
+}
+
+int main(int argc, const char* argv[])
+{
+    std::string automaton_filename, corpus_filename, output_filename, optimizer = "Hessian";
+    int epochs = 20, initflags = 0, device = 0;
+    bool normalize = false, print = false, suppress = false, evaluate = false, initx = false, full = false;
+    double eta = 1.0, tolerance = 1e-6;
+    auto is = [](const char* a, std::initializer_list<const char*> names) {
+        for (const char* n : names) if (std::strcmp(a, n) == 0) return true;
+        return false;
+    };
+    for (int i = 1; i < argc; ++i) {
+        const char* a = argv[i];
+        auto next = [&]() -> const char* {
+            if (i + 1 >= argc) { std::cerr << "Missing value for \"" << a << "\"!" << std::endl; exit(1); }
+            return argv[++i];
+        };
+        if (is(a, {"-h", "--help"})) { usage(); return 0; }
+        else if (is(a, {"-c", "--corpus"})) corpus_filename = next();
+        else if (is(a, {"-a", "--automaton", "--load"})) automaton_filename = next();
+        else if (is(a, {"-o", "--output"})) output_filename = next();
+        else if (is(a, {"-e", "--epoch", "--epochs"})) epochs = atoi(next());
+        else if (is(a, {"-l", "--learning", "--eta"})) eta = atof(next());
+        else if (is(a, {"-tol", "--tol", "--tolerance"})) tolerance = atof(next());
+        else if (is(a, {"-eval", "--eval", "--evaluate"})) evaluate = true;
+        else if (is(a, {"-n", "--normalize"})) normalize = true;
+        else if (is(a, {"-p", "--print"})) print = true;
+        else if (is(a, {"-s", "--suppress"})) suppress = true;
+        else if (is(a, {"-t", "--thread", "--threads"})) next();
+        else if (is(a, {"-r", "--recognize"})) { const int r = atoi(next()); if (r != 0 && r != 1) { std::cerr << "-r must be 0 or 1" << std::endl; return 1; } }
+        else if (is(a, {"-opt", "--optimizer"})) { optimizer = next(); if (optimizer != "Hessian" && optimizer != "QuasiNewton") { std::cerr << "Unknown optimizer \"" << optimizer << "\"!" << std::endl; return 1; } }
+        else if (is(a, {"-pr", "--print-recognize"})) print = true;
+        else if (is(a, {"-x", "--initx", "--initial"})) initx = true;
+        else if (is(a, {"-i", "--init"})) initflags = atoi(next());
+        else if (is(a, {"--device"})) device = atoi(next());
+        else if (is(a, {"--full"})) full = true;
+        else if (is(a, {"-m", "--matrices", "--matrix"})) { next(); std::cerr << "-m is not supported: the DP backend has no path matrices to cache" << std::endl; return 1; }
+        else { std::cerr << "Unknown argument \"" << a << "\"!" << std::endl; return 1; }
+    }
+    try {
+        Fsa fsa;
+        std::unique_ptr<Learner> learner(optimizer == "Hessian" ? (Learner*)(new HessianLearner()) : (Learner*)(new QuasiNewtonLearner()));
+        BackendOptions bo; bo.device = device;
+        learner->SetBackend(bo);
+        std::cerr << "Corpus: "; std::cerr.flush();
+        Corpus corpus;
+        if (FILE* f = fopen(corpus_filename.c_str(), "r")) { corpus.Read(f); fclose(f); }
+        else { std::cerr << "\nUnable to open \"" << corpus_filename << "\"!" << std::endl; return 1; }
+        std::cerr << "\n\tsize: " << corpus.size() << "\n\tsum: " << corpus.Sum();
+        corpus.Renormalize();
+        std::cerr << ", renormalized to " << corpus.Sum() << std::endl;
+        std::cerr << "Automaton: "; std::cerr.flush();
+        if (FILE* f = fopen(automaton_filename.c_str(), "r")) { fsa.Read(f); fclose(f); }
+        else { std::cerr << "\nUnable to open \"" << automaton_filename << "\"!" << std::endl; return 1; }
+        std::cerr << "\n\tstates: " << fsa.GetNumberOfStates() << "\n\ttransitions: " << fsa.GetNumberOfTransitions()
+                  << "\n\temissions: " << fsa.GetNumberOfEmissions() << "\n\tparameters: " << fsa.GetNumberOfParameters()
+                  << "\n\tconstraints: " << fsa.GetNumberOfConstraints() << "\n\tfree parameters: " << fsa.GetNumberOfFreeParameters() << std::endl;
+        std::cerr << "Recognize: "; std::cerr.flush();
+        learner->BuildFrom(fsa, corpus, true);
+        std::cerr << "\n\tstrings: " << learner->GetNumberOfStrings() << "\n\tpaths: " << learner->GetNumberOfPaths()
+                  << "\n\tcommon support: " << learner->GetCommonSupport()
+                  << "\n\tunique paths: " << (learner->HasUniquePaths() ? "true" : "false")
+                  << "\nAfter trimming:\n\tparameters: " << learner->GetNumberOfParameters()
+                  << "\n\tconstraints: " << learner->GetNumberOfConstraints() << std::endl;
+        if (learner->GetNumberOfParameters() == 0) { std::cerr << "Empty automaton!" << std::endl; return 1; }
+        if (learner->GetNumberOfStrings() == 0) { std::cerr << "Automaton cannot generate any of the strings!" << std::endl; return 1; }
+        learner->Finalize();
+        std::cerr << "Initialize ... "; std::cerr.flush();
+        if (initx) {
+            std::vector<double> x;
+            while (std::cin && (int)x.size() < learner->GetNumberOfParameters()) { x.emplace_back(); std::cin >> x.back(); }
+            if (!std::cin) throw MyError("Cannot read initial x value!");
+            learner->Init(initflags, x.data());
+        } else learner->Init(initflags);
+        std::cerr << "done" << std::endl;
+        const int width = (int)std::ceil(std::log10(epochs + 1));
+        if (epochs > 0) {
+            std::cerr << "Optimization:" << std::endl;
+            for (int e = 1; e <= epochs; ++e) {
+                if (e % 20 == 1) std::cerr << "epoch\t" << learner->GetOptimizationHeader() << std::endl;
+                learner->OptimizationStep(eta, print);
+                fprintf(stderr, "%0*d\t", width, e);
+                const auto info = learner->GetOptimizationInfo();
+                for (double x : info) { PrintFixedWidth(stderr, x, 9); fputs(" ", stderr); }
+                std::cerr << std::endl;
+                for (double x : info)
+                    if (!std::isfinite(x)) {
+                        std::cerr << std::endl;
+                        throw LearnerError(std::to_string(x) + " detected at epoch " + std::to_string(e));
+                    }
+                if (learner->HaltCondition(tolerance)) break;
+            }
+        }
+        if (normalize) learner->Renormalize();
+        if (evaluate) {
+            const auto results = learner->GetOptimizationResult(print);
+            std::cerr.precision(DBL_DIG);
+            std::cerr << "Result:";
+            for (double x : results) std::cerr << ' ' << x;
+            std::cerr << std::endl;
+        }
+        if (!suppress) {
+            FILE* outf = output_filename.empty() ? stdout : fopen(output_filename.c_str(), "w");
+            if (!outf) throw MyError("Unable to open output file \"" + output_filename + "\" for writing!");
+            learner->RewriteWeights(fsa);
+            const std::string s = fsa.DumpString(full);
+            fwrite(s.data(), 1, s.size(), outf);
+            if (outf != stdout) fclose(outf);
+        }
+    } catch (std::exception& e) {
+        fprintf(stderr, "%s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
