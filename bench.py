@@ -1,0 +1,359 @@
+#!/usr/bin/env python3
+"""bench.py -- forward-backward + gradient throughput (symbols/s) of the w-fsa evaluation path.
+
+One "step" = one objective + gradient evaluation (what one optimiser epoch needs,
+/root/reference/src/QuasiNewtonLearner.cpp:162-168) over a synthetic corpus of BASELINE.json's
+config 4: WFSA 256 states / 64 symbols / 8 224 combined arcs, 1M strings of length 32-128 per GPU
+(weak scaling: each rank evaluates its own 1M-string shard; [loglik, grad] are combined with one
+ncclAllReduce of exact 64-bit fixed-point sums inside the step).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (one JSON line on stdout)
+  python bench.py --impl reference ...                           the reference's CPU implementation
+  torchrun ... bench.py --gpus N ...                             one rank per GPU
+
+`value`  : kernel-resident throughput -- x already on the device, K evaluations timed with CUDA
+           events on the library's own stream, max over ranks.
+`e2e`    : the same metric through the C-ABI call a w-fsa maintainer would make
+           (wfsa_dev_eval with HOST buffers): H2D of x from pinned memory, all kernels,
+           D2H of [loglik, grad], every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "w-fsa_b200", "python"))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "fwd-bwd+grad symbols/sec"
+UNIT = "symbols/s"
+C4 = dict(n_states=256, n_sym=64, n_succ=8, n_emis=4, seed=1234)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation (oracle/_ref/wfsa_ref = unmodified reference sources +
+    MKL stand-in, single-threaded like the reference's mkl_sequential build) on a bounded sample of
+    the same workload: a step = one QuasiNewtonLearner::OptimizationStep.  Falls back to the CPU
+    port (oracle/wfsa_oracle.c) when the reference binary is not present."""
+    if rank != 0:
+        return
+    from wfsa_b200 import synth
+    model = synth.make_model(**C4)
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "wfsa_ref")
+    steps, warm = args.steps, args.warmup
+    if os.path.exists(ref_bin) and not args.cpu_port:
+        n = args.ref_strings
+        offs, toks, w = model.corpus(n, 32, 128, seed=1235)
+        with tempfile.TemporaryDirectory() as tmp:
+            fa, fc = os.path.join(tmp, "c4.wfsa"), os.path.join(tmp, "c4.corpus")
+            open(fa, "w").write(model.text())
+            open(fc, "w").write(model.corpus_text(offs, toks, w))
+
+            def run(epochs):
+                t = time.perf_counter()
+                subprocess.run([ref_bin, "-a", fa, "-c", fc, "-opt", "QuasiNewton", "-i", "7", "-e", str(epochs), "-tol", "0", "-s"],
+                               check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                return time.perf_counter() - t
+            t0 = run(0)                       # load + path enumeration (Learner::BuildFrom), one-time
+            t1 = run(warm + steps)
+        per_step = max(t1 - t0, 1e-9) / (warm + steps)
+        tokens = int(offs[-1])
+        kind, cores = "reference", 1
+        sample = "%d strings (%d symbols) of config 4; one-time path enumeration %.1f s excluded" % (n, tokens, t0)
+    else:
+        from oracle import oracle as O
+        low = model.lowered()
+        n = args.cpu_strings
+        offs, toks, w = model.corpus(n, 32, 128, seed=1235)
+        low.set_tokens(offs, toks, w / w.sum())
+        zt, ze = np.zeros(low.n_trans), np.zeros(low.n_emis)
+        cores = O.max_threads()
+        for _ in range(warm):
+            O.dp_eval(low, zt, ze, nthreads=cores)
+        t = time.perf_counter()
+        for _ in range(steps):
+            O.dp_eval(low, zt, ze, nthreads=cores)
+        per_step = (time.perf_counter() - t) / steps
+        tokens = int(offs[-1])
+        kind = "port"
+        sample = "%d strings (%d symbols) of config 4, CPU forward-backward port" % (n, tokens)
+    value = tokens / per_step
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warm, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config 4: WFSA 256 states / 64 symbols / ~8k arcs, strings of length 32-128 (bounded sample)",
+                       "strings": n, "symbols": tokens},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(model, budget_s=12.0):
+    """CPU forward-backward port (oracle) on a bounded sample, all host cores."""
+    from oracle import oracle as O
+    low = model.lowered()
+    cores = O.max_threads()
+    n = 20000
+    offs, toks, w = model.corpus(n, 32, 128, seed=99)
+    low.set_tokens(offs, toks, w / w.sum())
+    zt, ze = np.zeros(low.n_trans), np.zeros(low.n_emis)
+    t = time.perf_counter()
+    O.dp_eval(low, zt, ze, nthreads=cores)
+    dt = time.perf_counter() - t
+    reps = int(max(1, min(50, budget_s / max(dt, 1e-3))))
+    t = time.perf_counter()
+    for _ in range(reps):
+        O.dp_eval(low, zt, ze, nthreads=cores)
+    dt = (time.perf_counter() - t) / reps
+    return {"value": float(offs[-1]) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d strings (%d symbols) of config 4 x %d repetitions, oracle/wfsa_oracle.c forward-backward, OpenMP" % (n, int(offs[-1]), reps)}
+
+
+def run_ours(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    import wfsa_b200 as W
+    from wfsa_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the w-fsa B200 backend has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    model = synth.make_model(**C4)
+    low = model.lowered()
+    n_strings = args.strings
+    if args.scaling == "strong":
+        offs, toks, w = model.corpus(n_strings, 32, 128, seed=1235)
+        total_w = float(w.sum())
+        cuts = synth.balanced_ranges(offs, world)
+        a, b = cuts[rank], cuts[rank + 1]
+        toks = toks[offs[a]:offs[b]]
+        offs = offs[a:b + 1] - offs[a]
+        w = w[a:b]
+    else:
+        offs, toks, w = model.corpus(n_strings, 32, 128, seed=1235 + 7919 * rank)
+        total_w = float(w.sum()) * world          # every shard has the same expected weight; exact value is irrelevant
+        if world > 1:
+            tw = torch.tensor([float(w.sum())], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tw)
+            total_w = float(tw.item())
+    low.set_tokens(offs, toks, w / total_w)
+    my_tokens = int(offs[-1])
+
+    dev = W.Device(low, device=local, force_kernel=args.kernel, accum_mode=args.accum, accum_variant=args.variant)
+    if world > 1:
+        uid = np.zeros(W.UNIQUE_ID_BYTES, dtype=np.uint8)
+        if rank == 0:
+            W.lib().wfsa_dev_comm_unique_id(uid.ctypes.data_as(W.C.c_void_p))
+        t = torch.from_numpy(uid).cuda()
+        dist.broadcast(t, 0)
+        dev.comm_init(t.cpu().numpy().tobytes(), rank, world)
+    rec, pc, used = dev.structure()
+    assert rec.all(), "synthetic strings are random walks of the automaton: all must be recognised"
+    trimmed = np.where(used > 0, 0, -2).astype(np.int32)
+    n = 0
+    for i in range(len(trimmed)):            # config 4 has no lone survivors; plain compaction
+        if trimmed[i] == 0:
+            trimmed[i] = n
+            n += 1
+    dev.set_param_map(trimmed, n, rec)
+    info = dev.info()
+    x = np.random.RandomState(0).normal(-1.0, 0.3, size=n)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        dev.sync()
+
+    # ---- kernel-resident timing
+    dev.upload_x(x)
+    for _ in range(args.warmup):
+        dev.eval_launch()
+    dev.sync()
+    launches0 = dev.info()["kernels_launched"]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    dev.timer_begin()
+    for _ in range(args.steps):
+        dev.eval_launch()
+    ms = dev.timer_end()
+    barrier()
+    kms, klaunches = dev.timer_kernel_ms()
+    launches = dev.info()["kernels_launched"] - launches0
+    ll, grad = dev.eval_fetch()
+    # ---- end to end through the host-buffer C-ABI call
+    for _ in range(max(1, args.warmup // 2)):
+        dev.eval(x, want_logq=False)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        ll_e, _, g_e = dev.eval(x, want_logq=False)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    assert ll_e == ll and np.array_equal(g_e, grad), "resident and host-buffer evaluations must agree bitwise"
+
+    tok_total, ms_max, e2e_max, kms_max = float(my_tokens), ms, e2e_s, kms
+    if world > 1:
+        v = torch.tensor([ms, e2e_s, kms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        ms_max, e2e_max, kms_max = [float(a) for a in v.tolist()]
+        tt = torch.tensor([float(my_tokens)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt)
+        tok_total = float(tt.item())
+    if rank == 0:
+        steps = args.steps
+        value = tok_total * steps / (ms_max * 1e-3)
+        e2e = tok_total * steps / e2e_max
+        peak, peak_src = peaks()
+        alg_bytes = 4.0 * my_tokens + 20.0 * len(w) + 8.0 * n + float(info["table_bytes"])
+        k_ms = kms_max / max(klaunches, 1)
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config 4: synthetic WFSA 256 states / 64 symbols / %d combined arcs, %d strings of length 32-128 per GPU"
+                                   % (info["n_arcs"], n_strings if args.scaling == "weak" else n_strings // world),
+                       "strings_per_gpu": len(w), "symbols_per_gpu": my_tokens, "parameters": n,
+                       "kernel": {1: "K2 warp-per-string", 2: "K3 CTA-per-string", 3: "generic"}[info["kernel"]],
+                       "accumulators": {1: "shared memory (64-bit fixed point)", 2: "global REDs (64-bit fixed point)"}[info["accum_mode"]],
+                       "grid": info["grid"], "block": info["block"], "smem_bytes": info["smem_bytes"],
+                       "l2_policy": "inputs larger than L2 (%.0f MB of tokens per evaluation vs 126 MB L2)" % (4e-6 * my_tokens),
+                       "collective": "ncclAllReduce(int64 sum) of [loglik, grad] per step" if world > 1 else "none",
+                       "seeds": {"automaton": C4["seed"], "strings": 1235}},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "k2_fwdbwd" if info["kernel"] == 1 else "k3_fwdbwd",
+                         "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_share_of_step": kms_max / ms_max},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * (n + 2),
+                    "ms_per_step": e2e_max * 1e3 / steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "loglik": ll,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(model)
+        print(json.dumps(line), flush=True)
+    dev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--strings", type=int, default=1000000, help="strings per GPU (weak) or in total (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--kernel", type=int, default=0)
+    ap.add_argument("--accum", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ref-strings", type=int, default=8000, help="--impl reference: strings in the bounded sample")
+    ap.add_argument("--cpu-strings", type=int, default=20000)
+    ap.add_argument("--cpu-port", action="store_true", help="--impl reference: time the CPU port instead of oracle/_ref")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank, world, local = dist_env()
+    if world == 1 and args.gpus > 1 and args.impl == "ours":
+        # launched without torchrun: re-launch one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()

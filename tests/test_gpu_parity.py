@@ -1,0 +1,372 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything goes through the C ABI
+(libwfsa_b200.so): the Session tests drive the C++ host mirror of the reference's Learner
+classes, the Device tests call wfsa_dev_* directly.  Checked against
+  * golden vectors produced by the unmodified reference (tests/golden, oracle/make_golden.py),
+  * the CPU oracle (oracle/wfsa_oracle.c, itself pinned by tests/test_cpu_oracle.py),
+  * size-independent properties at BASELINE.json's full config-4 size.
+Tolerances: log q, KL: 1e-9 relative (observed ~1e-15); gradient / H_f: 1e-9 relative per
+component with a floor of 1e-6 * max|.| (the accumulators are 64-bit fixed point);
+learned weights after a fixed epoch count: 1e-6 absolute (north_star)."""
+import math
+
+import numpy as np
+import pytest
+
+import wfsa_b200 as W
+from helpers import fnum, golden_to_mine, good_cases, key, load_cases, vec_tol_ok
+from oracle import oracle as O
+from wfsa_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+# ----------------------------------------------------------------------------------------------
+# Sessions against the reference's golden vectors
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", good_cases(), ids=lambda c: c["name"])
+def test_structure_objective_gradient_hessian(case):
+    s = W.Session(case["fsa_text"], case["corpus_text"], "Hessian")
+    d = s.describe()
+    assert d["strings"] == case["strings"] and fnum(d["paths"]) == case["paths"]
+    assert abs(fnum(d["common_support"]) - fnum(case["common_support"])) < 1e-14
+    assert d["unique_paths"] == case["unique_paths"] and d["n"] == case["n"] and d["k"] == case["k"]
+    assert [int(fnum(pc)) for _, pc in d["shard"]] == [w["paths"] for w in case["corpus"]]
+    mine = {key(e): e for e in d["edges"]}
+    for e in case["edges"]:
+        m = mine[key(e)]["trimmed"]
+        assert (m == -2) == (e["trimmed"] == -2) and (m == -1) == (e["trimmed"] == -1), key(e)
+    perm = golden_to_mine(case, d["edges"])
+    # x read from the file (after Trim compaction)
+    xf = np.array([fnum(v) for v in d["x"]])
+    assert np.array_equal(xf[perm], np.array([fnum(v) for v in case["x_file"]]))
+    for ev in case["evals"]:
+        x = np.zeros(case["n"])
+        x[perm] = [fnum(v) for v in ev["x"]]
+        r = s.eval(x)
+        ref_lq = np.array([fnum(v) for v in ev["logq"]])
+        assert np.allclose(r["logq"], ref_lq, rtol=1e-9, atol=1e-12)
+        assert abs(r["kl"] - fnum(ev["kl"])) <= 1e-9 * max(1.0, abs(fnum(ev["kl"])))
+        ok, err = vec_tol_ok(r["grad"][perm], [fnum(v) for v in ev["grad"]], 1e-9)
+        assert ok, err
+        if "Hf" in ev:
+            Hg = np.array(ev["Hf"], dtype=float)
+            Hg = np.triu(Hg) + np.triu(Hg, 1).T
+            H = s.hessian(x)[np.ix_(perm, perm)]
+            assert np.allclose(H, Hg, rtol=1e-9, atol=1e-11 * max(1.0, np.abs(Hg).max()))
+    s.close()
+
+
+def _runs():
+    out = []
+    for case in good_cases():
+        for i, run in enumerate(case.get("runs", [])):
+            if "reference_error" in run:
+                continue
+            out.append(pytest.param(case, run, id="%s-%s-i%d-e%d" % (case["name"], run["optimizer"], run["flags"], run["epochs"])))
+    return out
+
+
+@pytest.mark.parametrize("case,run", _runs())
+def test_optimisation_trajectory(case, run):
+    """Same optimiser, same -i flags, same epochs: KL / graderr / g / lambda per epoch and the learned
+    weights must follow the reference's run (src/main.cpp:271-304)."""
+    s = W.Session(case["fsa_text"], case["corpus_text"], run["optimizer"])
+    d = s.describe()
+    perm = golden_to_mine(case, d["edges"])
+    s.init(run["flags"])
+    x0 = s.x()
+    assert np.allclose(x0[perm], [fnum(v) for v in run["x_init"]][:case["n"]], rtol=1e-12, atol=1e-12)
+    hess = run["optimizer"] == "Hessian"
+    ref_rows = run["trajectory"]
+    n_cmp = len(ref_rows) - (1 if run["error"] else 0)       # the row that made the reference stop is not compared
+    halted = False
+    for row in ref_rows[:n_cmp]:
+        info = s.step(run["eta"])
+        ref = [fnum(v) for v in row["info"]]
+        cols = [0, 1, 2, 3, 6] if hess else [0, 1, 2, 3, 4]
+        for c in cols:
+            assert math.isclose(info[c], ref[c], rel_tol=2e-6, abs_tol=2e-8), (row["epoch"], c, info[c], ref[c])
+        if hess and not run["error"]:
+            assert (info[4], info[5]) == (ref[4], ref[5]), ("inertia", row["epoch"])
+            if (run["flags"] & 8) and not case["unique_paths"]:      # smallest path posterior
+                assert math.isclose(info[7], ref[7], rel_tol=2e-6, abs_tol=1e-12), ("rmin", row["epoch"])
+        if "x" in row:
+            xr = np.array([fnum(v) for v in row["x"]][:case["n"]])
+            assert np.allclose(s.x()[perm], xr, rtol=1e-6, atol=1e-6), row["epoch"]
+        halted = s.halt(run["tol"])
+        if halted:
+            break
+    if not run["error"]:
+        assert halted == run["halted"]
+        dump = W.parse(s.dump(True), case["corpus_text"])
+        mine = {key(e): fnum(e["file_logprob"]) for e in dump["edges"]}
+        for e in run["final_edges"]:
+            ref = fnum(e["logprob"])
+            if math.isinf(ref):
+                assert mine[key(e)] == ref
+            else:
+                assert abs(mine[key(e)] - ref) <= 1e-6, (key(e), mine[key(e)], ref)
+    s.close()
+
+
+def test_evaluation_result_line():
+    """-eval output of HessianLearner (src/HessianLearner.cpp:349-372) on talk: golden values in SURVEY.md 8c."""
+    case = [c for c in load_cases("fixtures") if c["name"] == "talk.wfsa+talk.corpus"][0]
+    s = W.Session(case["fsa_text"], case["corpus_text"], "Hessian")
+    s.init(31)
+    for _ in range(20):
+        s.step(1.0)
+        if s.halt(1e-6):
+            break
+    s.renormalize()
+    r = s.result()
+    ref = [-0.27031007207211, 0.27031007207211, 0.549306144334055, 0.346573590279973, -38.3012866549895, 3.58351893845611, 4, 1]
+    assert np.allclose(r[[0, 1, 2, 3, 5, 6, 7]], np.array(ref)[[0, 1, 2, 3, 5, 6, 7]], rtol=1e-9, atol=1e-12)
+    assert abs(r[4] - ref[4]) < 1e-3      # log det of a nearly singular Hessian: solver dependent
+    s.close()
+
+
+@pytest.mark.parametrize("case", [c for c in load_cases("fixtures") + load_cases("random") if c.get("degenerate")],
+                         ids=lambda c: c["name"])
+def test_degenerate_inputs(case):
+    """"Empty automaton!" / no recognised string: the reference exits 1 (src/main.cpp:217-228)."""
+    s = W.Session(case["fsa_text"], case["corpus_text"], "QuasiNewton")
+    d = s.describe()
+    assert d["degenerate"] and d["strings"] == case["strings"] and fnum(d["paths"]) == case["paths"]
+    assert d["degenerate_message"] == ("Empty automaton!" if d["n"] == 0 else "Automaton cannot generate any of the strings!")
+    with pytest.raises(W.WfsaError) as ei:
+        s.init(7)
+    assert ei.value.code == 102
+    s.close()
+
+
+def test_epsilon_cycle_is_rejected():
+    fsa = "\n^\n$\n^  0\n^ a 0\na  0 x 0\na a 0 $ 0\n"          # state a emits "" and loops on itself
+    with pytest.raises(W.WfsaError) as ei:
+        W.Session(fsa, "\nx 1\n", "QuasiNewton")
+    assert "cycle of empty emissions" in ei.value.message
+
+
+# ----------------------------------------------------------------------------------------------
+# The raw device ABI against the CPU oracle
+# ----------------------------------------------------------------------------------------------
+def build_device(low, **kw):
+    dev = W.Device(low, **kw)
+    rec, pc, used = dev.structure()
+    params = np.concatenate([low.trans_param, low.emis_param])
+    edge_used = np.array([r < 0 or used[r] for r in params])
+    trimmed, n, Ccol = O.trim(low, edge_used)
+    dev.set_param_map(trimmed, n, rec)
+    return dev, rec, pc, trimmed, n
+
+
+def oracle_grad(low, trimmed, n, ee):
+    params = np.concatenate([low.trans_param, low.emis_param])
+    g = np.zeros(n)
+    for e, r in enumerate(params):
+        if r >= 0 and trimmed[r] >= 0:
+            g[trimmed[r]] = -ee[e]
+    return g
+
+
+@pytest.fixture(scope="module")
+def medium():
+    model = synth.make_model(256, 64, 8, 4, seed=11)
+    low = model.lowered()
+    offs, toks, w = model.corpus(3000, 32, 128, seed=12)
+    # a few strings that are not recognised: unknown symbol, random junk
+    toks = toks.copy()
+    toks[offs[5]] = -1
+    rng = np.random.RandomState(5)
+    toks[offs[9]:offs[10]] = rng.randint(0, 64, size=offs[10] - offs[9])
+    low.set_tokens(offs, toks, w / w.sum())
+    return model, low
+
+
+@pytest.mark.parametrize("kernel,accum,variant", [(1, 1, 0), (1, 1, 1), (1, 2, 0), (2, 0, 0), (3, 0, 0)])
+def test_kernels_match_cpu_oracle(medium, kernel, accum, variant):
+    model, low = medium
+    count = 3000 if kernel != 3 else 300          # the generic kernel is the slow, dense one
+    dev, rec, pc, trimmed, n = build_device(low, force_kernel=kernel, accum_mode=accum, accum_variant=variant, count=count)
+    assert dev.info()["kernel"] == kernel
+    zt, ze = np.zeros(low.n_trans), np.zeros(low.n_emis)
+    opc, _, _ = O.dp_eval(low, zt, ze, count=count, want_grad=False, want_counts=True)
+    assert np.array_equal(rec.astype(bool), opc > 0) and not rec[5] and not rec[9]
+    assert np.allclose(pc, opc, rtol=1e-12)
+    rng = np.random.RandomState(1)
+    for x in (np.zeros(n), rng.normal(-1.5, 0.8, size=n)):
+        ll, logq, grad = dev.eval(x)
+        ltw, lew = low.edge_logweights(x, trimmed)
+        _, olq, oee = O.dp_eval(low, ltw, lew, count=count)
+        r = rec.astype(bool)
+        assert np.allclose(logq[r], olq[r], rtol=1e-12, atol=1e-10)
+        assert np.all(np.isneginf(logq[~r]))
+        p = low.p[:count]
+        assert abs(ll - float(np.sum(p[r] * olq[r]))) <= 1e-10 * abs(ll)
+        # oracle gradient restricted to recognised strings == all strings (unrecognised contribute 0)
+        ok, err = vec_tol_ok(grad, oracle_grad(low, trimmed, n, oee), 1e-9)
+        assert ok, err
+    dev.close()
+
+
+def test_accumulation_variants_are_bitwise_identical(medium):
+    """64-bit fixed-point accumulation: shared-memory (split / CAS) and global REDs, and repeated runs,
+    give the same bits; two half-shards add up to the whole."""
+    model, low = medium
+    outs = []
+    rng = np.random.RandomState(2)
+    x = None
+    for accum, variant in ((1, 0), (1, 1), (2, 0), (1, 0)):
+        dev, rec, pc, trimmed, n = build_device(low, force_kernel=1, accum_mode=accum, accum_variant=variant)
+        if x is None:
+            x = rng.normal(-1.0, 0.5, size=n)
+        outs.append(dev.eval(x))
+        dev.close()
+    for o in outs[1:]:
+        assert o[0] == outs[0][0] and np.array_equal(o[2], outs[0][2]) and np.array_equal(o[1], outs[0][1])
+    # additivity over shards (what the multi-GPU all-reduce relies on)
+    tot_ll, tot_g = 0.0, np.zeros_like(outs[0][2])
+    for first, count in ((0, 1400), (1400, 1600)):
+        dev = W.Device(low, force_kernel=1, first=first, count=count)
+        rec, pc, used = dev.structure()
+        dev.set_param_map(trimmed, n, rec)      # the map of the whole corpus (used flags are all-reduced in real runs)
+        ll, _, g = dev.eval(x)
+        tot_ll += ll
+        tot_g += g
+        dev.close()
+    assert abs(tot_ll - outs[0][0]) <= 1e-13 * abs(outs[0][0])
+    assert np.allclose(tot_g, outs[0][2], rtol=1e-13, atol=1e-18)
+
+
+def test_edge_cases():
+    # emissions all one token; "" is in the language (start -> end); b is a dead end
+    fsa = "\n^\n$\n^  0\n^ a -0.5 b -1 $ -2\na x -1 y -0.3\na a -0.7 $ -0.9\nb x 0\nb b 0\n"
+    words = [("", 2.0), ("x", 1.0), ("xy", 1.0), ("zz", 1.0), ("xq", 3.0), ("yyyy", 1.0)]
+    d = W.parse(fsa, "\nx 1\n")
+    low = W.Lowered(d, corpus=words)
+    for kernel in (1, 2, 3):
+        dev, rec, pc, trimmed, n = build_device(low, force_kernel=kernel)
+        assert rec.tolist() == [1, 1, 1, 0, 0, 1] and pc.tolist() == [1, 1, 1, 0, 0, 1]
+        x = np.array([-0.4, -1.1, -0.2, -0.6, -0.8, -1.3])[:n]
+        ll, logq, grad = dev.eval(x)
+        ltw, lew = low.edge_logweights(x, trimmed)
+        _, olq, oee = O.enum_eval(low, ltw, lew)
+        assert np.allclose(logq[rec > 0], olq[rec > 0], rtol=1e-13) and np.all(np.isneginf(logq[rec == 0]))
+        ok, err = vec_tol_ok(grad, oracle_grad(low, trimmed, n, oee), 1e-9)
+        assert ok, (kernel, err)
+        dev.close()
+    # an empty shard is legal (a rank may own no strings)
+    low0 = W.Lowered(d, corpus=[])
+    dev = W.Device(low0)
+    rec, pc, used = dev.structure()
+    assert len(rec) == 0 and not used.any()
+    dev.set_param_map(np.full(low0.n_raw, -2, dtype=np.int32), 0, rec)
+    ll, _, g = dev.eval(np.zeros(0))
+    assert ll == 0.0 and len(g) == 0
+    dev.close()
+
+
+def test_long_strings_need_rescaling():
+    """4000-token strings with small weights: q ~ e^-14000, far below DBL_MIN; the lazy power-of-two
+    rescaling must keep log q and the posteriors exact (the reference underflows here)."""
+    model = synth.make_model(64, 16, 4, 3, seed=21)
+    low = model.lowered()
+    offs, toks, w = model.corpus(40, 3500, 4000, seed=22)
+    low.set_tokens(offs, toks, w / w.sum())
+    for kernel in (1, 2):
+        dev, rec, pc, trimmed, n = build_device(low, force_kernel=kernel)
+        assert rec.all()
+        rng = np.random.RandomState(4)
+        for x in (rng.normal(-3.0, 1.0, size=n), rng.normal(+2.5, 1.0, size=n)):
+            ll, logq, grad = dev.eval(x)
+            ltw, lew = low.edge_logweights(x, trimmed)
+            _, olq, oee = O.dp_eval(low, ltw, lew)
+            assert np.all(np.isfinite(logq)) and np.allclose(logq, olq, rtol=1e-11)
+            ok, err = vec_tol_ok(grad, oracle_grad(low, trimmed, n, oee), 1e-9)
+            assert ok, (kernel, err)
+        dev.close()
+
+
+def test_config5_shape_cta_kernel():
+    """Down-scaled config 5 (dense: more than 32 states emit a symbol -> CTA-per-string kernel)."""
+    model = synth.make_model(512, 64, 16, 8, seed=31)       # 64 states per symbol
+    low = model.lowered()
+    offs, toks, w = model.corpus(400, 16, 48, seed=32)
+    low.set_tokens(offs, toks, w / w.sum())
+    dev, rec, pc, trimmed, n = build_device(low)
+    assert dev.info()["kernel"] == 2 and rec.all()
+    x = np.random.RandomState(6).normal(-1.0, 0.4, size=n)
+    ll, logq, grad = dev.eval(x)
+    ltw, lew = low.edge_logweights(x, trimmed)
+    _, olq, oee = O.dp_eval(low, ltw, lew)
+    assert np.allclose(logq, olq, rtol=1e-12)
+    ok, err = vec_tol_ok(grad, oracle_grad(low, trimmed, n, oee), 1e-9)
+    assert ok, err
+    dev.close()
+
+
+def test_full_size_config4_properties():
+    """BASELINE config 4 at full size (1M strings, ~80M tokens): too big for the oracle, so check
+    size-independent identities: every position emits exactly one symbol and takes exactly one
+    transition (+1 into the end state), run-to-run bitwise determinism, and a 20k-string sample
+    against the oracle."""
+    model = synth.make_model(256, 64, 8, 4, seed=1234)
+    low = model.lowered()
+    offs, toks, w = model.corpus(1000000, 32, 128, seed=1235)
+    p = w / w.sum()
+    low.set_tokens(offs, toks, p)
+    dev, rec, pc, trimmed, n = build_device(low)
+    assert rec.all() and dev.info()["kernel"] == 1
+    assert n == low.n_raw            # nothing is trimmed at this size
+    x = np.zeros(n)
+    ll, logq, grad = dev.eval(x)
+    lens = np.diff(offs)
+    params = np.concatenate([low.trans_param, low.emis_param])
+    is_emis = np.concatenate([np.zeros(low.n_trans, bool), np.ones(low.n_emis, bool)])
+    ge = -sum(grad[trimmed[r]] for r, em in zip(params, is_emis) if r >= 0 and em)
+    gt = -sum(grad[trimmed[r]] for r, em in zip(params, is_emis) if r >= 0 and not em)
+    assert abs(ge - float(np.sum(p * lens))) <= 1e-10 * ge
+    assert abs(gt - float(np.sum(p * (lens + 1)))) <= 1e-10 * gt
+    assert abs(ll - float(np.sum(p * logq))) <= 1e-10 * abs(ll)
+    ll2, logq2, grad2 = dev.eval(x)
+    assert ll2 == ll and np.array_equal(grad, grad2) and np.array_equal(logq, logq2)
+    ltw, lew = low.edge_logweights(x, trimmed)
+    _, olq, _ = O.dp_eval(low, ltw, lew, first=500000, count=20000, want_grad=False)
+    assert np.allclose(logq[500000:520000], olq, rtol=1e-12)
+    dev.close()
+
+
+def test_hessian_contraction_random_blocks():
+    """K5 (FP64 tensor-core contraction) on random dense path blocks against numpy."""
+    rng = np.random.RandomState(9)
+    fsa = "\n^\n$\n^  0\n^ a 0 b 0\na x 0 y 0\na a 0 $ 0 b 0\nb x 0 y 0\nb b 0 $ 0 a 0\n"
+    low = W.Lowered(W.parse(fsa, "\nx 1\nxy 1\n"))
+    dev, rec, pc, trimmed, n = build_device(low)
+    nb = 37
+    path_off, col_off, val_off, cols, counts, ps = [0], [0], [0], [], [], []
+    for b in range(nb):
+        L, D = rng.randint(2, 40), rng.randint(1, n + 1)
+        c = rng.choice(n, D, replace=False)
+        M = rng.randint(0, 4, size=(L, D)).astype(float)
+        cols.extend(c.tolist()); counts.extend(M.reshape(-1).tolist()); ps.append(rng.uniform(0.01, 0.2))
+        path_off.append(path_off[-1] + L); col_off.append(len(cols)); val_off.append(len(counts))
+    arr = lambda v, t: np.ascontiguousarray(np.array(v, dtype=t))
+    po, co, vo = arr(path_off, np.int64), arr(col_off, np.int64), arr(val_off, np.int64)
+    cl, ct, pp = arr(cols, np.int32), arr(counts, np.float64), arr(ps, np.float64)
+    import ctypes as C
+    pb = W.PathBlocks(nb, W._p(po, W.I64P), W._p(co, W.I64P), W._p(cl, W.I32P), W._p(vo, W.I64P), W._p(ct, W.F64P), W._p(pp, W.F64P))
+    dev._ck(dev.L.wfsa_dev_set_path_blocks(dev.h, C.byref(pb)))
+    x = rng.normal(-1, 0.7, size=n)
+    H = np.zeros((n, n)); rmin = C.c_double()
+    dev._ck(dev.L.wfsa_dev_hessian(dev.h, W._p(x, W.F64P), W._p(H, W.F64P), C.byref(rmin)))
+    Href = np.zeros((n, n)); rm = np.inf
+    for b in range(nb):
+        c = cl[co[b]:co[b + 1]]
+        M = ct[vo[b]:vo[b + 1]].reshape(path_off[b + 1] - path_off[b], len(c))
+        s = M @ x[c]
+        r = np.exp(s - s.max()); r /= r.sum()
+        rm = min(rm, r.min())
+        g = M.T @ r
+        Href[np.ix_(c, c)] += pp[b] * (np.outer(g, g) - M.T @ (r[:, None] * M))
+    assert np.allclose(H, Href, rtol=1e-9, atol=1e-11) and abs(rmin.value - rm) <= 1e-12
+    dev.close()

@@ -112,6 +112,7 @@ struct wfsa_dev {
     DevBuf<double> d_hb_counts, d_hb_p, d_hb_r, d_H, d_rmin;
     DevBuf<unsigned long long> d_Hfx;
     int64_t hb_blocks = -1, hb_paths = 0;
+    int hb_fx_log2 = 40;
     // comm
     ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
     // timing
@@ -612,6 +613,21 @@ extern "C" int wfsa_dev_set_path_blocks(wfsa_dev* h, const wfsa_path_blocks* b)
     CK(h->d_H.alloc(std::max<size_t>((size_t)h->n * h->n, 1)));
     CK(h->d_rmin.alloc(1));
     CK(cudaStreamSynchronize(h->stream));
+    // fixed-point scale of H: |H_jk| <= sum_s p_s * cmax^2 <= cmax^2 (p sums to <= 1 over all ranks)
+    double cmax = 1.0;
+    for (double c : counts) cmax = std::max(cmax, std::fabs(c));
+    long long bound = (long long)std::ceil(cmax * cmax) + 1;
+    if (h->comm) {
+        long long* d = reinterpret_cast<long long*>(h->d_red.p);
+        CK(cudaMemcpyAsync(d, &bound, 8, cudaMemcpyHostToDevice, h->stream));
+        int rc = nccl_allreduce(h, d, 1, ncclInt64, ncclMax);
+        if (rc != WFSA_OK) return rc;
+        CK(cudaMemcpyAsync(&bound, d, 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    int bits = 1;
+    while ((1ll << bits) <= bound && bits < 50) ++bits;
+    h->hb_fx_log2 = 61 - bits;
     h->hb_blocks = nb; h->hb_paths = po[nb];
     return WFSA_OK;
 }
@@ -626,8 +642,7 @@ extern "C" int wfsa_dev_hessian(wfsa_dev* h, const double* x, double* Hf, double
     CK(cudaMemsetAsync(h->d_Hfx.p, 0, std::max<size_t>(nn, 1) * 8, h->stream));
     const double inf = INFINITY;
     CK(cudaMemcpyAsync(h->d_rmin.p, &inf, 8, cudaMemcpyHostToDevice, h->stream));
-    // |H_jk| <= p_s * (max count)^2 summed over strings; 2^40 head room is ample for counts < 2^10
-    const double fx = std::ldexp(1.0, 40);
+    const double fx = std::ldexp(1.0, h->hb_fx_log2);
     if (h->hb_blocks > 0) {
         HessParams P{};
         P.n_blocks = h->hb_blocks; P.path_off = h->d_hb_path_off.p; P.col_off = h->d_hb_col_off.p; P.cols = h->d_hb_cols.p;
