@@ -96,9 +96,18 @@ __device__ __forceinline__ unsigned long long stack_ld(const unsigned long long*
     return (i < cap) ? s[i] : g[i - cap];
 }
 
+struct PairTablesD {
+    const uint32_t* __restrict__ pair_row;    // [(n_sym+1)*n_sym]  start << 10 | count
+    const uint16_t* __restrict__ pair_arcs;   // [n_arcs]           src_slot | dst_slot << 5
+    const uint32_t* __restrict__ cand_off;    // [n_sym+2]
+    const double* __restrict__ aw;            // [n_arcs]  a(u,v) * b(v,c_next), recomputed per evaluation
+    const double* __restrict__ fw;            // [n_slots] a(state of slot, end), 0 if none
+    int n_sym, n_arcs, n_slots, start_final_tid;
+};
+
 struct K2Params {
-    FastTablesD T;
-    EvalWeightsD W;
+    PairTablesD T;
+    const double* __restrict__ tw;   // only for the empty string (start -> end)
     CorpusD C;
     EvalOutD O;
     int n_acc_smem;                  // accumulators kept in shared memory (0 => ACC_GLOBAL)
@@ -107,25 +116,58 @@ struct K2Params {
     size_t gl_stack_words;           // per warp
 };
 
+__host__ __device__ inline size_t k2_table_bytes(int n_sym, int n_arcs, int n_slots)
+{
+    size_t b = (size_t)n_arcs * 8 + (size_t)n_slots * 8;               // aw, fw
+    b += ((size_t)(n_sym + 1) * n_sym + (size_t)n_sym + 2) * 4;         // pair_row, cand_off
+    b = (b + 7) & ~(size_t)7;
+    b += ((size_t)n_arcs * 2 + 7) & ~(size_t)7;                          // pair_arcs
+    return b;
+}
+
 // ------------------------------------------------------------------------------------------
-// K2: one warp per string, candidates of the current symbol across lanes (<= 32 of them),
-// alpha/beta in registers, gathers through warp shuffles, lattice on a per-warp stack.
+// K2: one warp per string.  Lane j <-> j-th candidate (state emitting the current symbol, at most
+// 32 of them); alpha / beta live in registers.  A step between consecutive symbols (c_prev, c)
+// walks the combined arcs of that symbol pair -- about n_arcs / n_sym^2 of them (2 for config 4) --
+// with warp-uniform shared-memory reads and one shuffle per arc.  The automaton (pair table,
+// per-arc weights, final weights) is staged once per CTA into shared memory; the per-warp
+// lattice stack and the per-arc gradient accumulators live there too.
 // ------------------------------------------------------------------------------------------
-template <int MODE, int ACC>
+template <int MODE, int ACC, int TABS>
 __global__ void __launch_bounds__(1024, 1) k2_fwdbwd(const K2Params P)
 {
     extern __shared__ unsigned long long smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int A = P.T.n_sym, NA = P.T.n_arcs, NS = P.T.n_slots;
     unsigned long long* acc_s = smem;
-    unsigned long long* stack = smem + P.n_acc_smem + (size_t)warp * P.stack_cap;
+    unsigned long long* sp_base = smem + P.n_acc_smem;
+    const double* aw = P.T.aw;
+    const double* fw = P.T.fw;
+    const uint32_t* pair_row = P.T.pair_row;
+    const uint32_t* cand_off = P.T.cand_off;
+    const uint16_t* pair_arcs = P.T.pair_arcs;
+    if (TABS) {
+        double* s_aw = reinterpret_cast<double*>(sp_base);
+        double* s_fw = s_aw + NA;
+        uint32_t* s_row = reinterpret_cast<uint32_t*>(s_fw + NS);
+        const int n_row = (A + 1) * A;
+        uint32_t* s_coff = s_row + n_row;
+        uint16_t* s_arcs = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(sp_base) +
+                                                       ((((size_t)NA + NS) * 8 + ((size_t)n_row + A + 2) * 4 + 7) & ~(size_t)7));
+        for (int i = threadIdx.x; i < NA; i += blockDim.x) { s_aw[i] = aw[i]; s_arcs[i] = pair_arcs[i]; }
+        for (int i = threadIdx.x; i < NS; i += blockDim.x) s_fw[i] = fw[i];
+        for (int i = threadIdx.x; i < n_row; i += blockDim.x) s_row[i] = pair_row[i];
+        for (int i = threadIdx.x; i < A + 2; i += blockDim.x) s_coff[i] = cand_off[i];
+        aw = s_aw; fw = s_fw; pair_row = s_row; cand_off = s_coff; pair_arcs = s_arcs;
+        sp_base += k2_table_bytes(A, NA, NS) / 8;
+    }
+    unsigned long long* stack = sp_base + (size_t)warp * P.stack_cap;
     const long long gw = (long long)blockIdx.x * nwarps + warp, GW = (long long)gridDim.x * nwarps;
     unsigned long long* gstack = P.gl_stack + (size_t)gw * P.gl_stack_words;
     const int cap = P.stack_cap;
     for (int i = threadIdx.x; i < P.n_acc_smem; i += blockDim.x) acc_s[i] = 0ull;
     __syncthreads();
 
-    const FastTablesD& T = P.T;
-    const int A = T.n_sym;
     const unsigned lt_mask = (1u << lane) - 1u;
     long long ll_fx = 0;
     unsigned long long bad = 0;
@@ -139,16 +181,16 @@ __global__ void __launch_bounds__(1024, 1) k2_fwdbwd(const K2Params P)
 
         if (len == 0) {   // the empty string is accepted iff start -> end exists
             if (lane == 0) {
-                const double q = T.start_final_tid >= 0 ? P.W.tw[T.start_final_tid] : 0.0;
+                const double q = P.T.start_final_tid >= 0 ? P.tw[P.T.start_final_tid] : 0.0;
                 if (MODE == MODE_STRUCT) {
                     P.O.path_count[sid] = q;
-                    if (q != 0.0) atomicAdd(P.O.red + 2 + T.start_final_tid, 1ull);
+                    if (q != 0.0) atomicAdd(P.O.red + 2 + P.T.start_final_tid, 1ull);
                 } else {
                     const double lq = log(q);
                     if (P.O.logq) P.O.logq[sid] = lq;
                     if (q > 0.0 && isfinite(lq)) {
                         ll_fx += __double2ll_rn(ps * lq * P.O.ll_scale);
-                        atomicAdd(P.O.red + 2 + T.start_final_tid, (unsigned long long)__double2ll_rn(ps * P.O.fx_scale));
+                        atomicAdd(P.O.red + 2 + P.T.start_final_tid, (unsigned long long)__double2ll_rn(ps * P.O.fx_scale));
                     } else bad++;
                 }
             }
@@ -157,29 +199,22 @@ __global__ void __launch_bounds__(1024, 1) k2_fwdbwd(const K2Params P)
 
         // ---------------- forward ----------------
         double alpha = (lane == 0) ? 1.0 : 0.0;   // START pseudo position: only the start state
-        int E = 0, sp = 0, cprev = A, tokreg = 0;
+        int E = 0, sp = 0, cprev = A, tokreg = 0, c = 0;
         bool dead = false;
-        uint32_t slot = 0;
         for (int t = 0; t < len; ++t) {
             if ((t & 31) == 0) tokreg = (t + lane < len) ? __ldcs(tok + t + lane) : -1;
-            const int c = __shfl_sync(FULL, tokreg, t & 31);
+            c = __shfl_sync(FULL, tokreg, t & 31);
             if ((unsigned)c >= (unsigned)A) { dead = true; break; }
-            const uint32_t c0 = T.cand_off[c], ncand = T.cand_off[c + 1] - c0;
-            const bool valid = (uint32_t)lane < ncand;
-            slot = c0 + lane;
-            uint32_t row = 0;
-            if (valid) row = T.frow[(size_t)T.slot_state[slot] * (A + 1) + cprev];
-            const int cnt = row & ((1u << kRowCntBitsD) - 1);
-            const uint32_t st = row >> kRowCntBitsD;
-            const int maxcnt = __reduce_max_sync(FULL, cnt);
+            const uint32_t row = pair_row[cprev * A + c];
+            const int cnt = row & 1023;
+            const uint32_t st = row >> 10;
             double a_new = 0.0;
-            for (int k = 0; k < maxcnt; ++k) {
-                uint32_t ent = 0; double a = 0.0;
-                if (k < cnt) { ent = T.fent[st + k]; a = P.W.tw[ent >> kSlotBitsD]; }
-                const double au = __shfl_sync(FULL, alpha, ent & 31);
-                a_new = fma(a, au, a_new);
+            for (int j = 0; j < cnt; ++j) {
+                const uint32_t arc = pair_arcs[st + j];
+                const double v = __shfl_sync(FULL, alpha, arc & 31);
+                if (lane == (int)(arc >> 5)) a_new = fma(aw[st + j], v, a_new);
             }
-            alpha = valid ? a_new * P.W.sw[slot] : 0.0;
+            alpha = a_new;
             const unsigned mask = __ballot_sync(FULL, alpha != 0.0);
             if (mask == 0) { dead = true; break; }
             if ((t & (kRescaleEvery - 1)) == kRescaleEvery - 1) {
@@ -198,8 +233,10 @@ __global__ void __launch_bounds__(1024, 1) k2_fwdbwd(const K2Params P)
             cprev = c;
         }
         double qh = 0.0, fin = 0.0;
+        int fslot = 0;
         if (!dead) {
-            fin = (alpha != 0.0) ? P.W.fw[slot] : 0.0;   // slot of the last position
+            fslot = (int)cand_off[c] + lane;              // c = last symbol
+            fin = (alpha != 0.0) ? fw[fslot] : 0.0;
             qh = warp_sum(alpha * fin);
         }
         if (dead || !(qh > 0.0) || !isfinite(qh)) {
@@ -222,83 +259,60 @@ __global__ void __launch_bounds__(1024, 1) k2_fwdbwd(const K2Params P)
 
         // ---------------- backward ----------------
         const double invq = 1.0 / qh;
-        double bt;            // beta~ of the position processed last
-        int F = 0, cnext;
+        const double sc0 = (MODE == MODE_STRUCT) ? 1.0 : invq * ps * P.O.fx_scale;
+        double beta;          // beta of the position processed last (lanes = its candidates)
+        int F = 0, cnext = c;
         {   // position len-1: beta = a(v,end); posterior of the final transition
             const unsigned long long meta = stack_ld(stack, gstack, cap, sp - 1);
-            const unsigned mask = (unsigned)meta;
-            const int n = __popc(mask);
-            sp -= n + 1;
-            const bool on = (mask >> lane) & 1u;
-            // alpha (registers) still holds position len-1
-            if (on && fin != 0.0) {
-                if (MODE == MODE_STRUCT) acc_add<ACC>(acc_s, P.O.acc_global, T.n_arcs + (int)slot, 1);
-                else acc_add<ACC>(acc_s, P.O.acc_global, T.n_arcs + (int)slot,
-                                  __double2ll_rn(alpha * fin * invq * ps * P.O.fx_scale));
+            sp -= __popc((unsigned)meta) + 1;
+            if (alpha != 0.0 && fin != 0.0) {             // alpha (registers) still holds position len-1
+                if (MODE == MODE_STRUCT) acc_add<ACC>(acc_s, P.O.acc_global, NA + fslot, 1);
+                else acc_add<ACC>(acc_s, P.O.acc_global, NA + fslot, __double2ll_rn(alpha * fin * sc0));
             }
-            bt = on ? fin * P.W.sw[slot] : 0.0;
-            const int t = len - 1;
-            cnext = __shfl_sync(FULL, tokreg, t & 31);   // tokreg holds the last chunk
+            beta = (alpha != 0.0) ? fin : 0.0;
         }
-        for (int t = len - 2; t >= 0; --t) {
-            if ((t & 31) == 31) tokreg = __ldg(tok + (t - 31) + lane);
-            const int c = __shfl_sync(FULL, tokreg, t & 31);
-            const uint32_t c0 = T.cand_off[c];
-            const unsigned long long meta = stack_ld(stack, gstack, cap, sp - 1);
-            const unsigned mask = (unsigned)meta;
-            const int Et = (int)(meta >> 32);
-            const int n = __popc(mask);
-            sp -= n + 1;
-            const bool on = (mask >> lane) & 1u;
-            slot = c0 + lane;
-            double al = 0.0;
-            uint32_t row = 0;
-            if (on) {
-                al = __longlong_as_double((long long)stack_ld(stack, gstack, cap, sp + __popc(mask & lt_mask)));
-                row = T.brow[(size_t)T.slot_state[slot] * A + cnext];
+        for (int t = len - 2; t >= -1; --t) {
+            double al; int Et; int cc;
+            if (t >= 0) {
+                if ((t & 31) == 31) tokreg = __ldg(tok + (t - 31) + lane);
+                cc = __shfl_sync(FULL, tokreg, t & 31);
+                const unsigned long long meta = stack_ld(stack, gstack, cap, sp - 1);
+                const unsigned mask = (unsigned)meta;
+                Et = (int)(meta >> 32);
+                sp -= __popc(mask) + 1;
+                al = ((mask >> lane) & 1u) ? __longlong_as_double((long long)stack_ld(stack, gstack, cap, sp + __popc(mask & lt_mask))) : 0.0;
+            } else {          // the START pseudo position
+                cc = A; Et = 0; al = (lane == 0) ? 1.0 : 0.0;
             }
-            const int cnt = row & ((1u << kRowCntBitsD) - 1);
-            const uint32_t st = row >> kRowCntBitsD;
-            const int maxcnt = __reduce_max_sync(FULL, cnt);
+            const uint32_t row = pair_row[cc * A + cnext];
+            const int cnt = row & 1023;
+            const uint32_t st = row >> 10;
             const int d = Et + F - EQ;
-            double sc = invq * ps * P.O.fx_scale;
-            if (d != 0) sc = scalbn(sc, d);
+            double sc = sc0;
+            if (MODE != MODE_STRUCT && d != 0) sc = scalbn(sc0, d);
             double b = 0.0;
-            for (int k = 0; k < maxcnt; ++k) {
-                uint32_t ent = 0; double a = 0.0;
-                if (k < cnt) { ent = T.bent[st + k]; a = P.W.tw[ent >> kSlotBitsD]; }
-                const double term = a * __shfl_sync(FULL, bt, ent & 31);
-                b += term;
-                if (k < cnt && term != 0.0) {
-                    if (MODE == MODE_STRUCT) acc_add<ACC>(acc_s, P.O.acc_global, (int)(st + k), 1);
-                    else acc_add<ACC>(acc_s, P.O.acc_global, (int)(st + k), __double2ll_rn(al * term * sc));
+            for (int j = 0; j < cnt; ++j) {
+                const uint32_t arc = pair_arcs[st + j];
+                const double bv = __shfl_sync(FULL, beta, arc >> 5);
+                if (lane == (int)(arc & 31)) {
+                    const double term = aw[st + j] * bv;
+                    b += term;
+                    if (al != 0.0 && term != 0.0) {
+                        if (MODE == MODE_STRUCT) acc_add<ACC>(acc_s, P.O.acc_global, (int)(st + j), 1);
+                        else acc_add<ACC>(acc_s, P.O.acc_global, (int)(st + j), __double2ll_rn(al * term * sc));
+                    }
                 }
             }
-            bt = on ? b * P.W.sw[slot] : 0.0;
-            if ((t & (kRescaleEvery - 1)) == 0) {
-                const int emax = __reduce_max_sync(FULL, bt != 0.0 ? biased_exp(bt) : -1);
+            beta = (al != 0.0) ? b : 0.0;
+            if (t >= 0 && (t & (kRescaleEvery - 1)) == 0) {
+                const int emax = __reduce_max_sync(FULL, beta != 0.0 ? biased_exp(beta) : -1);
                 if (emax >= 0 && (emax < 1023 - kRescaleBand || emax > 1023 + kRescaleBand)) {
                     const int shift = 1023 - emax;
-                    bt = scalbn(bt, shift);
+                    beta = scalbn(beta, shift);
                     F -= shift;
                 }
             }
-            cnext = c;
-        }
-        {   // arcs out of the start state: lane k handles entry k of row (start, c_0)
-            const uint32_t row = T.brow[(size_t)T.start_state * A + cnext];
-            const int cnt = row & ((1u << kRowCntBitsD) - 1);
-            const uint32_t st = row >> kRowCntBitsD;
-            uint32_t ent = 0; double a = 0.0;
-            if (lane < cnt) { ent = T.bent[st + lane]; a = P.W.tw[ent >> kSlotBitsD]; }
-            const double term = a * __shfl_sync(FULL, bt, ent & 31);
-            const int d = F - EQ;
-            double sc = invq * ps * P.O.fx_scale;
-            if (d != 0) sc = scalbn(sc, d);
-            if (lane < cnt && term != 0.0) {
-                if (MODE == MODE_STRUCT) acc_add<ACC>(acc_s, P.O.acc_global, (int)(st + lane), 1);
-                else acc_add<ACC>(acc_s, P.O.acc_global, (int)(st + lane), __double2ll_rn(term * sc));
-            }
+            cnext = cc;
         }
         __syncwarp();
     }
@@ -560,6 +574,12 @@ __device__ __forceinline__ double logaddexp_d(double a, double b)
     return m + log1p(exp(-fabs(a - b)));
 }
 
+// semiring: MODE_EVAL = (logaddexp, +) on log-weights; MODE_STRUCT = (+, *) on path counts
+// (linear domain so that counts stay exact integers; every weight is 1)
+template <int MODE> __device__ __forceinline__ double sr_zero() { return MODE == MODE_STRUCT ? 0.0 : -INFINITY; }
+template <int MODE> __device__ __forceinline__ double sr_plus(double a, double b) { return MODE == MODE_STRUCT ? a + b : logaddexp_d(a, b); }
+template <int MODE> __device__ __forceinline__ double sr_times(double a, double b) { return MODE == MODE_STRUCT ? a * b : a + b; }
+
 template <int MODE>
 __global__ void __launch_bounds__(128) kg_fwdbwd(const GenericParams P)
 {
@@ -575,21 +595,22 @@ __global__ void __launch_bounds__(128) kg_fwdbwd(const GenericParams P)
     const size_t lat_sz = (size_t)(P.max_len + 1) * S;
     double* la = P.scratch + (size_t)i * 2 * lat_sz;
     double* lb = la + lat_sz;
-    for (size_t k = 0; k < (size_t)(len + 1) * S; ++k) { la[k] = -INFINITY; lb[k] = -INFINITY; }
-    la[G.start_state] = 0.0;
-    double lq = -INFINITY;
+    const double ZERO = sr_zero<MODE>();
+    for (size_t k = 0; k < (size_t)(len + 1) * S; ++k) { la[k] = ZERO; lb[k] = ZERO; }
+    la[G.start_state] = (MODE == MODE_STRUCT) ? 1.0 : 0.0;
+    double lq = ZERO;
     // forward
     for (int pos = 0; pos <= len; ++pos) {
         for (int oi = 0; oi < S; ++oi) {
             const int u = G.eps_order[oi];
             const double au = la[(size_t)pos * S + u];
-            if (au == -INFINITY || u == G.end_state) continue;
+            if (au == ZERO || u == G.end_state) continue;
             for (int t = G.trans_row[u]; t < G.trans_row[u + 1]; ++t) {
                 const int v = G.trans_dst[t];
-                const double w = au + P.ltw[t];
-                if (w == -INFINITY) continue;
+                const double w = (MODE == MODE_STRUCT) ? au : au + P.ltw[t];
+                if (w == ZERO) continue;
                 if (v == G.end_state) {
-                    if (pos == len) lq = logaddexp_d(lq, w);
+                    if (pos == len) lq = sr_plus<MODE>(lq, w);
                     continue;
                 }
                 for (int e = G.emis_row[v]; e < G.emis_row[v + 1]; ++e) {
@@ -599,39 +620,43 @@ __global__ void __launch_bounds__(128) kg_fwdbwd(const GenericParams P)
                     for (int k = 0; k < el; ++k) if (tok[pos + k] != G.emis_tok[e0 + k]) { m = false; break; }
                     if (!m) continue;
                     double* dst = la + (size_t)(pos + el) * S + v;
-                    *dst = logaddexp_d(*dst, w + P.lew[e]);
+                    *dst = sr_plus<MODE>(*dst, (MODE == MODE_STRUCT) ? w : w + P.lew[e]);
                 }
             }
         }
     }
-    if (!(lq > -INFINITY) || !isfinite(lq)) {
-        if (MODE == MODE_STRUCT) P.O.path_count[sid] = 0.0;
-        else { if (P.O.logq) P.O.logq[sid] = -INFINITY; atomicAdd(P.O.red + 1, 1ull); }
-        return;
-    }
-    if (MODE == MODE_STRUCT) P.O.path_count[sid] = exp(lq);
-    else {
+    if (MODE == MODE_STRUCT) {
+        P.O.path_count[sid] = lq;
+        if (!(lq > 0.0)) return;
+    } else {
+        if (!(lq > -INFINITY) || !isfinite(lq)) {
+            if (P.O.logq) P.O.logq[sid] = -INFINITY;
+            atomicAdd(P.O.red + 1, 1ull);
+            return;
+        }
         if (P.O.logq) P.O.logq[sid] = lq;
         atomicAdd(P.O.red, (unsigned long long)__double2ll_rn(ps * lq * P.O.ll_scale));
     }
-    // backward: lb[pos][u] = log sum over continuations of (pos,u); posteriors on the way
+    // backward: lb[pos][u] = sum over continuations of (pos,u); posteriors on the way
     unsigned long long* eacc = P.O.red + 2;
     for (int pos = len; pos >= 0; --pos) {
         for (int oi = S - 1; oi >= 0; --oi) {
             const int u = G.eps_order[oi];
             const double au = la[(size_t)pos * S + u];
-            if (au == -INFINITY || u == G.end_state) continue;
-            double bu = -INFINITY;
+            if (au == ZERO || u == G.end_state) continue;
+            double bu = ZERO;
             for (int t = G.trans_row[u]; t < G.trans_row[u + 1]; ++t) {
                 const int v = G.trans_dst[t];
-                const double w = P.ltw[t];
-                if (w == -INFINITY) continue;
+                const double w = (MODE == MODE_STRUCT) ? 1.0 : P.ltw[t];
+                if (w == ZERO) continue;
                 if (v == G.end_state) {
                     if (pos == len) {
-                        bu = logaddexp_d(bu, w);
-                        const double g = exp(au + w - lq);
+                        bu = sr_plus<MODE>(bu, w);
                         if (MODE == MODE_STRUCT) atomicAdd(eacc + t, 1ull);
-                        else { const long long fx = __double2ll_rn(g * ps * P.O.fx_scale); if (fx) atomicAdd(eacc + t, (unsigned long long)fx); }
+                        else {
+                            const long long fx = __double2ll_rn(exp(au + w - lq) * ps * P.O.fx_scale);
+                            if (fx) atomicAdd(eacc + t, (unsigned long long)fx);
+                        }
                     }
                     continue;
                 }
@@ -642,10 +667,10 @@ __global__ void __launch_bounds__(128) kg_fwdbwd(const GenericParams P)
                     for (int k = 0; k < el; ++k) if (tok[pos + k] != G.emis_tok[e0 + k]) { m = false; break; }
                     if (!m) continue;
                     const double bv = lb[(size_t)(pos + el) * S + v];
-                    if (bv == -INFINITY) continue;
-                    const double term = w + P.lew[e] + bv;
-                    if (term == -INFINITY) continue;
-                    bu = logaddexp_d(bu, term);
+                    if (bv == ZERO) continue;
+                    const double term = (MODE == MODE_STRUCT) ? bv : w + P.lew[e] + bv;
+                    if (term == ZERO) continue;
+                    bu = sr_plus<MODE>(bu, term);
                     if (MODE == MODE_STRUCT) { atomicAdd(eacc + t, 1ull); atomicAdd(eacc + G.n_trans + e, 1ull); }
                     else {
                         const long long fx = __double2ll_rn(exp(au + term - lq) * ps * P.O.fx_scale);
@@ -692,6 +717,14 @@ __global__ void k_weights(int n_trans, int n_emis, int n_slots, const int32_t* _
         sw[s] = slot_emis[s] < 0 ? 1.0 : weight_of(emis_tp[slot_emis[s]], x, unit);
         fw[s] = slot_final[s] < 0 ? 0.0 : weight_of(trans_tp[slot_final[s]], x, unit);
     }
+}
+
+// per combined arc (pair-major order): aw = a(u,v) * b(v, c_next)
+__global__ void k_arc_weights(int n_arcs, const int32_t* __restrict__ parc_tid, const int32_t* __restrict__ parc_slot,
+                              const double* __restrict__ tw, const double* __restrict__ sw, double* aw)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_arcs) aw[i] = tw[parc_tid[i]] * sw[parc_slot[i]];
 }
 
 // combined-arc / final accumulators -> per-edge accumulators (integer adds: order independent)

@@ -86,7 +86,11 @@ struct wfsa_dev {
     DevBuf<double> d_p;
     // automaton tables
     DevBuf<uint32_t> d_cand_off, d_slot_state, d_frow, d_fent, d_brow, d_bent;
-    DevBuf<int32_t> d_slot_emis, d_slot_final, d_arc_tid, d_arc_eid;
+    DevBuf<int32_t> d_slot_emis, d_slot_final, d_arc_tid, d_arc_eid, d_parc_tid, d_parc_eid, d_parc_slot;
+    DevBuf<uint32_t> d_pair_row;
+    DevBuf<uint16_t> d_pair_arcs;
+    DevBuf<double> d_aw;
+    int tab_smem = 0;
     DevBuf<int32_t> d_emis_row, d_emis_tok_off, d_emis_tok, d_trans_row, d_trans_dst, d_eps_order;
     DevBuf<int32_t> d_trans_tp, d_emis_tp, d_edge_tp, d_edge_raw;
     // per evaluation
@@ -153,12 +157,14 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     DevBuf<int32_t>* i32[] = {&h->d_tokens, &h->d_order, &h->d_slot_emis, &h->d_slot_final, &h->d_arc_tid, &h->d_arc_eid,
                               &h->d_emis_row, &h->d_emis_tok_off, &h->d_emis_tok, &h->d_trans_row, &h->d_trans_dst,
-                              &h->d_eps_order, &h->d_trans_tp, &h->d_emis_tp, &h->d_edge_tp, &h->d_edge_raw, &h->d_hb_cols};
+                              &h->d_eps_order, &h->d_trans_tp, &h->d_emis_tp, &h->d_edge_tp, &h->d_edge_raw, &h->d_hb_cols,
+                              &h->d_parc_tid, &h->d_parc_eid, &h->d_parc_slot};
     for (auto* b : i32) b->release();
-    DevBuf<uint32_t>* u32[] = {&h->d_cand_off, &h->d_slot_state, &h->d_frow, &h->d_fent, &h->d_brow, &h->d_bent};
+    DevBuf<uint32_t>* u32[] = {&h->d_cand_off, &h->d_slot_state, &h->d_frow, &h->d_fent, &h->d_brow, &h->d_bent, &h->d_pair_row};
+    h->d_pair_arcs.release();
     for (auto* b : u32) b->release();
     DevBuf<double>* f64[] = {&h->d_p, &h->d_x, &h->d_tw, &h->d_sw, &h->d_fw, &h->d_ltw, &h->d_lew, &h->d_logq, &h->d_pathcnt,
-                             &h->d_out, &h->d_k3lat, &h->d_gscratch, &h->d_hb_counts, &h->d_hb_p, &h->d_hb_r, &h->d_H, &h->d_rmin};
+                             &h->d_out, &h->d_k3lat, &h->d_gscratch, &h->d_aw, &h->d_hb_counts, &h->d_hb_p, &h->d_hb_r, &h->d_H, &h->d_rmin};
     for (auto* b : f64) b->release();
     DevBuf<int64_t>* i64[] = {&h->d_offs, &h->d_hb_path_off, &h->d_hb_col_off, &h->d_hb_val_off};
     for (auto* b : i64) b->release();
@@ -177,23 +183,25 @@ static int choose_launch(wfsa_dev* h)
 {
     const FastLayout& L = h->fast;
     if (h->kernel == 1) {
-        // K2: 1 CTA per SM, as many warps as shared memory allows next to the accumulators
+        // K2: 1 CTA per SM; shared memory = [accumulators] [automaton tables] [per-warp lattice stacks]
         const size_t max_smem = 227 * 1024;
         const size_t n_acc = (size_t)L.n_arcs + L.n_slots;
+        const size_t tab = k2_table_bytes(h->fsa.n_sym, L.n_arcs, L.n_slots);
+        const int warps = 32;
+        const size_t min_stack = (size_t)warps * 128 * 8;
+        h->tab_smem = (tab + min_stack <= max_smem) ? 1 : 0;
+        const size_t tab_used = h->tab_smem ? tab : 0;
         int accum = h->opt.accum_mode;
-        const bool fits = n_acc * 8 <= 120 * 1024;
+        const bool fits = h->tab_smem && n_acc * 8 + tab_used + (size_t)warps * 160 * 8 <= max_smem;
         if (accum == 0) accum = fits ? 1 : 2;
         if (accum == 1 && !fits) accum = 2;
         h->accum = accum;
         h->n_acc_smem = accum == 1 ? (int)n_acc : 0;
-        int warps = 32;
-        size_t avail = max_smem - (size_t)h->n_acc_smem * 8;
-        int cap = (int)std::min<size_t>(avail / 8 / warps, 640);
-        if (cap < 96) { warps = 16; cap = (int)std::min<size_t>(avail / 8 / warps, 640); }
-        h->stack_cap = std::max(cap, 8);
+        const size_t avail = max_smem - (size_t)h->n_acc_smem * 8 - tab_used;
+        h->stack_cap = (int)std::min<size_t>(avail / 8 / warps, 1024);
         h->block = warps * 32;
         h->grid = h->sm_count;
-        h->smem_bytes = ((size_t)h->n_acc_smem + (size_t)warps * h->stack_cap) * 8;
+        h->smem_bytes = (size_t)h->n_acc_smem * 8 + tab_used + (size_t)warps * h->stack_cap * 8;
         h->glstack_words = (size_t)(h->max_len + 1) * 33 + 8;
         const size_t total = (size_t)h->grid * warps * h->glstack_words;
         CK(h->d_glstack.alloc(total));
@@ -262,9 +270,9 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
     msg = build_generic_layout(h->fsa, h->gen, status);
     if (status != WFSA_OK) { h->err = msg; return bail(status); }
     int kernel = h->opt.force_kernel;
-    if (kernel == 0) kernel = !h->fast.ok ? 3 : (h->fast.max_cand <= 32 ? 1 : 2);
+    if (kernel == 0) kernel = !h->fast.ok ? 3 : (h->fast.pair_ok ? 1 : 2);
     if ((kernel == 1 || kernel == 2) && !h->fast.ok) { h->err = "forced fast kernel but emissions are not all one token long"; return bail(WFSA_ERR_INVALID); }
-    if (kernel == 1 && h->fast.max_cand > 32) { h->err = "forced warp-per-string kernel but more than 32 states emit one symbol"; return bail(WFSA_ERR_INVALID); }
+    if (kernel == 1 && !h->fast.pair_ok) { h->err = "forced warp-per-string kernel but more than 32 states emit one symbol"; return bail(WFSA_ERR_INVALID); }
     if (kernel < 1 || kernel > 3) { h->err = "force_kernel out of range"; return bail(WFSA_ERR_INVALID); }
     h->kernel = kernel;
 
@@ -307,6 +315,11 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
         CKB(h->d_slot_emis.upload(L.slot_emis, st)); CKB(h->d_slot_final.upload(L.slot_final, st));
         CKB(h->d_arc_tid.upload(L.arc_tid, st)); CKB(h->d_arc_eid.upload(L.arc_eid, st));
         CKB(h->d_acc.alloc((size_t)L.n_arcs + L.n_slots));
+        if (L.pair_ok) {
+            CKB(h->d_pair_row.upload(L.pair_row, st)); CKB(h->d_pair_arcs.upload(L.pair_arcs, st));
+            CKB(h->d_parc_tid.upload(L.parc_tid, st)); CKB(h->d_parc_eid.upload(L.parc_eid, st)); CKB(h->d_parc_slot.upload(L.parc_slot, st));
+            CKB(h->d_aw.alloc(std::max(L.n_arcs, 1)));
+        }
         CKB(h->d_sw.alloc(L.n_slots)); CKB(h->d_fw.alloc(L.n_slots));
         h->table_bytes = 4 * (L.cand_off.size() + L.slot_state.size() + L.frow.size() + L.fent.size() + L.brow.size() + L.bent.size()) +
                          8 * ((size_t)F.n_trans() + 2 * L.n_slots);
@@ -327,10 +340,13 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
     CKB(h->d_used.alloc(std::max(F.n_raw, 1)));
     if (choose_launch(h) != WFSA_OK) return bail(WFSA_ERR_CUDA);
     if (h->kernel == 1) {
-        cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_SMEM_CAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_SMEM_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        const int mx = 227 * 1024;
+        cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_SMEM_CAS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_SMEM_SPLIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_GLOBAL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_GLOBAL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     }
     CKB(cudaStreamSynchronize(st));
 #undef CKB
@@ -379,24 +395,37 @@ static int launch_pipeline(wfsa_dev* h, int mode, const int32_t* d_order, int64_
         }
         if (h->kev_used < h->kev.size()) { e0 = h->kev[h->kev_used].first; e1 = h->kev[h->kev_used].second; h->kev_used++; }
     }
-    if (e0) cudaEventRecord(e0, st);
+    if (e0 && h->kernel != 1) cudaEventRecord(e0, st);
+    if (e0 && h->kernel == 1 && n_order <= 0) cudaEventRecord(e0, st);
     if (n_order > 0) {
         if (h->kernel == 1) {
+            const FastLayout& L = h->fast;
+            k_arc_weights<<<(L.n_arcs + 255) / 256, 256, 0, st>>>(L.n_arcs, h->d_parc_tid.p, h->d_parc_slot.p, h->d_tw.p, h->d_sw.p, h->d_aw.p);
+            h->launches++;
             K2Params P{};
-            P.T = fast_tables(h); P.W = EvalWeightsD{h->d_tw.p, h->d_sw.p, h->d_fw.p}; P.C = C; P.O = O;
+            P.T = PairTablesD{h->d_pair_row.p, h->d_pair_arcs.p, h->d_cand_off.p, h->d_aw.p, h->d_fw.p,
+                              h->fsa.n_sym, L.n_arcs, L.n_slots, L.start_final_tid};
+            P.tw = h->d_tw.p; P.C = C; P.O = O;
             P.stack_cap = h->stack_cap; P.gl_stack = h->d_glstack.p; P.gl_stack_words = h->glstack_words;
-            if (mode == MODE_STRUCT) {
+            const size_t tab = h->tab_smem ? k2_table_bytes(h->fsa.n_sym, L.n_arcs, L.n_slots) : 0;
+            if (e0) cudaEventRecord(e0, st);
+            if (mode == MODE_STRUCT || h->accum != 1) {
                 P.n_acc_smem = 0;
-                const size_t smem = (size_t)(h->block / 32) * h->stack_cap * 8;
-                k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL><<<h->grid, h->block, smem, st>>>(P);
-            } else if (h->accum == 1) {
-                P.n_acc_smem = h->n_acc_smem;
-                if (h->opt.reserved == 1) k2_fwdbwd<MODE_EVAL, ACC_SMEM_CAS><<<h->grid, h->block, h->smem_bytes, st>>>(P);
-                else k2_fwdbwd<MODE_EVAL, ACC_SMEM_SPLIT><<<h->grid, h->block, h->smem_bytes, st>>>(P);
+                // without shared accumulators the stacks may use what they left free
+                const size_t avail = 227 * 1024 - tab;
+                P.stack_cap = (int)std::min<size_t>(avail / 8 / (h->block / 32), 1024);
+                const size_t smem = tab + (size_t)(h->block / 32) * P.stack_cap * 8;
+                if (mode == MODE_STRUCT) {
+                    if (h->tab_smem) k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL, 1><<<h->grid, h->block, smem, st>>>(P);
+                    else k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL, 0><<<h->grid, h->block, smem, st>>>(P);
+                } else {
+                    if (h->tab_smem) k2_fwdbwd<MODE_EVAL, ACC_GLOBAL, 1><<<h->grid, h->block, smem, st>>>(P);
+                    else k2_fwdbwd<MODE_EVAL, ACC_GLOBAL, 0><<<h->grid, h->block, smem, st>>>(P);
+                }
             } else {
-                P.n_acc_smem = 0;
-                const size_t smem = (size_t)(h->block / 32) * h->stack_cap * 8;
-                k2_fwdbwd<MODE_EVAL, ACC_GLOBAL><<<h->grid, h->block, smem, st>>>(P);
+                P.n_acc_smem = h->n_acc_smem;
+                if (h->opt.reserved == 1) k2_fwdbwd<MODE_EVAL, ACC_SMEM_CAS, 1><<<h->grid, h->block, h->smem_bytes, st>>>(P);
+                else k2_fwdbwd<MODE_EVAL, ACC_SMEM_SPLIT, 1><<<h->grid, h->block, h->smem_bytes, st>>>(P);
             }
             h->launches++;
         } else if (h->kernel == 2) {
@@ -425,7 +454,8 @@ static int launch_pipeline(wfsa_dev* h, int mode, const int32_t* d_order, int64_
     if (h->fast.ok && h->kernel != 3) {
         const int total = h->fast.n_arcs + h->fast.n_slots;
         k_arcs_to_edges<<<(total + 255) / 256, 256, 0, st>>>(h->fast.n_arcs, h->fast.n_slots, F.n_trans(), h->d_acc.p,
-                                                            h->d_arc_tid.p, h->d_arc_eid.p, h->d_slot_final.p, h->d_red.p + 2);
+                                                            h->kernel == 1 ? h->d_parc_tid.p : h->d_arc_tid.p,
+                                                            h->kernel == 1 ? h->d_parc_eid.p : h->d_arc_eid.p, h->d_slot_final.p, h->d_red.p + 2);
         h->launches++;
         CK(cudaGetLastError());
     }
