@@ -96,17 +96,18 @@ __device__ __forceinline__ unsigned long long stack_ld(const unsigned long long*
     return (i < cap) ? s[i] : g[i - cap];
 }
 
-struct PairTablesD {
-    const uint32_t* __restrict__ pair_row;    // [(n_sym+1)*n_sym]  start << 10 | count
-    const uint16_t* __restrict__ pair_arcs;   // [n_arcs]           src_slot | dst_slot << 5
+struct WarpTablesD {
+    const uint16_t* __restrict__ brow;        // [n_states*n_sym + 1] row starts of (state, next symbol)
+    const uint8_t* __restrict__ bent;         // [n_arcs] target slot inside E[c_next]
+    const uint16_t* __restrict__ slot_state;  // [n_slots]
     const uint32_t* __restrict__ cand_off;    // [n_sym+2]
     const double* __restrict__ aw;            // [n_arcs]  a(u,v) * b(v,c_next), recomputed per evaluation
     const double* __restrict__ fw;            // [n_slots] a(state of slot, end), 0 if none
-    int n_sym, n_arcs, n_slots, start_final_tid;
+    int n_sym, n_states, n_arcs, n_slots, start_state, start_final_tid;
 };
 
 struct K2Params {
-    PairTablesD T;
+    WarpTablesD T;
     const double* __restrict__ tw;   // only for the empty string (start -> end)
     CorpusD C;
     EvalOutD O;
@@ -116,22 +117,32 @@ struct K2Params {
     size_t gl_stack_words;           // per warp
 };
 
-__host__ __device__ inline size_t k2_table_bytes(int n_sym, int n_arcs, int n_slots)
+// byte layout of the staged tables: aw | fw | cand_off | brow | slot_state | bent  (each 8-byte aligned)
+struct K2TableLayout { size_t aw, fw, coff, brow, sstate, bent, total; };
+__host__ __device__ inline K2TableLayout k2_table_layout(int n_sym, int n_states, int n_arcs, int n_slots)
 {
-    size_t b = (size_t)n_arcs * 8 + (size_t)n_slots * 8;               // aw, fw
-    b += ((size_t)(n_sym + 1) * n_sym + (size_t)n_sym + 2) * 4;         // pair_row, cand_off
-    b = (b + 7) & ~(size_t)7;
-    b += ((size_t)n_arcs * 2 + 7) & ~(size_t)7;                          // pair_arcs
-    return b;
+    K2TableLayout t;
+    size_t o = 0;
+    auto al = [](size_t v) { return (v + 7) & ~(size_t)7; };
+    t.aw = o; o += (size_t)n_arcs * 8;
+    t.fw = o; o += (size_t)n_slots * 8;
+    t.coff = o; o = al(o + ((size_t)n_sym + 2) * 4);
+    t.brow = o; o = al(o + ((size_t)n_states * n_sym + 1) * 2);
+    t.sstate = o; o = al(o + (size_t)n_slots * 2);
+    t.bent = o; o = al(o + (size_t)n_arcs);
+    t.total = o;
+    return t;
 }
 
 // ------------------------------------------------------------------------------------------
 // K2: one warp per string.  Lane j <-> j-th candidate (state emitting the current symbol, at most
-// 32 of them); alpha / beta live in registers.  A step between consecutive symbols (c_prev, c)
-// walks the combined arcs of that symbol pair -- about n_arcs / n_sym^2 of them (2 for config 4) --
-// with warp-uniform shared-memory reads and one shuffle per arc.  The automaton (pair table,
-// per-arc weights, final weights) is staged once per CTA into shared memory; the per-warp
-// lattice stack and the per-arc gradient accumulators live there too.
+// 32 of them); alpha / beta live in registers.
+//   forward : the few ACTIVE source lanes (ballot mask, ~2 for config 4) scatter along their
+//             (state, next symbol) CSR row; one shuffle pair per source;
+//   backward: every active lane gathers beta over its own row through shuffles and adds the arc
+//             posteriors to the per-arc accumulators.
+// The automaton (16-bit CSR rows, 8-bit targets, per-arc weights, final weights) is staged once
+// per CTA into shared memory next to the per-arc accumulators and the per-warp lattice stacks.
 // ------------------------------------------------------------------------------------------
 template <int MODE, int ACC, int TABS>
 __global__ void __launch_bounds__(1024, 1) k2_fwdbwd(const K2Params P)
@@ -143,23 +154,26 @@ __global__ void __launch_bounds__(1024, 1) k2_fwdbwd(const K2Params P)
     unsigned long long* sp_base = smem + P.n_acc_smem;
     const double* aw = P.T.aw;
     const double* fw = P.T.fw;
-    const uint32_t* pair_row = P.T.pair_row;
+    const uint16_t* brow = P.T.brow;
+    const uint8_t* bent = P.T.bent;
+    const uint16_t* slot_state = P.T.slot_state;
     const uint32_t* cand_off = P.T.cand_off;
-    const uint16_t* pair_arcs = P.T.pair_arcs;
     if (TABS) {
-        double* s_aw = reinterpret_cast<double*>(sp_base);
-        double* s_fw = s_aw + NA;
-        uint32_t* s_row = reinterpret_cast<uint32_t*>(s_fw + NS);
-        const int n_row = (A + 1) * A;
-        uint32_t* s_coff = s_row + n_row;
-        uint16_t* s_arcs = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(sp_base) +
-                                                       ((((size_t)NA + NS) * 8 + ((size_t)n_row + A + 2) * 4 + 7) & ~(size_t)7));
-        for (int i = threadIdx.x; i < NA; i += blockDim.x) { s_aw[i] = aw[i]; s_arcs[i] = pair_arcs[i]; }
-        for (int i = threadIdx.x; i < NS; i += blockDim.x) s_fw[i] = fw[i];
-        for (int i = threadIdx.x; i < n_row; i += blockDim.x) s_row[i] = pair_row[i];
+        const K2TableLayout tl = k2_table_layout(A, P.T.n_states, NA, NS);
+        unsigned char* base = reinterpret_cast<unsigned char*>(sp_base);
+        double* s_aw = reinterpret_cast<double*>(base + tl.aw);
+        double* s_fw = reinterpret_cast<double*>(base + tl.fw);
+        uint32_t* s_coff = reinterpret_cast<uint32_t*>(base + tl.coff);
+        uint16_t* s_brow = reinterpret_cast<uint16_t*>(base + tl.brow);
+        uint16_t* s_ss = reinterpret_cast<uint16_t*>(base + tl.sstate);
+        uint8_t* s_bent = base + tl.bent;
+        const int n_row = P.T.n_states * A + 1;
+        for (int i = threadIdx.x; i < NA; i += blockDim.x) { s_aw[i] = aw[i]; s_bent[i] = bent[i]; }
+        for (int i = threadIdx.x; i < NS; i += blockDim.x) { s_fw[i] = fw[i]; s_ss[i] = slot_state[i]; }
+        for (int i = threadIdx.x; i < n_row; i += blockDim.x) s_brow[i] = brow[i];
         for (int i = threadIdx.x; i < A + 2; i += blockDim.x) s_coff[i] = cand_off[i];
-        aw = s_aw; fw = s_fw; pair_row = s_row; cand_off = s_coff; pair_arcs = s_arcs;
-        sp_base += k2_table_bytes(A, NA, NS) / 8;
+        aw = s_aw; fw = s_fw; brow = s_brow; bent = s_bent; slot_state = s_ss; cand_off = s_coff;
+        sp_base += tl.total / 8;
     }
     unsigned long long* stack = sp_base + (size_t)warp * P.stack_cap;
     const long long gw = (long long)blockIdx.x * nwarps + warp, GW = (long long)gridDim.x * nwarps;
@@ -199,23 +213,31 @@ __global__ void __launch_bounds__(1024, 1) k2_fwdbwd(const K2Params P)
 
         // ---------------- forward ----------------
         double alpha = (lane == 0) ? 1.0 : 0.0;   // START pseudo position: only the start state
-        int E = 0, sp = 0, cprev = A, tokreg = 0, c = 0;
+        unsigned mask = 1u;                       // active lanes of the previous position
+        int my_state = P.T.start_state;           // state of this lane's slot at the previous position
+        int E = 0, sp = 0, tokreg = 0, c = 0;
         bool dead = false;
         for (int t = 0; t < len; ++t) {
             if ((t & 31) == 0) tokreg = (t + lane < len) ? __ldcs(tok + t + lane) : -1;
             c = __shfl_sync(FULL, tokreg, t & 31);
             if ((unsigned)c >= (unsigned)A) { dead = true; break; }
-            const uint32_t row = pair_row[cprev * A + c];
-            const int cnt = row & 1023;
-            const uint32_t st = row >> 10;
+            unsigned rc = 0;
+            if ((mask >> lane) & 1u) {
+                const int r = my_state * A + c;
+                const unsigned r0 = brow[r];
+                rc = (r0 << 8) | (brow[r + 1] - r0);
+            }
             double a_new = 0.0;
-            for (int j = 0; j < cnt; ++j) {
-                const uint32_t arc = pair_arcs[st + j];
-                const double v = __shfl_sync(FULL, alpha, arc & 31);
-                if (lane == (int)(arc >> 5)) a_new = fma(aw[st + j], v, a_new);
+            for (unsigned m = mask; m; m &= m - 1) {          // active sources scatter along their row
+                const int s = __ffs(m) - 1;
+                const unsigned rcs = __shfl_sync(FULL, rc, s);
+                const double val = __shfl_sync(FULL, alpha, s);
+                const unsigned r0 = rcs >> 8, cnt = rcs & 255u;
+                for (unsigned j = r0; j < r0 + cnt; ++j)
+                    if (lane == (int)bent[j]) a_new = fma(aw[j], val, a_new);
             }
             alpha = a_new;
-            const unsigned mask = __ballot_sync(FULL, alpha != 0.0);
+            mask = __ballot_sync(FULL, alpha != 0.0);
             if (mask == 0) { dead = true; break; }
             if ((t & (kRescaleEvery - 1)) == kRescaleEvery - 1) {
                 const int emax = __reduce_max_sync(FULL, alpha != 0.0 ? biased_exp(alpha) : -1);
@@ -225,12 +247,12 @@ __global__ void __launch_bounds__(1024, 1) k2_fwdbwd(const K2Params P)
                     E -= shift;
                 }
             }
+            if (alpha != 0.0) my_state = slot_state[cand_off[c] + lane];
             // push [values..., meta] on the lattice stack
             const int n = __popc(mask);
             if (alpha != 0.0) stack_st(stack, gstack, cap, sp + __popc(mask & lt_mask), (unsigned long long)__double_as_longlong(alpha));
             if (lane == 0) stack_st(stack, gstack, cap, sp + n, (unsigned long long)mask | ((unsigned long long)(unsigned)E << 32));
             sp += n + 1;
-            cprev = c;
         }
         double qh = 0.0, fin = 0.0;
         int fslot = 0;
@@ -272,38 +294,41 @@ __global__ void __launch_bounds__(1024, 1) k2_fwdbwd(const K2Params P)
             beta = (alpha != 0.0) ? fin : 0.0;
         }
         for (int t = len - 2; t >= -1; --t) {
-            double al; int Et; int cc;
+            double al = 0.0; int Et = 0; int cc = A; int st_id = 0; bool on;
             if (t >= 0) {
                 if ((t & 31) == 31) tokreg = __ldg(tok + (t - 31) + lane);
                 cc = __shfl_sync(FULL, tokreg, t & 31);
                 const unsigned long long meta = stack_ld(stack, gstack, cap, sp - 1);
-                const unsigned mask = (unsigned)meta;
+                const unsigned msk = (unsigned)meta;
                 Et = (int)(meta >> 32);
-                sp -= __popc(mask) + 1;
-                al = ((mask >> lane) & 1u) ? __longlong_as_double((long long)stack_ld(stack, gstack, cap, sp + __popc(mask & lt_mask))) : 0.0;
+                sp -= __popc(msk) + 1;
+                on = (msk >> lane) & 1u;
+                if (on) {
+                    al = __longlong_as_double((long long)stack_ld(stack, gstack, cap, sp + __popc(msk & lt_mask)));
+                    st_id = slot_state[cand_off[cc] + lane];
+                }
             } else {          // the START pseudo position
-                cc = A; Et = 0; al = (lane == 0) ? 1.0 : 0.0;
+                on = (lane == 0);
+                if (on) { al = 1.0; st_id = P.T.start_state; }
             }
-            const uint32_t row = pair_row[cc * A + cnext];
-            const int cnt = row & 1023;
-            const uint32_t st = row >> 10;
+            unsigned r0 = 0, cnt = 0;
+            if (on) { const int r = st_id * A + cnext; r0 = brow[r]; cnt = brow[r + 1] - r0; }
+            const unsigned maxcnt = __reduce_max_sync(FULL, cnt);
             const int d = Et + F - EQ;
             double sc = sc0;
             if (MODE != MODE_STRUCT && d != 0) sc = scalbn(sc0, d);
             double b = 0.0;
-            for (int j = 0; j < cnt; ++j) {
-                const uint32_t arc = pair_arcs[st + j];
-                const double bv = __shfl_sync(FULL, beta, arc >> 5);
-                if (lane == (int)(arc & 31)) {
-                    const double term = aw[st + j] * bv;
-                    b += term;
-                    if (al != 0.0 && term != 0.0) {
-                        if (MODE == MODE_STRUCT) acc_add<ACC>(acc_s, P.O.acc_global, (int)(st + j), 1);
-                        else acc_add<ACC>(acc_s, P.O.acc_global, (int)(st + j), __double2ll_rn(al * term * sc));
-                    }
+            for (unsigned k = 0; k < maxcnt; ++k) {
+                unsigned dst = 0; double w = 0.0;
+                if (k < cnt) { dst = bent[r0 + k]; w = aw[r0 + k]; }
+                const double term = w * __shfl_sync(FULL, beta, dst);
+                b += term;
+                if (k < cnt && term != 0.0) {
+                    if (MODE == MODE_STRUCT) acc_add<ACC>(acc_s, P.O.acc_global, (int)(r0 + k), 1);
+                    else acc_add<ACC>(acc_s, P.O.acc_global, (int)(r0 + k), __double2ll_rn(al * term * sc));
                 }
             }
-            beta = (al != 0.0) ? b : 0.0;
+            beta = on ? b : 0.0;
             if (t >= 0 && (t & (kRescaleEvery - 1)) == 0) {
                 const int emax = __reduce_max_sync(FULL, beta != 0.0 ? biased_exp(beta) : -1);
                 if (emax >= 0 && (emax < 1023 - kRescaleBand || emax > 1023 + kRescaleBand)) {
@@ -719,12 +744,13 @@ __global__ void k_weights(int n_trans, int n_emis, int n_slots, const int32_t* _
     }
 }
 
-// per combined arc (pair-major order): aw = a(u,v) * b(v, c_next)
-__global__ void k_arc_weights(int n_arcs, const int32_t* __restrict__ parc_tid, const int32_t* __restrict__ parc_slot,
-                              const double* __restrict__ tw, const double* __restrict__ sw, double* aw)
+// per combined arc (bwd-CSR order): aw = a(u,v) * b(v, c_next)
+__global__ void k_arc_weights(int n_arcs, const int32_t* __restrict__ arc_tid, const int32_t* __restrict__ arc_eid,
+                              const int32_t* __restrict__ emis_tp, const double* __restrict__ tw,
+                              const double* __restrict__ x, int unit, double* aw)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_arcs) aw[i] = tw[parc_tid[i]] * sw[parc_slot[i]];
+    if (i < n_arcs) aw[i] = tw[arc_tid[i]] * weight_of(emis_tp[arc_eid[i]], x, unit);
 }
 
 // combined-arc / final accumulators -> per-edge accumulators (integer adds: order independent)

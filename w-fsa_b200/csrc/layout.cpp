@@ -159,38 +159,16 @@ std::string build_fast_layout(const HostFsa& f, FastLayout& L, int& status)
     for (auto& r : brow_eid) L.arc_eid.insert(L.arc_eid.end(), r.begin(), r.end());
     for (int a = 0; a < L.n_arcs; ++a) L.arc_tid[a] = (int32_t)(L.bent[a] >> kSlotBits);
     L.ok = true;
-    // symbol-pair table for the warp-per-string kernel
-    if (L.max_cand <= 32 && (size_t)L.n_arcs < (1u << 22)) {
-        const size_t R = (size_t)(A + 1) * A;
-        std::vector<std::vector<uint32_t>> prow(R);       // packed src | dst<<5 | tid<<10 (tid only used here)
-        std::vector<std::vector<std::pair<int, int>>> pmeta(R);   // (tid, global dst slot)
-        for (int u = 0; u < S; ++u) {
-            if (u == f.end) continue;
-            for (int t = f.trans_row[u]; t < f.trans_row[u + 1]; ++t) {
-                const int v = f.trans_dst[t];
-                if (v == f.end) continue;
-                for (auto& su : slots_of_state[u])
-                    for (auto& sv : slots_of_state[v]) {
-                        if (sv.first == A) continue;
-                        const size_t r = (size_t)su.first * A + sv.first;
-                        prow[r].push_back((uint32_t)su.second | ((uint32_t)sv.second << 5));
-                        pmeta[r].push_back({t, (int)L.cand_off[sv.first] + sv.second});
-                    }
-            }
-        }
-        bool fits = true;
-        L.pair_row.assign(R, 0);
-        for (size_t r = 0; r < R && fits; ++r) {
-            if (prow[r].size() >= 1024) { fits = false; break; }
-            L.pair_row[r] = ((uint32_t)L.pair_arcs.size() << 10) | (uint32_t)prow[r].size();
-            for (size_t i = 0; i < prow[r].size(); ++i) {
-                L.pair_arcs.push_back((uint16_t)prow[r][i]);
-                L.parc_tid.push_back(pmeta[r][i].first);
-                L.parc_slot.push_back(pmeta[r][i].second);
-                L.parc_eid.push_back(L.slot_emis[pmeta[r][i].second]);
-            }
-        }
-        L.pair_ok = fits && (int)L.pair_arcs.size() == L.n_arcs;
+    // compact tables for the warp-per-string kernel
+    if (L.max_cand <= 32 && L.n_arcs < 65536 && S < 65536) {
+        L.brow16.resize(L.brow.size() + 1);
+        for (size_t r = 0; r < L.brow.size(); ++r) L.brow16[r] = (uint16_t)(L.brow[r] >> kRowCntBits);
+        L.brow16[L.brow.size()] = (uint16_t)L.n_arcs;
+        L.bent_dst.resize(L.n_arcs);
+        for (int a = 0; a < L.n_arcs; ++a) L.bent_dst[a] = (uint8_t)(L.bent[a] & ((1u << kSlotBits) - 1));
+        L.slot_state16.resize(L.n_slots);
+        for (int i = 0; i < L.n_slots; ++i) L.slot_state16[i] = (uint16_t)L.slot_state[i];
+        L.warp_ok = true;
     }
     return "";
 }

@@ -48,15 +48,13 @@ struct FastLayout {
     std::vector<int32_t> arc_tid;    // [n_arcs] transition edge of combined arc
     std::vector<int32_t> arc_eid;    // [n_arcs] emission edge of the arc's target slot
     int start_final_tid = -1;        // transition start->end (accepts the empty string)
-    // Symbol-pair table (warp-per-string kernel): the combined arcs between the candidates of
-    // consecutive symbols, grouped by (c_prev, c_next); one table serves both sweeps.
-    //   pair_row[c_prev * n_sym + c_next] = start << 10 | count   (c_prev == n_sym: START)
-    //   pair_arcs[j] = src_slot | dst_slot << 5                   (slots < 32)
-    // j is the pair-major id of the combined arc (accumulator index).
-    bool pair_ok = false;
-    std::vector<uint32_t> pair_row;
-    std::vector<uint16_t> pair_arcs;
-    std::vector<int32_t> parc_tid, parc_eid, parc_slot;   // [n_arcs] transition, emission edge, global dst slot
+    // Compact tables of the warp-per-string kernel (staged in shared memory): the bwd CSR above with
+    // 16-bit row starts, 8-bit target slots and 16-bit slot->state; usable when at most 32 states
+    // emit one symbol and the automaton has fewer than 65536 combined arcs.
+    bool warp_ok = false;
+    std::vector<uint16_t> brow16;        // [n_states*n_sym + 1] row starts (arc ids are bwd-CSR positions)
+    std::vector<uint8_t> bent_dst;       // [n_arcs] target slot inside E[c_next]
+    std::vector<uint16_t> slot_state16;  // [n_slots]
 };
 
 struct GenericLayout {

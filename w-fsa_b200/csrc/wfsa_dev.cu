@@ -86,9 +86,9 @@ struct wfsa_dev {
     DevBuf<double> d_p;
     // automaton tables
     DevBuf<uint32_t> d_cand_off, d_slot_state, d_frow, d_fent, d_brow, d_bent;
-    DevBuf<int32_t> d_slot_emis, d_slot_final, d_arc_tid, d_arc_eid, d_parc_tid, d_parc_eid, d_parc_slot;
-    DevBuf<uint32_t> d_pair_row;
-    DevBuf<uint16_t> d_pair_arcs;
+    DevBuf<int32_t> d_slot_emis, d_slot_final, d_arc_tid, d_arc_eid;
+    DevBuf<uint16_t> d_brow16, d_sstate16;
+    DevBuf<uint8_t> d_bent8;
     DevBuf<double> d_aw;
     int tab_smem = 0;
     DevBuf<int32_t> d_emis_row, d_emis_tok_off, d_emis_tok, d_trans_row, d_trans_dst, d_eps_order;
@@ -157,11 +157,10 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     DevBuf<int32_t>* i32[] = {&h->d_tokens, &h->d_order, &h->d_slot_emis, &h->d_slot_final, &h->d_arc_tid, &h->d_arc_eid,
                               &h->d_emis_row, &h->d_emis_tok_off, &h->d_emis_tok, &h->d_trans_row, &h->d_trans_dst,
-                              &h->d_eps_order, &h->d_trans_tp, &h->d_emis_tp, &h->d_edge_tp, &h->d_edge_raw, &h->d_hb_cols,
-                              &h->d_parc_tid, &h->d_parc_eid, &h->d_parc_slot};
+                              &h->d_eps_order, &h->d_trans_tp, &h->d_emis_tp, &h->d_edge_tp, &h->d_edge_raw, &h->d_hb_cols};
     for (auto* b : i32) b->release();
-    DevBuf<uint32_t>* u32[] = {&h->d_cand_off, &h->d_slot_state, &h->d_frow, &h->d_fent, &h->d_brow, &h->d_bent, &h->d_pair_row};
-    h->d_pair_arcs.release();
+    DevBuf<uint32_t>* u32[] = {&h->d_cand_off, &h->d_slot_state, &h->d_frow, &h->d_fent, &h->d_brow, &h->d_bent};
+    h->d_brow16.release(); h->d_sstate16.release(); h->d_bent8.release();
     for (auto* b : u32) b->release();
     DevBuf<double>* f64[] = {&h->d_p, &h->d_x, &h->d_tw, &h->d_sw, &h->d_fw, &h->d_ltw, &h->d_lew, &h->d_logq, &h->d_pathcnt,
                              &h->d_out, &h->d_k3lat, &h->d_gscratch, &h->d_aw, &h->d_hb_counts, &h->d_hb_p, &h->d_hb_r, &h->d_H, &h->d_rmin};
@@ -186,7 +185,7 @@ static int choose_launch(wfsa_dev* h)
         // K2: 1 CTA per SM; shared memory = [accumulators] [automaton tables] [per-warp lattice stacks]
         const size_t max_smem = 227 * 1024;
         const size_t n_acc = (size_t)L.n_arcs + L.n_slots;
-        const size_t tab = k2_table_bytes(h->fsa.n_sym, L.n_arcs, L.n_slots);
+        const size_t tab = k2_table_layout(h->fsa.n_sym, h->fsa.n_states, L.n_arcs, L.n_slots).total;
         const int warps = 32;
         const size_t min_stack = (size_t)warps * 128 * 8;
         h->tab_smem = (tab + min_stack <= max_smem) ? 1 : 0;
@@ -270,9 +269,9 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
     msg = build_generic_layout(h->fsa, h->gen, status);
     if (status != WFSA_OK) { h->err = msg; return bail(status); }
     int kernel = h->opt.force_kernel;
-    if (kernel == 0) kernel = !h->fast.ok ? 3 : (h->fast.pair_ok ? 1 : 2);
+    if (kernel == 0) kernel = !h->fast.ok ? 3 : (h->fast.warp_ok ? 1 : 2);
     if ((kernel == 1 || kernel == 2) && !h->fast.ok) { h->err = "forced fast kernel but emissions are not all one token long"; return bail(WFSA_ERR_INVALID); }
-    if (kernel == 1 && !h->fast.pair_ok) { h->err = "forced warp-per-string kernel but more than 32 states emit one symbol"; return bail(WFSA_ERR_INVALID); }
+    if (kernel == 1 && !h->fast.warp_ok) { h->err = "forced warp-per-string kernel but more than 32 states emit one symbol"; return bail(WFSA_ERR_INVALID); }
     if (kernel < 1 || kernel > 3) { h->err = "force_kernel out of range"; return bail(WFSA_ERR_INVALID); }
     h->kernel = kernel;
 
@@ -315,9 +314,8 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
         CKB(h->d_slot_emis.upload(L.slot_emis, st)); CKB(h->d_slot_final.upload(L.slot_final, st));
         CKB(h->d_arc_tid.upload(L.arc_tid, st)); CKB(h->d_arc_eid.upload(L.arc_eid, st));
         CKB(h->d_acc.alloc((size_t)L.n_arcs + L.n_slots));
-        if (L.pair_ok) {
-            CKB(h->d_pair_row.upload(L.pair_row, st)); CKB(h->d_pair_arcs.upload(L.pair_arcs, st));
-            CKB(h->d_parc_tid.upload(L.parc_tid, st)); CKB(h->d_parc_eid.upload(L.parc_eid, st)); CKB(h->d_parc_slot.upload(L.parc_slot, st));
+        if (L.warp_ok) {
+            CKB(h->d_brow16.upload(L.brow16, st)); CKB(h->d_bent8.upload(L.bent_dst, st)); CKB(h->d_sstate16.upload(L.slot_state16, st));
             CKB(h->d_aw.alloc(std::max(L.n_arcs, 1)));
         }
         CKB(h->d_sw.alloc(L.n_slots)); CKB(h->d_fw.alloc(L.n_slots));
@@ -400,14 +398,17 @@ static int launch_pipeline(wfsa_dev* h, int mode, const int32_t* d_order, int64_
     if (n_order > 0) {
         if (h->kernel == 1) {
             const FastLayout& L = h->fast;
-            k_arc_weights<<<(L.n_arcs + 255) / 256, 256, 0, st>>>(L.n_arcs, h->d_parc_tid.p, h->d_parc_slot.p, h->d_tw.p, h->d_sw.p, h->d_aw.p);
-            h->launches++;
+            if (L.n_arcs > 0) {
+                k_arc_weights<<<(L.n_arcs + 255) / 256, 256, 0, st>>>(L.n_arcs, h->d_arc_tid.p, h->d_arc_eid.p, h->d_emis_tp.p,
+                                                                      h->d_tw.p, h->d_x.p, unit, h->d_aw.p);
+                h->launches++;
+            }
             K2Params P{};
-            P.T = PairTablesD{h->d_pair_row.p, h->d_pair_arcs.p, h->d_cand_off.p, h->d_aw.p, h->d_fw.p,
-                              h->fsa.n_sym, L.n_arcs, L.n_slots, L.start_final_tid};
+            P.T = WarpTablesD{h->d_brow16.p, h->d_bent8.p, h->d_sstate16.p, h->d_cand_off.p, h->d_aw.p, h->d_fw.p,
+                              h->fsa.n_sym, h->fsa.n_states, L.n_arcs, L.n_slots, h->fsa.start, L.start_final_tid};
             P.tw = h->d_tw.p; P.C = C; P.O = O;
             P.stack_cap = h->stack_cap; P.gl_stack = h->d_glstack.p; P.gl_stack_words = h->glstack_words;
-            const size_t tab = h->tab_smem ? k2_table_bytes(h->fsa.n_sym, L.n_arcs, L.n_slots) : 0;
+            const size_t tab = h->tab_smem ? k2_table_layout(h->fsa.n_sym, h->fsa.n_states, L.n_arcs, L.n_slots).total : 0;
             if (e0) cudaEventRecord(e0, st);
             if (mode == MODE_STRUCT || h->accum != 1) {
                 P.n_acc_smem = 0;
@@ -454,8 +455,7 @@ static int launch_pipeline(wfsa_dev* h, int mode, const int32_t* d_order, int64_
     if (h->fast.ok && h->kernel != 3) {
         const int total = h->fast.n_arcs + h->fast.n_slots;
         k_arcs_to_edges<<<(total + 255) / 256, 256, 0, st>>>(h->fast.n_arcs, h->fast.n_slots, F.n_trans(), h->d_acc.p,
-                                                            h->kernel == 1 ? h->d_parc_tid.p : h->d_arc_tid.p,
-                                                            h->kernel == 1 ? h->d_parc_eid.p : h->d_arc_eid.p, h->d_slot_final.p, h->d_red.p + 2);
+                                                            h->d_arc_tid.p, h->d_arc_eid.p, h->d_slot_final.p, h->d_red.p + 2);
         h->launches++;
         CK(cudaGetLastError());
     }
