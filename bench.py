@@ -216,7 +216,8 @@ def run_ours(args, rank, world, local):
     low.set_tokens(offs, toks, w / total_w)
     my_tokens = int(offs[-1])
 
-    dev = W.Device(low, device=local, force_kernel=args.kernel, accum_mode=args.accum, accum_variant=args.variant)
+    variant = args.variant | (args.replicas << 8) | (2 if args.noacc else 0)
+    dev = W.Device(low, device=local, force_kernel=args.kernel, accum_mode=args.accum, accum_variant=variant)
     if world > 1:
         uid = np.zeros(W.UNIQUE_ID_BYTES, dtype=np.uint8)
         if rank == 0:
@@ -315,6 +316,7 @@ def run_ours(args, rank, world, local):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * (n + 2),
                     "ms_per_step": e2e_max * 1e3 / steps},
             "gpu_launches": int(launches),
+            **({"INVALID": "--noacc timing experiment: gradient accumulation skipped"} if args.noacc else {}),
             "clocks": clocks,
             "loglik": ll,
         }
@@ -337,6 +339,8 @@ def main():
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--accum", type=int, default=0)
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--replicas", type=int, default=0, help="copies of the global accumulators (0 = library default)")
+    ap.add_argument("--noacc", action="store_true", help="timing experiment: skip gradient accumulation (INVALID as a result)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ref-strings", type=int, default=8000, help="--impl reference: strings in the bounded sample")
     ap.add_argument("--cpu-strings", type=int, default=20000)

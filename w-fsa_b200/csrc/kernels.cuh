@@ -24,7 +24,7 @@ constexpr int kRescaleEvery = 4;       // positions between exponent checks
 constexpr int kRescaleBand = 300;      // rescale when the largest entry leaves 2^(+-300)
 
 enum { MODE_EVAL = 0, MODE_STRUCT = 1 };
-enum { ACC_SMEM_CAS = 0, ACC_SMEM_SPLIT = 1, ACC_GLOBAL = 2 };
+enum { ACC_SMEM_CAS = 0, ACC_SMEM_SPLIT = 1, ACC_GLOBAL = 2, ACC_NONE = 3 /* timing experiments only */ };
 
 struct FastTablesD {
     const uint32_t* __restrict__ cand_off;    // [n_sym+2]
@@ -72,7 +72,7 @@ __device__ __forceinline__ int biased_exp(double a) { return (__double2hiint(a) 
 template <int ACC>
 __device__ __forceinline__ void acc_add(unsigned long long* acc_s, unsigned long long* acc_g, int idx, long long v)
 {
-    if (v == 0) return;
+    if (v == 0 || ACC == ACC_NONE) return;
     if (ACC == ACC_GLOBAL) {
         atomicAdd(acc_g + idx, (unsigned long long)v);                       // REDG.E.ADD.64
     } else if (ACC == ACC_SMEM_CAS) {
@@ -115,6 +115,7 @@ struct K2Params {
     int stack_cap;                   // lattice stack words per warp in shared memory
     unsigned long long* gl_stack;    // overflow of the lattice stacks
     size_t gl_stack_words;           // per warp
+    int replicas;                    // copies of the global accumulators (CTA b uses copy b % replicas)
 };
 
 // byte layout of the staged tables: aw | fw | cand_off | brow | slot_state | bent  (each 8-byte aligned)
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(1024, 1) k2_fwdbwd(const K2Params P)
     const long long gw = (long long)blockIdx.x * nwarps + warp, GW = (long long)gridDim.x * nwarps;
     unsigned long long* gstack = P.gl_stack + (size_t)gw * P.gl_stack_words;
     const int cap = P.stack_cap;
+    unsigned long long* const acc_g = P.O.acc_global + (size_t)(blockIdx.x % P.replicas) * (size_t)(NA + NS);
     for (int i = threadIdx.x; i < P.n_acc_smem; i += blockDim.x) acc_s[i] = 0ull;
     __syncthreads();
 
@@ -288,8 +290,8 @@ __global__ void __launch_bounds__(1024, 1) k2_fwdbwd(const K2Params P)
             const unsigned long long meta = stack_ld(stack, gstack, cap, sp - 1);
             sp -= __popc((unsigned)meta) + 1;
             if (alpha != 0.0 && fin != 0.0) {             // alpha (registers) still holds position len-1
-                if (MODE == MODE_STRUCT) acc_add<ACC>(acc_s, P.O.acc_global, NA + fslot, 1);
-                else acc_add<ACC>(acc_s, P.O.acc_global, NA + fslot, __double2ll_rn(alpha * fin * sc0));
+                if (MODE == MODE_STRUCT) acc_add<ACC>(acc_s, acc_g, NA + fslot, 1);
+                else acc_add<ACC>(acc_s, acc_g, NA + fslot, __double2ll_rn(alpha * fin * sc0));
             }
             beta = (alpha != 0.0) ? fin : 0.0;
         }
@@ -324,8 +326,8 @@ __global__ void __launch_bounds__(1024, 1) k2_fwdbwd(const K2Params P)
                 const double term = w * __shfl_sync(FULL, beta, dst);
                 b += term;
                 if (k < cnt && term != 0.0) {
-                    if (MODE == MODE_STRUCT) acc_add<ACC>(acc_s, P.O.acc_global, (int)(r0 + k), 1);
-                    else acc_add<ACC>(acc_s, P.O.acc_global, (int)(r0 + k), __double2ll_rn(al * term * sc));
+                    if (MODE == MODE_STRUCT) acc_add<ACC>(acc_s, acc_g, (int)(r0 + k), 1);
+                    else acc_add<ACC>(acc_s, acc_g, (int)(r0 + k), __double2ll_rn(al * term * sc));
                 }
             }
             beta = on ? b : 0.0;
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(1024, 1) k2_fwdbwd(const K2Params P)
         __syncthreads();
         for (int i = threadIdx.x; i < P.n_acc_smem; i += blockDim.x) {
             const unsigned long long v = acc_s[i];
-            if (v) atomicAdd(P.O.acc_global + i, v);
+            if (v) atomicAdd(acc_g + i, v);
         }
     }
 }
@@ -754,19 +756,20 @@ __global__ void k_arc_weights(int n_arcs, const int32_t* __restrict__ arc_tid, c
 }
 
 // combined-arc / final accumulators -> per-edge accumulators (integer adds: order independent)
-__global__ void k_arcs_to_edges(int n_arcs, int n_slots, int n_trans, const unsigned long long* __restrict__ acc,
+__global__ void k_arcs_to_edges(int n_arcs, int n_slots, int n_trans, const unsigned long long* __restrict__ acc, int replicas,
                                 const int32_t* __restrict__ arc_tid, const int32_t* __restrict__ arc_eid,
                                 const int32_t* __restrict__ slot_final, unsigned long long* edge_acc)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = 0;
+    if (i < n_arcs + n_slots)
+        for (int r = 0; r < replicas; ++r) v += acc[(size_t)r * (n_arcs + n_slots) + i];
     if (i < n_arcs) {
-        const unsigned long long v = acc[i];
         if (v) {
             atomicAdd(edge_acc + arc_tid[i], v);
             if (arc_eid[i] >= 0) atomicAdd(edge_acc + n_trans + arc_eid[i], v);
         }
     } else if (i < n_arcs + n_slots) {
-        const unsigned long long v = acc[i];
         const int f = slot_final[i - n_arcs];
         if (v && f >= 0) atomicAdd(edge_acc + f, v);
     }

@@ -90,7 +90,8 @@ struct wfsa_dev {
     DevBuf<uint16_t> d_brow16, d_sstate16;
     DevBuf<uint8_t> d_bent8;
     DevBuf<double> d_aw;
-    int tab_smem = 0;
+    int tab_smem = 0, replicas = 1;
+    long long step_bound = 1;
     DevBuf<int32_t> d_emis_row, d_emis_tok_off, d_emis_tok, d_trans_row, d_trans_dst, d_eps_order;
     DevBuf<int32_t> d_trans_tp, d_emis_tp, d_edge_tp, d_edge_raw;
     // per evaluation
@@ -191,7 +192,7 @@ static int choose_launch(wfsa_dev* h)
         h->tab_smem = (tab + min_stack <= max_smem) ? 1 : 0;
         const size_t tab_used = h->tab_smem ? tab : 0;
         int accum = h->opt.accum_mode;
-        const bool fits = h->tab_smem && n_acc * 8 + tab_used + (size_t)warps * 160 * 8 <= max_smem;
+        const bool fits = h->tab_smem && n_acc * 8 + tab_used + (size_t)warps * 128 * 8 <= max_smem;
         if (accum == 0) accum = fits ? 1 : 2;
         if (accum == 1 && !fits) accum = 2;
         h->accum = accum;
@@ -313,7 +314,9 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
         CKB(h->d_brow.upload(L.brow, st)); CKB(h->d_bent.upload(L.bent, st));
         CKB(h->d_slot_emis.upload(L.slot_emis, st)); CKB(h->d_slot_final.upload(L.slot_final, st));
         CKB(h->d_arc_tid.upload(L.arc_tid, st)); CKB(h->d_arc_eid.upload(L.arc_eid, st));
-        CKB(h->d_acc.alloc((size_t)L.n_arcs + L.n_slots));
+        h->replicas = std::max(1, std::min(256, (h->opt.reserved >> 8) & 0xff));
+        if (((h->opt.reserved >> 8) & 0xff) == 0) h->replicas = 16;
+        CKB(h->d_acc.alloc(((size_t)L.n_arcs + L.n_slots) * h->replicas));
         if (L.warp_ok) {
             CKB(h->d_brow16.upload(L.brow16, st)); CKB(h->d_bent8.upload(L.bent_dst, st)); CKB(h->d_sstate16.upload(L.slot_state16, st));
             CKB(h->d_aw.alloc(std::max(L.n_arcs, 1)));
@@ -343,6 +346,7 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
         cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_SMEM_SPLIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_GLOBAL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_GLOBAL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_NONE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     }
@@ -408,6 +412,7 @@ static int launch_pipeline(wfsa_dev* h, int mode, const int32_t* d_order, int64_
                               h->fsa.n_sym, h->fsa.n_states, L.n_arcs, L.n_slots, h->fsa.start, L.start_final_tid};
             P.tw = h->d_tw.p; P.C = C; P.O = O;
             P.stack_cap = h->stack_cap; P.gl_stack = h->d_glstack.p; P.gl_stack_words = h->glstack_words;
+            P.replicas = h->replicas;
             const size_t tab = h->tab_smem ? k2_table_layout(h->fsa.n_sym, h->fsa.n_states, L.n_arcs, L.n_slots).total : 0;
             if (e0) cudaEventRecord(e0, st);
             if (mode == MODE_STRUCT || h->accum != 1) {
@@ -419,13 +424,15 @@ static int launch_pipeline(wfsa_dev* h, int mode, const int32_t* d_order, int64_
                 if (mode == MODE_STRUCT) {
                     if (h->tab_smem) k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL, 1><<<h->grid, h->block, smem, st>>>(P);
                     else k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL, 0><<<h->grid, h->block, smem, st>>>(P);
+                } else if (h->opt.reserved & 2) {
+                    k2_fwdbwd<MODE_EVAL, ACC_NONE, 1><<<h->grid, h->block, smem, st>>>(P);      // timing experiment
                 } else {
                     if (h->tab_smem) k2_fwdbwd<MODE_EVAL, ACC_GLOBAL, 1><<<h->grid, h->block, smem, st>>>(P);
                     else k2_fwdbwd<MODE_EVAL, ACC_GLOBAL, 0><<<h->grid, h->block, smem, st>>>(P);
                 }
             } else {
                 P.n_acc_smem = h->n_acc_smem;
-                if (h->opt.reserved == 1) k2_fwdbwd<MODE_EVAL, ACC_SMEM_CAS, 1><<<h->grid, h->block, h->smem_bytes, st>>>(P);
+                if (h->opt.reserved & 1) k2_fwdbwd<MODE_EVAL, ACC_SMEM_CAS, 1><<<h->grid, h->block, h->smem_bytes, st>>>(P);
                 else k2_fwdbwd<MODE_EVAL, ACC_SMEM_SPLIT, 1><<<h->grid, h->block, h->smem_bytes, st>>>(P);
             }
             h->launches++;
@@ -454,7 +461,7 @@ static int launch_pipeline(wfsa_dev* h, int mode, const int32_t* d_order, int64_
     CK(cudaGetLastError());
     if (h->fast.ok && h->kernel != 3) {
         const int total = h->fast.n_arcs + h->fast.n_slots;
-        k_arcs_to_edges<<<(total + 255) / 256, 256, 0, st>>>(h->fast.n_arcs, h->fast.n_slots, F.n_trans(), h->d_acc.p,
+        k_arcs_to_edges<<<(total + 255) / 256, 256, 0, st>>>(h->fast.n_arcs, h->fast.n_slots, F.n_trans(), h->d_acc.p, h->replicas,
                                                             h->d_arc_tid.p, h->d_arc_eid.p, h->d_slot_final.p, h->d_red.p + 2);
         h->launches++;
         CK(cudaGetLastError());
@@ -544,6 +551,7 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
         CK(cudaMemcpyAsync(&bound, d, 8, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
+    h->step_bound = bound;
     int bits = 1;
     while ((1ll << bits) <= bound && bits < 40) ++bits;
     h->fx_log2 = 62 - bits;
@@ -566,6 +574,14 @@ extern "C" int wfsa_dev_upload_x(wfsa_dev* h, const double* x)
     if (!h || (!x && h->n > 0)) return set_err(h, WFSA_ERR_INVALID, "upload_x: bad arguments");
     if (h->n < 0) return set_err(h, WFSA_ERR_STATE, "upload_x before set_param_map");
     CK(cudaSetDevice(h->device));
+    {   // fixed-point scale of loglik: |sum_s p_s log q_s| <= max steps * (2 max|x| + log(fan-out))
+        double mx = 0.0; bool finite = true;
+        for (int i = 0; i < h->n; ++i) { if (!std::isfinite(x[i])) finite = false; else mx = std::max(mx, std::fabs(x[i])); }
+        double B = (double)h->step_bound * (2.0 * mx + std::log((double)h->n_edges + 2.0)) + 1.0;
+        int bits = 1;
+        while (std::ldexp(1.0, bits) <= B && bits < 40) ++bits;
+        h->ll_log2 = finite ? 62 - bits : 22;
+    }
     if (h->n) {
         std::memcpy(h->h_x, x, (size_t)h->n * 8);
         CK(cudaMemcpyAsync(h->d_x.p, h->h_x, (size_t)h->n * 8, cudaMemcpyHostToDevice, h->stream));
