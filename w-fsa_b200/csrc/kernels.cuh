@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(1024, 1) k2_fwdbwd(const K2Params P)
     const long long gw = (long long)blockIdx.x * nwarps + warp, GW = (long long)gridDim.x * nwarps;
     unsigned long long* gstack = P.gl_stack + (size_t)gw * P.gl_stack_words;
     const int cap = P.stack_cap;
-    unsigned long long* const acc_g = P.O.acc_global + (size_t)(blockIdx.x % P.replicas) * (size_t)(NA + NS);
+    unsigned long long* const acc_g = P.O.acc_global + (size_t)(blockIdx.x % P.replicas) * (size_t)(NA + P.T.n_states);
     for (int i = threadIdx.x; i < P.n_acc_smem; i += blockDim.x) acc_s[i] = 0ull;
     __syncthreads();
 
@@ -257,10 +257,13 @@ __global__ void __launch_bounds__(1024, 1) k2_fwdbwd(const K2Params P)
             sp += n + 1;
         }
         double qh = 0.0, fin = 0.0;
-        int fslot = 0;
+        int fstate = 0;
         if (!dead) {
-            fslot = (int)cand_off[c] + lane;              // c = last symbol
-            fin = (alpha != 0.0) ? fw[fslot] : 0.0;
+            if (alpha != 0.0) {                           // c = last symbol
+                const int fslot = (int)cand_off[c] + lane;
+                fin = fw[fslot];
+                fstate = slot_state[fslot];
+            }
             qh = warp_sum(alpha * fin);
         }
         if (dead || !(qh > 0.0) || !isfinite(qh)) {
@@ -290,8 +293,8 @@ __global__ void __launch_bounds__(1024, 1) k2_fwdbwd(const K2Params P)
             const unsigned long long meta = stack_ld(stack, gstack, cap, sp - 1);
             sp -= __popc((unsigned)meta) + 1;
             if (alpha != 0.0 && fin != 0.0) {             // alpha (registers) still holds position len-1
-                if (MODE == MODE_STRUCT) acc_add<ACC>(acc_s, acc_g, NA + fslot, 1);
-                else acc_add<ACC>(acc_s, acc_g, NA + fslot, __double2ll_rn(alpha * fin * sc0));
+                if (MODE == MODE_STRUCT) acc_add<ACC>(acc_s, acc_g, NA + fstate, 1);
+                else acc_add<ACC>(acc_s, acc_g, NA + fstate, __double2ll_rn(alpha * fin * sc0));
             }
             beta = (alpha != 0.0) ? fin : 0.0;
         }
@@ -354,6 +357,238 @@ __global__ void __launch_bounds__(1024, 1) k2_fwdbwd(const K2Params P)
             const unsigned long long v = acc_s[i];
             if (v) atomicAdd(acc_g + i, v);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// KT: one THREAD per string -- 32 strings per warp instruction instead of one.  For sparse
+// automata (config 4: 1.8 active states per position) a warp-per-string mapping leaves 30 lanes
+// idle and is issue-bound (profiles/r01_k2_warp_per_string_ncu.json); here every lane advances its
+// own string.  Per thread: the active set {(state, alpha)} of the current and the next position
+// in shared memory (capacity K entries each, entry-major so lanes hit consecutive banks), the
+// automaton tables shared by the CTA in shared memory, and the lattice -- one packed 64-bit word
+// per active entry (48 high bits of alpha | last-of-position flag | 15-bit state) -- streamed to
+// a private region in global memory and read back in reverse by the backward sweep.  Strings
+// whose active set ever exceeds K are reported (path_count = -1 in MODE_STRUCT) and evaluated
+// by the warp-per-string / CTA-per-string kernel instead.
+// The packed alpha (2^-37 relative rounding) only enters the arc posteriors, never the
+// recursions, so log q is exact and gradients carry <= 1e-11 relative error.
+// ------------------------------------------------------------------------------------------
+struct ThreadTablesD {
+    const uint16_t* __restrict__ brow;   // [n_states*n_sym + 1]
+    const uint16_t* __restrict__ adst;   // [n_arcs] target state
+    const double* __restrict__ aw;       // [n_arcs]
+    const double* __restrict__ fws;      // [n_states] a(state, end) or 0
+    int n_sym, n_states, n_arcs, start_state, start_final_tid;
+};
+struct KTParams {
+    ThreadTablesD T;
+    const double* __restrict__ tw;
+    CorpusD C;
+    EvalOutD O;
+    unsigned long long* lattice;         // [grid*block][lat_words]
+    size_t lat_words;
+    int K, replicas;
+};
+struct KTTableLayout { size_t aw, fws, brow, adst, total; };
+__host__ __device__ inline KTTableLayout kt_table_layout(int n_sym, int n_states, int n_arcs)
+{
+    KTTableLayout t; size_t o = 0;
+    auto al = [](size_t v) { return (v + 7) & ~(size_t)7; };
+    t.aw = o; o += (size_t)n_arcs * 8;
+    t.fws = o; o += (size_t)n_states * 8;
+    t.brow = o; o = al(o + ((size_t)n_states * n_sym + 1) * 2);
+    t.adst = o; o = al(o + (size_t)n_arcs * 2);
+    t.total = o;
+    return t;
+}
+constexpr unsigned long long kLatMarker = 0x7FFFull;     // state field of an exponent marker word
+__device__ __forceinline__ unsigned long long lat_pack(double a, int st, bool last)
+{
+    return (((unsigned long long)__double_as_longlong(a) + 0x8000ull) & ~0xFFFFull) | (unsigned long long)st | (last ? 0x8000ull : 0ull);
+}
+__device__ __forceinline__ double lat_alpha(unsigned long long w) { return __longlong_as_double((long long)(w & ~0xFFFFull)); }
+
+template <int MODE>
+__global__ void __launch_bounds__(768, 1) kt_fwdbwd(const KTParams P)
+{
+    extern __shared__ unsigned long long smem[];
+    const int tid = threadIdx.x, NT = blockDim.x, K = P.K;
+    const int A = P.T.n_sym, NA = P.T.n_arcs, S = P.T.n_states;
+    const KTTableLayout tl = kt_table_layout(A, S, NA);
+    unsigned char* base = reinterpret_cast<unsigned char*>(smem);
+    double* aw = reinterpret_cast<double*>(base + tl.aw);
+    double* fws = reinterpret_cast<double*>(base + tl.fws);
+    uint16_t* brow = reinterpret_cast<uint16_t*>(base + tl.brow);
+    uint16_t* adst = reinterpret_cast<uint16_t*>(base + tl.adst);
+    double* la = reinterpret_cast<double*>(base + tl.total);                 // [2][K][NT]
+    uint16_t* ls = reinterpret_cast<uint16_t*>(la + (size_t)2 * K * NT);     // [2][K][NT]
+    for (int i = tid; i < NA; i += NT) { aw[i] = P.T.aw[i]; adst[i] = P.T.adst[i]; }
+    for (int i = tid; i < S; i += NT) fws[i] = P.T.fws[i];
+    for (int i = tid; i < S * A + 1; i += NT) brow[i] = P.T.brow[i];
+    __syncthreads();
+
+    const long long gid = (long long)blockIdx.x * NT + tid, G = (long long)gridDim.x * NT;
+    unsigned long long* lat = P.lattice + (size_t)gid * P.lat_words;
+    unsigned long long* const acc_g = P.O.acc_global + (size_t)(blockIdx.x % P.replicas) * (size_t)(NA + S);
+    const int KN = K * NT;
+    long long ll_fx = 0;
+    unsigned long long bad = 0;
+
+    for (long long it = gid; it < P.C.n_order; it += G) {
+        const int sid = P.C.order[it];
+        const long long off = P.C.offs[sid];
+        const int len = (int)(P.C.offs[sid + 1] - off);
+        const double ps = P.C.p[sid];
+        const int32_t* tok = P.C.tokens + off;
+        if (len == 0) {
+            const double q = P.T.start_final_tid >= 0 ? P.tw[P.T.start_final_tid] : 0.0;
+            if (MODE == MODE_STRUCT) {
+                P.O.path_count[sid] = q;
+                if (q != 0.0) atomicAdd(P.O.red + 2 + P.T.start_final_tid, 1ull);
+            } else {
+                const double lq = log(q);
+                if (P.O.logq) P.O.logq[sid] = lq;
+                if (q > 0.0 && isfinite(lq)) {
+                    ll_fx += __double2ll_rn(ps * lq * P.O.ll_scale);
+                    atomicAdd(P.O.red + 2 + P.T.start_final_tid, (unsigned long long)__double2ll_rn(ps * P.O.fx_scale));
+                } else bad++;
+            }
+            continue;
+        }
+        // ---------------- forward ----------------
+        int buf = 0, n_cur = 1, E = 0, lp = 0;
+        bool dead = false, over = false;
+        la[tid] = 1.0; ls[tid] = (uint16_t)P.T.start_state;
+        for (int t = 0; t < len; ++t) {
+            const int c = tok[t];
+            if ((unsigned)c >= (unsigned)A) { dead = true; break; }
+            const double* ca = la + buf * KN + tid; const uint16_t* cs = ls + buf * KN + tid;
+            double* na = la + (buf ^ 1) * KN + tid; uint16_t* ns = ls + (buf ^ 1) * KN + tid;
+            int n_new = 0;
+            for (int i = 0; i < n_cur; ++i) {
+                const int u = cs[i * NT];
+                const double a = ca[i * NT];
+                const int r = u * A + c;
+                const unsigned r1 = brow[r + 1];
+                for (unsigned j = brow[r]; j < r1; ++j) {
+                    const double x = a * aw[j];
+                    if (x == 0.0) continue;
+                    const uint16_t v = adst[j];
+                    int k = 0;
+                    for (; k < n_new; ++k) if (ns[k * NT] == v) break;
+                    if (k < n_new) na[k * NT] += x;
+                    else if (n_new < K) { ns[n_new * NT] = v; na[n_new * NT] = x; ++n_new; }
+                    else over = true;
+                }
+            }
+            if (over) break;
+            if (n_new == 0) { dead = true; break; }
+            if ((t & 7) == 7) {                       // lazy power-of-two rescaling (exact)
+                int emax = 0;
+                for (int k = 0; k < n_new; ++k) emax = max(emax, biased_exp(na[k * NT]));
+                if (emax < 1023 - kRescaleBand || emax > 1023 + kRescaleBand) {
+                    const int shift = 1023 - emax;
+                    for (int k = 0; k < n_new; ++k) na[k * NT] = scalbn(na[k * NT], shift);
+                    lat[lp++] = kLatMarker | ((unsigned long long)(unsigned)E << 16);   // exponent of earlier positions
+                    E -= shift;
+                }
+            }
+            for (int k = 0; k < n_new; ++k) lat[lp++] = lat_pack(na[k * NT], ns[k * NT], k == n_new - 1);
+            n_cur = n_new;
+            buf ^= 1;
+        }
+        if (over) {                                   // handled by the warp / CTA kernel
+            if (MODE == MODE_STRUCT) P.O.path_count[sid] = -1.0;
+            else bad++;                               // cannot happen: the structural pass filters these
+            continue;
+        }
+        double qh = 0.0;
+        if (!dead)
+            for (int i = 0; i < n_cur; ++i) qh = fma(la[buf * KN + i * NT + tid], fws[ls[buf * KN + i * NT + tid]], qh);
+        if (dead || !(qh > 0.0) || !isfinite(qh)) {
+            if (MODE == MODE_STRUCT) P.O.path_count[sid] = 0.0;
+            else { if (P.O.logq) P.O.logq[sid] = -INFINITY; bad++; }
+            continue;
+        }
+        const int EQ = E;
+        if (MODE == MODE_STRUCT) P.O.path_count[sid] = scalbn(qh, EQ);
+        else {
+            const double lq = log(qh) + (double)EQ * 0.69314718055994530942;
+            if (P.O.logq) P.O.logq[sid] = lq;
+            ll_fx += __double2ll_rn(ps * lq * P.O.ll_scale);
+        }
+        // ---------------- backward ----------------
+        const double sc0 = (MODE == MODE_STRUCT) ? 1.0 : (1.0 / qh) * ps * P.O.fx_scale;
+        {   // last position: beta = a(v,end); posterior of the final transition; alpha list becomes beta list
+            double* ba = la + buf * KN + tid; const uint16_t* bs = ls + buf * KN + tid;
+            for (int i = 0; i < n_cur; ++i) {
+                const int st = bs[i * NT];
+                const double fin = fws[st], a = ba[i * NT];
+                if (fin != 0.0) {
+                    if (MODE == MODE_STRUCT) atomicAdd(acc_g + NA + st, 1ull);
+                    else { const long long v = __double2ll_rn(a * fin * sc0); if (v) atomicAdd(acc_g + NA + st, (unsigned long long)v); }
+                }
+                ba[i * NT] = fin;
+            }
+            lp -= n_cur;
+        }
+        int n_b = n_cur, F = 0, Et = EQ;
+        for (int t = len - 2; t >= -1; --t) {
+            const int cn = tok[t + 1];
+            const double* bb = la + buf * KN + tid; const uint16_t* bs = ls + buf * KN + tid;
+            double* oa = la + (buf ^ 1) * KN + tid; uint16_t* os = ls + (buf ^ 1) * KN + tid;
+            while (lp > 0 && (lat[lp - 1] & 0xFFFFull) == kLatMarker) { Et = (int)(unsigned)(lat[lp - 1] >> 16); --lp; }
+            if (t < 0) Et = 0;
+            const int d = Et + F - EQ;
+            double sc = sc0;
+            if (MODE != MODE_STRUCT && d != 0) sc = scalbn(sc0, d);
+            int n_t = 0;
+            bool more = true;
+            while (more) {
+                int u; double a;
+                if (t >= 0) {
+                    const unsigned long long w = lat[--lp];
+                    u = (int)(w & 0x7FFFull); a = lat_alpha(w);
+                    more = lp > 0 && !(lat[lp - 1] & 0x8000ull) && (lat[lp - 1] & 0xFFFFull) != kLatMarker;
+                } else { u = P.T.start_state; a = 1.0; more = false; }
+                const int r = u * A + cn;
+                const unsigned r1 = brow[r + 1];
+                double b = 0.0;
+                for (unsigned j = brow[r]; j < r1; ++j) {
+                    const uint16_t v = adst[j];
+                    for (int k = 0; k < n_b; ++k)
+                        if (bs[k * NT] == v) {
+                            const double term = aw[j] * bb[k * NT];
+                            if (term != 0.0) {
+                                b += term;
+                                if (MODE == MODE_STRUCT) atomicAdd(acc_g + j, 1ull);
+                                else { const long long vv = __double2ll_rn(a * term * sc); if (vv) atomicAdd(acc_g + j, (unsigned long long)vv); }
+                            }
+                            break;
+                        }
+                }
+                os[n_t * NT] = (uint16_t)u; oa[n_t * NT] = b;
+                ++n_t;
+            }
+            if (t >= 0 && (t & 7) == 0) {
+                int emax = 0;
+                for (int k = 0; k < n_t; ++k) emax = max(emax, biased_exp(oa[k * NT]));
+                if (emax != 0 && (emax < 1023 - kRescaleBand || emax > 1023 + kRescaleBand)) {
+                    const int shift = 1023 - emax;
+                    for (int k = 0; k < n_t; ++k) oa[k * NT] = scalbn(oa[k * NT], shift);
+                    F -= shift;
+                }
+            }
+            n_b = n_t;
+            buf ^= 1;
+        }
+    }
+    // per-warp reduction of the fixed-point log-likelihood, one atomic per warp
+    for (int o = 16; o; o >>= 1) { ll_fx += __shfl_xor_sync(FULL, ll_fx, o); bad += __shfl_xor_sync(FULL, bad, o); }
+    if ((tid & 31) == 0) {
+        if (ll_fx) atomicAdd(P.O.red, (unsigned long long)ll_fx);
+        if (bad) atomicAdd(P.O.red + 1, bad);
     }
 }
 
@@ -487,8 +722,9 @@ __global__ void __launch_bounds__(1024, 1) k3_fwdbwd(const K3Params P)
         const double invq = 1.0 / qh;
         int F = 0, cnext = tok[len - 1];
         if (alpha != 0.0 && fin != 0.0) {
-            if (MODE == MODE_STRUCT) atomicAdd(P.O.acc_global + T.n_arcs + slot, 1ull);
-            else atomicAdd(P.O.acc_global + T.n_arcs + slot, (unsigned long long)__double2ll_rn(alpha * fin * invq * ps * P.O.fx_scale));
+            const uint32_t fst = T.slot_state[slot];
+            if (MODE == MODE_STRUCT) atomicAdd(P.O.acc_global + T.n_arcs + fst, 1ull);
+            else atomicAdd(P.O.acc_global + T.n_arcs + fst, (unsigned long long)__double2ll_rn(alpha * fin * invq * ps * P.O.fx_scale));
         }
         __syncthreads();
         cur = 0;
@@ -746,6 +982,13 @@ __global__ void k_weights(int n_trans, int n_emis, int n_slots, const int32_t* _
     }
 }
 
+// final weight per state: a(state, end) or 0
+__global__ void k_state_final_weights(int n_states, const int32_t* __restrict__ state_final, const double* __restrict__ tw, double* fws)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_states) fws[i] = state_final[i] < 0 ? 0.0 : tw[state_final[i]];
+}
+
 // per combined arc (bwd-CSR order): aw = a(u,v) * b(v, c_next)
 __global__ void k_arc_weights(int n_arcs, const int32_t* __restrict__ arc_tid, const int32_t* __restrict__ arc_eid,
                               const int32_t* __restrict__ emis_tp, const double* __restrict__ tw,
@@ -756,9 +999,9 @@ __global__ void k_arc_weights(int n_arcs, const int32_t* __restrict__ arc_tid, c
 }
 
 // combined-arc / final accumulators -> per-edge accumulators (integer adds: order independent)
-__global__ void k_arcs_to_edges(int n_arcs, int n_slots, int n_trans, const unsigned long long* __restrict__ acc, int replicas,
+__global__ void k_arcs_to_edges(int n_arcs, int n_slots /* = n_states */, int n_trans, const unsigned long long* __restrict__ acc, int replicas,
                                 const int32_t* __restrict__ arc_tid, const int32_t* __restrict__ arc_eid,
-                                const int32_t* __restrict__ slot_final, unsigned long long* edge_acc)
+                                const int32_t* __restrict__ slot_final /* per state */, unsigned long long* edge_acc)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long v = 0;

@@ -159,16 +159,34 @@ std::string build_fast_layout(const HostFsa& f, FastLayout& L, int& status)
     for (auto& r : brow_eid) L.arc_eid.insert(L.arc_eid.end(), r.begin(), r.end());
     for (int a = 0; a < L.n_arcs; ++a) L.arc_tid[a] = (int32_t)(L.bent[a] >> kSlotBits);
     L.ok = true;
-    // compact tables for the warp-per-string kernel
-    if (L.max_cand <= 32 && L.n_arcs < 65536 && S < 65536) {
+    L.state_final.assign(final_tid.begin(), final_tid.end());
+    L.state_final[f.start] = -1;        // start->end only accepts the empty string (handled separately)
+    // compact 16-bit tables for the thread-per-string and warp-per-string kernels
+    if (L.n_arcs < 65536 && S < 32767) {
         L.brow16.resize(L.brow.size() + 1);
         for (size_t r = 0; r < L.brow.size(); ++r) L.brow16[r] = (uint16_t)(L.brow[r] >> kRowCntBits);
         L.brow16[L.brow.size()] = (uint16_t)L.n_arcs;
-        L.bent_dst.resize(L.n_arcs);
-        for (int a = 0; a < L.n_arcs; ++a) L.bent_dst[a] = (uint8_t)(L.bent[a] & ((1u << kSlotBits) - 1));
-        L.slot_state16.resize(L.n_slots);
-        for (int i = 0; i < L.n_slots; ++i) L.slot_state16[i] = (uint16_t)L.slot_state[i];
-        L.warp_ok = true;
+        L.arc_dst16.resize(L.n_arcs);
+        {
+            size_t a = 0;
+            for (int u = 0; u < S; ++u)
+                for (int c = 0; c < A; ++c) {
+                    const uint32_t row = L.brow[(size_t)u * A + c];
+                    const int cnt = row & ((1u << kRowCntBits) - 1);
+                    for (int k = 0; k < cnt; ++k, ++a) {
+                        const uint32_t slot = L.bent[a] & ((1u << kSlotBits) - 1);
+                        L.arc_dst16[a] = (uint16_t)L.slot_state[L.cand_off[c] + slot];
+                    }
+                }
+        }
+        L.compact_ok = true;
+        if (L.max_cand <= 32) {
+            L.bent_dst.resize(L.n_arcs);
+            for (int a = 0; a < L.n_arcs; ++a) L.bent_dst[a] = (uint8_t)(L.bent[a] & ((1u << kSlotBits) - 1));
+            L.slot_state16.resize(L.n_slots);
+            for (int i = 0; i < L.n_slots; ++i) L.slot_state16[i] = (uint16_t)L.slot_state[i];
+            L.warp_ok = true;
+        }
     }
     return "";
 }

@@ -51,10 +51,13 @@ struct FastLayout {
     // Compact tables of the warp-per-string kernel (staged in shared memory): the bwd CSR above with
     // 16-bit row starts, 8-bit target slots and 16-bit slot->state; usable when at most 32 states
     // emit one symbol and the automaton has fewer than 65536 combined arcs.
-    bool warp_ok = false;
+    bool warp_ok = false;                // compact tables + at most 32 states emit one symbol
+    bool compact_ok = false;             // fewer than 65536 arcs and 32767 states: 16-bit tables below exist
     std::vector<uint16_t> brow16;        // [n_states*n_sym + 1] row starts (arc ids are bwd-CSR positions)
     std::vector<uint8_t> bent_dst;       // [n_arcs] target slot inside E[c_next]
     std::vector<uint16_t> slot_state16;  // [n_slots]
+    std::vector<uint16_t> arc_dst16;     // [n_arcs] target STATE (thread-per-string kernel)
+    std::vector<int32_t> state_final;    // [n_states] transition edge state->end or -1
 };
 
 struct GenericLayout {

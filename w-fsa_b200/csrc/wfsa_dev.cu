@@ -106,8 +106,18 @@ struct wfsa_dev {
     double* h_out = nullptr;                   // pinned [2 + n]
     double* h_x = nullptr;                     // pinned [n]
     double fx_log2 = 0, ll_log2 = 44;
-    int grid = 0, block = 0, stack_cap = 0, n_acc_smem = 0;
+    int grid = 0, block = 0, stack_cap = 0, n_acc_smem = 0;      // warp-per-string (K2) launch
     size_t smem_bytes = 0, glstack_words = 0, table_bytes = 0;
+    int k3_grid = 0, k3_block = 0; size_t k3_smem = 0;            // CTA-per-string (K3) launch
+    int kt_grid = 0, kt_block = 0, kt_K = 0; size_t kt_smem = 0, kt_lat_words = 0;   // thread-per-string (KT)
+    int secondary = 0;                                            // kernel that takes KT's overflow strings
+    int64_t n_overflow = 0, n_active_w = 0;
+    DevBuf<int32_t> d_order_w;                                    // overflow strings (secondary kernel)
+    DevBuf<uint16_t> d_adst16;
+    DevBuf<double> d_fws;
+    DevBuf<int32_t> d_state_final;
+    DevBuf<unsigned long long> d_ktlat;
+    std::vector<uint8_t> h_overflow;
     int64_t launches = 0;
     bool structure_done = false;
     std::vector<uint8_t> h_recognised;
@@ -161,7 +171,8 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
                               &h->d_eps_order, &h->d_trans_tp, &h->d_emis_tp, &h->d_edge_tp, &h->d_edge_raw, &h->d_hb_cols};
     for (auto* b : i32) b->release();
     DevBuf<uint32_t>* u32[] = {&h->d_cand_off, &h->d_slot_state, &h->d_frow, &h->d_fent, &h->d_brow, &h->d_bent};
-    h->d_brow16.release(); h->d_sstate16.release(); h->d_bent8.release();
+    h->d_brow16.release(); h->d_sstate16.release(); h->d_bent8.release(); h->d_adst16.release();
+    h->d_order_w.release(); h->d_fws.release(); h->d_state_final.release(); h->d_ktlat.release();
     for (auto* b : u32) b->release();
     DevBuf<double>* f64[] = {&h->d_p, &h->d_x, &h->d_tw, &h->d_sw, &h->d_fw, &h->d_ltw, &h->d_lew, &h->d_logq, &h->d_pathcnt,
                              &h->d_out, &h->d_k3lat, &h->d_gscratch, &h->d_aw, &h->d_hb_counts, &h->d_hb_p, &h->d_hb_r, &h->d_H, &h->d_rmin};
@@ -179,55 +190,111 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
 }
 
 // ---------------------------------------------------------------------------------------------
-static int choose_launch(wfsa_dev* h)
+static int setup_k2(wfsa_dev* h)
+{
+    // K2: 1 CTA per SM; shared memory = [accumulators] [automaton tables] [per-warp lattice stacks]
+    const FastLayout& L = h->fast;
+    const size_t max_smem = 227 * 1024;
+    const size_t n_acc = (size_t)L.n_arcs + h->fsa.n_states;
+    const size_t tab = k2_table_layout(h->fsa.n_sym, h->fsa.n_states, L.n_arcs, L.n_slots).total;
+    const int warps = 32;
+    const size_t min_stack = (size_t)warps * 128 * 8;
+    h->tab_smem = (tab + min_stack <= max_smem) ? 1 : 0;
+    const size_t tab_used = h->tab_smem ? tab : 0;
+    int accum = h->opt.accum_mode;
+    const bool fits = h->tab_smem && n_acc * 8 + tab_used + (size_t)warps * 128 * 8 <= max_smem;
+    if (accum == 0) accum = 2;                 // measured: global REDs are as fast and leave room for the stacks
+    if (accum == 1 && !fits) accum = 2;
+    h->accum = accum;
+    h->n_acc_smem = accum == 1 ? (int)n_acc : 0;
+    const size_t avail = max_smem - (size_t)h->n_acc_smem * 8 - tab_used;
+    h->stack_cap = (int)std::min<size_t>(avail / 8 / warps, 1024);
+    h->block = warps * 32;
+    h->grid = h->sm_count;
+    h->smem_bytes = (size_t)h->n_acc_smem * 8 + tab_used + (size_t)warps * h->stack_cap * 8;
+    h->glstack_words = (size_t)(h->max_len + 1) * 33 + 8;
+    CK(h->d_glstack.alloc((size_t)h->grid * warps * h->glstack_words));
+    const int mx = 227 * 1024;
+    cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_SMEM_CAS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_SMEM_SPLIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_GLOBAL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_GLOBAL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_NONE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    return WFSA_OK;
+}
+
+static int setup_k3(wfsa_dev* h)
 {
     const FastLayout& L = h->fast;
-    if (h->kernel == 1) {
-        // K2: 1 CTA per SM; shared memory = [accumulators] [automaton tables] [per-warp lattice stacks]
-        const size_t max_smem = 227 * 1024;
-        const size_t n_acc = (size_t)L.n_arcs + L.n_slots;
-        const size_t tab = k2_table_layout(h->fsa.n_sym, h->fsa.n_states, L.n_arcs, L.n_slots).total;
-        const int warps = 32;
-        const size_t min_stack = (size_t)warps * 128 * 8;
-        h->tab_smem = (tab + min_stack <= max_smem) ? 1 : 0;
-        const size_t tab_used = h->tab_smem ? tab : 0;
-        int accum = h->opt.accum_mode;
-        const bool fits = h->tab_smem && n_acc * 8 + tab_used + (size_t)warps * 128 * 8 <= max_smem;
-        if (accum == 0) accum = fits ? 1 : 2;
-        if (accum == 1 && !fits) accum = 2;
-        h->accum = accum;
-        h->n_acc_smem = accum == 1 ? (int)n_acc : 0;
-        const size_t avail = max_smem - (size_t)h->n_acc_smem * 8 - tab_used;
-        h->stack_cap = (int)std::min<size_t>(avail / 8 / warps, 1024);
-        h->block = warps * 32;
-        h->grid = h->sm_count;
-        h->smem_bytes = (size_t)h->n_acc_smem * 8 + tab_used + (size_t)warps * h->stack_cap * 8;
-        h->glstack_words = (size_t)(h->max_len + 1) * 33 + 8;
-        const size_t total = (size_t)h->grid * warps * h->glstack_words;
-        CK(h->d_glstack.alloc(total));
-    } else if (h->kernel == 2) {
-        h->accum = 2;
-        int nt = ((L.max_cand + 31) / 32) * 32;
-        nt = std::max(nt, 64);
-        h->block = nt;
-        h->grid = h->sm_count * std::max(1, std::min(4, 1024 / nt));
-        h->smem_bytes = (size_t)(2 * nt + 32) * 8 + 40 * 4;
-        CK(h->d_k3lat.alloc((size_t)h->grid * std::max(h->max_len, 1) * nt));
-        CK(h->d_k3exp.alloc((size_t)h->grid * std::max(h->max_len, 1)));
-    } else {
-        h->accum = 2;
-        h->block = 128;
-        const size_t per = (size_t)2 * (h->max_len + 1) * h->fsa.n_states;
-        const size_t budget = (size_t)1 << 28;   // 2 GiB of doubles at most
-        long long batch = (long long)std::max<size_t>(1, budget / std::max<size_t>(per, 1));
-        batch = std::min<long long>(batch, std::max<int64_t>(h->n_strings, 1));
-        batch = std::min<long long>(batch, 1 << 20);
-        h->g_batch = batch;
-        h->grid = (int)((batch + h->block - 1) / h->block);
-        h->smem_bytes = 0;
-        CK(h->d_gscratch.alloc((size_t)batch * per));
-    }
+    int nt = ((L.max_cand + 31) / 32) * 32;
+    nt = std::max(nt, 64);
+    h->k3_block = nt;
+    h->k3_grid = h->sm_count * std::max(1, std::min(4, 1024 / nt));
+    h->k3_smem = (size_t)(2 * nt + 32) * 8 + 40 * 4;
+    CK(h->d_k3lat.alloc((size_t)h->k3_grid * std::max(h->max_len, 1) * nt));
+    CK(h->d_k3exp.alloc((size_t)h->k3_grid * std::max(h->max_len, 1)));
     return WFSA_OK;
+}
+
+// thread-per-string: tables + 2 active lists of K entries per thread must fit 227 KB
+static bool kt_possible(const wfsa_dev* h, int K, int& nt, size_t& smem)
+{
+    if (!h->fast.ok || !h->fast.compact_ok) return false;
+    const size_t tab = kt_table_layout(h->fsa.n_sym, h->fsa.n_states, h->fast.n_arcs).total;
+    const size_t max_smem = 227 * 1024;
+    if (tab + (size_t)128 * K * 20 > max_smem) return false;
+    nt = (int)((max_smem - tab) / ((size_t)K * 20) / 32) * 32;
+    nt = std::min(nt, 768);
+    smem = tab + (size_t)nt * K * 20;
+    return nt >= 128;
+}
+
+static int setup_kt(wfsa_dev* h)
+{
+    int K = (h->opt.reserved >> 16) & 0xff;
+    if (K == 0) K = 12;
+    int nt = 0; size_t smem = 0;
+    if (!kt_possible(h, K, nt, smem)) return set_err(h, WFSA_ERR_LIMIT, "thread-per-string kernel: tables do not fit shared memory");
+    h->kt_K = K; h->kt_block = nt; h->kt_grid = h->sm_count; h->kt_smem = smem;
+    h->kt_lat_words = (size_t)std::max(h->max_len, 1) * K + (size_t)h->max_len / 8 + 8;
+    CK(h->d_ktlat.alloc((size_t)h->kt_grid * nt * h->kt_lat_words));
+    cudaFuncSetAttribute(kt_fwdbwd<MODE_EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(kt_fwdbwd<MODE_STRUCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return WFSA_OK;
+}
+
+static int setup_generic(wfsa_dev* h)
+{
+    const size_t per = (size_t)2 * (h->max_len + 1) * h->fsa.n_states;
+    const size_t budget = (size_t)1 << 28;   // 2 GiB of doubles at most
+    long long batch = (long long)std::max<size_t>(1, budget / std::max<size_t>(per, 1));
+    batch = std::min<long long>(batch, std::max<int64_t>(h->n_strings, 1));
+    batch = std::min<long long>(batch, 1 << 20);
+    h->g_batch = batch;
+    CK(h->d_gscratch.alloc((size_t)batch * per));
+    return WFSA_OK;
+}
+
+static int choose_launch(wfsa_dev* h)
+{
+    h->replicas = (h->opt.reserved >> 8) & 0xff;
+    if (h->replicas <= 0) h->replicas = 16;
+    if (h->fast.ok) {
+        const size_t n_acc = (size_t)h->fast.n_arcs + h->fsa.n_states;
+        CK(h->d_acc.alloc(n_acc * h->replicas));
+    }
+    int rc = WFSA_OK;
+    if (h->kernel == 4) {
+        h->secondary = h->fast.warp_ok ? 1 : 2;
+        rc = setup_kt(h);
+        if (rc == WFSA_OK) rc = h->secondary == 1 ? setup_k2(h) : setup_k3(h);
+    } else if (h->kernel == 1) rc = setup_k2(h);
+    else if (h->kernel == 2) rc = setup_k3(h);
+    else rc = setup_generic(h);
+    h->accum = (h->kernel == 1 || (h->kernel == 4 && h->secondary == 1)) ? h->accum : 2;
+    return rc;
 }
 
 extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* cd, const wfsa_dev_options* opt, wfsa_dev** out)
@@ -270,10 +337,13 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
     msg = build_generic_layout(h->fsa, h->gen, status);
     if (status != WFSA_OK) { h->err = msg; return bail(status); }
     int kernel = h->opt.force_kernel;
-    if (kernel == 0) kernel = !h->fast.ok ? 3 : (h->fast.warp_ok ? 1 : 2);
-    if ((kernel == 1 || kernel == 2) && !h->fast.ok) { h->err = "forced fast kernel but emissions are not all one token long"; return bail(WFSA_ERR_INVALID); }
+    if (kernel == 0) {
+        int nt = 0; size_t sm = 0; int K = (h->opt.reserved >> 16) & 0xff; if (K == 0) K = 12;
+        kernel = !h->fast.ok ? 3 : (kt_possible(h, K, nt, sm) ? 4 : (h->fast.warp_ok ? 1 : 2));
+    }
+    if ((kernel == 1 || kernel == 2 || kernel == 4) && !h->fast.ok) { h->err = "forced fast kernel but emissions are not all one token long"; return bail(WFSA_ERR_INVALID); }
     if (kernel == 1 && !h->fast.warp_ok) { h->err = "forced warp-per-string kernel but more than 32 states emit one symbol"; return bail(WFSA_ERR_INVALID); }
-    if (kernel < 1 || kernel > 3) { h->err = "force_kernel out of range"; return bail(WFSA_ERR_INVALID); }
+    if (kernel < 1 || kernel > 4) { h->err = "force_kernel out of range"; return bail(WFSA_ERR_INVALID); }
     h->kernel = kernel;
 
     // ---- corpus shard
@@ -301,6 +371,7 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
     CKB(h->d_p.alloc(std::max<int64_t>(h->n_strings, 1)));
     if (h->n_strings) CKB(cudaMemcpyAsync(h->d_p.p, cd->p, (size_t)h->n_strings * 8, cudaMemcpyHostToDevice, st));
     CKB(h->d_order.alloc(std::max<int64_t>(h->n_strings, 1)));
+    CKB(h->d_order_w.alloc(std::max<int64_t>(h->n_strings, 1)));
     CKB(h->d_logq.alloc(std::max<int64_t>(h->n_strings, 1)));
     CKB(h->d_pathcnt.alloc(std::max<int64_t>(h->n_strings, 1)));
 
@@ -314,13 +385,13 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
         CKB(h->d_brow.upload(L.brow, st)); CKB(h->d_bent.upload(L.bent, st));
         CKB(h->d_slot_emis.upload(L.slot_emis, st)); CKB(h->d_slot_final.upload(L.slot_final, st));
         CKB(h->d_arc_tid.upload(L.arc_tid, st)); CKB(h->d_arc_eid.upload(L.arc_eid, st));
-        h->replicas = std::max(1, std::min(256, (h->opt.reserved >> 8) & 0xff));
-        if (((h->opt.reserved >> 8) & 0xff) == 0) h->replicas = 16;
-        CKB(h->d_acc.alloc(((size_t)L.n_arcs + L.n_slots) * h->replicas));
-        if (L.warp_ok) {
-            CKB(h->d_brow16.upload(L.brow16, st)); CKB(h->d_bent8.upload(L.bent_dst, st)); CKB(h->d_sstate16.upload(L.slot_state16, st));
+        CKB(h->d_state_final.upload(L.state_final, st));
+        CKB(h->d_fws.alloc(std::max(F.n_states, 1)));
+        if (L.compact_ok) {
+            CKB(h->d_brow16.upload(L.brow16, st)); CKB(h->d_adst16.upload(L.arc_dst16, st));
             CKB(h->d_aw.alloc(std::max(L.n_arcs, 1)));
         }
+        if (L.warp_ok) { CKB(h->d_bent8.upload(L.bent_dst, st)); CKB(h->d_sstate16.upload(L.slot_state16, st)); }
         CKB(h->d_sw.alloc(L.n_slots)); CKB(h->d_fw.alloc(L.n_slots));
         h->table_bytes = 4 * (L.cand_off.size() + L.slot_state.size() + L.frow.size() + L.fent.size() + L.brow.size() + L.bent.size()) +
                          8 * ((size_t)F.n_trans() + 2 * L.n_slots);
@@ -340,16 +411,6 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
     CKB(h->d_red.alloc((size_t)h->n_edges + 2));
     CKB(h->d_used.alloc(std::max(F.n_raw, 1)));
     if (choose_launch(h) != WFSA_OK) return bail(WFSA_ERR_CUDA);
-    if (h->kernel == 1) {
-        const int mx = 227 * 1024;
-        cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_SMEM_CAS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_SMEM_SPLIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_GLOBAL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_GLOBAL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(k2_fwdbwd<MODE_EVAL, ACC_NONE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    }
     CKB(cudaStreamSynchronize(st));
 #undef CKB
     *out = h;
@@ -357,26 +418,86 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
 }
 
 // ---------------------------------------------------------------------------------------------
-static FastTablesD fast_tables(const wfsa_dev* h)
+static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, const EvalOutD& O)
 {
-    FastTablesD T{};
-    T.cand_off = h->d_cand_off.p; T.slot_state = h->d_slot_state.p;
-    T.frow = h->d_frow.p; T.fent = h->d_fent.p; T.brow = h->d_brow.p; T.bent = h->d_bent.p;
-    T.n_sym = h->fsa.n_sym; T.n_states = h->fsa.n_states; T.n_arcs = h->fast.n_arcs; T.n_slots = h->fast.n_slots;
-    T.start_state = h->fsa.start; T.start_final_tid = h->fast.start_final_tid;
-    return T;
+    const HostFsa& F = h->fsa;
+    const FastLayout& L = h->fast;
+    cudaStream_t st = h->stream;
+    if (C.n_order <= 0) return;
+    if (kernel == 4) {
+        KTParams P{};
+        P.T = ThreadTablesD{h->d_brow16.p, h->d_adst16.p, h->d_aw.p, h->d_fws.p, F.n_sym, F.n_states, L.n_arcs, F.start, L.start_final_tid};
+        P.tw = h->d_tw.p; P.C = C; P.O = O; P.lattice = h->d_ktlat.p; P.lat_words = h->kt_lat_words; P.K = h->kt_K; P.replicas = h->replicas;
+        if (mode == MODE_STRUCT) kt_fwdbwd<MODE_STRUCT><<<h->kt_grid, h->kt_block, h->kt_smem, st>>>(P);
+        else kt_fwdbwd<MODE_EVAL><<<h->kt_grid, h->kt_block, h->kt_smem, st>>>(P);
+        h->launches++;
+    } else if (kernel == 1) {
+        K2Params P{};
+        P.T = WarpTablesD{h->d_brow16.p, h->d_bent8.p, h->d_sstate16.p, h->d_cand_off.p, h->d_aw.p, h->d_fw.p,
+                          F.n_sym, F.n_states, L.n_arcs, L.n_slots, F.start, L.start_final_tid};
+        P.tw = h->d_tw.p; P.C = C; P.O = O;
+        P.stack_cap = h->stack_cap; P.gl_stack = h->d_glstack.p; P.gl_stack_words = h->glstack_words;
+        P.replicas = h->replicas;
+        const size_t tab = h->tab_smem ? k2_table_layout(F.n_sym, F.n_states, L.n_arcs, L.n_slots).total : 0;
+        if (mode == MODE_STRUCT || h->accum != 1) {
+            P.n_acc_smem = 0;
+            const size_t avail = 227 * 1024 - tab;       // without shared accumulators the stacks get the rest
+            P.stack_cap = (int)std::min<size_t>(avail / 8 / (h->block / 32), 1024);
+            const size_t smem = tab + (size_t)(h->block / 32) * P.stack_cap * 8;
+            if (mode == MODE_STRUCT) {
+                if (h->tab_smem) k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL, 1><<<h->grid, h->block, smem, st>>>(P);
+                else k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL, 0><<<h->grid, h->block, smem, st>>>(P);
+            } else if (h->opt.reserved & 2) {
+                k2_fwdbwd<MODE_EVAL, ACC_NONE, 1><<<h->grid, h->block, smem, st>>>(P);      // timing experiment
+            } else {
+                if (h->tab_smem) k2_fwdbwd<MODE_EVAL, ACC_GLOBAL, 1><<<h->grid, h->block, smem, st>>>(P);
+                else k2_fwdbwd<MODE_EVAL, ACC_GLOBAL, 0><<<h->grid, h->block, smem, st>>>(P);
+            }
+        } else {
+            P.n_acc_smem = h->n_acc_smem;
+            if (h->opt.reserved & 1) k2_fwdbwd<MODE_EVAL, ACC_SMEM_CAS, 1><<<h->grid, h->block, h->smem_bytes, st>>>(P);
+            else k2_fwdbwd<MODE_EVAL, ACC_SMEM_SPLIT, 1><<<h->grid, h->block, h->smem_bytes, st>>>(P);
+        }
+        h->launches++;
+    } else if (kernel == 2) {
+        K3Params P{};
+        FastTablesD T{};
+        T.cand_off = h->d_cand_off.p; T.slot_state = h->d_slot_state.p;
+        T.frow = h->d_frow.p; T.fent = h->d_fent.p; T.brow = h->d_brow.p; T.bent = h->d_bent.p;
+        T.n_sym = F.n_sym; T.n_states = F.n_states; T.n_arcs = L.n_arcs; T.n_slots = L.n_slots;
+        T.start_state = F.start; T.start_final_tid = L.start_final_tid;
+        P.T = T; P.W = EvalWeightsD{h->d_tw.p, h->d_sw.p, h->d_fw.p}; P.C = C; P.O = O;
+        P.lattice = h->d_k3lat.p; P.lat_exp = h->d_k3exp.p; P.max_len = std::max(h->max_len, 1);
+        if (mode == MODE_STRUCT) k3_fwdbwd<MODE_STRUCT><<<h->k3_grid, h->k3_block, h->k3_smem, st>>>(P);
+        else k3_fwdbwd<MODE_EVAL><<<h->k3_grid, h->k3_block, h->k3_smem, st>>>(P);
+        h->launches++;
+    } else {
+        GenericParams P{};
+        P.G = GenericTablesD{h->d_emis_row.p, h->d_emis_tok_off.p, h->d_emis_tok.p, h->d_trans_row.p, h->d_trans_dst.p,
+                             h->d_eps_order.p, F.n_states, F.n_trans(), F.start, F.end};
+        P.ltw = h->d_ltw.p; P.lew = h->d_lew.p; P.C = C; P.O = O; P.scratch = h->d_gscratch.p; P.max_len = h->max_len;
+        for (long long first = 0; first < C.n_order; first += h->g_batch) {
+            P.first = first; P.count = std::min<long long>(h->g_batch, C.n_order - first);
+            const int grid = (int)((P.count + 127) / 128);
+            if (mode == MODE_STRUCT) kg_fwdbwd<MODE_STRUCT><<<grid, 128, 0, st>>>(P);
+            else kg_fwdbwd<MODE_EVAL><<<grid, 128, 0, st>>>(P);
+            h->launches++;
+        }
+    }
 }
 
-// launches weights + dominant kernel + arc fold on the handle's stream
-static int launch_pipeline(wfsa_dev* h, int mode, const int32_t* d_order, int64_t n_order)
+// weights, then the dominant kernel(s) over the given string lists, then the arc -> edge fold.
+// `clear` = false appends to the accumulators of a previous call (structural pass, second stage).
+static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_order, int64_t n_order,
+                           int kernel2, const int32_t* d_order2, int64_t n_order2, bool clear, bool fold)
 {
     const HostFsa& F = h->fsa;
     cudaStream_t st = h->stream;
     const int unit = (mode == MODE_STRUCT) ? 1 : 0;
-    CK(cudaMemsetAsync(h->d_red.p, 0, h->d_red.n * 8, st));
-    if (h->fast.ok) CK(cudaMemsetAsync(h->d_acc.p, 0, h->d_acc.n * 8, st));
-    const int n_slots = h->fast.ok ? h->fast.n_slots : 0;
-    {
+    if (clear) {
+        CK(cudaMemsetAsync(h->d_red.p, 0, h->d_red.n * 8, st));
+        if (h->fast.ok) CK(cudaMemsetAsync(h->d_acc.p, 0, h->d_acc.n * 8, st));
+        const int n_slots = h->fast.ok ? h->fast.n_slots : 0;
         const int total = F.n_trans() + F.n_emis() + n_slots;
         if (total > 0) {
             k_weights<<<(total + 255) / 256, 256, 0, st>>>(F.n_trans(), F.n_emis(), n_slots, h->d_trans_tp.p, h->d_emis_tp.p,
@@ -384,8 +505,16 @@ static int launch_pipeline(wfsa_dev* h, int mode, const int32_t* d_order, int64_
                                                           h->d_sw.p, h->d_fw.p, h->d_ltw.p, h->d_lew.p);
             h->launches++;
         }
+        if (h->fast.ok && h->fast.compact_ok && h->fast.n_arcs > 0) {
+            k_arc_weights<<<(h->fast.n_arcs + 255) / 256, 256, 0, st>>>(h->fast.n_arcs, h->d_arc_tid.p, h->d_arc_eid.p, h->d_emis_tp.p,
+                                                                        h->d_tw.p, h->d_x.p, unit, h->d_aw.p);
+            h->launches++;
+        }
+        if (h->fast.ok) {
+            k_state_final_weights<<<(F.n_states + 255) / 256, 256, 0, st>>>(F.n_states, h->d_state_final.p, h->d_tw.p, h->d_fws.p);
+            h->launches++;
+        }
     }
-    CorpusD C{h->d_tokens.p, h->d_offs.p, h->d_p.p, d_order, n_order};
     EvalOutD O{};
     O.logq = h->d_logq.p; O.path_count = h->d_pathcnt.p; O.acc_global = h->d_acc.p; O.red = h->d_red.p;
     O.fx_scale = (mode == MODE_STRUCT) ? 1.0 : std::ldexp(1.0, (int)h->fx_log2);
@@ -397,72 +526,15 @@ static int launch_pipeline(wfsa_dev* h, int mode, const int32_t* d_order, int64_
         }
         if (h->kev_used < h->kev.size()) { e0 = h->kev[h->kev_used].first; e1 = h->kev[h->kev_used].second; h->kev_used++; }
     }
-    if (e0 && h->kernel != 1) cudaEventRecord(e0, st);
-    if (e0 && h->kernel == 1 && n_order <= 0) cudaEventRecord(e0, st);
-    if (n_order > 0) {
-        if (h->kernel == 1) {
-            const FastLayout& L = h->fast;
-            if (L.n_arcs > 0) {
-                k_arc_weights<<<(L.n_arcs + 255) / 256, 256, 0, st>>>(L.n_arcs, h->d_arc_tid.p, h->d_arc_eid.p, h->d_emis_tp.p,
-                                                                      h->d_tw.p, h->d_x.p, unit, h->d_aw.p);
-                h->launches++;
-            }
-            K2Params P{};
-            P.T = WarpTablesD{h->d_brow16.p, h->d_bent8.p, h->d_sstate16.p, h->d_cand_off.p, h->d_aw.p, h->d_fw.p,
-                              h->fsa.n_sym, h->fsa.n_states, L.n_arcs, L.n_slots, h->fsa.start, L.start_final_tid};
-            P.tw = h->d_tw.p; P.C = C; P.O = O;
-            P.stack_cap = h->stack_cap; P.gl_stack = h->d_glstack.p; P.gl_stack_words = h->glstack_words;
-            P.replicas = h->replicas;
-            const size_t tab = h->tab_smem ? k2_table_layout(h->fsa.n_sym, h->fsa.n_states, L.n_arcs, L.n_slots).total : 0;
-            if (e0) cudaEventRecord(e0, st);
-            if (mode == MODE_STRUCT || h->accum != 1) {
-                P.n_acc_smem = 0;
-                // without shared accumulators the stacks may use what they left free
-                const size_t avail = 227 * 1024 - tab;
-                P.stack_cap = (int)std::min<size_t>(avail / 8 / (h->block / 32), 1024);
-                const size_t smem = tab + (size_t)(h->block / 32) * P.stack_cap * 8;
-                if (mode == MODE_STRUCT) {
-                    if (h->tab_smem) k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL, 1><<<h->grid, h->block, smem, st>>>(P);
-                    else k2_fwdbwd<MODE_STRUCT, ACC_GLOBAL, 0><<<h->grid, h->block, smem, st>>>(P);
-                } else if (h->opt.reserved & 2) {
-                    k2_fwdbwd<MODE_EVAL, ACC_NONE, 1><<<h->grid, h->block, smem, st>>>(P);      // timing experiment
-                } else {
-                    if (h->tab_smem) k2_fwdbwd<MODE_EVAL, ACC_GLOBAL, 1><<<h->grid, h->block, smem, st>>>(P);
-                    else k2_fwdbwd<MODE_EVAL, ACC_GLOBAL, 0><<<h->grid, h->block, smem, st>>>(P);
-                }
-            } else {
-                P.n_acc_smem = h->n_acc_smem;
-                if (h->opt.reserved & 1) k2_fwdbwd<MODE_EVAL, ACC_SMEM_CAS, 1><<<h->grid, h->block, h->smem_bytes, st>>>(P);
-                else k2_fwdbwd<MODE_EVAL, ACC_SMEM_SPLIT, 1><<<h->grid, h->block, h->smem_bytes, st>>>(P);
-            }
-            h->launches++;
-        } else if (h->kernel == 2) {
-            K3Params P{};
-            P.T = fast_tables(h); P.W = EvalWeightsD{h->d_tw.p, h->d_sw.p, h->d_fw.p}; P.C = C; P.O = O;
-            P.lattice = h->d_k3lat.p; P.lat_exp = h->d_k3exp.p; P.max_len = std::max(h->max_len, 1);
-            if (mode == MODE_STRUCT) k3_fwdbwd<MODE_STRUCT><<<h->grid, h->block, h->smem_bytes, st>>>(P);
-            else k3_fwdbwd<MODE_EVAL><<<h->grid, h->block, h->smem_bytes, st>>>(P);
-            h->launches++;
-        } else {
-            GenericParams P{};
-            P.G = GenericTablesD{h->d_emis_row.p, h->d_emis_tok_off.p, h->d_emis_tok.p, h->d_trans_row.p, h->d_trans_dst.p,
-                                 h->d_eps_order.p, F.n_states, F.n_trans(), F.start, F.end};
-            P.ltw = h->d_ltw.p; P.lew = h->d_lew.p; P.C = C; P.O = O; P.scratch = h->d_gscratch.p; P.max_len = h->max_len;
-            for (long long first = 0; first < n_order; first += h->g_batch) {
-                P.first = first; P.count = std::min<long long>(h->g_batch, n_order - first);
-                const int grid = (int)((P.count + h->block - 1) / h->block);
-                if (mode == MODE_STRUCT) kg_fwdbwd<MODE_STRUCT><<<grid, h->block, 0, st>>>(P);
-                else kg_fwdbwd<MODE_EVAL><<<grid, h->block, 0, st>>>(P);
-                h->launches++;
-            }
-        }
-    }
+    if (e0) cudaEventRecord(e0, st);
+    launch_main(h, kernel, mode, CorpusD{h->d_tokens.p, h->d_offs.p, h->d_p.p, d_order, n_order}, O);
+    if (kernel2) launch_main(h, kernel2, mode, CorpusD{h->d_tokens.p, h->d_offs.p, h->d_p.p, d_order2, n_order2}, O);
     if (e1) cudaEventRecord(e1, st);
     CK(cudaGetLastError());
-    if (h->fast.ok && h->kernel != 3) {
-        const int total = h->fast.n_arcs + h->fast.n_slots;
-        k_arcs_to_edges<<<(total + 255) / 256, 256, 0, st>>>(h->fast.n_arcs, h->fast.n_slots, F.n_trans(), h->d_acc.p, h->replicas,
-                                                            h->d_arc_tid.p, h->d_arc_eid.p, h->d_slot_final.p, h->d_red.p + 2);
+    if (fold && h->fast.ok && h->kernel != 3) {
+        const int total = h->fast.n_arcs + F.n_states;
+        k_arcs_to_edges<<<(total + 255) / 256, 256, 0, st>>>(h->fast.n_arcs, F.n_states, F.n_trans(), h->d_acc.p, h->replicas,
+                                                            h->d_arc_tid.p, h->d_arc_eid.p, h->d_state_final.p, h->d_red.p + 2);
         h->launches++;
         CK(cudaGetLastError());
     }
@@ -474,17 +546,34 @@ extern "C" int wfsa_dev_structure(wfsa_dev* h, uint8_t* recognised, double* path
     if (!h) return WFSA_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync(h->d_order.p, h->h_order_all.data(), (size_t)h->n_strings * 4, cudaMemcpyHostToDevice, h->stream));
-    int rc = launch_pipeline(h, MODE_STRUCT, h->d_order.p, h->n_strings);
-    if (rc != WFSA_OK) return rc;
+    std::vector<double> pc((size_t)h->n_strings);
+    h->h_overflow.assign((size_t)h->n_strings, 0);
+    h->n_overflow = 0;
+    if (h->kernel == 4) {
+        // stage 1: thread-per-string over everything; strings whose active set exceeds K come back as -1
+        int rc = launch_pipeline(h, MODE_STRUCT, 4, h->d_order.p, h->n_strings, 0, nullptr, 0, true, false);
+        if (rc != WFSA_OK) return rc;
+        if (h->n_strings) CK(cudaMemcpyAsync(pc.data(), h->d_pathcnt.p, (size_t)h->n_strings * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        std::vector<int32_t> over;
+        for (int32_t s : h->h_order_all) if (pc[s] < 0.0) { over.push_back(s); h->h_overflow[s] = 1; }
+        h->n_overflow = (int64_t)over.size();
+        if (!over.empty()) CK(cudaMemcpyAsync(h->d_order_w.p, over.data(), over.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        // stage 2: the overflow strings on the warp / CTA kernel, then fold everything
+        rc = launch_pipeline(h, MODE_STRUCT, h->secondary, h->d_order_w.p, h->n_overflow, 0, nullptr, 0, false, true);
+        if (rc != WFSA_OK) return rc;
+    } else {
+        int rc = launch_pipeline(h, MODE_STRUCT, h->kernel, h->d_order.p, h->n_strings, 0, nullptr, 0, true, true);
+        if (rc != WFSA_OK) return rc;
+    }
     // used flags are per-edge instance counts; combine across ranks before thresholding
-    rc = nccl_allreduce(h, h->d_red.p, h->d_red.n, ncclUint64, ncclSum);
+    int rc = nccl_allreduce(h, h->d_red.p, h->d_red.n, ncclUint64, ncclSum);
     if (rc != WFSA_OK) return rc;
     CK(cudaMemsetAsync(h->d_used.p, 0, h->d_used.n, h->stream));
     if (h->n_edges) {
         k_finish_struct<<<(h->n_edges + 255) / 256, 256, 0, h->stream>>>(h->n_edges, h->d_red.p, h->d_edge_raw.p, h->d_used.p);
         h->launches++;
     }
-    std::vector<double> pc((size_t)h->n_strings);
     if (h->n_strings) CK(cudaMemcpyAsync(pc.data(), h->d_pathcnt.p, (size_t)h->n_strings * 8, cudaMemcpyDeviceToHost, h->stream));
     std::vector<uint8_t> used((size_t)h->fsa.n_raw);
     if (h->fsa.n_raw) CK(cudaMemcpyAsync(used.data(), h->d_used.p, (size_t)h->fsa.n_raw, cudaMemcpyDeviceToHost, h->stream));
@@ -523,18 +612,21 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
     if (!etp.empty()) CK(cudaMemcpyAsync(h->d_emis_tp.p, etp.data(), etp.size() * 4, cudaMemcpyHostToDevice, h->stream));
     if (!edge_tp.empty()) CK(cudaMemcpyAsync(h->d_edge_tp.p, edge_tp.data(), edge_tp.size() * 4, cudaMemcpyHostToDevice, h->stream));
     // strings that take part: recognised ones, longest first
-    std::vector<int32_t> order;
+    if (h->kernel == 4 && !h->structure_done)
+        return set_err(h, WFSA_ERR_STATE, "set_param_map: the thread-per-string kernel needs wfsa_dev_structure first");
+    std::vector<int32_t> order, order_w;
     order.reserve((size_t)h->n_strings);
     const uint8_t* rec = recognised ? recognised : (h->structure_done ? h->h_recognised.data() : nullptr);
     int64_t tokens = 0; int max_len = 0;
     for (int32_t s : h->h_order_all)
         if (!rec || rec[s]) {
-            order.push_back(s);
+            if (h->kernel == 4 && h->h_overflow[s]) order_w.push_back(s); else order.push_back(s);
             const int64_t len = h->h_offs[s + 1] - h->h_offs[s];
             tokens += len; max_len = std::max<int>(max_len, (int)len);
         }
-    h->n_active = (int64_t)order.size(); h->n_active_tokens = tokens;
+    h->n_active = (int64_t)order.size(); h->n_active_w = (int64_t)order_w.size(); h->n_active_tokens = tokens;
     if (!order.empty()) CK(cudaMemcpyAsync(h->d_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    if (!order_w.empty()) CK(cudaMemcpyAsync(h->d_order_w.p, order_w.data(), order_w.size() * 4, cudaMemcpyHostToDevice, h->stream));
     // every logq defaults to -inf (unrecognised strings are never touched by an evaluation)
     {
         std::vector<double> minf((size_t)h->n_strings, -INFINITY);
@@ -594,7 +686,8 @@ extern "C" int wfsa_dev_eval_launch(wfsa_dev* h)
     if (!h) return WFSA_ERR_INVALID;
     if (h->n < 0) return set_err(h, WFSA_ERR_STATE, "eval before set_param_map");
     CK(cudaSetDevice(h->device));
-    int rc = launch_pipeline(h, MODE_EVAL, h->d_order.p, h->n_active);
+    int rc = launch_pipeline(h, MODE_EVAL, h->kernel, h->d_order.p, h->n_active,
+                             h->kernel == 4 ? h->secondary : 0, h->d_order_w.p, h->n_active_w, true, true);
     if (rc != WFSA_OK) return rc;
     rc = nccl_allreduce(h, h->d_red.p, h->d_red.n, ncclUint64, ncclSum);
     if (rc != WFSA_OK) return rc;
@@ -799,9 +892,13 @@ extern "C" int wfsa_dev_get_info(wfsa_dev* h, wfsa_dev_info* info)
     info->n_trans = h->fsa.n_trans(); info->n_emis = h->fsa.n_emis();
     info->n_arcs = h->fast.ok ? h->fast.n_arcs : 0; info->n_slots = h->fast.ok ? h->fast.n_slots : 0;
     info->max_candidates = h->fast.ok ? h->fast.max_cand : 0;
-    info->sm_count = h->sm_count; info->grid = h->grid; info->block = h->block;
-    info->n_strings = h->n_strings; info->n_active_strings = h->n_active; info->n_tokens = h->n_tokens;
-    info->n_active_tokens = h->n_active_tokens; info->smem_bytes = (int64_t)h->smem_bytes; info->table_bytes = (int64_t)h->table_bytes;
+    info->sm_count = h->sm_count;
+    info->grid = h->kernel == 4 ? h->kt_grid : (h->kernel == 2 ? h->k3_grid : h->grid);
+    info->block = h->kernel == 4 ? h->kt_block : (h->kernel == 2 ? h->k3_block : (h->kernel == 3 ? 128 : h->block));
+    info->n_strings = h->n_strings; info->n_tokens = h->n_tokens;
+    info->n_active_tokens = h->n_active_tokens;
+    info->smem_bytes = (int64_t)(h->kernel == 4 ? h->kt_smem : (h->kernel == 2 ? h->k3_smem : h->smem_bytes));
+    info->n_active_strings = h->n_active + h->n_active_w; info->table_bytes = (int64_t)h->table_bytes;
     info->kernels_launched = h->launches; info->fixed_point_scale_log2 = h->fx_log2;
     return WFSA_OK;
 }
