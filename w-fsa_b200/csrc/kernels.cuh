@@ -384,11 +384,14 @@ struct ThreadTablesD {
 struct KTParams {
     ThreadTablesD T;
     const double* __restrict__ tw;
-    CorpusD C;
+    CorpusD C;                           // C.order = strings of this kernel, longest first; 32 consecutive = one warp group
     EvalOutD O;
-    unsigned long long* lattice;         // [grid*block][lat_words]
-    size_t lat_words;
-    int K, replicas;
+    const int32_t* __restrict__ tokT;    // tokens of group g, position t, lane l at goff[g] + t*32 + l (coalesced)
+    const int64_t* __restrict__ goff;    // [n_groups]
+    long long n_groups;
+    unsigned long long* lattice;         // per warp: [max_len][K][32] packed (alpha | flag | state) words
+    uint32_t* latcnt;                    // per warp: [max_len][32]   entries | exponent << 8
+    int max_len, K, replicas;
 };
 struct KTTableLayout { size_t aw, fws, brow, adst, total; };
 __host__ __device__ inline KTTableLayout kt_table_layout(int n_sym, int n_states, int n_arcs)
@@ -402,10 +405,9 @@ __host__ __device__ inline KTTableLayout kt_table_layout(int n_sym, int n_states
     t.total = o;
     return t;
 }
-constexpr unsigned long long kLatMarker = 0x7FFFull;     // state field of an exponent marker word
-__device__ __forceinline__ unsigned long long lat_pack(double a, int st, bool last)
+__device__ __forceinline__ unsigned long long lat_pack(double a, int st)
 {
-    return (((unsigned long long)__double_as_longlong(a) + 0x8000ull) & ~0xFFFFull) | (unsigned long long)st | (last ? 0x8000ull : 0ull);
+    return (((unsigned long long)__double_as_longlong(a) + 0x8000ull) & ~0xFFFFull) | (unsigned long long)st;
 }
 __device__ __forceinline__ double lat_alpha(unsigned long long w) { return __longlong_as_double((long long)(w & ~0xFFFFull)); }
 
@@ -413,7 +415,7 @@ template <int MODE>
 __global__ void __launch_bounds__(768, 1) kt_fwdbwd(const KTParams P)
 {
     extern __shared__ unsigned long long smem[];
-    const int tid = threadIdx.x, NT = blockDim.x, K = P.K;
+    const int tid = threadIdx.x, NT = blockDim.x, K = P.K, lane = tid & 31;
     const int A = P.T.n_sym, NA = P.T.n_arcs, S = P.T.n_states;
     const KTTableLayout tl = kt_table_layout(A, S, NA);
     unsigned char* base = reinterpret_cast<unsigned char*>(smem);
@@ -428,19 +430,21 @@ __global__ void __launch_bounds__(768, 1) kt_fwdbwd(const KTParams P)
     for (int i = tid; i < S * A + 1; i += NT) brow[i] = P.T.brow[i];
     __syncthreads();
 
-    const long long gid = (long long)blockIdx.x * NT + tid, G = (long long)gridDim.x * NT;
-    unsigned long long* lat = P.lattice + (size_t)gid * P.lat_words;
+    const long long gwarp = ((long long)blockIdx.x * NT + tid) >> 5, GW = ((long long)gridDim.x * NT) >> 5;
+    unsigned long long* const lat = P.lattice + (size_t)gwarp * P.max_len * K * 32 + lane;
+    uint32_t* const cw = P.latcnt + (size_t)gwarp * P.max_len * 32 + lane;
     unsigned long long* const acc_g = P.O.acc_global + (size_t)(blockIdx.x % P.replicas) * (size_t)(NA + S);
-    const int KN = K * NT;
+    const int KN = K * NT, K32 = K * 32;
     long long ll_fx = 0;
     unsigned long long bad = 0;
 
-    for (long long it = gid; it < P.C.n_order; it += G) {
+    for (long long g = gwarp; g < P.n_groups; g += GW) {
+        const long long it = g * 32 + lane;
+        if (it >= P.C.n_order) continue;
         const int sid = P.C.order[it];
-        const long long off = P.C.offs[sid];
-        const int len = (int)(P.C.offs[sid + 1] - off);
+        const int len = (int)(P.C.offs[sid + 1] - P.C.offs[sid]);
         const double ps = P.C.p[sid];
-        const int32_t* tok = P.C.tokens + off;
+        const int32_t* tok = P.tokT + P.goff[g] + lane;        // token t at tok[t*32]
         if (len == 0) {
             const double q = P.T.start_final_tid >= 0 ? P.tw[P.T.start_final_tid] : 0.0;
             if (MODE == MODE_STRUCT) {
@@ -457,11 +461,12 @@ __global__ void __launch_bounds__(768, 1) kt_fwdbwd(const KTParams P)
             continue;
         }
         // ---------------- forward ----------------
-        int buf = 0, n_cur = 1, E = 0, lp = 0;
+        int buf = 0, n_cur = 1, E = 0;
         bool dead = false, over = false;
         la[tid] = 1.0; ls[tid] = (uint16_t)P.T.start_state;
+        int c = __ldcs(tok);
         for (int t = 0; t < len; ++t) {
-            const int c = tok[t];
+            const int cnx = (t + 1 < len) ? __ldcs(tok + (size_t)(t + 1) * 32) : 0;     // prefetch the next token
             if ((unsigned)c >= (unsigned)A) { dead = true; break; }
             const double* ca = la + buf * KN + tid; const uint16_t* cs = ls + buf * KN + tid;
             double* na = la + (buf ^ 1) * KN + tid; uint16_t* ns = ls + (buf ^ 1) * KN + tid;
@@ -490,13 +495,15 @@ __global__ void __launch_bounds__(768, 1) kt_fwdbwd(const KTParams P)
                 if (emax < 1023 - kRescaleBand || emax > 1023 + kRescaleBand) {
                     const int shift = 1023 - emax;
                     for (int k = 0; k < n_new; ++k) na[k * NT] = scalbn(na[k * NT], shift);
-                    lat[lp++] = kLatMarker | ((unsigned long long)(unsigned)E << 16);   // exponent of earlier positions
                     E -= shift;
                 }
             }
-            for (int k = 0; k < n_new; ++k) lat[lp++] = lat_pack(na[k * NT], ns[k * NT], k == n_new - 1);
+            unsigned long long* lt = lat + (size_t)t * K32;
+            for (int k = 0; k < n_new; ++k) lt[k * 32] = lat_pack(na[k * NT], ns[k * NT]);
+            cw[(size_t)t * 32] = (uint32_t)n_new | ((uint32_t)E << 8);
             n_cur = n_new;
             buf ^= 1;
+            c = cnx;
         }
         if (over) {                                   // handled by the warp / CTA kernel
             if (MODE == MODE_STRUCT) P.O.path_count[sid] = -1.0;
@@ -531,27 +538,28 @@ __global__ void __launch_bounds__(768, 1) kt_fwdbwd(const KTParams P)
                 }
                 ba[i * NT] = fin;
             }
-            lp -= n_cur;
         }
-        int n_b = n_cur, F = 0, Et = EQ;
+        int n_b = n_cur, F = 0;
+        int cn = tok[(size_t)(len - 1) * 32];
+        // software pipeline: count word, first entry and token of the next (earlier) position are in flight
+        uint32_t pf_cw = len >= 2 ? cw[(size_t)(len - 2) * 32] : 1u;
+        unsigned long long pf_w0 = len >= 2 ? lat[(size_t)(len - 2) * K32] : 0ull;
+        int pf_c = len >= 2 ? tok[(size_t)(len - 2) * 32] : 0;
         for (int t = len - 2; t >= -1; --t) {
-            const int cn = tok[t + 1];
+            const uint32_t cwv = pf_cw; const unsigned long long w0 = pf_w0; const int cthis = pf_c;
+            if (t >= 1) { pf_cw = cw[(size_t)(t - 1) * 32]; pf_w0 = lat[(size_t)(t - 1) * K32]; pf_c = tok[(size_t)(t - 1) * 32]; }
             const double* bb = la + buf * KN + tid; const uint16_t* bs = ls + buf * KN + tid;
             double* oa = la + (buf ^ 1) * KN + tid; uint16_t* os = ls + (buf ^ 1) * KN + tid;
-            while (lp > 0 && (lat[lp - 1] & 0xFFFFull) == kLatMarker) { Et = (int)(unsigned)(lat[lp - 1] >> 16); --lp; }
-            if (t < 0) Et = 0;
+            const int n_t = (t >= 0) ? (int)(cwv & 255u) : 1;
+            const int Et = (t >= 0) ? ((int)cwv >> 8) : 0;
             const int d = Et + F - EQ;
             double sc = sc0;
             if (MODE != MODE_STRUCT && d != 0) sc = scalbn(sc0, d);
-            int n_t = 0;
-            bool more = true;
-            while (more) {
+            const unsigned long long* lt = lat + (size_t)(t >= 0 ? t : 0) * K32;
+            for (int i = 0; i < n_t; ++i) {
                 int u; double a;
-                if (t >= 0) {
-                    const unsigned long long w = lat[--lp];
-                    u = (int)(w & 0x7FFFull); a = lat_alpha(w);
-                    more = lp > 0 && !(lat[lp - 1] & 0x8000ull) && (lat[lp - 1] & 0xFFFFull) != kLatMarker;
-                } else { u = P.T.start_state; a = 1.0; more = false; }
+                if (t >= 0) { const unsigned long long w = (i == 0) ? w0 : lt[i * 32]; u = (int)(w & 0xFFFFull); a = lat_alpha(w); }
+                else { u = P.T.start_state; a = 1.0; }
                 const int r = u * A + cn;
                 const unsigned r1 = brow[r + 1];
                 double b = 0.0;
@@ -568,8 +576,7 @@ __global__ void __launch_bounds__(768, 1) kt_fwdbwd(const KTParams P)
                             break;
                         }
                 }
-                os[n_t * NT] = (uint16_t)u; oa[n_t * NT] = b;
-                ++n_t;
+                os[i * NT] = (uint16_t)u; oa[i * NT] = b;
             }
             if (t >= 0 && (t & 7) == 0) {
                 int emax = 0;
@@ -582,11 +589,12 @@ __global__ void __launch_bounds__(768, 1) kt_fwdbwd(const KTParams P)
             }
             n_b = n_t;
             buf ^= 1;
+            cn = cthis;
         }
     }
     // per-warp reduction of the fixed-point log-likelihood, one atomic per warp
     for (int o = 16; o; o >>= 1) { ll_fx += __shfl_xor_sync(FULL, ll_fx, o); bad += __shfl_xor_sync(FULL, bad, o); }
-    if ((tid & 31) == 0) {
+    if (lane == 0) {
         if (ll_fx) atomicAdd(P.O.red, (unsigned long long)ll_fx);
         if (bad) atomicAdd(P.O.red + 1, bad);
     }

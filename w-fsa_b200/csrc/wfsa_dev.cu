@@ -117,6 +117,10 @@ struct wfsa_dev {
     DevBuf<double> d_fws;
     DevBuf<int32_t> d_state_final;
     DevBuf<unsigned long long> d_ktlat;
+    DevBuf<uint32_t> d_ktcnt;
+    DevBuf<int32_t> d_tokT; DevBuf<int64_t> d_goff;
+    std::vector<int32_t> h_tokens;
+    long long kt_groups = 0;
     std::vector<uint8_t> h_overflow;
     int64_t launches = 0;
     bool structure_done = false;
@@ -173,6 +177,7 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     DevBuf<uint32_t>* u32[] = {&h->d_cand_off, &h->d_slot_state, &h->d_frow, &h->d_fent, &h->d_brow, &h->d_bent};
     h->d_brow16.release(); h->d_sstate16.release(); h->d_bent8.release(); h->d_adst16.release();
     h->d_order_w.release(); h->d_fws.release(); h->d_state_final.release(); h->d_ktlat.release();
+    h->d_ktcnt.release(); h->d_tokT.release(); h->d_goff.release();
     for (auto* b : u32) b->release();
     DevBuf<double>* f64[] = {&h->d_p, &h->d_x, &h->d_tw, &h->d_sw, &h->d_fw, &h->d_ltw, &h->d_lew, &h->d_logq, &h->d_pathcnt,
                              &h->d_out, &h->d_k3lat, &h->d_gscratch, &h->d_aw, &h->d_hb_counts, &h->d_hb_p, &h->d_hb_r, &h->d_H, &h->d_rmin};
@@ -258,8 +263,10 @@ static int setup_kt(wfsa_dev* h)
     int nt = 0; size_t smem = 0;
     if (!kt_possible(h, K, nt, smem)) return set_err(h, WFSA_ERR_LIMIT, "thread-per-string kernel: tables do not fit shared memory");
     h->kt_K = K; h->kt_block = nt; h->kt_grid = h->sm_count; h->kt_smem = smem;
-    h->kt_lat_words = (size_t)std::max(h->max_len, 1) * K + (size_t)h->max_len / 8 + 8;
-    CK(h->d_ktlat.alloc((size_t)h->kt_grid * nt * h->kt_lat_words));
+    const size_t warps = (size_t)h->kt_grid * nt / 32;
+    h->kt_lat_words = (size_t)std::max(h->max_len, 1) * K * 32;      // per warp
+    CK(h->d_ktlat.alloc(warps * h->kt_lat_words));
+    CK(h->d_ktcnt.alloc(warps * (size_t)std::max(h->max_len, 1) * 32));
     cudaFuncSetAttribute(kt_fwdbwd<MODE_EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(kt_fwdbwd<MODE_STRUCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     return WFSA_OK;
@@ -367,6 +374,7 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
 #define CKB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(e_ == cudaErrorMemoryAllocation ? WFSA_ERR_NOMEM : WFSA_ERR_CUDA); } } while (0)
     CKB(h->d_tokens.alloc(std::max<int64_t>(h->n_tokens, 1) + 32));
     if (h->n_tokens) CKB(cudaMemcpyAsync(h->d_tokens.p, cd->tokens, (size_t)h->n_tokens * 4, cudaMemcpyHostToDevice, st));
+    if (kernel == 4 && h->n_tokens) h->h_tokens.assign(cd->tokens, cd->tokens + h->n_tokens);
     CKB(h->d_offs.upload(h->h_offs, st));
     CKB(h->d_p.alloc(std::max<int64_t>(h->n_strings, 1)));
     if (h->n_strings) CKB(cudaMemcpyAsync(h->d_p.p, cd->p, (size_t)h->n_strings * 8, cudaMemcpyHostToDevice, st));
@@ -418,6 +426,31 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// warp-interleaved copy of the tokens of an order list: group g = 32 consecutive strings, token t of
+// lane l at goff[g] + t*32 + l, so that a warp of the thread-per-string kernel reads 128 contiguous bytes
+static int upload_transposed_tokens(wfsa_dev* h, const std::vector<int32_t>& order)
+{
+    const long long n = (long long)order.size();
+    const long long groups = (n + 31) / 32;
+    std::vector<int64_t> goff((size_t)groups + 1, 0);
+    for (long long g = 0; g < groups; ++g) {
+        int64_t mx = 0;
+        for (long long i = g * 32; i < std::min(n, g * 32 + 32); ++i) mx = std::max<int64_t>(mx, h->h_offs[order[i] + 1] - h->h_offs[order[i]]);
+        goff[g + 1] = goff[g] + mx * 32;
+    }
+    std::vector<int32_t> tokT((size_t)goff[groups] + 32, -1);
+    for (long long i = 0; i < n; ++i) {
+        const int64_t off = h->h_offs[order[i]], len = h->h_offs[order[i] + 1] - off;
+        int32_t* dst = tokT.data() + goff[i / 32] + (i % 32);
+        for (int64_t t = 0; t < len; ++t) dst[t * 32] = h->h_tokens[off + t];
+    }
+    CK(h->d_tokT.upload(tokT, h->stream));
+    CK(h->d_goff.upload(goff, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->kt_groups = groups;
+    return WFSA_OK;
+}
+
 static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, const EvalOutD& O)
 {
     const HostFsa& F = h->fsa;
@@ -427,7 +460,9 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
     if (kernel == 4) {
         KTParams P{};
         P.T = ThreadTablesD{h->d_brow16.p, h->d_adst16.p, h->d_aw.p, h->d_fws.p, F.n_sym, F.n_states, L.n_arcs, F.start, L.start_final_tid};
-        P.tw = h->d_tw.p; P.C = C; P.O = O; P.lattice = h->d_ktlat.p; P.lat_words = h->kt_lat_words; P.K = h->kt_K; P.replicas = h->replicas;
+        P.tw = h->d_tw.p; P.C = C; P.O = O; P.lattice = h->d_ktlat.p; P.latcnt = h->d_ktcnt.p;
+        P.tokT = h->d_tokT.p; P.goff = h->d_goff.p; P.n_groups = h->kt_groups;
+        P.max_len = std::max(h->max_len, 1); P.K = h->kt_K; P.replicas = h->replicas;
         if (mode == MODE_STRUCT) kt_fwdbwd<MODE_STRUCT><<<h->kt_grid, h->kt_block, h->kt_smem, st>>>(P);
         else kt_fwdbwd<MODE_EVAL><<<h->kt_grid, h->kt_block, h->kt_smem, st>>>(P);
         h->launches++;
@@ -551,7 +586,9 @@ extern "C" int wfsa_dev_structure(wfsa_dev* h, uint8_t* recognised, double* path
     h->n_overflow = 0;
     if (h->kernel == 4) {
         // stage 1: thread-per-string over everything; strings whose active set exceeds K come back as -1
-        int rc = launch_pipeline(h, MODE_STRUCT, 4, h->d_order.p, h->n_strings, 0, nullptr, 0, true, false);
+        int rc = upload_transposed_tokens(h, h->h_order_all);
+        if (rc != WFSA_OK) return rc;
+        rc = launch_pipeline(h, MODE_STRUCT, 4, h->d_order.p, h->n_strings, 0, nullptr, 0, true, false);
         if (rc != WFSA_OK) return rc;
         if (h->n_strings) CK(cudaMemcpyAsync(pc.data(), h->d_pathcnt.p, (size_t)h->n_strings * 8, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -627,6 +664,7 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
     h->n_active = (int64_t)order.size(); h->n_active_w = (int64_t)order_w.size(); h->n_active_tokens = tokens;
     if (!order.empty()) CK(cudaMemcpyAsync(h->d_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, h->stream));
     if (!order_w.empty()) CK(cudaMemcpyAsync(h->d_order_w.p, order_w.data(), order_w.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    if (h->kernel == 4) { const int rc = upload_transposed_tokens(h, order); if (rc != WFSA_OK) return rc; }
     // every logq defaults to -inf (unrecognised strings are never touched by an evaluation)
     {
         std::vector<double> minf((size_t)h->n_strings, -INFINITY);
