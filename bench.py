@@ -35,6 +35,7 @@ import numpy as np  # noqa: E402
 METRIC = "fwd-bwd+grad symbols/sec"
 UNIT = "symbols/s"
 C4 = dict(n_states=256, n_sym=64, n_succ=8, n_emis=4, seed=1234)
+C5 = dict(n_states=4096, n_sym=256, n_succ=64, n_emis=16, seed=4321)    # config 5 (dense, CTA-per-string kernel)
 
 
 def peaks():
@@ -195,7 +196,8 @@ def run_ours(args, rank, world, local):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    model = synth.make_model(**C4)
+    cfg = C5 if args.config == "c5" else C4
+    model = synth.make_model(**cfg)
     low = model.lowered()
     n_strings = args.strings
     if args.scaling == "strong":
@@ -300,15 +302,15 @@ def run_ours(args, rank, world, local):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config 4: synthetic WFSA 256 states / 64 symbols / %d combined arcs, %d strings of length 32-128 per GPU"
-                                   % (info["n_arcs"], n_strings if args.scaling == "weak" else n_strings // world),
+            "config": {"workload": "config %s: synthetic WFSA %d states / %d symbols / %d combined arcs, %d strings of length 32-128 per GPU"
+                                   % (args.config[1:], cfg["n_states"], cfg["n_sym"], info["n_arcs"], n_strings if args.scaling == "weak" else n_strings // world),
                        "strings_per_gpu": len(w), "symbols_per_gpu": my_tokens, "parameters": n,
                        "kernel": {1: "K2 warp-per-string", 2: "K3 CTA-per-string", 3: "generic", 4: "KT thread-per-string (+ warp-per-string for overflow strings)"}[info["kernel"]],
                        "accumulators": {1: "shared memory (64-bit fixed point)", 2: "global REDs (64-bit fixed point)"}[info["accum_mode"]],
                        "grid": info["grid"], "block": info["block"], "smem_bytes": info["smem_bytes"],
                        "l2_policy": "inputs larger than L2 (%.0f MB of tokens per evaluation vs 126 MB L2)" % (4e-6 * my_tokens),
                        "collective": "ncclAllReduce(int64 sum) of [loglik, grad] per step" if world > 1 else "none",
-                       "seeds": {"automaton": C4["seed"], "strings": 1235}},
+                       "seeds": {"automaton": cfg["seed"], "strings": 1235}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": {1: "k2_fwdbwd", 2: "k3_fwdbwd", 3: "kg_fwdbwd", 4: "kt_fwdbwd"}[info["kernel"]],
                          "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
@@ -320,7 +322,7 @@ def run_ours(args, rank, world, local):
             "clocks": clocks,
             "loglik": ll,
         }
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and args.config == "c4":
             line["cpu_baseline"] = cpu_baseline(model)
         print(json.dumps(line), flush=True)
     dev.close()
@@ -339,6 +341,7 @@ def main():
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--accum", type=int, default=0)
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--config", default="c4", choices=["c4", "c5"], help="BASELINE.json config 4 (default, the metric's workload) or 5")
     ap.add_argument("--K", type=int, default=0, help="thread-per-string kernel: active-set capacity per string (0 = default 12)")
     ap.add_argument("--replicas", type=int, default=0, help="copies of the global accumulators (0 = library default)")
     ap.add_argument("--noacc", action="store_true", help="timing experiment: skip gradient accumulation (INVALID as a result)")

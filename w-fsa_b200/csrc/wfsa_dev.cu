@@ -259,7 +259,7 @@ static bool kt_possible(const wfsa_dev* h, int K, int& nt, size_t& smem)
 static int setup_kt(wfsa_dev* h)
 {
     int K = (h->opt.reserved >> 16) & 0xff;
-    if (K == 0) K = 12;
+    if (K == 0) K = 8;
     int nt = 0; size_t smem = 0;
     if (!kt_possible(h, K, nt, smem)) return set_err(h, WFSA_ERR_LIMIT, "thread-per-string kernel: tables do not fit shared memory");
     h->kt_K = K; h->kt_block = nt; h->kt_grid = h->sm_count; h->kt_smem = smem;
@@ -345,7 +345,7 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
     if (status != WFSA_OK) { h->err = msg; return bail(status); }
     int kernel = h->opt.force_kernel;
     if (kernel == 0) {
-        int nt = 0; size_t sm = 0; int K = (h->opt.reserved >> 16) & 0xff; if (K == 0) K = 12;
+        int nt = 0; size_t sm = 0; int K = (h->opt.reserved >> 16) & 0xff; if (K == 0) K = 8;
         kernel = !h->fast.ok ? 3 : (kt_possible(h, K, nt, sm) ? 4 : (h->fast.warp_ok ? 1 : 2));
     }
     if ((kernel == 1 || kernel == 2 || kernel == 4) && !h->fast.ok) { h->err = "forced fast kernel but emissions are not all one token long"; return bail(WFSA_ERR_INVALID); }
