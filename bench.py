@@ -218,7 +218,7 @@ def run_ours(args, rank, world, local):
     low.set_tokens(offs, toks, w / total_w)
     my_tokens = int(offs[-1])
 
-    variant = args.variant | (args.replicas << 8) | (2 if args.noacc else 0) | (args.K << 16)
+    variant = args.variant | (args.replicas << 8) | (2 if args.noacc else 0) | (args.K << 16) | ((args.threads // 32) << 24)
     dev = W.Device(low, device=local, force_kernel=args.kernel, accum_mode=args.accum, accum_variant=variant)
     if world > 1:
         uid = np.zeros(W.UNIQUE_ID_BYTES, dtype=np.uint8)
@@ -305,14 +305,18 @@ def run_ours(args, rank, world, local):
             "config": {"workload": "config %s: synthetic WFSA %d states / %d symbols / %d combined arcs, %d strings of length 32-128 per GPU"
                                    % (args.config[1:], cfg["n_states"], cfg["n_sym"], info["n_arcs"], n_strings if args.scaling == "weak" else n_strings // world),
                        "strings_per_gpu": len(w), "symbols_per_gpu": my_tokens, "parameters": n,
-                       "kernel": {1: "K2 warp-per-string", 2: "K3 CTA-per-string", 3: "generic", 4: "KT thread-per-string (+ warp-per-string for overflow strings)"}[info["kernel"]],
+                       "kernel": {1: "K2 warp-per-string", 2: "K3 CTA-per-string", 3: "generic", 4: "KT thread-per-string (+ warp-per-string for overflow strings)",
+                                  5: "KL thread-per-string over compiled lattices (+ warp-per-string for overflow strings)"}[info["kernel"]],
                        "accumulators": {1: "shared memory (64-bit fixed point)", 2: "global REDs (64-bit fixed point)"}[info["accum_mode"]],
                        "grid": info["grid"], "block": info["block"], "smem_bytes": info["smem_bytes"],
+                       **({"lattice": {"edges": info["lattice_edges"], "bridge_edges": info["lattice_bridge_edges"],
+                                       "stream_words": info["lattice_words"], "overflow_strings": info["n_overflow_strings"],
+                                       "pool_slots": info["pool_slots"]}} if info["kernel"] == 5 else {}),
                        "l2_policy": "inputs larger than L2 (%.0f MB of tokens per evaluation vs 126 MB L2)" % (4e-6 * my_tokens),
                        "collective": "ncclAllReduce(int64 sum) of [loglik, grad] per step" if world > 1 else "none",
                        "seeds": {"automaton": cfg["seed"], "strings": 1235}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": {1: "k2_fwdbwd", 2: "k3_fwdbwd", 3: "kg_fwdbwd", 4: "kt_fwdbwd"}[info["kernel"]],
+                         "traffic": traffic, "peak_source": peak_src, "kernel": {1: "k2_fwdbwd", 2: "k3_fwdbwd", 3: "kg_fwdbwd", 4: "kt_fwdbwd", 5: "kl_fwdbwd"}[info["kernel"]],
                          "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_share_of_step": kms_max / ms_max},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * (n + 2),
@@ -343,6 +347,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--config", default="c4", choices=["c4", "c5"], help="BASELINE.json config 4 (default, the metric's workload) or 5")
     ap.add_argument("--K", type=int, default=0, help="thread-per-string kernel: active-set capacity per string (0 = default 12)")
+    ap.add_argument("--threads", type=int, default=0, help="compiled-lattice kernel: threads per CTA (0 = as many as fit, <= 1024)")
     ap.add_argument("--replicas", type=int, default=0, help="copies of the global accumulators (0 = library default)")
     ap.add_argument("--noacc", action="store_true", help="timing experiment: skip gradient accumulation (INVALID as a result)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -67,7 +67,8 @@ typedef struct {
 
 typedef struct {
     int32_t device;              /* CUDA device ordinal                                       */
-    int32_t force_kernel;        /* 0 auto, 1 warp-per-string, 2 CTA-per-string, 3 generic    */
+    int32_t force_kernel;        /* 0 auto, 1 warp-per-string, 2 CTA-per-string, 3 generic,
+                                    4 thread-per-string (table walk), 5 thread-per-string (compiled lattices) */
     int32_t accum_mode;          /* 0 auto, 1 shared-memory accumulators, 2 global (L2) REDs  */
     int32_t reserved;
 } wfsa_dev_options;
@@ -142,7 +143,8 @@ int wfsa_dev_timer_kernel_ms(wfsa_dev* h, float* ms, int64_t* launches);
 
 /* Introspection */
 typedef struct {
-    int32_t kernel;              /* 1 warp-per-string, 2 CTA-per-string, 3 generic              */
+    int32_t kernel;              /* 1 warp-per-string, 2 CTA-per-string, 3 generic, 4 thread-per-string
+                                    (table walk), 5 thread-per-string over compiled lattices       */
     int32_t accum_mode;          /* 1 shared, 2 global                                          */
     int32_t n_trans, n_emis, n_arcs, n_slots;
     int32_t max_candidates;      /* max over symbols of states emitting it                      */
@@ -151,8 +153,27 @@ typedef struct {
     int64_t smem_bytes, table_bytes;
     int64_t kernels_launched;    /* total kernels this handle has launched                      */
     double  fixed_point_scale_log2;
+    /* compiled-lattice kernel (5): stream words incl. padding, lattice edges, edges whose posterior is
+       exactly 1 (folded into constant accumulators), strings handed to the secondary kernel, pool size */
+    int64_t lattice_words, lattice_edges, lattice_bridge_edges, n_overflow_strings;
+    int32_t pool_slots, reserved;
 } wfsa_dev_info;
 int wfsa_dev_get_info(wfsa_dev* h, wfsa_dev_info* info);
+
+/* Host-only introspection (no device needed): compiles the lattice stream of ONE string exactly as
+ * wfsa_dev_set_param_map does for the compiled-lattice kernel (w-fsa_b200/csrc/lattice.hpp documents
+ * the word format), so that tests can interpret the stream on the CPU.  trimmed may be NULL (no
+ * parameter removed).  *n_words = words written, 0 = no accepting path, -1 = needs more than n_slots
+ * pool slots.  arc_tid / arc_eid (capacity arc_capacity, may be NULL) receive the combined-arc table:
+ * arc -> (transition edge, emission edge or -1 for a final transition). */
+int wfsa_lattice_compile(const wfsa_fsa_desc* fsa, const int32_t* trimmed, const int32_t* tokens, int32_t len,
+                         int32_t n_slots, uint32_t* words, int64_t capacity, int64_t* n_words,
+                         int32_t* arc_tid, int32_t* arc_eid, int32_t arc_capacity, int32_t* n_arcs);
+
+/* Host-only: compiles a whole shard the way wfsa_dev_set_param_map does and reports
+ * out[0..7] = lattice edges, bridge edges, stream words incl. padding, longest stream, strings
+ * needing more than n_slots slots, strings without an accepting path, groups of 32, host milliseconds. */
+int wfsa_lattice_stats(const wfsa_fsa_desc* fsa, const wfsa_corpus_desc* corpus, int32_t n_slots, double* out8);
 
 void wfsa_dev_destroy(wfsa_dev* h);
 const char* wfsa_dev_last_error(const wfsa_dev* h);   /* h may be NULL: last create() error */

@@ -1,0 +1,85 @@
+// w-fsa_b200/csrc/lattice.hpp -- compiled per-string lattices of the thread-per-string kernel KL.
+//
+// The reference freezes the structure of every corpus string once, as the path matrices P and M
+// (/root/reference/src/Learner.cpp:276-348), and every later evaluation is arithmetic on that
+// frozen structure (src/Learner.cpp:515-553).  The device path does the same with a structure that
+// does not grow with the number of paths: the *trimmed lattice* of the string -- nodes
+// (position, state) that lie on an accepting path, edges = combined arcs (transition u->v taken,
+// then v emits a substring that matches the input, inc/Recognize.h:49-57) plus the final
+// transitions into the end state.  Which nodes/edges exist depends only on the automaton, the
+// string and the trim map, never on the weights x, so it is compiled once per
+// wfsa_dev_set_param_map and streamed by every evaluation.
+//
+// Stream of one string = 32-bit words in a topological order of the edges (grouped by source node):
+//
+//   EDGE  bit31=1 | first_in<<29 | last_out<<28 | bridge<<27 | dst_slot<<23 | src_slot<<19 | arc
+//         forward :  x = pool[src] * w[arc];  pool[dst] = first_in ? x : pool[dst] + x
+//         backward:  post = x * pool[dst];    pool[src] = last_out ? w*pool[dst] : pool[src] + ...
+//         A node owns a pool slot from its first incoming edge to its last outgoing edge; the
+//         same interval is the life time of its alpha in the forward sweep and of its beta in
+//         the backward sweep, so one slot assignment serves both.
+//         bridge = every accepting path uses this edge (posterior exactly 1): its contribution
+//         p_s to the gradient is folded into a constant accumulator at compile time.
+//   CHECK every kCheckEvery-th word (same index in all 32 streams of a warp => no divergence):
+//         low 16 bits = mask of live slots; the kernel renormalises the live values by a power
+//         of two when their largest exponent leaves a band (exact) and records the exponent.
+//   FIN   bit30=1 | slot of the end node   (last word of the stream; q = pool[slot])
+//   PAD   0
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "layout.hpp"
+
+namespace wfsa {
+
+constexpr uint32_t kLatEdge = 1u << 31, kLatFin = 1u << 30, kLatFirstIn = 1u << 29, kLatLastOut = 1u << 28,
+                   kLatBridge = 1u << 27;
+constexpr int kLatDstShift = 23, kLatSrcShift = 19, kLatArcBits = 15, kLatMaxSlots = 16;
+constexpr int kCheckEvery = 16;           // words between CHECK words (power of two, multiple of the kernel's chunk)
+
+// combined arcs of an automaton: (transition, emission of its target) pairs and final transitions
+struct LatticeArcs {
+    int n_arcs = 0;
+    std::vector<int32_t> arc_tid, arc_eid;     // [n_arcs]; arc_eid = -1 for a final transition
+    // compile index: row (state u, first token c) for c in [0, n_sym), c = n_sym: empty emissions
+    int n_sym = 0, n_states = 0;
+    std::vector<int32_t> row;                  // [n_states*(n_sym+1) + 1]
+    std::vector<int32_t> ent_arc, ent_dst, ent_eid;
+    std::vector<int32_t> final_arc;            // [n_states] arc id of u -> end, or -1
+    std::vector<int32_t> eps_rank;             // [n_states] position in GenericLayout::eps_order
+    bool has_eps = false, layered = false;     // layered: every emission is exactly one token long
+};
+void build_lattice_arcs(const HostFsa& f, const GenericLayout& g, LatticeArcs& out);
+
+struct LatticeScratch {
+    std::vector<int32_t> node_of;              // [(max_len+1)*n_states] -> node id or -1
+    std::vector<int32_t> npos, nstate, nslot, nout, per_pos;
+    std::vector<uint8_t> coreach, done;
+    std::vector<int32_t> esrc, edst, earc;
+    std::vector<std::vector<int32_t>> bucket;  // node ids by position
+};
+
+// Compiles one string.  arc_alive[a] == 0 removes arc a (a trimmed-away parameter: weight 0).
+// Returns 1 and appends the stream to `words` (without padding), 0 when the string has no accepting
+// path, -1 when more than n_slots nodes are alive at once (the caller evaluates such strings with
+// another kernel).  bridge_arcs receives the arcs of bridge edges (for the constant accumulators).
+int compile_lattice(const HostFsa& f, const LatticeArcs& A, const uint8_t* arc_alive, const int32_t* tok, int len,
+                    int n_slots, LatticeScratch& S, std::vector<uint32_t>& words, std::vector<int32_t>& bridge_arcs);
+
+// Whole shard: compiled streams of the strings in `ids`, grouped 32 to a warp (longest streams first),
+// transposed so that word i of lane l of group g is at goff[g] + i*32 + l.
+struct CompiledCorpus {
+    std::vector<uint32_t> words;
+    std::vector<int64_t> goff;                 // [n_groups+1]
+    std::vector<int32_t> gsid;                 // [n_groups*32] string id or -1
+    std::vector<int32_t> overflow;             // strings that need more than n_slots slots
+    std::vector<int32_t> rejected;             // strings without an accepting path
+    std::vector<long long> const_acc;          // [n_arcs] fixed-point constant gradient part (bridge edges)
+    int64_t n_edges = 0, n_bridge = 0, n_words = 0, max_words = 0;
+};
+void compile_corpus(const HostFsa& f, const LatticeArcs& A, const uint8_t* arc_alive, const int32_t* tokens,
+                    const int64_t* offs, const double* p, const std::vector<int32_t>& ids, int n_slots, double fx_scale,
+                    bool use_bridges, int max_stream_words, CompiledCorpus& out);
+
+}  // namespace wfsa

@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -19,6 +20,7 @@
 #include "../../include/wfsa_dev.h"
 #include "kernels.cuh"
 #include "layout.hpp"
+#include "lattice.hpp"
 
 using namespace wfsa;
 
@@ -110,7 +112,19 @@ struct wfsa_dev {
     size_t smem_bytes = 0, glstack_words = 0, table_bytes = 0;
     int k3_grid = 0, k3_block = 0; size_t k3_smem = 0;            // CTA-per-string (K3) launch
     int kt_grid = 0, kt_block = 0, kt_K = 0; size_t kt_smem = 0, kt_lat_words = 0;   // thread-per-string (KT)
-    int secondary = 0;                                            // kernel that takes KT's overflow strings
+    int secondary = 0;                                            // kernel that takes KT's / KL's overflow strings
+    int skernel = 0;                                              // kernel of the structural pass
+    // compiled-lattice thread-per-string kernel (KL)
+    LatticeArcs larcs;
+    int kl_grid = 0, kl_block = 0, kl_K = 0; size_t kl_smem = 0;
+    bool kl_bridges = true;
+    int64_t kl_groups = 0, kl_words = 0, kl_edges = 0, kl_bridge_edges = 0, kl_max_words = 0;
+    DevBuf<uint32_t> d_klwords, d_klcounter;
+    DevBuf<int64_t> d_klgoff;
+    DevBuf<int32_t> d_klgsid, d_kl_arc_tid, d_kl_arc_eid;
+    DevBuf<double> d_klaw, d_klxs;
+    DevBuf<unsigned long long> d_klacc, d_klconst;
+    std::vector<double> h_p;
     int64_t n_overflow = 0, n_active_w = 0;
     DevBuf<int32_t> d_order_w;                                    // overflow strings (secondary kernel)
     DevBuf<uint16_t> d_adst16;
@@ -178,6 +192,9 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     h->d_brow16.release(); h->d_sstate16.release(); h->d_bent8.release(); h->d_adst16.release();
     h->d_order_w.release(); h->d_fws.release(); h->d_state_final.release(); h->d_ktlat.release();
     h->d_ktcnt.release(); h->d_tokT.release(); h->d_goff.release();
+    h->d_klwords.release(); h->d_klcounter.release(); h->d_klgoff.release(); h->d_klgsid.release();
+    h->d_kl_arc_tid.release(); h->d_kl_arc_eid.release(); h->d_klaw.release(); h->d_klxs.release();
+    h->d_klacc.release(); h->d_klconst.release();
     for (auto* b : u32) b->release();
     DevBuf<double>* f64[] = {&h->d_p, &h->d_x, &h->d_tw, &h->d_sw, &h->d_fw, &h->d_ltw, &h->d_lew, &h->d_logq, &h->d_pathcnt,
                              &h->d_out, &h->d_k3lat, &h->d_gscratch, &h->d_aw, &h->d_hb_counts, &h->d_hb_p, &h->d_hb_r, &h->d_H, &h->d_rmin};
@@ -272,6 +289,38 @@ static int setup_kt(wfsa_dev* h)
     return WFSA_OK;
 }
 
+// compiled-lattice kernel: per-arc weights + kLatMaxSlots pool doubles per thread must fit 227 KB
+static bool kl_possible(const wfsa_dev* h, int K, int want_nt, int& nt, size_t& smem)
+{
+    const LatticeArcs& A = h->larcs;
+    if (A.n_arcs <= 0 || A.n_arcs >= (1 << kLatArcBits)) return false;
+    const size_t tab = (size_t)A.n_arcs * 8, max_smem = 227 * 1024;
+    if (tab + (size_t)128 * K * 8 > max_smem) return false;
+    nt = (int)((max_smem - tab) / ((size_t)K * 8) / 32) * 32;
+    nt = std::min(nt, 1024);
+    if (want_nt > 0) nt = std::min(nt, want_nt);
+    smem = tab + (size_t)nt * K * 8;
+    return nt >= 128;
+}
+
+static int setup_kl(wfsa_dev* h)
+{
+    int K = (h->opt.reserved >> 16) & 0xff;
+    if (K == 0 || K > kLatMaxSlots) K = kLatMaxSlots;
+    int nt = 0; size_t smem = 0;
+    if (!kl_possible(h, K, ((h->opt.reserved >> 24) & 0x7f) * 32, nt, smem))
+        return set_err(h, WFSA_ERR_LIMIT, "compiled-lattice kernel: the arc weights do not fit shared memory");
+    h->kl_K = K; h->kl_block = nt; h->kl_grid = h->sm_count; h->kl_smem = smem;
+    h->kl_bridges = !(h->opt.reserved & 4);
+    const LatticeArcs& A = h->larcs;
+    CK(h->d_kl_arc_tid.upload(A.arc_tid, h->stream)); CK(h->d_kl_arc_eid.upload(A.arc_eid, h->stream));
+    CK(h->d_klaw.alloc(A.n_arcs)); CK(h->d_klacc.alloc((size_t)A.n_arcs * h->replicas)); CK(h->d_klconst.alloc(A.n_arcs));
+    CK(h->d_klcounter.alloc(1));
+    cudaFuncSetAttribute(kl_fwdbwd<ACC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(kl_fwdbwd<ACC_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return WFSA_OK;
+}
+
 static int setup_generic(wfsa_dev* h)
 {
     const size_t per = (size_t)2 * (h->max_len + 1) * h->fsa.n_states;
@@ -293,14 +342,22 @@ static int choose_launch(wfsa_dev* h)
         CK(h->d_acc.alloc(n_acc * h->replicas));
     }
     int rc = WFSA_OK;
-    if (h->kernel == 4) {
+    h->skernel = h->kernel;
+    if (h->kernel == 5) {
+        h->secondary = h->fast.warp_ok ? 1 : (h->fast.ok ? 2 : 3);
+        int nt = 0; size_t sm = 0; int K = (h->opt.reserved >> 16) & 0xff; if (K == 0) K = 8;
+        h->skernel = (h->fast.ok && kt_possible(h, K, nt, sm)) ? 4 : h->secondary;
+        rc = setup_kl(h);
+        if (rc == WFSA_OK && h->skernel == 4) rc = setup_kt(h);
+        if (rc == WFSA_OK) rc = h->secondary == 1 ? setup_k2(h) : (h->secondary == 2 ? setup_k3(h) : setup_generic(h));
+    } else if (h->kernel == 4) {
         h->secondary = h->fast.warp_ok ? 1 : 2;
         rc = setup_kt(h);
         if (rc == WFSA_OK) rc = h->secondary == 1 ? setup_k2(h) : setup_k3(h);
     } else if (h->kernel == 1) rc = setup_k2(h);
     else if (h->kernel == 2) rc = setup_k3(h);
     else rc = setup_generic(h);
-    h->accum = (h->kernel == 1 || (h->kernel == 4 && h->secondary == 1)) ? h->accum : 2;
+    h->accum = (h->kernel == 1 || (h->kernel >= 4 && h->secondary == 1)) ? h->accum : 2;
     return rc;
 }
 
@@ -343,14 +400,17 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
     if (status != WFSA_OK) { h->err = msg; return bail(status); }
     msg = build_generic_layout(h->fsa, h->gen, status);
     if (status != WFSA_OK) { h->err = msg; return bail(status); }
+    build_lattice_arcs(h->fsa, h->gen, h->larcs);
     int kernel = h->opt.force_kernel;
     if (kernel == 0) {
         int nt = 0; size_t sm = 0; int K = (h->opt.reserved >> 16) & 0xff; if (K == 0) K = 8;
-        kernel = !h->fast.ok ? 3 : (kt_possible(h, K, nt, sm) ? 4 : (h->fast.warp_ok ? 1 : 2));
+        if (kl_possible(h, kLatMaxSlots, 0, nt, sm)) kernel = 5;
+        else kernel = !h->fast.ok ? 3 : (kt_possible(h, K, nt, sm) ? 4 : (h->fast.warp_ok ? 1 : 2));
     }
+    if (kernel == 5) { int nt = 0; size_t sm = 0; if (!kl_possible(h, kLatMaxSlots, 0, nt, sm)) { h->err = "forced compiled-lattice kernel but the arc weights do not fit shared memory"; return bail(WFSA_ERR_INVALID); } }
     if ((kernel == 1 || kernel == 2 || kernel == 4) && !h->fast.ok) { h->err = "forced fast kernel but emissions are not all one token long"; return bail(WFSA_ERR_INVALID); }
     if (kernel == 1 && !h->fast.warp_ok) { h->err = "forced warp-per-string kernel but more than 32 states emit one symbol"; return bail(WFSA_ERR_INVALID); }
-    if (kernel < 1 || kernel > 4) { h->err = "force_kernel out of range"; return bail(WFSA_ERR_INVALID); }
+    if (kernel < 1 || kernel > 5) { h->err = "force_kernel out of range"; return bail(WFSA_ERR_INVALID); }
     h->kernel = kernel;
 
     // ---- corpus shard
@@ -374,7 +434,8 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
 #define CKB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(e_ == cudaErrorMemoryAllocation ? WFSA_ERR_NOMEM : WFSA_ERR_CUDA); } } while (0)
     CKB(h->d_tokens.alloc(std::max<int64_t>(h->n_tokens, 1) + 32));
     if (h->n_tokens) CKB(cudaMemcpyAsync(h->d_tokens.p, cd->tokens, (size_t)h->n_tokens * 4, cudaMemcpyHostToDevice, st));
-    if (kernel == 4 && h->n_tokens) h->h_tokens.assign(cd->tokens, cd->tokens + h->n_tokens);
+    if (kernel >= 4 && h->n_tokens) h->h_tokens.assign(cd->tokens, cd->tokens + h->n_tokens);
+    if (h->n_strings) h->h_p.assign(cd->p, cd->p + h->n_strings);
     CKB(h->d_offs.upload(h->h_offs, st));
     CKB(h->d_p.alloc(std::max<int64_t>(h->n_strings, 1)));
     if (h->n_strings) CKB(cudaMemcpyAsync(h->d_p.p, cd->p, (size_t)h->n_strings * 8, cudaMemcpyHostToDevice, st));
@@ -457,7 +518,17 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
     const FastLayout& L = h->fast;
     cudaStream_t st = h->stream;
     if (C.n_order <= 0) return;
-    if (kernel == 4) {
+    if (kernel == 5) {
+        KLParams P{};
+        P.aw = h->d_klaw.p; P.words = h->d_klwords.p; P.goff = h->d_klgoff.p; P.gsid = h->d_klgsid.p; P.p = h->d_p.p;
+        P.n_groups = h->kl_groups; P.xs = h->d_klxs.p; P.xs_rows = (size_t)std::max<int64_t>(h->kl_max_words, 1);
+        P.counter = h->d_klcounter.p; P.O = O; P.O.acc_global = h->d_klacc.p;
+        P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas;
+        cudaMemsetAsync(h->d_klcounter.p, 0, 4, st);
+        if (h->opt.reserved & 2) kl_fwdbwd<ACC_NONE><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // timing experiment
+        else kl_fwdbwd<ACC_GLOBAL><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
+        h->launches++;
+    } else if (kernel == 4) {
         KTParams P{};
         P.T = ThreadTablesD{h->d_brow16.p, h->d_adst16.p, h->d_aw.p, h->d_fws.p, F.n_sym, F.n_states, L.n_arcs, F.start, L.start_final_tid};
         P.tw = h->d_tw.p; P.C = C; P.O = O; P.lattice = h->d_ktlat.p; P.latcnt = h->d_ktcnt.p;
@@ -549,6 +620,15 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
             k_state_final_weights<<<(F.n_states + 255) / 256, 256, 0, st>>>(F.n_states, h->d_state_final.p, h->d_tw.p, h->d_fws.p);
             h->launches++;
         }
+        if (kernel == 5) {
+            const int na = h->larcs.n_arcs;
+            k_arc_weights<<<(na + 255) / 256, 256, 0, st>>>(na, h->d_kl_arc_tid.p, h->d_kl_arc_eid.p, h->d_emis_tp.p, h->d_tw.p,
+                                                          h->d_x.p, unit, h->d_klaw.p);
+            h->launches++;
+            // replica 0 starts from the constant part (bridge edges: posterior exactly 1), the others from 0
+            CK(cudaMemcpyAsync(h->d_klacc.p, h->d_klconst.p, (size_t)na * 8, cudaMemcpyDeviceToDevice, st));
+            if (h->replicas > 1) CK(cudaMemsetAsync(h->d_klacc.p + na, 0, (size_t)na * (h->replicas - 1) * 8, st));
+        }
     }
     EvalOutD O{};
     O.logq = h->d_logq.p; O.path_count = h->d_pathcnt.p; O.acc_global = h->d_acc.p; O.red = h->d_red.p;
@@ -566,7 +646,15 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
     if (kernel2) launch_main(h, kernel2, mode, CorpusD{h->d_tokens.p, h->d_offs.p, h->d_p.p, d_order2, n_order2}, O);
     if (e1) cudaEventRecord(e1, st);
     CK(cudaGetLastError());
-    if (fold && h->fast.ok && h->kernel != 3) {
+    if (fold && kernel == 5) {
+        const int na = h->larcs.n_arcs;
+        k_arcs_to_edges<<<(na + 255) / 256, 256, 0, st>>>(na, 0, F.n_trans(), h->d_klacc.p, h->replicas, h->d_kl_arc_tid.p,
+                                                         h->d_kl_arc_eid.p, nullptr, h->d_red.p + 2);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    const bool fast_used = kernel == 5 ? (kernel2 == 1 || kernel2 == 2) && n_order2 > 0 : (kernel != 3);
+    if (fold && h->fast.ok && fast_used) {
         const int total = h->fast.n_arcs + F.n_states;
         k_arcs_to_edges<<<(total + 255) / 256, 256, 0, st>>>(h->fast.n_arcs, F.n_states, F.n_trans(), h->d_acc.p, h->replicas,
                                                             h->d_arc_tid.p, h->d_arc_eid.p, h->d_state_final.p, h->d_red.p + 2);
@@ -584,7 +672,7 @@ extern "C" int wfsa_dev_structure(wfsa_dev* h, uint8_t* recognised, double* path
     std::vector<double> pc((size_t)h->n_strings);
     h->h_overflow.assign((size_t)h->n_strings, 0);
     h->n_overflow = 0;
-    if (h->kernel == 4) {
+    if (h->skernel == 4) {
         // stage 1: thread-per-string over everything; strings whose active set exceeds K come back as -1
         int rc = upload_transposed_tokens(h, h->h_order_all);
         if (rc != WFSA_OK) return rc;
@@ -600,7 +688,7 @@ extern "C" int wfsa_dev_structure(wfsa_dev* h, uint8_t* recognised, double* path
         rc = launch_pipeline(h, MODE_STRUCT, h->secondary, h->d_order_w.p, h->n_overflow, 0, nullptr, 0, false, true);
         if (rc != WFSA_OK) return rc;
     } else {
-        int rc = launch_pipeline(h, MODE_STRUCT, h->kernel, h->d_order.p, h->n_strings, 0, nullptr, 0, true, true);
+        int rc = launch_pipeline(h, MODE_STRUCT, h->skernel, h->d_order.p, h->n_strings, 0, nullptr, 0, true, true);
         if (rc != WFSA_OK) return rc;
     }
     // used flags are per-edge instance counts; combine across ranks before thresholding
@@ -662,8 +750,10 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
             tokens += len; max_len = std::max<int>(max_len, (int)len);
         }
     h->n_active = (int64_t)order.size(); h->n_active_w = (int64_t)order_w.size(); h->n_active_tokens = tokens;
-    if (!order.empty()) CK(cudaMemcpyAsync(h->d_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, h->stream));
-    if (!order_w.empty()) CK(cudaMemcpyAsync(h->d_order_w.p, order_w.data(), order_w.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    if (h->kernel != 5) {
+        if (!order.empty()) CK(cudaMemcpyAsync(h->d_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        if (!order_w.empty()) CK(cudaMemcpyAsync(h->d_order_w.p, order_w.data(), order_w.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    }
     if (h->kernel == 4) { const int rc = upload_transposed_tokens(h, order); if (rc != WFSA_OK) return rc; }
     // every logq defaults to -inf (unrecognised strings are never touched by an evaluation)
     {
@@ -685,6 +775,35 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
     int bits = 1;
     while ((1ll << bits) <= bound && bits < 40) ++bits;
     h->fx_log2 = 62 - bits;
+    if (h->kernel == 5) {
+        // compile the trimmed lattice of every participating string (structure is independent of x)
+        const LatticeArcs& A = h->larcs;
+        std::vector<uint8_t> alive((size_t)A.n_arcs);
+        for (int a = 0; a < A.n_arcs; ++a)
+            alive[a] = ttp[A.arc_tid[a]] != -2 && (A.arc_eid[a] < 0 || etp[A.arc_eid[a]] != -2);
+        CompiledCorpus cc;
+        compile_corpus(h->fsa, A, alive.data(), h->h_tokens.data(), h->h_offs.data(), h->h_p.data(), order, h->kl_K,
+                       std::ldexp(1.0, (int)h->fx_log2), h->kl_bridges, 8192, cc);
+        // strings that need more pool slots, and strings without a path under this trim map (their q is 0:
+        // the numeric kernels report them as non-finite), go to the secondary kernel
+        order_w = cc.overflow;
+        order_w.insert(order_w.end(), cc.rejected.begin(), cc.rejected.end());
+        h->n_active = (int64_t)order.size() - (int64_t)order_w.size(); h->n_active_w = (int64_t)order_w.size();
+        h->kl_groups = (int64_t)cc.goff.size() - 1; h->kl_words = cc.n_words; h->kl_edges = cc.n_edges;
+        h->kl_bridge_edges = cc.n_bridge; h->kl_max_words = cc.max_words;
+        CK(h->d_klwords.upload(cc.words, h->stream)); CK(h->d_klgoff.upload(cc.goff, h->stream));
+        CK(h->d_klgsid.upload(cc.gsid, h->stream));
+        std::vector<unsigned long long> cacc(cc.const_acc.begin(), cc.const_acc.end());
+        CK(cudaMemcpyAsync(h->d_klconst.p, cacc.data(), cacc.size() * 8, cudaMemcpyHostToDevice, h->stream));
+        if (!order_w.empty()) CK(cudaMemcpyAsync(h->d_order_w.p, order_w.data(), order_w.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        const size_t warps = (size_t)h->kl_grid * h->kl_block / 32;
+        const size_t need = warps * (size_t)std::max<int64_t>(cc.max_words, 1) * 32;
+        if (h->d_klxs.n < need) {
+            const cudaError_t e = h->d_klxs.alloc(need);
+            if (e != cudaSuccess) return set_err(h, WFSA_ERR_NOMEM, "compiled-lattice kernel: cannot allocate the per-warp x stacks");
+        }
+        CK(cudaStreamSynchronize(h->stream));
+    }
     if (h->n != n) {
         if (h->h_out) cudaFreeHost(h->h_out);
         if (h->h_x) cudaFreeHost(h->h_x);
@@ -725,7 +844,7 @@ extern "C" int wfsa_dev_eval_launch(wfsa_dev* h)
     if (h->n < 0) return set_err(h, WFSA_ERR_STATE, "eval before set_param_map");
     CK(cudaSetDevice(h->device));
     int rc = launch_pipeline(h, MODE_EVAL, h->kernel, h->d_order.p, h->n_active,
-                             h->kernel == 4 ? h->secondary : 0, h->d_order_w.p, h->n_active_w, true, true);
+                             h->kernel >= 4 ? h->secondary : 0, h->d_order_w.p, h->n_active_w, true, true);
     if (rc != WFSA_OK) return rc;
     rc = nccl_allreduce(h, h->d_red.p, h->d_red.n, ncclUint64, ncclSum);
     if (rc != WFSA_OK) return rc;
@@ -922,6 +1041,66 @@ extern "C" int wfsa_dev_timer_kernel_ms(wfsa_dev* h, float* ms, int64_t* launche
     return WFSA_OK;
 }
 
+extern "C" int wfsa_lattice_compile(const wfsa_fsa_desc* fd, const int32_t* trimmed, const int32_t* tokens, int32_t len,
+                                    int32_t n_slots, uint32_t* words, int64_t capacity, int64_t* n_words,
+                                    int32_t* arc_tid, int32_t* arc_eid, int32_t arc_capacity, int32_t* n_arcs)
+{
+    g_create_error.clear();
+    if (!fd || len < 0 || (len && !tokens) || !n_words || n_slots < 1 || n_slots > kLatMaxSlots) { g_create_error = "lattice_compile: bad arguments"; return WFSA_ERR_INVALID; }
+    HostFsa f; GenericLayout g; LatticeArcs A;
+    int status = WFSA_OK;
+    std::string msg = copy_and_validate(fd, f, status);
+    if (status == WFSA_OK) msg = build_generic_layout(f, g, status);
+    if (status != WFSA_OK) { g_create_error = msg; return status; }
+    build_lattice_arcs(f, g, A);
+    if (A.n_arcs >= (1 << kLatArcBits)) { g_create_error = "lattice_compile: too many combined arcs"; return WFSA_ERR_LIMIT; }
+    if (n_arcs) *n_arcs = A.n_arcs;
+    if (arc_tid && arc_eid) {
+        if (arc_capacity < A.n_arcs) { g_create_error = "lattice_compile: arc_capacity too small"; return WFSA_ERR_INVALID; }
+        std::copy(A.arc_tid.begin(), A.arc_tid.end(), arc_tid);
+        std::copy(A.arc_eid.begin(), A.arc_eid.end(), arc_eid);
+    }
+    std::vector<uint8_t> alive((size_t)A.n_arcs, 1);
+    if (trimmed)
+        for (int a = 0; a < A.n_arcs; ++a) {
+            const int tp = f.trans_param[A.arc_tid[a]], ep = A.arc_eid[a] < 0 ? -1 : f.emis_param[A.arc_eid[a]];
+            alive[a] = (tp < 0 || trimmed[tp] != -2) && (ep < 0 || trimmed[ep] != -2);
+        }
+    LatticeScratch S;
+    std::vector<uint32_t> w;
+    std::vector<int32_t> bridges;
+    const int rc = compile_lattice(f, A, alive.data(), tokens, len, n_slots, S, w, bridges);
+    if (rc != 1) { *n_words = rc; return WFSA_OK; }
+    if ((int64_t)w.size() > capacity || !words) { g_create_error = "lattice_compile: capacity too small"; *n_words = (int64_t)w.size(); return WFSA_ERR_INVALID; }
+    std::copy(w.begin(), w.end(), words);
+    *n_words = (int64_t)w.size();
+    return WFSA_OK;
+}
+
+extern "C" int wfsa_lattice_stats(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* cd, int32_t n_slots, double* out8)
+{
+    g_create_error.clear();
+    if (!fd || !cd || !out8 || n_slots < 1 || n_slots > kLatMaxSlots || cd->n_strings < 0) { g_create_error = "lattice_stats: bad arguments"; return WFSA_ERR_INVALID; }
+    HostFsa f; GenericLayout g; LatticeArcs A;
+    int status = WFSA_OK;
+    std::string msg = copy_and_validate(fd, f, status);
+    if (status == WFSA_OK) msg = build_generic_layout(f, g, status);
+    if (status != WFSA_OK) { g_create_error = msg; return status; }
+    build_lattice_arcs(f, g, A);
+    std::vector<int32_t> ids((size_t)cd->n_strings);
+    std::iota(ids.begin(), ids.end(), 0);
+    std::stable_sort(ids.begin(), ids.end(), [&](int32_t a, int32_t b) {
+        return (cd->offsets[a + 1] - cd->offsets[a]) > (cd->offsets[b + 1] - cd->offsets[b]);
+    });
+    CompiledCorpus cc;
+    const auto t0 = std::chrono::steady_clock::now();
+    compile_corpus(f, A, nullptr, cd->tokens, cd->offsets, cd->p, ids, n_slots, 1.0, true, 8192, cc);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    out8[0] = (double)cc.n_edges; out8[1] = (double)cc.n_bridge; out8[2] = (double)cc.n_words; out8[3] = (double)cc.max_words;
+    out8[4] = (double)cc.overflow.size(); out8[5] = (double)cc.rejected.size(); out8[6] = (double)cc.goff.size() - 1; out8[7] = ms;
+    return WFSA_OK;
+}
+
 extern "C" int wfsa_dev_get_info(wfsa_dev* h, wfsa_dev_info* info)
 {
     if (!h || !info) return WFSA_ERR_INVALID;
@@ -931,11 +1110,16 @@ extern "C" int wfsa_dev_get_info(wfsa_dev* h, wfsa_dev_info* info)
     info->n_arcs = h->fast.ok ? h->fast.n_arcs : 0; info->n_slots = h->fast.ok ? h->fast.n_slots : 0;
     info->max_candidates = h->fast.ok ? h->fast.max_cand : 0;
     info->sm_count = h->sm_count;
-    info->grid = h->kernel == 4 ? h->kt_grid : (h->kernel == 2 ? h->k3_grid : h->grid);
-    info->block = h->kernel == 4 ? h->kt_block : (h->kernel == 2 ? h->k3_block : (h->kernel == 3 ? 128 : h->block));
+    info->grid = h->kernel == 5 ? h->kl_grid : (h->kernel == 4 ? h->kt_grid : (h->kernel == 2 ? h->k3_grid : h->grid));
+    info->block = h->kernel == 5 ? h->kl_block : (h->kernel == 4 ? h->kt_block : (h->kernel == 2 ? h->k3_block : (h->kernel == 3 ? 128 : h->block)));
     info->n_strings = h->n_strings; info->n_tokens = h->n_tokens;
     info->n_active_tokens = h->n_active_tokens;
-    info->smem_bytes = (int64_t)(h->kernel == 4 ? h->kt_smem : (h->kernel == 2 ? h->k3_smem : h->smem_bytes));
+    info->smem_bytes = (int64_t)(h->kernel == 5 ? h->kl_smem : (h->kernel == 4 ? h->kt_smem : (h->kernel == 2 ? h->k3_smem : h->smem_bytes)));
+    if (h->kernel == 5) {
+        info->n_arcs = h->larcs.n_arcs;
+        info->lattice_words = h->kl_words; info->lattice_edges = h->kl_edges; info->lattice_bridge_edges = h->kl_bridge_edges;
+        info->n_overflow_strings = h->n_active_w; info->pool_slots = h->kl_K;
+    }
     info->n_active_strings = h->n_active + h->n_active_w; info->table_bytes = (int64_t)h->table_bytes;
     info->kernels_launched = h->launches; info->fixed_point_scale_log2 = h->fx_log2;
     return WFSA_OK;

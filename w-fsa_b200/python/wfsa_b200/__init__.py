@@ -20,7 +20,7 @@ DEV_SYMBOLS = [
     "wfsa_dev_eval_launch", "wfsa_dev_eval_fetch", "wfsa_dev_sync", "wfsa_dev_set_path_blocks", "wfsa_dev_hessian",
     "wfsa_dev_comm_unique_id", "wfsa_dev_comm_init", "wfsa_dev_allreduce_f64", "wfsa_dev_timer_begin",
     "wfsa_dev_timer_end", "wfsa_dev_timer_kernel_ms", "wfsa_dev_get_info", "wfsa_dev_destroy", "wfsa_dev_last_error",
-    "wfsa_dev_version",
+    "wfsa_dev_version", "wfsa_lattice_compile", "wfsa_lattice_stats",
 ]
 HOST_SYMBOLS = [
     "wfsa_host_parse", "wfsa_host_last_error", "wfsa_session_create", "wfsa_session_destroy", "wfsa_session_error",
@@ -54,7 +54,9 @@ class DevInfo(C.Structure):
                 ("n_arcs", C.c_int32), ("n_slots", C.c_int32), ("max_candidates", C.c_int32), ("sm_count", C.c_int32),
                 ("grid", C.c_int32), ("block", C.c_int32), ("n_strings", C.c_int64), ("n_active_strings", C.c_int64),
                 ("n_tokens", C.c_int64), ("n_active_tokens", C.c_int64), ("smem_bytes", C.c_int64),
-                ("table_bytes", C.c_int64), ("kernels_launched", C.c_int64), ("fixed_point_scale_log2", C.c_double)]
+                ("table_bytes", C.c_int64), ("kernels_launched", C.c_int64), ("fixed_point_scale_log2", C.c_double),
+                ("lattice_words", C.c_int64), ("lattice_edges", C.c_int64), ("lattice_bridge_edges", C.c_int64),
+                ("n_overflow_strings", C.c_int64), ("pool_slots", C.c_int32), ("reserved", C.c_int32)]
 
 
 class PathBlocks(C.Structure):
@@ -130,6 +132,9 @@ def lib():
         L.wfsa_dev_timer_end.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.wfsa_dev_timer_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), I64P]
         L.wfsa_dev_get_info.argtypes = [C.c_void_p, C.POINTER(DevInfo)]
+        L.wfsa_lattice_stats.argtypes = [C.POINTER(FsaDesc), C.POINTER(CorpusDesc), C.c_int32, F64P]
+        L.wfsa_lattice_compile.argtypes = [C.POINTER(FsaDesc), I32P, I32P, C.c_int32, C.c_int32, C.POINTER(C.c_uint32), C.c_int64,
+                                           I64P, I32P, I32P, C.c_int32, I32P]
         _lib = L
     return _lib
 
