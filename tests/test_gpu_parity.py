@@ -132,8 +132,9 @@ def test_evaluation_result_line():
     ref = [-0.27031007207211, 0.27031007207211, 0.549306144334055, 0.346573590279973, -38.3012866549895, 3.58351893845611, 4, 1]
     assert np.allclose(r[[0, 1, 2, 3, 5, 6, 7]], np.array(ref)[[0, 1, 2, 3, 5, 6, 7]], rtol=1e-9, atol=1e-12)
     # r[4] is the log-determinant of a singular Hessian (the optimum is not unique): pure rounding noise,
-    # solver dependent -- only its order of magnitude is meaningful
-    assert -45 < r[4] < -30
+    # solver dependent: the reference build prints -38.3 (|det| ~ 1e-17) here and inf -- its
+    # answer for a non-positive determinant, src/Utils.cpp:349-351 -- on test5; both are the same statement
+    assert r[4] == np.inf or -60 < r[4] < -30
     s.close()
 
 
