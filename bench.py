@@ -306,17 +306,21 @@ def run_ours(args, rank, world, local):
                                    % (args.config[1:], cfg["n_states"], cfg["n_sym"], info["n_arcs"], n_strings if args.scaling == "weak" else n_strings // world),
                        "strings_per_gpu": len(w), "symbols_per_gpu": my_tokens, "parameters": n,
                        "kernel": {1: "K2 warp-per-string", 2: "K3 CTA-per-string", 3: "generic", 4: "KT thread-per-string (+ warp-per-string for overflow strings)",
-                                  5: "KL thread-per-string over compiled lattices (+ warp-per-string for overflow strings)"}[info["kernel"]],
+                                  5: "KL thread-per-string over compiled lattices (+ warp-per-string for overflow strings)",
+                                  6: "KR+KS segmented compiled lattices: region types (thread per type) + per-string sums (thread per string)"}[info["kernel"]],
                        "accumulators": {1: "shared memory (64-bit fixed point)", 2: "global REDs (64-bit fixed point)"}[info["accum_mode"]],
                        "grid": info["grid"], "block": info["block"], "smem_bytes": info["smem_bytes"],
                        **({"lattice": {"edges": info["lattice_edges"], "bridge_edges": info["lattice_bridge_edges"],
                                        "stream_words": info["lattice_words"], "overflow_strings": info["n_overflow_strings"],
-                                       "pool_slots": info["pool_slots"]}} if info["kernel"] == 5 else {}),
+                                       "pool_slots": info["pool_slots"]}} if info["kernel"] >= 5 else {}),
+                       **({"segments": {"region_types": info["seg_types"], "region_instances": info["seg_region_instances"],
+                                        "region_edges": info["seg_region_edges"], "type_edges": info["seg_type_edges"],
+                                        "compile_host_ms": info["seg_host_ms"]}} if info["kernel"] == 6 else {}),
                        "l2_policy": "inputs larger than L2 (%.0f MB of tokens per evaluation vs 126 MB L2)" % (4e-6 * my_tokens),
                        "collective": "ncclAllReduce(int64 sum) of [loglik, grad] per step" if world > 1 else "none",
                        "seeds": {"automaton": cfg["seed"], "strings": 1235}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": {1: "k2_fwdbwd", 2: "k3_fwdbwd", 3: "kg_fwdbwd", 4: "kt_fwdbwd", 5: "kl_fwdbwd"}[info["kernel"]],
+                         "traffic": traffic, "peak_source": peak_src, "kernel": {1: "k2_fwdbwd", 2: "k3_fwdbwd", 3: "kg_fwdbwd", 4: "kt_fwdbwd", 5: "kl_fwdbwd", 6: "kr_regions+ks_strings"}[info["kernel"]],
                          "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_share_of_step": kms_max / ms_max},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * (n + 2),

@@ -68,7 +68,8 @@ typedef struct {
 typedef struct {
     int32_t device;              /* CUDA device ordinal                                       */
     int32_t force_kernel;        /* 0 auto, 1 warp-per-string, 2 CTA-per-string, 3 generic,
-                                    4 thread-per-string (table walk), 5 thread-per-string (compiled lattices) */
+                                    4 thread-per-string (table walk), 5 thread-per-string (compiled lattices),
+                                    6 segmented compiled lattices (region types + per-string sums) */
     int32_t accum_mode;          /* 0 auto, 1 shared-memory accumulators, 2 global (L2) REDs  */
     int32_t reserved;
 } wfsa_dev_options;
@@ -144,7 +145,8 @@ int wfsa_dev_timer_kernel_ms(wfsa_dev* h, float* ms, int64_t* launches);
 /* Introspection */
 typedef struct {
     int32_t kernel;              /* 1 warp-per-string, 2 CTA-per-string, 3 generic, 4 thread-per-string
-                                    (table walk), 5 thread-per-string over compiled lattices       */
+                                    (table walk), 5 thread-per-string over compiled lattices,
+                                    6 segmented compiled lattices (kr_regions + ks_strings)        */
     int32_t accum_mode;          /* 1 shared, 2 global                                          */
     int32_t n_trans, n_emis, n_arcs, n_slots;
     int32_t max_candidates;      /* max over symbols of states emitting it                      */
@@ -157,6 +159,10 @@ typedef struct {
        exactly 1 (folded into constant accumulators), strings handed to the secondary kernel, pool size */
     int64_t lattice_words, lattice_edges, lattice_bridge_edges, n_overflow_strings;
     int32_t pool_slots, reserved;
+    /* segmented kernels (6): distinct region types, region instances over all strings, edges of all
+       instances / of the distinct types (what one evaluation walks), host milliseconds of the compile */
+    int64_t seg_types, seg_region_instances, seg_region_edges, seg_type_edges;
+    double  seg_host_ms;
 } wfsa_dev_info;
 int wfsa_dev_get_info(wfsa_dev* h, wfsa_dev_info* info);
 
@@ -174,6 +180,18 @@ int wfsa_lattice_compile(const wfsa_fsa_desc* fsa, const int32_t* trimmed, const
  * out[0..7] = lattice edges, bridge edges, stream words incl. padding, longest stream, strings
  * needing more than n_slots slots, strings without an accepting path, groups of 32, host milliseconds. */
 int wfsa_lattice_stats(const wfsa_fsa_desc* fsa, const wfsa_corpus_desc* corpus, int32_t n_slots, double* out8);
+
+/* Host-only introspection of the SEGMENTED compiled form (w-fsa_b200/csrc/lattice.hpp, kernels 6): compiles a
+ * whole shard exactly as wfsa_dev_set_param_map does and exposes the arrays the device kernels read, so that
+ * tests can interpret them on the CPU.  All strings of the corpus take part, longest first.
+ * which: 0 rwords(u32) 1 rgoff(i64) 2 rgrows(i32) 3 typeW(f64) 4 swords(u32) 5 sgoff(i64) 6 sgref(i32)
+ *        7 ksid(i32) 8 kp(f64) 9 overflow(i32) 10 rejected(i32) 11 const_acc(i64)
+ *        12 stats(i64): types, region instances, instance edges, type edges, bridges, strings, host microseconds */
+typedef struct wfsa_segmented wfsa_segmented;
+int wfsa_segmented_compile(const wfsa_fsa_desc* fsa, const wfsa_corpus_desc* corpus, const int32_t* trimmed,
+                           int32_t n_slots, double fx_scale, wfsa_segmented** out);
+int wfsa_segmented_get(const wfsa_segmented* s, int which, const void** data, int64_t* count);
+void wfsa_segmented_free(wfsa_segmented* s);
 
 void wfsa_dev_destroy(wfsa_dev* h);
 const char* wfsa_dev_last_error(const wfsa_dev* h);   /* h may be NULL: last create() error */

@@ -1,0 +1,180 @@
+"""Segmented compiled lattices (w-fsa_b200/csrc/lattice.cpp: compile_segments / compile_corpus_segmented)
+checked on the CPU.  The arrays the device kernels kr_regions and ks_strings read
+(w-fsa_b200/csrc/kernels_seg.cuh) are interpreted here word by word with the same recurrences and must
+reproduce the oracle's per-string log q and expected edge counts.  This pins bridges, region words,
+type merging, the group layouts and the constant accumulators without a GPU."""
+import numpy as np
+import pytest
+
+import wfsa_b200 as W
+from helpers import good_cases
+from oracle import oracle as O
+from test_cpu_lattice import compile_string
+from wfsa_b200 import synth
+
+EDGE, FIN, FIRST_IN, LAST_OUT = 1 << 31, 1 << 30, 1 << 29, 1 << 28
+FX = float(2 ** 40)
+
+
+def region_fwdbwd(col, aw, big):
+    """(log q, {arc: posterior}) of one region given as its column of words."""
+    pool = np.full(16, np.nan)
+    pool[0] = 1.0
+    xs = np.zeros(len(col))
+    q, last, n_edges = None, None, 0
+    for i, w in enumerate(col):
+        w = int(w)
+        if big and i % 16 == 15:
+            assert not (w & (EDGE | FIN))
+            for s in range(16):
+                if w >> s & 1:
+                    assert np.isfinite(pool[s]), "live slot without a value"
+            continue
+        if w & EDGE:
+            src, dst, arc = (w >> 19) & 15, (w >> 23) & 15, w & 0x7fff
+            assert src != dst and np.isfinite(pool[src])
+            assert bool(w & FIRST_IN) == (not np.isfinite(pool[dst])), "first_in flag must match slot liveness"
+            xs[i] = pool[src] * aw[arc]
+            pool[dst] = xs[i] if w & FIRST_IN else pool[dst] + xs[i]
+            if w & LAST_OUT:
+                pool[src] = np.nan                            # the slot is free again
+            last = dst
+            n_edges += 1
+        elif w & FIN:
+            assert big
+            q = pool[w & 15]
+            assert (w & 15) == last
+        else:
+            assert w == 0, "padding must be zero"
+    if not big:
+        q = pool[last]
+    assert n_edges >= 2 and (big == (n_edges > 16))
+    beta = np.full(16, np.nan)
+    beta[last] = 1.0
+    post = {}
+    for i in range(len(col) - 1, -1, -1):
+        w = int(col[i])
+        if (big and i % 16 == 15) or not (w & EDGE):
+            continue
+        src, dst, arc = (w >> 19) & 15, (w >> 23) & 15, w & 0x7fff
+        c = aw[arc] * beta[dst]
+        beta[src] = c if w & LAST_OUT else beta[src] + c
+        post[arc] = post.get(arc, 0.0) + xs[i] * beta[dst] / q
+    assert abs(beta[0] / q - 1.0) < 1e-12, "beta(entry) must equal q"
+    return np.log(q), post
+
+
+def interpret(seg, aw, n_arcs):
+    """lq per type slot, acc per arc (float), log q per string id."""
+    rgoff, rgrows, W_ = seg["rgoff"], seg["rgrows"], seg["typeW"]
+    n_rg = len(rgrows)
+    lq = np.zeros(n_rg * 32 + 1)
+    acc = seg["const_acc"].astype(np.float64) / FX
+    seen = set()
+    for g in range(n_rg):
+        rows = int(rgrows[g])
+        assert rows in (4, 8, 12, 16) or (rows > 16 and rows % 16 == 0)
+        block = seg["rwords"][rgoff[g]:rgoff[g] + rows * 32].reshape(rows, 32)
+        for l in range(32):
+            col = block[:, l]
+            if not (int(col[0]) & EDGE):
+                assert W_[g * 32 + l] == 0.0 and not col.any()
+                continue
+            key = col.tobytes()
+            assert key not in seen, "identical regions must be merged into one type"
+            seen.add(key)
+            assert W_[g * 32 + l] > 0.0
+            lq[g * 32 + l], post = region_fwdbwd(col, aw, rows > 16)
+            for arc, v in post.items():
+                acc[arc] += W_[g * 32 + l] * v
+    sgoff, sgref, ksid, kp = seg["sgoff"], seg["sgref"], seg["ksid"], seg["kp"]
+    logq = {}
+    with np.errstate(divide="ignore"):
+        logaw = np.append(np.log(aw), 0.0)
+    for g in range(len(sgref)):
+        rows = int((sgoff[g + 1] - sgoff[g]) // 32)
+        block = seg["swords"][sgoff[g]:sgoff[g + 1]].reshape(rows, 32)
+        assert (rows - sgref[g]) % 4 == 0
+        for l in range(32):
+            sid = int(ksid[g * 32 + l])
+            refs = block[:sgref[g], l].astype(np.int64)
+            pairs = block[sgref[g]:, l]
+            arcs = np.concatenate([pairs & 0xffff, pairs >> 16]).astype(np.int64)
+            assert arcs.max(initial=0) <= n_arcs and refs.max(initial=0) <= n_rg * 32
+            if sid < 0:
+                assert (refs == n_rg * 32).all() and (arcs == n_arcs).all() and kp[g * 32 + l] == 0.0
+                continue
+            logq[sid] = logaw[arcs].sum() + lq[refs].sum()
+    return lq, acc, logq
+
+
+def check(low, trimmed, x, n_slots=16):
+    ltw, lew = low.edge_logweights(x, trimmed)
+    pc, olq, oee = O.dp_eval(low, ltw, lew, want_counts=True)
+    _, _, tid, eid = compile_string(low, trimmed, np.zeros(0, dtype=np.int32))
+    with np.errstate(divide="ignore"):
+        aw = np.exp(ltw[tid] + np.where(eid >= 0, lew[np.maximum(eid, 0)], 0.0))
+    seg = W.segmented_compile(low, trimmed, n_slots=n_slots, fx_scale=FX)
+    n_strings = len(low.offsets) - 1
+    handled = set(int(s) for s in seg["ksid"] if s >= 0)
+    assert handled.isdisjoint(seg["overflow"]) and handled.isdisjoint(seg["rejected"])
+    assert len(handled) + len(seg["overflow"]) + len(seg["rejected"]) == n_strings
+    for s in seg["rejected"]:
+        assert pc[s] == 0 or not np.isfinite(olq[s])
+    lq, acc, logq = interpret(seg, aw, len(tid))
+    for s, v in logq.items():
+        assert abs(v - olq[s]) <= 1e-12 * max(1.0, abs(olq[s])), (s, v, olq[s])
+    st = seg["stats"]
+    assert st[0] == np.count_nonzero(seg["typeW"]) and st[5] == len(handled) and st[0] <= st[1]
+    # expected edge counts of the handled strings only
+    ee = np.zeros(low.n_trans + low.n_emis)
+    np.add.at(ee, tid, acc)
+    np.add.at(ee, low.n_trans + eid[eid >= 0], acc[eid >= 0])
+    return seg, ee, oee, olq, handled
+
+
+@pytest.mark.parametrize("case", good_cases(("fixtures", "random")), ids=lambda c: c["name"])
+def test_segmented_form_matches_oracle(case):
+    d = W.parse(case["fsa_text"], case["corpus_text"])
+    low = W.Lowered(d)
+    zt, ze = np.zeros(low.n_trans), np.zeros(low.n_emis)
+    _, _, ee0 = O.dp_eval(low, zt, ze, want_counts=True)
+    trimmed, n, _ = O.trim(low, ee0 > 0)
+    x = np.random.RandomState(5).normal(-1.0, 0.7, size=n)
+    seg, ee, oee, _, handled = check(low, trimmed, x)
+    assert len(seg["overflow"]) == 0
+    # the 2^-40 quantum of the constant accumulators bounds the absolute error per bridge
+    assert np.allclose(ee, oee, rtol=1e-10, atol=1e-9)
+
+
+def test_config4_shape_bridges_regions_and_type_merging():
+    model = synth.make_model(64, 16, 4, 3, seed=11)
+    low = model.lowered()
+    offs, toks, w = model.corpus(600, 8, 60, seed=12)
+    low.set_tokens(offs, toks, w / w.sum())
+    zt, ze = np.zeros(low.n_trans), np.zeros(low.n_emis)
+    _, _, ee0 = O.dp_eval(low, zt, ze)
+    trimmed, n, _ = O.trim(low, ee0 > 0)
+    x = np.random.RandomState(6).normal(-1.0, 0.5, size=n)
+    seg, ee, oee, _, handled = check(low, trimmed, x)
+    st = seg["stats"]
+    assert len(seg["overflow"]) == 0 and len(handled) == 600
+    assert st[4] > 0 and st[1] > st[0] > 0, "expected bridges and merged region types"
+    assert (seg["rgrows"] > 16).any() and (seg["rgrows"] <= 16).any(), "expected small and big regions"
+    assert np.allclose(ee, oee, rtol=1e-10, atol=1e-9)
+    # a pool of 2 slots cannot hold an ambiguous region: such strings are reported, never mis-compiled
+    seg2, _, _, _, handled2 = check(low, trimmed, x, n_slots=2)
+    assert len(seg2["overflow"]) > 0 and len(handled2) < 600
+
+
+def test_trimmed_arcs_are_removed_from_segments():
+    model = synth.make_model(32, 8, 3, 2, seed=3)
+    low = model.lowered()
+    offs, toks, w = model.corpus(80, 5, 20, seed=4)
+    low.set_tokens(offs, toks, w / w.sum())
+    trimmed = np.arange(low.n_raw, dtype=np.int32)
+    trimmed[::5] = -2                                     # weight 0: some strings lose paths or all of them
+    x = np.random.RandomState(1).normal(-1.0, 0.5, size=low.n_raw)
+    seg, _, _, olq, handled = check(low, trimmed, x)
+    for s in range(80):
+        assert (s in handled) == bool(np.isfinite(olq[s]))

@@ -195,7 +195,7 @@ def medium():
     return model, low
 
 
-@pytest.mark.parametrize("kernel,accum,variant", [(5, 0, 0), (5, 0, 4 << 16), (5, 0, 4), (4, 0, 0), (4, 0, 4 << 16), (1, 1, 0), (1, 1, 1), (1, 2, 0), (2, 0, 0), (3, 0, 0)])
+@pytest.mark.parametrize("kernel,accum,variant", [(6, 0, 0), (6, 0, 4 << 16), (5, 0, 0), (5, 0, 4 << 16), (5, 0, 4), (4, 0, 0), (4, 0, 4 << 16), (1, 1, 0), (1, 1, 1), (1, 2, 0), (2, 0, 0), (3, 0, 0)])
 def test_kernels_match_cpu_oracle(medium, kernel, accum, variant):
     model, low = medium
     count = 3000 if kernel != 3 else 300          # the generic kernel is the slow, dense one
@@ -225,6 +225,13 @@ def test_kernels_match_cpu_oracle(medium, kernel, accum, variant):
         assert i["n_active_strings"] == int(rec.sum()) and i["lattice_edges"] > 0
         assert (i["n_overflow_strings"] > 0) == (variant == 4 << 16)
         assert (i["lattice_bridge_edges"] > 0) == (variant != 4)
+    if kernel == 6:
+        # segmented form: bridges + merged region types; with 4 pool slots some regions do not fit and their
+        # strings go to the warp-per-string kernel
+        i = dev.info()
+        assert i["n_active_strings"] == int(rec.sum()) and i["lattice_bridge_edges"] > 0
+        assert 0 < i["seg_types"] <= i["seg_region_instances"] and i["seg_type_edges"] <= i["seg_region_edges"]
+        assert (i["n_overflow_strings"] > 0) == (variant == 4 << 16)
     if kernel == 4:
         # K = 12 (default) handles every string of this corpus on the thread-per-string kernel;
         # K = 4 pushes the strings whose active set exceeds 4 states onto the warp-per-string kernel
@@ -270,7 +277,7 @@ def test_edge_cases():
     words = [("", 2.0), ("x", 1.0), ("xy", 1.0), ("zz", 1.0), ("xq", 3.0), ("yyyy", 1.0)]
     d = W.parse(fsa, "\nx 1\n")
     low = W.Lowered(d, corpus=words)
-    for kernel in (5, 4, 1, 2, 3):
+    for kernel in (6, 5, 4, 1, 2, 3):
         dev, rec, pc, trimmed, n = build_device(low, force_kernel=kernel)
         assert rec.tolist() == [1, 1, 1, 0, 0, 1] and pc.tolist() == [1, 1, 1, 0, 0, 1]
         x = np.array([-0.4, -1.1, -0.2, -0.6, -0.8, -1.3])[:n]
@@ -299,7 +306,7 @@ def test_long_strings_need_rescaling():
     low = model.lowered()
     offs, toks, w = model.corpus(40, 3500, 4000, seed=22)
     low.set_tokens(offs, toks, w / w.sum())
-    for kernel in (5, 4, 1, 2):
+    for kernel in (6, 5, 4, 1, 2):
         dev, rec, pc, trimmed, n = build_device(low, force_kernel=kernel)
         assert rec.all()
         if kernel == 5:          # streams of up to 8192 words stay on the compiled-lattice kernel
@@ -344,7 +351,7 @@ def test_full_size_config4_properties():
     p = w / w.sum()
     low.set_tokens(offs, toks, p)
     dev, rec, pc, trimmed, n = build_device(low)
-    assert rec.all() and dev.info()["kernel"] == 5 and dev.info()["n_overflow_strings"] == 0
+    assert rec.all() and dev.info()["kernel"] == 6 and dev.info()["n_overflow_strings"] == 0
     assert n == low.n_raw            # nothing is trimmed at this size
     x = np.zeros(n)
     ll, logq, grad = dev.eval(x)

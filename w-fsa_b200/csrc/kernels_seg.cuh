@@ -1,0 +1,283 @@
+// w-fsa_b200/csrc/kernels_seg.cuh -- sm_100a kernels over the SEGMENTED compiled lattices (lattice.hpp).
+//
+// Every string's trimmed lattice is cut at the nodes all of its accepting paths share.  Between two
+// cuts lies either one edge (a bridge) or a small DAG (a region); path weights factor over segments:
+//     log q_s = sum_{bridges of s} log w[arc]  +  sum_{regions of s} log q_region
+//     E_s[count(arc)] = [arc is a bridge of s]  +  posterior of the arc inside its region
+// so one evaluation (Learner::ComputeModeledProbs + ComputeObjective + ComputeGrad,
+// /root/reference/src/Learner.cpp:515-553, src/QuasiNewtonLearner.cpp:93-125) becomes
+//   KR  kr_regions : forward-backward over every distinct region TYPE once (thread per type):
+//                    lq[type] = log q_type,  acc[arc] += W_type * posterior   (64-bit fixed-point REDs)
+//   KS  ks_strings : thread per string: log q_s = sum of log w over its bridge arcs (16-bit ids, table in
+//                    shared memory) + sum of lq[type] over its regions; loglik += p_s log q_s
+// and the bridges' part of the gradient is a constant computed when the lattices are compiled.
+#pragma once
+#include "kernels.cuh"
+
+namespace wfsa {
+
+struct KRParams {
+    const double* __restrict__ aw;        // [n_arcs] a(u,v) * b(v,e)
+    const uint32_t* __restrict__ words;   // word j of lane l of group g at goff[g] + j*32 + l
+    const int64_t* __restrict__ goff;     // [n_groups+1]
+    const int32_t* __restrict__ grows;    // [n_groups] 4/8/12/16 = small region class, else big (multiple of 16)
+    const double* __restrict__ typeW;     // [n_groups*32]
+    double* lq;                           // [n_groups*32 + 1] log q per type (last = dummy, stays 0)
+    long long n_groups;
+    double* xs;                           // big regions: per warp [xs_rows][32]
+    size_t xs_rows;
+    unsigned int* counter;                // dynamic group scheduler
+    unsigned long long* acc;              // [replicas][n_arcs]
+    double fx_scale;
+    int n_arcs, replicas;
+};
+
+// One small region per thread, NE word rows, everything in registers except the pool.
+template <int NE, int ACC>
+__device__ __forceinline__ void kr_small(const KRParams& P, const double* aw, double* pool, int NT, long long g, int lane,
+                                         unsigned long long* acc_g)
+{
+    const uint32_t* wp = P.words + P.goff[g] + lane;
+    uint32_t w[NE];
+#pragma unroll
+    for (int j = 0; j < NE; ++j) w[j] = __ldcs(wp + (size_t)j * 32);
+    const double W = P.typeW[g * 32 + lane];
+    double xs[NE];
+    pool[0] = 1.0;                                            // the entry node owns slot 0
+    int last = 0;
+#pragma unroll
+    for (int j = 0; j < NE; ++j) {
+        const uint32_t wj = w[j];
+        if (wj & kLEdge) {
+            const int src = (wj >> 19) & 15, dst = (wj >> 23) & 15, arc = wj & 0x7fff;
+            const double xv = pool[src * NT] * aw[arc];
+            xs[j] = xv;
+            double* pd = pool + dst * NT;
+            *pd = (wj & kLFirstIn) ? xv : *pd + xv;
+            last = dst;
+        }
+    }
+    const double q = pool[last * NT];
+    const bool ok = (w[0] & kLEdge) && q > 0.0 && isfinite(q);
+    if (w[0] & kLEdge) P.lq[g * 32 + lane] = ok ? log(q) : -INFINITY;
+    const double sc = ok ? W * P.fx_scale / q : 0.0;
+    pool[last * NT] = 1.0;
+#pragma unroll
+    for (int j = NE - 1; j >= 0; --j) {
+        const uint32_t wj = w[j];
+        if (wj & kLEdge) {
+            const int src = (wj >> 19) & 15, dst = (wj >> 23) & 15, arc = wj & 0x7fff;
+            const double bd = pool[dst * NT];
+            const double c = aw[arc] * bd;
+            double* psrc = pool + src * NT;
+            *psrc = (wj & kLLastOut) ? c : *psrc + c;
+            if (ACC != ACC_NONE) {
+                const long long v = __double2ll_rn(xs[j] * bd * sc);
+                if (v) atomicAdd(acc_g + arc, (unsigned long long)v);
+            }
+        }
+    }
+}
+
+// One big region per thread: the KL stream loop (CHECK words rescale, x values on a per-warp stack).
+template <int ACC>
+__device__ __forceinline__ void kr_big(const KRParams& P, const double* aw, double* pool, int NT, long long g, int lane,
+                                       double* xs, unsigned long long* acc_g)
+{
+    const long long o = P.goff[g];
+    const int nw = (int)((P.goff[g + 1] - o) >> 5);
+    const uint32_t* wp = P.words + o + lane;
+    const double W = P.typeW[g * 32 + lane];
+    pool[0] = 1.0;
+    int E = 0, EQ = 0;
+    double qh = 0.0;
+    bool any = false;
+    for (int i0 = 0; i0 < nw; i0 += 8) {
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = __ldcs(wp + (size_t)(i0 + j) * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t wj = w[j];
+            if (j == 7 && (i0 & 8)) {                         // CHECK word (same index in all lanes)
+                const uint32_t m0 = wj & 0xffffu;
+                if (m0) {
+                    int emax = 0;
+                    for (uint32_t m = m0; m; m &= m - 1) emax = max(emax, pool_exp(pool + (__ffs(m) - 1) * NT));
+                    reinterpret_cast<long long*>(xs)[(size_t)(i0 + j) * 32] = E;
+                    if (emax != 0 && (emax < 1023 - kLBand || emax > 1023 + kLBand)) {
+                        const int shift = 1023 - emax;
+                        for (uint32_t m = m0; m; m &= m - 1) { double* q = pool + (__ffs(m) - 1) * NT; *q = scalbn(*q, shift); }
+                        E -= shift;
+                    }
+                }
+            } else if (wj & kLEdge) {
+                const int src = (wj >> 19) & 15, dst = (wj >> 23) & 15, arc = wj & 0x7fff;
+                const double xv = pool[src * NT] * aw[arc];
+                xs[(size_t)(i0 + j) * 32] = xv;
+                double* pd = pool + dst * NT;
+                *pd = (wj & kLFirstIn) ? xv : *pd + xv;
+                any = true;
+            } else if (wj & kLFin) {
+                qh = pool[(wj & 15) * NT];
+                EQ = E;
+            }
+        }
+    }
+    const bool ok = any && qh > 0.0 && isfinite(qh);
+    if (any) P.lq[g * 32 + lane] = ok ? log(qh) + (double)EQ * 0.69314718055994530942 : -INFINITY;
+    const double sc0 = ok ? W * P.fx_scale / qh : 0.0;
+    double sc = sc0;
+    int F = 0;
+    for (int i0 = nw - 8; i0 >= 0; i0 -= 8) {
+        uint32_t w[8];
+        double xv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = __ldcs(wp + (size_t)(i0 + j) * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool chk = (j == 7 && (i0 & 8));
+            const bool need = chk ? (w[j] & 0xffffu) != 0 : (w[j] & kLEdge) != 0;
+            xv[j] = need ? xs[(size_t)(i0 + j) * 32] : 0.0;
+        }
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+            const uint32_t wj = w[j];
+            if (j == 7 && (i0 & 8)) {
+                const uint32_t m0 = wj & 0xffffu;
+                if (m0) {
+                    const int Et = (int)__double_as_longlong(xv[j]);
+                    int emax = 0;
+                    for (uint32_t m = m0; m; m &= m - 1) emax = max(emax, pool_exp(pool + (__ffs(m) - 1) * NT));
+                    if (emax != 0 && (emax < 1023 - kLBand || emax > 1023 + kLBand)) {
+                        const int shift = 1023 - emax;
+                        for (uint32_t m = m0; m; m &= m - 1) { double* q = pool + (__ffs(m) - 1) * NT; *q = scalbn(*q, shift); }
+                        F -= shift;
+                    }
+                    sc = scalbn(sc0, Et + F - EQ);
+                }
+            } else if (wj & kLEdge) {
+                const int src = (wj >> 19) & 15, dst = (wj >> 23) & 15, arc = wj & 0x7fff;
+                const double bd = pool[dst * NT];
+                const double c = aw[arc] * bd;
+                double* psrc = pool + src * NT;
+                *psrc = (wj & kLLastOut) ? c : *psrc + c;
+                if (ACC != ACC_NONE && ok) {
+                    const long long v = __double2ll_rn(xv[j] * bd * sc);
+                    if (v) atomicAdd(acc_g + arc, (unsigned long long)v);
+                }
+            } else if (wj & kLFin) {
+                pool[(wj & 15) * NT] = 1.0;
+            }
+        }
+    }
+}
+
+template <int ACC>
+__global__ void __launch_bounds__(1024, 1) kr_regions(const KRParams P)
+{
+    extern __shared__ unsigned long long smem[];
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
+    double* aw = reinterpret_cast<double*>(smem);
+    double* pool = aw + P.n_arcs + tid;                       // slot s of this thread at pool[s*NT]
+    for (int i = tid; i < P.n_arcs; i += NT) aw[i] = P.aw[i];
+    __syncthreads();
+    const long long gwarp = ((long long)blockIdx.x * NT + tid) >> 5;
+    double* const xs = P.xs + (size_t)gwarp * P.xs_rows * 32 + lane;
+    unsigned long long* const acc_g = P.acc + (size_t)(blockIdx.x % P.replicas) * (size_t)P.n_arcs;
+    for (;;) {
+        long long g = 0;
+        if (lane == 0) g = (long long)atomicAdd(P.counter, 1u);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= P.n_groups) break;
+        const int rows = P.grows[g];
+        switch (rows) {
+            case 4: kr_small<4, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
+            case 8: kr_small<8, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
+            case 12: kr_small<12, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
+            case 16: kr_small<16, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
+            default: kr_big<ACC>(P, aw, pool, NT, g, lane, xs, acc_g); break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+struct KSParams {
+    const double* __restrict__ logaw;     // [n_arcs] log weight of every combined arc
+    const uint32_t* __restrict__ words;   // row r of lane l of group g at goff[g] + r*32 + l
+    const int64_t* __restrict__ goff;     // [n_groups+1]
+    const int32_t* __restrict__ gref;     // [n_groups] leading rows that hold region type ids
+    const double* __restrict__ lq;        // log q per region type (written by kr_regions)
+    const double* __restrict__ p;         // [n_groups*32] p_s in group order (0 = padding lane)
+    double* logq;                         // [n_groups*32] log q_s in group order
+    long long n_groups;
+    unsigned int* counter;
+    unsigned long long* red;              // red[0] fixed-point loglik, red[1] non-finite strings
+    double ll_scale;
+    int n_arcs;
+};
+
+__global__ void __launch_bounds__(512, 2) ks_strings(const KSParams P)
+{
+    extern __shared__ unsigned long long smem[];
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
+    double* tab = reinterpret_cast<double*>(smem);            // [n_arcs + 1]; id n_arcs (padding) -> 0
+    for (int i = tid; i <= P.n_arcs; i += NT) tab[i] = i < P.n_arcs ? P.logaw[i] : 0.0;
+    __syncthreads();
+    long long ll_fx = 0;
+    unsigned long long bad = 0;
+    for (;;) {
+        long long g = 0;
+        if (lane == 0) g = (long long)atomicAdd(P.counter, 1u);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= P.n_groups) break;
+        const long long o = P.goff[g];
+        const int rows = (int)((P.goff[g + 1] - o) >> 5), nref = P.gref[g];
+        const uint32_t* wp = P.words + o + lane;
+        const double ps = P.p[g * 32 + lane];
+        double r = 0.0;
+        for (int i = 0; i < nref; ++i) r += P.lq[__ldcs(wp + (size_t)i * 32)];
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        for (int i = nref; i < rows; i += 4) {
+            const uint32_t a = __ldcs(wp + (size_t)i * 32), b = __ldcs(wp + (size_t)(i + 1) * 32);
+            const uint32_t c = __ldcs(wp + (size_t)(i + 2) * 32), d = __ldcs(wp + (size_t)(i + 3) * 32);
+            s0 += tab[a & 0xffffu]; s1 += tab[a >> 16];
+            s2 += tab[b & 0xffffu]; s3 += tab[b >> 16];
+            s0 += tab[c & 0xffffu]; s1 += tab[c >> 16];
+            s2 += tab[d & 0xffffu]; s3 += tab[d >> 16];
+        }
+        const double lqs = ((s0 + s1) + (s2 + s3)) + r;
+        if (ps != 0.0) {
+            P.logq[g * 32 + lane] = lqs;
+            if (isfinite(lqs)) ll_fx += __double2ll_rn(ps * lqs * P.ll_scale);
+            else bad++;
+        }
+    }
+    for (int o = 16; o; o >>= 1) { ll_fx += __shfl_xor_sync(FULL, ll_fx, o); bad += __shfl_xor_sync(FULL, bad, o); }
+    if (lane == 0) {
+        if (ll_fx) atomicAdd(P.red, (unsigned long long)ll_fx);
+        if (bad) atomicAdd(P.red + 1, bad);
+    }
+}
+
+// log q of the strings of the segmented path, group order -> string id order
+__global__ void k_scatter_logq(long long n, const int32_t* __restrict__ ksid, const double* __restrict__ logq_k, double* logq)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && ksid[i] >= 0) logq[ksid[i]] = logq_k[i];
+}
+
+// per combined arc: aw = a(u,v) * b(v,e) and its logarithm, straight from x
+__global__ void k_arc_weights_log(int n_arcs, const int32_t* __restrict__ arc_tid, const int32_t* __restrict__ arc_eid,
+                                  const int32_t* __restrict__ trans_tp, const int32_t* __restrict__ emis_tp,
+                                  const double* __restrict__ x, double* aw, double* logaw)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_arcs) {
+        const double l = logweight_of(trans_tp[arc_tid[i]], x, 0) + (arc_eid[i] < 0 ? 0.0 : logweight_of(emis_tp[arc_eid[i]], x, 0));
+        logaw[i] = l;
+        aw[i] = exp(l);
+    }
+}
+
+}  // namespace wfsa

@@ -2,7 +2,9 @@
 #include "lattice.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstring>
 #include <numeric>
 #include <thread>
 
@@ -59,8 +61,11 @@ void build_lattice_arcs(const HostFsa& f, const GenericLayout& g, LatticeArcs& A
     }
 }
 
-int compile_lattice(const HostFsa& f, const LatticeArcs& A, const uint8_t* alive, const int32_t* tok, int len,
-                    int n_slots, LatticeScratch& S, std::vector<uint32_t>& words, std::vector<int32_t>& bridge_arcs)
+// Forward reachability + co-reachability of one string's lattice.  On return S.esrc/edst/earc hold every
+// forward-reachable edge in a topological order (grouped by source node), S.coreach marks the nodes that
+// reach the end node.  Returns the end node id, or -1 when the string has no accepting path.
+static int build_and_trim(const HostFsa& f, const LatticeArcs& A, const uint8_t* alive, const int32_t* tok, int len,
+                          LatticeScratch& S)
 {
     const int NSt = f.n_states, NS = f.n_sym;
     const size_t need = (size_t)(len + 1) * NSt;
@@ -139,12 +144,21 @@ int compile_lattice(const HostFsa& f, const LatticeArcs& A, const uint8_t* alive
     // reset the scratch index for the next string
     for (int n = 0; n < n_nodes; ++n) if (S.npos[n] <= len) S.node_of[(size_t)S.npos[n] * NSt + S.nstate[n]] = -1;
     for (int pos = 0; pos <= len; ++pos) S.bucket[pos].clear();
-    if (end_node < 0) return 0;
+    if (end_node < 0) return -1;
     // ---- co-reachability (edges are ordered by source in topological order => reverse sweep)
     S.coreach.assign(n_nodes, 0);
     S.coreach[end_node] = 1;
     for (int e = n_e - 1; e >= 0; --e) if (S.coreach[S.edst[e]]) S.coreach[S.esrc[e]] = 1;
-    if (!S.coreach[0]) return 0;
+    if (!S.coreach[0]) return -1;
+    return end_node;
+}
+
+int compile_lattice(const HostFsa& f, const LatticeArcs& A, const uint8_t* alive, const int32_t* tok, int len,
+                    int n_slots, LatticeScratch& S, std::vector<uint32_t>& words, std::vector<int32_t>& bridge_arcs)
+{
+    const int end_node = build_and_trim(f, A, alive, tok, len, S);
+    if (end_node < 0) return 0;
+    const int n_nodes = (int)S.npos.size(), n_e = (int)S.esrc.size();
     S.nout.assign(n_nodes, 0);
     S.per_pos.assign(len + 2, 0);
     for (int n = 0; n < n_nodes; ++n) if (S.coreach[n]) S.per_pos[S.npos[n]]++;
@@ -283,6 +297,301 @@ void compile_corpus(const HostFsa& f, const LatticeArcs& A, const uint8_t* alive
         fill(0);
         for (auto& x : th) x.join();
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Segmented form
+// ---------------------------------------------------------------------------------------------
+int compile_segments(const HostFsa& f, const LatticeArcs& A, const uint8_t* alive, const int32_t* tok, int len,
+                     int n_slots, LatticeScratch& S, SegString& out)
+{
+    out.bridges.clear(); out.rwords.clear(); out.roff.assign(1, 0);
+    out.status = 0;
+    const int end_node = build_and_trim(f, A, alive, tok, len, S);
+    if (end_node < 0) return 0;
+    const int n_nodes = (int)S.npos.size(), n_e = (int)S.esrc.size();
+    // kept edges (both ends on an accepting path) and the topological index of their nodes
+    S.kept.clear();
+    S.topo.assign(n_nodes, -1);
+    int nt = 0;
+    for (int e = 0; e < n_e; ++e) {
+        if (!S.coreach[S.edst[e]]) continue;
+        S.kept.push_back(e);
+        if (S.topo[S.esrc[e]] < 0) S.topo[S.esrc[e]] = nt++;
+    }
+    S.topo[end_node] = nt;
+    S.nslot.assign(n_nodes, -1);
+    const int nk = (int)S.kept.size();
+    // one segment = kept edges [b, e): all edges whose source lies between two consecutive cut nodes
+    auto emit_segment = [&](int b, int e) -> bool {
+        if (e - b == 1) { out.bridges.push_back((uint16_t)S.earc[S.kept[b]]); return true; }
+        const bool big = e - b > kSegSmallMax;
+        const size_t base = out.rwords.size();
+        uint32_t free_mask = n_slots >= 32 ? 0xffffffffu : ((1u << n_slots) - 1u), live = 0;
+        auto alloc = [&]() -> int {
+            if (!free_mask) return -1;
+            const int sl = __builtin_ctz(free_mask);
+            free_mask &= free_mask - 1; live |= 1u << sl;
+            return sl;
+        };
+        auto check_word = [&]() {
+            if (big && ((out.rwords.size() - base) & (kCheckEvery - 1)) == kCheckEvery - 1) out.rwords.push_back(live & 0xffffu);
+        };
+        int cur_src = -1, exit_slot = -1;
+        size_t last_edge = 0;
+        S.nslot[S.esrc[S.kept[b]]] = alloc();              // the entry node owns slot 0
+        for (int i = b; i < e; ++i) {
+            const int ed = S.kept[i], sN = S.esrc[ed], dN = S.edst[ed];
+            if (sN != cur_src) {
+                if (cur_src >= 0) {
+                    out.rwords[last_edge] |= kLatLastOut;
+                    const int sl = S.nslot[cur_src];
+                    free_mask |= 1u << sl; live &= ~(1u << sl);
+                }
+                cur_src = sN;
+            }
+            check_word();
+            uint32_t w = kLatEdge | (uint32_t)S.earc[ed];
+            if (S.nslot[dN] < 0) {
+                S.nslot[dN] = alloc();
+                if (S.nslot[dN] < 0) return false;
+                w |= kLatFirstIn;
+            }
+            exit_slot = S.nslot[dN];
+            w |= (uint32_t)S.nslot[dN] << kLatDstShift | (uint32_t)S.nslot[sN] << kLatSrcShift;
+            last_edge = out.rwords.size();
+            out.rwords.push_back(w);
+        }
+        out.rwords[last_edge] |= kLatLastOut;
+        { const int sl = S.nslot[cur_src]; free_mask |= 1u << sl; live &= ~(1u << sl); }
+        if (big) { check_word(); out.rwords.push_back(kLatFin | (uint32_t)exit_slot); }
+        // slots are region-local: forget them (the exit node is the entry of the next segment)
+        for (int i = b; i < e; ++i) { S.nslot[S.esrc[S.kept[i]]] = -1; S.nslot[S.edst[S.kept[i]]] = -1; }
+        out.roff.push_back((int32_t)out.rwords.size());
+        return true;
+    };
+    int seg_begin = 0, maxdst = 0, cur = -1;
+    for (int i = 0; i < nk; ++i) {
+        const int ed = S.kept[i], sN = S.esrc[ed];
+        if (sN != cur) {
+            cur = sN;
+            if (S.topo[sN] == maxdst && i > seg_begin) {       // sN is a cut node: close the segment before it
+                if (!emit_segment(seg_begin, i)) { out.status = -1; return -1; }
+                seg_begin = i;
+            }
+        }
+        maxdst = std::max(maxdst, S.topo[S.edst[ed]]);
+    }
+    if (nk > seg_begin && !emit_segment(seg_begin, nk)) { out.status = -1; return -1; }
+    out.status = 1;
+    return 1;
+}
+
+namespace {
+inline uint64_t fnv1a(const uint32_t* w, size_t n)
+{
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+    return h ^ (h >> 29);
+}
+}  // namespace
+
+void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint8_t* alive, const int32_t* tokens,
+                              const int64_t* offs, const double* p, const std::vector<int32_t>& ids, int n_slots,
+                              double fx_scale, SegmentedCorpus& out)
+{
+    const auto t_begin = std::chrono::steady_clock::now();
+    out = SegmentedCorpus();
+    const size_t n = ids.size();
+    out.const_acc.assign(A.n_arcs, 0);
+    unsigned hw = std::thread::hardware_concurrency();
+    const int T = (int)std::max<size_t>(1, std::min<size_t>({(size_t)(hw ? hw : 4), (size_t)64, n / 256 + 1}));
+    // ---- 1. per-string compilation, strings i = t, t+T, ... on thread t
+    struct Local {
+        std::vector<uint16_t> bridges; std::vector<int64_t> boff;      // bridges of string j at [boff[j], boff[j+1])
+        std::vector<uint32_t> rwords;                                   // region words
+        std::vector<int64_t> rbeg; std::vector<int32_t> rlen;           // per region
+        std::vector<uint64_t> rhash;
+        std::vector<int64_t> sreg;                                      // regions of string j at [sreg[j], sreg[j+1])
+        std::vector<int8_t> status;
+        std::vector<long long> cacc;
+    };
+    std::vector<Local> loc(T);
+    auto work = [&](int t) {
+        Local& L = loc[t];
+        LatticeScratch S; SegString seg;
+        L.cacc.assign(A.n_arcs, 0);
+        L.boff.push_back(0); L.sreg.push_back(0);
+        for (size_t i = t; i < n; i += T) {
+            const int32_t sid = ids[i];
+            const int len = (int)(offs[sid + 1] - offs[sid]);
+            const int rc = compile_segments(f, A, alive, tokens + offs[sid], len, n_slots, S, seg);
+            L.status.push_back((int8_t)rc);
+            if (rc == 1) {
+                const long long c = llrint(p[sid] * fx_scale);
+                for (uint16_t a : seg.bridges) L.cacc[a] += c;
+                L.bridges.insert(L.bridges.end(), seg.bridges.begin(), seg.bridges.end());
+                for (size_t r = 0; r + 1 < seg.roff.size(); ++r) {
+                    const int b = seg.roff[r], e = seg.roff[r + 1];
+                    L.rbeg.push_back((int64_t)L.rwords.size()); L.rlen.push_back(e - b);
+                    L.rhash.push_back(fnv1a(seg.rwords.data() + b, (size_t)(e - b)));
+                    L.rwords.insert(L.rwords.end(), seg.rwords.begin() + b, seg.rwords.begin() + e);
+                }
+            }
+            L.boff.push_back((int64_t)L.bridges.size());
+            L.sreg.push_back((int64_t)L.rbeg.size());
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
+    for (int t = 0; t < T; ++t)
+        for (int a = 0; a < A.n_arcs; ++a) out.const_acc[a] += loc[t].cacc[a];
+    // ---- 2. merge identical regions into types, strings visited in `ids` order (deterministic weights)
+    struct Type { int t; int64_t beg; int32_t len; double W; };
+    std::vector<Type> types;
+    std::vector<int32_t> bucket_head((size_t)1 << 20, -1);               // open hashing on the low hash bits
+    std::vector<int32_t> next_in_bucket;
+    std::vector<uint64_t> thash;
+    std::vector<std::vector<int32_t>> reg_type(T);                        // type of every region, per thread
+    for (int t = 0; t < T; ++t) reg_type[t].resize(loc[t].rbeg.size());
+    std::vector<int64_t> ok;                                              // indices into ids
+    for (size_t i = 0; i < n; ++i) {
+        const Local& L = loc[i % T];
+        const size_t j = i / T;
+        const int st = L.status[j];
+        if (st < 0) { out.overflow.push_back(ids[i]); continue; }
+        if (st == 0) { out.rejected.push_back(ids[i]); continue; }
+        ok.push_back((int64_t)i);
+        const double ps = p[ids[i]];
+        out.n_bridge += L.boff[j + 1] - L.boff[j];
+        for (int64_t r = L.sreg[j]; r < L.sreg[j + 1]; ++r) {
+            const uint64_t h = L.rhash[r];
+            const uint32_t* w = L.rwords.data() + L.rbeg[r];
+            const int32_t len = L.rlen[r];
+            int32_t& head = bucket_head[h & (bucket_head.size() - 1)];
+            int32_t ty = head;
+            for (; ty >= 0; ty = next_in_bucket[ty]) {
+                const Type& Y = types[ty];
+                if (thash[ty] == h && Y.len == len && !std::memcmp(loc[Y.t].rwords.data() + Y.beg, w, (size_t)len * 4)) break;
+            }
+            if (ty < 0) {
+                ty = (int32_t)types.size();
+                types.push_back(Type{(int)(i % T), L.rbeg[r], len, 0.0});
+                thash.push_back(h); next_in_bucket.push_back(head); head = ty;
+            }
+            types[ty].W += ps;
+            reg_type[i % T][r] = ty;
+            out.n_region_instances++;
+            for (int32_t k = 0; k < len; ++k) out.n_region_edges += (w[k] >> 31);
+        }
+    }
+    out.n_strings = (int64_t)ok.size();
+    out.n_types = (int64_t)types.size();
+    // ---- 3. KR layout: types by class (big ones first, longest first; then 16, 12, 8, 4 rows), sorted by content
+    auto rows_of = [&](const Type& Y) -> int {
+        int edges = 0;
+        const uint32_t* w = loc[Y.t].rwords.data() + Y.beg;
+        bool fin = false;
+        for (int32_t k = 0; k < Y.len; ++k) { edges += (w[k] >> 31); fin = fin || (!(w[k] >> 31) && (w[k] & kLatFin)); }
+        if (!fin) return (edges + kSegSmallStep - 1) / kSegSmallStep * kSegSmallStep;      // small: bare edge words
+        return (Y.len + kCheckEvery - 1) / kCheckEvery * kCheckEvery;                      // big: padded stream
+    };
+    std::vector<int32_t> order(types.size()), trows(types.size());
+    for (size_t i = 0; i < types.size(); ++i) { order[i] = (int32_t)i; trows[i] = rows_of(types[i]); }
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        if (trows[a] != trows[b]) return trows[a] > trows[b];
+        const Type &X = types[a], &Y = types[b];
+        const uint32_t* wa = loc[X.t].rwords.data() + X.beg; const uint32_t* wb = loc[Y.t].rwords.data() + Y.beg;
+        const int32_t m = std::min(X.len, Y.len);
+        for (int32_t k = 0; k < m; ++k) if (wa[k] != wb[k]) return (wa[k] & 0x7fffu) != (wb[k] & 0x7fffu) ? (wa[k] & 0x7fffu) < (wb[k] & 0x7fffu) : wa[k] < wb[k];
+        return X.len < Y.len;
+    });
+    std::vector<int32_t> type_slot(types.size(), -1);                     // type -> g*32 + lane
+    out.rgoff.assign(1, 0);
+    {
+        size_t i = 0;
+        while (i < order.size()) {
+            const int rows = trows[order[i]];
+            const bool small = rows <= kSegSmallMax;
+            size_t j = i;
+            // a group holds up to 32 types of one class (small: identical rows; big: rows of its first = longest)
+            while (j < order.size() && j - i < 32 && (small ? trows[order[j]] == rows : trows[order[j]] > kSegSmallMax)) ++j;
+            const int64_t g = (int64_t)out.rgrows.size();
+            out.rgrows.push_back(rows);
+            out.rgoff.push_back(out.rgoff.back() + (int64_t)rows * 32);
+            for (size_t k = i; k < j; ++k) type_slot[order[k]] = (int32_t)(g * 32 + (int64_t)(k - i));
+            if (!small) out.max_big_rows = std::max<int64_t>(out.max_big_rows, rows);
+            i = j;
+        }
+    }
+    const int64_t n_rg = (int64_t)out.rgrows.size();
+    out.rwords.assign((size_t)out.rgoff[n_rg] + 32, 0u);
+    out.typeW.assign((size_t)n_rg * 32, 0.0);
+    for (size_t ty = 0; ty < types.size(); ++ty) {
+        const Type& Y = types[ty];
+        const int32_t slot = type_slot[ty];
+        const int64_t g = slot >> 5; const int l = slot & 31;
+        const uint32_t* w = loc[Y.t].rwords.data() + Y.beg;
+        uint32_t* dst = out.rwords.data() + out.rgoff[g] + l;
+        for (int32_t k = 0; k < Y.len; ++k) { dst[(size_t)k * 32] = w[k]; out.n_type_edges += (w[k] >> 31); }
+        out.typeW[slot] = Y.W;
+    }
+    // ---- 4. KS layout: strings by (bridge words, region refs), longest first
+    const int32_t dummy_type = (int32_t)(n_rg * 32);
+    auto nbw = [&](int64_t i) { const Local& L = loc[i % T]; return (int)((L.boff[i / T + 1] - L.boff[i / T] + 1) / 2); };
+    auto nref = [&](int64_t i) { const Local& L = loc[i % T]; return (int)(L.sreg[i / T + 1] - L.sreg[i / T]); };
+    std::stable_sort(ok.begin(), ok.end(), [&](int64_t a, int64_t b) {
+        const int wa = nbw(a), wb = nbw(b);
+        return wa != wb ? wa > wb : nref(a) > nref(b);
+    });
+    const int64_t n_sg = ((int64_t)ok.size() + 31) / 32;
+    out.sgoff.assign((size_t)n_sg + 1, 0);
+    out.sgref.assign((size_t)n_sg, 0);
+    out.ksid.assign((size_t)n_sg * 32, -1);
+    out.kp.assign((size_t)n_sg * 32, 0.0);
+    for (int64_t g = 0; g < n_sg; ++g) {
+        int mr = 0, mb = 0;
+        for (int64_t k = g * 32; k < std::min<int64_t>((int64_t)ok.size(), g * 32 + 32); ++k) { mr = std::max(mr, nref(ok[k])); mb = std::max(mb, nbw(ok[k])); }
+        mb = (mb + 3) / 4 * 4;
+        out.sgref[g] = mr;
+        out.sgoff[g + 1] = out.sgoff[g] + (int64_t)(mr + mb) * 32;
+    }
+    const uint32_t pad_arc = (uint32_t)A.n_arcs;                          // table entry n_arcs holds log w = 0
+    out.swords.assign((size_t)out.sgoff[n_sg] + 32, pad_arc | (pad_arc << 16));
+    auto fill = [&](int t) {
+        for (int64_t g = t; g < n_sg; g += T) {
+            uint32_t* base = out.swords.data() + out.sgoff[g];
+            const int mr = out.sgref[g];
+            for (int l = 0; l < 32; ++l) {
+                const int64_t k = g * 32 + l;
+                for (int r = 0; r < mr; ++r) base[(size_t)r * 32 + l] = (uint32_t)dummy_type;
+                if (k >= (int64_t)ok.size()) continue;
+                const int64_t i = ok[k];
+                const Local& L = loc[i % T];
+                const size_t j = i / T;
+                out.ksid[k] = ids[i]; out.kp[k] = p[ids[i]];
+                int r = 0;
+                for (int64_t q = L.sreg[j]; q < L.sreg[j + 1]; ++q, ++r) base[(size_t)r * 32 + l] = (uint32_t)type_slot[reg_type[i % T][q]];
+                const uint16_t* b = L.bridges.data() + L.boff[j];
+                const int64_t nb = L.boff[j + 1] - L.boff[j];
+                for (int64_t q = 0; q < nb; q += 2) {
+                    const uint32_t lo = b[q], hi = q + 1 < nb ? b[q + 1] : pad_arc;
+                    base[(size_t)(mr + q / 2) * 32 + l] = lo | (hi << 16);
+                }
+            }
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(fill, t);
+        fill(0);
+        for (auto& x : th) x.join();
+    }
+    out.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
 }
 
 }  // namespace wfsa

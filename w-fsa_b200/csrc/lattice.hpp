@@ -54,7 +54,7 @@ void build_lattice_arcs(const HostFsa& f, const GenericLayout& g, LatticeArcs& o
 
 struct LatticeScratch {
     std::vector<int32_t> node_of;              // [(max_len+1)*n_states] -> node id or -1
-    std::vector<int32_t> npos, nstate, nslot, nout, per_pos;
+    std::vector<int32_t> npos, nstate, nslot, nout, per_pos, topo, kept;
     std::vector<uint8_t> coreach, done;
     std::vector<int32_t> esrc, edst, earc;
     std::vector<std::vector<int32_t>> bucket;  // node ids by position
@@ -81,5 +81,62 @@ struct CompiledCorpus {
 void compile_corpus(const HostFsa& f, const LatticeArcs& A, const uint8_t* arc_alive, const int32_t* tokens,
                     const int64_t* offs, const double* p, const std::vector<int32_t>& ids, int n_slots, double fx_scale,
                     bool use_bridges, int max_stream_words, CompiledCorpus& out);
+
+
+// ---------------------------------------------------------------------------------------------
+// Segmented form (kernels KR + KS, kernels_seg.cuh).  A *cut node* of the trimmed lattice is a node
+// every accepting path goes through (start, end, and every node no kept edge jumps over in the
+// topological order).  Consecutive cut nodes delimit SEGMENTS; path weights factor over segments:
+//     q(string) = prod_segments q_seg        posterior(edge) depends on its own segment only.
+//   - a segment of ONE edge is a *bridge*: it contributes log w[arc] to log q and posterior exactly 1
+//     (p_s goes to the constant accumulator of the arc at compile time);
+//   - any other segment is a *region*: a small DAG between two cut nodes, evaluated by forward-
+//     backward with region-local pool slots (entry node = slot 0, alpha(entry) = 1).
+// This is what the reference's unique-path shortcut (logq = P.x, src/Learner.cpp:517-525) and its
+// removal of columns "identical in every path" from H_f (src/HessianLearner.cpp:409-443) do, applied
+// per segment instead of per string.  Regions that compile to the same words (same sub-lattice: same
+// entry state, same consumed symbols) are merged into one TYPE with weight W = sum of the p_s of its
+// instances; KR evaluates every type once per evaluation (log q_type and the posteriors scaled by W),
+// KS adds up, per string, log w over its bridges and log q_type over its regions.
+//
+// Region words: EDGE words as above with region-local slots.  Regions of at most kSegSmallMax edges
+// are stored as bare EDGE words (the exit node is the dst of the last edge); larger regions use the
+// full stream format above (CHECK every kCheckEvery-th word, FIN last) so that they can be rescaled.
+constexpr int kSegSmallMax = 16;          // edges of a "small" region (unrolled in registers on the device)
+constexpr int kSegSmallStep = 4;          // small regions are padded to 4, 8, 12 or 16 word rows
+
+struct SegString {                         // one string, compiled
+    int status = 0;                        // 1 ok, 0 no accepting path, -1 needs another kernel
+    std::vector<uint16_t> bridges;         // arcs of the bridge segments
+    std::vector<uint32_t> rwords;          // region words, concatenated
+    std::vector<int32_t> roff;             // [n_regions+1] into rwords
+};
+int compile_segments(const HostFsa& f, const LatticeArcs& A, const uint8_t* arc_alive, const int32_t* tok, int len,
+                     int n_slots, LatticeScratch& S, SegString& out);
+
+struct SegmentedCorpus {
+    // KR: region types in groups of 32 (one warp), word j of lane l of group g at rgoff[g] + j*32 + l;
+    // type id = g*32 + l; rgrows[g] = word rows of the group (4/8/12/16 = small, otherwise a multiple of 16)
+    std::vector<uint32_t> rwords;
+    std::vector<int64_t> rgoff;                // [n_rgroups+1]
+    std::vector<int32_t> rgrows;               // [n_rgroups]
+    std::vector<double> typeW;                 // [n_rgroups*32] sum of p_s over the instances (0 = padding lane)
+    int64_t n_types = 0, n_region_instances = 0, n_region_edges = 0, n_type_edges = 0, max_big_rows = 0;
+    // KS: strings in groups of 32, longest first; string position kpos = g*32 + l
+    //   rows [0, sgref[g])        : region type ids (padding = dummy type n_rgroups*32, log q = 0)
+    //   rows [sgref[g], rows(g))  : two 16-bit bridge arcs per word (padding = n_arcs, log w = 0)
+    std::vector<uint32_t> swords;
+    std::vector<int64_t> sgoff;                // [n_sgroups+1]
+    std::vector<int32_t> sgref;                // [n_sgroups]
+    std::vector<int32_t> ksid;                 // [n_sgroups*32] string id or -1
+    std::vector<double> kp;                    // [n_sgroups*32] p_s (0 = padding lane)
+    std::vector<int32_t> overflow, rejected;
+    std::vector<long long> const_acc;          // [n_arcs] fixed-point constant gradient part (bridges)
+    int64_t n_bridge = 0, n_strings = 0;
+    double host_ms = 0;
+};
+void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint8_t* arc_alive, const int32_t* tokens,
+                              const int64_t* offs, const double* p, const std::vector<int32_t>& ids, int n_slots,
+                              double fx_scale, SegmentedCorpus& out);
 
 }  // namespace wfsa

@@ -19,6 +19,7 @@
 
 #include "../../include/wfsa_dev.h"
 #include "kernels.cuh"
+#include "kernels_seg.cuh"
 #include "layout.hpp"
 #include "lattice.hpp"
 
@@ -124,6 +125,15 @@ struct wfsa_dev {
     DevBuf<int32_t> d_klgsid, d_kl_arc_tid, d_kl_arc_eid;
     DevBuf<double> d_klaw, d_klxs;
     DevBuf<unsigned long long> d_klacc, d_klconst;
+    // segmented compiled lattices (KR + KS, kernel 6)
+    size_t ks_smem = 0; int ks_grid = 0, ks_block = 512;
+    int64_t kr_groups = 0, ks_groups = 0, seg_types = 0, seg_instances = 0, seg_region_edges = 0, seg_type_edges = 0,
+            seg_bridges = 0, seg_words = 0;
+    double seg_host_ms = 0;
+    DevBuf<uint32_t> d_krwords, d_kswords;
+    DevBuf<int64_t> d_krgoff, d_ksgoff;
+    DevBuf<int32_t> d_krgrows, d_ksgref, d_kssid;
+    DevBuf<double> d_krW, d_krlq, d_ksp, d_kslogq, d_klogaw;
     std::vector<double> h_p;
     int64_t n_overflow = 0, n_active_w = 0;
     DevBuf<int32_t> d_order_w;                                    // overflow strings (secondary kernel)
@@ -195,6 +205,9 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     h->d_klwords.release(); h->d_klcounter.release(); h->d_klgoff.release(); h->d_klgsid.release();
     h->d_kl_arc_tid.release(); h->d_kl_arc_eid.release(); h->d_klaw.release(); h->d_klxs.release();
     h->d_klacc.release(); h->d_klconst.release();
+    h->d_krwords.release(); h->d_kswords.release(); h->d_krgoff.release(); h->d_ksgoff.release(); h->d_krgrows.release();
+    h->d_ksgref.release(); h->d_kssid.release(); h->d_krW.release(); h->d_krlq.release(); h->d_ksp.release();
+    h->d_kslogq.release(); h->d_klogaw.release();
     for (auto* b : u32) b->release();
     DevBuf<double>* f64[] = {&h->d_p, &h->d_x, &h->d_tw, &h->d_sw, &h->d_fw, &h->d_ltw, &h->d_lew, &h->d_logq, &h->d_pathcnt,
                              &h->d_out, &h->d_k3lat, &h->d_gscratch, &h->d_aw, &h->d_hb_counts, &h->d_hb_p, &h->d_hb_r, &h->d_H, &h->d_rmin};
@@ -315,7 +328,15 @@ static int setup_kl(wfsa_dev* h)
     const LatticeArcs& A = h->larcs;
     CK(h->d_kl_arc_tid.upload(A.arc_tid, h->stream)); CK(h->d_kl_arc_eid.upload(A.arc_eid, h->stream));
     CK(h->d_klaw.alloc(A.n_arcs)); CK(h->d_klacc.alloc((size_t)A.n_arcs * h->replicas)); CK(h->d_klconst.alloc(A.n_arcs));
-    CK(h->d_klcounter.alloc(1));
+    CK(h->d_klcounter.alloc(2));
+    if (h->kernel == 6) {
+        CK(h->d_klogaw.alloc(A.n_arcs));
+        h->ks_smem = ((size_t)A.n_arcs + 1) * 8;
+        h->ks_grid = h->sm_count * 2;
+        cudaFuncSetAttribute(kr_regions<ACC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(kr_regions<ACC_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(ks_strings, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    }
     cudaFuncSetAttribute(kl_fwdbwd<ACC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(kl_fwdbwd<ACC_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     return WFSA_OK;
@@ -343,7 +364,7 @@ static int choose_launch(wfsa_dev* h)
     }
     int rc = WFSA_OK;
     h->skernel = h->kernel;
-    if (h->kernel == 5) {
+    if (h->kernel == 5 || h->kernel == 6) {
         h->secondary = h->fast.warp_ok ? 1 : (h->fast.ok ? 2 : 3);
         int nt = 0; size_t sm = 0; int K = (h->opt.reserved >> 16) & 0xff; if (K == 0) K = 8;
         h->skernel = (h->fast.ok && kt_possible(h, K, nt, sm)) ? 4 : h->secondary;
@@ -404,13 +425,14 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
     int kernel = h->opt.force_kernel;
     if (kernel == 0) {
         int nt = 0; size_t sm = 0; int K = (h->opt.reserved >> 16) & 0xff; if (K == 0) K = 8;
-        if (kl_possible(h, kLatMaxSlots, 0, nt, sm)) kernel = 5;
+        if (kl_possible(h, kLatMaxSlots, 0, nt, sm)) kernel = h->larcs.n_arcs < 65535 ? 6 : 5;
         else kernel = !h->fast.ok ? 3 : (kt_possible(h, K, nt, sm) ? 4 : (h->fast.warp_ok ? 1 : 2));
     }
-    if (kernel == 5) { int nt = 0; size_t sm = 0; if (!kl_possible(h, kLatMaxSlots, 0, nt, sm)) { h->err = "forced compiled-lattice kernel but the arc weights do not fit shared memory"; return bail(WFSA_ERR_INVALID); } }
+    if (kernel == 6 && h->larcs.n_arcs >= 65535) { h->err = "forced segmented kernel but the automaton has 65535 or more combined arcs"; return bail(WFSA_ERR_INVALID); }
+    if (kernel == 5 || kernel == 6) { int nt = 0; size_t sm = 0; if (!kl_possible(h, kLatMaxSlots, 0, nt, sm)) { h->err = "forced compiled-lattice kernel but the arc weights do not fit shared memory"; return bail(WFSA_ERR_INVALID); } }
     if ((kernel == 1 || kernel == 2 || kernel == 4) && !h->fast.ok) { h->err = "forced fast kernel but emissions are not all one token long"; return bail(WFSA_ERR_INVALID); }
     if (kernel == 1 && !h->fast.warp_ok) { h->err = "forced warp-per-string kernel but more than 32 states emit one symbol"; return bail(WFSA_ERR_INVALID); }
-    if (kernel < 1 || kernel > 5) { h->err = "force_kernel out of range"; return bail(WFSA_ERR_INVALID); }
+    if (kernel < 1 || kernel > 6) { h->err = "force_kernel out of range"; return bail(WFSA_ERR_INVALID); }
     h->kernel = kernel;
 
     // ---- corpus shard
@@ -518,7 +540,26 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
     const FastLayout& L = h->fast;
     cudaStream_t st = h->stream;
     if (C.n_order <= 0) return;
-    if (kernel == 5) {
+    if (kernel == 6) {
+        cudaMemsetAsync(h->d_klcounter.p, 0, 8, st);
+        if (h->kr_groups > 0) {
+            KRParams P{};
+            P.aw = h->d_klaw.p; P.words = h->d_krwords.p; P.goff = h->d_krgoff.p; P.grows = h->d_krgrows.p; P.typeW = h->d_krW.p;
+            P.lq = h->d_krlq.p; P.n_groups = h->kr_groups; P.xs = h->d_klxs.p; P.xs_rows = (size_t)std::max<int64_t>(h->kl_max_words, 1);
+            P.counter = h->d_klcounter.p; P.acc = h->d_klacc.p; P.fx_scale = O.fx_scale; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas;
+            if (h->opt.reserved & 2) kr_regions<ACC_NONE><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // timing experiment
+            else kr_regions<ACC_GLOBAL><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
+            h->launches++;
+        }
+        KSParams S{};
+        S.logaw = h->d_klogaw.p; S.words = h->d_kswords.p; S.goff = h->d_ksgoff.p; S.gref = h->d_ksgref.p; S.lq = h->d_krlq.p;
+        S.p = h->d_ksp.p; S.logq = h->d_kslogq.p; S.n_groups = h->ks_groups; S.counter = h->d_klcounter.p + 1; S.red = O.red;
+        S.ll_scale = O.ll_scale; S.n_arcs = h->larcs.n_arcs;
+        if (h->ks_groups > 0) {
+            ks_strings<<<h->ks_grid, h->ks_block, h->ks_smem, st>>>(S);
+            h->launches++;
+        }
+    } else if (kernel == 5) {
         KLParams P{};
         P.aw = h->d_klaw.p; P.words = h->d_klwords.p; P.goff = h->d_klgoff.p; P.gsid = h->d_klgsid.p; P.p = h->d_p.p;
         P.n_groups = h->kl_groups; P.xs = h->d_klxs.p; P.xs_rows = (size_t)std::max<int64_t>(h->kl_max_words, 1);
@@ -620,10 +661,14 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
             k_state_final_weights<<<(F.n_states + 255) / 256, 256, 0, st>>>(F.n_states, h->d_state_final.p, h->d_tw.p, h->d_fws.p);
             h->launches++;
         }
-        if (kernel == 5) {
+        if (kernel == 5 || kernel == 6) {
             const int na = h->larcs.n_arcs;
-            k_arc_weights<<<(na + 255) / 256, 256, 0, st>>>(na, h->d_kl_arc_tid.p, h->d_kl_arc_eid.p, h->d_emis_tp.p, h->d_tw.p,
-                                                          h->d_x.p, unit, h->d_klaw.p);
+            if (kernel == 6)
+                k_arc_weights_log<<<(na + 255) / 256, 256, 0, st>>>(na, h->d_kl_arc_tid.p, h->d_kl_arc_eid.p, h->d_trans_tp.p,
+                                                                  h->d_emis_tp.p, h->d_x.p, h->d_klaw.p, h->d_klogaw.p);
+            else
+                k_arc_weights<<<(na + 255) / 256, 256, 0, st>>>(na, h->d_kl_arc_tid.p, h->d_kl_arc_eid.p, h->d_emis_tp.p, h->d_tw.p,
+                                                              h->d_x.p, unit, h->d_klaw.p);
             h->launches++;
             // replica 0 starts from the constant part (bridge edges: posterior exactly 1), the others from 0
             CK(cudaMemcpyAsync(h->d_klacc.p, h->d_klconst.p, (size_t)na * 8, cudaMemcpyDeviceToDevice, st));
@@ -646,14 +691,14 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
     if (kernel2) launch_main(h, kernel2, mode, CorpusD{h->d_tokens.p, h->d_offs.p, h->d_p.p, d_order2, n_order2}, O);
     if (e1) cudaEventRecord(e1, st);
     CK(cudaGetLastError());
-    if (fold && kernel == 5) {
+    if (fold && (kernel == 5 || kernel == 6)) {
         const int na = h->larcs.n_arcs;
         k_arcs_to_edges<<<(na + 255) / 256, 256, 0, st>>>(na, 0, F.n_trans(), h->d_klacc.p, h->replicas, h->d_kl_arc_tid.p,
                                                          h->d_kl_arc_eid.p, nullptr, h->d_red.p + 2);
         h->launches++;
         CK(cudaGetLastError());
     }
-    const bool fast_used = kernel == 5 ? (kernel2 == 1 || kernel2 == 2) && n_order2 > 0 : (kernel != 3);
+    const bool fast_used = (kernel == 5 || kernel == 6) ? (kernel2 == 1 || kernel2 == 2) && n_order2 > 0 : (kernel != 3);
     if (fold && h->fast.ok && fast_used) {
         const int total = h->fast.n_arcs + F.n_states;
         k_arcs_to_edges<<<(total + 255) / 256, 256, 0, st>>>(h->fast.n_arcs, F.n_states, F.n_trans(), h->d_acc.p, h->replicas,
@@ -750,7 +795,7 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
             tokens += len; max_len = std::max<int>(max_len, (int)len);
         }
     h->n_active = (int64_t)order.size(); h->n_active_w = (int64_t)order_w.size(); h->n_active_tokens = tokens;
-    if (h->kernel != 5) {
+    if (h->kernel != 5 && h->kernel != 6) {
         if (!order.empty()) CK(cudaMemcpyAsync(h->d_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, h->stream));
         if (!order_w.empty()) CK(cudaMemcpyAsync(h->d_order_w.p, order_w.data(), order_w.size() * 4, cudaMemcpyHostToDevice, h->stream));
     }
@@ -775,6 +820,42 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
     int bits = 1;
     while ((1ll << bits) <= bound && bits < 40) ++bits;
     h->fx_log2 = 62 - bits;
+    if (h->kernel == 6) {
+        // compile every participating string into bridges + region types (structure is independent of x)
+        const LatticeArcs& A = h->larcs;
+        std::vector<uint8_t> alive((size_t)A.n_arcs);
+        for (int a = 0; a < A.n_arcs; ++a)
+            alive[a] = ttp[A.arc_tid[a]] != -2 && (A.arc_eid[a] < 0 || etp[A.arc_eid[a]] != -2);
+        SegmentedCorpus sc;
+        compile_corpus_segmented(h->fsa, A, alive.data(), h->h_tokens.data(), h->h_offs.data(), h->h_p.data(), order, h->kl_K,
+                                 std::ldexp(1.0, (int)h->fx_log2), sc);
+        order_w = sc.overflow;
+        order_w.insert(order_w.end(), sc.rejected.begin(), sc.rejected.end());
+        h->n_active = (int64_t)order.size() - (int64_t)order_w.size(); h->n_active_w = (int64_t)order_w.size();
+        h->kr_groups = (int64_t)sc.rgrows.size(); h->ks_groups = (int64_t)sc.sgref.size();
+        h->seg_types = sc.n_types; h->seg_instances = sc.n_region_instances; h->seg_region_edges = sc.n_region_edges;
+        h->seg_type_edges = sc.n_type_edges; h->seg_bridges = sc.n_bridge; h->seg_host_ms = sc.host_ms;
+        h->seg_words = (int64_t)sc.rwords.size() + (int64_t)sc.swords.size();
+        h->kl_max_words = sc.max_big_rows;
+        CK(h->d_krwords.upload(sc.rwords, h->stream)); CK(h->d_krgoff.upload(sc.rgoff, h->stream));
+        CK(h->d_krgrows.upload(sc.rgrows, h->stream)); CK(h->d_krW.upload(sc.typeW, h->stream));
+        CK(h->d_krlq.alloc((size_t)h->kr_groups * 32 + 1));
+        CK(cudaMemsetAsync(h->d_krlq.p, 0, h->d_krlq.n * 8, h->stream));
+        CK(h->d_kswords.upload(sc.swords, h->stream)); CK(h->d_ksgoff.upload(sc.sgoff, h->stream));
+        CK(h->d_ksgref.upload(sc.sgref, h->stream)); CK(h->d_kssid.upload(sc.ksid, h->stream));
+        CK(h->d_ksp.upload(sc.kp, h->stream));
+        CK(h->d_kslogq.alloc(std::max<size_t>((size_t)h->ks_groups * 32, 1)));
+        std::vector<unsigned long long> cacc(sc.const_acc.begin(), sc.const_acc.end());
+        CK(cudaMemcpyAsync(h->d_klconst.p, cacc.data(), cacc.size() * 8, cudaMemcpyHostToDevice, h->stream));
+        if (!order_w.empty()) CK(cudaMemcpyAsync(h->d_order_w.p, order_w.data(), order_w.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        const size_t warps = (size_t)h->kl_grid * h->kl_block / 32;
+        const size_t need = warps * (size_t)std::max<int64_t>(sc.max_big_rows, 1) * 32;
+        if (h->d_klxs.n < need) {
+            const cudaError_t e = h->d_klxs.alloc(need);
+            if (e != cudaSuccess) return set_err(h, WFSA_ERR_NOMEM, "segmented kernel: cannot allocate the per-warp x stacks");
+        }
+        CK(cudaStreamSynchronize(h->stream));
+    }
     if (h->kernel == 5) {
         // compile the trimmed lattice of every participating string (structure is independent of x)
         const LatticeArcs& A = h->larcs;
@@ -870,6 +951,11 @@ extern "C" int wfsa_dev_eval_fetch(wfsa_dev* h, double* loglik, double* logq, do
     if (!h) return WFSA_ERR_INVALID;
     if (h->n < 0) return set_err(h, WFSA_ERR_STATE, "fetch before set_param_map");
     CK(cudaMemcpyAsync(h->h_out, h->d_out.p, ((size_t)h->n + 2) * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (logq && h->kernel == 6 && h->ks_groups > 0) {
+        const long long nk = h->ks_groups * 32;
+        k_scatter_logq<<<(unsigned)((nk + 255) / 256), 256, 0, h->stream>>>(nk, h->d_kssid.p, h->d_kslogq.p, h->d_logq.p);
+        h->launches++;
+    }
     if (logq && h->n_strings) CK(cudaMemcpyAsync(logq, h->d_logq.p, (size_t)h->n_strings * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
@@ -1101,6 +1187,61 @@ extern "C" int wfsa_lattice_stats(const wfsa_fsa_desc* fd, const wfsa_corpus_des
     return WFSA_OK;
 }
 
+struct wfsa_segmented {
+    SegmentedCorpus sc;
+    LatticeArcs arcs;
+    std::vector<int64_t> stats;
+};
+
+extern "C" int wfsa_segmented_compile(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* cd, const int32_t* trimmed,
+                                      int32_t n_slots, double fx_scale, wfsa_segmented** out)
+{
+    g_create_error.clear();
+    if (!fd || !cd || !out || n_slots < 1 || n_slots > kLatMaxSlots || cd->n_strings < 0) { g_create_error = "segmented_compile: bad arguments"; return WFSA_ERR_INVALID; }
+    *out = nullptr;
+    HostFsa f; GenericLayout g;
+    int status = WFSA_OK;
+    std::string msg = copy_and_validate(fd, f, status);
+    if (status == WFSA_OK) msg = build_generic_layout(f, g, status);
+    if (status != WFSA_OK) { g_create_error = msg; return status; }
+    wfsa_segmented* s = new wfsa_segmented();
+    build_lattice_arcs(f, g, s->arcs);
+    const LatticeArcs& A = s->arcs;
+    if (A.n_arcs >= 65535 || A.n_arcs >= (1 << kLatArcBits)) { delete s; g_create_error = "segmented_compile: too many combined arcs"; return WFSA_ERR_LIMIT; }
+    std::vector<uint8_t> alive((size_t)A.n_arcs, 1);
+    if (trimmed)
+        for (int a = 0; a < A.n_arcs; ++a) {
+            const int tp = f.trans_param[A.arc_tid[a]], ep = A.arc_eid[a] < 0 ? -1 : f.emis_param[A.arc_eid[a]];
+            alive[a] = (tp < 0 || trimmed[tp] != -2) && (ep < 0 || trimmed[ep] != -2);
+        }
+    std::vector<int32_t> ids((size_t)cd->n_strings);
+    std::iota(ids.begin(), ids.end(), 0);
+    std::stable_sort(ids.begin(), ids.end(), [&](int32_t a, int32_t b) {
+        return (cd->offsets[a + 1] - cd->offsets[a]) > (cd->offsets[b + 1] - cd->offsets[b]);
+    });
+    compile_corpus_segmented(f, A, alive.data(), cd->tokens, cd->offsets, cd->p, ids, n_slots, fx_scale, s->sc);
+    s->stats = {s->sc.n_types, s->sc.n_region_instances, s->sc.n_region_edges, s->sc.n_type_edges, s->sc.n_bridge, s->sc.n_strings,
+                (int64_t)(s->sc.host_ms * 1000.0)};
+    *out = s;
+    return WFSA_OK;
+}
+
+extern "C" int wfsa_segmented_get(const wfsa_segmented* s, int which, const void** data, int64_t* count)
+{
+    if (!s || !data || !count) return WFSA_ERR_INVALID;
+    const SegmentedCorpus& c = s->sc;
+#define SEG_ARR(i, v) case i: *data = (v).data(); *count = (int64_t)(v).size(); return WFSA_OK;
+    switch (which) {
+        SEG_ARR(0, c.rwords) SEG_ARR(1, c.rgoff) SEG_ARR(2, c.rgrows) SEG_ARR(3, c.typeW) SEG_ARR(4, c.swords) SEG_ARR(5, c.sgoff)
+        SEG_ARR(6, c.sgref) SEG_ARR(7, c.ksid) SEG_ARR(8, c.kp) SEG_ARR(9, c.overflow) SEG_ARR(10, c.rejected) SEG_ARR(11, c.const_acc)
+        SEG_ARR(12, s->stats)
+        default: return WFSA_ERR_INVALID;
+    }
+#undef SEG_ARR
+}
+
+extern "C" void wfsa_segmented_free(wfsa_segmented* s) { delete s; }
+
 extern "C" int wfsa_dev_get_info(wfsa_dev* h, wfsa_dev_info* info)
 {
     if (!h || !info) return WFSA_ERR_INVALID;
@@ -1110,15 +1251,22 @@ extern "C" int wfsa_dev_get_info(wfsa_dev* h, wfsa_dev_info* info)
     info->n_arcs = h->fast.ok ? h->fast.n_arcs : 0; info->n_slots = h->fast.ok ? h->fast.n_slots : 0;
     info->max_candidates = h->fast.ok ? h->fast.max_cand : 0;
     info->sm_count = h->sm_count;
-    info->grid = h->kernel == 5 ? h->kl_grid : (h->kernel == 4 ? h->kt_grid : (h->kernel == 2 ? h->k3_grid : h->grid));
-    info->block = h->kernel == 5 ? h->kl_block : (h->kernel == 4 ? h->kt_block : (h->kernel == 2 ? h->k3_block : (h->kernel == 3 ? 128 : h->block)));
+    info->grid = h->kernel >= 5 ? h->kl_grid : (h->kernel == 4 ? h->kt_grid : (h->kernel == 2 ? h->k3_grid : h->grid));
+    info->block = h->kernel >= 5 ? h->kl_block : (h->kernel == 4 ? h->kt_block : (h->kernel == 2 ? h->k3_block : (h->kernel == 3 ? 128 : h->block)));
     info->n_strings = h->n_strings; info->n_tokens = h->n_tokens;
     info->n_active_tokens = h->n_active_tokens;
-    info->smem_bytes = (int64_t)(h->kernel == 5 ? h->kl_smem : (h->kernel == 4 ? h->kt_smem : (h->kernel == 2 ? h->k3_smem : h->smem_bytes)));
+    info->smem_bytes = (int64_t)(h->kernel >= 5 ? h->kl_smem : (h->kernel == 4 ? h->kt_smem : (h->kernel == 2 ? h->k3_smem : h->smem_bytes)));
     if (h->kernel == 5) {
         info->n_arcs = h->larcs.n_arcs;
         info->lattice_words = h->kl_words; info->lattice_edges = h->kl_edges; info->lattice_bridge_edges = h->kl_bridge_edges;
         info->n_overflow_strings = h->n_active_w; info->pool_slots = h->kl_K;
+    }
+    if (h->kernel == 6) {
+        info->n_arcs = h->larcs.n_arcs;
+        info->lattice_words = h->seg_words; info->lattice_edges = h->seg_bridges + h->seg_region_edges;
+        info->lattice_bridge_edges = h->seg_bridges; info->n_overflow_strings = h->n_active_w; info->pool_slots = h->kl_K;
+        info->seg_types = h->seg_types; info->seg_region_instances = h->seg_instances; info->seg_region_edges = h->seg_region_edges;
+        info->seg_type_edges = h->seg_type_edges; info->seg_host_ms = h->seg_host_ms;
     }
     info->n_active_strings = h->n_active + h->n_active_w; info->table_bytes = (int64_t)h->table_bytes;
     info->kernels_launched = h->launches; info->fixed_point_scale_log2 = h->fx_log2;

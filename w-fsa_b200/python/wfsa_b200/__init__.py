@@ -20,7 +20,8 @@ DEV_SYMBOLS = [
     "wfsa_dev_eval_launch", "wfsa_dev_eval_fetch", "wfsa_dev_sync", "wfsa_dev_set_path_blocks", "wfsa_dev_hessian",
     "wfsa_dev_comm_unique_id", "wfsa_dev_comm_init", "wfsa_dev_allreduce_f64", "wfsa_dev_timer_begin",
     "wfsa_dev_timer_end", "wfsa_dev_timer_kernel_ms", "wfsa_dev_get_info", "wfsa_dev_destroy", "wfsa_dev_last_error",
-    "wfsa_dev_version", "wfsa_lattice_compile", "wfsa_lattice_stats",
+    "wfsa_dev_version", "wfsa_lattice_compile", "wfsa_lattice_stats", "wfsa_segmented_compile", "wfsa_segmented_get",
+    "wfsa_segmented_free",
 ]
 HOST_SYMBOLS = [
     "wfsa_host_parse", "wfsa_host_last_error", "wfsa_session_create", "wfsa_session_destroy", "wfsa_session_error",
@@ -56,7 +57,9 @@ class DevInfo(C.Structure):
                 ("n_tokens", C.c_int64), ("n_active_tokens", C.c_int64), ("smem_bytes", C.c_int64),
                 ("table_bytes", C.c_int64), ("kernels_launched", C.c_int64), ("fixed_point_scale_log2", C.c_double),
                 ("lattice_words", C.c_int64), ("lattice_edges", C.c_int64), ("lattice_bridge_edges", C.c_int64),
-                ("n_overflow_strings", C.c_int64), ("pool_slots", C.c_int32), ("reserved", C.c_int32)]
+                ("n_overflow_strings", C.c_int64), ("pool_slots", C.c_int32), ("reserved", C.c_int32),
+                ("seg_types", C.c_int64), ("seg_region_instances", C.c_int64), ("seg_region_edges", C.c_int64),
+                ("seg_type_edges", C.c_int64), ("seg_host_ms", C.c_double)]
 
 
 class PathBlocks(C.Structure):
@@ -135,8 +138,43 @@ def lib():
         L.wfsa_lattice_stats.argtypes = [C.POINTER(FsaDesc), C.POINTER(CorpusDesc), C.c_int32, F64P]
         L.wfsa_lattice_compile.argtypes = [C.POINTER(FsaDesc), I32P, I32P, C.c_int32, C.c_int32, C.POINTER(C.c_uint32), C.c_int64,
                                            I64P, I32P, I32P, C.c_int32, I32P]
+        L.wfsa_segmented_compile.argtypes = [C.POINTER(FsaDesc), C.POINTER(CorpusDesc), I32P, C.c_int32, C.c_double,
+                                             C.POINTER(C.c_void_p)]
+        L.wfsa_segmented_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), I64P]
+        L.wfsa_segmented_free.argtypes = [C.c_void_p]
+        L.wfsa_segmented_free.restype = None
         _lib = L
     return _lib
+
+
+_SEG_ARRAYS = [("rwords", np.uint32), ("rgoff", np.int64), ("rgrows", np.int32), ("typeW", np.float64), ("swords", np.uint32),
+               ("sgoff", np.int64), ("sgref", np.int32), ("ksid", np.int32), ("kp", np.float64), ("overflow", np.int32),
+               ("rejected", np.int32), ("const_acc", np.int64), ("stats", np.int64)]
+
+
+def segmented_compile(lowered, trimmed=None, n_slots=16, fx_scale=1.0):
+    """Host-only: the segmented compiled form of a shard (include/wfsa_dev.h wfsa_segmented_*) as numpy arrays,
+    plus the combined-arc table (arc -> transition edge, emission edge or -1)."""
+    L = lib()
+    fd, cd = lowered.fsa_desc(), lowered.corpus_desc()
+    tr = None if trimmed is None else np.ascontiguousarray(trimmed, dtype=np.int32)
+    h = C.c_void_p()
+    rc = L.wfsa_segmented_compile(C.byref(fd), C.byref(cd), _p(tr, I32P), n_slots, fx_scale, C.byref(h))
+    if rc != 0:
+        raise WfsaError(rc, L.wfsa_dev_last_error(None).decode())
+    out = {}
+    try:
+        for i, (name, dt) in enumerate(_SEG_ARRAYS):
+            ptr, cnt = C.c_void_p(), C.c_int64()
+            L.wfsa_segmented_get(h, i, C.byref(ptr), C.byref(cnt))
+            if cnt.value:
+                buf = (C.c_char * (cnt.value * np.dtype(dt).itemsize)).from_address(ptr.value)
+                out[name] = np.frombuffer(buf, dtype=dt).copy()
+            else:
+                out[name] = np.zeros(0, dtype=dt)
+    finally:
+        L.wfsa_segmented_free(h)
+    return out
 
 
 def _p(a, t):
