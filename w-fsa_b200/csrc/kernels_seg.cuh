@@ -20,7 +20,7 @@ struct KRParams {
     const double* __restrict__ aw;        // [n_arcs] a(u,v) * b(v,e)
     const uint32_t* __restrict__ words;   // word j of lane l of group g at goff[g] + j*32 + l
     const int64_t* __restrict__ goff;     // [n_groups+1]
-    const int32_t* __restrict__ grows;    // [n_groups] 4/8/12/16 = small region class, else big (multiple of 16)
+    const int32_t* __restrict__ grows;    // [n_groups] 4/8 = small region class, else big (multiple of 16)
     const double* __restrict__ typeW;     // [n_groups*32]
     double* lq;                           // [n_groups*32 + 1] log q per type (last = dummy, stays 0)
     long long n_groups;
@@ -31,6 +31,25 @@ struct KRParams {
     double fx_scale;
     int n_arcs, replicas;
 };
+
+// Fixed-point add of one value per lane into acc[key].  Region types are sorted by their arcs, so neighbouring
+// lanes mostly hold the same arc at the same edge position: runs of equal keys are summed with shuffles
+// (integers: exact, order independent) and only the first lane of a run issues the RED.  Must be called by
+// all 32 lanes; key < 0 = nothing to add.
+__device__ __forceinline__ void red_runs(unsigned long long* acc_g, int key, long long v, int lane)
+{
+    const int kp = __shfl_up_sync(FULL, key, 1);
+    const bool head = lane == 0 || kp != key;
+    const unsigned heads = __ballot_sync(FULL, head);
+    const unsigned later = lane == 31 ? 0u : heads & ~((2u << lane) - 1u);
+    const int end = later ? __ffs(later) - 1 : 32;          // first lane of the next run
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long v2 = __shfl_down_sync(FULL, v, d);
+        if (lane + d < end) v += v2;
+    }
+    if (head && key >= 0 && v) atomicAdd(acc_g + key, (unsigned long long)v);
+}
 
 // One small region per thread, NE word rows, everything in registers except the pool.
 template <int NE, int ACC>
@@ -65,17 +84,19 @@ __device__ __forceinline__ void kr_small(const KRParams& P, const double* aw, do
 #pragma unroll
     for (int j = NE - 1; j >= 0; --j) {
         const uint32_t wj = w[j];
+        int key = -1;
+        long long v = 0;
         if (wj & kLEdge) {
             const int src = (wj >> 19) & 15, dst = (wj >> 23) & 15, arc = wj & 0x7fff;
             const double bd = pool[dst * NT];
             const double c = aw[arc] * bd;
             double* psrc = pool + src * NT;
             *psrc = (wj & kLLastOut) ? c : *psrc + c;
-            if (ACC != ACC_NONE) {
-                const long long v = __double2ll_rn(xs[j] * bd * sc);
-                if (v) atomicAdd(acc_g + arc, (unsigned long long)v);
-            }
+            key = arc;
+            v = __double2ll_rn(xs[j] * bd * sc);
         }
+        if (ACC == ACC_GLOBAL) red_runs(acc_g, key, v, lane);
+        else if (ACC == ACC_SMEM_CAS) { if (v) atomicAdd(acc_g + key, (unsigned long long)v); }   // plain REDs (experiment)
     }
 }
 
@@ -156,25 +177,28 @@ __device__ __forceinline__ void kr_big(const KRParams& P, const double* aw, doub
                     }
                     sc = scalbn(sc0, Et + F - EQ);
                 }
-            } else if (wj & kLEdge) {
-                const int src = (wj >> 19) & 15, dst = (wj >> 23) & 15, arc = wj & 0x7fff;
-                const double bd = pool[dst * NT];
-                const double c = aw[arc] * bd;
-                double* psrc = pool + src * NT;
-                *psrc = (wj & kLLastOut) ? c : *psrc + c;
-                if (ACC != ACC_NONE && ok) {
-                    const long long v = __double2ll_rn(xv[j] * bd * sc);
-                    if (v) atomicAdd(acc_g + arc, (unsigned long long)v);
+            } else {
+                int key = -1;
+                long long v = 0;
+                if (wj & kLEdge) {
+                    const int src = (wj >> 19) & 15, dst = (wj >> 23) & 15, arc = wj & 0x7fff;
+                    const double bd = pool[dst * NT];
+                    const double c = aw[arc] * bd;
+                    double* psrc = pool + src * NT;
+                    *psrc = (wj & kLLastOut) ? c : *psrc + c;
+                    if (ok) { key = arc; v = __double2ll_rn(xv[j] * bd * sc); }
+                } else if (wj & kLFin) {
+                    pool[(wj & 15) * NT] = 1.0;
                 }
-            } else if (wj & kLFin) {
-                pool[(wj & 15) * NT] = 1.0;
+                if (ACC == ACC_GLOBAL) red_runs(acc_g, key, v, lane);
+                else if (ACC == ACC_SMEM_CAS) { if (v) atomicAdd(acc_g + key, (unsigned long long)v); }
             }
         }
     }
 }
 
-template <int ACC>
-__global__ void __launch_bounds__(1024, 1) kr_regions(const KRParams P)
+template <int ACC, int MAXNT>
+__global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
 {
     extern __shared__ unsigned long long smem[];
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
@@ -194,8 +218,6 @@ __global__ void __launch_bounds__(1024, 1) kr_regions(const KRParams P)
         switch (rows) {
             case 4: kr_small<4, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
             case 8: kr_small<8, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
-            case 12: kr_small<12, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
-            case 16: kr_small<16, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
             default: kr_big<ACC>(P, aw, pool, NT, g, lane, xs, acc_g); break;
         }
     }
@@ -219,10 +241,10 @@ struct KSParams {
 
 __global__ void __launch_bounds__(512, 2) ks_strings(const KSParams P)
 {
-    extern __shared__ unsigned long long smem[];
+    extern __shared__ __align__(128) unsigned long long smem[];
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
-    double* tab = reinterpret_cast<double*>(smem);            // [n_arcs + 1]; id n_arcs (padding) -> 0
-    for (int i = tid; i <= P.n_arcs; i += NT) tab[i] = i < P.n_arcs ? P.logaw[i] : 0.0;
+    double* tab = reinterpret_cast<double*>(smem);            // [n_arcs + 16]; ids n_arcs.. (padding, one per bank pair) -> 0
+    for (int i = tid; i < P.n_arcs + 16; i += NT) tab[i] = i < P.n_arcs ? P.logaw[i] : 0.0;
     __syncthreads();
     long long ll_fx = 0;
     unsigned long long bad = 0;
@@ -277,6 +299,68 @@ __global__ void k_arc_weights_log(int n_arcs, const int32_t* __restrict__ arc_ti
         const double l = logweight_of(trans_tp[arc_tid[i]], x, 0) + (arc_eid[i] < 0 ? 0.0 : logweight_of(emis_tp[arc_eid[i]], x, 0));
         logaw[i] = l;
         aw[i] = exp(l);
+    }
+}
+
+
+// One launch in front of an evaluation of the segmented path: arc weights from x, accumulators reset
+// (replica 0 starts from the constant bridge part), reduction cells, scheduler counters and the output cleared.
+struct Prep6Params {
+    int n_arcs, replicas, n_red, n_out;
+    const int32_t* __restrict__ arc_tid; const int32_t* __restrict__ arc_eid;
+    const int32_t* __restrict__ trans_tp; const int32_t* __restrict__ emis_tp;
+    const double* __restrict__ x;
+    const unsigned long long* __restrict__ const_acc;
+    double* aw; double* logaw;
+    unsigned long long* acc; unsigned long long* red;
+    unsigned int* counters;            // [2]
+    double* out;
+};
+__global__ void k_prep6(const Prep6Params P)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.n_arcs) {
+        const double l = logweight_of(P.trans_tp[P.arc_tid[i]], P.x, 0) + (P.arc_eid[i] < 0 ? 0.0 : logweight_of(P.emis_tp[P.arc_eid[i]], P.x, 0));
+        P.logaw[i] = l;
+        P.aw[i] = exp(l);
+    }
+    if (i < P.n_arcs * P.replicas) P.acc[i] = i < P.n_arcs ? P.const_acc[i] : 0ull;
+    if (i < P.n_red) P.red[i] = 0ull;
+    if (i < P.n_out) P.out[i] = 0.0;
+    if (i < 2) P.counters[i] = 0u;
+}
+
+// One launch behind it: per-arc accumulators (all replicas) -> per-edge sums (a gather over the arcs of the
+// edge, fixed order, integer adds) -> and, without a communicator, straight to [loglik, bad, grad].
+struct Fin6Params {
+    int n_edges, n_arcs, replicas, n, finish;
+    const int32_t* __restrict__ e_off;      // [n_edges+1] arcs of every edge (transition edges, then emission edges)
+    const int32_t* __restrict__ e_arc;
+    const unsigned long long* __restrict__ acc;
+    unsigned long long* red;
+    const int32_t* __restrict__ edge_tp;
+    double inv_fx, inv_ll;
+    double* out;
+};
+__global__ void k_fold_finish6(const Fin6Params P)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0 && P.finish) {
+        const double bad = (double)P.red[1];
+        P.out[0] = bad > 0 ? -INFINITY : (double)(long long)P.red[0] * P.inv_ll;
+        P.out[1] = bad;
+    }
+    if (e >= P.n_edges) return;
+    unsigned long long s = 0;
+    for (int k = P.e_off[e]; k < P.e_off[e + 1]; ++k) {
+        const int a = P.e_arc[k];
+        for (int r = 0; r < P.replicas; ++r) s += P.acc[(size_t)r * P.n_arcs + a];
+    }
+    s += P.red[2 + e];
+    P.red[2 + e] = s;
+    if (P.finish) {
+        const int tp = P.edge_tp[e];
+        if (tp >= 0 && tp < P.n) P.out[2 + tp] = -(double)(long long)s * P.inv_fx;
     }
 }
 

@@ -396,6 +396,77 @@ inline uint64_t fnv1a(const uint32_t* w, size_t n)
 }
 }  // namespace
 
+// Schedules the bridge arcs of the (up to) 16 strings of one half-warp into time slots so that, in every slot,
+// the 16 lanes read table entries of 16 different classes (class = arc id mod 16 = the pair of shared-memory
+// banks an 8-byte entry lives in): a proper edge colouring of the bipartite multigraph lanes x classes, which
+// needs max(longest string, fullest class) colours (Koenig).  A lane that has nothing to read in a slot gets
+// one of 16 padding entries (ids n_arcs .. n_arcs+15, all log w = 0) of a class nobody else uses in that slot.
+struct BridgeScheduler {
+    uint16_t pad0;
+    std::vector<int16_t> laneCol, classCol;          // [16][D] colour -> class of the lane's edge / lane of the class's edge
+    std::vector<std::vector<uint16_t>> bucket;       // [16*16] arcs of (lane, class)
+    explicit BridgeScheduler(uint16_t pad) : pad0(pad), bucket(256) {}
+    int run(const uint16_t* const* arcs, const int* cnt, std::vector<uint16_t>& out)
+    {
+        int degL[16] = {0}, degK[16] = {0};
+        for (auto& b : bucket) b.clear();
+        for (int l = 0; l < 16; ++l)
+            for (int i = 0; i < cnt[l]; ++i) { const int k = arcs[l][i] & 15; bucket[l * 16 + k].push_back(arcs[l][i]); degL[l]++; degK[k]++; }
+        int D = 0;
+        for (int i = 0; i < 16; ++i) D = std::max(D, std::max(degL[i], degK[i]));
+        out.assign((size_t)D * 16, 0);
+        if (D == 0) return 0;
+        laneCol.assign((size_t)16 * D, -1); classCol.assign((size_t)16 * D, -1);
+        int freeL[16] = {0}, freeK[16] = {0};           // lowest colour that may be free (hint; verified below)
+        std::vector<int> path;
+        for (int l = 0; l < 16; ++l)
+            for (int k = 0; k < 16; ++k)
+                for (size_t m = 0; m < bucket[l * 16 + k].size(); ++m) {
+                    int a = freeL[l]; while (laneCol[(size_t)l * D + a] >= 0) ++a;
+                    int b = freeK[k]; while (classCol[(size_t)k * D + b] >= 0) ++b;
+                    freeL[l] = a; freeK[k] = b;
+                    if (classCol[(size_t)k * D + a] >= 0) {
+                        // colour a is taken at class k: flip the a/b alternating path that starts there
+                        path.clear();
+                        int ck = k;
+                        for (;;) {
+                            const int x = classCol[(size_t)ck * D + a];
+                            if (x < 0) break;
+                            path.push_back(x); path.push_back(ck); path.push_back(a);
+                            const int nk = laneCol[(size_t)x * D + b];
+                            if (nk < 0) break;
+                            path.push_back(x); path.push_back(nk); path.push_back(b);
+                            ck = nk;
+                        }
+                        for (size_t q = 0; q < path.size(); q += 3) { laneCol[(size_t)path[q] * D + path[q + 2]] = -1; classCol[(size_t)path[q + 1] * D + path[q + 2]] = -1; }
+                        for (size_t q = 0; q < path.size(); q += 3) {
+                            const int c2 = path[q + 2] == a ? b : a;
+                            laneCol[(size_t)path[q] * D + c2] = (int16_t)path[q + 1]; classCol[(size_t)path[q + 1] * D + c2] = (int16_t)path[q];
+                        }
+                        for (size_t q = 0; q < path.size(); q += 3) {       // the hints of touched nodes may have moved down
+                            freeL[path[q]] = std::min(freeL[path[q]], std::min(a, b)); freeK[path[q + 1]] = std::min(freeK[path[q + 1]], std::min(a, b));
+                        }
+                    }
+                    laneCol[(size_t)l * D + a] = (int16_t)k; classCol[(size_t)k * D + a] = (int16_t)l;
+                }
+        size_t taken[256] = {0};
+        for (int c = 0; c < D; ++c) {
+            unsigned used = 0;
+            for (int l = 0; l < 16; ++l) { const int k = laneCol[(size_t)l * D + c]; if (k >= 0) used |= 1u << k; }
+            for (int l = 0; l < 16; ++l) {
+                const int k = laneCol[(size_t)l * D + c];
+                if (k >= 0) out[(size_t)c * 16 + l] = bucket[l * 16 + k][taken[l * 16 + k]++];
+                else {
+                    const int fk = __builtin_ctz(~used & 0xffffu);               // a class no lane reads in this slot
+                    used |= 1u << fk;
+                    out[(size_t)c * 16 + l] = (uint16_t)(pad0 + ((fk - pad0) & 15));   // the padding entry of class fk
+                }
+            }
+        }
+        return D;
+    }
+};
+
 void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint8_t* alive, const int32_t* tokens,
                               const int64_t* offs, const double* p, const std::vector<int32_t>& ids, int n_slots,
                               double fx_scale, SegmentedCorpus& out)
@@ -540,12 +611,13 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
         for (int32_t k = 0; k < Y.len; ++k) { dst[(size_t)k * 32] = w[k]; out.n_type_edges += (w[k] >> 31); }
         out.typeW[slot] = Y.W;
     }
-    // ---- 4. KS layout: strings by (bridge words, region refs), longest first
+    // ---- 4. KS layout: strings by bridge count, longest first; the bridges of the 16 strings of a half-warp are
+    //         scheduled so that the 16 table reads of one shared-memory phase fall into 16 different bank pairs
     const int32_t dummy_type = (int32_t)(n_rg * 32);
-    auto nbw = [&](int64_t i) { const Local& L = loc[i % T]; return (int)((L.boff[i / T + 1] - L.boff[i / T] + 1) / 2); };
+    auto nbr = [&](int64_t i) { const Local& L = loc[i % T]; return (int)(L.boff[i / T + 1] - L.boff[i / T]); };
     auto nref = [&](int64_t i) { const Local& L = loc[i % T]; return (int)(L.sreg[i / T + 1] - L.sreg[i / T]); };
     std::stable_sort(ok.begin(), ok.end(), [&](int64_t a, int64_t b) {
-        const int wa = nbw(a), wb = nbw(b);
+        const int wa = nbr(a), wb = nbr(b);
         return wa != wb ? wa > wb : nref(a) > nref(b);
     });
     const int64_t n_sg = ((int64_t)ok.size() + 31) / 32;
@@ -553,15 +625,48 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
     out.sgref.assign((size_t)n_sg, 0);
     out.ksid.assign((size_t)n_sg * 32, -1);
     out.kp.assign((size_t)n_sg * 32, 0.0);
-    for (int64_t g = 0; g < n_sg; ++g) {
-        int mr = 0, mb = 0;
-        for (int64_t k = g * 32; k < std::min<int64_t>((int64_t)ok.size(), g * 32 + 32); ++k) { mr = std::max(mr, nref(ok[k])); mb = std::max(mb, nbw(ok[k])); }
-        mb = (mb + 3) / 4 * 4;
-        out.sgref[g] = mr;
-        out.sgoff[g + 1] = out.sgoff[g] + (int64_t)(mr + mb) * 32;
+    std::vector<std::vector<uint16_t>> gsched((size_t)n_sg);              // per group: [slots][32] arc ids
+    std::vector<int32_t> gslots((size_t)n_sg, 0);
+    auto schedule = [&](int t) {
+        BridgeScheduler sch((uint16_t)A.n_arcs);
+        const uint16_t* ptr[16]; int cnt[16];
+        std::vector<uint16_t> half[2];
+        for (int64_t g = t; g < n_sg; g += T) {
+            int slots[2] = {0, 0};
+            for (int hh = 0; hh < 2; ++hh) {
+                for (int l = 0; l < 16; ++l) {
+                    const int64_t k = g * 32 + hh * 16 + l;
+                    if (k < (int64_t)ok.size()) {
+                        const int64_t i = ok[k];
+                        const Local& L = loc[i % T];
+                        ptr[l] = L.bridges.data() + L.boff[i / T]; cnt[l] = (int)(L.boff[i / T + 1] - L.boff[i / T]);
+                    } else { ptr[l] = nullptr; cnt[l] = 0; }
+                }
+                slots[hh] = sch.run(ptr, cnt, half[hh]);
+            }
+            const int S2 = (std::max(slots[0], slots[1]) + 7) / 8 * 8;       // two slots per word, rows in fours
+            gslots[g] = S2;
+            std::vector<uint16_t>& G = gsched[g];
+            G.resize((size_t)S2 * 32);
+            for (int s2 = 0; s2 < S2; ++s2)
+                for (int hh = 0; hh < 2; ++hh)
+                    for (int l = 0; l < 16; ++l)
+                        G[(size_t)s2 * 32 + hh * 16 + l] = s2 < slots[hh] ? half[hh][(size_t)s2 * 16 + l] : (uint16_t)(A.n_arcs + l);
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(schedule, t);
+        schedule(0);
+        for (auto& x : th) x.join();
     }
-    const uint32_t pad_arc = (uint32_t)A.n_arcs;                          // table entry n_arcs holds log w = 0
-    out.swords.assign((size_t)out.sgoff[n_sg] + 32, pad_arc | (pad_arc << 16));
+    for (int64_t g = 0; g < n_sg; ++g) {
+        int mr = 0;
+        for (int64_t k = g * 32; k < std::min<int64_t>((int64_t)ok.size(), g * 32 + 32); ++k) mr = std::max(mr, nref(ok[k]));
+        out.sgref[g] = mr;
+        out.sgoff[g + 1] = out.sgoff[g] + (int64_t)(mr + gslots[g] / 2) * 32;
+    }
+    out.swords.assign((size_t)out.sgoff[n_sg] + 32, 0u);
     auto fill = [&](int t) {
         for (int64_t g = t; g < n_sg; g += T) {
             uint32_t* base = out.swords.data() + out.sgoff[g];
@@ -569,20 +674,19 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
             for (int l = 0; l < 32; ++l) {
                 const int64_t k = g * 32 + l;
                 for (int r = 0; r < mr; ++r) base[(size_t)r * 32 + l] = (uint32_t)dummy_type;
-                if (k >= (int64_t)ok.size()) continue;
-                const int64_t i = ok[k];
-                const Local& L = loc[i % T];
-                const size_t j = i / T;
-                out.ksid[k] = ids[i]; out.kp[k] = p[ids[i]];
-                int r = 0;
-                for (int64_t q = L.sreg[j]; q < L.sreg[j + 1]; ++q, ++r) base[(size_t)r * 32 + l] = (uint32_t)type_slot[reg_type[i % T][q]];
-                const uint16_t* b = L.bridges.data() + L.boff[j];
-                const int64_t nb = L.boff[j + 1] - L.boff[j];
-                for (int64_t q = 0; q < nb; q += 2) {
-                    const uint32_t lo = b[q], hi = q + 1 < nb ? b[q + 1] : pad_arc;
-                    base[(size_t)(mr + q / 2) * 32 + l] = lo | (hi << 16);
+                if (k < (int64_t)ok.size()) {
+                    const int64_t i = ok[k];
+                    const Local& L = loc[i % T];
+                    const size_t j = i / T;
+                    out.ksid[k] = ids[i]; out.kp[k] = p[ids[i]];
+                    int r = 0;
+                    for (int64_t q = L.sreg[j]; q < L.sreg[j + 1]; ++q, ++r) base[(size_t)r * 32 + l] = (uint32_t)type_slot[reg_type[i % T][q]];
                 }
+                const std::vector<uint16_t>& G = gsched[g];
+                for (int s2 = 0; s2 < gslots[g]; s2 += 2)
+                    base[(size_t)(mr + s2 / 2) * 32 + l] = (uint32_t)G[(size_t)s2 * 32 + l] | ((uint32_t)G[(size_t)(s2 + 1) * 32 + l] << 16);
             }
+            std::vector<uint16_t>().swap(gsched[g]);
         }
     };
     {

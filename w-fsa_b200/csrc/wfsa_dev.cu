@@ -132,7 +132,7 @@ struct wfsa_dev {
     double seg_host_ms = 0;
     DevBuf<uint32_t> d_krwords, d_kswords;
     DevBuf<int64_t> d_krgoff, d_ksgoff;
-    DevBuf<int32_t> d_krgrows, d_ksgref, d_kssid;
+    DevBuf<int32_t> d_krgrows, d_ksgref, d_kssid, d_eoff, d_earc;
     DevBuf<double> d_krW, d_krlq, d_ksp, d_kslogq, d_klogaw;
     std::vector<double> h_p;
     int64_t n_overflow = 0, n_active_w = 0;
@@ -147,7 +147,7 @@ struct wfsa_dev {
     long long kt_groups = 0;
     std::vector<uint8_t> h_overflow;
     int64_t launches = 0;
-    bool structure_done = false;
+    bool structure_done = false, lean_finished = false, lean_now = false;
     std::vector<uint8_t> h_recognised;
     // Hessian
     DevBuf<int64_t> d_hb_path_off, d_hb_col_off, d_hb_val_off;
@@ -207,7 +207,7 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     h->d_klacc.release(); h->d_klconst.release();
     h->d_krwords.release(); h->d_kswords.release(); h->d_krgoff.release(); h->d_ksgoff.release(); h->d_krgrows.release();
     h->d_ksgref.release(); h->d_kssid.release(); h->d_krW.release(); h->d_krlq.release(); h->d_ksp.release();
-    h->d_kslogq.release(); h->d_klogaw.release();
+    h->d_kslogq.release(); h->d_klogaw.release(); h->d_eoff.release(); h->d_earc.release();
     for (auto* b : u32) b->release();
     DevBuf<double>* f64[] = {&h->d_p, &h->d_x, &h->d_tw, &h->d_sw, &h->d_fw, &h->d_ltw, &h->d_lew, &h->d_logq, &h->d_pathcnt,
                              &h->d_out, &h->d_k3lat, &h->d_gscratch, &h->d_aw, &h->d_hb_counts, &h->d_hb_p, &h->d_hb_r, &h->d_H, &h->d_rmin};
@@ -331,10 +331,23 @@ static int setup_kl(wfsa_dev* h)
     CK(h->d_klcounter.alloc(2));
     if (h->kernel == 6) {
         CK(h->d_klogaw.alloc(A.n_arcs));
-        h->ks_smem = ((size_t)A.n_arcs + 1) * 8;
+        {   // arcs of every edge (transition edges, then emission edges) for the gather in k_fold_finish6
+            const int nt = h->fsa.n_trans(), ne = nt + h->fsa.n_emis();
+            std::vector<int32_t> off((size_t)ne + 1, 0), arc;
+            for (int a = 0; a < A.n_arcs; ++a) { off[A.arc_tid[a] + 1]++; if (A.arc_eid[a] >= 0) off[nt + A.arc_eid[a] + 1]++; }
+            for (int e = 0; e < ne; ++e) off[e + 1] += off[e];
+            arc.resize((size_t)off[ne]);
+            std::vector<int32_t> fill(off.begin(), off.end() - 1);
+            for (int a = 0; a < A.n_arcs; ++a) { arc[fill[A.arc_tid[a]]++] = a; if (A.arc_eid[a] >= 0) arc[fill[nt + A.arc_eid[a]]++] = a; }
+            CK(h->d_eoff.upload(off, h->stream)); CK(h->d_earc.upload(arc, h->stream));
+        }
+        h->ks_smem = ((size_t)A.n_arcs + 16) * 8;
         h->ks_grid = h->sm_count * 2;
-        cudaFuncSetAttribute(kr_regions<ACC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(kr_regions<ACC_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(kr_regions<ACC_GLOBAL, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(kr_regions<ACC_GLOBAL, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(kr_regions<ACC_GLOBAL, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(kr_regions<ACC_SMEM_CAS, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(kr_regions<ACC_NONE, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(ks_strings, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
     cudaFuncSetAttribute(kl_fwdbwd<ACC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -425,10 +438,10 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
     int kernel = h->opt.force_kernel;
     if (kernel == 0) {
         int nt = 0; size_t sm = 0; int K = (h->opt.reserved >> 16) & 0xff; if (K == 0) K = 8;
-        if (kl_possible(h, kLatMaxSlots, 0, nt, sm)) kernel = h->larcs.n_arcs < 65535 ? 6 : 5;
+        if (kl_possible(h, kLatMaxSlots, 0, nt, sm)) kernel = h->larcs.n_arcs < 65520 ? 6 : 5;
         else kernel = !h->fast.ok ? 3 : (kt_possible(h, K, nt, sm) ? 4 : (h->fast.warp_ok ? 1 : 2));
     }
-    if (kernel == 6 && h->larcs.n_arcs >= 65535) { h->err = "forced segmented kernel but the automaton has 65535 or more combined arcs"; return bail(WFSA_ERR_INVALID); }
+    if (kernel == 6 && h->larcs.n_arcs >= 65520) { h->err = "forced segmented kernel but the automaton has 65520 or more combined arcs"; return bail(WFSA_ERR_INVALID); }
     if (kernel == 5 || kernel == 6) { int nt = 0; size_t sm = 0; if (!kl_possible(h, kLatMaxSlots, 0, nt, sm)) { h->err = "forced compiled-lattice kernel but the arc weights do not fit shared memory"; return bail(WFSA_ERR_INVALID); } }
     if ((kernel == 1 || kernel == 2 || kernel == 4) && !h->fast.ok) { h->err = "forced fast kernel but emissions are not all one token long"; return bail(WFSA_ERR_INVALID); }
     if (kernel == 1 && !h->fast.warp_ok) { h->err = "forced warp-per-string kernel but more than 32 states emit one symbol"; return bail(WFSA_ERR_INVALID); }
@@ -541,14 +554,17 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
     cudaStream_t st = h->stream;
     if (C.n_order <= 0) return;
     if (kernel == 6) {
-        cudaMemsetAsync(h->d_klcounter.p, 0, 8, st);
+        if (!h->lean_now) cudaMemsetAsync(h->d_klcounter.p, 0, 8, st);
         if (h->kr_groups > 0) {
             KRParams P{};
             P.aw = h->d_klaw.p; P.words = h->d_krwords.p; P.goff = h->d_krgoff.p; P.grows = h->d_krgrows.p; P.typeW = h->d_krW.p;
             P.lq = h->d_krlq.p; P.n_groups = h->kr_groups; P.xs = h->d_klxs.p; P.xs_rows = (size_t)std::max<int64_t>(h->kl_max_words, 1);
             P.counter = h->d_klcounter.p; P.acc = h->d_klacc.p; P.fx_scale = O.fx_scale; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas;
-            if (h->opt.reserved & 2) kr_regions<ACC_NONE><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // timing experiment
-            else kr_regions<ACC_GLOBAL><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
+            if (h->opt.reserved & 2) kr_regions<ACC_NONE, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // timing experiment
+            else if (h->opt.reserved & 1) kr_regions<ACC_SMEM_CAS, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // plain REDs
+            else if (h->kl_block <= 512) kr_regions<ACC_GLOBAL, 512><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
+            else if (h->kl_block <= 768) kr_regions<ACC_GLOBAL, 768><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
+            else kr_regions<ACC_GLOBAL, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
             h->launches++;
         }
         KSParams S{};
@@ -641,7 +657,18 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
     const HostFsa& F = h->fsa;
     cudaStream_t st = h->stream;
     const int unit = (mode == MODE_STRUCT) ? 1 : 0;
-    if (clear) {
+    // segmented path without overflow strings: one prep launch, KR, KS, one fold(+finish) launch
+    const bool lean6 = kernel == 6 && mode == MODE_EVAL && clear && fold && (kernel2 == 0 || n_order2 == 0);
+    if (lean6) {
+        Prep6Params P{};
+        P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas; P.n_red = (int)h->d_red.n; P.n_out = (int)h->d_out.n;
+        P.arc_tid = h->d_kl_arc_tid.p; P.arc_eid = h->d_kl_arc_eid.p; P.trans_tp = h->d_trans_tp.p; P.emis_tp = h->d_emis_tp.p;
+        P.x = h->d_x.p; P.const_acc = h->d_klconst.p; P.aw = h->d_klaw.p; P.logaw = h->d_klogaw.p; P.acc = h->d_klacc.p;
+        P.red = h->d_red.p; P.counters = h->d_klcounter.p; P.out = h->d_out.p;
+        const int total = std::max({P.n_arcs * P.replicas, P.n_red, P.n_out, 2});
+        k_prep6<<<(total + 255) / 256, 256, 0, st>>>(P);
+        h->launches++;
+    } else if (clear) {
         CK(cudaMemsetAsync(h->d_red.p, 0, h->d_red.n * 8, st));
         if (h->fast.ok) CK(cudaMemsetAsync(h->d_acc.p, 0, h->d_acc.n * 8, st));
         const int n_slots = h->fast.ok ? h->fast.n_slots : 0;
@@ -687,10 +714,23 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
         if (h->kev_used < h->kev.size()) { e0 = h->kev[h->kev_used].first; e1 = h->kev[h->kev_used].second; h->kev_used++; }
     }
     if (e0) cudaEventRecord(e0, st);
+    h->lean_now = lean6;
     launch_main(h, kernel, mode, CorpusD{h->d_tokens.p, h->d_offs.p, h->d_p.p, d_order, n_order}, O);
     if (kernel2) launch_main(h, kernel2, mode, CorpusD{h->d_tokens.p, h->d_offs.p, h->d_p.p, d_order2, n_order2}, O);
     if (e1) cudaEventRecord(e1, st);
     CK(cudaGetLastError());
+    if (lean6) {
+        Fin6Params P{};
+        P.n_edges = h->n_edges; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas; P.n = h->n; P.finish = h->comm ? 0 : 1;
+        P.e_off = h->d_eoff.p; P.e_arc = h->d_earc.p; P.acc = h->d_klacc.p; P.red = h->d_red.p; P.edge_tp = h->d_edge_tp.p;
+        P.inv_fx = std::ldexp(1.0, -(int)h->fx_log2); P.inv_ll = std::ldexp(1.0, -(int)h->ll_log2); P.out = h->d_out.p;
+        k_fold_finish6<<<(std::max(h->n_edges, 1) + 127) / 128, 128, 0, st>>>(P);
+        h->launches++;
+        CK(cudaGetLastError());
+        h->lean_finished = !h->comm;
+        return WFSA_OK;
+    }
+    h->lean_finished = false;
     if (fold && (kernel == 5 || kernel == 6)) {
         const int na = h->larcs.n_arcs;
         k_arcs_to_edges<<<(na + 255) / 256, 256, 0, st>>>(na, 0, F.n_trans(), h->d_klacc.p, h->replicas, h->d_kl_arc_tid.p,
@@ -927,6 +967,7 @@ extern "C" int wfsa_dev_eval_launch(wfsa_dev* h)
     int rc = launch_pipeline(h, MODE_EVAL, h->kernel, h->d_order.p, h->n_active,
                              h->kernel >= 4 ? h->secondary : 0, h->d_order_w.p, h->n_active_w, true, true);
     if (rc != WFSA_OK) return rc;
+    if (h->lean_finished) return WFSA_OK;          // k_fold_finish6 already wrote [loglik, bad, grad]
     rc = nccl_allreduce(h, h->d_red.p, h->d_red.n, ncclUint64, ncclSum);
     if (rc != WFSA_OK) return rc;
     CK(cudaMemsetAsync(h->d_out.p, 0, h->d_out.n * 8, h->stream));
@@ -1207,7 +1248,7 @@ extern "C" int wfsa_segmented_compile(const wfsa_fsa_desc* fd, const wfsa_corpus
     wfsa_segmented* s = new wfsa_segmented();
     build_lattice_arcs(f, g, s->arcs);
     const LatticeArcs& A = s->arcs;
-    if (A.n_arcs >= 65535 || A.n_arcs >= (1 << kLatArcBits)) { delete s; g_create_error = "segmented_compile: too many combined arcs"; return WFSA_ERR_LIMIT; }
+    if (A.n_arcs >= 65520 || A.n_arcs >= (1 << kLatArcBits)) { delete s; g_create_error = "segmented_compile: too many combined arcs"; return WFSA_ERR_LIMIT; }
     std::vector<uint8_t> alive((size_t)A.n_arcs, 1);
     if (trimmed)
         for (int a = 0; a < A.n_arcs; ++a) {
