@@ -344,23 +344,30 @@ struct Fin6Params {
 };
 __global__ void k_fold_finish6(const Fin6Params P)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e == 0 && P.finish) {
+    // one warp per edge: its lanes share the (arc, replica) cells of the edge, then a shuffle sum (integers)
+    const int lane = threadIdx.x & 31;
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (e == 0 && lane == 0 && P.finish) {
         const double bad = (double)P.red[1];
         P.out[0] = bad > 0 ? -INFINITY : (double)(long long)P.red[0] * P.inv_ll;
         P.out[1] = bad;
     }
     if (e >= P.n_edges) return;
+    const int k0 = P.e_off[e], cells = (P.e_off[e + 1] - k0) * P.replicas;
     unsigned long long s = 0;
-    for (int k = P.e_off[e]; k < P.e_off[e + 1]; ++k) {
-        const int a = P.e_arc[k];
-        for (int r = 0; r < P.replicas; ++r) s += P.acc[(size_t)r * P.n_arcs + a];
+    for (int c = lane; c < cells; c += 32) {
+        const int a = P.e_arc[k0 + c / P.replicas], r = c % P.replicas;
+        s += P.acc[(size_t)r * P.n_arcs + a];
     }
-    s += P.red[2 + e];
-    P.red[2 + e] = s;
-    if (P.finish) {
-        const int tp = P.edge_tp[e];
-        if (tp >= 0 && tp < P.n) P.out[2 + tp] = -(double)(long long)s * P.inv_fx;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if (lane == 0) {
+        s += P.red[2 + e];
+        P.red[2 + e] = s;
+        if (P.finish) {
+            const int tp = P.edge_tp[e];
+            if (tp >= 0 && tp < P.n) P.out[2 + tp] = -(double)(long long)s * P.inv_fx;
+        }
     }
 }
 

@@ -724,7 +724,7 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
         P.n_edges = h->n_edges; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas; P.n = h->n; P.finish = h->comm ? 0 : 1;
         P.e_off = h->d_eoff.p; P.e_arc = h->d_earc.p; P.acc = h->d_klacc.p; P.red = h->d_red.p; P.edge_tp = h->d_edge_tp.p;
         P.inv_fx = std::ldexp(1.0, -(int)h->fx_log2); P.inv_ll = std::ldexp(1.0, -(int)h->ll_log2); P.out = h->d_out.p;
-        k_fold_finish6<<<(std::max(h->n_edges, 1) + 127) / 128, 128, 0, st>>>(P);
+        k_fold_finish6<<<(std::max(h->n_edges, 1) + 7) / 8, 256, 0, st>>>(P);      // one warp per edge
         h->launches++;
         CK(cudaGetLastError());
         h->lean_finished = !h->comm;
