@@ -48,7 +48,7 @@ def region_fwdbwd(col, aw, big):
             assert w == 0, "padding must be zero"
     if not big:
         q = pool[last]
-    assert n_edges >= 2 and (big == (n_edges > 8))
+    assert n_edges >= 2 and (big == (n_edges > 16))
     beta = np.full(16, np.nan)
     beta[last] = 1.0
     post = {}
@@ -73,7 +73,7 @@ def interpret(seg, aw, n_arcs):
     seen = set()
     for g in range(n_rg):
         rows = int(rgrows[g])
-        assert rows in (4, 8) or (rows >= 16 and rows % 16 == 0)
+        assert rows in (4, 8, 12, 16) or (rows >= 32 and rows % 16 == 0)
         block = seg["rwords"][rgoff[g]:rgoff[g] + rows * 32].reshape(rows, 32)
         for l in range(32):
             col = block[:, l]
@@ -84,7 +84,7 @@ def interpret(seg, aw, n_arcs):
             assert key not in seen, "identical regions must be merged into one type"
             seen.add(key)
             assert W_[g * 32 + l] > 0.0
-            lq[g * 32 + l], post = region_fwdbwd(col, aw, rows >= 16)
+            lq[g * 32 + l], post = region_fwdbwd(col, aw, rows > 16)
             for arc, v in post.items():
                 acc[arc] += W_[g * 32 + l] * v
     sgoff, sgref, ksid, kp = seg["sgoff"], seg["sgref"], seg["ksid"], seg["kp"]
@@ -165,7 +165,7 @@ def test_config4_shape_bridges_regions_and_type_merging():
     st = seg["stats"]
     assert len(seg["overflow"]) == 0 and len(handled) == 600
     assert st[4] > 0 and st[1] > st[0] > 0, "expected bridges and merged region types"
-    assert (seg["rgrows"] >= 16).any() and (seg["rgrows"] <= 8).any(), "expected small and big regions"
+    assert (seg["rgrows"] > 16).any() and (seg["rgrows"] <= 16).any(), "expected small and big regions"
     assert np.allclose(ee, oee, rtol=1e-10, atol=1e-9)
     # a pool of 2 slots cannot hold an ambiguous region: such strings are reported, never mis-compiled
     seg2, _, _, _, handled2 = check(low, trimmed, x, n_slots=2)

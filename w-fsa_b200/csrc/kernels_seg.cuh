@@ -20,7 +20,7 @@ struct KRParams {
     const double* __restrict__ aw;        // [n_arcs] a(u,v) * b(v,e)
     const uint32_t* __restrict__ words;   // word j of lane l of group g at goff[g] + j*32 + l
     const int64_t* __restrict__ goff;     // [n_groups+1]
-    const int32_t* __restrict__ grows;    // [n_groups] 4/8 = small region class, else big (multiple of 16)
+    const int32_t* __restrict__ grows;    // [n_groups] 4/8/12/16 = small region class, else big (multiple of 16, >= 32)
     const double* __restrict__ typeW;     // [n_groups*32]
     double* lq;                           // [n_groups*32 + 1] log q per type (last = dummy, stays 0)
     long long n_groups;
@@ -32,71 +32,82 @@ struct KRParams {
     int n_arcs, replicas;
 };
 
-// Fixed-point add of one value per lane into acc[key].  Region types are sorted by their arcs, so neighbouring
-// lanes mostly hold the same arc at the same edge position: runs of equal keys are summed with shuffles
-// (integers: exact, order independent) and only the first lane of a run issues the RED.  Must be called by
-// all 32 lanes; key < 0 = nothing to add.
-__device__ __forceinline__ void red_runs(unsigned long long* acc_g, int key, long long v, int lane)
+// Adds one fixed-point value per lane into acc[key].  Region types are sorted by their arcs, so at the first
+// edge positions a whole warp usually holds ONE arc: then the 32 values are summed with shuffles (integers:
+// exact, order independent) and a single RED is issued; otherwise every lane issues its own.
+// Must be called by all 32 lanes; key < 0 = nothing to add.
+__device__ __forceinline__ void red_uniform(unsigned long long* acc_g, int key, long long v, int lane)
 {
-    const int kp = __shfl_up_sync(FULL, key, 1);
-    const bool head = lane == 0 || kp != key;
-    const unsigned heads = __ballot_sync(FULL, head);
-    const unsigned later = lane == 31 ? 0u : heads & ~((2u << lane) - 1u);
-    const int end = later ? __ffs(later) - 1 : 32;          // first lane of the next run
+    const int k0 = __shfl_sync(FULL, key, 0);
+    if (__all_sync(FULL, key == k0)) {
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const long long v2 = __shfl_down_sync(FULL, v, d);
-        if (lane + d < end) v += v2;
-    }
-    if (head && key >= 0 && v) atomicAdd(acc_g + key, (unsigned long long)v);
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if (lane == 0 && key >= 0 && v) atomicAdd(acc_g + key, (unsigned long long)v);
+    } else if (key >= 0 && v) atomicAdd(acc_g + key, (unsigned long long)v);
 }
 
-// One small region per thread, NE word rows, everything in registers except the pool.
+// One small region per thread, NE <= 16 word rows (bare EDGE words).  The x values of the forward sweep stay in
+// registers; the words are held in registers for NE <= 8 and re-read (L1) by the backward sweep otherwise.
 template <int NE, int ACC>
 __device__ __forceinline__ void kr_small(const KRParams& P, const double* aw, double* pool, int NT, long long g, int lane,
                                          unsigned long long* acc_g)
 {
+    constexpr int NB = (NE + 7) / 8;                          // batches of up to 8 words
     const uint32_t* wp = P.words + P.goff[g] + lane;
-    uint32_t w[NE];
-#pragma unroll
-    for (int j = 0; j < NE; ++j) w[j] = __ldcs(wp + (size_t)j * 32);
     const double W = P.typeW[g * 32 + lane];
     double xs[NE];
+    uint32_t w[8];
     pool[0] = 1.0;                                            // the entry node owns slot 0
     int last = 0;
+    bool any = false;
 #pragma unroll
-    for (int j = 0; j < NE; ++j) {
-        const uint32_t wj = w[j];
-        if (wj & kLEdge) {
-            const int src = (wj >> 19) & 15, dst = (wj >> 23) & 15, arc = wj & 0x7fff;
-            const double xv = pool[src * NT] * aw[arc];
-            xs[j] = xv;
-            double* pd = pool + dst * NT;
-            *pd = (wj & kLFirstIn) ? xv : *pd + xv;
-            last = dst;
+    for (int b = 0; b < NB; ++b) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (b * 8 + j < NE) w[j] = __ldcs(wp + (size_t)(b * 8 + j) * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (b * 8 + j >= NE) continue;
+            const uint32_t wj = w[j];
+            if (wj & kLEdge) {
+                const int src = (wj >> 19) & 15, dst = (wj >> 23) & 15, arc = wj & 0x7fff;
+                const double xv = pool[src * NT] * aw[arc];
+                xs[b * 8 + j] = xv;
+                double* pd = pool + dst * NT;
+                *pd = (wj & kLFirstIn) ? xv : *pd + xv;
+                last = dst;
+                any = true;
+            }
         }
     }
     const double q = pool[last * NT];
-    const bool ok = (w[0] & kLEdge) && q > 0.0 && isfinite(q);
-    if (w[0] & kLEdge) P.lq[g * 32 + lane] = ok ? log(q) : -INFINITY;
+    const bool ok = any && q > 0.0 && isfinite(q);
+    if (any) P.lq[g * 32 + lane] = ok ? log(q) : -INFINITY;
     const double sc = ok ? W * P.fx_scale / q : 0.0;
     pool[last * NT] = 1.0;
 #pragma unroll
-    for (int j = NE - 1; j >= 0; --j) {
-        const uint32_t wj = w[j];
-        int key = -1;
-        long long v = 0;
-        if (wj & kLEdge) {
-            const int src = (wj >> 19) & 15, dst = (wj >> 23) & 15, arc = wj & 0x7fff;
-            const double bd = pool[dst * NT];
-            const double c = aw[arc] * bd;
-            double* psrc = pool + src * NT;
-            *psrc = (wj & kLLastOut) ? c : *psrc + c;
-            key = arc;
-            v = __double2ll_rn(xs[j] * bd * sc);
+    for (int b = NB - 1; b >= 0; --b) {
+        if (NB > 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (b * 8 + j < NE) w[j] = __ldg(wp + (size_t)(b * 8 + j) * 32);
         }
-        if (ACC == ACC_GLOBAL) red_runs(acc_g, key, v, lane);
-        else if (ACC == ACC_SMEM_CAS) { if (v) atomicAdd(acc_g + key, (unsigned long long)v); }   // plain REDs (experiment)
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+            if (b * 8 + j >= NE) continue;
+            const uint32_t wj = w[j];
+            int key = -1;
+            long long v = 0;
+            if (wj & kLEdge) {
+                const int src = (wj >> 19) & 15, dst = (wj >> 23) & 15, arc = wj & 0x7fff;
+                const double bd = pool[dst * NT];
+                const double c = aw[arc] * bd;
+                double* psrc = pool + src * NT;
+                *psrc = (wj & kLLastOut) ? c : *psrc + c;
+                key = arc;
+                v = __double2ll_rn(xs[b * 8 + j] * bd * sc);
+            }
+            if (ACC == ACC_GLOBAL && b * 8 + j < 2) red_uniform(acc_g, key, v, lane);
+            else if (ACC != ACC_NONE) { if (v) atomicAdd(acc_g + key, (unsigned long long)v); }
+        }
     }
 }
 
@@ -190,8 +201,7 @@ __device__ __forceinline__ void kr_big(const KRParams& P, const double* aw, doub
                 } else if (wj & kLFin) {
                     pool[(wj & 15) * NT] = 1.0;
                 }
-                if (ACC == ACC_GLOBAL) red_runs(acc_g, key, v, lane);
-                else if (ACC == ACC_SMEM_CAS) { if (v) atomicAdd(acc_g + key, (unsigned long long)v); }
+                if (ACC != ACC_NONE && v) atomicAdd(acc_g + key, (unsigned long long)v);
             }
         }
     }
@@ -218,6 +228,8 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
         switch (rows) {
             case 4: kr_small<4, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
             case 8: kr_small<8, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
+            case 12: kr_small<12, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
+            case 16: kr_small<16, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
             default: kr_big<ACC>(P, aw, pool, NT, g, lane, xs, acc_g); break;
         }
     }
@@ -239,7 +251,8 @@ struct KSParams {
     int n_arcs;
 };
 
-__global__ void __launch_bounds__(512, 2) ks_strings(const KSParams P)
+template <int MAXNT, int MINB>
+__global__ void __launch_bounds__(MAXNT, MINB) ks_strings(const KSParams P)
 {
     extern __shared__ __align__(128) unsigned long long smem[];
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
@@ -248,32 +261,54 @@ __global__ void __launch_bounds__(512, 2) ks_strings(const KSParams P)
     __syncthreads();
     long long ll_fx = 0;
     unsigned long long bad = 0;
-    for (;;) {
-        long long g = 0;
-        if (lane == 0) g = (long long)atomicAdd(P.counter, 1u);
-        g = __shfl_sync(FULL, g, 0);
-        if (g >= P.n_groups) break;
+    long long g = 0;
+    if (lane == 0) g = (long long)atomicAdd(P.counter, 1u);
+    g = __shfl_sync(FULL, g, 0);
+    while (g < P.n_groups) {
+        long long gn = 0;                                     // the next group's id is fetched while this one streams
+        if (lane == 0) gn = (long long)atomicAdd(P.counter, 1u);
         const long long o = P.goff[g];
         const int rows = (int)((P.goff[g + 1] - o) >> 5), nref = P.gref[g];
         const uint32_t* wp = P.words + o + lane;
-        const double ps = P.p[g * 32 + lane];
-        double r = 0.0;
-        for (int i = 0; i < nref; ++i) r += P.lq[__ldcs(wp + (size_t)i * 32)];
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        for (int i = nref; i < rows; i += 4) {
-            const uint32_t a = __ldcs(wp + (size_t)i * 32), b = __ldcs(wp + (size_t)(i + 1) * 32);
-            const uint32_t c = __ldcs(wp + (size_t)(i + 2) * 32), d = __ldcs(wp + (size_t)(i + 3) * 32);
-            s0 += tab[a & 0xffffu]; s1 += tab[a >> 16];
-            s2 += tab[b & 0xffffu]; s3 += tab[b >> 16];
-            s0 += tab[c & 0xffffu]; s1 += tab[c >> 16];
-            s2 += tab[d & 0xffffu]; s3 += tab[d >> 16];
+        double s0 = 0.0, s1 = 0.0;
+        // bridge words: chunks of 8 rows, the next chunk's loads are in flight while this one is summed
+        int i = nref;
+        uint32_t a[8];
+        const int nfull = (rows - nref) >> 3;
+        if (nfull > 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = __ldcs(wp + (size_t)(i + j) * 32);
         }
-        const double lqs = ((s0 + s1) + (s2 + s3)) + r;
+        for (int c = 0; c < nfull; ++c) {
+            i += 8;
+            uint32_t b[8];
+            if (c + 1 < nfull) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) b[j] = __ldcs(wp + (size_t)(i + j) * 32);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s0 += tab[a[j] & 0xffffu]; s1 += tab[a[j] >> 16]; }
+            if (c + 1 < nfull) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = b[j];
+            }
+        }
+        if (i < rows) {                                       // rows - nref is a multiple of 4
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[j] = __ldcs(wp + (size_t)(i + j) * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s0 += tab[a[j] & 0xffffu]; s1 += tab[a[j] >> 16]; }
+        }
+        double r = 0.0;
+        for (int k = 0; k < nref; ++k) r += P.lq[__ldcs(wp + (size_t)k * 32)];
+        const double ps = P.p[g * 32 + lane];
+        const double lqs = (s0 + s1) + r;
         if (ps != 0.0) {
             P.logq[g * 32 + lane] = lqs;
             if (isfinite(lqs)) ll_fx += __double2ll_rn(ps * lqs * P.ll_scale);
             else bad++;
         }
+        g = __shfl_sync(FULL, gn, 0);
     }
     for (int o = 16; o; o >>= 1) { ll_fx += __shfl_xor_sync(FULL, ll_fx, o); bad += __shfl_xor_sync(FULL, bad, o); }
     if (lane == 0) {

@@ -102,8 +102,8 @@ void compile_corpus(const HostFsa& f, const LatticeArcs& A, const uint8_t* arc_a
 // Region words: EDGE words as above with region-local slots.  Regions of at most kSegSmallMax edges
 // are stored as bare EDGE words (the exit node is the dst of the last edge); larger regions use the
 // full stream format above (CHECK every kCheckEvery-th word, FIN last) so that they can be rescaled.
-constexpr int kSegSmallMax = 8;           // edges of a "small" region (unrolled in registers on the device)
-constexpr int kSegSmallStep = 4;          // small regions are padded to 4 or 8 word rows
+constexpr int kSegSmallMax = 16;          // edges of a "small" region (unrolled in registers on the device)
+constexpr int kSegSmallStep = 4;          // small regions are padded to 4, 8, 12 or 16 word rows
 
 struct SegString {                         // one string, compiled
     int status = 0;                        // 1 ok, 0 no accepting path, -1 needs another kernel
@@ -116,7 +116,7 @@ int compile_segments(const HostFsa& f, const LatticeArcs& A, const uint8_t* arc_
 
 struct SegmentedCorpus {
     // KR: region types in groups of 32 (one warp), word j of lane l of group g at rgoff[g] + j*32 + l;
-    // type id = g*32 + l; rgrows[g] = word rows of the group (4/8 = small, otherwise a multiple of 16)
+    // type id = g*32 + l; rgrows[g] = word rows of the group (4/8/12/16 = small, otherwise a multiple of 16, at least 32)
     std::vector<uint32_t> rwords;
     std::vector<int64_t> rgoff;                // [n_rgroups+1]
     std::vector<int32_t> rgrows;               // [n_rgroups]
