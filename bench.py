@@ -261,6 +261,7 @@ def run_ours(args, rank, world, local):
     ms = dev.timer_end()
     barrier()
     kms, klaunches = dev.timer_kernel_ms()
+    split = dev.timer_split_ms()
     launches = dev.info()["kernels_launched"] - launches0
     ll, grad = dev.eval_fetch()
     # ---- end to end through the host-buffer C-ABI call
@@ -329,7 +330,10 @@ def run_ours(args, rank, world, local):
                        "seeds": {"automaton": cfg["seed"], "strings": 1235}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": {1: "k2_fwdbwd", 2: "k3_fwdbwd", 3: "kg_fwdbwd", 4: "kt_fwdbwd", 5: "kl_fwdbwd", 6: "kr_regions+ks_strings"}[info["kernel"]],
-                         "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_ms": k_ms,
+                         **({"kernels_ms": {"kr_regions": split[0] / max(klaunches, 1), "ks_strings": split[1] / max(klaunches, 1)}}
+                            if info["kernel"] == 6 else {}),
+                         "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_share_of_step": kms_max / ms_max},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * (n + 2),
                     "ms_per_step": e2e_max * 1e3 / steps},

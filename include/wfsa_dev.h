@@ -141,6 +141,8 @@ int wfsa_dev_timer_begin(wfsa_dev* h);
 int wfsa_dev_timer_end(wfsa_dev* h, float* ms);
 /* ms spent in the dominant kernel (forward-backward) over the launches since timer_begin. */
 int wfsa_dev_timer_kernel_ms(wfsa_dev* h, float* ms, int64_t* launches);
+/* segmented kernels (6): the same time split into kr_regions (first) and ks_strings (second); 0 otherwise */
+int wfsa_dev_timer_split_ms(wfsa_dev* h, float* first_ms, float* second_ms);
 
 /* Introspection */
 typedef struct {

@@ -219,11 +219,9 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
     const long long gwarp = ((long long)blockIdx.x * NT + tid) >> 5;
     double* const xs = P.xs + (size_t)gwarp * P.xs_rows * 32 + lane;
     unsigned long long* const acc_g = P.acc + (size_t)(blockIdx.x % P.replicas) * (size_t)P.n_arcs;
-    for (;;) {
-        long long g = 0;
-        if (lane == 0) g = (long long)atomicAdd(P.counter, 1u);
-        g = __shfl_sync(FULL, g, 0);
-        if (g >= P.n_groups) break;
+    // groups are sorted by cost (big regions first, then 16, 12, 8, 4 rows): a static round-robin is balanced
+    const long long GW = ((long long)gridDim.x * NT) >> 5;
+    for (long long g = gwarp; g < P.n_groups; g += GW) {
         const int rows = P.grows[g];
         switch (rows) {
             case 4: kr_small<4, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
@@ -261,20 +259,27 @@ __global__ void __launch_bounds__(MAXNT, MINB) ks_strings(const KSParams P)
     __syncthreads();
     long long ll_fx = 0;
     unsigned long long bad = 0;
-    long long g = 0;
-    if (lane == 0) g = (long long)atomicAdd(P.counter, 1u);
-    g = __shfl_sync(FULL, g, 0);
-    while (g < P.n_groups) {
-        long long gn = 0;                                     // the next group's id is fetched while this one streams
-        if (lane == 0) gn = (long long)atomicAdd(P.counter, 1u);
-        const long long o = P.goff[g];
-        const int rows = (int)((P.goff[g + 1] - o) >> 5), nref = P.gref[g];
+    // groups are sorted by length, so a static round-robin over the warps is balanced (no scheduler atomics);
+    // the descriptor of a warp's next group is loaded while the current one streams
+    const long long gw0 = ((long long)blockIdx.x * NT + tid) >> 5, GW = ((long long)gridDim.x * NT) >> 5;
+    long long o = 0, o1 = 0; int nref = 0;
+    if (gw0 < P.n_groups) { o = P.goff[gw0]; o1 = P.goff[gw0 + 1]; nref = P.gref[gw0]; }
+    for (long long g = gw0; g < P.n_groups; g += GW) {
+        const int rows = (int)((o1 - o) >> 5);
         const uint32_t* wp = P.words + o + lane;
+        const int nref_g = nref;
+        if (g + GW < P.n_groups) { o = P.goff[g + GW]; o1 = P.goff[g + GW + 1]; nref = P.gref[g + GW]; }
+        // the first region references are gathered now and added after the bridge sum (their latency overlaps it)
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        if (nref_g > 0) v0 = P.lq[__ldcs(wp)];
+        if (nref_g > 1) v1 = P.lq[__ldcs(wp + 32)];
+        if (nref_g > 2) v2 = P.lq[__ldcs(wp + 64)];
+        if (nref_g > 3) v3 = P.lq[__ldcs(wp + 96)];
         double s0 = 0.0, s1 = 0.0;
         // bridge words: chunks of 8 rows, the next chunk's loads are in flight while this one is summed
-        int i = nref;
+        int i = nref_g;
         uint32_t a[8];
-        const int nfull = (rows - nref) >> 3;
+        const int nfull = (rows - nref_g) >> 3;
         if (nfull > 0) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) a[j] = __ldcs(wp + (size_t)(i + j) * 32);
@@ -299,8 +304,8 @@ __global__ void __launch_bounds__(MAXNT, MINB) ks_strings(const KSParams P)
 #pragma unroll
             for (int j = 0; j < 4; ++j) { s0 += tab[a[j] & 0xffffu]; s1 += tab[a[j] >> 16]; }
         }
-        double r = 0.0;
-        for (int k = 0; k < nref; ++k) r += P.lq[__ldcs(wp + (size_t)k * 32)];
+        double r = (v0 + v1) + (v2 + v3);
+        for (int k = 4; k < nref_g; ++k) r += P.lq[__ldcs(wp + (size_t)k * 32)];
         const double ps = P.p[g * 32 + lane];
         const double lqs = (s0 + s1) + r;
         if (ps != 0.0) {
@@ -308,7 +313,6 @@ __global__ void __launch_bounds__(MAXNT, MINB) ks_strings(const KSParams P)
             if (isfinite(lqs)) ll_fx += __double2ll_rn(ps * lqs * P.ll_scale);
             else bad++;
         }
-        g = __shfl_sync(FULL, gn, 0);
     }
     for (int o = 16; o; o >>= 1) { ll_fx += __shfl_xor_sync(FULL, ll_fx, o); bad += __shfl_xor_sync(FULL, bad, o); }
     if (lane == 0) {

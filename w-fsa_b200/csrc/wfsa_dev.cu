@@ -163,6 +163,8 @@ struct wfsa_dev {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kev;
     size_t kev_used = 0; bool timing = false;
+    std::vector<cudaEvent_t> kev_mid;           // segmented path: between kr_regions and ks_strings
+    cudaEvent_t mid_now = nullptr;
 };
 
 #define CK(call)                                                                              \
@@ -221,6 +223,7 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     if (h->ev_begin) cudaEventDestroy(h->ev_begin);
     if (h->ev_end) cudaEventDestroy(h->ev_end);
     for (auto& e : h->kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto& e : h->kev_mid) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -344,9 +347,9 @@ static int setup_kl(wfsa_dev* h)
         }
         h->ks_smem = ((size_t)A.n_arcs + 16) * 8;
         {   // KS launch shape: WFSA_KS_SHAPE = "<threads>x<CTAs per SM>" selects one of the compiled variants (tuning)
-            int nt = 768, nb = 2;
+            int nt = 512, nb = 2;
             if (const char* e = getenv("WFSA_KS_SHAPE")) sscanf(e, "%dx%d", &nt, &nb);
-            if (!((nt == 1024 && nb == 2) || (nt == 768 && nb == 2) || (nt == 512 && nb == 2) || (nt == 512 && nb == 3) || (nt == 1024 && nb == 1))) { nt = 1024; nb = 2; }
+            if (!((nt == 1024 && nb == 2) || (nt == 768 && nb == 2) || (nt == 512 && nb == 2) || (nt == 512 && nb == 3) || (nt == 1024 && nb == 1))) { nt = 512; nb = 2; }
             if (h->ks_smem * nb > 220 * 1024) { nt = 1024; nb = 1; }
             h->ks_block = nt; h->ks_grid = h->sm_count * nb; h->ks_ctas = nb;
         }
@@ -578,6 +581,7 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
             else kr_regions<ACC_GLOBAL, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
             h->launches++;
         }
+        if (h->mid_now) cudaEventRecord(h->mid_now, st);
         KSParams S{};
         S.logaw = h->d_klogaw.p; S.words = h->d_kswords.p; S.goff = h->d_ksgoff.p; S.gref = h->d_ksgref.p; S.lq = h->d_krlq.p;
         S.p = h->d_ksp.p; S.logq = h->d_kslogq.p; S.n_groups = h->ks_groups; S.counter = h->d_klcounter.p + 1; S.red = O.red;
@@ -726,13 +730,15 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
         if (h->kev_used == h->kev.size() && h->kev.size() < 8192) {
             cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); h->kev.push_back({a, b});
         }
-        if (h->kev_used < h->kev.size()) { e0 = h->kev[h->kev_used].first; e1 = h->kev[h->kev_used].second; h->kev_used++; }
+        while (h->kev_mid.size() < h->kev.size()) { cudaEvent_t m; cudaEventCreate(&m); h->kev_mid.push_back(m); }
+        if (h->kev_used < h->kev.size()) { e0 = h->kev[h->kev_used].first; e1 = h->kev[h->kev_used].second; h->mid_now = h->kev_mid[h->kev_used]; h->kev_used++; }
     }
     if (e0) cudaEventRecord(e0, st);
     h->lean_now = lean6;
     launch_main(h, kernel, mode, CorpusD{h->d_tokens.p, h->d_offs.p, h->d_p.p, d_order, n_order}, O);
     if (kernel2) launch_main(h, kernel2, mode, CorpusD{h->d_tokens.p, h->d_offs.p, h->d_p.p, d_order2, n_order2}, O);
     if (e1) cudaEventRecord(e1, st);
+    h->mid_now = nullptr;
     CK(cudaGetLastError());
     if (lean6) {
         Fin6Params P{};
@@ -1180,6 +1186,23 @@ extern "C" int wfsa_dev_timer_kernel_ms(wfsa_dev* h, float* ms, int64_t* launche
     }
     if (ms) *ms = total;
     if (launches) *launches = (int64_t)h->kev_used;
+    return WFSA_OK;
+}
+
+extern "C" int wfsa_dev_timer_split_ms(wfsa_dev* h, float* first_ms, float* second_ms)
+{
+    if (!h) return WFSA_ERR_INVALID;
+    float a = 0.f, b = 0.f;
+    if (h->kernel == 6)
+        for (size_t i = 0; i < h->kev_used && i < h->kev_mid.size(); ++i) {
+            float t = 0.f;
+            CK(cudaEventSynchronize(h->kev[i].second));
+            if (cudaEventElapsedTime(&t, h->kev[i].first, h->kev_mid[i]) == cudaSuccess) a += t;
+            if (cudaEventElapsedTime(&t, h->kev_mid[i], h->kev[i].second) == cudaSuccess) b += t;
+        }
+    cudaGetLastError();
+    if (first_ms) *first_ms = a;
+    if (second_ms) *second_ms = b;
     return WFSA_OK;
 }
 
