@@ -219,9 +219,13 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
     const long long gwarp = ((long long)blockIdx.x * NT + tid) >> 5;
     double* const xs = P.xs + (size_t)gwarp * P.xs_rows * 32 + lane;
     unsigned long long* const acc_g = P.acc + (size_t)(blockIdx.x % P.replicas) * (size_t)P.n_arcs;
-    // groups are sorted by cost (big regions first, then 16, 12, 8, 4 rows): a static round-robin is balanced
-    const long long GW = ((long long)gridDim.x * NT) >> 5;
-    for (long long g = gwarp; g < P.n_groups; g += GW) {
+    // groups are sorted by cost (big regions first, then 16, 12, 8, 4 rows) and handed out dynamically
+    long long g = 0;
+    if (lane == 0) g = (long long)atomicAdd(P.counter, 1u);
+    g = __shfl_sync(FULL, g, 0);
+    while (g < P.n_groups) {
+        long long gn = 0;
+        if (lane == 0) gn = (long long)atomicAdd(P.counter, 1u);
         const int rows = P.grows[g];
         switch (rows) {
             case 4: kr_small<4, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
@@ -230,6 +234,7 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
             case 16: kr_small<16, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
             default: kr_big<ACC>(P, aw, pool, NT, g, lane, xs, acc_g); break;
         }
+        g = __shfl_sync(FULL, gn, 0);
     }
 }
 
@@ -259,16 +264,17 @@ __global__ void __launch_bounds__(MAXNT, MINB) ks_strings(const KSParams P)
     __syncthreads();
     long long ll_fx = 0;
     unsigned long long bad = 0;
-    // groups are sorted by length, so a static round-robin over the warps is balanced (no scheduler atomics);
-    // the descriptor of a warp's next group is loaded while the current one streams
-    const long long gw0 = ((long long)blockIdx.x * NT + tid) >> 5, GW = ((long long)gridDim.x * NT) >> 5;
-    long long o = 0, o1 = 0; int nref = 0;
-    if (gw0 < P.n_groups) { o = P.goff[gw0]; o1 = P.goff[gw0 + 1]; nref = P.gref[gw0]; }
-    for (long long g = gw0; g < P.n_groups; g += GW) {
-        const int rows = (int)((o1 - o) >> 5);
+    // dynamic group scheduler (measured: a static round-robin is 20% slower -- SMs do not run at one speed);
+    // the id of a warp's next group is fetched while the current one streams
+    long long g = 0;
+    if (lane == 0) g = (long long)atomicAdd(P.counter, 1u);
+    g = __shfl_sync(FULL, g, 0);
+    while (g < P.n_groups) {
+        long long gn = 0;
+        if (lane == 0) gn = (long long)atomicAdd(P.counter, 1u);
+        const long long o = P.goff[g];
+        const int rows = (int)((P.goff[g + 1] - o) >> 5), nref_g = P.gref[g];
         const uint32_t* wp = P.words + o + lane;
-        const int nref_g = nref;
-        if (g + GW < P.n_groups) { o = P.goff[g + GW]; o1 = P.goff[g + GW + 1]; nref = P.gref[g + GW]; }
         // the first region references are gathered now and added after the bridge sum (their latency overlaps it)
         double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
         if (nref_g > 0) v0 = P.lq[__ldcs(wp)];
@@ -313,6 +319,7 @@ __global__ void __launch_bounds__(MAXNT, MINB) ks_strings(const KSParams P)
             if (isfinite(lqs)) ll_fx += __double2ll_rn(ps * lqs * P.ll_scale);
             else bad++;
         }
+        g = __shfl_sync(FULL, gn, 0);
     }
     for (int o = 16; o; o >>= 1) { ll_fx += __shfl_xor_sync(FULL, ll_fx, o); bad += __shfl_xor_sync(FULL, bad, o); }
     if (lane == 0) {
