@@ -325,7 +325,9 @@ static int setup_kl(wfsa_dev* h)
     int K = (h->opt.reserved >> 16) & 0xff;
     if (K == 0 || K > kLatMaxSlots) K = kLatMaxSlots;
     int nt = 0; size_t smem = 0;
-    if (!kl_possible(h, K, ((h->opt.reserved >> 24) & 0x7f) * 32, nt, smem))
+    int want_nt = ((h->opt.reserved >> 24) & 0x7f) * 32;
+    if (want_nt == 0 && h->kernel == 6) want_nt = 512;       // measured: 16 warps leave the L1 to the register spills
+    if (!kl_possible(h, K, want_nt, nt, smem))
         return set_err(h, WFSA_ERR_LIMIT, "compiled-lattice kernel: the arc weights do not fit shared memory");
     h->kl_K = K; h->kl_block = nt; h->kl_grid = h->sm_count; h->kl_smem = smem;
     h->kl_bridges = !(h->opt.reserved & 4);
