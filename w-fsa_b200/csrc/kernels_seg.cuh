@@ -328,6 +328,134 @@ __global__ void __launch_bounds__(MAXNT, MINB) ks_strings(const KSParams P)
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// KS, asynchronous variant: the word rows of a warp's groups are copied global -> shared memory with
+// cp.async (LDGSTS, 4 bytes per lane = one 128-byte row per instruction) into a per-warp ring, kKsDepth
+// chunks of 8 rows ahead of the consumer, so the bytes in flight do not live in registers.  ks_strings above
+// is bound by memory latency (70% of its stall samples wait on global loads at 3.5 TB/s); here every lane
+// only ever reads back the words it copied itself, so a lane-local cp.async.wait_group is all the
+// synchronisation the data path needs.  Group ids come from the dynamic scheduler two groups ahead, group
+// descriptors one group ahead; the region-type gathers of a group go through cp.async as well.
+// ------------------------------------------------------------------------------------------
+constexpr int kKsChunk = 8, kKsRing = 4, kKsDepth = 3, kKsRefs = 8, kKsFifo = 8;
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__host__ __device__ inline size_t ks_ring_smem(int n_arcs, int nwarps)
+{
+    const size_t tab = (((size_t)n_arcs + 16) * 8 + 127) & ~(size_t)127;
+    return tab + (size_t)nwarps * ((size_t)kKsRing * kKsChunk * 32 * 4 + (size_t)kKsRefs * 32 * 8 + (size_t)kKsFifo * 16);
+}
+
+template <int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, 1) ks_strings_ring(const KSParams P)
+{
+    extern __shared__ __align__(128) unsigned long long smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* tab = reinterpret_cast<double*>(smem);
+    unsigned char* after = reinterpret_cast<unsigned char*>(smem) + ((((size_t)P.n_arcs + 16) * 8 + 127) & ~(size_t)127);
+    uint32_t* ring = reinterpret_cast<uint32_t*>(after) + (size_t)warp * (kKsRing * kKsChunk * 32) + lane;
+    double* rq = reinterpret_cast<double*>(after + (size_t)NWARPS * kKsRing * kKsChunk * 32 * 4) + (size_t)warp * (kKsRefs * 32) + lane;
+    int4* fifo = reinterpret_cast<int4*>(after + (size_t)NWARPS * (kKsRing * kKsChunk * 32 * 4 + kKsRefs * 32 * 8)) + (size_t)warp * kKsFifo;
+    for (int i = tid; i < P.n_arcs + 16; i += NWARPS * 32) tab[i] = i < P.n_arcs ? P.logaw[i] : 0.0;
+    __syncthreads();
+
+    long long ll_fx = 0;
+    unsigned long long bad = 0;
+    // ---- producer state (warp uniform)
+    bool pvalid = false; long long po = 0; int prows = 0, pi = 0;
+    // descriptor of the group after the producer's (loads may still be in flight), raw id of the one after that
+    bool nvalid = false; long long ng = 0, no = 0, no1 = 0; int nnref = 0;
+    long long nn_raw = 0;
+    unsigned n_push = 0, n_pop = 0, n_issued = 0;
+    auto grab = [&]() -> long long { long long v = 0; if (lane == 0) v = (long long)atomicAdd(P.counter, 1u); return v; };
+    auto advance = [&]() {
+        pvalid = nvalid; po = no; prows = (int)((no1 - no) >> 5); pi = 0;
+        if (pvalid) {
+            if (lane == 0) fifo[n_push % kKsFifo] = make_int4((int)ng, prows, nnref, 0);
+            ++n_push;
+        }
+        const long long id = __shfl_sync(FULL, nn_raw, 0);
+        ng = id; nvalid = id < P.n_groups;
+        if (nvalid) { no = P.goff[id]; no1 = P.goff[id + 1]; nnref = P.gref[id]; }
+        nn_raw = nvalid ? grab() : P.n_groups;
+    };
+    auto issue = [&]() {
+        if (pvalid) {
+            const int nrow = min(kKsChunk, prows - pi);
+            const uint32_t* src = P.words + po + (size_t)pi * 32 + lane;
+            uint32_t* dst = ring + (size_t)(n_issued % kKsRing) * (kKsChunk * 32);
+#pragma unroll
+            for (int j = 0; j < kKsChunk; ++j) if (j < nrow) cp_async4(dst + j * 32, src + (size_t)j * 32);
+            pi += nrow;
+        }
+        cp_async_commit();
+        ++n_issued;
+        if (pvalid && pi == prows) advance();
+    };
+    {   // first group: id and descriptor synchronously, then the chain runs ahead on its own
+        const long long id = __shfl_sync(FULL, grab(), 0);
+        ng = id; nvalid = id < P.n_groups;
+        if (nvalid) { no = P.goff[id]; no1 = P.goff[id + 1]; nnref = P.gref[id]; }
+        nn_raw = nvalid ? grab() : P.n_groups;
+        advance();
+    }
+#pragma unroll
+    for (int d = 0; d < kKsDepth; ++d) issue();
+
+    // ---- consumer
+    unsigned n_consumed = 0;
+    while (n_pop < n_push) {
+        __syncwarp();
+        const int4 de = fifo[n_pop % kKsFifo];
+        ++n_pop;
+        const int g = de.x, rows = de.y, nref = de.z;
+        const bool async_refs = rows > kKsChunk * kKsDepth;          // long enough for the gathers to land on their own
+        const double ps = P.p[(long long)g * 32 + lane];             // needed at the end of the group only
+        double s0 = 0.0, s1 = 0.0, r = 0.0;
+        for (int i0 = 0; i0 < rows; i0 += kKsChunk) {
+            cp_async_wait<kKsDepth - 1>();
+            const uint32_t* src = ring + (size_t)(n_consumed % kKsRing) * (kKsChunk * 32);
+            uint32_t w[kKsChunk];
+#pragma unroll
+            for (int j = 0; j < kKsChunk; ++j) w[j] = src[j * 32];
+            ++n_consumed;
+#pragma unroll
+            for (int j = 0; j < kKsChunk; ++j) {
+                const int i = i0 + j;
+                if (i >= rows) break;
+                if (i < nref) {
+                    if (async_refs && i < kKsRefs) cp_async8(rq + i * 32, P.lq + w[j]);
+                    else r += P.lq[w[j]];
+                } else { s0 += tab[w[j] & 0xffffu]; s1 += tab[w[j] >> 16]; }
+            }
+            issue();                                                   // refills the ring slot that was just read
+        }
+        if (async_refs) for (int k = 0; k < min(nref, kKsRefs); ++k) r += rq[k * 32];
+        const double lqs = (s0 + s1) + r;
+        if (ps != 0.0) {
+            P.logq[(long long)g * 32 + lane] = lqs;
+            if (isfinite(lqs)) ll_fx += __double2ll_rn(ps * lqs * P.ll_scale);
+            else bad++;
+        }
+    }
+    cp_async_wait<0>();
+    for (int o = 16; o; o >>= 1) { ll_fx += __shfl_xor_sync(FULL, ll_fx, o); bad += __shfl_xor_sync(FULL, bad, o); }
+    if (lane == 0) {
+        if (ll_fx) atomicAdd(P.red, (unsigned long long)ll_fx);
+        if (bad) atomicAdd(P.red + 1, bad);
+    }
+}
+
 // log q of the strings of the segmented path, group order -> string id order
 __global__ void k_scatter_logq(long long n, const int32_t* __restrict__ ksid, const double* __restrict__ logq_k, double* logq)
 {
