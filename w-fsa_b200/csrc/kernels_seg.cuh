@@ -456,6 +456,144 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ks_strings_ring(const KSParams
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// KS, TMA variant: same per-warp ring, but a chunk of 8 rows (1 KB, contiguous) is moved by ONE bulk copy
+// (cp.async.bulk global -> shared, completion on an mbarrier per ring slot) issued by lane 0, so the data
+// movement costs the LSU one instruction per kilobyte instead of one LDGSTS per 128-byte row
+// (ks_strings_ring: 8 cycles per LDGSTS made it slower than the register version).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+                 "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+__host__ __device__ inline size_t ks_tma_smem(int n_arcs, int nwarps)
+{
+    const size_t tab = (((size_t)n_arcs + 16) * 8 + 1023) & ~(size_t)1023;
+    return tab + (size_t)nwarps * ((size_t)kKsRing * kKsChunk * 32 * 4 + (size_t)kKsRefs * 32 * 8 + (size_t)kKsFifo * 16 + (size_t)kKsRing * 8);
+}
+
+template <int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, 1) ks_strings_tma(const KSParams P)
+{
+    extern __shared__ __align__(1024) unsigned long long smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* tab = reinterpret_cast<double*>(smem);
+    unsigned char* after = reinterpret_cast<unsigned char*>(smem) + ((((size_t)P.n_arcs + 16) * 8 + 1023) & ~(size_t)1023);
+    uint32_t* ring0 = reinterpret_cast<uint32_t*>(after) + (size_t)warp * (kKsRing * kKsChunk * 32);
+    unsigned char* a2 = after + (size_t)NWARPS * kKsRing * kKsChunk * 32 * 4;
+    double* rq = reinterpret_cast<double*>(a2) + (size_t)warp * (kKsRefs * 32) + lane;
+    unsigned char* a3 = a2 + (size_t)NWARPS * kKsRefs * 32 * 8;
+    int4* fifo = reinterpret_cast<int4*>(a3) + (size_t)warp * kKsFifo;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(a3 + (size_t)NWARPS * kKsFifo * 16) + (size_t)warp * kKsRing;
+    for (int i = tid; i < P.n_arcs + 16; i += NWARPS * 32) tab[i] = i < P.n_arcs ? P.logaw[i] : 0.0;
+    if (lane == 0) {
+        for (int s = 0; s < kKsRing; ++s) mbar_init(bars + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    long long ll_fx = 0;
+    unsigned long long bad = 0;
+    bool pvalid = false; long long po = 0; int prows = 0, pi = 0;
+    bool nvalid = false; long long ng = 0, no = 0, no1 = 0; int nnref = 0;
+    long long nn_raw = 0;
+    unsigned n_push = 0, n_pop = 0, n_issued = 0;
+    auto grab = [&]() -> long long { long long v = 0; if (lane == 0) v = (long long)atomicAdd(P.counter, 1u); return v; };
+    auto advance = [&]() {
+        pvalid = nvalid; po = no; prows = (int)((no1 - no) >> 5); pi = 0;
+        if (pvalid) {
+            if (lane == 0) fifo[n_push % kKsFifo] = make_int4((int)ng, prows, nnref, 0);
+            ++n_push;
+        }
+        const long long id = __shfl_sync(FULL, nn_raw, 0);
+        ng = id; nvalid = id < P.n_groups;
+        if (nvalid) { no = P.goff[id]; no1 = P.goff[id + 1]; nnref = P.gref[id]; }
+        nn_raw = nvalid ? grab() : P.n_groups;
+    };
+    auto issue = [&]() {                                     // one chunk of the producer's group, if there is one
+        if (!pvalid) return;
+        __syncwarp();                                         // every lane is done with the slot that gets refilled
+        const int nrow = min(kKsChunk, prows - pi);
+        if (lane == 0) {
+            const unsigned slot = n_issued % kKsRing;
+            mbar_expect_tx(bars + slot, (unsigned)nrow * 128u);
+            bulk_g2s(ring0 + (size_t)slot * (kKsChunk * 32), P.words + po + (size_t)pi * 32, (unsigned)nrow * 128u, bars + slot);
+        }
+        pi += nrow;
+        ++n_issued;
+        if (pi == prows) advance();
+    };
+    {
+        const long long id = __shfl_sync(FULL, grab(), 0);
+        ng = id; nvalid = id < P.n_groups;
+        if (nvalid) { no = P.goff[id]; no1 = P.goff[id + 1]; nnref = P.gref[id]; }
+        nn_raw = nvalid ? grab() : P.n_groups;
+        advance();
+    }
+#pragma unroll
+    for (int d = 0; d < kKsDepth; ++d) issue();
+
+    unsigned n_consumed = 0;
+    while (n_pop < n_push) {
+        __syncwarp();
+        const int4 de = fifo[n_pop % kKsFifo];
+        ++n_pop;
+        const int g = de.x, rows = de.y, nref = de.z;
+        const double ps = P.p[(long long)g * 32 + lane];             // needed at the end of the group only
+        double s0 = 0.0, s1 = 0.0, r = 0.0;
+        for (int i0 = 0; i0 < rows; i0 += kKsChunk) {
+            const unsigned slot = n_consumed % kKsRing;
+            mbar_wait(bars + slot, (n_consumed / kKsRing) & 1u);
+            const uint32_t* src = ring0 + (size_t)slot * (kKsChunk * 32) + lane;
+            uint32_t w[kKsChunk];
+#pragma unroll
+            for (int j = 0; j < kKsChunk; ++j) w[j] = src[j * 32];
+            ++n_consumed;
+#pragma unroll
+            for (int j = 0; j < kKsChunk; ++j) {
+                const int i = i0 + j;
+                if (i >= rows) break;
+                if (i < nref) {
+                    if (i < kKsRefs) cp_async8(rq + i * 32, P.lq + w[j]);
+                    else r += P.lq[w[j]];
+                } else { s0 += tab[w[j] & 0xffffu]; s1 += tab[w[j] >> 16]; }
+            }
+            if (i0 == 0) cp_async_commit();
+            issue();
+        }
+        cp_async_wait<0>();
+        for (int k = 0; k < min(nref, kKsRefs); ++k) r += rq[k * 32];
+        const double lqs = (s0 + s1) + r;
+        if (ps != 0.0) {
+            P.logq[(long long)g * 32 + lane] = lqs;
+            if (isfinite(lqs)) ll_fx += __double2ll_rn(ps * lqs * P.ll_scale);
+            else bad++;
+        }
+    }
+    for (int o = 16; o; o >>= 1) { ll_fx += __shfl_xor_sync(FULL, ll_fx, o); bad += __shfl_xor_sync(FULL, bad, o); }
+    if (lane == 0) {
+        if (ll_fx) atomicAdd(P.red, (unsigned long long)ll_fx);
+        if (bad) atomicAdd(P.red + 1, bad);
+    }
+}
+
 // log q of the strings of the segmented path, group order -> string id order
 __global__ void k_scatter_logq(long long n, const int32_t* __restrict__ ksid, const double* __restrict__ logq_k, double* logq)
 {

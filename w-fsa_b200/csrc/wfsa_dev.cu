@@ -353,15 +353,19 @@ static int setup_kl(wfsa_dev* h)
             h->ks_ring = 0;
             if (const char* e = getenv("WFSA_KS_SHAPE")) {
                 if (!strncmp(e, "ring", 4)) h->ks_ring = atoi(e + 4);
+                else if (!strncmp(e, "tma", 3)) h->ks_ring = 100 + atoi(e + 3);
                 else sscanf(e, "%dx%d", &nt, &nb);
             }
-            if (h->ks_ring && h->ks_ring != 16 && h->ks_ring != 24 && h->ks_ring != 8) h->ks_ring = 16;
-            if (h->ks_ring && ks_ring_smem(A.n_arcs, h->ks_ring) > 227 * 1024) h->ks_ring = 0;
+            if (h->ks_ring) { const int nw = h->ks_ring % 100; if (nw != 16 && nw != 24 && nw != 8) h->ks_ring = h->ks_ring / 100 * 100 + 16; }
+            if (h->ks_ring && ks_tma_smem(A.n_arcs, h->ks_ring % 100) > 227 * 1024) h->ks_ring = 0;
             if (!((nt == 1024 && nb == 2) || (nt == 768 && nb == 2) || (nt == 512 && nb == 2) || (nt == 512 && nb == 3) || (nt == 1024 && nb == 1))) { nt = 512; nb = 2; }
             if (h->ks_smem * nb > 220 * 1024) { nt = 1024; nb = 1; }
             h->ks_block = nt; h->ks_grid = h->sm_count * nb; h->ks_ctas = nb;
-            if (h->ks_ring) { h->ks_block = h->ks_ring * 32; h->ks_grid = h->sm_count; h->ks_ctas = 1; }
+            if (h->ks_ring) { h->ks_block = (h->ks_ring % 100) * 32; h->ks_grid = h->sm_count; h->ks_ctas = 1; }
         }
+        cudaFuncSetAttribute(ks_strings_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(ks_strings_tma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(ks_strings_tma<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(ks_strings_ring<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(ks_strings_ring<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(ks_strings_ring<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -599,7 +603,10 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
         S.p = h->d_ksp.p; S.logq = h->d_kslogq.p; S.n_groups = h->ks_groups; S.counter = h->d_klcounter.p + 1; S.red = O.red;
         S.ll_scale = O.ll_scale; S.n_arcs = h->larcs.n_arcs;
         if (h->ks_groups > 0) {
-            if (h->ks_ring == 8) ks_strings_ring<8><<<h->ks_grid, 256, ks_ring_smem(S.n_arcs, 8), st>>>(S);
+            if (h->ks_ring == 108) ks_strings_tma<8><<<h->ks_grid, 256, ks_tma_smem(S.n_arcs, 8), st>>>(S);
+            else if (h->ks_ring == 116) ks_strings_tma<16><<<h->ks_grid, 512, ks_tma_smem(S.n_arcs, 16), st>>>(S);
+            else if (h->ks_ring == 124) ks_strings_tma<24><<<h->ks_grid, 768, ks_tma_smem(S.n_arcs, 24), st>>>(S);
+            else if (h->ks_ring == 8) ks_strings_ring<8><<<h->ks_grid, 256, ks_ring_smem(S.n_arcs, 8), st>>>(S);
             else if (h->ks_ring == 16) ks_strings_ring<16><<<h->ks_grid, 512, ks_ring_smem(S.n_arcs, 16), st>>>(S);
             else if (h->ks_ring == 24) ks_strings_ring<24><<<h->ks_grid, 768, ks_ring_smem(S.n_arcs, 24), st>>>(S);
             else if (h->ks_block == 1024 && h->ks_ctas == 2) ks_strings<1024, 2><<<h->ks_grid, 1024, h->ks_smem, st>>>(S);
