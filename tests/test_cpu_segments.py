@@ -91,25 +91,34 @@ def interpret(seg, aw, n_arcs):
     logq = {}
     with np.errstate(divide="ignore"):
         logaw = np.concatenate([np.log(aw), np.zeros(16)])          # 16 padding entries, one per bank pair
-    n_lookups = n_conflict_free = 0
-    for g in range(len(sgref)):
-        rows = int((sgoff[g + 1] - sgoff[g]) // 32)
-        block = seg["swords"][sgoff[g]:sgoff[g + 1]].reshape(rows, 32)
-        assert (rows - sgref[g]) % 4 == 0
-        pairs = block[sgref[g]:]
-        for ids in (pairs & 0xffff, pairs >> 16):                   # one 8-byte table read per lane each
-            for half in (ids[:, :16], ids[:, 16:]):                 # a 64-bit shared load is served half-warp by half-warp
-                cls = np.sort(half & 15, axis=1)
-                assert (cls == np.arange(16)).all(), "a half-warp must read 16 different bank pairs in every slot"
-        for l in range(32):
-            sid = int(ksid[g * 32 + l])
-            refs = block[:sgref[g], l].astype(np.int64)
-            arcs = np.concatenate([pairs[:, l] & 0xffff, pairs[:, l] >> 16]).astype(np.int64)
-            assert arcs.max(initial=0) < n_arcs + 16 and refs.max(initial=0) <= n_rg * 32
-            if sid < 0:
-                assert (refs == n_rg * 32).all() and (arcs >= n_arcs).all() and kp[g * 32 + l] == 0.0
-                continue
-            logq[sid] = logaw[arcs].sum() + lq[refs].sum()
+    SUPER, CH = 16, 8                                                # kKsSuper, kKsChunkRows
+    assert len(sgref) == (len(sgoff) - 1) * SUPER and len(ksid) == len(sgref) * 32
+    n_phase = n_conflict = 0
+    for sg in range(len(sgoff) - 1):
+        chunks = int((sgoff[sg + 1] - sgoff[sg]) // (SUPER * CH * 32))
+        assert chunks >= 1 and sgoff[sg] + chunks * SUPER * CH * 32 == sgoff[sg + 1]
+        blk = seg["swords"][sgoff[sg]:sgoff[sg + 1]].reshape(chunks, SUPER, CH, 32)
+        for w in range(SUPER):
+            g = sg * SUPER + w
+            block = blk[:, w].reshape(chunks * CH, 32)                # the rows of group g in order
+            pairs = block[sgref[g]:]
+            for ids in (pairs & 0xffff, pairs >> 16):                 # one 8-byte table read per lane each
+                for half in (ids[:, :16], ids[:, 16:]):               # a 64-bit shared load is served half-warp by half-warp
+                    for row in half & 15:
+                        cnt = np.bincount(row, minlength=16)
+                        assert cnt.max() <= 2, "at most a two-way bank conflict per slot"
+                        n_phase += 1
+                        n_conflict += int(cnt.max() > 1)
+            for l in range(32):
+                sid = int(ksid[g * 32 + l])
+                refs = block[:sgref[g], l].astype(np.int64)
+                arcs = np.concatenate([pairs[:, l] & 0xffff, pairs[:, l] >> 16]).astype(np.int64)
+                assert arcs.max(initial=0) < n_arcs + 16 and refs.max(initial=0) <= n_rg * 32
+                if sid < 0:
+                    assert (refs == n_rg * 32).all() and (arcs >= n_arcs).all() and kp[g * 32 + l] == 0.0
+                    continue
+                logq[sid] = logaw[arcs].sum() + lq[refs].sum()
+    assert n_conflict <= 0.35 * max(n_phase, 1), "the schedule should leave most slots conflict free"
     return lq, acc, logq
 
 

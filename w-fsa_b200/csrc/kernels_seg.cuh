@@ -241,351 +241,87 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
 // ------------------------------------------------------------------------------------------
 struct KSParams {
     const double* __restrict__ logaw;     // [n_arcs] log weight of every combined arc
-    const uint32_t* __restrict__ words;   // row r of lane l of group g at goff[g] + r*32 + l
-    const int64_t* __restrict__ goff;     // [n_groups+1]
-    const int32_t* __restrict__ gref;     // [n_groups] leading rows that hold region type ids
+    const uint32_t* __restrict__ words;   // chunk-interleaved super-groups (lattice.hpp, SegmentedCorpus)
+    const int64_t* __restrict__ sgoff;    // [n_sgroups+1]
+    const int32_t* __restrict__ gref;     // [n_sgroups*16] leading rows of a group that hold region type ids
     const double* __restrict__ lq;        // log q per region type (written by kr_regions)
-    const double* __restrict__ p;         // [n_groups*32] p_s in group order (0 = padding lane)
-    double* logq;                         // [n_groups*32] log q_s in group order
-    long long n_groups;
+    const double* __restrict__ p;         // [n_sgroups*16*32] p_s in group order (0 = padding lane)
+    double* logq;                         // [n_sgroups*16*32] log q_s in group order
+    long long n_sgroups;
     unsigned int* counter;
     unsigned long long* red;              // red[0] fixed-point loglik, red[1] non-finite strings
     double ll_scale;
     int n_arcs;
 };
 
-template <int MAXNT, int MINB>
-__global__ void __launch_bounds__(MAXNT, MINB) ks_strings(const KSParams P)
+// KS: one CTA of 16 warps per super-group of 16 groups, one warp per group, one thread per string.
+//   log q_s = sum over the string's bridge arcs of log w[arc]  (two 16-bit ids per word; 8-byte table in shared
+//             memory; the host scheduled the ids so that a half-warp reads 16 different bank pairs)
+//           + sum over its regions of lq[type]                  (gathers from L2)
+// The words of a super-group are interleaved chunk by chunk, so the 16 warps stream ONE contiguous region
+// (DRAM sees long bursts: 5.6 TB/s against 4.3 TB/s with one private block per warp, profiles/microbench_stream.cu).
+// Measured dead ends, kept in the history: a cp.async (LDGSTS) ring and a TMA bulk-copy ring per warp were both
+// slower than this register double buffer (the limit was DRAM burst locality, not bytes in flight).
+constexpr int kKsRows = 8, kKsWarps = 16;      // = kKsChunkRows, kKsSuper of lattice.hpp
+
+__global__ void __launch_bounds__(kKsWarps * 32, 2) ks_strings(const KSParams P)
 {
     extern __shared__ __align__(128) unsigned long long smem[];
-    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
+    __shared__ long long s_next[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* tab = reinterpret_cast<double*>(smem);            // [n_arcs + 16]; ids n_arcs.. (padding, one per bank pair) -> 0
-    for (int i = tid; i < P.n_arcs + 16; i += NT) tab[i] = i < P.n_arcs ? P.logaw[i] : 0.0;
+    for (int i = tid; i < P.n_arcs + 16; i += kKsWarps * 32) tab[i] = i < P.n_arcs ? P.logaw[i] : 0.0;
+    if (tid == 0) s_next[0] = (long long)atomicAdd(P.counter, 1u);
     __syncthreads();
     long long ll_fx = 0;
     unsigned long long bad = 0;
-    // dynamic group scheduler (measured: a static round-robin is 20% slower -- SMs do not run at one speed);
-    // the id of a warp's next group is fetched while the current one streams
-    long long g = 0;
-    if (lane == 0) g = (long long)atomicAdd(P.counter, 1u);
-    g = __shfl_sync(FULL, g, 0);
-    while (g < P.n_groups) {
-        long long gn = 0;
-        if (lane == 0) gn = (long long)atomicAdd(P.counter, 1u);
-        const long long o = P.goff[g];
-        const int rows = (int)((P.goff[g + 1] - o) >> 5), nref_g = P.gref[g];
-        const uint32_t* wp = P.words + o + lane;
-        // the first region references are gathered now and added after the bridge sum (their latency overlaps it)
-        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-        if (nref_g > 0) v0 = P.lq[__ldcs(wp)];
-        if (nref_g > 1) v1 = P.lq[__ldcs(wp + 32)];
-        if (nref_g > 2) v2 = P.lq[__ldcs(wp + 64)];
-        if (nref_g > 3) v3 = P.lq[__ldcs(wp + 96)];
-        double s0 = 0.0, s1 = 0.0;
-        // bridge words: chunks of 8 rows, the next chunk's loads are in flight while this one is summed
-        int i = nref_g;
-        uint32_t a[8];
-        const int nfull = (rows - nref_g) >> 3;
-        if (nfull > 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = __ldcs(wp + (size_t)(i + j) * 32);
-        }
-        for (int c = 0; c < nfull; ++c) {
-            i += 8;
-            uint32_t b[8];
-            if (c + 1 < nfull) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) b[j] = __ldcs(wp + (size_t)(i + j) * 32);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { s0 += tab[a[j] & 0xffffu]; s1 += tab[a[j] >> 16]; }
-            if (c + 1 < nfull) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) a[j] = b[j];
-            }
-        }
-        if (i < rows) {                                       // rows - nref is a multiple of 4
-#pragma unroll
-            for (int j = 0; j < 4; ++j) a[j] = __ldcs(wp + (size_t)(i + j) * 32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { s0 += tab[a[j] & 0xffffu]; s1 += tab[a[j] >> 16]; }
-        }
-        double r = (v0 + v1) + (v2 + v3);
-        for (int k = 4; k < nref_g; ++k) r += P.lq[__ldcs(wp + (size_t)k * 32)];
+    int par = 0;
+    for (long long sg = s_next[0]; sg < P.n_sgroups;) {
+        if (tid == 0) s_next[par ^ 1] = (long long)atomicAdd(P.counter, 1u);   // the next super-group, fetched early
+        const long long o = P.sgoff[sg];
+        const int chunks = (int)((P.sgoff[sg + 1] - o) / (kKsWarps * kKsRows * 32));
+        const long long g = sg * kKsWarps + warp;
+        const int nref = P.gref[g];
         const double ps = P.p[g * 32 + lane];
-        const double lqs = (s0 + s1) + r;
+        const uint32_t* wp = P.words + o + (size_t)warp * (kKsRows * 32) + lane;   // chunk c at wp + c * (16*8*32)
+        constexpr size_t CS = (size_t)kKsWarps * kKsRows * 32;
+        double s0 = 0.0, s1 = 0.0, r = 0.0, v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        uint32_t a[kKsRows];
+#pragma unroll
+        for (int j = 0; j < kKsRows; ++j) a[j] = __ldcs(wp + j * 32);
+        for (int c = 0; c < chunks; ++c) {
+            uint32_t b[kKsRows];
+            if (c + 1 < chunks) {
+#pragma unroll
+                for (int j = 0; j < kKsRows; ++j) b[j] = __ldcs(wp + (size_t)(c + 1) * CS + j * 32);
+            }
+            if (c * kKsRows < nref) {                           // chunk with region references (the first one, rarely two)
+#pragma unroll
+                for (int j = 0; j < kKsRows; ++j) {
+                    const int i = c * kKsRows + j;
+                    if (i < nref) {
+                        const double v = P.lq[a[j]];            // the first four are added at the end (latency overlaps)
+                        if (i == 0) v0 = v; else if (i == 1) v1 = v; else if (i == 2) v2 = v; else if (i == 3) v3 = v; else r += v;
+                    } else { s0 += tab[a[j] & 0xffffu]; s1 += tab[a[j] >> 16]; }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < kKsRows; ++j) { s0 += tab[a[j] & 0xffffu]; s1 += tab[a[j] >> 16]; }
+            }
+            if (c + 1 < chunks) {
+#pragma unroll
+                for (int j = 0; j < kKsRows; ++j) a[j] = b[j];
+            }
+        }
+        const double lqs = (s0 + s1) + (r + ((v0 + v1) + (v2 + v3)));
         if (ps != 0.0) {
             P.logq[g * 32 + lane] = lqs;
             if (isfinite(lqs)) ll_fx += __double2ll_rn(ps * lqs * P.ll_scale);
             else bad++;
         }
-        g = __shfl_sync(FULL, gn, 0);
-    }
-    for (int o = 16; o; o >>= 1) { ll_fx += __shfl_xor_sync(FULL, ll_fx, o); bad += __shfl_xor_sync(FULL, bad, o); }
-    if (lane == 0) {
-        if (ll_fx) atomicAdd(P.red, (unsigned long long)ll_fx);
-        if (bad) atomicAdd(P.red + 1, bad);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// KS, asynchronous variant: the word rows of a warp's groups are copied global -> shared memory with
-// cp.async (LDGSTS, 4 bytes per lane = one 128-byte row per instruction) into a per-warp ring, kKsDepth
-// chunks of 8 rows ahead of the consumer, so the bytes in flight do not live in registers.  ks_strings above
-// is bound by memory latency (70% of its stall samples wait on global loads at 3.5 TB/s); here every lane
-// only ever reads back the words it copied itself, so a lane-local cp.async.wait_group is all the
-// synchronisation the data path needs.  Group ids come from the dynamic scheduler two groups ahead, group
-// descriptors one group ahead; the region-type gathers of a group go through cp.async as well.
-// ------------------------------------------------------------------------------------------
-constexpr int kKsChunk = 8, kKsRing = 4, kKsDepth = 3, kKsRefs = 8, kKsFifo = 8;
-
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-__host__ __device__ inline size_t ks_ring_smem(int n_arcs, int nwarps)
-{
-    const size_t tab = (((size_t)n_arcs + 16) * 8 + 127) & ~(size_t)127;
-    return tab + (size_t)nwarps * ((size_t)kKsRing * kKsChunk * 32 * 4 + (size_t)kKsRefs * 32 * 8 + (size_t)kKsFifo * 16);
-}
-
-template <int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32, 1) ks_strings_ring(const KSParams P)
-{
-    extern __shared__ __align__(128) unsigned long long smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* tab = reinterpret_cast<double*>(smem);
-    unsigned char* after = reinterpret_cast<unsigned char*>(smem) + ((((size_t)P.n_arcs + 16) * 8 + 127) & ~(size_t)127);
-    uint32_t* ring = reinterpret_cast<uint32_t*>(after) + (size_t)warp * (kKsRing * kKsChunk * 32) + lane;
-    double* rq = reinterpret_cast<double*>(after + (size_t)NWARPS * kKsRing * kKsChunk * 32 * 4) + (size_t)warp * (kKsRefs * 32) + lane;
-    int4* fifo = reinterpret_cast<int4*>(after + (size_t)NWARPS * (kKsRing * kKsChunk * 32 * 4 + kKsRefs * 32 * 8)) + (size_t)warp * kKsFifo;
-    for (int i = tid; i < P.n_arcs + 16; i += NWARPS * 32) tab[i] = i < P.n_arcs ? P.logaw[i] : 0.0;
-    __syncthreads();
-
-    long long ll_fx = 0;
-    unsigned long long bad = 0;
-    // ---- producer state (warp uniform)
-    bool pvalid = false; long long po = 0; int prows = 0, pi = 0;
-    // descriptor of the group after the producer's (loads may still be in flight), raw id of the one after that
-    bool nvalid = false; long long ng = 0, no = 0, no1 = 0; int nnref = 0;
-    long long nn_raw = 0;
-    unsigned n_push = 0, n_pop = 0, n_issued = 0;
-    auto grab = [&]() -> long long { long long v = 0; if (lane == 0) v = (long long)atomicAdd(P.counter, 1u); return v; };
-    auto advance = [&]() {
-        pvalid = nvalid; po = no; prows = (int)((no1 - no) >> 5); pi = 0;
-        if (pvalid) {
-            if (lane == 0) fifo[n_push % kKsFifo] = make_int4((int)ng, prows, nnref, 0);
-            ++n_push;
-        }
-        const long long id = __shfl_sync(FULL, nn_raw, 0);
-        ng = id; nvalid = id < P.n_groups;
-        if (nvalid) { no = P.goff[id]; no1 = P.goff[id + 1]; nnref = P.gref[id]; }
-        nn_raw = nvalid ? grab() : P.n_groups;
-    };
-    auto issue = [&]() {
-        if (pvalid) {
-            const int nrow = min(kKsChunk, prows - pi);
-            const uint32_t* src = P.words + po + (size_t)pi * 32 + lane;
-            uint32_t* dst = ring + (size_t)(n_issued % kKsRing) * (kKsChunk * 32);
-#pragma unroll
-            for (int j = 0; j < kKsChunk; ++j) if (j < nrow) cp_async4(dst + j * 32, src + (size_t)j * 32);
-            pi += nrow;
-        }
-        cp_async_commit();
-        ++n_issued;
-        if (pvalid && pi == prows) advance();
-    };
-    {   // first group: id and descriptor synchronously, then the chain runs ahead on its own
-        const long long id = __shfl_sync(FULL, grab(), 0);
-        ng = id; nvalid = id < P.n_groups;
-        if (nvalid) { no = P.goff[id]; no1 = P.goff[id + 1]; nnref = P.gref[id]; }
-        nn_raw = nvalid ? grab() : P.n_groups;
-        advance();
-    }
-#pragma unroll
-    for (int d = 0; d < kKsDepth; ++d) issue();
-
-    // ---- consumer
-    unsigned n_consumed = 0;
-    while (n_pop < n_push) {
-        __syncwarp();
-        const int4 de = fifo[n_pop % kKsFifo];
-        ++n_pop;
-        const int g = de.x, rows = de.y, nref = de.z;
-        const bool async_refs = rows > kKsChunk * kKsDepth;          // long enough for the gathers to land on their own
-        const double ps = P.p[(long long)g * 32 + lane];             // needed at the end of the group only
-        double s0 = 0.0, s1 = 0.0, r = 0.0;
-        for (int i0 = 0; i0 < rows; i0 += kKsChunk) {
-            cp_async_wait<kKsDepth - 1>();
-            const uint32_t* src = ring + (size_t)(n_consumed % kKsRing) * (kKsChunk * 32);
-            uint32_t w[kKsChunk];
-#pragma unroll
-            for (int j = 0; j < kKsChunk; ++j) w[j] = src[j * 32];
-            ++n_consumed;
-#pragma unroll
-            for (int j = 0; j < kKsChunk; ++j) {
-                const int i = i0 + j;
-                if (i >= rows) break;
-                if (i < nref) {
-                    if (async_refs && i < kKsRefs) cp_async8(rq + i * 32, P.lq + w[j]);
-                    else r += P.lq[w[j]];
-                } else { s0 += tab[w[j] & 0xffffu]; s1 += tab[w[j] >> 16]; }
-            }
-            issue();                                                   // refills the ring slot that was just read
-        }
-        if (async_refs) for (int k = 0; k < min(nref, kKsRefs); ++k) r += rq[k * 32];
-        const double lqs = (s0 + s1) + r;
-        if (ps != 0.0) {
-            P.logq[(long long)g * 32 + lane] = lqs;
-            if (isfinite(lqs)) ll_fx += __double2ll_rn(ps * lqs * P.ll_scale);
-            else bad++;
-        }
-    }
-    cp_async_wait<0>();
-    for (int o = 16; o; o >>= 1) { ll_fx += __shfl_xor_sync(FULL, ll_fx, o); bad += __shfl_xor_sync(FULL, bad, o); }
-    if (lane == 0) {
-        if (ll_fx) atomicAdd(P.red, (unsigned long long)ll_fx);
-        if (bad) atomicAdd(P.red + 1, bad);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// KS, TMA variant: same per-warp ring, but a chunk of 8 rows (1 KB, contiguous) is moved by ONE bulk copy
-// (cp.async.bulk global -> shared, completion on an mbarrier per ring slot) issued by lane 0, so the data
-// movement costs the LSU one instruction per kilobyte instead of one LDGSTS per 128-byte row
-// (ks_strings_ring: 8 cycles per LDGSTS made it slower than the register version).
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
-{
-    asm volatile(
-        "{\n.reg .pred p;\nWAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
-                 "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-
-__host__ __device__ inline size_t ks_tma_smem(int n_arcs, int nwarps)
-{
-    const size_t tab = (((size_t)n_arcs + 16) * 8 + 1023) & ~(size_t)1023;
-    return tab + (size_t)nwarps * ((size_t)kKsRing * kKsChunk * 32 * 4 + (size_t)kKsRefs * 32 * 8 + (size_t)kKsFifo * 16 + (size_t)kKsRing * 8);
-}
-
-template <int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32, 1) ks_strings_tma(const KSParams P)
-{
-    extern __shared__ __align__(1024) unsigned long long smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* tab = reinterpret_cast<double*>(smem);
-    unsigned char* after = reinterpret_cast<unsigned char*>(smem) + ((((size_t)P.n_arcs + 16) * 8 + 1023) & ~(size_t)1023);
-    uint32_t* ring0 = reinterpret_cast<uint32_t*>(after) + (size_t)warp * (kKsRing * kKsChunk * 32);
-    unsigned char* a2 = after + (size_t)NWARPS * kKsRing * kKsChunk * 32 * 4;
-    double* rq = reinterpret_cast<double*>(a2) + (size_t)warp * (kKsRefs * 32) + lane;
-    unsigned char* a3 = a2 + (size_t)NWARPS * kKsRefs * 32 * 8;
-    int4* fifo = reinterpret_cast<int4*>(a3) + (size_t)warp * kKsFifo;
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(a3 + (size_t)NWARPS * kKsFifo * 16) + (size_t)warp * kKsRing;
-    for (int i = tid; i < P.n_arcs + 16; i += NWARPS * 32) tab[i] = i < P.n_arcs ? P.logaw[i] : 0.0;
-    if (lane == 0) {
-        for (int s = 0; s < kKsRing; ++s) mbar_init(bars + s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    __syncthreads();
-
-    long long ll_fx = 0;
-    unsigned long long bad = 0;
-    bool pvalid = false; long long po = 0; int prows = 0, pi = 0;
-    bool nvalid = false; long long ng = 0, no = 0, no1 = 0; int nnref = 0;
-    long long nn_raw = 0;
-    unsigned n_push = 0, n_pop = 0, n_issued = 0;
-    auto grab = [&]() -> long long { long long v = 0; if (lane == 0) v = (long long)atomicAdd(P.counter, 1u); return v; };
-    auto advance = [&]() {
-        pvalid = nvalid; po = no; prows = (int)((no1 - no) >> 5); pi = 0;
-        if (pvalid) {
-            if (lane == 0) fifo[n_push % kKsFifo] = make_int4((int)ng, prows, nnref, 0);
-            ++n_push;
-        }
-        const long long id = __shfl_sync(FULL, nn_raw, 0);
-        ng = id; nvalid = id < P.n_groups;
-        if (nvalid) { no = P.goff[id]; no1 = P.goff[id + 1]; nnref = P.gref[id]; }
-        nn_raw = nvalid ? grab() : P.n_groups;
-    };
-    auto issue = [&]() {                                     // one chunk of the producer's group, if there is one
-        if (!pvalid) return;
-        __syncwarp();                                         // every lane is done with the slot that gets refilled
-        const int nrow = min(kKsChunk, prows - pi);
-        if (lane == 0) {
-            const unsigned slot = n_issued % kKsRing;
-            mbar_expect_tx(bars + slot, (unsigned)nrow * 128u);
-            bulk_g2s(ring0 + (size_t)slot * (kKsChunk * 32), P.words + po + (size_t)pi * 32, (unsigned)nrow * 128u, bars + slot);
-        }
-        pi += nrow;
-        ++n_issued;
-        if (pi == prows) advance();
-    };
-    {
-        const long long id = __shfl_sync(FULL, grab(), 0);
-        ng = id; nvalid = id < P.n_groups;
-        if (nvalid) { no = P.goff[id]; no1 = P.goff[id + 1]; nnref = P.gref[id]; }
-        nn_raw = nvalid ? grab() : P.n_groups;
-        advance();
-    }
-#pragma unroll
-    for (int d = 0; d < kKsDepth; ++d) issue();
-
-    unsigned n_consumed = 0;
-    while (n_pop < n_push) {
-        __syncwarp();
-        const int4 de = fifo[n_pop % kKsFifo];
-        ++n_pop;
-        const int g = de.x, rows = de.y, nref = de.z;
-        const double ps = P.p[(long long)g * 32 + lane];             // needed at the end of the group only
-        double s0 = 0.0, s1 = 0.0, r = 0.0;
-        for (int i0 = 0; i0 < rows; i0 += kKsChunk) {
-            const unsigned slot = n_consumed % kKsRing;
-            mbar_wait(bars + slot, (n_consumed / kKsRing) & 1u);
-            const uint32_t* src = ring0 + (size_t)slot * (kKsChunk * 32) + lane;
-            uint32_t w[kKsChunk];
-#pragma unroll
-            for (int j = 0; j < kKsChunk; ++j) w[j] = src[j * 32];
-            ++n_consumed;
-#pragma unroll
-            for (int j = 0; j < kKsChunk; ++j) {
-                const int i = i0 + j;
-                if (i >= rows) break;
-                if (i < nref) {
-                    if (i < kKsRefs) cp_async8(rq + i * 32, P.lq + w[j]);
-                    else r += P.lq[w[j]];
-                } else { s0 += tab[w[j] & 0xffffu]; s1 += tab[w[j] >> 16]; }
-            }
-            if (i0 == 0) cp_async_commit();
-            issue();
-        }
-        cp_async_wait<0>();
-        for (int k = 0; k < min(nref, kKsRefs); ++k) r += rq[k * 32];
-        const double lqs = (s0 + s1) + r;
-        if (ps != 0.0) {
-            P.logq[(long long)g * 32 + lane] = lqs;
-            if (isfinite(lqs)) ll_fx += __double2ll_rn(ps * lqs * P.ll_scale);
-            else bad++;
-        }
+        __syncthreads();
+        par ^= 1;
+        sg = s_next[par];
     }
     for (int o = 16; o; o >>= 1) { ll_fx += __shfl_xor_sync(FULL, ll_fx, o); bad += __shfl_xor_sync(FULL, bad, o); }
     if (lane == 0) {

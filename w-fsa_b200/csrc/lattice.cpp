@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <thread>
@@ -396,32 +397,50 @@ inline uint64_t fnv1a(const uint32_t* w, size_t n)
 }
 }  // namespace
 
-// Schedules the bridge arcs of the (up to) 16 strings of one half-warp into time slots so that, in every slot,
-// the 16 lanes read table entries of 16 different classes (class = arc id mod 16 = the pair of shared-memory
-// banks an 8-byte entry lives in): a proper edge colouring of the bipartite multigraph lanes x classes, which
-// needs max(longest string, fullest class) colours (Koenig).  A lane that has nothing to read in a slot gets
-// one of 16 padding entries (ids n_arcs .. n_arcs+15, all log w = 0) of a class nobody else uses in that slot.
+// Schedules the bridge arcs of the (up to) 16 strings of one half-warp into time slots.  In one slot every lane
+// reads one 8-byte table entry; entries whose ids agree mod 16 live in the same pair of shared-memory banks, and
+// a slot costs one wavefront per lane sharing a bank pair.  The schedule is a proper edge colouring of the
+// bipartite multigraph lanes x classes with T = (longest string of the half-warp) colours, i.e. no padding
+// beyond the length differences; a class that holds more than T arcs is split in two virtual classes that may
+// both appear in one slot (a two-way conflict -- cheaper than a padded slot, which costs a wavefront AND
+// memory traffic).  Lanes with nothing to read in a slot get one of 16 padding entries (ids n_arcs ..
+// n_arcs+15, log w = 0), of a class nobody else reads in that slot when there is one.
 struct BridgeScheduler {
+    static constexpr int NK = 32;                    // virtual classes
     uint16_t pad0;
-    std::vector<int16_t> laneCol, classCol;          // [16][D] colour -> class of the lane's edge / lane of the class's edge
-    std::vector<std::vector<uint16_t>> bucket;       // [16*16] arcs of (lane, class)
-    explicit BridgeScheduler(uint16_t pad) : pad0(pad), bucket(256) {}
+    int slack_pct = 8;
+    std::vector<int16_t> laneCol, classCol;          // [16][T] / [NK][T]: colour -> class of the lane's edge / lane of the class's edge
+    std::vector<std::vector<uint16_t>> bucket;       // [16*NK] arcs of (lane, virtual class)
+    explicit BridgeScheduler(uint16_t pad) : pad0(pad), bucket(16 * NK)
+    {
+        if (const char* e = std::getenv("WFSA_KS_SLACK")) slack_pct = std::max(0, std::min(100, std::atoi(e)));   // tuning knob
+    }
     int run(const uint16_t* const* arcs, const int* cnt, std::vector<uint16_t>& out)
     {
-        int degL[16] = {0}, degK[16] = {0};
-        for (auto& b : bucket) b.clear();
+        int degL[16] = {0}, load[16] = {0};
         for (int l = 0; l < 16; ++l)
-            for (int i = 0; i < cnt[l]; ++i) { const int k = arcs[l][i] & 15; bucket[l * 16 + k].push_back(arcs[l][i]); degL[l]++; degK[k]++; }
-        int D = 0;
-        for (int i = 0; i < 16; ++i) D = std::max(D, std::max(degL[i], degK[i]));
-        out.assign((size_t)D * 16, 0);
-        if (D == 0) return 0;
-        laneCol.assign((size_t)16 * D, -1); classCol.assign((size_t)16 * D, -1);
-        int freeL[16] = {0}, freeK[16] = {0};           // lowest colour that may be free (hint; verified below)
+            for (int i = 0; i < cnt[l]; ++i) { degL[l]++; load[arcs[l][i] & 15]++; }
+        int maxdeg = 0, maxload = 0;
+        for (int i = 0; i < 16; ++i) { maxdeg = std::max(maxdeg, degL[i]); maxload = std::max(maxload, load[i]); }
+        // slots: the longest string, plus up to slack_pct % padding when that removes conflicts
+        int T = std::max(maxdeg, std::min(maxload, maxdeg + (maxdeg * slack_pct + 99) / 100));
+        T = std::max(T, (maxload + 1) / 2);
+        out.assign((size_t)T * 16, 0);
+        if (T == 0) return 0;
+        for (auto& b : bucket) b.clear();
+        int filled[16] = {0};
+        for (int l = 0; l < 16; ++l)
+            for (int i = 0; i < cnt[l]; ++i) {
+                const int k = arcs[l][i] & 15;
+                bucket[l * NK + (filled[k]++ < T ? k : k + 16)].push_back(arcs[l][i]);
+            }
+        const int D = T;
+        laneCol.assign((size_t)16 * D, -1); classCol.assign((size_t)NK * D, -1);
+        int freeL[16] = {0}, freeK[NK] = {0};           // lowest colour that may be free (hint; verified below)
         std::vector<int> path;
         for (int l = 0; l < 16; ++l)
-            for (int k = 0; k < 16; ++k)
-                for (size_t m = 0; m < bucket[l * 16 + k].size(); ++m) {
+            for (int k = 0; k < NK; ++k)
+                for (size_t m = 0; m < bucket[l * NK + k].size(); ++m) {
                     int a = freeL[l]; while (laneCol[(size_t)l * D + a] >= 0) ++a;
                     int b = freeK[k]; while (classCol[(size_t)k * D + b] >= 0) ++b;
                     freeL[l] = a; freeK[k] = b;
@@ -449,15 +468,16 @@ struct BridgeScheduler {
                     }
                     laneCol[(size_t)l * D + a] = (int16_t)k; classCol[(size_t)k * D + a] = (int16_t)l;
                 }
-        size_t taken[256] = {0};
+        size_t taken[16 * NK] = {0};
         for (int c = 0; c < D; ++c) {
             unsigned used = 0;
-            for (int l = 0; l < 16; ++l) { const int k = laneCol[(size_t)l * D + c]; if (k >= 0) used |= 1u << k; }
+            for (int l = 0; l < 16; ++l) { const int k = laneCol[(size_t)l * D + c]; if (k >= 0) used |= 1u << (k & 15); }
             for (int l = 0; l < 16; ++l) {
                 const int k = laneCol[(size_t)l * D + c];
-                if (k >= 0) out[(size_t)c * 16 + l] = bucket[l * 16 + k][taken[l * 16 + k]++];
+                if (k >= 0) out[(size_t)c * 16 + l] = bucket[l * NK + k][taken[l * NK + k]++];
                 else {
-                    const int fk = __builtin_ctz(~used & 0xffffu);               // a class no lane reads in this slot
+                    const unsigned fr = ~used & 0xffffu;                         // bank pairs no lane reads in this slot
+                    const int fk = fr ? __builtin_ctz(fr) : l;
                     used |= 1u << fk;
                     out[(size_t)c * 16 + l] = (uint16_t)(pad0 + ((fk - pad0) & 15));   // the padding entry of class fk
                 }
@@ -621,10 +641,6 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
         return wa != wb ? wa > wb : nref(a) > nref(b);
     });
     const int64_t n_sg = ((int64_t)ok.size() + 31) / 32;
-    out.sgoff.assign((size_t)n_sg + 1, 0);
-    out.sgref.assign((size_t)n_sg, 0);
-    out.ksid.assign((size_t)n_sg * 32, -1);
-    out.kp.assign((size_t)n_sg * 32, 0.0);
     std::vector<std::vector<uint16_t>> gsched((size_t)n_sg);              // per group: [slots][32] arc ids
     std::vector<int32_t> gslots((size_t)n_sg, 0);
     auto schedule = [&](int t) {
@@ -644,7 +660,7 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
                 }
                 slots[hh] = sch.run(ptr, cnt, half[hh]);
             }
-            const int S2 = (std::max(slots[0], slots[1]) + 7) / 8 * 8;       // two slots per word, rows in fours
+            const int S2 = (std::max(slots[0], slots[1]) + 1) / 2 * 2;       // two slots per word
             gslots[g] = S2;
             std::vector<uint16_t>& G = gsched[g];
             G.resize((size_t)S2 * 32);
@@ -660,33 +676,58 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
         schedule(0);
         for (auto& x : th) x.join();
     }
+    // super-groups of kKsSuper groups (the warps of one CTA), chunk-interleaved:
+    //   word (sg, chunk c, group-in-super w, row j, lane l) at sgoff[sg] + (((c*kKsSuper + w)*kKsChunkRows + j)*32 + l
+    // so that the warps of a CTA, walking their groups chunk by chunk, read one contiguous region together
+    // (profiles/microbench_stream.cu: 5.6 TB/s against 4.3 TB/s for one private block per warp)
+    const int64_t n_ssg = (n_sg + kKsSuper - 1) / kKsSuper;
+    const int64_t n_sgp = n_ssg * kKsSuper;                                  // groups incl. the padding of the last super-group
+    out.sgref.assign((size_t)n_sgp, 0);
+    out.ksid.assign((size_t)n_sgp * 32, -1);
+    out.kp.assign((size_t)n_sgp * 32, 0.0);
+    out.sgoff.assign((size_t)n_ssg + 1, 0);
     for (int64_t g = 0; g < n_sg; ++g) {
         int mr = 0;
         for (int64_t k = g * 32; k < std::min<int64_t>((int64_t)ok.size(), g * 32 + 32); ++k) mr = std::max(mr, nref(ok[k]));
         out.sgref[g] = mr;
-        out.sgoff[g + 1] = out.sgoff[g] + (int64_t)(mr + gslots[g] / 2) * 32;
     }
-    out.swords.assign((size_t)out.sgoff[n_sg] + 32, 0u);
+    for (int64_t sg = 0; sg < n_ssg; ++sg) {
+        int chunks = 1;
+        for (int64_t g = sg * kKsSuper; g < std::min(n_sg, (sg + 1) * kKsSuper); ++g)
+            chunks = std::max(chunks, (out.sgref[g] + gslots[g] / 2 + kKsChunkRows - 1) / kKsChunkRows);
+        out.sgoff[sg + 1] = out.sgoff[sg] + (int64_t)chunks * kKsSuper * kKsChunkRows * 32;
+    }
+    out.swords.assign((size_t)out.sgoff[n_ssg] + 32, 0u);
     auto fill = [&](int t) {
-        for (int64_t g = t; g < n_sg; g += T) {
-            uint32_t* base = out.swords.data() + out.sgoff[g];
-            const int mr = out.sgref[g];
-            for (int l = 0; l < 32; ++l) {
-                const int64_t k = g * 32 + l;
-                for (int r = 0; r < mr; ++r) base[(size_t)r * 32 + l] = (uint32_t)dummy_type;
-                if (k < (int64_t)ok.size()) {
-                    const int64_t i = ok[k];
-                    const Local& L = loc[i % T];
-                    const size_t j = i / T;
-                    out.ksid[k] = ids[i]; out.kp[k] = p[ids[i]];
-                    int r = 0;
-                    for (int64_t q = L.sreg[j]; q < L.sreg[j + 1]; ++q, ++r) base[(size_t)r * 32 + l] = (uint32_t)type_slot[reg_type[i % T][q]];
+        for (int64_t sg = t; sg < n_ssg; sg += T) {
+            uint32_t* sbase = out.swords.data() + out.sgoff[sg];
+            const int chunks = (int)((out.sgoff[sg + 1] - out.sgoff[sg]) / (kKsSuper * kKsChunkRows * 32));
+            for (int w = 0; w < kKsSuper; ++w) {
+                const int64_t g = sg * kKsSuper + w;
+                const int mr = g < n_sg ? out.sgref[g] : 0;
+                const int slots = g < n_sg ? gslots[g] : 0;
+                auto at = [&](int row, int l) -> uint32_t& {
+                    return sbase[(((size_t)(row / kKsChunkRows) * kKsSuper + w) * kKsChunkRows + row % kKsChunkRows) * 32 + l];
+                };
+                for (int l = 0; l < 32; ++l) {
+                    const int64_t k = g * 32 + l;
+                    for (int r = 0; r < mr; ++r) at(r, l) = (uint32_t)dummy_type;
+                    if (g < n_sg && k < (int64_t)ok.size()) {
+                        const int64_t i = ok[k];
+                        const Local& L = loc[i % T];
+                        const size_t j = i / T;
+                        out.ksid[k] = ids[i]; out.kp[k] = p[ids[i]];
+                        int r = 0;
+                        for (int64_t q = L.sreg[j]; q < L.sreg[j + 1]; ++q, ++r) at(r, l) = (uint32_t)type_slot[reg_type[i % T][q]];
+                    }
+                    const uint32_t padw = (uint32_t)(A.n_arcs + (l & 15)) * 0x10001u;     // both halves: the lane's own padding entry
+                    for (int row = mr; row < chunks * kKsChunkRows; ++row) {
+                        const int s2 = (row - mr) * 2;
+                        at(row, l) = s2 < slots ? (uint32_t)gsched[g][(size_t)s2 * 32 + l] | ((uint32_t)gsched[g][(size_t)(s2 + 1) * 32 + l] << 16) : padw;
+                    }
                 }
-                const std::vector<uint16_t>& G = gsched[g];
-                for (int s2 = 0; s2 < gslots[g]; s2 += 2)
-                    base[(size_t)(mr + s2 / 2) * 32 + l] = (uint32_t)G[(size_t)s2 * 32 + l] | ((uint32_t)G[(size_t)(s2 + 1) * 32 + l] << 16);
+                if (g < n_sg) std::vector<uint16_t>().swap(gsched[g]);
             }
-            std::vector<uint16_t>().swap(gsched[g]);
         }
     };
     {

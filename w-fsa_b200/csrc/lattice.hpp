@@ -103,6 +103,8 @@ void compile_corpus(const HostFsa& f, const LatticeArcs& A, const uint8_t* arc_a
 // are stored as bare EDGE words (the exit node is the dst of the last edge); larger regions use the
 // full stream format above (CHECK every kCheckEvery-th word, FIN last) so that they can be rescaled.
 constexpr int kSegSmallMax = 16;          // edges of a "small" region (unrolled in registers on the device)
+constexpr int kKsSuper = 16;              // groups (warps) per super-group of the KS layout
+constexpr int kKsChunkRows = 8;           // rows per interleaving chunk of the KS layout
 constexpr int kSegSmallStep = 4;          // small regions are padded to 4, 8, 12 or 16 word rows
 
 struct SegString {                         // one string, compiled
@@ -122,15 +124,18 @@ struct SegmentedCorpus {
     std::vector<int32_t> rgrows;               // [n_rgroups]
     std::vector<double> typeW;                 // [n_rgroups*32] sum of p_s over the instances (0 = padding lane)
     int64_t n_types = 0, n_region_instances = 0, n_region_edges = 0, n_type_edges = 0, max_big_rows = 0;
-    // KS: strings in groups of 32, longest first; string position kpos = g*32 + l
-    //   rows [0, sgref[g])        : region type ids (padding = dummy type n_rgroups*32, log q = 0)
-    //   rows [sgref[g], rows(g))  : two 16-bit bridge arcs per word (padding ids n_arcs .. n_arcs+15, log w = 0),
-    //                               scheduled per half-warp so that one shared-memory phase reads 16 different bank pairs
+    // KS: strings in groups of 32 (one warp), longest first; string position kpos = g*32 + l.  kKsSuper groups
+    // form a super-group (one CTA); its words are chunk-interleaved:
+    //   word (super-group sg, chunk c, group w in sg, row j in chunk, lane l)
+    //        at sgoff[sg] + (((c*kKsSuper + w)*kKsChunkRows + j)*32 + l,   chunks(sg) from sgoff[sg+1]-sgoff[sg]
+    //   rows [0, sgref[g])   of group g: region type ids (padding = dummy type n_rgroups*32, log q = 0)
+    //   the rows after them  : two 16-bit bridge arcs per word (padding ids n_arcs .. n_arcs+15, log w = 0),
+    //                          scheduled per half-warp against shared-memory bank conflicts (BridgeScheduler)
     std::vector<uint32_t> swords;
-    std::vector<int64_t> sgoff;                // [n_sgroups+1]
-    std::vector<int32_t> sgref;                // [n_sgroups]
-    std::vector<int32_t> ksid;                 // [n_sgroups*32] string id or -1
-    std::vector<double> kp;                    // [n_sgroups*32] p_s (0 = padding lane)
+    std::vector<int64_t> sgoff;                // [n_supergroups+1]
+    std::vector<int32_t> sgref;                // [n_supergroups*kKsSuper]
+    std::vector<int32_t> ksid;                 // [n_supergroups*kKsSuper*32] string id or -1
+    std::vector<double> kp;                    // [n_supergroups*kKsSuper*32] p_s (0 = padding lane)
     std::vector<int32_t> overflow, rejected;
     std::vector<long long> const_acc;          // [n_arcs] fixed-point constant gradient part (bridges)
     int64_t n_bridge = 0, n_strings = 0;

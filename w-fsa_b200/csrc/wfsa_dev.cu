@@ -127,7 +127,7 @@ struct wfsa_dev {
     DevBuf<double> d_klaw, d_klxs;
     DevBuf<unsigned long long> d_klacc, d_klconst;
     // segmented compiled lattices (KR + KS, kernel 6)
-    size_t ks_smem = 0; int ks_grid = 0, ks_block = 1024, ks_ctas = 2, ks_ring = 0;
+    size_t ks_smem = 0; int ks_grid = 0, ks_block = 512, ks_ctas = 2;
     int64_t kr_groups = 0, ks_groups = 0, seg_types = 0, seg_instances = 0, seg_region_edges = 0, seg_type_edges = 0,
             seg_bridges = 0, seg_words = 0;
     double seg_host_ms = 0;
@@ -348,37 +348,15 @@ static int setup_kl(wfsa_dev* h)
             CK(h->d_eoff.upload(off, h->stream)); CK(h->d_earc.upload(arc, h->stream));
         }
         h->ks_smem = ((size_t)A.n_arcs + 16) * 8;
-        {   // KS launch shape: WFSA_KS_SHAPE = "<threads>x<CTAs per SM>" selects one of the compiled variants (tuning)
-            int nt = 512, nb = 2;
-            h->ks_ring = 0;
-            if (const char* e = getenv("WFSA_KS_SHAPE")) {
-                if (!strncmp(e, "ring", 4)) h->ks_ring = atoi(e + 4);
-                else if (!strncmp(e, "tma", 3)) h->ks_ring = 100 + atoi(e + 3);
-                else sscanf(e, "%dx%d", &nt, &nb);
-            }
-            if (h->ks_ring) { const int nw = h->ks_ring % 100; if (nw != 16 && nw != 24 && nw != 8) h->ks_ring = h->ks_ring / 100 * 100 + 16; }
-            if (h->ks_ring && ks_tma_smem(A.n_arcs, h->ks_ring % 100) > 227 * 1024) h->ks_ring = 0;
-            if (!((nt == 1024 && nb == 2) || (nt == 768 && nb == 2) || (nt == 512 && nb == 2) || (nt == 512 && nb == 3) || (nt == 1024 && nb == 1))) { nt = 512; nb = 2; }
-            if (h->ks_smem * nb > 220 * 1024) { nt = 1024; nb = 1; }
-            h->ks_block = nt; h->ks_grid = h->sm_count * nb; h->ks_ctas = nb;
-            if (h->ks_ring) { h->ks_block = (h->ks_ring % 100) * 32; h->ks_grid = h->sm_count; h->ks_ctas = 1; }
-        }
-        cudaFuncSetAttribute(ks_strings_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(ks_strings_tma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(ks_strings_tma<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(ks_strings_ring<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(ks_strings_ring<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(ks_strings_ring<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        h->ks_block = kKsWarps * 32;
+        h->ks_ctas = h->ks_smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
+        h->ks_grid = h->sm_count * h->ks_ctas;
         cudaFuncSetAttribute(kr_regions<ACC_GLOBAL, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(kr_regions<ACC_GLOBAL, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(kr_regions<ACC_GLOBAL, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(kr_regions<ACC_SMEM_CAS, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(kr_regions<ACC_NONE, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(ks_strings<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(ks_strings<768, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(ks_strings<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(ks_strings<512, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(ks_strings<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(ks_strings, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
     cudaFuncSetAttribute(kl_fwdbwd<ACC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(kl_fwdbwd<ACC_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -599,21 +577,11 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
         }
         if (h->mid_now) cudaEventRecord(h->mid_now, st);
         KSParams S{};
-        S.logaw = h->d_klogaw.p; S.words = h->d_kswords.p; S.goff = h->d_ksgoff.p; S.gref = h->d_ksgref.p; S.lq = h->d_krlq.p;
-        S.p = h->d_ksp.p; S.logq = h->d_kslogq.p; S.n_groups = h->ks_groups; S.counter = h->d_klcounter.p + 1; S.red = O.red;
+        S.logaw = h->d_klogaw.p; S.words = h->d_kswords.p; S.sgoff = h->d_ksgoff.p; S.gref = h->d_ksgref.p; S.lq = h->d_krlq.p;
+        S.p = h->d_ksp.p; S.logq = h->d_kslogq.p; S.n_sgroups = h->ks_groups; S.counter = h->d_klcounter.p + 1; S.red = O.red;
         S.ll_scale = O.ll_scale; S.n_arcs = h->larcs.n_arcs;
         if (h->ks_groups > 0) {
-            if (h->ks_ring == 108) ks_strings_tma<8><<<h->ks_grid, 256, ks_tma_smem(S.n_arcs, 8), st>>>(S);
-            else if (h->ks_ring == 116) ks_strings_tma<16><<<h->ks_grid, 512, ks_tma_smem(S.n_arcs, 16), st>>>(S);
-            else if (h->ks_ring == 124) ks_strings_tma<24><<<h->ks_grid, 768, ks_tma_smem(S.n_arcs, 24), st>>>(S);
-            else if (h->ks_ring == 8) ks_strings_ring<8><<<h->ks_grid, 256, ks_ring_smem(S.n_arcs, 8), st>>>(S);
-            else if (h->ks_ring == 16) ks_strings_ring<16><<<h->ks_grid, 512, ks_ring_smem(S.n_arcs, 16), st>>>(S);
-            else if (h->ks_ring == 24) ks_strings_ring<24><<<h->ks_grid, 768, ks_ring_smem(S.n_arcs, 24), st>>>(S);
-            else if (h->ks_block == 1024 && h->ks_ctas == 2) ks_strings<1024, 2><<<h->ks_grid, 1024, h->ks_smem, st>>>(S);
-            else if (h->ks_block == 768) ks_strings<768, 2><<<h->ks_grid, 768, h->ks_smem, st>>>(S);
-            else if (h->ks_block == 512 && h->ks_ctas == 3) ks_strings<512, 3><<<h->ks_grid, 512, h->ks_smem, st>>>(S);
-            else if (h->ks_block == 512) ks_strings<512, 2><<<h->ks_grid, 512, h->ks_smem, st>>>(S);
-            else ks_strings<1024, 1><<<h->ks_grid, 1024, h->ks_smem, st>>>(S);
+            ks_strings<<<h->ks_grid, h->ks_block, h->ks_smem, st>>>(S);
             h->launches++;
         }
     } else if (kernel == 5) {
@@ -915,7 +883,7 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
         order_w = sc.overflow;
         order_w.insert(order_w.end(), sc.rejected.begin(), sc.rejected.end());
         h->n_active = (int64_t)order.size() - (int64_t)order_w.size(); h->n_active_w = (int64_t)order_w.size();
-        h->kr_groups = (int64_t)sc.rgrows.size(); h->ks_groups = (int64_t)sc.sgref.size();
+        h->kr_groups = (int64_t)sc.rgrows.size(); h->ks_groups = (int64_t)sc.sgoff.size() - 1;      // KS counts super-groups
         h->seg_types = sc.n_types; h->seg_instances = sc.n_region_instances; h->seg_region_edges = sc.n_region_edges;
         h->seg_type_edges = sc.n_type_edges; h->seg_bridges = sc.n_bridge; h->seg_host_ms = sc.host_ms;
         h->seg_words = (int64_t)sc.rwords.size() + (int64_t)sc.swords.size();
@@ -927,7 +895,7 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
         CK(h->d_kswords.upload(sc.swords, h->stream)); CK(h->d_ksgoff.upload(sc.sgoff, h->stream));
         CK(h->d_ksgref.upload(sc.sgref, h->stream)); CK(h->d_kssid.upload(sc.ksid, h->stream));
         CK(h->d_ksp.upload(sc.kp, h->stream));
-        CK(h->d_kslogq.alloc(std::max<size_t>((size_t)h->ks_groups * 32, 1)));
+        CK(h->d_kslogq.alloc(std::max<size_t>(sc.kp.size(), 1)));
         std::vector<unsigned long long> cacc(sc.const_acc.begin(), sc.const_acc.end());
         CK(cudaMemcpyAsync(h->d_klconst.p, cacc.data(), cacc.size() * 8, cudaMemcpyHostToDevice, h->stream));
         if (!order_w.empty()) CK(cudaMemcpyAsync(h->d_order_w.p, order_w.data(), order_w.size() * 4, cudaMemcpyHostToDevice, h->stream));
@@ -1036,7 +1004,7 @@ extern "C" int wfsa_dev_eval_fetch(wfsa_dev* h, double* loglik, double* logq, do
     if (h->n < 0) return set_err(h, WFSA_ERR_STATE, "fetch before set_param_map");
     CK(cudaMemcpyAsync(h->h_out, h->d_out.p, ((size_t)h->n + 2) * 8, cudaMemcpyDeviceToHost, h->stream));
     if (logq && h->kernel == 6 && h->ks_groups > 0) {
-        const long long nk = h->ks_groups * 32;
+        const long long nk = (long long)h->d_kssid.n;
         k_scatter_logq<<<(unsigned)((nk + 255) / 256), 256, 0, h->stream>>>(nk, h->d_kssid.p, h->d_kslogq.p, h->d_logq.p);
         h->launches++;
     }
