@@ -273,17 +273,6 @@ def run_ours(args, rank, world, local):
         ll_e, _, g_e = dev.eval(x, want_logq=False)
     e2e_s = time.perf_counter() - t0
     barrier()
-    if rank == 0 and len(sampler.lines) < 3:
-        # the timed regions are shorter than nvidia-smi's sampling period: keep the same load running (untimed)
-        # until the sampler has seen it, so that `clocks` describes the GPU under this workload
-        t_end = time.perf_counter() + 0.6
-        while time.perf_counter() < t_end:
-            for _ in range(50):
-                dev.eval_launch()
-            dev.sync()
-    clocks = sampler.stop() if rank == 0 else None
-    assert ll_e == ll and np.array_equal(g_e, grad), "resident and host-buffer evaluations must agree bitwise"
-
     tok_total, ms_max, e2e_max, kms_max = float(my_tokens), ms, e2e_s, kms
     if world > 1:
         v = torch.tensor([ms, e2e_s, kms], dtype=torch.float64, device="cuda")
@@ -292,6 +281,20 @@ def run_ours(args, rank, world, local):
         tt = torch.tensor([float(my_tokens)], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt)
         tok_total = float(tt.item())
+    if ms_max < 600.0:
+        # the timed regions are shorter than nvidia-smi's sampling period: keep the same load running (untimed)
+        # for ~0.6 s so that `clocks` describes the GPU under this workload.  Every rank runs the same number of
+        # evaluations (they contain a collective), derived from the all-reduced step time.
+        extra = int(min(20000, max(50, 600.0 / max(ms_max / args.steps, 1e-3))))
+        for i in range(extra):
+            dev.eval_launch()
+            if i % 200 == 199:
+                dev.sync()
+        dev.sync()
+        barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    assert ll_e == ll and np.array_equal(g_e, grad), "resident and host-buffer evaluations must agree bitwise"
+
     if rank == 0:
         steps = args.steps
         value = tok_total * steps / (ms_max * 1e-3)

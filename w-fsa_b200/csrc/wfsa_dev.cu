@@ -981,7 +981,7 @@ extern "C" int wfsa_dev_eval_launch(wfsa_dev* h)
     if (h->lean_finished) return WFSA_OK;          // k_fold_finish6 already wrote [loglik, bad, grad]
     rc = nccl_allreduce(h, h->d_red.p, h->d_red.n, ncclUint64, ncclSum);
     if (rc != WFSA_OK) return rc;
-    CK(cudaMemsetAsync(h->d_out.p, 0, h->d_out.n * 8, h->stream));
+    if (!h->lean_now) CK(cudaMemsetAsync(h->d_out.p, 0, h->d_out.n * 8, h->stream));   // k_prep6 already cleared it
     const int total = std::max(h->n_edges, 1);
     k_finish_eval<<<(total + 255) / 256, 256, 0, h->stream>>>(h->n_edges, h->n, h->d_red.p, h->d_edge_tp.p,
                                                              std::ldexp(1.0, -(int)h->fx_log2), std::ldexp(1.0, -(int)h->ll_log2), h->d_out.p);
