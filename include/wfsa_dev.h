@@ -185,7 +185,8 @@ int wfsa_lattice_stats(const wfsa_fsa_desc* fsa, const wfsa_corpus_desc* corpus,
 
 /* Host-only introspection of the SEGMENTED compiled form (w-fsa_b200/csrc/lattice.hpp, kernels 6): compiles a
  * whole shard exactly as wfsa_dev_set_param_map does and exposes the arrays the device kernels read, so that
- * tests can interpret them on the CPU.  All strings of the corpus take part, longest first.
+ * tests can interpret them on the CPU.  All strings of the corpus take part, longest first.  n_slots = pool slots
+ * (1..16), plus 64 to keep every region in DAG form (no path lists).
  * which: 0 rwords(u32) 1 rgoff(i64) 2 rgrows(i32) 3 typeW(f64) 4 swords(u32) 5 sgoff(i64) 6 sgref(i32)
  *        7 ksid(i32) 8 kp(f64) 9 overflow(i32) 10 rejected(i32) 11 const_acc(i64)
  *        12 stats(i64): types, region instances, instance edges, type edges, bridges, strings, host microseconds */

@@ -71,8 +71,33 @@ def interpret(seg, aw, n_arcs):
     lq = np.zeros(n_rg * 32 + 1)
     acc = seg["const_acc"].astype(np.float64) / FX
     seen = set()
+    n_path_types = n_dag_types = 0
     for g in range(n_rg):
-        rows = int(rgrows[g])
+        desc = int(rgrows[g])
+        if desc & 0x10000:                                   # path form: PP paths (zero-weight padding) of L edges
+            PP, L = (desc >> 8) & 0xff, desc & 0xff
+            assert PP in (2, 3, 4, 6, 8) and 1 <= L <= 16
+            assert rgoff[g + 1] - rgoff[g] == PP * L * 32
+            block = seg["rwords"][rgoff[g]:rgoff[g + 1]].reshape(L, PP, 32).astype(np.int64)
+            assert block.max() <= n_arcs
+            awz = np.append(aw, 0.0)
+            for l in range(32):
+                if W_[g * 32 + l] == 0.0:
+                    assert (block[:, :, l] == n_arcs).all()
+                    continue
+                key = (desc, block[:, :, l].tobytes())
+                assert key not in seen, "identical regions must be merged into one type"
+                seen.add(key)
+                r = awz[block[:, :, l]].prod(axis=0)             # product along each path
+                real = (block[:, :, l] != n_arcs).all(axis=0)
+                assert real.sum() >= 2 and ((block[:, :, l] == n_arcs).all(axis=0) | real).all()
+                q = r.sum()
+                lq[g * 32 + l] = np.log(q)
+                for p_ in np.where(real)[0]:
+                    np.add.at(acc, block[:, p_, l], W_[g * 32 + l] * r[p_] / q)
+                n_path_types += 1
+            continue
+        rows = desc
         assert rows in (4, 8, 12, 16) or (rows >= 32 and rows % 16 == 0)
         block = seg["rwords"][rgoff[g]:rgoff[g] + rows * 32].reshape(rows, 32)
         for l in range(32):
@@ -87,6 +112,8 @@ def interpret(seg, aw, n_arcs):
             lq[g * 32 + l], post = region_fwdbwd(col, aw, rows > 16)
             for arc, v in post.items():
                 acc[arc] += W_[g * 32 + l] * v
+            n_dag_types += 1
+    interpret.counts = (n_path_types, n_dag_types)
     sgoff, sgref, ksid, kp = seg["sgoff"], seg["sgref"], seg["ksid"], seg["kp"]
     logq = {}
     with np.errstate(divide="ignore"):
@@ -174,7 +201,13 @@ def test_config4_shape_bridges_regions_and_type_merging():
     st = seg["stats"]
     assert len(seg["overflow"]) == 0 and len(handled) == 600
     assert st[4] > 0 and st[1] > st[0] > 0, "expected bridges and merged region types"
-    assert (seg["rgrows"] > 16).any() and (seg["rgrows"] <= 16).any(), "expected small and big regions"
+    assert interpret.counts[0] > 0 and interpret.counts[1] > 0, "expected regions in path form and in DAG form"
+    # DAG form only (bit 6 of n_slots): the same numbers, small and big DAG regions
+    seg_d, ee_d, _, _, handled_d = check(low, trimmed, x, n_slots=16 | 64)
+    assert interpret.counts[0] == 0 and len(handled_d) == 600
+    dag_rows = seg_d["rgrows"]
+    assert (dag_rows > 16).any() and (dag_rows <= 16).any(), "expected small and big DAG regions"
+    assert np.allclose(ee_d, oee, rtol=1e-10, atol=1e-9)
     assert np.allclose(ee, oee, rtol=1e-10, atol=1e-9)
     # a pool of 2 slots cannot hold an ambiguous region: such strings are reported, never mis-compiled
     seg2, _, _, _, handled2 = check(low, trimmed, x, n_slots=2)

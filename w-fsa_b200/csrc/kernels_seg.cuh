@@ -20,7 +20,7 @@ struct KRParams {
     const double* __restrict__ aw;        // [n_arcs] a(u,v) * b(v,e)
     const uint32_t* __restrict__ words;   // word j of lane l of group g at goff[g] + j*32 + l
     const int64_t* __restrict__ goff;     // [n_groups+1]
-    const int32_t* __restrict__ grows;    // [n_groups] 4/8/12/16 = small region class, else big (multiple of 16, >= 32)
+    const int32_t* __restrict__ grows;    // [n_groups] 0x10000|paths<<8|length = path form; 4/8/12/16 = small DAG; else big DAG (multiple of 16)
     const double* __restrict__ typeW;     // [n_groups*32]
     double* lq;                           // [n_groups*32 + 1] log q per type (last = dummy, stays 0)
     long long n_groups;
@@ -107,6 +107,47 @@ __device__ __forceinline__ void kr_small(const KRParams& P, const double* aw, do
             }
             if (ACC == ACC_GLOBAL && b * 8 + j < 2) red_uniform(acc_g, key, v, lane);
             else if (ACC != ACC_NONE) { if (v) atomicAdd(acc_g + key, (unsigned long long)v); }
+        }
+    }
+}
+
+// One region in PATH FORM per thread: PP paths (padded with zero-weight paths) of L edges each, arc of edge l of
+// path p at row l*PP + p.  q = sum_p prod_l w[arc]; every edge of path p gets the posterior r_p / q.  Registers
+// only: PP independent multiply chains, no pool, no flags (the reference's P.x / exp / M algebra,
+// src/Learner.cpp:530-545, for one small segment).
+template <int PP, int ACC>
+__device__ __forceinline__ void kr_paths(const KRParams& P, const double* aw, int L, long long g, int lane, unsigned long long* acc_g)
+{
+    const uint32_t* wp = P.words + P.goff[g] + lane;
+    const double W = P.typeW[g * 32 + lane];
+    double r[PP];
+#pragma unroll
+    for (int p = 0; p < PP; ++p) r[p] = 1.0;
+    for (int l = 0; l < L; ++l) {
+        uint32_t a[PP];
+#pragma unroll
+        for (int p = 0; p < PP; ++p) a[p] = __ldg(wp + (size_t)(l * PP + p) * 32);
+#pragma unroll
+        for (int p = 0; p < PP; ++p) r[p] *= aw[a[p]];
+    }
+    double q = 0.0;
+#pragma unroll
+    for (int p = 0; p < PP; ++p) q += r[p];
+    const bool ok = W > 0.0 && q > 0.0 && isfinite(q);
+    if (W > 0.0) P.lq[g * 32 + lane] = ok ? log(q) : -INFINITY;
+    if (ACC == ACC_NONE) return;
+    const double sc = ok ? W * P.fx_scale / q : 0.0;
+    long long v[PP];
+#pragma unroll
+    for (int p = 0; p < PP; ++p) v[p] = __double2ll_rn(r[p] * sc);
+    for (int l = 0; l < L; ++l) {
+        uint32_t a[PP];
+#pragma unroll
+        for (int p = 0; p < PP; ++p) a[p] = __ldg(wp + (size_t)(l * PP + p) * 32);
+#pragma unroll
+        for (int p = 0; p < PP; ++p) {
+            if (ACC == ACC_GLOBAL && l == 0 && p < 2) red_uniform(acc_g, v[p] ? (int)a[p] : -1, v[p], lane);
+            else if (v[p]) atomicAdd(acc_g + a[p], (unsigned long long)v[p]);
         }
     }
 }
@@ -212,9 +253,9 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
 {
     extern __shared__ unsigned long long smem[];
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
-    double* aw = reinterpret_cast<double*>(smem);
-    double* pool = aw + P.n_arcs + tid;                       // slot s of this thread at pool[s*NT]
-    for (int i = tid; i < P.n_arcs; i += NT) aw[i] = P.aw[i];
+    double* aw = reinterpret_cast<double*>(smem);             // [n_arcs + 1]; the last entry is the zero weight of padding
+    double* pool = aw + P.n_arcs + 1 + tid;                   // slot s of this thread at pool[s*NT]
+    for (int i = tid; i <= P.n_arcs; i += NT) aw[i] = i < P.n_arcs ? P.aw[i] : 0.0;
     __syncthreads();
     const long long gwarp = ((long long)blockIdx.x * NT + tid) >> 5;
     double* const xs = P.xs + (size_t)gwarp * P.xs_rows * 32 + lane;
@@ -229,7 +270,16 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
         long long gn = 0;
         if (lane == 0) gn = (long long)atomicAdd(P.counter, 1u);
         const int rows = P.grows[g];
-        switch (rows) {
+        if (rows & 0x10000) {                                  // path form: paths << 8 | length
+            const int L = rows & 0xff;
+            switch ((rows >> 8) & 0xff) {
+                case 2: kr_paths<2, ACC>(P, aw, L, g, lane, acc_g); break;
+                case 3: kr_paths<3, ACC>(P, aw, L, g, lane, acc_g); break;
+                case 4: kr_paths<4, ACC>(P, aw, L, g, lane, acc_g); break;
+                case 6: kr_paths<6, ACC>(P, aw, L, g, lane, acc_g); break;
+                default: kr_paths<8, ACC>(P, aw, L, g, lane, acc_g); break;
+            }
+        } else switch (rows) {
             case 4: kr_small<4, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
             case 8: kr_small<8, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
             case 12: kr_small<12, ACC>(P, aw, pool, NT, g, lane, acc_g); break;

@@ -322,10 +322,58 @@ int compile_segments(const HostFsa& f, const LatticeArcs& A, const uint8_t* aliv
     }
     S.topo[end_node] = nt;
     S.nslot.assign(n_nodes, -1);
+    S.nout.assign(n_nodes, -1);
     const int nk = (int)S.kept.size();
+    const bool allow_paths = !(n_slots & 64);             // bit 6 of n_slots: DAG form only (tests, experiments)
+    n_slots &= 63;
+    // PATH FORM of a region: when it has at most kSegMaxPaths paths, all of one length L <= kSegMaxPathLen, the region
+    // is stored as its explicit path list (what the reference's P matrix holds for a whole string,
+    // src/Learner.cpp:295-314, here for one small segment): header word, then L*P arcs, edge l of path p at
+    // [1 + l*P + p].  q = sum_p prod_l w, posterior of a path = its product / q: registers only on the device.
+    std::vector<int32_t>& pstk = S.per_pos;                 // scratch: DFS stack of edge indices (kept[] positions)
+    std::vector<int32_t>& first_out = S.nout;               // scratch: first kept edge of a node inside the segment
+    auto try_paths = [&](int b, int e) -> bool {
+        if (!allow_paths) return false;
+        const int entry = S.esrc[S.kept[b]], exitn = S.edst[S.kept[e - 1]];
+        for (int i = b; i < e; ++i) first_out[S.esrc[S.kept[i]]] = -1;
+        for (int i = e - 1; i >= b; --i) first_out[S.esrc[S.kept[i]]] = i;      // edges of a node are contiguous
+        int n_paths = 0, L = -1;
+        std::vector<int32_t>& arcs = S.topo_tmp;            // path-major arcs of the paths found so far
+        arcs.clear();
+        pstk.clear();
+        // iterative DFS: pstk holds the current path as kept[] positions
+        int node = entry, next_edge = first_out[entry];
+        for (;;) {
+            if (node == exitn) {
+                if (L < 0) L = (int)pstk.size();
+                if ((int)pstk.size() != L || L > kSegMaxPathLen || ++n_paths > kSegMaxPaths) return false;
+                for (int i : pstk) arcs.push_back(S.earc[S.kept[i]]);
+                next_edge = -1;                             // backtrack
+            }
+            if (next_edge >= 0 && next_edge < e && S.esrc[S.kept[next_edge]] == node) {
+                if ((int)pstk.size() >= kSegMaxPathLen) return false;
+                pstk.push_back(next_edge);
+                node = S.edst[S.kept[next_edge]];
+                next_edge = node == exitn ? -1 : first_out[node];
+                continue;
+            }
+            if (pstk.empty()) break;
+            const int last = pstk.back();
+            pstk.pop_back();
+            node = S.esrc[S.kept[last]];
+            next_edge = last + 1;
+        }
+        if (n_paths < 2) return false;
+        out.rwords.push_back(kLatFin | (uint32_t)n_paths << 8 | (uint32_t)L);   // header: bit 31 clear, bit 30 set
+        for (int l = 0; l < L; ++l)
+            for (int q = 0; q < n_paths; ++q) out.rwords.push_back(kLatEdge | (uint32_t)arcs[(size_t)q * L + l]);
+        out.roff.push_back((int32_t)out.rwords.size());
+        return true;
+    };
     // one segment = kept edges [b, e): all edges whose source lies between two consecutive cut nodes
     auto emit_segment = [&](int b, int e) -> bool {
         if (e - b == 1) { out.bridges.push_back((uint16_t)S.earc[S.kept[b]]); return true; }
+        if (try_paths(b, e)) return true;
         const bool big = e - b > kSegSmallMax;
         const size_t base = out.rwords.size();
         uint32_t free_mask = n_slots >= 32 ? 0xffffffffu : ((1u << n_slots) - 1u), live = 0;
@@ -582,19 +630,25 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
     }
     out.n_strings = (int64_t)ok.size();
     out.n_types = (int64_t)types.size();
-    // ---- 3. KR layout: types by class (big ones first, longest first; then 16, 12, 8, 4 rows), sorted by content
-    auto rows_of = [&](const Type& Y) -> int {
-        int edges = 0;
+    // ---- 3. KR layout: types by class, sorted by content.  Class key (descending = roughly by cost):
+    //   DAG form, big   : 3<<24 | rows          rows = padded stream length (multiple of 16), groups may mix rows
+    //   DAG form, small : 2<<24 | rows          rows = 4, 8, 12, 16 bare edge words
+    //   path form       : 1<<24 | P'<<8 | L     P' = paths padded to 2, 3, 4, 6 or 8; word (l, p) at row l*P' + p
+    auto pad_paths = [](int P) { return P <= 4 ? std::max(P, 2) : (P <= 6 ? 6 : 8); };
+    auto class_of = [&](const Type& Y) -> int {
         const uint32_t* w = loc[Y.t].rwords.data() + Y.beg;
+        if (!(w[0] >> 31)) return (1 << 24) | pad_paths((int)((w[0] >> 8) & 0xff)) << 8 | (int)(w[0] & 0xff);     // path form header
+        int edges = 0;
         bool fin = false;
         for (int32_t k = 0; k < Y.len; ++k) { edges += (w[k] >> 31); fin = fin || (!(w[k] >> 31) && (w[k] & kLatFin)); }
-        if (!fin) return (edges + kSegSmallStep - 1) / kSegSmallStep * kSegSmallStep;      // small: bare edge words
-        return (Y.len + kCheckEvery - 1) / kCheckEvery * kCheckEvery;                      // big: padded stream
+        if (!fin) return (2 << 24) | (edges + kSegSmallStep - 1) / kSegSmallStep * kSegSmallStep;
+        return (3 << 24) | (Y.len + kCheckEvery - 1) / kCheckEvery * kCheckEvery;
     };
-    std::vector<int32_t> order(types.size()), trows(types.size());
-    for (size_t i = 0; i < types.size(); ++i) { order[i] = (int32_t)i; trows[i] = rows_of(types[i]); }
+    auto rows_of_class = [](int c) { return (c >> 24) == 1 ? ((c >> 8) & 0xff) * (c & 0xff) : (c & 0xffffff); };
+    std::vector<int32_t> order(types.size()), tcls(types.size());
+    for (size_t i = 0; i < types.size(); ++i) { order[i] = (int32_t)i; tcls[i] = class_of(types[i]); }
     std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-        if (trows[a] != trows[b]) return trows[a] > trows[b];
+        if (tcls[a] != tcls[b]) return tcls[a] > tcls[b];
         const Type &X = types[a], &Y = types[b];
         const uint32_t* wa = loc[X.t].rwords.data() + X.beg; const uint32_t* wb = loc[Y.t].rwords.data() + Y.beg;
         const int32_t m = std::min(X.len, Y.len);
@@ -606,29 +660,43 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
     {
         size_t i = 0;
         while (i < order.size()) {
-            const int rows = trows[order[i]];
-            const bool small = rows <= kSegSmallMax;
+            const int cls = tcls[order[i]];
+            const bool bigdag = (cls >> 24) == 3;
             size_t j = i;
-            // a group holds up to 32 types of one class (small: identical rows; big: rows of its first = longest)
-            while (j < order.size() && j - i < 32 && (small ? trows[order[j]] == rows : trows[order[j]] > kSegSmallMax)) ++j;
+            // a group holds up to 32 types of one class (big DAGs: any big class, rows of its first = longest)
+            while (j < order.size() && j - i < 32 && (bigdag ? (tcls[order[j]] >> 24) == 3 : tcls[order[j]] == cls)) ++j;
             const int64_t g = (int64_t)out.rgrows.size();
-            out.rgrows.push_back(rows);
+            const int rows = rows_of_class(cls);
+            out.rgrows.push_back((cls >> 24) == 1 ? (0x10000 | (cls & 0xffff)) : rows);
             out.rgoff.push_back(out.rgoff.back() + (int64_t)rows * 32);
             for (size_t k = i; k < j; ++k) type_slot[order[k]] = (int32_t)(g * 32 + (int64_t)(k - i));
-            if (!small) out.max_big_rows = std::max<int64_t>(out.max_big_rows, rows);
+            if (bigdag) out.max_big_rows = std::max<int64_t>(out.max_big_rows, rows);
             i = j;
         }
     }
     const int64_t n_rg = (int64_t)out.rgrows.size();
     out.rwords.assign((size_t)out.rgoff[n_rg] + 32, 0u);
     out.typeW.assign((size_t)n_rg * 32, 0.0);
+    for (int64_t g = 0; g < n_rg; ++g)
+        if (out.rgrows[g] & 0x10000) {                                    // path form: every unused cell reads the zero-weight arc
+            uint32_t* dst = out.rwords.data() + out.rgoff[g];
+            const int64_t cells = out.rgoff[g + 1] - out.rgoff[g];
+            for (int64_t k = 0; k < cells; ++k) dst[k] = (uint32_t)A.n_arcs;
+        }
     for (size_t ty = 0; ty < types.size(); ++ty) {
         const Type& Y = types[ty];
         const int32_t slot = type_slot[ty];
         const int64_t g = slot >> 5; const int l = slot & 31;
         const uint32_t* w = loc[Y.t].rwords.data() + Y.beg;
         uint32_t* dst = out.rwords.data() + out.rgoff[g] + l;
-        for (int32_t k = 0; k < Y.len; ++k) { dst[(size_t)k * 32] = w[k]; out.n_type_edges += (w[k] >> 31); }
+        if (!(w[0] >> 31)) {
+            const int P = (int)((w[0] >> 8) & 0xff), L = (int)(w[0] & 0xff), PP = pad_paths(P);
+            for (int el = 0; el < L; ++el)
+                for (int q = 0; q < P; ++q) dst[(size_t)(el * PP + q) * 32] = w[1 + el * P + q] & 0x7fffu;
+            out.n_type_edges += (int64_t)P * L;
+        } else {
+            for (int32_t k = 0; k < Y.len; ++k) { dst[(size_t)k * 32] = w[k]; out.n_type_edges += (w[k] >> 31); }
+        }
         out.typeW[slot] = Y.W;
     }
     // ---- 4. KS layout: strings by bridge count, longest first; the bridges of the 16 strings of a half-warp are

@@ -54,7 +54,7 @@ void build_lattice_arcs(const HostFsa& f, const GenericLayout& g, LatticeArcs& o
 
 struct LatticeScratch {
     std::vector<int32_t> node_of;              // [(max_len+1)*n_states] -> node id or -1
-    std::vector<int32_t> npos, nstate, nslot, nout, per_pos, topo, kept;
+    std::vector<int32_t> npos, nstate, nslot, nout, per_pos, topo, kept, topo_tmp;
     std::vector<uint8_t> coreach, done;
     std::vector<int32_t> esrc, edst, earc;
     std::vector<std::vector<int32_t>> bucket;  // node ids by position
@@ -103,6 +103,8 @@ void compile_corpus(const HostFsa& f, const LatticeArcs& A, const uint8_t* arc_a
 // are stored as bare EDGE words (the exit node is the dst of the last edge); larger regions use the
 // full stream format above (CHECK every kCheckEvery-th word, FIN last) so that they can be rescaled.
 constexpr int kSegSmallMax = 16;          // edges of a "small" region (unrolled in registers on the device)
+constexpr int kSegMaxPaths = 8;           // path form: a region with at most this many paths ...
+constexpr int kSegMaxPathLen = 16;        // ... all of one length, at most this many edges
 constexpr int kKsSuper = 16;              // groups (warps) per super-group of the KS layout
 constexpr int kKsChunkRows = 8;           // rows per interleaving chunk of the KS layout
 constexpr int kSegSmallStep = 4;          // small regions are padded to 4, 8, 12 or 16 word rows

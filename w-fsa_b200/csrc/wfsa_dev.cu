@@ -311,7 +311,7 @@ static bool kl_possible(const wfsa_dev* h, int K, int want_nt, int& nt, size_t& 
 {
     const LatticeArcs& A = h->larcs;
     if (A.n_arcs <= 0 || A.n_arcs >= (1 << kLatArcBits)) return false;
-    const size_t tab = (size_t)A.n_arcs * 8, max_smem = 227 * 1024;
+    const size_t tab = ((size_t)A.n_arcs + 1) * 8, max_smem = 227 * 1024;     // + the zero weight of padding (kr_regions)
     if (tab + (size_t)128 * K * 8 > max_smem) return false;
     nt = (int)((max_smem - tab) / ((size_t)K * 8) / 32) * 32;
     nt = std::min(nt, 1024);
@@ -1266,7 +1266,7 @@ extern "C" int wfsa_segmented_compile(const wfsa_fsa_desc* fd, const wfsa_corpus
                                       int32_t n_slots, double fx_scale, wfsa_segmented** out)
 {
     g_create_error.clear();
-    if (!fd || !cd || !out || n_slots < 1 || n_slots > kLatMaxSlots || cd->n_strings < 0) { g_create_error = "segmented_compile: bad arguments"; return WFSA_ERR_INVALID; }
+    if (!fd || !cd || !out || (n_slots & 63) < 1 || (n_slots & 63) > kLatMaxSlots || cd->n_strings < 0) { g_create_error = "segmented_compile: bad arguments"; return WFSA_ERR_INVALID; }   // bit 6: DAG form only
     *out = nullptr;
     HostFsa f; GenericLayout g;
     int status = WFSA_OK;
