@@ -129,7 +129,7 @@ struct wfsa_dev {
     // segmented compiled lattices (KR + KS, kernel 6)
     size_t ks_smem = 0; int ks_grid = 0, ks_block = 512, ks_ctas = 2;
     int64_t kr_dag_groups = 0;                  // groups [0, kr_dag_groups) are in DAG form, the rest in path form
-    size_t kp_smem = 0; int kp_grid = 0;
+    size_t kp_smem = 0; int kp_grid = 0, kp_ctas = 2;
     int64_t kr_groups = 0, ks_groups = 0, seg_types = 0, seg_instances = 0, seg_region_edges = 0, seg_type_edges = 0,
             seg_bridges = 0, seg_words = 0;
     double seg_host_ms = 0;
@@ -167,6 +167,7 @@ struct wfsa_dev {
     size_t kev_used = 0; bool timing = false;
     std::vector<cudaEvent_t> kev_mid;           // segmented path: between kr_regions and ks_strings
     cudaEvent_t mid_now = nullptr;
+    cudaStream_t stream2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;    // kr_regions (DAG form) next to kr_paths_kernel
 };
 
 #define CK(call)                                                                              \
@@ -226,6 +227,9 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     if (h->ev_end) cudaEventDestroy(h->ev_end);
     for (auto& e : h->kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto& e : h->kev_mid) cudaEventDestroy(e);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -352,9 +356,12 @@ static int setup_kl(wfsa_dev* h)
         h->ks_smem = ((size_t)A.n_arcs + 16) * 8;
         h->kp_smem = ((size_t)A.n_arcs + 1) * 8;
         h->kp_grid = h->sm_count * (int)std::max<size_t>(1, std::min<size_t>(3, (size_t)(220 * 1024) / (h->kp_smem + 1024)));
-        cudaFuncSetAttribute(kr_paths_kernel<ACC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(kr_paths_kernel<ACC_SMEM_CAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(kr_paths_kernel<ACC_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(kr_paths_kernel<ACC_GLOBAL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(kr_paths_kernel<ACC_GLOBAL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(kr_paths_kernel<ACC_SMEM_CAS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(kr_paths_kernel<ACC_NONE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (const char* e = getenv("WFSA_KP_CTAS")) h->kp_ctas = atoi(e) == 3 ? 3 : 2;                         // tuning knob
+        h->kp_grid = h->sm_count * h->kp_ctas;
         h->ks_block = kKsWarps * 32;
         h->ks_ctas = h->ks_smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
         h->ks_grid = h->sm_count * h->ks_ctas;
@@ -576,22 +583,38 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
             P.lq = h->d_krlq.p; P.xs = h->d_klxs.p; P.xs_rows = (size_t)std::max<int64_t>(h->kl_max_words, 1);
             P.acc = h->d_klacc.p; P.fx_scale = O.fx_scale; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas;
             if (const char* e = getenv("WFSA_KR_SKIP")) P.skip = atoi(e);      // timing experiments only (results are wrong)
+            // The few regions in DAG form are latency bound (one long dependency chain per thread, a handful of
+            // groups per SM): they run on a second stream next to the path-form kernel instead of in front of it.
+            const bool fork = h->kr_dag_groups > 0 && h->kr_groups > h->kr_dag_groups && !getenv("WFSA_KR_SERIAL");
+            cudaStream_t sd = st;
+            if (fork) {
+                if (!h->stream2) {
+                    cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+                    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+                }
+                cudaEventRecord(h->ev_fork, st);
+                cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+                sd = h->stream2;
+            }
             if (h->kr_dag_groups > 0) {                                        // regions in DAG form
                 P.g_first = 0; P.n_groups = h->kr_dag_groups; P.counter = h->d_klcounter.p;
-                if (h->opt.reserved & 2) kr_regions<ACC_NONE, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // timing experiment
-                else if (h->opt.reserved & 1) kr_regions<ACC_SMEM_CAS, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // plain REDs
-                else if (h->kl_block <= 512) kr_regions<ACC_GLOBAL, 512><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
-                else if (h->kl_block <= 768) kr_regions<ACC_GLOBAL, 768><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
-                else kr_regions<ACC_GLOBAL, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
+                if (h->opt.reserved & 2) kr_regions<ACC_NONE, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, sd>>>(P);   // timing experiment
+                else if (h->opt.reserved & 1) kr_regions<ACC_SMEM_CAS, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, sd>>>(P);   // plain REDs
+                else if (h->kl_block <= 512) kr_regions<ACC_GLOBAL, 512><<<h->kl_grid, h->kl_block, h->kl_smem, sd>>>(P);
+                else if (h->kl_block <= 768) kr_regions<ACC_GLOBAL, 768><<<h->kl_grid, h->kl_block, h->kl_smem, sd>>>(P);
+                else kr_regions<ACC_GLOBAL, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, sd>>>(P);
                 h->launches++;
+                if (fork) cudaEventRecord(h->ev_join, sd);
             }
             if (h->kr_groups > h->kr_dag_groups) {                             // regions in path form
                 P.g_first = h->kr_dag_groups; P.n_groups = h->kr_groups; P.counter = h->d_klcounter.p + 2;
-                if (h->opt.reserved & 2) kr_paths_kernel<ACC_NONE><<<h->kp_grid, 256, h->kp_smem, st>>>(P);
-                else if (h->opt.reserved & 1) kr_paths_kernel<ACC_SMEM_CAS><<<h->kp_grid, 256, h->kp_smem, st>>>(P);
-                else kr_paths_kernel<ACC_GLOBAL><<<h->kp_grid, 256, h->kp_smem, st>>>(P);
+                if (h->opt.reserved & 2) kr_paths_kernel<ACC_NONE, 2><<<h->kp_grid, 256, h->kp_smem, st>>>(P);
+                else if (h->opt.reserved & 1) kr_paths_kernel<ACC_SMEM_CAS, 2><<<h->kp_grid, 256, h->kp_smem, st>>>(P);
+                else if (h->kp_ctas == 3) kr_paths_kernel<ACC_GLOBAL, 3><<<h->kp_grid, 256, h->kp_smem, st>>>(P);
+                else kr_paths_kernel<ACC_GLOBAL, 2><<<h->kp_grid, 256, h->kp_smem, st>>>(P);
                 h->launches++;
             }
+            if (fork) cudaStreamWaitEvent(st, h->ev_join, 0);
         }
         if (h->mid_now) cudaEventRecord(h->mid_now, st);
         KSParams S{};
