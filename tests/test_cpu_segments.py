@@ -77,11 +77,9 @@ def interpret(seg, aw, n_arcs):
         if desc & 0x10000:                                   # path form: PP paths (zero-weight padding) of L edges
             PP, L = (desc >> 8) & 0xff, desc & 0xff
             assert PP in (2, 3, 4, 6, 8) and 1 <= L <= 16
-            lane_words = (PP * L + 3) // 4 * 4                # lane-major: a lane's arcs are contiguous, padded to 16 bytes
-            assert PP * L <= 32 and rgoff[g + 1] - rgoff[g] == lane_words * 32
-            raw = seg["rwords"][rgoff[g]:rgoff[g + 1]].reshape(32, lane_words).astype(np.int64)
-            assert raw.max() <= n_arcs and (raw[:, PP * L:] == n_arcs).all()
-            block = raw[:, :PP * L].reshape(32, L, PP).transpose(1, 2, 0)   # [edge l][path p][lane]
+            assert rgoff[g + 1] - rgoff[g] == PP * L * 32
+            block = seg["rwords"][rgoff[g]:rgoff[g + 1]].reshape(L, PP, 32).astype(np.int64)
+            assert block.max() <= n_arcs
             awz = np.append(aw, 0.0)
             for l in range(32):
                 if W_[g * 32 + l] == 0.0:

@@ -23,15 +23,15 @@ struct KRParams {
     const int32_t* __restrict__ grows;    // [n_groups] 0x10000|paths<<8|length = path form; 4/8/12/16 = small DAG; else big DAG (multiple of 16)
     const double* __restrict__ typeW;     // [n_groups*32]
     double* lq;                           // [n_groups*32 + 1] log q per type (last = dummy, stays 0)
-    long long n_groups;                   // groups [g_first, n_groups) belong to this launch
-    long long g_first;
+    long long n_groups;
     double* xs;                           // big regions: per warp [xs_rows][32]
     size_t xs_rows;
     unsigned int* counter;                // dynamic group scheduler
     unsigned long long* acc;              // [replicas][n_arcs]
     double fx_scale;
     int n_arcs, replicas;
-    int skip;                             // timing experiments only: 1 skips path-form groups, 2 DAG groups, 4 big DAG groups
+    long long n_first;                    // scheduler: tickets [0, n_first) map to the groups in order (the big DAG regions),
+    long long stride;                     // the others to n_first + ((ticket - n_first) * stride) % (n_groups - n_first)
 };
 
 // Adds one fixed-point value per lane into acc[key].  Region types are sorted by their arcs, so at the first
@@ -46,28 +46,6 @@ __device__ __forceinline__ void red_uniform(unsigned long long* acc_g, int key, 
         for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
         if (lane == 0 && key >= 0 && v) atomicAdd(acc_g + key, (unsigned long long)v);
     } else if (key >= 0 && v) atomicAdd(acc_g + key, (unsigned long long)v);
-}
-
-// The same for partly uniform rows: runs of adjacent lanes with one key (the types of a group are sorted) are summed
-// with a segmented shuffle scan and only the first lane of a run issues the RED -- but only when the warp has few
-// runs: the scan costs ~30 issue slots, a RED lane ~1 LSU cycle.  Must be called by all 32 lanes.
-__device__ __forceinline__ void red_adaptive(unsigned long long* acc_g, int key, long long v, int lane)
-{
-    const int kp = __shfl_up_sync(FULL, key, 1);
-    const bool head = lane == 0 || kp != key;
-    const unsigned heads = __ballot_sync(FULL, head);
-    if (__popc(heads) > 12) {                                 // mostly distinct keys: plain REDs
-        if (key >= 0 && v) atomicAdd(acc_g + key, (unsigned long long)v);
-        return;
-    }
-    const unsigned later = lane == 31 ? 0u : heads & ~((2u << lane) - 1u);
-    const int end = later ? __ffs(later) - 1 : 32;          // first lane of the next run
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const long long v2 = __shfl_down_sync(FULL, v, d);
-        if (lane + d < end) v += v2;
-    }
-    if (head && key >= 0 && v) atomicAdd(acc_g + key, (unsigned long long)v);
 }
 
 // One small region per thread, NE <= 16 word rows (bare EDGE words).  The x values of the forward sweep stay in
@@ -135,29 +113,25 @@ __device__ __forceinline__ void kr_small(const KRParams& P, const double* aw, do
     }
 }
 
-// One region in PATH FORM per thread: PP paths (padded with zero-weight paths) of L edges each, PP*L <= 32.
-// The words of a group are stored lane-major (a lane's PP*L arcs, padded to a multiple of 4, are contiguous), so a
-// thread fetches its whole region with up to eight 16-byte loads issued together and keeps it in registers:
-// arc of edge l of path p = word l*PP + p.  q = sum_p prod_l w[arc]; every edge of path p gets the posterior
-// r_p / q.  PP independent multiply chains, no pool, no flags (the reference's P.x / exp / M algebra,
+// One region in PATH FORM per thread: PP paths (padded with zero-weight paths) of L edges each, arc of edge l of
+// path p at row l*PP + p.  q = sum_p prod_l w[arc]; every edge of path p gets the posterior r_p / q.  Registers
+// only: PP independent multiply chains, no pool, no flags (the reference's P.x / exp / M algebra,
 // src/Learner.cpp:530-545, for one small segment).
 template <int PP, int ACC>
 __device__ __forceinline__ void kr_paths(const KRParams& P, const double* aw, int L, long long g, int lane, unsigned long long* acc_g)
 {
-    const int n = PP * L, rows4 = (n + 3) >> 2;               // arcs, 16-byte words per lane
-    const uint4* wq = reinterpret_cast<const uint4*>(P.words + P.goff[g]) + (size_t)lane * rows4;
+    const uint32_t* wp = P.words + P.goff[g] + lane;
     const double W = P.typeW[g * 32 + lane];
     double r[PP];
 #pragma unroll
     for (int p = 0; p < PP; ++p) r[p] = 1.0;
+    for (int l = 0; l < L; ++l) {
+        uint32_t a[PP];
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-        if (k < rows4) {
-            const uint4 t = __ldg(wq + k);
-            const uint32_t a[4] = {t.x, t.y, t.z, t.w};
+        for (int p = 0; p < PP; ++p) a[p] = __ldg(wp + (size_t)(l * PP + p) * 32);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) if (4 * k + e < n) r[(4 * k + e) % PP] *= aw[a[e]];
-        }
+        for (int p = 0; p < PP; ++p) r[p] *= aw[a[p]];
+    }
     double q = 0.0;
 #pragma unroll
     for (int p = 0; p < PP; ++p) q += r[p];
@@ -168,21 +142,16 @@ __device__ __forceinline__ void kr_paths(const KRParams& P, const double* aw, in
     long long v[PP];
 #pragma unroll
     for (int p = 0; p < PP; ++p) v[p] = __double2ll_rn(r[p] * sc);
+    for (int l = 0; l < L; ++l) {
+        uint32_t a[PP];
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-        if (k < rows4) {
-            const uint4 t = __ldg(wq + k);                    // re-read (L1): keeps the arcs out of the live registers
-            const uint32_t a[4] = {t.x, t.y, t.z, t.w};
+        for (int p = 0; p < PP; ++p) a[p] = __ldg(wp + (size_t)(l * PP + p) * 32);
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (4 * k + e < n) {
-                    const long long ve = v[(4 * k + e) % PP];
-                    const int key = ve ? (int)a[e] : -1;
-                    if (ACC == ACC_GLOBAL && 4 * k + e < PP) red_uniform(acc_g, key, ve, lane);
-                    else if (ACC == ACC_GLOBAL) red_adaptive(acc_g, key, ve, lane);
-                    else if (ve) atomicAdd(acc_g + key, (unsigned long long)ve);
-                }
+        for (int p = 0; p < PP; ++p) {
+            if (ACC == ACC_GLOBAL && l == 0 && p < 2) red_uniform(acc_g, v[p] ? (int)a[p] : -1, v[p], lane);
+            else if (v[p]) atomicAdd(acc_g + a[p], (unsigned long long)v[p]);
         }
+    }
 }
 
 // One big region per thread: the KL stream loop (CHECK words rescale, x values on a per-warp stack).
@@ -296,18 +265,28 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
     // groups are sorted by cost (big regions first, then 16, 12, 8, 4 rows) and handed out dynamically, one at a
     // time; the id of the next group is requested while the current one is processed.  Measured alternatives, all
     // slower: static round-robin (87 us against 58 us), two requests in flight (76 us), four groups per atomic (135 us)
+    // Tickets from the scheduler can be mapped to groups with a stride (P.stride > 1), so that concurrently running
+    // warps work on regions far apart in the sorted order; the big DAG regions (one long dependency chain per
+    // thread) keep their place at the front.  Measured on config 4: no gain over the sorted order (stride 1) here,
+    // although a split-off path-form kernel went from 82 us to 54 us with it (L2 atomics serialise per address).
+    const long long n_rest = P.n_groups - P.n_first;
+    auto group_of = [&](long long t) { return t < P.n_first || t >= P.n_groups ? t : P.n_first + ((t - P.n_first) * P.stride) % n_rest; };
     long long g = 0;
-    if (lane == 0) g = P.g_first + (long long)atomicAdd(P.counter, 1u);
+    if (lane == 0) g = group_of((long long)atomicAdd(P.counter, 1u));
     g = __shfl_sync(FULL, g, 0);
     while (g < P.n_groups) {
         long long gn = 0;
-        if (lane == 0) gn = P.g_first + (long long)atomicAdd(P.counter, 1u);
+        if (lane == 0) gn = group_of((long long)atomicAdd(P.counter, 1u));
         const int rows = P.grows[g];
-        if (P.skip && (((P.skip & 1) && (rows & 0x10000)) || ((P.skip & 2) && !(rows & 0x10000)) || ((P.skip & 4) && !(rows & 0x10000) && rows > 16))) {
-            g = __shfl_sync(FULL, gn, 0);
-            continue;
-        }
-        if (rows & 0x10000) {                                  // path form groups belong to kr_paths_kernel
+        if (rows & 0x10000) {                                  // path form: paths << 8 | length
+            const int L = rows & 0xff;
+            switch ((rows >> 8) & 0xff) {
+                case 2: kr_paths<2, ACC>(P, aw, L, g, lane, acc_g); break;
+                case 3: kr_paths<3, ACC>(P, aw, L, g, lane, acc_g); break;
+                case 4: kr_paths<4, ACC>(P, aw, L, g, lane, acc_g); break;
+                case 6: kr_paths<6, ACC>(P, aw, L, g, lane, acc_g); break;
+                default: kr_paths<8, ACC>(P, aw, L, g, lane, acc_g); break;
+            }
         } else switch (rows) {
             case 4: kr_small<4, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
             case 8: kr_small<8, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
@@ -316,104 +295,6 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
             default: kr_big<ACC>(P, aw, pool, NT, g, lane, xs, acc_g); break;
         }
         g = __shfl_sync(FULL, gn, 0);
-    }
-}
-
-// kKpBatch consecutive path-form groups of ONE small class (at most 8 arcs per lane: two 16-byte words) at once:
-// all their loads are issued together, so the latency chain  scheduler -> descriptor -> words -> table  is paid once
-// per batch instead of once per group (ncu: 60% of the stall samples of the one-group-at-a-time version waited on it).
-constexpr int kKpBatch = 4;
-
-template <int PP, int ACC>
-__device__ __forceinline__ void kr_paths_batch(const KRParams& P, const double* aw, int L, long long g0, long long off0, int lane,
-                                               unsigned long long* acc_g)
-{
-    const int n = PP * L, rows4 = (n + 3) >> 2;               // rows4 <= 2
-    const size_t gstride = (size_t)rows4 * 32;                // uint4 per group: consecutive groups of a class are contiguous
-    const uint4* wq = reinterpret_cast<const uint4*>(P.words + off0) + (size_t)lane * rows4;
-    uint4 t[kKpBatch][2];
-    double W[kKpBatch];
-#pragma unroll
-    for (int b = 0; b < kKpBatch; ++b) {
-        t[b][0] = __ldcs(wq + b * gstride);
-        if (rows4 > 1) t[b][1] = __ldcs(wq + b * gstride + 1);
-        W[b] = P.typeW[(g0 + b) * 32 + lane];
-    }
-#pragma unroll
-    for (int b = 0; b < kKpBatch; ++b) {
-        const uint32_t a[8] = {t[b][0].x, t[b][0].y, t[b][0].z, t[b][0].w, t[b][1].x, t[b][1].y, t[b][1].z, t[b][1].w};
-        double r[PP];
-#pragma unroll
-        for (int p = 0; p < PP; ++p) r[p] = 1.0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) if (i < n) r[i % PP] *= aw[a[i]];
-        double q = 0.0;
-#pragma unroll
-        for (int p = 0; p < PP; ++p) q += r[p];
-        const bool ok = W[b] > 0.0 && q > 0.0 && isfinite(q);
-        if (W[b] > 0.0) P.lq[(g0 + b) * 32 + lane] = ok ? log(q) : -INFINITY;
-        if (ACC == ACC_NONE) continue;
-        const double sc = ok ? W[b] * P.fx_scale / q : 0.0;
-        long long v[PP];
-#pragma unroll
-        for (int p = 0; p < PP; ++p) v[p] = __double2ll_rn(r[p] * sc);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (i < n) {
-                const long long ve = v[i % PP];
-                const int key = ve ? (int)a[i] : -1;
-                if (ACC == ACC_GLOBAL && i < PP) red_uniform(acc_g, key, ve, lane);
-                else if (ACC == ACC_GLOBAL) red_adaptive(acc_g, key, ve, lane);
-                else if (ve) atomicAdd(acc_g + key, (unsigned long long)ve);
-            }
-    }
-}
-
-// The path-form groups: no pool, 68 KB of arc weights per CTA, so several CTAs share an SM.
-template <int ACC, int KPB>
-__global__ void __launch_bounds__(256, KPB) kr_paths_kernel(const KRParams P)
-{
-    extern __shared__ unsigned long long smem[];
-    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
-    double* aw = reinterpret_cast<double*>(smem);             // [n_arcs + 1]; the last entry is the zero weight of padding
-    for (int i = tid; i <= P.n_arcs; i += NT) aw[i] = i < P.n_arcs ? P.aw[i] : 0.0;
-    __syncthreads();
-    unsigned long long* const acc_g = P.acc + (size_t)(blockIdx.x % P.replicas) * (size_t)P.n_arcs;
-    long long g0 = 0;
-    if (lane == 0) g0 = P.g_first + (long long)atomicAdd(P.counter, (unsigned)kKpBatch);
-    g0 = __shfl_sync(FULL, g0, 0);
-    while (g0 < P.n_groups) {
-        long long gn = 0;
-        if (lane == 0) gn = P.g_first + (long long)atomicAdd(P.counter, (unsigned)kKpBatch);
-        // descriptors of the batch: lane i holds group g0 + i
-        const long long gi = min(g0 + lane, P.n_groups - 1);
-        const int my_rows = lane < kKpBatch ? P.grows[gi] : 0;
-        const long long my_off = lane < kKpBatch ? P.goff[gi] : 0;
-        const int rows0 = __shfl_sync(FULL, my_rows, 0);
-        const long long off0 = __shfl_sync(FULL, my_off, 0);
-        const bool same = __all_sync(FULL, lane >= kKpBatch || (my_rows == rows0 && g0 + lane < P.n_groups));
-        const int PP0 = (rows0 >> 8) & 0xff, L0 = rows0 & 0xff;
-        if (P.skip & 1) { g0 = __shfl_sync(FULL, gn, 0); continue; }
-        if (same && PP0 * L0 <= 8 && PP0 <= 4) {
-            switch (PP0) {
-                case 2: kr_paths_batch<2, ACC>(P, aw, L0, g0, off0, lane, acc_g); break;
-                case 3: kr_paths_batch<3, ACC>(P, aw, L0, g0, off0, lane, acc_g); break;
-                default: kr_paths_batch<4, ACC>(P, aw, L0, g0, off0, lane, acc_g); break;
-            }
-        } else {
-            for (int b = 0; b < kKpBatch && g0 + b < P.n_groups; ++b) {
-                const int rows = __shfl_sync(FULL, my_rows, b);
-                const int L = rows & 0xff;
-                switch ((rows >> 8) & 0xff) {
-                    case 2: kr_paths<2, ACC>(P, aw, L, g0 + b, lane, acc_g); break;
-                    case 3: kr_paths<3, ACC>(P, aw, L, g0 + b, lane, acc_g); break;
-                    case 4: kr_paths<4, ACC>(P, aw, L, g0 + b, lane, acc_g); break;
-                    case 6: kr_paths<6, ACC>(P, aw, L, g0 + b, lane, acc_g); break;
-                    default: kr_paths<8, ACC>(P, aw, L, g0 + b, lane, acc_g); break;
-                }
-            }
-        }
-        g0 = __shfl_sync(FULL, gn, 0);
     }
 }
 
@@ -540,7 +421,7 @@ struct Prep6Params {
     const unsigned long long* __restrict__ const_acc;
     double* aw; double* logaw;
     unsigned long long* acc; unsigned long long* red;
-    unsigned int* counters;            // [4]
+    unsigned int* counters;            // [2]
     double* out;
 };
 __global__ void k_prep6(const Prep6Params P)
@@ -554,7 +435,7 @@ __global__ void k_prep6(const Prep6Params P)
     if (i < P.n_arcs * P.replicas) P.acc[i] = i < P.n_arcs ? P.const_acc[i] : 0ull;
     if (i < P.n_red) P.red[i] = 0ull;
     if (i < P.n_out) P.out[i] = 0.0;
-    if (i < 4) P.counters[i] = 0u;
+    if (i < 2) P.counters[i] = 0u;
 }
 
 // One launch behind it: per-arc accumulators (all replicas) -> per-edge sums (a gather over the arcs of the

@@ -364,7 +364,6 @@ int compile_segments(const HostFsa& f, const LatticeArcs& A, const uint8_t* aliv
             next_edge = last + 1;
         }
         if (n_paths < 2) return false;
-        if ((n_paths <= 4 ? std::max(n_paths, 2) : (n_paths <= 6 ? 6 : 8)) * L > kSegMaxPathWords) return false;
         out.rwords.push_back(kLatFin | (uint32_t)n_paths << 8 | (uint32_t)L);   // header: bit 31 clear, bit 30 set
         for (int l = 0; l < L; ++l)
             for (int q = 0; q < n_paths; ++q) out.rwords.push_back(kLatEdge | (uint32_t)arcs[(size_t)q * L + l]);
@@ -645,8 +644,7 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
         if (!fin) return (2 << 24) | (edges + kSegSmallStep - 1) / kSegSmallStep * kSegSmallStep;
         return (3 << 24) | (Y.len + kCheckEvery - 1) / kCheckEvery * kCheckEvery;
     };
-    // rows of 32 words a group of the class occupies (path form: lane-major, a lane's words padded to a multiple of 4)
-    auto rows_of_class = [](int c) { return (c >> 24) == 1 ? (((c >> 8) & 0xff) * (c & 0xff) + 3) / 4 * 4 : (c & 0xffffff); };
+    auto rows_of_class = [](int c) { return (c >> 24) == 1 ? ((c >> 8) & 0xff) * (c & 0xff) : (c & 0xffffff); };
     std::vector<int32_t> order(types.size()), tcls(types.size());
     for (size_t i = 0; i < types.size(); ++i) { order[i] = (int32_t)i; tcls[i] = class_of(types[i]); }
     std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
@@ -693,10 +691,8 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
         uint32_t* dst = out.rwords.data() + out.rgoff[g] + l;
         if (!(w[0] >> 31)) {
             const int P = (int)((w[0] >> 8) & 0xff), L = (int)(w[0] & 0xff), PP = pad_paths(P);
-            const int lane_words = (PP * L + 3) / 4 * 4;                  // lane-major: this lane's arcs are contiguous
-            uint32_t* mine = out.rwords.data() + out.rgoff[g] + (size_t)l * lane_words;
             for (int el = 0; el < L; ++el)
-                for (int q = 0; q < P; ++q) mine[el * PP + q] = w[1 + el * P + q] & 0x7fffu;
+                for (int q = 0; q < P; ++q) dst[(size_t)(el * PP + q) * 32] = w[1 + el * P + q] & 0x7fffu;
             out.n_type_edges += (int64_t)P * L;
         } else {
             for (int32_t k = 0; k < Y.len; ++k) { dst[(size_t)k * 32] = w[k]; out.n_type_edges += (w[k] >> 31); }

@@ -128,8 +128,7 @@ struct wfsa_dev {
     DevBuf<unsigned long long> d_klacc, d_klconst;
     // segmented compiled lattices (KR + KS, kernel 6)
     size_t ks_smem = 0; int ks_grid = 0, ks_block = 512, ks_ctas = 2;
-    int64_t kr_dag_groups = 0;                  // groups [0, kr_dag_groups) are in DAG form, the rest in path form
-    size_t kp_smem = 0; int kp_grid = 0, kp_ctas = 2;
+    int64_t kr_big_groups = 0, kr_stride = 1;   // scheduler ticket -> group map of kr_regions
     int64_t kr_groups = 0, ks_groups = 0, seg_types = 0, seg_instances = 0, seg_region_edges = 0, seg_type_edges = 0,
             seg_bridges = 0, seg_words = 0;
     double seg_host_ms = 0;
@@ -167,7 +166,6 @@ struct wfsa_dev {
     size_t kev_used = 0; bool timing = false;
     std::vector<cudaEvent_t> kev_mid;           // segmented path: between kr_regions and ks_strings
     cudaEvent_t mid_now = nullptr;
-    cudaStream_t stream2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;    // kr_regions (DAG form) next to kr_paths_kernel
 };
 
 #define CK(call)                                                                              \
@@ -227,9 +225,6 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     if (h->ev_end) cudaEventDestroy(h->ev_end);
     for (auto& e : h->kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto& e : h->kev_mid) cudaEventDestroy(e);
-    if (h->stream2) cudaStreamDestroy(h->stream2);
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -340,7 +335,7 @@ static int setup_kl(wfsa_dev* h)
     const LatticeArcs& A = h->larcs;
     CK(h->d_kl_arc_tid.upload(A.arc_tid, h->stream)); CK(h->d_kl_arc_eid.upload(A.arc_eid, h->stream));
     CK(h->d_klaw.alloc(A.n_arcs)); CK(h->d_klacc.alloc((size_t)A.n_arcs * h->replicas)); CK(h->d_klconst.alloc(A.n_arcs));
-    CK(h->d_klcounter.alloc(4));
+    CK(h->d_klcounter.alloc(2));
     if (h->kernel == 6) {
         CK(h->d_klogaw.alloc(A.n_arcs));
         {   // arcs of every edge (transition edges, then emission edges) for the gather in k_fold_finish6
@@ -354,14 +349,6 @@ static int setup_kl(wfsa_dev* h)
             CK(h->d_eoff.upload(off, h->stream)); CK(h->d_earc.upload(arc, h->stream));
         }
         h->ks_smem = ((size_t)A.n_arcs + 16) * 8;
-        h->kp_smem = ((size_t)A.n_arcs + 1) * 8;
-        h->kp_grid = h->sm_count * (int)std::max<size_t>(1, std::min<size_t>(3, (size_t)(220 * 1024) / (h->kp_smem + 1024)));
-        cudaFuncSetAttribute(kr_paths_kernel<ACC_GLOBAL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(kr_paths_kernel<ACC_GLOBAL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(kr_paths_kernel<ACC_SMEM_CAS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(kr_paths_kernel<ACC_NONE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (const char* e = getenv("WFSA_KP_CTAS")) h->kp_ctas = atoi(e) == 3 ? 3 : 2;                         // tuning knob
-        h->kp_grid = h->sm_count * h->kp_ctas;
         h->ks_block = kKsWarps * 32;
         h->ks_ctas = h->ks_smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
         h->ks_grid = h->sm_count * h->ks_ctas;
@@ -576,45 +563,19 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
     cudaStream_t st = h->stream;
     if (C.n_order <= 0) return;
     if (kernel == 6) {
-        if (!h->lean_now) cudaMemsetAsync(h->d_klcounter.p, 0, 16, st);
+        if (!h->lean_now) cudaMemsetAsync(h->d_klcounter.p, 0, 8, st);
         if (h->kr_groups > 0) {
             KRParams P{};
             P.aw = h->d_klaw.p; P.words = h->d_krwords.p; P.goff = h->d_krgoff.p; P.grows = h->d_krgrows.p; P.typeW = h->d_krW.p;
-            P.lq = h->d_krlq.p; P.xs = h->d_klxs.p; P.xs_rows = (size_t)std::max<int64_t>(h->kl_max_words, 1);
-            P.acc = h->d_klacc.p; P.fx_scale = O.fx_scale; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas;
-            if (const char* e = getenv("WFSA_KR_SKIP")) P.skip = atoi(e);      // timing experiments only (results are wrong)
-            // The few regions in DAG form are latency bound (one long dependency chain per thread, a handful of
-            // groups per SM): they run on a second stream next to the path-form kernel instead of in front of it.
-            const bool fork = h->kr_dag_groups > 0 && h->kr_groups > h->kr_dag_groups && !getenv("WFSA_KR_SERIAL");
-            cudaStream_t sd = st;
-            if (fork) {
-                if (!h->stream2) {
-                    cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
-                    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
-                }
-                cudaEventRecord(h->ev_fork, st);
-                cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
-                sd = h->stream2;
-            }
-            if (h->kr_dag_groups > 0) {                                        // regions in DAG form
-                P.g_first = 0; P.n_groups = h->kr_dag_groups; P.counter = h->d_klcounter.p;
-                if (h->opt.reserved & 2) kr_regions<ACC_NONE, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, sd>>>(P);   // timing experiment
-                else if (h->opt.reserved & 1) kr_regions<ACC_SMEM_CAS, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, sd>>>(P);   // plain REDs
-                else if (h->kl_block <= 512) kr_regions<ACC_GLOBAL, 512><<<h->kl_grid, h->kl_block, h->kl_smem, sd>>>(P);
-                else if (h->kl_block <= 768) kr_regions<ACC_GLOBAL, 768><<<h->kl_grid, h->kl_block, h->kl_smem, sd>>>(P);
-                else kr_regions<ACC_GLOBAL, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, sd>>>(P);
-                h->launches++;
-                if (fork) cudaEventRecord(h->ev_join, sd);
-            }
-            if (h->kr_groups > h->kr_dag_groups) {                             // regions in path form
-                P.g_first = h->kr_dag_groups; P.n_groups = h->kr_groups; P.counter = h->d_klcounter.p + 2;
-                if (h->opt.reserved & 2) kr_paths_kernel<ACC_NONE, 2><<<h->kp_grid, 256, h->kp_smem, st>>>(P);
-                else if (h->opt.reserved & 1) kr_paths_kernel<ACC_SMEM_CAS, 2><<<h->kp_grid, 256, h->kp_smem, st>>>(P);
-                else if (h->kp_ctas == 3) kr_paths_kernel<ACC_GLOBAL, 3><<<h->kp_grid, 256, h->kp_smem, st>>>(P);
-                else kr_paths_kernel<ACC_GLOBAL, 2><<<h->kp_grid, 256, h->kp_smem, st>>>(P);
-                h->launches++;
-            }
-            if (fork) cudaStreamWaitEvent(st, h->ev_join, 0);
+            P.lq = h->d_krlq.p; P.n_groups = h->kr_groups; P.xs = h->d_klxs.p; P.xs_rows = (size_t)std::max<int64_t>(h->kl_max_words, 1);
+            P.counter = h->d_klcounter.p; P.acc = h->d_klacc.p; P.fx_scale = O.fx_scale; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas;
+            P.n_first = h->kr_big_groups; P.stride = h->kr_stride;
+            if (h->opt.reserved & 2) kr_regions<ACC_NONE, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // timing experiment
+            else if (h->opt.reserved & 1) kr_regions<ACC_SMEM_CAS, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // plain REDs
+            else if (h->kl_block <= 512) kr_regions<ACC_GLOBAL, 512><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
+            else if (h->kl_block <= 768) kr_regions<ACC_GLOBAL, 768><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
+            else kr_regions<ACC_GLOBAL, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
+            h->launches++;
         }
         if (h->mid_now) cudaEventRecord(h->mid_now, st);
         KSParams S{};
@@ -924,8 +885,15 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
         order_w = sc.overflow;
         order_w.insert(order_w.end(), sc.rejected.begin(), sc.rejected.end());
         h->n_active = (int64_t)order.size() - (int64_t)order_w.size(); h->n_active_w = (int64_t)order_w.size();
-        h->kr_dag_groups = 0;
-        for (int32_t r : sc.rgrows) if (!(r & 0x10000)) h->kr_dag_groups++;          // DAG classes sort before path classes
+        h->kr_big_groups = 0;
+        for (int32_t r : sc.rgrows) if (!(r & 0x10000) && r > kSegSmallMax) h->kr_big_groups++;      // big DAG classes sort first
+        {
+            const int64_t rest = (int64_t)sc.rgrows.size() - h->kr_big_groups;
+            int64_t stride = getenv("WFSA_KR_STRIDE") ? atoll(getenv("WFSA_KR_STRIDE")) : 1;     // tuning knob; 1 = sorted order (measured best)
+            stride = rest > 1 ? stride % rest : 1;
+            while (stride > 1 && std::__gcd(stride, rest) != 1) --stride;
+            h->kr_stride = std::max<int64_t>(stride, 1);
+        }
         h->kr_groups = (int64_t)sc.rgrows.size(); h->ks_groups = (int64_t)sc.sgoff.size() - 1;      // KS counts super-groups
         h->seg_types = sc.n_types; h->seg_instances = sc.n_region_instances; h->seg_region_edges = sc.n_region_edges;
         h->seg_type_edges = sc.n_type_edges; h->seg_bridges = sc.n_bridge; h->seg_host_ms = sc.host_ms;
