@@ -31,6 +31,7 @@ struct KRParams {
     unsigned long long* acc;              // [replicas][n_arcs]
     double fx_scale;
     int n_arcs, replicas;
+    int n_params, pool_doubles;           // trimmed parameters; doubles the pool area of a CTA holds
     long long n_first;                    // scheduler: tickets [0, n_first) map to the groups in order (the big DAG regions),
     long long stride;                     // the others to n_first + ((ticket - n_first) * stride) % (n_groups - n_first)
 };
@@ -258,9 +259,26 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
     double* aw = reinterpret_cast<double*>(smem);             // [n_arcs + 1]; the last entry is the zero weight of padding
     double* pool = aw + P.n_arcs + 1 + tid;                   // slot s of this thread at pool[s*NT]
-    // arc weights a(u,v) * b(v,e) straight from x (the exp(P.x) of src/Learner.cpp:530-533, per arc instead of per path)
-    for (int i = tid; i <= P.n_arcs; i += NT)
-        aw[i] = i < P.n_arcs ? exp(logweight_of(P.arc_tp[2 * i], P.x, 0) + logweight_of(P.arc_tp[2 * i + 1], P.x, 0)) : 0.0;
+    // arc weights a(u,v) * b(v,e) straight from x (the exp(P.x) of src/Learner.cpp:530-533, per arc instead of per
+    // path): one exp per PARAMETER into the (not yet used) pool area, then one product per arc
+    {
+        double* ex = aw + P.n_arcs + 1;
+        const bool fits = P.n_params <= P.pool_doubles;
+        if (fits) {
+            for (int i = tid; i < P.n_params; i += NT) ex[i] = exp(P.x[i]);
+            __syncthreads();
+        }
+        for (int i = tid; i <= P.n_arcs; i += NT) {
+            double w = 0.0;
+            if (i < P.n_arcs) {
+                const int t = P.arc_tp[2 * i], e = P.arc_tp[2 * i + 1];
+                const double wt = t >= 0 ? (fits ? ex[t] : exp(P.x[t])) : (t == -1 ? 1.0 : 0.0);
+                const double we = e >= 0 ? (fits ? ex[e] : exp(P.x[e])) : (e == -1 ? 1.0 : 0.0);
+                w = wt * we;
+            }
+            aw[i] = w;                                        // (aw and ex do not overlap)
+        }
+    }
     __syncthreads();
     const long long gwarp = ((long long)blockIdx.x * NT + tid) >> 5;
     double* const xs = P.xs + (size_t)gwarp * P.xs_rows * 32 + lane;
@@ -349,23 +367,6 @@ __global__ void __launch_bounds__(kKsWarps * 32, 2) ks_strings(const KSParams P)
     for (int i = tid; i < P.n_arcs + 16; i += kKsWarps * 32)
         tab[i] = i < P.n_arcs ? logweight_of(P.arc_tp[2 * i], P.x, 0) + logweight_of(P.arc_tp[2 * i + 1], P.x, 0) : 0.0;
     if (tid == 0) s_next[0] = (long long)atomicAdd(P.counter, 1u);
-    // ---- fold: the region kernel is complete, so the per-arc accumulators are final.  One warp per edge: gather
-    //      over the (arc, replica) cells of the edge, shuffle sum (integers: exact, any order), conversion.
-    for (int e = blockIdx.x * kKsWarps + warp; e < P.n_edges; e += gridDim.x * kKsWarps) {
-        const int k0 = P.e_off[e], cells = (P.e_off[e + 1] - k0) * P.replicas;
-        unsigned long long sum = 0;
-        for (int c = lane; c < cells; c += 32) sum += P.acc[(size_t)(c % P.replicas) * P.n_arcs + P.e_arc[k0 + c / P.replicas]];
-#pragma unroll
-        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
-        if (lane == 0) {
-            P.red[2 + e] = sum;
-            const int tp = P.edge_tp[e];
-            if (P.finish && tp >= 0 && tp < P.n) P.out[2 + tp] = -(double)(long long)sum * P.inv_fx;
-        }
-    }
-    // ---- the other accumulator buffer (consumed by the previous evaluation's fold) starts the next evaluation
-    for (int i = blockIdx.x * (kKsWarps * 32) + tid; i < P.n_arcs * P.replicas; i += gridDim.x * (kKsWarps * 32))
-        P.acc_next[i] = i < P.n_arcs ? P.const_acc[i] : 0ull;
     __syncthreads();
     long long ll_fx = 0;
     unsigned long long bad = 0;
@@ -417,6 +418,30 @@ __global__ void __launch_bounds__(kKsWarps * 32, 2) ks_strings(const KSParams P)
         par ^= 1;
         sg = s_next[par];
     }
+    // ---- fold (the region kernel is complete, so the per-arc accumulators are final), done by the warps as they run
+    //      out of strings -- it fills the tail of the kernel.  One warp per edge: gather over the (arc, replica) cells
+    //      of the edge, shuffle sum (integers: exact, any order), conversion.
+    for (;;) {                                                 // eight edges per ticket: CTAs that finish early take the work
+        int e0 = 0;
+        if (lane == 0) e0 = (int)atomicAdd(P.counters + 3, 8u);
+        e0 = __shfl_sync(FULL, e0, 0);
+        if (e0 >= P.n_edges) break;
+        for (int e = e0; e < min(e0 + 8, P.n_edges); ++e) {
+        const int k0 = P.e_off[e], cells = (P.e_off[e + 1] - k0) * P.replicas;
+        unsigned long long sum = 0;
+        for (int c = lane; c < cells; c += 32) sum += P.acc[(size_t)(c % P.replicas) * P.n_arcs + P.e_arc[k0 + c / P.replicas]];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+        if (lane == 0) {
+            P.red[2 + e] = sum;
+            const int tp = P.edge_tp[e];
+            if (P.finish && tp >= 0 && tp < P.n) P.out[2 + tp] = -(double)(long long)sum * P.inv_fx;
+        }
+        }
+    }
+    // ---- the other accumulator buffer (consumed by the previous evaluation's fold) starts the next evaluation
+    for (int i = blockIdx.x * (kKsWarps * 32) + tid; i < P.n_arcs * P.replicas; i += gridDim.x * (kKsWarps * 32))
+        P.acc_next[i] = i < P.n_arcs ? P.const_acc[i] : 0ull;
     for (int o = 16; o; o >>= 1) { ll_fx += __shfl_xor_sync(FULL, ll_fx, o); bad += __shfl_xor_sync(FULL, bad, o); }
     if (lane == 0) {
         if (ll_fx) atomicAdd(P.red, (unsigned long long)ll_fx);
