@@ -1184,16 +1184,14 @@ __global__ void k_arcs_to_edges(int n_arcs, int n_slots /* = n_states */, int n_
 }
 
 // out[0] = loglik, out[1] = #non-finite strings, out[2+i] = grad_i = -sum_s p_s E_s[count_i]
-// rearm: red[0], red[1] are cleared after use (the two-launch segmented path accumulates into them again)
-__global__ void k_finish_eval(int n_edges, int n, unsigned long long* red,
-                              const int32_t* __restrict__ edge_tp, double inv_fx, double inv_ll, double* out, int rearm)
+__global__ void k_finish_eval(int n_edges, int n, const unsigned long long* __restrict__ red,
+                              const int32_t* __restrict__ edge_tp, double inv_fx, double inv_ll, double* out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         const double bad = (double)red[1];
         out[0] = bad > 0 ? -INFINITY : (double)(long long)red[0] * inv_ll;
         out[1] = bad;
-        if (rearm) { red[0] = 0ull; red[1] = 0ull; }
     }
     if (i < n_edges) {
         const int tp = edge_tp[i];

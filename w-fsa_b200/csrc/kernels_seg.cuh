@@ -17,8 +17,7 @@
 namespace wfsa {
 
 struct KRParams {
-    const double* __restrict__ x;         // [n] natural-log weights of the trimmed parameters
-    const int32_t* __restrict__ arc_tp;   // [2*n_arcs] trimmed parameter of the arc's transition, of its emission (-1 pinned, -2 removed)
+    const double* __restrict__ aw;        // [n_arcs] a(u,v) * b(v,e)
     const uint32_t* __restrict__ words;   // word j of lane l of group g at goff[g] + j*32 + l
     const int64_t* __restrict__ goff;     // [n_groups+1]
     const int32_t* __restrict__ grows;    // [n_groups] 0x10000|paths<<8|length = path form; 4/8/12/16 = small DAG; else big DAG (multiple of 16)
@@ -31,7 +30,6 @@ struct KRParams {
     unsigned long long* acc;              // [replicas][n_arcs]
     double fx_scale;
     int n_arcs, replicas;
-    int n_params, pool_doubles;           // trimmed parameters; doubles the pool area of a CTA holds
     long long n_first;                    // scheduler: tickets [0, n_first) map to the groups in order (the big DAG regions),
     long long stride;                     // the others to n_first + ((ticket - n_first) * stride) % (n_groups - n_first)
 };
@@ -259,26 +257,7 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
     double* aw = reinterpret_cast<double*>(smem);             // [n_arcs + 1]; the last entry is the zero weight of padding
     double* pool = aw + P.n_arcs + 1 + tid;                   // slot s of this thread at pool[s*NT]
-    // arc weights a(u,v) * b(v,e) straight from x (the exp(P.x) of src/Learner.cpp:530-533, per arc instead of per
-    // path): one exp per PARAMETER into the (not yet used) pool area, then one product per arc
-    {
-        double* ex = aw + P.n_arcs + 1;
-        const bool fits = P.n_params <= P.pool_doubles;
-        if (fits) {
-            for (int i = tid; i < P.n_params; i += NT) ex[i] = exp(P.x[i]);
-            __syncthreads();
-        }
-        for (int i = tid; i <= P.n_arcs; i += NT) {
-            double w = 0.0;
-            if (i < P.n_arcs) {
-                const int t = P.arc_tp[2 * i], e = P.arc_tp[2 * i + 1];
-                const double wt = t >= 0 ? (fits ? ex[t] : exp(P.x[t])) : (t == -1 ? 1.0 : 0.0);
-                const double we = e >= 0 ? (fits ? ex[e] : exp(P.x[e])) : (e == -1 ? 1.0 : 0.0);
-                w = wt * we;
-            }
-            aw[i] = w;                                        // (aw and ex do not overlap)
-        }
-    }
+    for (int i = tid; i <= P.n_arcs; i += NT) aw[i] = i < P.n_arcs ? P.aw[i] : 0.0;
     __syncthreads();
     const long long gwarp = ((long long)blockIdx.x * NT + tid) >> 5;
     double* const xs = P.xs + (size_t)gwarp * P.xs_rows * 32 + lane;
@@ -321,8 +300,7 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
 
 // ------------------------------------------------------------------------------------------
 struct KSParams {
-    const double* __restrict__ x;         // [n] natural-log weights of the trimmed parameters
-    const int32_t* __restrict__ arc_tp;   // [2*n_arcs] as in KRParams
+    const double* __restrict__ logaw;     // [n_arcs] log weight of every combined arc
     const uint32_t* __restrict__ words;   // chunk-interleaved super-groups (lattice.hpp, SegmentedCorpus)
     const int64_t* __restrict__ sgoff;    // [n_sgroups+1]
     const int32_t* __restrict__ gref;     // [n_sgroups*16] leading rows of a group that hold region type ids
@@ -334,18 +312,6 @@ struct KSParams {
     unsigned long long* red;              // red[0] fixed-point loglik, red[1] non-finite strings
     double ll_scale;
     int n_arcs;
-    // fold + finish + re-initialisation, done by the same launch (the region kernel has completed by then):
-    int n_edges, replicas, n, finish;
-    const int32_t* __restrict__ e_off;      // [n_edges+1] arcs of every edge (transition edges, then emission edges)
-    const int32_t* __restrict__ e_arc;
-    const unsigned long long* __restrict__ acc;        // this evaluation's accumulators [replicas][n_arcs]
-    unsigned long long* acc_next;                      // the other buffer: reset here for the next evaluation
-    const unsigned long long* __restrict__ const_acc;  // [n_arcs] constant bridge part (replica 0 starts from it)
-    const int32_t* __restrict__ edge_tp;
-    double inv_fx, inv_ll;
-    double* out;                            // [2 + n] loglik, non-finite strings, grad
-    unsigned int* done;                     // CTAs that have finished
-    unsigned int* counters;                 // [4] scheduler counters, reset by the last CTA
 };
 
 // KS: one CTA of 16 warps per super-group of 16 groups, one warp per group, one thread per string.
@@ -364,8 +330,7 @@ __global__ void __launch_bounds__(kKsWarps * 32, 2) ks_strings(const KSParams P)
     __shared__ long long s_next[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* tab = reinterpret_cast<double*>(smem);            // [n_arcs + 16]; ids n_arcs.. (padding, one per bank pair) -> 0
-    for (int i = tid; i < P.n_arcs + 16; i += kKsWarps * 32)
-        tab[i] = i < P.n_arcs ? logweight_of(P.arc_tp[2 * i], P.x, 0) + logweight_of(P.arc_tp[2 * i + 1], P.x, 0) : 0.0;
+    for (int i = tid; i < P.n_arcs + 16; i += kKsWarps * 32) tab[i] = i < P.n_arcs ? P.logaw[i] : 0.0;
     if (tid == 0) s_next[0] = (long long)atomicAdd(P.counter, 1u);
     __syncthreads();
     long long ll_fx = 0;
@@ -418,50 +383,10 @@ __global__ void __launch_bounds__(kKsWarps * 32, 2) ks_strings(const KSParams P)
         par ^= 1;
         sg = s_next[par];
     }
-    // ---- fold (the region kernel is complete, so the per-arc accumulators are final), done by the warps as they run
-    //      out of strings -- it fills the tail of the kernel.  One warp per edge: gather over the (arc, replica) cells
-    //      of the edge, shuffle sum (integers: exact, any order), conversion.
-    for (;;) {                                                 // eight edges per ticket: CTAs that finish early take the work
-        int e0 = 0;
-        if (lane == 0) e0 = (int)atomicAdd(P.counters + 3, 8u);
-        e0 = __shfl_sync(FULL, e0, 0);
-        if (e0 >= P.n_edges) break;
-        for (int e = e0; e < min(e0 + 8, P.n_edges); ++e) {
-        const int k0 = P.e_off[e], cells = (P.e_off[e + 1] - k0) * P.replicas;
-        unsigned long long sum = 0;
-        for (int c = lane; c < cells; c += 32) sum += P.acc[(size_t)(c % P.replicas) * P.n_arcs + P.e_arc[k0 + c / P.replicas]];
-#pragma unroll
-        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
-        if (lane == 0) {
-            P.red[2 + e] = sum;
-            const int tp = P.edge_tp[e];
-            if (P.finish && tp >= 0 && tp < P.n) P.out[2 + tp] = -(double)(long long)sum * P.inv_fx;
-        }
-        }
-    }
-    // ---- the other accumulator buffer (consumed by the previous evaluation's fold) starts the next evaluation
-    for (int i = blockIdx.x * (kKsWarps * 32) + tid; i < P.n_arcs * P.replicas; i += gridDim.x * (kKsWarps * 32))
-        P.acc_next[i] = i < P.n_arcs ? P.const_acc[i] : 0ull;
     for (int o = 16; o; o >>= 1) { ll_fx += __shfl_xor_sync(FULL, ll_fx, o); bad += __shfl_xor_sync(FULL, bad, o); }
     if (lane == 0) {
         if (ll_fx) atomicAdd(P.red, (unsigned long long)ll_fx);
         if (bad) atomicAdd(P.red + 1, bad);
-    }
-    // ---- the last CTA to finish writes [loglik, bad] and re-arms the counters for the next evaluation
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        if (atomicAdd(P.done, 1u) == gridDim.x - 1) {
-            __threadfence();
-            if (P.finish) {
-                const unsigned long long r0 = atomicAdd(P.red, 0ull), r1 = atomicAdd(P.red + 1, 0ull);
-                P.out[0] = r1 > 0 ? -INFINITY : (double)(long long)r0 * P.inv_ll;
-                P.out[1] = (double)r1;
-                P.red[0] = 0ull; P.red[1] = 0ull;
-            }
-            P.counters[0] = 0u; P.counters[1] = 0u; P.counters[2] = 0u; P.counters[3] = 0u;
-            *P.done = 0u;
-        }
     }
 }
 
@@ -486,19 +411,72 @@ __global__ void k_arc_weights_log(int n_arcs, const int32_t* __restrict__ arc_ti
 }
 
 
-// Brings the buffers of the two-launch evaluation (kr_regions, ks_strings) into their start state; needed once
-// after wfsa_dev_set_param_map and after any evaluation that took another route -- in steady state ks_strings
-// leaves everything ready for the next evaluation itself.
-__global__ void k_init6(int n_arcs, int replicas, int n_red, const unsigned long long* __restrict__ const_acc,
-                        unsigned long long* acc_both /* [2][replicas][n_arcs] */, unsigned long long* red,
-                        unsigned int* counters /* [4] */, unsigned int* done)
+// One launch in front of an evaluation of the segmented path: arc weights from x, accumulators reset
+// (replica 0 starts from the constant bridge part), reduction cells, scheduler counters and the output cleared.
+struct Prep6Params {
+    int n_arcs, replicas, n_red, n_out;
+    const int32_t* __restrict__ arc_tid; const int32_t* __restrict__ arc_eid;
+    const int32_t* __restrict__ trans_tp; const int32_t* __restrict__ emis_tp;
+    const double* __restrict__ x;
+    const unsigned long long* __restrict__ const_acc;
+    double* aw; double* logaw;
+    unsigned long long* acc; unsigned long long* red;
+    unsigned int* counters;            // [2]
+    double* out;
+};
+__global__ void k_prep6(const Prep6Params P)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int cells = n_arcs * replicas;
-    if (i < 2 * cells) acc_both[i] = (i % cells) < n_arcs ? const_acc[i % cells] : 0ull;
-    if (i < n_red) red[i] = 0ull;
-    if (i < 4) counters[i] = 0u;
-    if (i == 0) *done = 0u;
+    if (i < P.n_arcs) {
+        const double l = logweight_of(P.trans_tp[P.arc_tid[i]], P.x, 0) + (P.arc_eid[i] < 0 ? 0.0 : logweight_of(P.emis_tp[P.arc_eid[i]], P.x, 0));
+        P.logaw[i] = l;
+        P.aw[i] = exp(l);
+    }
+    if (i < P.n_arcs * P.replicas) P.acc[i] = i < P.n_arcs ? P.const_acc[i] : 0ull;
+    if (i < P.n_red) P.red[i] = 0ull;
+    if (i < P.n_out) P.out[i] = 0.0;
+    if (i < 2) P.counters[i] = 0u;
+}
+
+// One launch behind it: per-arc accumulators (all replicas) -> per-edge sums (a gather over the arcs of the
+// edge, fixed order, integer adds) -> and, without a communicator, straight to [loglik, bad, grad].
+struct Fin6Params {
+    int n_edges, n_arcs, replicas, n, finish;
+    const int32_t* __restrict__ e_off;      // [n_edges+1] arcs of every edge (transition edges, then emission edges)
+    const int32_t* __restrict__ e_arc;
+    const unsigned long long* __restrict__ acc;
+    unsigned long long* red;
+    const int32_t* __restrict__ edge_tp;
+    double inv_fx, inv_ll;
+    double* out;
+};
+__global__ void k_fold_finish6(const Fin6Params P)
+{
+    // one warp per edge: its lanes share the (arc, replica) cells of the edge, then a shuffle sum (integers)
+    const int lane = threadIdx.x & 31;
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (e == 0 && lane == 0 && P.finish) {
+        const double bad = (double)P.red[1];
+        P.out[0] = bad > 0 ? -INFINITY : (double)(long long)P.red[0] * P.inv_ll;
+        P.out[1] = bad;
+    }
+    if (e >= P.n_edges) return;
+    const int k0 = P.e_off[e], cells = (P.e_off[e + 1] - k0) * P.replicas;
+    unsigned long long s = 0;
+    for (int c = lane; c < cells; c += 32) {
+        const int a = P.e_arc[k0 + c / P.replicas], r = c % P.replicas;
+        s += P.acc[(size_t)r * P.n_arcs + a];
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if (lane == 0) {
+        s += P.red[2 + e];
+        P.red[2 + e] = s;
+        if (P.finish) {
+            const int tp = P.edge_tp[e];
+            if (tp >= 0 && tp < P.n) P.out[2 + tp] = -(double)(long long)s * P.inv_fx;
+        }
+    }
 }
 
 }  // namespace wfsa

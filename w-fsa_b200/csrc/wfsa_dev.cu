@@ -149,10 +149,7 @@ struct wfsa_dev {
     long long kt_groups = 0;
     std::vector<uint8_t> h_overflow;
     int64_t launches = 0;
-    bool structure_done = false, lean_finished = false, lean_now = false, lean_clean = false;
-    int acc_phase = 0;                          // which half of d_klacc the next two-launch evaluation accumulates into
-    DevBuf<int32_t> d_arc_tp2;                  // [2*n_arcs] trimmed parameters of every combined arc
-    DevBuf<unsigned int> d_done;
+    bool structure_done = false, lean_finished = false, lean_now = false;
     std::vector<uint8_t> h_recognised;
     // Hessian
     DevBuf<int64_t> d_hb_path_off, d_hb_col_off, d_hb_val_off;
@@ -214,7 +211,7 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     h->d_klacc.release(); h->d_klconst.release();
     h->d_krwords.release(); h->d_kswords.release(); h->d_krgoff.release(); h->d_ksgoff.release(); h->d_krgrows.release();
     h->d_ksgref.release(); h->d_kssid.release(); h->d_krW.release(); h->d_krlq.release(); h->d_ksp.release();
-    h->d_kslogq.release(); h->d_klogaw.release(); h->d_eoff.release(); h->d_earc.release(); h->d_arc_tp2.release(); h->d_done.release();
+    h->d_kslogq.release(); h->d_klogaw.release(); h->d_eoff.release(); h->d_earc.release();
     for (auto* b : u32) b->release();
     DevBuf<double>* f64[] = {&h->d_p, &h->d_x, &h->d_tw, &h->d_sw, &h->d_fw, &h->d_ltw, &h->d_lew, &h->d_logq, &h->d_pathcnt,
                              &h->d_out, &h->d_k3lat, &h->d_gscratch, &h->d_aw, &h->d_hb_counts, &h->d_hb_p, &h->d_hb_r, &h->d_H, &h->d_rmin};
@@ -337,10 +334,8 @@ static int setup_kl(wfsa_dev* h)
     h->kl_bridges = !(h->opt.reserved & 4);
     const LatticeArcs& A = h->larcs;
     CK(h->d_kl_arc_tid.upload(A.arc_tid, h->stream)); CK(h->d_kl_arc_eid.upload(A.arc_eid, h->stream));
-    CK(h->d_klaw.alloc(A.n_arcs)); CK(h->d_klacc.alloc((size_t)A.n_arcs * h->replicas * 2)); CK(h->d_klconst.alloc(A.n_arcs));
-    CK(h->d_arc_tp2.alloc((size_t)A.n_arcs * 2)); CK(h->d_done.alloc(1));
-    CK(cudaMemsetAsync(h->d_done.p, 0, 4, h->stream));      // every ks_strings launch counts it up to the grid size and resets it
-    CK(h->d_klcounter.alloc(4));
+    CK(h->d_klaw.alloc(A.n_arcs)); CK(h->d_klacc.alloc((size_t)A.n_arcs * h->replicas)); CK(h->d_klconst.alloc(A.n_arcs));
+    CK(h->d_klcounter.alloc(2));
     if (h->kernel == 6) {
         CK(h->d_klogaw.alloc(A.n_arcs));
         {   // arcs of every edge (transition edges, then emission edges) for the gather in k_fold_finish6
@@ -568,14 +563,13 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
     cudaStream_t st = h->stream;
     if (C.n_order <= 0) return;
     if (kernel == 6) {
-        if (!h->lean_now) cudaMemsetAsync(h->d_klcounter.p, 0, 16, st);
+        if (!h->lean_now) cudaMemsetAsync(h->d_klcounter.p, 0, 8, st);
         if (h->kr_groups > 0) {
             KRParams P{};
-            P.x = h->d_x.p; P.arc_tp = h->d_arc_tp2.p; P.words = h->d_krwords.p; P.goff = h->d_krgoff.p; P.grows = h->d_krgrows.p; P.typeW = h->d_krW.p;
+            P.aw = h->d_klaw.p; P.words = h->d_krwords.p; P.goff = h->d_krgoff.p; P.grows = h->d_krgrows.p; P.typeW = h->d_krW.p;
             P.lq = h->d_krlq.p; P.n_groups = h->kr_groups; P.xs = h->d_klxs.p; P.xs_rows = (size_t)std::max<int64_t>(h->kl_max_words, 1);
-            P.counter = h->d_klcounter.p; P.acc = h->d_klacc.p + (h->lean_now ? (size_t)h->acc_phase * h->larcs.n_arcs * h->replicas : 0); P.fx_scale = O.fx_scale; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas;
+            P.counter = h->d_klcounter.p; P.acc = h->d_klacc.p; P.fx_scale = O.fx_scale; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas;
             P.n_first = h->kr_big_groups; P.stride = h->kr_stride;
-            P.n_params = h->n; P.pool_doubles = h->kl_block * h->kl_K;
             if (h->opt.reserved & 2) kr_regions<ACC_NONE, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // timing experiment
             else if (h->opt.reserved & 1) kr_regions<ACC_SMEM_CAS, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // plain REDs
             else if (h->kl_block <= 512) kr_regions<ACC_GLOBAL, 512><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
@@ -585,18 +579,9 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
         }
         if (h->mid_now) cudaEventRecord(h->mid_now, st);
         KSParams S{};
-        S.x = h->d_x.p; S.arc_tp = h->d_arc_tp2.p; S.words = h->d_kswords.p; S.sgoff = h->d_ksgoff.p; S.gref = h->d_ksgref.p; S.lq = h->d_krlq.p;
+        S.logaw = h->d_klogaw.p; S.words = h->d_kswords.p; S.sgoff = h->d_ksgoff.p; S.gref = h->d_ksgref.p; S.lq = h->d_krlq.p;
         S.p = h->d_ksp.p; S.logq = h->d_kslogq.p; S.n_sgroups = h->ks_groups; S.counter = h->d_klcounter.p + 1; S.red = O.red;
         S.ll_scale = O.ll_scale; S.n_arcs = h->larcs.n_arcs;
-        {   // fold + finish + re-initialisation inside ks_strings (two-launch evaluation); otherwise no edges to fold here
-            const size_t half = (size_t)h->larcs.n_arcs * h->replicas;
-            S.n_edges = h->lean_now ? h->n_edges : 0; S.replicas = h->replicas; S.n = h->n; S.finish = (h->lean_now && !h->comm) ? 1 : 0;
-            S.e_off = h->d_eoff.p; S.e_arc = h->d_earc.p; S.acc = h->d_klacc.p + (h->lean_now ? (size_t)h->acc_phase * half : 0);
-            S.acc_next = h->d_klacc.p + (size_t)(h->acc_phase ^ 1) * half; S.const_acc = h->d_klconst.p; S.edge_tp = h->d_edge_tp.p;
-            S.inv_fx = std::ldexp(1.0, -(int)h->fx_log2); S.inv_ll = std::ldexp(1.0, -(int)h->ll_log2); S.out = h->d_out.p;
-            S.done = h->d_done.p; S.counters = h->d_klcounter.p;
-            if (!h->lean_now) { S.replicas = 0; }       // n_arcs * 0 cells: the other buffer is left alone
-        }
         if (h->ks_groups > 0) {
             ks_strings<<<h->ks_grid, h->ks_block, h->ks_smem, st>>>(S);
             h->launches++;
@@ -683,21 +668,18 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
     const HostFsa& F = h->fsa;
     cudaStream_t st = h->stream;
     const int unit = (mode == MODE_STRUCT) ? 1 : 0;
-    // segmented path without overflow strings: TWO launches per evaluation.  kr_regions and ks_strings compute their
-    // arc weights from x themselves; ks_strings also folds the accumulators, writes [loglik, bad, grad] and leaves
-    // every buffer ready for the next evaluation (the accumulators are double buffered).
+    // segmented path without overflow strings: one prep launch, KR, KS, one fold(+finish) launch
     const bool lean6 = kernel == 6 && mode == MODE_EVAL && clear && fold && (kernel2 == 0 || n_order2 == 0);
     if (lean6) {
-        if (!h->lean_clean) {
-            const int na = h->larcs.n_arcs, total = std::max({2 * na * h->replicas, (int)h->d_red.n, 4});
-            k_init6<<<(total + 255) / 256, 256, 0, st>>>(na, h->replicas, (int)h->d_red.n, h->d_klconst.p, h->d_klacc.p, h->d_red.p,
-                                                        h->d_klcounter.p, h->d_done.p);
-            h->launches++;
-            h->acc_phase = 0;
-            h->lean_clean = true;
-        }
+        Prep6Params P{};
+        P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas; P.n_red = (int)h->d_red.n; P.n_out = (int)h->d_out.n;
+        P.arc_tid = h->d_kl_arc_tid.p; P.arc_eid = h->d_kl_arc_eid.p; P.trans_tp = h->d_trans_tp.p; P.emis_tp = h->d_emis_tp.p;
+        P.x = h->d_x.p; P.const_acc = h->d_klconst.p; P.aw = h->d_klaw.p; P.logaw = h->d_klogaw.p; P.acc = h->d_klacc.p;
+        P.red = h->d_red.p; P.counters = h->d_klcounter.p; P.out = h->d_out.p;
+        const int total = std::max({P.n_arcs * P.replicas, P.n_red, P.n_out, 2});
+        k_prep6<<<(total + 255) / 256, 256, 0, st>>>(P);
+        h->launches++;
     } else if (clear) {
-        h->lean_clean = false;
         CK(cudaMemsetAsync(h->d_red.p, 0, h->d_red.n * 8, st));
         if (h->fast.ok) CK(cudaMemsetAsync(h->d_acc.p, 0, h->d_acc.n * 8, st));
         const int n_slots = h->fast.ok ? h->fast.n_slots : 0;
@@ -719,11 +701,13 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
         }
         if (kernel == 5 || kernel == 6) {
             const int na = h->larcs.n_arcs;
-            if (kernel == 5) {        // the segmented kernels compute their arc weights from x themselves
+            if (kernel == 6)
+                k_arc_weights_log<<<(na + 255) / 256, 256, 0, st>>>(na, h->d_kl_arc_tid.p, h->d_kl_arc_eid.p, h->d_trans_tp.p,
+                                                                  h->d_emis_tp.p, h->d_x.p, h->d_klaw.p, h->d_klogaw.p);
+            else
                 k_arc_weights<<<(na + 255) / 256, 256, 0, st>>>(na, h->d_kl_arc_tid.p, h->d_kl_arc_eid.p, h->d_emis_tp.p, h->d_tw.p,
                                                               h->d_x.p, unit, h->d_klaw.p);
-                h->launches++;
-            }
+            h->launches++;
             // replica 0 starts from the constant part (bridge edges: posterior exactly 1), the others from 0
             CK(cudaMemcpyAsync(h->d_klacc.p, h->d_klconst.p, (size_t)na * 8, cudaMemcpyDeviceToDevice, st));
             if (h->replicas > 1) CK(cudaMemsetAsync(h->d_klacc.p + na, 0, (size_t)na * (h->replicas - 1) * 8, st));
@@ -749,8 +733,13 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
     h->mid_now = nullptr;
     CK(cudaGetLastError());
     if (lean6) {
+        Fin6Params P{};
+        P.n_edges = h->n_edges; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas; P.n = h->n; P.finish = h->comm ? 0 : 1;
+        P.e_off = h->d_eoff.p; P.e_arc = h->d_earc.p; P.acc = h->d_klacc.p; P.red = h->d_red.p; P.edge_tp = h->d_edge_tp.p;
+        P.inv_fx = std::ldexp(1.0, -(int)h->fx_log2); P.inv_ll = std::ldexp(1.0, -(int)h->ll_log2); P.out = h->d_out.p;
+        k_fold_finish6<<<(std::max(h->n_edges, 1) + 7) / 8, 256, 0, st>>>(P);      // one warp per edge
+        h->launches++;
         CK(cudaGetLastError());
-        h->acc_phase ^= 1;                       // ks_strings has re-initialised the other half
         h->lean_finished = !h->comm;
         return WFSA_OK;
     }
@@ -890,13 +879,6 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
         std::vector<uint8_t> alive((size_t)A.n_arcs);
         for (int a = 0; a < A.n_arcs; ++a)
             alive[a] = ttp[A.arc_tid[a]] != -2 && (A.arc_eid[a] < 0 || etp[A.arc_eid[a]] != -2);
-        {
-            std::vector<int32_t> tp2((size_t)A.n_arcs * 2);
-            for (int a = 0; a < A.n_arcs; ++a) { tp2[2 * a] = ttp[A.arc_tid[a]]; tp2[2 * a + 1] = A.arc_eid[a] < 0 ? -1 : etp[A.arc_eid[a]]; }
-            CK(cudaMemcpyAsync(h->d_arc_tp2.p, tp2.data(), tp2.size() * 4, cudaMemcpyHostToDevice, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
-            h->lean_clean = false;
-        }
         SegmentedCorpus sc;
         compile_corpus_segmented(h->fsa, A, alive.data(), h->h_tokens.data(), h->h_offs.data(), h->h_p.data(), order, h->kl_K,
                                  std::ldexp(1.0, (int)h->fx_log2), sc);
@@ -1010,11 +992,10 @@ extern "C" int wfsa_dev_eval_launch(wfsa_dev* h)
     if (h->lean_finished) return WFSA_OK;          // k_fold_finish6 already wrote [loglik, bad, grad]
     rc = nccl_allreduce(h, h->d_red.p, h->d_red.n, ncclUint64, ncclSum);
     if (rc != WFSA_OK) return rc;
-    if (!h->lean_now) CK(cudaMemsetAsync(h->d_out.p, 0, h->d_out.n * 8, h->stream));   // (every entry is rewritten on the lean path)
+    if (!h->lean_now) CK(cudaMemsetAsync(h->d_out.p, 0, h->d_out.n * 8, h->stream));   // k_prep6 already cleared it
     const int total = std::max(h->n_edges, 1);
     k_finish_eval<<<(total + 255) / 256, 256, 0, h->stream>>>(h->n_edges, h->n, h->d_red.p, h->d_edge_tp.p,
-                                                             std::ldexp(1.0, -(int)h->fx_log2), std::ldexp(1.0, -(int)h->ll_log2), h->d_out.p,
-                                                             h->lean_now ? 1 : 0);
+                                                             std::ldexp(1.0, -(int)h->fx_log2), std::ldexp(1.0, -(int)h->ll_log2), h->d_out.p);
     h->launches++;
     CK(cudaGetLastError());
     return WFSA_OK;
@@ -1083,7 +1064,6 @@ extern "C" int wfsa_dev_set_path_blocks(wfsa_dev* h, const wfsa_path_blocks* b)
     long long bound = (long long)std::ceil(cmax * cmax) + 1;
     if (h->comm) {
         long long* d = reinterpret_cast<long long*>(h->d_red.p);
-        h->lean_clean = false;                  // d_red is borrowed as a scratch cell
         CK(cudaMemcpyAsync(d, &bound, 8, cudaMemcpyHostToDevice, h->stream));
         int rc = nccl_allreduce(h, d, 1, ncclInt64, ncclMax);
         if (rc != WFSA_OK) return rc;
