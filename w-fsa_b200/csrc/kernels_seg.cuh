@@ -479,4 +479,66 @@ __global__ void k_fold_finish6(const Fin6Params P)
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// One-shot all-reduce of the evaluation result over NVLink peer memory, fused with the finish step.
+// The payload ([loglik, bad, per-edge accumulators]: ~27 KB of exact 64-bit integers for config 4) is far too small
+// for ncclAllReduce to be anything but latency: here every rank WRITES its payload into its slot of every peer's
+// buffer (plain stores through NVLink / NVSwitch into IPC-mapped memory), publishes an epoch flag behind a system
+// fence, waits for the other ranks' flags, sums the slots in rank order (so every rank gets the same bits) and
+// converts to [loglik, bad, grad] -- one single-CTA launch instead of a collective plus two small kernels.
+// Buffers are double buffered by epoch parity; a rank cannot be two epochs ahead of a peer because it needs that
+// peer's contribution to finish the epoch in between.  The wait is bounded (~2 s): out[1] = NaN on time-out.
+// Layout of a rank's buffer (uint64 words): data[2][nranks][words] then flags[2][nranks].
+// ------------------------------------------------------------------------------------------
+struct PeerParams {
+    unsigned long long* peers[8];          // IPC-mapped base of every rank's buffer (own entry = local pointer)
+    int nranks, rank, words, n_edges, n, rearm;
+    unsigned long long epoch;              // 1, 2, ...
+    unsigned long long* red;               // in: this rank's payload; out: the sums
+    const int32_t* __restrict__ edge_tp;
+    double inv_fx, inv_ll;
+    double* out;
+};
+
+__global__ void __launch_bounds__(1024, 1) k_peer_allreduce_finish(const PeerParams P)
+{
+    const int tid = threadIdx.x, ph = (int)(P.epoch & 1ull);
+    const size_t slot = ((size_t)ph * P.nranks + P.rank) * P.words;
+    const size_t flag0 = (size_t)2 * P.nranks * P.words + (size_t)ph * P.nranks;
+    for (int i = tid; i < P.words; i += blockDim.x) {
+        const unsigned long long v = P.red[i];
+        for (int r = 0; r < P.nranks; ++r) P.peers[r][slot + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < P.nranks) *reinterpret_cast<volatile unsigned long long*>(P.peers[tid] + flag0 + P.rank) = P.epoch;
+    __shared__ int s_timeout;
+    if (tid == 0) s_timeout = 0;
+    __syncthreads();
+    if (tid < P.nranks) {
+        const volatile unsigned long long* f = P.peers[P.rank] + flag0 + tid;
+        const long long t0 = clock64();
+        while (*f != P.epoch)
+            if (clock64() - t0 > 4000000000ll) { s_timeout = 1; break; }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const unsigned long long* mine = P.peers[P.rank] + (size_t)ph * P.nranks * P.words;
+    for (int i = tid; i < P.words; i += blockDim.x) {
+        unsigned long long sum = 0;
+        for (int r = 0; r < P.nranks; ++r) sum += *reinterpret_cast<const volatile unsigned long long*>(mine + (size_t)r * P.words + i);
+        if (i >= 2) {
+            P.red[i] = sum;
+            const int e = i - 2;
+            if (e < P.n_edges) { const int tp = P.edge_tp[e]; if (tp >= 0 && tp < P.n) P.out[2 + tp] = -(double)(long long)sum * P.inv_fx; }
+        } else P.red[i] = P.rearm ? 0ull : sum;
+        if (i == 0) {
+            unsigned long long bad = 0;
+            for (int r = 0; r < P.nranks; ++r) bad += *reinterpret_cast<const volatile unsigned long long*>(mine + (size_t)r * P.words + 1);
+            P.out[0] = bad > 0 ? -INFINITY : (double)(long long)sum * P.inv_ll;
+            P.out[1] = s_timeout ? NAN : (double)bad;
+        }
+    }
+}
+
 }  // namespace wfsa

@@ -160,6 +160,9 @@ struct wfsa_dev {
     int hb_fx_log2 = 40;
     // comm
     ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
+    // one-shot all-reduce over NVLink peer memory (k_peer_allreduce_finish); falls back to NCCL when it cannot be set up
+    bool peer_ok = false; unsigned long long peer_epoch = 0; int peer_words = 0;
+    unsigned long long* peer_local = nullptr; unsigned long long* peer_ptrs[8] = {nullptr};
     // timing
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kev;
@@ -197,6 +200,8 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int r = 0; r < 8; ++r) if (h->peer_ptrs[r] && r != h->rank) cudaIpcCloseMemHandle(h->peer_ptrs[r]);
+    if (h->peer_local) cudaFree(h->peer_local);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     DevBuf<int32_t>* i32[] = {&h->d_tokens, &h->d_order, &h->d_slot_emis, &h->d_slot_final, &h->d_arc_tid, &h->d_arc_eid,
                               &h->d_emis_row, &h->d_emis_tok_off, &h->d_emis_tok, &h->d_trans_row, &h->d_trans_dst,
@@ -813,6 +818,8 @@ extern "C" int wfsa_dev_structure(wfsa_dev* h, uint8_t* recognised, double* path
     return WFSA_OK;
 }
 
+static int setup_peer_allreduce(wfsa_dev* h);
+
 extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32_t n, const uint8_t* recognised)
 {
     if (!h || n < 0 || (!trimmed && h->fsa.n_raw > 0)) return set_err(h, WFSA_ERR_INVALID, "set_param_map: bad arguments");
@@ -958,6 +965,7 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
     }
     h->n = n;
     CK(cudaStreamSynchronize(h->stream));
+    if (h->comm) { const int rc = setup_peer_allreduce(h); if (rc != WFSA_OK) return rc; }
     return WFSA_OK;
 }
 
@@ -981,6 +989,62 @@ extern "C" int wfsa_dev_upload_x(wfsa_dev* h, const double* x)
     return WFSA_OK;
 }
 
+// Allocates this rank's peer buffer, exchanges the IPC handles through one NCCL all-reduce (every rank fills its own
+// slot of a zeroed table) and maps the peers.  Collective: called by every rank at the same point (set_param_map).
+// Any failure leaves peer_ok = false on ALL ranks (the outcome is all-reduced), and NCCL stays in charge.
+static int setup_peer_allreduce(wfsa_dev* h)
+{
+    h->peer_ok = false;
+    if (!h->comm || h->nranks > 8 || getenv("WFSA_NO_PEER")) return WFSA_OK;
+    const int words = (int)h->d_red.n;
+    if (h->peer_local && h->peer_words == words) { h->peer_ok = true; return WFSA_OK; }
+    if (h->peer_local) return WFSA_OK;                       // sized for another parameter map: keep NCCL (rare)
+    const size_t total = (size_t)2 * h->nranks * words + (size_t)2 * h->nranks;
+    unsigned long long ok = 1;
+    cudaIpcMemHandle_t mine;
+    std::memset(&mine, 0, sizeof(mine));
+    if (cudaMalloc(&h->peer_local, total * 8) != cudaSuccess) { h->peer_local = nullptr; ok = 0; }
+    if (ok && cudaMemset(h->peer_local, 0, total * 8) != cudaSuccess) ok = 0;
+    if (ok && cudaIpcGetMemHandle(&mine, h->peer_local) != cudaSuccess) ok = 0;
+    cudaGetLastError();
+    // table: per rank 8 words of handle + 1 word "ok"
+    const int per = (int)(sizeof(cudaIpcMemHandle_t) / 8) + 1;
+    std::vector<unsigned long long> tab((size_t)h->nranks * per, 0ull);
+    std::memcpy(&tab[(size_t)h->rank * per], &mine, sizeof(mine));
+    tab[(size_t)h->rank * per + per - 1] = ok;
+    DevBuf<unsigned long long> d_tab;
+    CK(d_tab.upload(tab, h->stream));
+    int rc = nccl_allreduce(h, d_tab.p, tab.size(), ncclUint64, ncclSum);
+    if (rc != WFSA_OK) { d_tab.release(); return rc; }
+    CK(cudaMemcpyAsync(tab.data(), d_tab.p, tab.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    d_tab.release();
+    unsigned long long all_ok = 1;
+    for (int r = 0; r < h->nranks; ++r) all_ok &= tab[(size_t)r * per + per - 1];
+    unsigned long long mapped = all_ok;
+    if (all_ok)
+        for (int r = 0; r < h->nranks; ++r) {
+            if (r == h->rank) { h->peer_ptrs[r] = h->peer_local; continue; }
+            cudaIpcMemHandle_t hd;
+            std::memcpy(&hd, &tab[(size_t)r * per], sizeof(hd));
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { mapped = 0; cudaGetLastError(); break; }
+            h->peer_ptrs[r] = (unsigned long long*)ptr;
+        }
+    // every rank must take the same route
+    unsigned long long* d_flag = reinterpret_cast<unsigned long long*>(h->d_red.p);
+    unsigned long long bad = mapped ? 0 : 1;
+    CK(cudaMemcpyAsync(d_flag, &bad, 8, cudaMemcpyHostToDevice, h->stream));
+    rc = nccl_allreduce(h, d_flag, 1, ncclUint64, ncclSum);
+    if (rc != WFSA_OK) return rc;
+    CK(cudaMemcpyAsync(&bad, d_flag, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->peer_words = words;
+    h->peer_epoch = 0;
+    h->peer_ok = bad == 0;
+    return WFSA_OK;
+}
+
 extern "C" int wfsa_dev_eval_launch(wfsa_dev* h)
 {
     if (!h) return WFSA_ERR_INVALID;
@@ -990,6 +1054,18 @@ extern "C" int wfsa_dev_eval_launch(wfsa_dev* h)
                              h->kernel >= 4 ? h->secondary : 0, h->d_order_w.p, h->n_active_w, true, true);
     if (rc != WFSA_OK) return rc;
     if (h->lean_finished) return WFSA_OK;          // k_fold_finish6 already wrote [loglik, bad, grad]
+    if (h->comm && h->peer_ok) {
+        PeerParams P{};
+        for (int r = 0; r < h->nranks; ++r) P.peers[r] = h->peer_ptrs[r];
+        P.nranks = h->nranks; P.rank = h->rank; P.words = h->peer_words; P.n_edges = h->n_edges; P.n = h->n; P.rearm = 0;
+        P.epoch = ++h->peer_epoch; P.red = h->d_red.p; P.edge_tp = h->d_edge_tp.p;
+        P.inv_fx = std::ldexp(1.0, -(int)h->fx_log2); P.inv_ll = std::ldexp(1.0, -(int)h->ll_log2); P.out = h->d_out.p;
+        if (!h->lean_now) CK(cudaMemsetAsync(h->d_out.p, 0, h->d_out.n * 8, h->stream));
+        k_peer_allreduce_finish<<<1, 1024, 0, h->stream>>>(P);
+        h->launches++;
+        CK(cudaGetLastError());
+        return WFSA_OK;
+    }
     rc = nccl_allreduce(h, h->d_red.p, h->d_red.n, ncclUint64, ncclSum);
     if (rc != WFSA_OK) return rc;
     if (!h->lean_now) CK(cudaMemsetAsync(h->d_out.p, 0, h->d_out.n * 8, h->stream));   // k_prep6 already cleared it
