@@ -312,6 +312,12 @@ struct KSParams {
     unsigned long long* red;              // red[0] fixed-point loglik, red[1] non-finite strings
     double ll_scale;
     int n_arcs;
+    // single-GPU finish of [loglik, bad] by the last CTA (the gradient part is folded by k_fold_finish6, which runs
+    // next to this kernel on a second stream: it only depends on the region kernel)
+    int finish_ll;
+    double inv_ll;
+    double* out;
+    unsigned int* done;                   // CTAs that have finished; the last one resets it
 };
 
 // KS: one CTA of 16 warps per super-group of 16 groups, one warp per group, one thread per string.
@@ -388,6 +394,19 @@ __global__ void __launch_bounds__(kKsWarps * 32, 2) ks_strings(const KSParams P)
         if (ll_fx) atomicAdd(P.red, (unsigned long long)ll_fx);
         if (bad) atomicAdd(P.red + 1, bad);
     }
+    if (P.finish_ll) {                                         // the last CTA to finish writes [loglik, bad]
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(P.done, 1u) == gridDim.x - 1) {
+                __threadfence();
+                const unsigned long long r0 = atomicAdd(P.red, 0ull), r1 = atomicAdd(P.red + 1, 0ull);
+                P.out[0] = r1 > 0 ? -INFINITY : (double)(long long)r0 * P.inv_ll;
+                P.out[1] = (double)r1;
+                *P.done = 0u;
+            }
+        }
+    }
 }
 
 // log q of the strings of the segmented path, group order -> string id order
@@ -441,7 +460,7 @@ __global__ void k_prep6(const Prep6Params P)
 // One launch behind it: per-arc accumulators (all replicas) -> per-edge sums (a gather over the arcs of the
 // edge, fixed order, integer adds) -> and, without a communicator, straight to [loglik, bad, grad].
 struct Fin6Params {
-    int n_edges, n_arcs, replicas, n, finish;
+    int n_edges, n_arcs, replicas, n, finish;      // finish: bit 0 = write grad, bit 1 = write [loglik, bad] as well
     const int32_t* __restrict__ e_off;      // [n_edges+1] arcs of every edge (transition edges, then emission edges)
     const int32_t* __restrict__ e_arc;
     const unsigned long long* __restrict__ acc;
@@ -455,7 +474,7 @@ __global__ void k_fold_finish6(const Fin6Params P)
     // one warp per edge: its lanes share the (arc, replica) cells of the edge, then a shuffle sum (integers)
     const int lane = threadIdx.x & 31;
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (e == 0 && lane == 0 && P.finish) {
+    if (e == 0 && lane == 0 && (P.finish & 2)) {
         const double bad = (double)P.red[1];
         P.out[0] = bad > 0 ? -INFINITY : (double)(long long)P.red[0] * P.inv_ll;
         P.out[1] = bad;
@@ -472,7 +491,7 @@ __global__ void k_fold_finish6(const Fin6Params P)
     if (lane == 0) {
         s += P.red[2 + e];
         P.red[2 + e] = s;
-        if (P.finish) {
+        if (P.finish & 1) {
             const int tp = P.edge_tp[e];
             if (tp >= 0 && tp < P.n) P.out[2 + tp] = -(double)(long long)s * P.inv_fx;
         }

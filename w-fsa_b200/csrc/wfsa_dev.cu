@@ -149,7 +149,7 @@ struct wfsa_dev {
     long long kt_groups = 0;
     std::vector<uint8_t> h_overflow;
     int64_t launches = 0;
-    bool structure_done = false, lean_finished = false, lean_now = false;
+    bool structure_done = false, lean_finished = false, lean_now = false, side_folded = false;
     std::vector<uint8_t> h_recognised;
     // Hessian
     DevBuf<int64_t> d_hb_path_off, d_hb_col_off, d_hb_val_off;
@@ -169,6 +169,8 @@ struct wfsa_dev {
     size_t kev_used = 0; bool timing = false;
     std::vector<cudaEvent_t> kev_mid;           // segmented path: between kr_regions and ks_strings
     cudaEvent_t mid_now = nullptr;
+    cudaStream_t stream2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;    // the fold runs next to ks_strings
+    DevBuf<unsigned int> d_done;
 };
 
 #define CK(call)                                                                              \
@@ -230,6 +232,10 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     if (h->ev_end) cudaEventDestroy(h->ev_end);
     for (auto& e : h->kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto& e : h->kev_mid) cudaEventDestroy(e);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    h->d_done.release();
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -341,6 +347,8 @@ static int setup_kl(wfsa_dev* h)
     CK(h->d_kl_arc_tid.upload(A.arc_tid, h->stream)); CK(h->d_kl_arc_eid.upload(A.arc_eid, h->stream));
     CK(h->d_klaw.alloc(A.n_arcs)); CK(h->d_klacc.alloc((size_t)A.n_arcs * h->replicas)); CK(h->d_klconst.alloc(A.n_arcs));
     CK(h->d_klcounter.alloc(2));
+    CK(h->d_done.alloc(1));
+    CK(cudaMemsetAsync(h->d_done.p, 0, 4, h->stream));      // every finishing ks_strings launch counts it up to the grid size and resets it
     if (h->kernel == 6) {
         CK(h->d_klogaw.alloc(A.n_arcs));
         {   // arcs of every edge (transition edges, then emission edges) for the gather in k_fold_finish6
@@ -583,14 +591,33 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
             h->launches++;
         }
         if (h->mid_now) cudaEventRecord(h->mid_now, st);
+        const bool side_fold = h->lean_now && !getenv("WFSA_SERIAL_FOLD");
+        if (side_fold) {
+            // the per-edge fold of the accumulators only depends on kr_regions: it runs on a second stream next to ks_strings
+            if (!h->stream2) {
+                cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+                cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+            }
+            cudaEventRecord(h->ev_fork, st);
+            cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+            Fin6Params Fp{};
+            Fp.n_edges = h->n_edges; Fp.n_arcs = h->larcs.n_arcs; Fp.replicas = h->replicas; Fp.n = h->n; Fp.finish = h->comm ? 0 : 1;
+            Fp.e_off = h->d_eoff.p; Fp.e_arc = h->d_earc.p; Fp.acc = h->d_klacc.p; Fp.red = h->d_red.p; Fp.edge_tp = h->d_edge_tp.p;
+            Fp.inv_fx = std::ldexp(1.0, -(int)h->fx_log2); Fp.inv_ll = std::ldexp(1.0, -(int)h->ll_log2); Fp.out = h->d_out.p;
+            k_fold_finish6<<<(std::max(h->n_edges, 1) + 7) / 8, 256, 0, h->stream2>>>(Fp);      // one warp per edge
+            h->launches++;
+            cudaEventRecord(h->ev_join, h->stream2);
+        }
         KSParams S{};
         S.logaw = h->d_klogaw.p; S.words = h->d_kswords.p; S.sgoff = h->d_ksgoff.p; S.gref = h->d_ksgref.p; S.lq = h->d_krlq.p;
         S.p = h->d_ksp.p; S.logq = h->d_kslogq.p; S.n_sgroups = h->ks_groups; S.counter = h->d_klcounter.p + 1; S.red = O.red;
         S.ll_scale = O.ll_scale; S.n_arcs = h->larcs.n_arcs;
+        S.finish_ll = (side_fold && !h->comm) ? 1 : 0; S.inv_ll = std::ldexp(1.0, -(int)h->ll_log2); S.out = h->d_out.p; S.done = h->d_done.p;
         if (h->ks_groups > 0) {
             ks_strings<<<h->ks_grid, h->ks_block, h->ks_smem, st>>>(S);
             h->launches++;
         }
+        if (side_fold) { cudaStreamWaitEvent(st, h->ev_join, 0); h->side_folded = true; }
     } else if (kernel == 5) {
         KLParams P{};
         P.aw = h->d_klaw.p; P.words = h->d_klwords.p; P.goff = h->d_klgoff.p; P.gsid = h->d_klgsid.p; P.p = h->d_p.p;
@@ -737,9 +764,14 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
     if (e1) cudaEventRecord(e1, st);
     h->mid_now = nullptr;
     CK(cudaGetLastError());
+    if (lean6 && h->side_folded) {               // folded next to ks_strings, [loglik, bad] written by its last CTA
+        h->side_folded = false;
+        h->lean_finished = !h->comm;
+        return WFSA_OK;
+    }
     if (lean6) {
         Fin6Params P{};
-        P.n_edges = h->n_edges; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas; P.n = h->n; P.finish = h->comm ? 0 : 1;
+        P.n_edges = h->n_edges; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas; P.n = h->n; P.finish = h->comm ? 0 : 3;
         P.e_off = h->d_eoff.p; P.e_arc = h->d_earc.p; P.acc = h->d_klacc.p; P.red = h->d_red.p; P.edge_tp = h->d_edge_tp.p;
         P.inv_fx = std::ldexp(1.0, -(int)h->fx_log2); P.inv_ll = std::ldexp(1.0, -(int)h->ll_log2); P.out = h->d_out.p;
         k_fold_finish6<<<(std::max(h->n_edges, 1) + 7) / 8, 256, 0, st>>>(P);      // one warp per edge
