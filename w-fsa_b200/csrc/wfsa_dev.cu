@@ -617,7 +617,7 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
             ks_strings<<<h->ks_grid, h->ks_block, h->ks_smem, st>>>(S);
             h->launches++;
         }
-        if (side_fold) { cudaStreamWaitEvent(st, h->ev_join, 0); h->side_folded = true; }
+        if (side_fold) h->side_folded = true;                   // joined by launch_pipeline, behind the kernel timing event
     } else if (kernel == 5) {
         KLParams P{};
         P.aw = h->d_klaw.p; P.words = h->d_klwords.p; P.goff = h->d_klgoff.p; P.gsid = h->d_klgsid.p; P.p = h->d_p.p;
@@ -762,6 +762,7 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
     launch_main(h, kernel, mode, CorpusD{h->d_tokens.p, h->d_offs.p, h->d_p.p, d_order, n_order}, O);
     if (kernel2) launch_main(h, kernel2, mode, CorpusD{h->d_tokens.p, h->d_offs.p, h->d_p.p, d_order2, n_order2}, O);
     if (e1) cudaEventRecord(e1, st);
+    if (h->side_folded) cudaStreamWaitEvent(st, h->ev_join, 0);
     h->mid_now = nullptr;
     CK(cudaGetLastError());
     if (lean6 && h->side_folded) {               // folded next to ks_strings, [loglik, bad] written by its last CTA
