@@ -328,7 +328,9 @@ def run_ours(args, rank, world, local):
                        **({"segments": {"region_types": info["seg_types"], "region_instances": info["seg_region_instances"],
                                         "region_edges": info["seg_region_edges"], "type_edges": info["seg_type_edges"],
                                         "compile_host_ms": info["seg_host_ms"]}} if info["kernel"] == 6 else {}),
-                       "l2_policy": "inputs larger than L2 (%.0f MB of tokens per evaluation vs 126 MB L2)" % (4e-6 * my_tokens),
+                       "l2_policy": ("inputs larger than L2 (%.0f MB of compiled streams read per evaluation vs 126 MB L2)" % (4e-6 * info["lattice_words"])
+                                     if info["kernel"] >= 5 else
+                                     "inputs larger than L2 (%.0f MB of tokens per evaluation vs 126 MB L2)" % (4e-6 * my_tokens)),
                        "collective": "ncclAllReduce(int64 sum) of [loglik, grad] per step" if world > 1 else "none",
                        "seeds": {"automaton": cfg["seed"], "strings": 1235}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
