@@ -30,6 +30,10 @@ struct KRParams {
     unsigned long long* acc;              // [replicas][n_arcs]
     double fx_scale;
     int n_arcs, replicas;
+    // pull form of the path-form gradient (lattice.hpp): the value of path p of the type at (g, lane) is stored at
+    // pv[pvoff[g] + p*32 + lane] and gathered per arc by k_pull_paths; pv == nullptr: one RED per (type, path, edge)
+    long long* pv;
+    const int64_t* __restrict__ pvoff;
     long long n_first;                    // scheduler: tickets [0, n_first) map to the groups in order (the big DAG regions),
     long long stride;                     // the others to n_first + ((ticket - n_first) * stride) % (n_groups - n_first)
 };
@@ -142,6 +146,12 @@ __device__ __forceinline__ void kr_paths(const KRParams& P, const double* aw, in
     long long v[PP];
 #pragma unroll
     for (int p = 0; p < PP; ++p) v[p] = __double2ll_rn(r[p] * sc);
+    if (ACC == ACC_GLOBAL && P.pv) {                           // pull form: PP coalesced stores instead of PP*L REDs
+        long long* dst = P.pv + P.pvoff[g] + lane;
+#pragma unroll
+        for (int p = 0; p < PP; ++p) dst[p * 32] = v[p];
+        return;
+    }
     for (int l = 0; l < L; ++l) {
         uint32_t a[PP];
 #pragma unroll
@@ -296,6 +306,26 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
         }
         g = __shfl_sync(FULL, gn, 0);
     }
+}
+
+// Pull form of the path-form gradient: chunk c adds the values pv[pidx[i]], i in [pcoff[c], pcoff[c+1]), of the
+// paths that contain arc pcarc[c] into that arc's accumulator -- one warp per chunk (at most kPullChunk entries:
+// coalesced index reads, gathers from the L2-resident pv, integer shuffle sum, ONE RED).  It replaces one RED per
+// (type, path, edge) -- 7 M per evaluation for config 4, issued at the LSU lane rate inside the latency-bound region
+// kernel -- and runs on the side stream next to ks_strings.
+__global__ void __launch_bounds__(256) k_pull_paths(long long n_chunks, const int64_t* __restrict__ pcoff, const int32_t* __restrict__ pcarc,
+                                                    const int32_t* __restrict__ pidx, const long long* __restrict__ pv,
+                                                    unsigned long long* acc)
+{
+    const int lane = threadIdx.x & 31;
+    const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= n_chunks) return;
+    const long long b = pcoff[c], e = pcoff[c + 1];
+    long long s = 0;
+    for (long long i = b + lane; i < e; i += 32) s += pv[pidx[i]];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if (lane == 0 && s) atomicAdd(acc + pcarc[c], (unsigned long long)s);
 }
 
 // ------------------------------------------------------------------------------------------

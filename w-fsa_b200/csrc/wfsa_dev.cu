@@ -171,6 +171,7 @@ struct wfsa_dev {
     cudaEvent_t mid_now = nullptr;
     cudaStream_t stream2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;    // the fold runs next to ks_strings
     DevBuf<unsigned int> d_done;
+    DevBuf<long long> d_pv; DevBuf<int64_t> d_pvoff, d_pcoff; DevBuf<int32_t> d_pidx, d_pcarc; int64_t n_pchunks = 0; bool pull = true;
 };
 
 #define CK(call)                                                                              \
@@ -235,7 +236,7 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
-    h->d_done.release();
+    h->d_done.release(); h->d_pv.release(); h->d_pvoff.release(); h->d_pcoff.release(); h->d_pidx.release(); h->d_pcarc.release();
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -583,6 +584,7 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
             P.lq = h->d_krlq.p; P.n_groups = h->kr_groups; P.xs = h->d_klxs.p; P.xs_rows = (size_t)std::max<int64_t>(h->kl_max_words, 1);
             P.counter = h->d_klcounter.p; P.acc = h->d_klacc.p; P.fx_scale = O.fx_scale; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas;
             P.n_first = h->kr_big_groups; P.stride = h->kr_stride;
+            P.pv = (h->lean_now && h->pull && !getenv("WFSA_SERIAL_FOLD") && h->n_pchunks > 0) ? h->d_pv.p : nullptr; P.pvoff = h->d_pvoff.p;
             if (h->opt.reserved & 2) kr_regions<ACC_NONE, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // timing experiment
             else if (h->opt.reserved & 1) kr_regions<ACC_SMEM_CAS, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // plain REDs
             else if (h->kl_block <= 512) kr_regions<ACC_GLOBAL, 512><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
@@ -600,6 +602,11 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
             }
             cudaEventRecord(h->ev_fork, st);
             cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+            if (h->pull && h->n_pchunks > 0) {                  // the path-form gradient: per-arc gather of the stored path values
+                k_pull_paths<<<(unsigned)((h->n_pchunks + 7) / 8), 256, 0, h->stream2>>>(h->n_pchunks, h->d_pcoff.p, h->d_pcarc.p, h->d_pidx.p,
+                                                                                       h->d_pv.p, h->d_klacc.p);
+                h->launches++;
+            }
             Fin6Params Fp{};
             Fp.n_edges = h->n_edges; Fp.n_arcs = h->larcs.n_arcs; Fp.replicas = h->replicas; Fp.n = h->n; Fp.finish = h->comm ? 0 : 1;
             Fp.e_off = h->d_eoff.p; Fp.e_arc = h->d_earc.p; Fp.acc = h->d_klacc.p; Fp.red = h->d_red.p; Fp.edge_tp = h->d_edge_tp.p;
@@ -941,6 +948,10 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
         h->kl_max_words = sc.max_big_rows;
         CK(h->d_krwords.upload(sc.rwords, h->stream)); CK(h->d_krgoff.upload(sc.rgoff, h->stream));
         CK(h->d_krgrows.upload(sc.rgrows, h->stream)); CK(h->d_krW.upload(sc.typeW, h->stream));
+        h->pull = !getenv("WFSA_NO_PULL");
+        h->n_pchunks = (int64_t)sc.pcarc.size();
+        CK(h->d_pv.alloc(std::max<size_t>((size_t)sc.n_pv, 1))); CK(h->d_pvoff.upload(sc.pvoff, h->stream));
+        CK(h->d_pcoff.upload(sc.pcoff, h->stream)); CK(h->d_pidx.upload(sc.pidx, h->stream)); CK(h->d_pcarc.upload(sc.pcarc, h->stream));
         CK(h->d_krlq.alloc((size_t)h->kr_groups * 32 + 1));
         CK(cudaMemsetAsync(h->d_krlq.p, 0, h->d_krlq.n * 8, h->stream));
         CK(h->d_kswords.upload(sc.swords, h->stream)); CK(h->d_ksgoff.upload(sc.sgoff, h->stream));
@@ -1423,7 +1434,7 @@ extern "C" int wfsa_segmented_get(const wfsa_segmented* s, int which, const void
     switch (which) {
         SEG_ARR(0, c.rwords) SEG_ARR(1, c.rgoff) SEG_ARR(2, c.rgrows) SEG_ARR(3, c.typeW) SEG_ARR(4, c.swords) SEG_ARR(5, c.sgoff)
         SEG_ARR(6, c.sgref) SEG_ARR(7, c.ksid) SEG_ARR(8, c.kp) SEG_ARR(9, c.overflow) SEG_ARR(10, c.rejected) SEG_ARR(11, c.const_acc)
-        SEG_ARR(12, s->stats)
+        SEG_ARR(12, s->stats) SEG_ARR(13, c.pvoff) SEG_ARR(14, c.pidx) SEG_ARR(15, c.pcoff) SEG_ARR(16, c.pcarc)
         default: return WFSA_ERR_INVALID;
     }
 #undef SEG_ARR
