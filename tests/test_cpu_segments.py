@@ -123,7 +123,7 @@ def interpret(seg, aw, n_arcs):
     pidx, pcoff, pcarc = seg["pidx"], seg["pcoff"], seg["pcarc"]
     assert len(pcoff) == len(pcarc) + 1 and (len(pidx) == pcoff[-1] if len(pcarc) else len(pidx) == 0)
     for c in range(len(pcarc)):
-        assert 0 < pcoff[c + 1] - pcoff[c] <= 256 and 0 <= pcarc[c] < n_arcs
+        assert 0 < pcoff[c + 1] - pcoff[c] <= 128 and 0 <= pcarc[c] < n_arcs
         acc[pcarc[c]] += pv[pidx[pcoff[c]:pcoff[c + 1]]].sum()
     sgoff, sgref, ksid, kp = seg["sgoff"], seg["sgref"], seg["ksid"], seg["kp"]
     logq = {}

@@ -320,9 +320,13 @@ __global__ void __launch_bounds__(256) k_pull_paths(long long n_chunks, const in
     const int lane = threadIdx.x & 31;
     const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c >= n_chunks) return;
-    const long long b = pcoff[c], e = pcoff[c + 1];
+    const long long b = pcoff[c], e = pcoff[c + 1];              // at most kPullChunkD = 128 entries: four per lane,
+    int id[4];                                                   // all index loads, then all gathers, in flight together
+#pragma unroll
+    for (int k = 0; k < 4; ++k) id[k] = b + lane + 32 * k < e ? pidx[b + lane + 32 * k] : -1;
     long long s = 0;
-    for (long long i = b + lane; i < e; i += 32) s += pv[pidx[i]];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (id[k] >= 0) s += pv[id[k]];
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
     if (lane == 0 && s) atomicAdd(acc + pcarc[c], (unsigned long long)s);

@@ -105,7 +105,7 @@ void compile_corpus(const HostFsa& f, const LatticeArcs& A, const uint8_t* arc_a
 constexpr int kSegSmallMax = 16;          // edges of a "small" region (unrolled in registers on the device)
 constexpr int kSegMaxPaths = 8;           // path form: a region with at most this many paths ...
 constexpr int kSegMaxPathLen = 16;        // ... all of one length, at most this many edges
-constexpr int kPullChunk = 256;           // list entries one warp of k_pull_paths sums
+constexpr int kPullChunk = 128;           // list entries one warp of k_pull_paths sums (four per lane)
 constexpr int kKsSuper = 16;              // groups (warps) per super-group of the KS layout
 constexpr int kKsChunkRows = 8;           // rows per interleaving chunk of the KS layout
 constexpr int kSegSmallStep = 4;          // small regions are padded to 4, 8, 12 or 16 word rows

@@ -171,7 +171,7 @@ struct wfsa_dev {
     cudaEvent_t mid_now = nullptr;
     cudaStream_t stream2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;    // the fold runs next to ks_strings
     DevBuf<unsigned int> d_done;
-    DevBuf<long long> d_pv; DevBuf<int64_t> d_pvoff, d_pcoff; DevBuf<int32_t> d_pidx, d_pcarc; int64_t n_pchunks = 0; bool pull = true;
+    DevBuf<long long> d_pv; DevBuf<int64_t> d_pvoff, d_pcoff; DevBuf<int32_t> d_pidx, d_pcarc; int64_t n_pchunks = 0; bool pull = false;
 };
 
 #define CK(call)                                                                              \
@@ -948,7 +948,7 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
         h->kl_max_words = sc.max_big_rows;
         CK(h->d_krwords.upload(sc.rwords, h->stream)); CK(h->d_krgoff.upload(sc.rgoff, h->stream));
         CK(h->d_krgrows.upload(sc.rgrows, h->stream)); CK(h->d_krW.upload(sc.typeW, h->stream));
-        h->pull = !getenv("WFSA_NO_PULL");
+        h->pull = getenv("WFSA_PULL") != nullptr;        // off by default: measured slower
         h->n_pchunks = (int64_t)sc.pcarc.size();
         CK(h->d_pv.alloc(std::max<size_t>((size_t)sc.n_pv, 1))); CK(h->d_pvoff.upload(sc.pvoff, h->stream));
         CK(h->d_pcoff.upload(sc.pcoff, h->stream)); CK(h->d_pidx.upload(sc.pidx, h->stream)); CK(h->d_pcarc.upload(sc.pcarc, h->stream));
