@@ -301,6 +301,13 @@ def run_ours(args, rank, world, local):
         e2e = tok_total * steps / e2e_max
         peak, peak_src = peaks()
         alg_bytes = 4.0 * my_tokens + 20.0 * len(w) + 8.0 * n + float(info["table_bytes"])
+        a_lat = None
+        if info["kernel"] == 2:
+            # CTA-per-string kernel: the alpha lattice of a string does not fit on chip; SURVEY 8(d) charges 16 B per
+            # live alpha entry (8 B written by the forward sweep, 8 B read back).  The kernel keeps one entry per
+            # candidate state of the position's symbol (exactly max_candidates for the synthetic config 5).
+            a_lat = float(info["max_candidates"]) * my_tokens
+            alg_bytes += 16.0 * a_lat
         k_ms = kms_max / max(klaunches, 1)
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         traffic = None
@@ -335,7 +342,7 @@ def run_ours(args, rank, world, local):
                        "seeds": {"automaton": cfg["seed"], "strings": 1235}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": {1: "k2_fwdbwd", 2: "k3_fwdbwd", 3: "kg_fwdbwd", 4: "kt_fwdbwd", 5: "kl_fwdbwd", 6: "kr_regions+ks_strings"}[info["kernel"]],
-                         "kernel_ms": k_ms,
+                         "kernel_ms": k_ms, **({"alpha_lattice_entries": a_lat} if a_lat else {}),
                          **({"kernels_ms": {"kr_regions": split[0] / max(klaunches, 1), "ks_strings": split[1] / max(klaunches, 1)}}
                             if info["kernel"] == 6 else {}),
                          "algorithmic_bytes_per_launch": alg_bytes,
