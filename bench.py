@@ -312,8 +312,8 @@ def run_ours(args, rank, world, local):
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            try:
+        if os.path.exists(tp) and info["kernel"] == 6 and args.config == "c4" and args.strings == 1000000:
+            try:                      # ncu capture of exactly this workload (kr_regions + ks_strings, one launch each)
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
