@@ -111,3 +111,23 @@ def test_descriptor_validation():
     with pytest.raises(W.WfsaError) as ei:
         W.Device(low)
     assert ei.value.code == 1                                          # WFSA_ERR_INVALID before any CUDA call
+
+
+@pytest.mark.parametrize("fsa,corpus", [("test3.wfsa", "test.corpus"), ("talk.wfsa", "talk.corpus"), ("test5.wfsa", "test5.corpus"),
+                                        ("test.list.wfsa", "test.corpus"), ("test.loop.wfsa", "test.corpus")])
+@pytest.mark.parametrize("order", ["0", "1"])
+def test_path_listing_matches_reference_binary(fsa, corpus, order):
+    """-pr lists every accepting path of every corpus string (src/main.cpp:178-203).  The listing happens before the
+    device is touched, so it can be compared here, without a GPU, against the unmodified reference build
+    (oracle/_ref/wfsa_ref) -- as a set of lines: the reference's order follows its hash-map iteration."""
+    import os
+    import subprocess
+    ref = os.path.join(ROOT, "oracle", "_ref", "wfsa_ref")
+    data = "/root/reference/data"
+    ours = os.path.join(ROOT, "w-fsa_b200", "_build", "wfsa")
+    if not (os.path.exists(ref) and os.path.isdir(data)):
+        pytest.skip("needs the reference build and its data (build container only)")
+    args = ["-a", os.path.join(data, fsa), "-c", os.path.join(data, corpus), "-pr", "-r", order, "-e", "0", "-s"]
+    want = sorted(ln for ln in subprocess.run([ref] + args, capture_output=True, text=True).stderr.splitlines() if " -> " in ln)
+    got = sorted(ln for ln in subprocess.run([ours] + args, capture_output=True, text=True).stderr.splitlines() if " -> " in ln)
+    assert want and got == want

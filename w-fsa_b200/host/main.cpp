@@ -3,13 +3,14 @@
 // Same options, same stderr/stdout protocol and exit codes as the reference executable
 // (/root/reference/src/main.cpp:68-106 options, :121-347 flow).  Not carried over: the MKL
 // micro-benchmarks (-testt/-testn), -t (MKL threads) and the -m path-matrix cache -- a DP
-// backend has no P/M matrices to cache.  -r is accepted and ignored (BFS/DFS only differ in
-// enumeration order).  Added: --device N, --full (dump weights with 17 digits).
+// backend has no P/M matrices to cache.  -r only orders the -p/-pr path listing (BFS/DFS).  Added: --device N, --full (dump weights with 17 digits).
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
+#include <deque>
 #include <iostream>
 #include <memory>
 #include <string>
@@ -30,6 +31,43 @@ static void PrintFixedWidth(FILE* out, double x, int width)      // src/Utils.cp
     else fprintf(out, "%*.*e", width, width - 7, x);
 }
 
+// -p / -pr: every accepting path of every corpus string, one per line on stderr, as the reference prints them
+// (/root/reference/src/main.cpp:178-203):   <emitted text>: <start> -> <state>"<emission>" -> ... -> <end>
+// This is the one place where paths are enumerated (inc/Recognize.h:35-96: a step takes a transition and the TARGET
+// state emits a prefix of what is left; the end state is entered only once the word is consumed).  It is a debugging
+// aid on the host and no part of the evaluation path; like the reference's breadth-first search it gives up on a
+// word after one second.
+static void print_paths(const Fsa& fsa, const Corpus& corpus, bool bfs)
+{
+    struct Item { size_t pos; int state; std::string text, trail; };
+    const auto& st = fsa.States();
+    const int end = fsa.EndIndex();
+    for (const auto& word : corpus) {
+        const std::string& w = word.first;
+        const auto t0 = std::chrono::steady_clock::now();
+        std::deque<Item> work;
+        work.push_back(Item{0, fsa.StartIndex(), "", fsa.GetStartState()});
+        while (!work.empty() && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() < 1.0) {
+            Item cur = bfs ? std::move(work.front()) : std::move(work.back());
+            if (bfs) work.pop_front(); else work.pop_back();
+            std::vector<Item> found;                           // depth-first: children are visited in file order
+            for (const auto& tr : st[cur.state].transitions) {
+                if (tr.next == end) {
+                    if (cur.pos == w.size()) fprintf(stderr, "%s: %s -> %s\n", cur.text.c_str(), cur.trail.c_str(), st[end].name.c_str());
+                    continue;
+                }
+                for (const auto& em : st[tr.next].emissions) {
+                    if (w.compare(cur.pos, em.str.size(), em.str) != 0 || cur.pos + em.str.size() > w.size()) continue;
+                    Item nx{cur.pos + em.str.size(), tr.next, cur.text + em.str, cur.trail + " -> " + st[tr.next].name};
+                    if (!em.str.empty()) nx.trail += '"' + em.str + '"';
+                    if (bfs) work.push_back(std::move(nx)); else found.push_back(std::move(nx));
+                }
+            }
+            for (auto it = found.rbegin(); it != found.rend(); ++it) work.push_back(std::move(*it));
+        }
+    }
+}
+
 static void usage()
 {
     std::cout <<
@@ -45,7 +83,7 @@ static void usage()
         "  -n, --normalize            normalize the automaton after optimization\n"
         "  -p, --print                prints extra info to stderr\n"
         "  -s, --suppress             suppresses printing of learned FSA to stdout\n"
-        "  -r, --recognize N          accepted for compatibility (0 BFS, 1 DFS); the DP needs neither\n"
+        "  -r, --recognize N          order of the -p/-pr path listing (0 breadth first, 1 depth first); the evaluation needs neither\n"
         "  -opt, --optimizer NAME     Hessian | QuasiNewton\n"
         "  -x, --initx, --initial     reads initial x vector from stdin\n"
         "  -i, --init FLAGS           1 uniform, 2 normalize, 4 init multipliers, 8 use H_f,\n"
@@ -58,7 +96,8 @@ int main(int argc, const char* argv[])
 {
     std::string automaton_filename, corpus_filename, output_filename, optimizer = "Hessian";
     int epochs = 20, initflags = 0, device = 0;
-    bool normalize = false, print = false, suppress = false, evaluate = false, initx = false, full = false;
+    bool normalize = false, print = false, print_recognize = false, suppress = false, evaluate = false, initx = false, full = false;
+    int recognize = 0;
     double eta = 1.0, tolerance = 1e-6;
     auto is = [](const char* a, std::initializer_list<const char*> names) {
         for (const char* n : names) if (std::strcmp(a, n) == 0) return true;
@@ -82,9 +121,9 @@ int main(int argc, const char* argv[])
         else if (is(a, {"-p", "--print"})) print = true;
         else if (is(a, {"-s", "--suppress"})) suppress = true;
         else if (is(a, {"-t", "--thread", "--threads"})) next();
-        else if (is(a, {"-r", "--recognize"})) { const int r = atoi(next()); if (r != 0 && r != 1) { std::cerr << "-r must be 0 or 1" << std::endl; return 1; } }
+        else if (is(a, {"-r", "--recognize"})) { recognize = atoi(next()); if (recognize != 0 && recognize != 1) { std::cerr << "-r must be 0 or 1" << std::endl; return 1; } }
         else if (is(a, {"-opt", "--optimizer"})) { optimizer = next(); if (optimizer != "Hessian" && optimizer != "QuasiNewton") { std::cerr << "Unknown optimizer \"" << optimizer << "\"!" << std::endl; return 1; } }
-        else if (is(a, {"-pr", "--print-recognize"})) print = true;
+        else if (is(a, {"-pr", "--print-recognize"})) print_recognize = true;
         else if (is(a, {"-x", "--initx", "--initial"})) initx = true;
         else if (is(a, {"-i", "--init"})) initflags = atoi(next());
         else if (is(a, {"--device"})) device = atoi(next());
@@ -110,6 +149,7 @@ int main(int argc, const char* argv[])
         std::cerr << "\n\tstates: " << fsa.GetNumberOfStates() << "\n\ttransitions: " << fsa.GetNumberOfTransitions()
                   << "\n\temissions: " << fsa.GetNumberOfEmissions() << "\n\tparameters: " << fsa.GetNumberOfParameters()
                   << "\n\tconstraints: " << fsa.GetNumberOfConstraints() << "\n\tfree parameters: " << fsa.GetNumberOfFreeParameters() << std::endl;
+        if (print || print_recognize) print_paths(fsa, corpus, recognize == 0);
         std::cerr << "Recognize: "; std::cerr.flush();
         learner->BuildFrom(fsa, corpus, true);
         std::cerr << "\n\tstrings: " << learner->GetNumberOfStrings() << "\n\tpaths: " << learner->GetNumberOfPaths()
