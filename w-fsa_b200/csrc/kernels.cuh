@@ -985,13 +985,10 @@ struct K3WParams {
     double* lattice;           // [warps][max_len][nt]
     int* lat_exp;              // [warps][max_len]
     int max_len, nt;           // nt = candidates per position rounded up to a multiple of 32
-    const double* __restrict__ fwent;   // [n_arcs] tw[fent[i] >> kSlotBitsD]: the weight next to its entry (no dependent look-up)
-    const double* __restrict__ bwent;   // [n_arcs] the same for bent
 };
-constexpr int kK3wMaxC = 10;   // candidates per lane handled with all their table reads in flight together
 
 template <int MODE>
-__global__ void __launch_bounds__(512, 1) k3w_fwdbwd(const K3WParams P)
+__global__ void __launch_bounds__(1024, 1) k3w_fwdbwd(const K3WParams P)
 {
     extern __shared__ unsigned long long smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, nt = P.nt;
@@ -1041,40 +1038,6 @@ __global__ void __launch_bounds__(512, 1) k3w_fwdbwd(const K3WParams P)
             const double* src = va + cur * nt;
             double* dst = va + (cur ^ 1) * nt;
             int e = -1;
-            if (nt <= 32 * kK3wMaxC) {
-                // every lane owns up to kK3wMaxC candidates; the look-ups of ALL of them are issued level by level
-                // (state -> row -> entries) instead of one dependent chain per candidate after the other
-                uint32_t row[kK3wMaxC]; double swv[kK3wMaxC];
-#pragma unroll
-                for (int i = 0; i < kK3wMaxC; ++i) {
-                    const uint32_t j = lane + 32 * i;
-                    row[i] = j < ncand ? T.slot_state[c0 + j] : 0xffffffffu;
-                }
-#pragma unroll
-                for (int i = 0; i < kK3wMaxC; ++i) {
-                    const uint32_t j = lane + 32 * i;
-                    const bool on = row[i] != 0xffffffffu;
-                    swv[i] = on ? P.W.sw[c0 + j] : 0.0;
-                    row[i] = on ? T.frow[(size_t)row[i] * (A + 1) + cprev] : 0u;
-                }
-#pragma unroll
-                for (int i = 0; i < kK3wMaxC; ++i) {
-                    const uint32_t j = lane + 32 * i;
-                    if (j >= (uint32_t)nt) break;
-                    const int cnt = row[i] & ((1u << kRowCntBitsD) - 1);
-                    const uint32_t st = row[i] >> kRowCntBitsD;
-                    double s = 0.0;
-                    uint32_t en[4]; double wv[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) if (k < cnt) { en[k] = T.fent[st + k]; wv[k] = P.fwent[st + k]; }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) if (k < cnt) s = fma(wv[k], src[en[k] & ((1u << kSlotBitsD) - 1)], s);
-                    for (int k = 4; k < cnt; ++k) s = fma(P.fwent[st + k], src[T.fent[st + k] & ((1u << kSlotBitsD) - 1)], s);
-                    const double alpha = s * swv[i];
-                    dst[j] = alpha;
-                    if (alpha != 0.0) e = max(e, biased_exp(alpha));
-                }
-            } else
             for (uint32_t j = lane; j < (uint32_t)nt; j += 32) {
                 double alpha = 0.0;
                 if (j < ncand) {
@@ -1083,7 +1046,10 @@ __global__ void __launch_bounds__(512, 1) k3w_fwdbwd(const K3WParams P)
                     const int cnt = row & ((1u << kRowCntBitsD) - 1);
                     const uint32_t st = row >> kRowCntBitsD;
                     double s = 0.0;
-                    for (int k = 0; k < cnt; ++k) s = fma(P.fwent[st + k], src[T.fent[st + k] & ((1u << kSlotBitsD) - 1)], s);
+                    for (int k = 0; k < cnt; ++k) {
+                        const uint32_t ent = T.fent[st + k];
+                        s = fma(P.W.tw[ent >> kSlotBitsD], src[ent & ((1u << kSlotBitsD) - 1)], s);
+                    }
                     alpha = s * P.W.sw[slot];
                 }
                 dst[j] = alpha;
@@ -1160,48 +1126,6 @@ __global__ void __launch_bounds__(512, 1) k3w_fwdbwd(const K3WParams P)
             const double* src = va + cur * nt;
             double* dst = va + (cur ^ 1) * nt;
             int e = -1;
-            if (nt <= 32 * kK3wMaxC) {
-                uint32_t row[kK3wMaxC]; double swv[kK3wMaxC], alv[kK3wMaxC];
-#pragma unroll
-                for (int i = 0; i < kK3wMaxC; ++i) {
-                    const uint32_t j = lane + 32 * i;
-                    alv[i] = j < nc ? al_t[j] : 0.0;
-                    row[i] = j < nc ? T.slot_state[cc0 + j] : 0xffffffffu;
-                }
-#pragma unroll
-                for (int i = 0; i < kK3wMaxC; ++i) {
-                    const uint32_t j = lane + 32 * i;
-                    const bool on = row[i] != 0xffffffffu && alv[i] != 0.0;
-                    swv[i] = on ? P.W.sw[cc0 + j] : 0.0;
-                    row[i] = on ? T.brow[(size_t)row[i] * A + cnext] : 0u;
-                }
-#pragma unroll
-                for (int i = 0; i < kK3wMaxC; ++i) {
-                    const uint32_t j = lane + 32 * i;
-                    if (j >= (uint32_t)nt) break;
-                    const int cnt = row[i] & ((1u << kRowCntBitsD) - 1);
-                    const uint32_t st = row[i] >> kRowCntBitsD;
-                    const double al = alv[i];
-                    double b = 0.0;
-                    uint32_t en[4]; double wv[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) if (k < cnt) { en[k] = T.bent[st + k]; wv[k] = P.bwent[st + k]; }
-                    for (int k = 0; k < cnt; ++k) {
-                        const double term = (k < 4 ? wv[k & 3] : P.bwent[st + k]) * src[(k < 4 ? en[k & 3] : T.bent[st + k]) & ((1u << kSlotBitsD) - 1)];
-                        b += term;
-                        if (term != 0.0) {
-                            if (MODE == MODE_STRUCT) atomicAdd(P.O.acc_global + st + k, 1ull);
-                            else {
-                                const long long v = __double2ll_rn(al * term * sc);
-                                if (v) atomicAdd(P.O.acc_global + st + k, (unsigned long long)v);
-                            }
-                        }
-                    }
-                    const double bt = b * swv[i];
-                    dst[j] = bt;
-                    if (bt != 0.0) e = max(e, biased_exp(bt));
-                }
-            } else
             for (uint32_t j = lane; j < (uint32_t)nt; j += 32) {
                 double bt = 0.0;
                 const double al = j < nc ? al_t[j] : 0.0;
@@ -1213,7 +1137,7 @@ __global__ void __launch_bounds__(512, 1) k3w_fwdbwd(const K3WParams P)
                     double b = 0.0;
                     for (int k = 0; k < cnt; ++k) {
                         const uint32_t ent = T.bent[st + k];
-                        const double term = P.bwent[st + k] * src[ent & ((1u << kSlotBitsD) - 1)];
+                        const double term = P.W.tw[ent >> kSlotBitsD] * src[ent & ((1u << kSlotBitsD) - 1)];
                         b += term;
                         if (term != 0.0) {
                             if (MODE == MODE_STRUCT) atomicAdd(P.O.acc_global + st + k, 1ull);
@@ -1251,7 +1175,7 @@ __global__ void __launch_bounds__(512, 1) k3w_fwdbwd(const K3WParams P)
             const double* src = va + cur * nt;
             for (int k = lane; k < cnt; k += 32) {
                 const uint32_t ent = T.bent[st + k];
-                const double term = P.bwent[st + k] * src[ent & ((1u << kSlotBitsD) - 1)];
+                const double term = P.W.tw[ent >> kSlotBitsD] * src[ent & ((1u << kSlotBitsD) - 1)];
                 if (term != 0.0) {
                     if (MODE == MODE_STRUCT) atomicAdd(P.O.acc_global + st + k, 1ull);
                     else {
@@ -1267,14 +1191,6 @@ __global__ void __launch_bounds__(512, 1) k3w_fwdbwd(const K3WParams P)
         if (ll_fx) atomicAdd(P.O.red, (unsigned long long)ll_fx);
         if (bad) atomicAdd(P.O.red + 1, bad);
     }
-}
-
-// weights next to the table entries of K3W: went[i] = tw[ent[i] >> kSlotBitsD], once per evaluation
-__global__ void k_ent_weights(int n, const uint32_t* __restrict__ fent, const uint32_t* __restrict__ bent,
-                              const double* __restrict__ tw, double* fwent, double* bwent)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { fwent[i] = tw[fent[i] >> kSlotBitsD]; bwent[i] = tw[bent[i] >> kSlotBitsD]; }
 }
 
 // ------------------------------------------------------------------------------------------

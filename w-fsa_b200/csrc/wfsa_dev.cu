@@ -113,7 +113,6 @@ struct wfsa_dev {
     int grid = 0, block = 0, stack_cap = 0, n_acc_smem = 0;      // warp-per-string (K2) launch
     size_t smem_bytes = 0, glstack_words = 0, table_bytes = 0;
     int k3_grid = 0, k3_block = 0; size_t k3_smem = 0;
-    DevBuf<double> d_fwent, d_bwent;
     bool k3w = false; int k3w_grid = 0, k3w_block = 0, k3w_nt = 0; size_t k3w_smem = 0;   // warp-per-string variant of K3            // CTA-per-string (K3) launch
     int kt_grid = 0, kt_block = 0, kt_K = 0; size_t kt_smem = 0, kt_lat_words = 0;   // thread-per-string (KT)
     int secondary = 0;                                            // kernel that takes KT's / KL's overflow strings
@@ -238,7 +237,7 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
-    h->d_done.release(); h->d_fwent.release(); h->d_bwent.release(); h->d_pv.release(); h->d_pvoff.release(); h->d_pcoff.release(); h->d_pidx.release(); h->d_pcarc.release();
+    h->d_done.release(); h->d_pv.release(); h->d_pvoff.release(); h->d_pcoff.release(); h->d_pidx.release(); h->d_pcarc.release();
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -287,11 +286,11 @@ static int setup_k3(wfsa_dev* h)
     h->k3_block = nt;
     h->k3_grid = h->sm_count * std::max(1, std::min(4, 1024 / nt));
     h->k3_smem = (size_t)(2 * nt + 32) * 8 + 40 * 4;
-    // K3W (default): one warp per string, 2*nt doubles of shared memory per warp, a lattice slab per warp in global memory
-    h->k3w = !getenv("WFSA_K3_CTA");
+    // K3W (WFSA_K3_WARP=1): one warp per string, 2*nt doubles of shared memory per warp, a lattice slab per warp in global memory
+    h->k3w = getenv("WFSA_K3_WARP") != nullptr;     // off by default: measured no faster than the CTA kernel
     if (h->k3w) {
         const size_t per_warp = (size_t)2 * nt * 8;
-        int warps = (int)std::min<size_t>(16, (size_t)(220 * 1024) / per_warp);      // 512 threads: 128 registers for the unrolled look-ups
+        int warps = (int)std::min<size_t>(32, (size_t)(220 * 1024) / per_warp);
         if (warps < 1) h->k3w = false;
         else {
             h->k3w_nt = nt; h->k3w_block = warps * 32; h->k3w_smem = per_warp * warps;
@@ -302,7 +301,6 @@ static int setup_k3(wfsa_dev* h)
             h->k3w_grid = grid;
             CK(h->d_k3lat.alloc((size_t)grid * warps * std::max(h->max_len, 1) * nt));
             CK(h->d_k3exp.alloc((size_t)grid * warps * std::max(h->max_len, 1)));
-            CK(h->d_fwent.alloc(std::max(L.n_arcs, 1))); CK(h->d_bwent.alloc(std::max(L.n_arcs, 1)));
             cudaFuncSetAttribute(k3w_fwdbwd<MODE_EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             cudaFuncSetAttribute(k3w_fwdbwd<MODE_STRUCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             return WFSA_OK;
@@ -706,9 +704,6 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
             K3WParams Q{};
             Q.T = T; Q.W = EvalWeightsD{h->d_tw.p, h->d_sw.p, h->d_fw.p}; Q.C = C; Q.O = O;
             Q.lattice = h->d_k3lat.p; Q.lat_exp = h->d_k3exp.p; Q.max_len = std::max(h->max_len, 1); Q.nt = h->k3w_nt;
-            Q.fwent = h->d_fwent.p; Q.bwent = h->d_bwent.p;
-            k_ent_weights<<<(L.n_arcs + 255) / 256, 256, 0, st>>>(L.n_arcs, h->d_fent.p, h->d_bent.p, h->d_tw.p, h->d_fwent.p, h->d_bwent.p);
-            h->launches++;
             if (mode == MODE_STRUCT) k3w_fwdbwd<MODE_STRUCT><<<h->k3w_grid, h->k3w_block, h->k3w_smem, st>>>(Q);
             else k3w_fwdbwd<MODE_EVAL><<<h->k3w_grid, h->k3w_block, h->k3w_smem, st>>>(Q);
             h->launches++;
