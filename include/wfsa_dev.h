@@ -141,8 +141,15 @@ int wfsa_dev_timer_begin(wfsa_dev* h);
 int wfsa_dev_timer_end(wfsa_dev* h, float* ms);
 /* ms spent in the dominant kernel (forward-backward) over the launches since timer_begin. */
 int wfsa_dev_timer_kernel_ms(wfsa_dev* h, float* ms, int64_t* launches);
-/* segmented kernels (6): the same time split into kr_regions (first) and ks_strings (second); 0 otherwise */
+/* segmented kernel (6): the same time split into kr_regions (first) and whatever follows it inside the timed bracket
+ * (second; overflow strings on the secondary kernel, else ~0); 0 otherwise */
 int wfsa_dev_timer_split_ms(wfsa_dev* h, float* first_ms, float* second_ms);
+/* Sum of the device times of the evaluations launched since timer_begin, each measured by its own event pair around
+ * the WHOLE evaluation (weights, kernels, fold, collective); `steps` = how many.  Work queued between two evaluations
+ * (wfsa_dev_l2_flush) is not included. */
+int wfsa_dev_timer_step_ms(wfsa_dev* h, float* ms, int64_t* steps);
+/* Benchmark helper: evicts the L2 cache (memset of a buffer twice its size on the evaluation stream). */
+int wfsa_dev_l2_flush(wfsa_dev* h);
 
 /* Introspection */
 typedef struct {

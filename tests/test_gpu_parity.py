@@ -242,6 +242,31 @@ def test_kernels_match_cpu_oracle(medium, kernel, accum, variant):
     dev.close()
 
 
+def test_segmented_objective_without_per_string_pass(medium):
+    """Kernel 6 finishes [loglik, grad] from the region types and the folded bridge constants alone; log q of every
+    string is computed only when it is fetched (ks_strings on demand) and must agree with that log-likelihood."""
+    model, low = medium
+    dev, rec, pc, trimmed, n = build_device(low, force_kernel=6)
+    r = rec.astype(bool)
+    p = low.p[:len(rec)]
+    rng = np.random.RandomState(3)
+    for x in (rng.normal(-1.0, 0.5, size=n), rng.normal(-12.0, 3.0, size=n)):
+        dev.upload_x(x)
+        dev.eval_launch()
+        ll0, g0 = dev.eval_fetch()                      # objective and gradient only
+        ll1, logq, g1 = dev.eval_fetch(want_logq=True)  # now the per-string pass runs, on the same evaluation
+        ll2, logq2, g2 = dev.eval_fetch(want_logq=True) # and is not repeated
+        assert ll0 == ll1 == ll2 and np.array_equal(g0, g1) and np.array_equal(g0, g2) and np.array_equal(logq, logq2)
+        assert abs(float(np.dot(p[r], logq[r])) - ll0) <= 1e-12 * abs(ll0)
+        ll3, logq3, g3 = dev.eval(x)                    # the one-call form
+        assert ll3 == ll0 and np.array_equal(g3, g0) and np.array_equal(logq3, logq)
+        ltw, lew = low.edge_logweights(x, trimmed)
+        _, olq, oee = O.dp_eval(low, ltw, lew, count=len(rec))
+        assert np.allclose(logq[r], olq[r], rtol=1e-12, atol=1e-10)
+        assert abs(ll0 - float(np.sum(p[r] * olq[r]))) <= 1e-10 * abs(ll0)
+    dev.close()
+
+
 def test_accumulation_variants_are_bitwise_identical(medium):
     """64-bit fixed-point accumulation: shared-memory (split / CAS) and global REDs, and repeated runs,
     give the same bits; two half-shards add up to the whole."""

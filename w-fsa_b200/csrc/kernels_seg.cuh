@@ -36,7 +36,23 @@ struct KRParams {
     const int64_t* __restrict__ pvoff;
     long long n_first;                    // scheduler: tickets [0, n_first) map to the groups in order (the big DAG regions),
     long long stride;                     // the others to n_first + ((ticket - n_first) * stride) % (n_groups - n_first)
+    // log-likelihood: sum_s p_s log q_s = sum_types W_type * lq_type + sum_arcs (bridge count of the arc) * log w[arc].
+    // The first sum is accumulated here (fixed point, one RED per CTA), the second one arrives as per-CTA partials of
+    // the weight kernel in llpart[n_llpart][2] = (value, non-finite terms) and is added by CTA 0.
+    double ll_scale;
+    unsigned long long* red;              // red[0] fixed-point loglik, red[1] non-finite terms
+    const long long* __restrict__ llpart;
+    int n_llpart;
 };
+
+// W * log q of one region type into the thread's fixed-point sum (W = 0: a padding lane)
+__device__ __forceinline__ void kr_loglik(const KRParams& P, double W, bool ok, double lq, long long& ll)
+{
+    if (W > 0.0) {
+        if (ok) ll += __double2ll_rn(W * lq * P.ll_scale);
+        else atomicAdd(P.red + 1, 1ull);
+    }
+}
 
 // Adds one fixed-point value per lane into acc[key].  Region types are sorted by their arcs, so at the first
 // edge positions a whole warp usually holds ONE arc: then the 32 values are summed with shuffles (integers:
@@ -55,11 +71,11 @@ __device__ __forceinline__ void red_uniform(unsigned long long* acc_g, int key, 
 // One small region per thread, NE <= 16 word rows (bare EDGE words).  The x values of the forward sweep stay in
 // registers; the words are held in registers for NE <= 8 and re-read (L1) by the backward sweep otherwise.
 template <int NE, int ACC>
-__device__ __forceinline__ void kr_small(const KRParams& P, const double* aw, double* pool, int NT, long long g, int lane,
-                                         unsigned long long* acc_g)
+__device__ __forceinline__ void kr_small(const KRParams& P, const double* aw, double* pool, int NT, long long g, long long off, int lane,
+                                         unsigned long long* acc_g, long long& ll)
 {
     constexpr int NB = (NE + 7) / 8;                          // batches of up to 8 words
-    const uint32_t* wp = P.words + P.goff[g] + lane;
+    const uint32_t* wp = P.words + off + lane;
     const double W = P.typeW[g * 32 + lane];
     double xs[NE];
     uint32_t w[8];
@@ -87,7 +103,11 @@ __device__ __forceinline__ void kr_small(const KRParams& P, const double* aw, do
     }
     const double q = pool[last * NT];
     const bool ok = any && q > 0.0 && isfinite(q);
-    if (any) P.lq[g * 32 + lane] = ok ? log(q) : -INFINITY;
+    if (any) {
+        const double lq = ok ? log(q) : -INFINITY;
+        P.lq[g * 32 + lane] = lq;
+        kr_loglik(P, W, ok, lq, ll);
+    }
     const double sc = ok ? W * P.fx_scale / q : 0.0;
     pool[last * NT] = 1.0;
 #pragma unroll
@@ -122,9 +142,10 @@ __device__ __forceinline__ void kr_small(const KRParams& P, const double* aw, do
 // only: PP independent multiply chains, no pool, no flags (the reference's P.x / exp / M algebra,
 // src/Learner.cpp:530-545, for one small segment).
 template <int PP, int ACC>
-__device__ __forceinline__ void kr_paths(const KRParams& P, const double* aw, int L, long long g, int lane, unsigned long long* acc_g)
+__device__ __forceinline__ void kr_paths(const KRParams& P, const double* aw, int L, long long g, long long off, int lane,
+                                         unsigned long long* acc_g, long long& ll)
 {
-    const uint32_t* wp = P.words + P.goff[g] + lane;
+    const uint32_t* wp = P.words + off + lane;
     const double W = P.typeW[g * 32 + lane];
     double r[PP];
 #pragma unroll
@@ -140,7 +161,11 @@ __device__ __forceinline__ void kr_paths(const KRParams& P, const double* aw, in
 #pragma unroll
     for (int p = 0; p < PP; ++p) q += r[p];
     const bool ok = W > 0.0 && q > 0.0 && isfinite(q);
-    if (W > 0.0) P.lq[g * 32 + lane] = ok ? log(q) : -INFINITY;
+    if (W > 0.0) {
+        const double lq = ok ? log(q) : -INFINITY;
+        P.lq[g * 32 + lane] = lq;
+        kr_loglik(P, W, ok, lq, ll);
+    }
     if (ACC == ACC_NONE) return;
     const double sc = ok ? W * P.fx_scale / q : 0.0;
     long long v[PP];
@@ -167,7 +192,7 @@ __device__ __forceinline__ void kr_paths(const KRParams& P, const double* aw, in
 // One big region per thread: the KL stream loop (CHECK words rescale, x values on a per-warp stack).
 template <int ACC>
 __device__ __forceinline__ void kr_big(const KRParams& P, const double* aw, double* pool, int NT, long long g, int lane,
-                                       double* xs, unsigned long long* acc_g)
+                                       double* xs, unsigned long long* acc_g, long long& ll)
 {
     const long long o = P.goff[g];
     const int nw = (int)((P.goff[g + 1] - o) >> 5);
@@ -210,7 +235,11 @@ __device__ __forceinline__ void kr_big(const KRParams& P, const double* aw, doub
         }
     }
     const bool ok = any && qh > 0.0 && isfinite(qh);
-    if (any) P.lq[g * 32 + lane] = ok ? log(qh) + (double)EQ * 0.69314718055994530942 : -INFINITY;
+    if (any) {
+        const double lq = ok ? log(qh) + (double)EQ * 0.69314718055994530942 : -INFINITY;
+        P.lq[g * 32 + lane] = lq;
+        kr_loglik(P, W, ok, lq, ll);
+    }
     const double sc0 = ok ? W * P.fx_scale / qh : 0.0;
     double sc = sc0;
     int F = 0;
@@ -281,30 +310,47 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
     // although a split-off path-form kernel went from 82 us to 54 us with it (L2 atomics serialise per address).
     const long long n_rest = P.n_groups - P.n_first;
     auto group_of = [&](long long t) { return t < P.n_first || t >= P.n_groups ? t : P.n_first + ((t - P.n_first) * P.stride) % n_rest; };
-    long long g = 0;
+    long long g = 0, ll = 0;
     if (lane == 0) g = group_of((long long)atomicAdd(P.counter, 1u));
     g = __shfl_sync(FULL, g, 0);
     while (g < P.n_groups) {
         long long gn = 0;
         if (lane == 0) gn = group_of((long long)atomicAdd(P.counter, 1u));
         const int rows = P.grows[g];
+        const long long off = P.goff[g];
         if (rows & 0x10000) {                                  // path form: paths << 8 | length
             const int L = rows & 0xff;
             switch ((rows >> 8) & 0xff) {
-                case 2: kr_paths<2, ACC>(P, aw, L, g, lane, acc_g); break;
-                case 3: kr_paths<3, ACC>(P, aw, L, g, lane, acc_g); break;
-                case 4: kr_paths<4, ACC>(P, aw, L, g, lane, acc_g); break;
-                case 6: kr_paths<6, ACC>(P, aw, L, g, lane, acc_g); break;
-                default: kr_paths<8, ACC>(P, aw, L, g, lane, acc_g); break;
+                case 2: kr_paths<2, ACC>(P, aw, L, g, off, lane, acc_g, ll); break;
+                case 3: kr_paths<3, ACC>(P, aw, L, g, off, lane, acc_g, ll); break;
+                case 4: kr_paths<4, ACC>(P, aw, L, g, off, lane, acc_g, ll); break;
+                case 6: kr_paths<6, ACC>(P, aw, L, g, off, lane, acc_g, ll); break;
+                default: kr_paths<8, ACC>(P, aw, L, g, off, lane, acc_g, ll); break;
             }
         } else switch (rows) {
-            case 4: kr_small<4, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
-            case 8: kr_small<8, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
-            case 12: kr_small<12, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
-            case 16: kr_small<16, ACC>(P, aw, pool, NT, g, lane, acc_g); break;
-            default: kr_big<ACC>(P, aw, pool, NT, g, lane, xs, acc_g); break;
+            case 4: kr_small<4, ACC>(P, aw, pool, NT, g, off, lane, acc_g, ll); break;
+            case 8: kr_small<8, ACC>(P, aw, pool, NT, g, off, lane, acc_g, ll); break;
+            case 12: kr_small<12, ACC>(P, aw, pool, NT, g, off, lane, acc_g, ll); break;
+            case 16: kr_small<16, ACC>(P, aw, pool, NT, g, off, lane, acc_g, ll); break;
+            default: kr_big<ACC>(P, aw, pool, NT, g, lane, xs, acc_g, ll); break;
         }
         g = __shfl_sync(FULL, gn, 0);
+    }
+    // the CTA's share of the log-likelihood: integer sums (exact, order independent), one RED per CTA
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ll += __shfl_xor_sync(FULL, ll, o);
+    __syncthreads();                                           // the pool is free now
+    long long* part = reinterpret_cast<long long*>(aw + P.n_arcs + 1);
+    if (lane == 0) part[tid >> 5] = ll;
+    __syncthreads();
+    if (tid == 0) {
+        long long s = 0;
+        for (int w = 0; w < (NT >> 5); ++w) s += part[w];
+        unsigned long long nf = 0;
+        if (blockIdx.x == 0)
+            for (int k = 0; k < P.n_llpart; ++k) { s += P.llpart[2 * k]; nf += (unsigned long long)P.llpart[2 * k + 1]; }
+        if (s) atomicAdd(P.red, (unsigned long long)s);
+        if (nf) atomicAdd(P.red + 1, nf);
     }
 }
 
@@ -424,7 +470,7 @@ __global__ void __launch_bounds__(kKsWarps * 32, 2) ks_strings(const KSParams P)
         sg = s_next[par];
     }
     for (int o = 16; o; o >>= 1) { ll_fx += __shfl_xor_sync(FULL, ll_fx, o); bad += __shfl_xor_sync(FULL, bad, o); }
-    if (lane == 0) {
+    if (lane == 0 && P.red) {                                  // red == nullptr: per-string log q only (the usual case)
         if (ll_fx) atomicAdd(P.red, (unsigned long long)ll_fx);
         if (bad) atomicAdd(P.red + 1, bad);
     }
@@ -443,6 +489,17 @@ __global__ void __launch_bounds__(kKsWarps * 32, 2) ks_strings(const KSParams P)
     }
 }
 
+// no region types at all: the bridge partials are the whole log-likelihood
+__global__ void k_add_llpart(const long long* __restrict__ llpart, int n, unsigned long long* red)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        long long s = 0, nf = 0;
+        for (int k = 0; k < n; ++k) { s += llpart[2 * k]; nf += llpart[2 * k + 1]; }
+        if (s) atomicAdd(red, (unsigned long long)s);
+        if (nf) atomicAdd(red + 1, (unsigned long long)nf);
+    }
+}
+
 // log q of the strings of the segmented path, group order -> string id order
 __global__ void k_scatter_logq(long long n, const int32_t* __restrict__ ksid, const double* __restrict__ logq_k, double* logq)
 {
@@ -450,17 +507,43 @@ __global__ void k_scatter_logq(long long n, const int32_t* __restrict__ ksid, co
     if (i < n && ksid[i] >= 0) logq[ksid[i]] = logq_k[i];
 }
 
+// The bridge part of the log-likelihood: sum over arcs of (sum_s p_s * times the arc is a bridge of s) * log w[arc].
+// const_acc holds the first factor in the fixed point of the gradient accumulators (it is the constant part of the
+// gradient as well).  Called by all threads of a 256-thread CTA with the arc of the thread (c = 0 beyond the last
+// arc); CTAs that hold arcs store their partial [value, non-finite terms] to llpart[blockIdx.x] (no reset needed).
+__device__ __forceinline__ void bridge_loglik_partial(unsigned long long c, double l, double inv_fx, double ll_scale, long long* llpart)
+{
+    __shared__ long long s_part[8][2];
+    long long v = 0, nf = 0;
+    if (c) {
+        if (isfinite(l)) v = __double2ll_rn((double)(long long)c * inv_fx * l * ll_scale);
+        else nf = 1;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { v += __shfl_xor_sync(FULL, v, o); nf += __shfl_xor_sync(FULL, nf, o); }
+    if ((threadIdx.x & 31) == 0) { s_part[threadIdx.x >> 5][0] = v; s_part[threadIdx.x >> 5][1] = nf; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { v += s_part[w][0]; nf += s_part[w][1]; }
+        llpart[2 * blockIdx.x] = v;
+        llpart[2 * blockIdx.x + 1] = nf;
+    }
+}
+
 // per combined arc: aw = a(u,v) * b(v,e) and its logarithm, straight from x
-__global__ void k_arc_weights_log(int n_arcs, const int32_t* __restrict__ arc_tid, const int32_t* __restrict__ arc_eid,
+__global__ void __launch_bounds__(256) k_arc_weights_log(int n_arcs, const int32_t* __restrict__ arc_tid, const int32_t* __restrict__ arc_eid,
                                   const int32_t* __restrict__ trans_tp, const int32_t* __restrict__ emis_tp,
-                                  const double* __restrict__ x, double* aw, double* logaw)
+                                  const double* __restrict__ x, double* aw, double* logaw,
+                                  const unsigned long long* __restrict__ const_acc, double inv_fx, double ll_scale, long long* llpart)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double l = 0.0;
     if (i < n_arcs) {
-        const double l = logweight_of(trans_tp[arc_tid[i]], x, 0) + (arc_eid[i] < 0 ? 0.0 : logweight_of(emis_tp[arc_eid[i]], x, 0));
+        l = logweight_of(trans_tp[arc_tid[i]], x, 0) + (arc_eid[i] < 0 ? 0.0 : logweight_of(emis_tp[arc_eid[i]], x, 0));
         logaw[i] = l;
         aw[i] = exp(l);
     }
+    bridge_loglik_partial(i < n_arcs ? const_acc[i] : 0ull, l, inv_fx, ll_scale, llpart);
 }
 
 
@@ -476,14 +559,20 @@ struct Prep6Params {
     unsigned long long* acc; unsigned long long* red;
     unsigned int* counters;            // [2]
     double* out;
+    double inv_fx, ll_scale;
+    long long* llpart;                 // [ceil(n_arcs / 256)][2]
 };
-__global__ void k_prep6(const Prep6Params P)
+__global__ void __launch_bounds__(256) k_prep6(const Prep6Params P)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P.n_arcs) {
-        const double l = logweight_of(P.trans_tp[P.arc_tid[i]], P.x, 0) + (P.arc_eid[i] < 0 ? 0.0 : logweight_of(P.emis_tp[P.arc_eid[i]], P.x, 0));
-        P.logaw[i] = l;
-        P.aw[i] = exp(l);
+    if (blockIdx.x * blockDim.x < P.n_arcs) {                  // CTA uniform
+        double l = 0.0;
+        if (i < P.n_arcs) {
+            l = logweight_of(P.trans_tp[P.arc_tid[i]], P.x, 0) + (P.arc_eid[i] < 0 ? 0.0 : logweight_of(P.emis_tp[P.arc_eid[i]], P.x, 0));
+            P.logaw[i] = l;
+            P.aw[i] = exp(l);
+        }
+        bridge_loglik_partial(i < P.n_arcs ? P.const_acc[i] : 0ull, l, P.inv_fx, P.ll_scale, P.llpart);
     }
     if (i < P.n_arcs * P.replicas) P.acc[i] = i < P.n_arcs ? P.const_acc[i] : 0ull;
     if (i < P.n_red) P.red[i] = 0ull;

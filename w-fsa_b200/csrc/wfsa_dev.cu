@@ -150,7 +150,7 @@ struct wfsa_dev {
     long long kt_groups = 0;
     std::vector<uint8_t> h_overflow;
     int64_t launches = 0;
-    bool structure_done = false, lean_finished = false, lean_now = false, side_folded = false;
+    bool structure_done = false, lean_finished = false, lean_now = false;
     std::vector<uint8_t> h_recognised;
     // Hessian
     DevBuf<int64_t> d_hb_path_off, d_hb_col_off, d_hb_val_off;
@@ -170,8 +170,11 @@ struct wfsa_dev {
     size_t kev_used = 0; bool timing = false;
     std::vector<cudaEvent_t> kev_mid;           // segmented path: between kr_regions and ks_strings
     cudaEvent_t mid_now = nullptr;
-    cudaStream_t stream2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;    // the fold runs next to ks_strings
     DevBuf<unsigned int> d_done;
+    DevBuf<unsigned char> d_flush; int flush_byte = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sev; size_t sev_used = 0;      // per-evaluation event pairs (timer)
+    DevBuf<long long> d_llpart;             // bridge part of the log-likelihood: per-CTA partials of the weight kernel
+    bool ks_done = false;                   // ks_strings has run for the last evaluation (it runs on demand)
     DevBuf<long long> d_pv; DevBuf<int64_t> d_pvoff, d_pcoff; DevBuf<int32_t> d_pidx, d_pcarc; int64_t n_pchunks = 0; bool pull = false;
 };
 
@@ -234,10 +237,8 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     if (h->ev_end) cudaEventDestroy(h->ev_end);
     for (auto& e : h->kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto& e : h->kev_mid) cudaEventDestroy(e);
-    if (h->stream2) cudaStreamDestroy(h->stream2);
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->ev_join) cudaEventDestroy(h->ev_join);
-    h->d_done.release(); h->d_pv.release(); h->d_pvoff.release(); h->d_pcoff.release(); h->d_pidx.release(); h->d_pcarc.release();
+    h->d_done.release(); h->d_llpart.release(); h->d_flush.release();
+    for (auto& e : h->sev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } h->d_pv.release(); h->d_pvoff.release(); h->d_pcoff.release(); h->d_pidx.release(); h->d_pcarc.release();
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -369,6 +370,7 @@ static int setup_kl(wfsa_dev* h)
     CK(h->d_kl_arc_tid.upload(A.arc_tid, h->stream)); CK(h->d_kl_arc_eid.upload(A.arc_eid, h->stream));
     CK(h->d_klaw.alloc(A.n_arcs)); CK(h->d_klacc.alloc((size_t)A.n_arcs * h->replicas)); CK(h->d_klconst.alloc(A.n_arcs));
     CK(h->d_klcounter.alloc(2));
+    CK(h->d_llpart.alloc(2 * (size_t)((std::max(h->larcs.n_arcs, 1) + 255) / 256)));
     CK(h->d_done.alloc(1));
     CK(cudaMemsetAsync(h->d_done.p, 0, 4, h->stream));      // every finishing ks_strings launch counts it up to the grid size and resets it
     if (h->kernel == 6) {
@@ -605,7 +607,8 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
             P.lq = h->d_krlq.p; P.n_groups = h->kr_groups; P.xs = h->d_klxs.p; P.xs_rows = (size_t)std::max<int64_t>(h->kl_max_words, 1);
             P.counter = h->d_klcounter.p; P.acc = h->d_klacc.p; P.fx_scale = O.fx_scale; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas;
             P.n_first = h->kr_big_groups; P.stride = h->kr_stride;
-            P.pv = (h->lean_now && h->pull && !getenv("WFSA_SERIAL_FOLD") && h->n_pchunks > 0) ? h->d_pv.p : nullptr; P.pvoff = h->d_pvoff.p;
+            P.ll_scale = O.ll_scale; P.red = O.red; P.llpart = h->d_llpart.p; P.n_llpart = (h->larcs.n_arcs + 255) / 256;
+            P.pv = (h->lean_now && h->pull && h->n_pchunks > 0) ? h->d_pv.p : nullptr; P.pvoff = h->d_pvoff.p;
             if (h->opt.reserved & 2) kr_regions<ACC_NONE, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // timing experiment
             else if (h->opt.reserved & 1) kr_regions<ACC_SMEM_CAS, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // plain REDs
             else if (h->kl_block <= 512) kr_regions<ACC_GLOBAL, 512><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
@@ -614,38 +617,19 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
             h->launches++;
         }
         if (h->mid_now) cudaEventRecord(h->mid_now, st);
-        const bool side_fold = h->lean_now && !getenv("WFSA_SERIAL_FOLD");
-        if (side_fold) {
-            // the per-edge fold of the accumulators only depends on kr_regions: it runs on a second stream next to ks_strings
-            if (!h->stream2) {
-                cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
-                cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
-            }
-            cudaEventRecord(h->ev_fork, st);
-            cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
-            if (h->pull && h->n_pchunks > 0) {                  // the path-form gradient: per-arc gather of the stored path values
-                k_pull_paths<<<(unsigned)((h->n_pchunks + 7) / 8), 256, 0, h->stream2>>>(h->n_pchunks, h->d_pcoff.p, h->d_pcarc.p, h->d_pidx.p,
-                                                                                       h->d_pv.p, h->d_klacc.p);
-                h->launches++;
-            }
-            Fin6Params Fp{};
-            Fp.n_edges = h->n_edges; Fp.n_arcs = h->larcs.n_arcs; Fp.replicas = h->replicas; Fp.n = h->n; Fp.finish = h->comm ? 0 : 1;
-            Fp.e_off = h->d_eoff.p; Fp.e_arc = h->d_earc.p; Fp.acc = h->d_klacc.p; Fp.red = h->d_red.p; Fp.edge_tp = h->d_edge_tp.p;
-            Fp.inv_fx = std::ldexp(1.0, -(int)h->fx_log2); Fp.inv_ll = std::ldexp(1.0, -(int)h->ll_log2); Fp.out = h->d_out.p;
-            k_fold_finish6<<<(std::max(h->n_edges, 1) + 7) / 8, 256, 0, h->stream2>>>(Fp);      // one warp per edge
-            h->launches++;
-            cudaEventRecord(h->ev_join, h->stream2);
-        }
-        KSParams S{};
-        S.logaw = h->d_klogaw.p; S.words = h->d_kswords.p; S.sgoff = h->d_ksgoff.p; S.gref = h->d_ksgref.p; S.lq = h->d_krlq.p;
-        S.p = h->d_ksp.p; S.logq = h->d_kslogq.p; S.n_sgroups = h->ks_groups; S.counter = h->d_klcounter.p + 1; S.red = O.red;
-        S.ll_scale = O.ll_scale; S.n_arcs = h->larcs.n_arcs;
-        S.finish_ll = (side_fold && !h->comm) ? 1 : 0; S.inv_ll = std::ldexp(1.0, -(int)h->ll_log2); S.out = h->d_out.p; S.done = h->d_done.p;
-        if (h->ks_groups > 0) {
-            ks_strings<<<h->ks_grid, h->ks_block, h->ks_smem, st>>>(S);
+        // [loglik, grad] are complete after kr_regions: the bridges of every string are folded into constants
+        // (gradient: const_acc; log-likelihood: the llpart partials of the weight kernel).  Per-string log q is
+        // only computed when a caller asks for it (wfsa_dev_eval_fetch with logq != NULL launches ks_strings).
+        h->ks_done = false;
+        if (h->kr_groups == 0 && h->larcs.n_arcs > 0) {          // no region at all (unique paths): the bridge part on its own
+            k_add_llpart<<<1, 32, 0, st>>>(h->d_llpart.p, (h->larcs.n_arcs + 255) / 256, O.red);
             h->launches++;
         }
-        if (side_fold) h->side_folded = true;                   // joined by launch_pipeline, behind the kernel timing event
+        if (h->lean_now && h->pull && h->n_pchunks > 0) {       // experiment: per-arc gather of the stored path values
+            k_pull_paths<<<(unsigned)((h->n_pchunks + 7) / 8), 256, 0, st>>>(h->n_pchunks, h->d_pcoff.p, h->d_pcarc.p, h->d_pidx.p,
+                                                                             h->d_pv.p, h->d_klacc.p);
+            h->launches++;
+        }
     } else if (kernel == 5) {
         KLParams P{};
         P.aw = h->d_klaw.p; P.words = h->d_klwords.p; P.goff = h->d_klgoff.p; P.gsid = h->d_klgsid.p; P.p = h->d_p.p;
@@ -745,6 +729,7 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
         P.arc_tid = h->d_kl_arc_tid.p; P.arc_eid = h->d_kl_arc_eid.p; P.trans_tp = h->d_trans_tp.p; P.emis_tp = h->d_emis_tp.p;
         P.x = h->d_x.p; P.const_acc = h->d_klconst.p; P.aw = h->d_klaw.p; P.logaw = h->d_klogaw.p; P.acc = h->d_klacc.p;
         P.red = h->d_red.p; P.counters = h->d_klcounter.p; P.out = h->d_out.p;
+        P.inv_fx = std::ldexp(1.0, -(int)h->fx_log2); P.ll_scale = std::ldexp(1.0, (int)h->ll_log2); P.llpart = h->d_llpart.p;
         const int total = std::max({P.n_arcs * P.replicas, P.n_red, P.n_out, 2});
         k_prep6<<<(total + 255) / 256, 256, 0, st>>>(P);
         h->launches++;
@@ -772,7 +757,9 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
             const int na = h->larcs.n_arcs;
             if (kernel == 6)
                 k_arc_weights_log<<<(na + 255) / 256, 256, 0, st>>>(na, h->d_kl_arc_tid.p, h->d_kl_arc_eid.p, h->d_trans_tp.p,
-                                                                  h->d_emis_tp.p, h->d_x.p, h->d_klaw.p, h->d_klogaw.p);
+                                                                  h->d_emis_tp.p, h->d_x.p, h->d_klaw.p, h->d_klogaw.p, h->d_klconst.p,
+                                                                  std::ldexp(1.0, -(int)h->fx_log2), std::ldexp(1.0, (int)h->ll_log2),
+                                                                  h->d_llpart.p);
             else
                 k_arc_weights<<<(na + 255) / 256, 256, 0, st>>>(na, h->d_kl_arc_tid.p, h->d_kl_arc_eid.p, h->d_emis_tp.p, h->d_tw.p,
                                                               h->d_x.p, unit, h->d_klaw.p);
@@ -799,14 +786,8 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
     launch_main(h, kernel, mode, CorpusD{h->d_tokens.p, h->d_offs.p, h->d_p.p, d_order, n_order}, O);
     if (kernel2) launch_main(h, kernel2, mode, CorpusD{h->d_tokens.p, h->d_offs.p, h->d_p.p, d_order2, n_order2}, O);
     if (e1) cudaEventRecord(e1, st);
-    if (h->side_folded) cudaStreamWaitEvent(st, h->ev_join, 0);
     h->mid_now = nullptr;
     CK(cudaGetLastError());
-    if (lean6 && h->side_folded) {               // folded next to ks_strings, [loglik, bad] written by its last CTA
-        h->side_folded = false;
-        h->lean_finished = !h->comm;
-        return WFSA_OK;
-    }
     if (lean6) {
         Fin6Params P{};
         P.n_edges = h->n_edges; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas; P.n = h->n; P.finish = h->comm ? 0 : 3;
@@ -1119,11 +1100,27 @@ static int setup_peer_allreduce(wfsa_dev* h)
     return WFSA_OK;
 }
 
+static int eval_launch_body(wfsa_dev* h);
+
 extern "C" int wfsa_dev_eval_launch(wfsa_dev* h)
 {
     if (!h) return WFSA_ERR_INVALID;
     if (h->n < 0) return set_err(h, WFSA_ERR_STATE, "eval before set_param_map");
     CK(cudaSetDevice(h->device));
+    cudaEvent_t s1 = nullptr;
+    if (h->timing) {                               // one event pair around the whole evaluation (weights, kernels, fold, collective)
+        if (h->sev_used == h->sev.size() && h->sev.size() < 8192) {
+            cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); h->sev.push_back({a, b});
+        }
+        if (h->sev_used < h->sev.size()) { cudaEventRecord(h->sev[h->sev_used].first, h->stream); s1 = h->sev[h->sev_used].second; h->sev_used++; }
+    }
+    const int rc = eval_launch_body(h);
+    if (s1) cudaEventRecord(s1, h->stream);
+    return rc;
+}
+
+static int eval_launch_body(wfsa_dev* h)
+{
     int rc = launch_pipeline(h, MODE_EVAL, h->kernel, h->d_order.p, h->n_active,
                              h->kernel >= 4 ? h->secondary : 0, h->d_order_w.p, h->n_active_w, true, true);
     if (rc != WFSA_OK) return rc;
@@ -1165,6 +1162,16 @@ extern "C" int wfsa_dev_eval_fetch(wfsa_dev* h, double* loglik, double* logq, do
     if (h->n < 0) return set_err(h, WFSA_ERR_STATE, "fetch before set_param_map");
     CK(cudaMemcpyAsync(h->h_out, h->d_out.p, ((size_t)h->n + 2) * 8, cudaMemcpyDeviceToHost, h->stream));
     if (logq && h->kernel == 6 && h->ks_groups > 0) {
+        if (!h->ks_done) {                       // per-string log q of the segmented path, from the lq of the last evaluation
+            KSParams S{};
+            S.logaw = h->d_klogaw.p; S.words = h->d_kswords.p; S.sgoff = h->d_ksgoff.p; S.gref = h->d_ksgref.p; S.lq = h->d_krlq.p;
+            S.p = h->d_ksp.p; S.logq = h->d_kslogq.p; S.n_sgroups = h->ks_groups; S.counter = h->d_klcounter.p + 1; S.red = nullptr;
+            S.ll_scale = 1.0; S.n_arcs = h->larcs.n_arcs; S.finish_ll = 0; S.inv_ll = 1.0; S.out = h->d_out.p; S.done = h->d_done.p;
+            CK(cudaMemsetAsync(h->d_klcounter.p + 1, 0, 4, h->stream));
+            ks_strings<<<h->ks_grid, h->ks_block, h->ks_smem, h->stream>>>(S);
+            h->launches++;
+            h->ks_done = true;
+        }
         const long long nk = (long long)h->d_kssid.n;
         k_scatter_logq<<<(unsigned)((nk + 255) / 256), 256, 0, h->stream>>>(nk, h->d_kssid.p, h->d_kslogq.p, h->d_logq.p);
         h->launches++;
@@ -1310,7 +1317,7 @@ extern "C" int wfsa_dev_allreduce_f64(wfsa_dev* h, double* values, int n, int op
 extern "C" int wfsa_dev_timer_begin(wfsa_dev* h)
 {
     if (!h) return WFSA_ERR_INVALID;
-    h->timing = true; h->kev_used = 0;
+    h->timing = true; h->kev_used = 0; h->sev_used = 0;
     CK(cudaEventRecord(h->ev_begin, h->stream));
     return WFSA_OK;
 }
@@ -1337,6 +1344,37 @@ extern "C" int wfsa_dev_timer_kernel_ms(wfsa_dev* h, float* ms, int64_t* launche
     }
     if (ms) *ms = total;
     if (launches) *launches = (int64_t)h->kev_used;
+    return WFSA_OK;
+}
+
+extern "C" int wfsa_dev_timer_step_ms(wfsa_dev* h, float* ms, int64_t* steps)
+{
+    if (!h) return WFSA_ERR_INVALID;
+    float total = 0.f;
+    for (size_t i = 0; i < h->sev_used; ++i) {
+        float t = 0.f;
+        CK(cudaEventSynchronize(h->sev[i].second));
+        CK(cudaEventElapsedTime(&t, h->sev[i].first, h->sev[i].second));
+        total += t;
+    }
+    if (ms) *ms = total;
+    if (steps) *steps = (int64_t)h->sev_used;
+    return WFSA_OK;
+}
+
+// Evicts the L2 between two timed evaluations: a memset of a buffer twice the size of the L2 on the evaluation
+// stream (it runs between the per-evaluation event pairs of wfsa_dev_timer_step_ms, not inside them).
+extern "C" int wfsa_dev_l2_flush(wfsa_dev* h)
+{
+    if (!h) return WFSA_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!h->d_flush.p) {
+        int l2 = 0;
+        CK(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, h->device));
+        CK(h->d_flush.alloc(2 * (size_t)std::max(l2, 64 << 20)));
+    }
+    h->flush_byte ^= 1;
+    CK(cudaMemsetAsync(h->d_flush.p, h->flush_byte, h->d_flush.n, h->stream));
     return WFSA_OK;
 }
 
