@@ -260,13 +260,15 @@ def run_ours(args, rank, world, local):
     # which would otherwise stay in the 126 MB L2 from one step to the next
     dev.timer_begin()
     for _ in range(args.steps):
-        dev.l2_flush()
+        if not args.no_flush:
+            dev.l2_flush()
         dev.eval_launch()
     bracket_ms = dev.timer_end()
     barrier()
     ms, nsteps = dev.timer_step_ms()
     assert nsteps == args.steps
     kms, klaunches = dev.timer_kernel_ms()
+    phases = dev.timer_phase_ms()
     launches = dev.info()["kernels_launched"] - launches0
     ll, grad = dev.eval_fetch()
     # ---- end to end through the host-buffer C-ABI call
@@ -292,6 +294,7 @@ def run_ours(args, rank, world, local):
     lq_ms = lq_s * 1e3 / min(args.steps, 5)
     barrier()
     tok_total, ms_max, e2e_max, kms_max = float(my_tokens), ms, e2e_s, kms
+    phases_all = [phases]
     if world > 1:
         v = torch.tensor([ms, e2e_s, kms], dtype=torch.float64, device="cuda")
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
@@ -299,6 +302,10 @@ def run_ours(args, rank, world, local):
         tt = torch.tensor([float(my_tokens)], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt)
         tok_total = float(tt.item())
+        ph = torch.tensor(phases, dtype=torch.float64, device="cuda")
+        allph = [torch.zeros_like(ph) for _ in range(world)]
+        dist.all_gather(allph, ph)
+        phases_all = [p.tolist() for p in allph]
     if ms_max < 600.0:
         # the timed regions are shorter than nvidia-smi's sampling period: keep the same load running (untimed)
         # for ~0.6 s so that `clocks` describes the GPU under this workload.  Every rank runs the same number of
@@ -369,12 +376,15 @@ def run_ours(args, rank, world, local):
                          "traffic": traffic, "peak_source": peak_src, "kernel": {1: "k2_fwdbwd", 2: "k3_fwdbwd", 3: "kg_fwdbwd", 4: "kt_fwdbwd", 5: "kl_fwdbwd", 6: "kr_regions"}[info["kernel"]],
                          "kernel_ms": k_ms, **({"alpha_lattice_entries": a_lat} if a_lat else {}),
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel_share_of_step": kms_max / ms_max},
+                         "kernel_share_of_step": kms_max / ms_max,
+                         # per rank: [weights and resets, dominant kernel, fold + collective + finish] in us per step
+                         "phases_us_per_rank": [[round(1e3 * v / steps, 2) for v in p] for p in phases_all]},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * (n + 2),
                     "ms_per_step": e2e_max * 1e3 / steps, "with_logq_ms_per_step": lq_ms,
                     "with_logq_d2h_bytes_per_step": 8 * (n + 2) + 8 * len(w)},
             "gpu_launches": int(launches),
             **({"INVALID": "--noacc timing experiment: gradient accumulation skipped"} if args.noacc else {}),
+            **({"INVALID": "--no-flush timing experiment: L2 warm from the previous step"} if args.no_flush else {}),
             "clocks": clocks,
             "loglik": ll,
         }
@@ -402,6 +412,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="compiled-lattice kernel: threads per CTA (0 = as many as fit, <= 1024)")
     ap.add_argument("--replicas", type=int, default=0, help="copies of the global accumulators (0 = library default)")
     ap.add_argument("--noacc", action="store_true", help="timing experiment: skip gradient accumulation (INVALID as a result)")
+    ap.add_argument("--no-flush", action="store_true", help="experiment: do not evict the L2 between steps (INVALID as a result)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ref-strings", type=int, default=8000, help="--impl reference: strings in the bounded sample")
     ap.add_argument("--cpu-strings", type=int, default=20000)

@@ -148,6 +148,9 @@ int wfsa_dev_timer_split_ms(wfsa_dev* h, float* first_ms, float* second_ms);
  * the WHOLE evaluation (weights, kernels, fold, collective); `steps` = how many.  Work queued between two evaluations
  * (wfsa_dev_l2_flush) is not included. */
 int wfsa_dev_timer_step_ms(wfsa_dev* h, float* ms, int64_t* steps);
+/* The same evaluations split into three phases (sums, ms): [0] start of the evaluation -> dominant kernel (weights,
+ * resets), [1] the dominant kernel(s), [2] from there to the end (fold, collective, conversion). */
+int wfsa_dev_timer_phase_ms(wfsa_dev* h, float* out3);
 /* Benchmark helper: evicts the L2 cache (memset of a buffer twice its size on the evaluation stream). */
 int wfsa_dev_l2_flush(wfsa_dev* h);
 

@@ -683,4 +683,83 @@ __global__ void __launch_bounds__(1024, 1) k_peer_allreduce_finish(const PeerPar
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fold + all-reduce + finish in ONE launch (the lean segmented path with a communicator).
+// One warp per payload word w (0 = loglik, 1 = non-finite terms, 2 + e = accumulator of edge e):
+//   1. the local value: red[w] for w < 2, else the gather over the (arc, replica) cells of the edge (k_fold_finish6);
+//   2. lane r < nranks sends it to rank r as two self-validating 8-byte packets {32 data bits, 32-bit epoch}
+//      (plain stores into the peer's IPC-mapped buffer; an aligned 8-byte store is a single transaction, so a packet
+//      whose upper half equals the epoch is complete -- no fence, no separate flag, no second round trip);
+//   3. lane r polls the two packets rank r sent for this word into the local buffer, the lanes add up with shuffles
+//      (integers: every rank gets the same bits) and lane 0 converts to out[].
+// Packets of epoch e live in buffer e & 1; a rank cannot start epoch e + 2 before every peer has finished reading
+// epoch e, because it needs their packets of epoch e + 1 first.  All CTAs of the grid are resident (host checks), so
+// no warp waits for a warp of its own GPU.  The wait is bounded (~2 s): out[1] = NaN on time-out.
+// Layout (uint64 words, relative to ll_off): pk[parity][sender rank][word][2].
+struct FoldPeerParams {
+    Fin6Params F;
+    unsigned long long* peers[8];
+    size_t ll_off;
+    int nranks, rank, words;
+    unsigned int flag;                     // low 32 bits of the epoch; epochs start at 1
+    int parity;
+};
+
+__device__ __forceinline__ unsigned long long ll_exchange(const FoldPeerParams& P, int w, unsigned long long s, int lane, bool& timeout)
+{
+    unsigned long long v = 0;
+    if (lane < P.nranks) {
+        volatile unsigned long long* dst = P.peers[lane] + P.ll_off + (((size_t)P.parity * P.nranks + P.rank) * P.words + w) * 2;
+        const unsigned long long fl = (unsigned long long)P.flag << 32;
+        dst[0] = (s & 0xffffffffull) | fl;
+        dst[1] = (s >> 32) | fl;
+        const volatile unsigned long long* src = P.peers[P.rank] + P.ll_off + (((size_t)P.parity * P.nranks + lane) * P.words + w) * 2;
+        const long long t0 = clock64();
+        unsigned long long a = src[0], b = src[1];
+        while ((unsigned int)(a >> 32) != P.flag || (unsigned int)(b >> 32) != P.flag) {
+            if (clock64() - t0 > 4000000000ll) { timeout = true; break; }
+            a = src[0]; b = src[1];
+        }
+        v = (a & 0xffffffffull) | (b << 32);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_fold_allreduce_finish6(const FoldPeerParams P)
+{
+    const Fin6Params& F = P.F;
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= P.words || w == 1) return;                        // warp 0 takes words 0 and 1
+    bool timeout = false;
+    if (w == 0) {
+        const unsigned long long ll = ll_exchange(P, 0, F.red[0], lane, timeout);
+        const unsigned long long bad = ll_exchange(P, 1, F.red[1], lane, timeout);
+        const bool any_to = __any_sync(FULL, timeout);
+        if (lane == 0) {
+            F.out[0] = bad > 0 ? -INFINITY : (double)(long long)ll * F.inv_ll;
+            if (any_to) F.out[1] = NAN; else if (bad) F.out[1] = (double)bad;      // out[] was cleared by k_prep6; NaN wins
+        }
+        return;
+    }
+    const int e = w - 2;
+    const int k0 = F.e_off[e], cells = (F.e_off[e + 1] - k0) * F.replicas;
+    unsigned long long s = 0;
+    for (int c = lane; c < cells; c += 32) {
+        const int a = F.e_arc[k0 + c / F.replicas], r = c % F.replicas;
+        s += F.acc[(size_t)r * F.n_arcs + a];
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    const unsigned long long sum = ll_exchange(P, w, s, lane, timeout);
+    if (__any_sync(FULL, timeout)) { if (lane == 0) F.out[1] = NAN; return; }
+    if (lane == 0) {
+        F.red[w] = sum;
+        const int tp = F.edge_tp[e];
+        if (tp >= 0 && tp < F.n) F.out[2 + tp] = -(double)(long long)sum * F.inv_fx;
+    }
+}
+
 }  // namespace wfsa

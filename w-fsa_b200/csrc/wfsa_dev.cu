@@ -162,7 +162,7 @@ struct wfsa_dev {
     // comm
     ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
     // one-shot all-reduce over NVLink peer memory (k_peer_allreduce_finish); falls back to NCCL when it cannot be set up
-    bool peer_ok = false; unsigned long long peer_epoch = 0; int peer_words = 0;
+    bool peer_ok = false; unsigned long long peer_epoch = 0, peer_ll_epoch = 0; int peer_words = 0; size_t peer_ll_off = 0; int fold_peer_ctas = 0;
     unsigned long long* peer_local = nullptr; unsigned long long* peer_ptrs[8] = {nullptr};
     // timing
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -793,6 +793,23 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
         P.n_edges = h->n_edges; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas; P.n = h->n; P.finish = h->comm ? 0 : 3;
         P.e_off = h->d_eoff.p; P.e_arc = h->d_earc.p; P.acc = h->d_klacc.p; P.red = h->d_red.p; P.edge_tp = h->d_edge_tp.p;
         P.inv_fx = std::ldexp(1.0, -(int)h->fx_log2); P.inv_ll = std::ldexp(1.0, -(int)h->ll_log2); P.out = h->d_out.p;
+        const int words = 2 + h->n_edges;
+        const int grid_f = (words + 7) / 8;
+        if (h->comm && h->peer_ok && h->peer_words == words && grid_f <= h->fold_peer_ctas && !getenv("WFSA_PEER_SINGLE_CTA")) {
+            // fold, all-reduce over peer memory and conversion in one launch; its warps wait for the peers' packets,
+            // so the whole grid must be resident (fold_peer_ctas: occupancy x SMs)
+            FoldPeerParams Q{};
+            Q.F = P;
+            for (int r = 0; r < h->nranks; ++r) Q.peers[r] = h->peer_ptrs[r];
+            Q.ll_off = h->peer_ll_off; Q.nranks = h->nranks; Q.rank = h->rank; Q.words = words;
+            ++h->peer_ll_epoch;
+            Q.flag = (unsigned int)(h->peer_ll_epoch % 0xfffffffeull) + 1u; Q.parity = (int)(h->peer_ll_epoch & 1ull);
+            k_fold_allreduce_finish6<<<grid_f, 256, 0, st>>>(Q);
+            h->launches++;
+            CK(cudaGetLastError());
+            h->lean_finished = true;
+            return WFSA_OK;
+        }
         k_fold_finish6<<<(std::max(h->n_edges, 1) + 7) / 8, 256, 0, st>>>(P);      // one warp per edge
         h->launches++;
         CK(cudaGetLastError());
@@ -1054,7 +1071,9 @@ static int setup_peer_allreduce(wfsa_dev* h)
     const int words = (int)h->d_red.n;
     if (h->peer_local && h->peer_words == words) { h->peer_ok = true; return WFSA_OK; }
     if (h->peer_local) return WFSA_OK;                       // sized for another parameter map: keep NCCL (rare)
-    const size_t total = (size_t)2 * h->nranks * words + (size_t)2 * h->nranks;
+    // [data of the single-CTA kernel: 2 x nranks x words][its flags: 2 x nranks][packets of the fused kernel: 2 x nranks x words x 2]
+    h->peer_ll_off = (size_t)2 * h->nranks * words + (size_t)2 * h->nranks;
+    const size_t total = h->peer_ll_off + (size_t)4 * h->nranks * words;
     unsigned long long ok = 1;
     cudaIpcMemHandle_t mine;
     std::memset(&mine, 0, sizeof(mine));
@@ -1095,7 +1114,12 @@ static int setup_peer_allreduce(wfsa_dev* h)
     CK(cudaMemcpyAsync(&bad, d_flag, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->peer_words = words;
-    h->peer_epoch = 0;
+    h->peer_epoch = 0; h->peer_ll_epoch = 0;
+    {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fold_allreduce_finish6, 256, 0) != cudaSuccess) { nb = 0; cudaGetLastError(); }
+        h->fold_peer_ctas = nb * h->sm_count;
+    }
     h->peer_ok = bad == 0;
     return WFSA_OK;
 }
@@ -1179,6 +1203,8 @@ extern "C" int wfsa_dev_eval_fetch(wfsa_dev* h, double* loglik, double* logq, do
     if (logq && h->n_strings) CK(cudaMemcpyAsync(logq, h->d_logq.p, (size_t)h->n_strings * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
+    if (h->comm && std::isnan(h->h_out[1]))
+        return set_err(h, WFSA_ERR_NCCL, "all-reduce over peer memory: a rank did not deliver its share within the time limit");
     if (loglik) *loglik = h->h_out[0];
     if (grad) std::memcpy(grad, h->h_out + 2, (size_t)h->n * 8);
     return WFSA_OK;
@@ -1375,6 +1401,24 @@ extern "C" int wfsa_dev_l2_flush(wfsa_dev* h)
     }
     h->flush_byte ^= 1;
     CK(cudaMemsetAsync(h->d_flush.p, h->flush_byte, h->d_flush.n, h->stream));
+    return WFSA_OK;
+}
+
+// [0] from the start of an evaluation to the dominant kernel(s) (weights, resets), [1] the dominant kernel(s),
+// [2] from there to the end of the evaluation (fold, collective, conversion); sums over the evaluations since timer_begin
+extern "C" int wfsa_dev_timer_phase_ms(wfsa_dev* h, float* out3)
+{
+    if (!h || !out3) return WFSA_ERR_INVALID;
+    out3[0] = out3[1] = out3[2] = 0.f;
+    const size_t n = std::min(h->sev_used, h->kev_used);
+    for (size_t i = 0; i < n; ++i) {
+        float t = 0.f;
+        CK(cudaEventSynchronize(h->sev[i].second));
+        if (cudaEventElapsedTime(&t, h->sev[i].first, h->kev[i].first) == cudaSuccess) out3[0] += t;
+        if (cudaEventElapsedTime(&t, h->kev[i].first, h->kev[i].second) == cudaSuccess) out3[1] += t;
+        if (cudaEventElapsedTime(&t, h->kev[i].second, h->sev[i].second) == cudaSuccess) out3[2] += t;
+    }
+    cudaGetLastError();
     return WFSA_OK;
 }
 
