@@ -262,6 +262,7 @@ def run_ours(args, rank, world, local):
     for _ in range(args.steps):
         if not args.no_flush:
             dev.l2_flush()
+        dev.rank_barrier()          # N > 1: the flushes of the ranks differ by several us; line the ranks up again (on the device)
         dev.eval_launch()
     bracket_ms = dev.timer_end()
     barrier()
@@ -278,6 +279,7 @@ def run_ours(args, rank, world, local):
     e2e_s = 0.0
     for i in range(args.steps):
         dev.l2_flush()
+        dev.rank_barrier()
         dev.sync()
         t0 = time.perf_counter()
         ll_e, _, g_e = dev.eval(x, want_logq=False)
@@ -287,6 +289,7 @@ def run_ours(args, rank, world, local):
     lq_s = 0.0
     for i in range(min(args.steps, 5)):
         dev.l2_flush()
+        dev.rank_barrier()
         dev.sync()
         t0 = time.perf_counter()
         ll_q, lq, g_q = dev.eval(x, want_logq=True)
@@ -368,7 +371,7 @@ def run_ours(args, rank, world, local):
                                         "region_edges": info["seg_region_edges"], "type_edges": info["seg_type_edges"],
                                         "compile_host_ms": info["seg_host_ms"]}} if info["kernel"] == 6 else {}),
                        "l2_policy": "L2 flushed between timed evaluations (memset of 2x the L2 size on the evaluation stream, outside the "
-                                    "per-evaluation event pairs); ms_per_step = sum of the event pairs / steps",
+                                    "per-evaluation event pairs; with N > 1 followed by a device-side barrier over the ranks, also outside); ms_per_step = sum of the event pairs / steps",
                        "bracket_ms_incl_flush": bracket_ms,
                        "collective": "ncclAllReduce(int64 sum) of [loglik, grad] per step" if world > 1 else "none",
                        "seeds": {"automaton": cfg["seed"], "strings": 1235}},

@@ -509,11 +509,11 @@ __global__ void k_scatter_logq(long long n, const int32_t* __restrict__ ksid, co
 
 // The bridge part of the log-likelihood: sum over arcs of (sum_s p_s * times the arc is a bridge of s) * log w[arc].
 // const_acc holds the first factor in the fixed point of the gradient accumulators (it is the constant part of the
-// gradient as well).  Called by all threads of a 256-thread CTA with the arc of the thread (c = 0 beyond the last
+// gradient as well).  Called by all threads of a CTA with the arc of the thread (c = 0 beyond the last
 // arc); CTAs that hold arcs store their partial [value, non-finite terms] to llpart[blockIdx.x] (no reset needed).
 __device__ __forceinline__ void bridge_loglik_partial(unsigned long long c, double l, double inv_fx, double ll_scale, long long* llpart)
 {
-    __shared__ long long s_part[8][2];
+    __shared__ long long s_part[32][2];
     long long v = 0, nf = 0;
     if (c) {
         if (isfinite(l)) v = __double2ll_rn((double)(long long)c * inv_fx * l * ll_scale);
@@ -560,7 +560,7 @@ struct Prep6Params {
     unsigned int* counters;            // [2]
     double* out;
     double inv_fx, ll_scale;
-    long long* llpart;                 // [ceil(n_arcs / 256)][2]
+    long long* llpart;                 // [ceil(n_arcs / blockDim.x)][2]
 };
 __global__ void __launch_bounds__(256) k_prep6(const Prep6Params P)
 {
@@ -592,7 +592,35 @@ struct Fin6Params {
     double inv_fx, inv_ll;
     double* out;
 };
-__global__ void k_fold_finish6(const Fin6Params P)
+// Sum of the (arc, replica) cells of one edge, by one warp.  The arc ids of the edge are read once (one per lane)
+// and handed out with shuffles, so the cell loads do not wait for an index load each, and four of them are in flight
+// per lane: an emission edge has ~8 arcs x 16 replicas = 128 cells, which took four dependent round trips (5-10 us,
+// the longest thing in the kernel) when every iteration loaded its own arc id first.
+__device__ __forceinline__ unsigned long long fold_edge(const Fin6Params& F, int e, int lane)
+{
+    const int k0 = F.e_off[e], na = F.e_off[e + 1] - k0;
+    unsigned long long s = 0;
+    for (int b = 0; b < na; b += 32) {
+        const int nb = min(32, na - b);
+        const int mine = lane < nb ? F.e_arc[k0 + b + lane] : 0;
+        const int cells = nb * F.replicas;
+        for (int c0 = 0; c0 < cells; c0 += 128) {
+            unsigned long long v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + j * 32 + lane;
+                const int a = __shfl_sync(FULL, mine, min(c / F.replicas, nb - 1));
+                v[j] = c < cells ? F.acc[(size_t)(c % F.replicas) * F.n_arcs + a] : 0ull;
+            }
+            s += (v[0] + v[1]) + (v[2] + v[3]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    return s;
+}
+
+__global__ void __launch_bounds__(256) k_fold_finish6(const Fin6Params P)
 {
     // one warp per edge: its lanes share the (arc, replica) cells of the edge, then a shuffle sum (integers)
     const int lane = threadIdx.x & 31;
@@ -603,14 +631,7 @@ __global__ void k_fold_finish6(const Fin6Params P)
         P.out[1] = bad;
     }
     if (e >= P.n_edges) return;
-    const int k0 = P.e_off[e], cells = (P.e_off[e + 1] - k0) * P.replicas;
-    unsigned long long s = 0;
-    for (int c = lane; c < cells; c += 32) {
-        const int a = P.e_arc[k0 + c / P.replicas], r = c % P.replicas;
-        s += P.acc[(size_t)r * P.n_arcs + a];
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    unsigned long long s = fold_edge(P, e, lane);
     if (lane == 0) {
         s += P.red[2 + e];
         P.red[2 + e] = s;
@@ -735,8 +756,8 @@ __global__ void __launch_bounds__(256) k_fold_allreduce_finish6(const FoldPeerPa
     if (w >= P.words || w == 1) return;                        // warp 0 takes words 0 and 1
     bool timeout = false;
     if (w == 0) {
-        const unsigned long long ll = ll_exchange(P, 0, F.red[0], lane, timeout);
-        const unsigned long long bad = ll_exchange(P, 1, F.red[1], lane, timeout);
+        const unsigned long long ll = ll_exchange(P, 0, F.red[0], lane, timeout);       // (two round trips for this one warp:
+        const unsigned long long bad = ll_exchange(P, 1, F.red[1], lane, timeout);      //  it has no gather to do before them)
         const bool any_to = __any_sync(FULL, timeout);
         if (lane == 0) {
             F.out[0] = bad > 0 ? -INFINITY : (double)(long long)ll * F.inv_ll;
@@ -745,20 +766,35 @@ __global__ void __launch_bounds__(256) k_fold_allreduce_finish6(const FoldPeerPa
         return;
     }
     const int e = w - 2;
-    const int k0 = F.e_off[e], cells = (F.e_off[e + 1] - k0) * F.replicas;
-    unsigned long long s = 0;
-    for (int c = lane; c < cells; c += 32) {
-        const int a = F.e_arc[k0 + c / F.replicas], r = c % F.replicas;
-        s += F.acc[(size_t)r * F.n_arcs + a];
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    const unsigned long long s = fold_edge(F, e, lane);
     const unsigned long long sum = ll_exchange(P, w, s, lane, timeout);
     if (__any_sync(FULL, timeout)) { if (lane == 0) F.out[1] = NAN; return; }
     if (lane == 0) {
         F.red[w] = sum;
         const int tp = F.edge_tp[e];
         if (tp >= 0 && tp < F.n) F.out[2 + tp] = -(double)(long long)sum * F.inv_fx;
+    }
+}
+
+// Device-side barrier over the ranks of the communicator through peer memory (benchmark helper: it lines the ranks
+// up between two timed evaluations).  One warp: lane r tells rank r "rank `rank` reached epoch e", then waits for
+// rank r's word.  Words of epoch e live at bar[(e & 1) * nranks + sender].  Bounded wait (~2 s).
+struct PeerBarrierParams {
+    unsigned long long* peers[8];
+    size_t bar_off;
+    int nranks, rank;
+    unsigned long long epoch;
+};
+__global__ void k_peer_barrier(const PeerBarrierParams P)
+{
+    const int lane = threadIdx.x;
+    if (lane < P.nranks) {
+        const size_t slot = P.bar_off + (size_t)(P.epoch & 1ull) * P.nranks;
+        *reinterpret_cast<volatile unsigned long long*>(P.peers[lane] + slot + P.rank) = P.epoch;
+        const volatile unsigned long long* src = P.peers[P.rank] + slot + lane;
+        const long long t0 = clock64();
+        while (*src != P.epoch)
+            if (clock64() - t0 > 4000000000ll) break;
     }
 }
 

@@ -162,7 +162,7 @@ struct wfsa_dev {
     // comm
     ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
     // one-shot all-reduce over NVLink peer memory (k_peer_allreduce_finish); falls back to NCCL when it cannot be set up
-    bool peer_ok = false; unsigned long long peer_epoch = 0, peer_ll_epoch = 0; int peer_words = 0; size_t peer_ll_off = 0; int fold_peer_ctas = 0;
+    bool peer_ok = false; unsigned long long peer_epoch = 0, peer_ll_epoch = 0; int peer_words = 0; size_t peer_ll_off = 0, peer_bar_off = 0; int fold_peer_ctas = 0; unsigned long long peer_bar_epoch = 0;
     unsigned long long* peer_local = nullptr; unsigned long long* peer_ptrs[8] = {nullptr};
     // timing
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -174,6 +174,7 @@ struct wfsa_dev {
     DevBuf<unsigned char> d_flush; int flush_byte = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sev; size_t sev_used = 0;      // per-evaluation event pairs (timer)
     DevBuf<long long> d_llpart;             // bridge part of the log-likelihood: per-CTA partials of the weight kernel
+    int llpart_n = 0;
     bool ks_done = false;                   // ks_strings has run for the last evaluation (it runs on demand)
     DevBuf<long long> d_pv; DevBuf<int64_t> d_pvoff, d_pcoff; DevBuf<int32_t> d_pidx, d_pcarc; int64_t n_pchunks = 0; bool pull = false;
 };
@@ -607,7 +608,7 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
             P.lq = h->d_krlq.p; P.n_groups = h->kr_groups; P.xs = h->d_klxs.p; P.xs_rows = (size_t)std::max<int64_t>(h->kl_max_words, 1);
             P.counter = h->d_klcounter.p; P.acc = h->d_klacc.p; P.fx_scale = O.fx_scale; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas;
             P.n_first = h->kr_big_groups; P.stride = h->kr_stride;
-            P.ll_scale = O.ll_scale; P.red = O.red; P.llpart = h->d_llpart.p; P.n_llpart = (h->larcs.n_arcs + 255) / 256;
+            P.ll_scale = O.ll_scale; P.red = O.red; P.llpart = h->d_llpart.p; P.n_llpart = h->llpart_n;
             P.pv = (h->lean_now && h->pull && h->n_pchunks > 0) ? h->d_pv.p : nullptr; P.pvoff = h->d_pvoff.p;
             if (h->opt.reserved & 2) kr_regions<ACC_NONE, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // timing experiment
             else if (h->opt.reserved & 1) kr_regions<ACC_SMEM_CAS, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // plain REDs
@@ -622,7 +623,7 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
         // only computed when a caller asks for it (wfsa_dev_eval_fetch with logq != NULL launches ks_strings).
         h->ks_done = false;
         if (h->kr_groups == 0 && h->larcs.n_arcs > 0) {          // no region at all (unique paths): the bridge part on its own
-            k_add_llpart<<<1, 32, 0, st>>>(h->d_llpart.p, (h->larcs.n_arcs + 255) / 256, O.red);
+            k_add_llpart<<<1, 32, 0, st>>>(h->d_llpart.p, h->llpart_n, O.red);
             h->launches++;
         }
         if (h->lean_now && h->pull && h->n_pchunks > 0) {       // experiment: per-arc gather of the stored path values
@@ -732,6 +733,7 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
         P.inv_fx = std::ldexp(1.0, -(int)h->fx_log2); P.ll_scale = std::ldexp(1.0, (int)h->ll_log2); P.llpart = h->d_llpart.p;
         const int total = std::max({P.n_arcs * P.replicas, P.n_red, P.n_out, 2});
         k_prep6<<<(total + 255) / 256, 256, 0, st>>>(P);
+        h->llpart_n = (P.n_arcs + 255) / 256;
         h->launches++;
     } else if (clear) {
         CK(cudaMemsetAsync(h->d_red.p, 0, h->d_red.n * 8, st));
@@ -755,14 +757,16 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
         }
         if (kernel == 5 || kernel == 6) {
             const int na = h->larcs.n_arcs;
-            if (kernel == 6)
+            if (kernel == 6) {
                 k_arc_weights_log<<<(na + 255) / 256, 256, 0, st>>>(na, h->d_kl_arc_tid.p, h->d_kl_arc_eid.p, h->d_trans_tp.p,
                                                                   h->d_emis_tp.p, h->d_x.p, h->d_klaw.p, h->d_klogaw.p, h->d_klconst.p,
                                                                   std::ldexp(1.0, -(int)h->fx_log2), std::ldexp(1.0, (int)h->ll_log2),
                                                                   h->d_llpart.p);
-            else
+                h->llpart_n = (na + 255) / 256;
+            } else {
                 k_arc_weights<<<(na + 255) / 256, 256, 0, st>>>(na, h->d_kl_arc_tid.p, h->d_kl_arc_eid.p, h->d_emis_tp.p, h->d_tw.p,
                                                               h->d_x.p, unit, h->d_klaw.p);
+            }
             h->launches++;
             // replica 0 starts from the constant part (bridge edges: posterior exactly 1), the others from 0
             CK(cudaMemcpyAsync(h->d_klacc.p, h->d_klconst.p, (size_t)na * 8, cudaMemcpyDeviceToDevice, st));
@@ -1073,7 +1077,8 @@ static int setup_peer_allreduce(wfsa_dev* h)
     if (h->peer_local) return WFSA_OK;                       // sized for another parameter map: keep NCCL (rare)
     // [data of the single-CTA kernel: 2 x nranks x words][its flags: 2 x nranks][packets of the fused kernel: 2 x nranks x words x 2]
     h->peer_ll_off = (size_t)2 * h->nranks * words + (size_t)2 * h->nranks;
-    const size_t total = h->peer_ll_off + (size_t)4 * h->nranks * words;
+    h->peer_bar_off = h->peer_ll_off + (size_t)4 * h->nranks * words;       // then the words of k_peer_barrier: 2 x nranks
+    const size_t total = h->peer_bar_off + (size_t)2 * h->nranks;
     unsigned long long ok = 1;
     cudaIpcMemHandle_t mine;
     std::memset(&mine, 0, sizeof(mine));
@@ -1114,7 +1119,7 @@ static int setup_peer_allreduce(wfsa_dev* h)
     CK(cudaMemcpyAsync(&bad, d_flag, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->peer_words = words;
-    h->peer_epoch = 0; h->peer_ll_epoch = 0;
+    h->peer_epoch = 0; h->peer_ll_epoch = 0; h->peer_bar_epoch = 0;
     {
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fold_allreduce_finish6, 256, 0) != cudaSuccess) { nb = 0; cudaGetLastError(); }
@@ -1420,6 +1425,25 @@ extern "C" int wfsa_dev_timer_phase_ms(wfsa_dev* h, float* out3)
     }
     cudaGetLastError();
     return WFSA_OK;
+}
+
+// Lines the ranks of the communicator up on the evaluation stream (benchmark helper, see wfsa_dev.h).
+extern "C" int wfsa_dev_rank_barrier(wfsa_dev* h)
+{
+    if (!h) return WFSA_ERR_INVALID;
+    if (!h->comm || h->nranks <= 1) return WFSA_OK;
+    CK(cudaSetDevice(h->device));
+    if (h->peer_ok) {
+        PeerBarrierParams B{};
+        for (int r = 0; r < h->nranks; ++r) B.peers[r] = h->peer_ptrs[r];
+        B.bar_off = h->peer_bar_off; B.nranks = h->nranks; B.rank = h->rank; B.epoch = ++h->peer_bar_epoch;
+        k_peer_barrier<<<1, 32, 0, h->stream>>>(B);
+        h->launches++;
+        CK(cudaGetLastError());
+        return WFSA_OK;
+    }
+    if (!h->d_flush.p) CK(h->d_flush.alloc(64));
+    return nccl_allreduce(h, h->d_flush.p, 1, ncclUint64, ncclSum);
 }
 
 extern "C" int wfsa_dev_timer_split_ms(wfsa_dev* h, float* first_ms, float* second_ms)
