@@ -138,6 +138,10 @@ int wfsa_dev_allreduce_f64(wfsa_dev* h, double* values, int n, int op);
 
 /* Timing on the handle's own stream with CUDA events (torch events cannot see this stream). */
 int wfsa_dev_timer_begin(wfsa_dev* h);
+/* Like timer_begin, but without the events between the kernels of an evaluation (only wfsa_dev_timer_step_ms is
+ * meaningful afterwards).  Events between kernels serialise the stream, so this is the timer to use for throughput:
+ * the kernels of an evaluation keep their programmatic dependent launches. */
+int wfsa_dev_timer_begin_steps(wfsa_dev* h);
 int wfsa_dev_timer_end(wfsa_dev* h, float* ms);
 /* ms spent in the dominant kernel (forward-backward) over the launches since timer_begin. */
 int wfsa_dev_timer_kernel_ms(wfsa_dev* h, float* ms, int64_t* launches);

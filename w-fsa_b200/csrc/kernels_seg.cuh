@@ -296,6 +296,10 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
     double* aw = reinterpret_cast<double*>(smem);             // [n_arcs + 1]; the last entry is the zero weight of padding
     double* pool = aw + P.n_arcs + 1 + tid;                   // slot s of this thread at pool[s*NT]
+    // programmatic dependent launch (when the host asked for it; no-ops otherwise): this grid may start while the
+    // weight kernel drains, and lets the fold kernel's CTAs be set up while it runs itself
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
     for (int i = tid; i <= P.n_arcs; i += NT) aw[i] = i < P.n_arcs ? P.aw[i] : 0.0;
     __syncthreads();
     const long long gwarp = ((long long)blockIdx.x * NT + tid) >> 5;
@@ -565,6 +569,7 @@ struct Prep6Params {
 __global__ void __launch_bounds__(256) k_prep6(const Prep6Params P)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    cudaTriggerProgrammaticLaunchCompletion();                 // kr_regions may be set up now (it waits for this grid to finish)
     if (blockIdx.x * blockDim.x < P.n_arcs) {                  // CTA uniform
         double l = 0.0;
         if (i < P.n_arcs) {
@@ -599,10 +604,12 @@ struct Fin6Params {
 __device__ __forceinline__ unsigned long long fold_edge(const Fin6Params& F, int e, int lane)
 {
     const int k0 = F.e_off[e], na = F.e_off[e + 1] - k0;
+    int first = lane < min(32, na) ? F.e_arc[k0 + lane] : 0;   // index loads do not depend on the region kernel ...
+    cudaGridDependencySynchronize();                           // ... the accumulator cells do (no-op without PDL)
     unsigned long long s = 0;
     for (int b = 0; b < na; b += 32) {
         const int nb = min(32, na - b);
-        const int mine = lane < nb ? F.e_arc[k0 + b + lane] : 0;
+        const int mine = b == 0 ? first : (lane < nb ? F.e_arc[k0 + b + lane] : 0);
         const int cells = nb * F.replicas;
         for (int c0 = 0; c0 < cells; c0 += 128) {
             unsigned long long v[4];
@@ -626,12 +633,13 @@ __global__ void __launch_bounds__(256) k_fold_finish6(const Fin6Params P)
     const int lane = threadIdx.x & 31;
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (e == 0 && lane == 0 && (P.finish & 2)) {
+        cudaGridDependencySynchronize();
         const double bad = (double)P.red[1];
         P.out[0] = bad > 0 ? -INFINITY : (double)(long long)P.red[0] * P.inv_ll;
         P.out[1] = bad;
     }
     if (e >= P.n_edges) return;
-    unsigned long long s = fold_edge(P, e, lane);
+    unsigned long long s = fold_edge(P, e, lane);              // (waits for kr_regions inside, after the index loads)
     if (lane == 0) {
         s += P.red[2 + e];
         P.red[2 + e] = s;
@@ -756,6 +764,7 @@ __global__ void __launch_bounds__(256) k_fold_allreduce_finish6(const FoldPeerPa
     if (w >= P.words || w == 1) return;                        // warp 0 takes words 0 and 1
     bool timeout = false;
     if (w == 0) {
+        cudaGridDependencySynchronize();
         const unsigned long long ll = ll_exchange(P, 0, F.red[0], lane, timeout);       // (two round trips for this one warp:
         const unsigned long long bad = ll_exchange(P, 1, F.red[1], lane, timeout);      //  it has no gather to do before them)
         const bool any_to = __any_sync(FULL, timeout);

@@ -175,6 +175,7 @@ struct wfsa_dev {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sev; size_t sev_used = 0;      // per-evaluation event pairs (timer)
     DevBuf<long long> d_llpart;             // bridge part of the log-likelihood: per-CTA partials of the weight kernel
     int llpart_n = 0;
+    bool pdl = true, pdl_now = false, timing_detail = true;     // programmatic dependent launches on the lean segmented path
     bool ks_done = false;                   // ks_strings has run for the last evaluation (it runs on demand)
     DevBuf<long long> d_pv; DevBuf<int64_t> d_pvoff, d_pcoff; DevBuf<int32_t> d_pidx, d_pcarc; int64_t n_pchunks = 0; bool pull = false;
 };
@@ -594,6 +595,20 @@ static int upload_transposed_tokens(wfsa_dev* h, const std::vector<int32_t>& ord
     return WFSA_OK;
 }
 
+// Launch with the programmatic-stream-serialization attribute: the grid may be set up (and run up to its
+// cudaGridDependencySynchronize()) while the previous kernel in the stream drains.  pdl = false: a plain launch.
+template <class Kern, class Params>
+static void launch_dep(Kern kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, const Params& params)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, params);
+}
+
 static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, const EvalOutD& O)
 {
     const HostFsa& F = h->fsa;
@@ -612,7 +627,7 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
             P.pv = (h->lean_now && h->pull && h->n_pchunks > 0) ? h->d_pv.p : nullptr; P.pvoff = h->d_pvoff.p;
             if (h->opt.reserved & 2) kr_regions<ACC_NONE, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // timing experiment
             else if (h->opt.reserved & 1) kr_regions<ACC_SMEM_CAS, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // plain REDs
-            else if (h->kl_block <= 512) kr_regions<ACC_GLOBAL, 512><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
+            else if (h->kl_block <= 512) launch_dep(kr_regions<ACC_GLOBAL, 512>, dim3(h->kl_grid), dim3(h->kl_block), h->kl_smem, st, h->pdl_now, P);
             else if (h->kl_block <= 768) kr_regions<ACC_GLOBAL, 768><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
             else kr_regions<ACC_GLOBAL, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
             h->launches++;
@@ -778,7 +793,7 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
     O.fx_scale = (mode == MODE_STRUCT) ? 1.0 : std::ldexp(1.0, (int)h->fx_log2);
     O.ll_scale = std::ldexp(1.0, (int)h->ll_log2);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (h->timing && mode == MODE_EVAL) {
+    if (h->timing && h->timing_detail && mode == MODE_EVAL) {
         if (h->kev_used == h->kev.size() && h->kev.size() < 8192) {
             cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); h->kev.push_back({a, b});
         }
@@ -787,6 +802,8 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
     }
     if (e0) cudaEventRecord(e0, st);
     h->lean_now = lean6;
+    // dependent launches only when no event sits between the kernels (an event record serialises the stream)
+    h->pdl_now = lean6 && !e0 && h->pdl;
     launch_main(h, kernel, mode, CorpusD{h->d_tokens.p, h->d_offs.p, h->d_p.p, d_order, n_order}, O);
     if (kernel2) launch_main(h, kernel2, mode, CorpusD{h->d_tokens.p, h->d_offs.p, h->d_p.p, d_order2, n_order2}, O);
     if (e1) cudaEventRecord(e1, st);
@@ -808,13 +825,13 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
             Q.ll_off = h->peer_ll_off; Q.nranks = h->nranks; Q.rank = h->rank; Q.words = words;
             ++h->peer_ll_epoch;
             Q.flag = (unsigned int)(h->peer_ll_epoch % 0xfffffffeull) + 1u; Q.parity = (int)(h->peer_ll_epoch & 1ull);
-            k_fold_allreduce_finish6<<<grid_f, 256, 0, st>>>(Q);
+            launch_dep(k_fold_allreduce_finish6, dim3(grid_f), dim3(256), 0, st, h->pdl_now, Q);
             h->launches++;
             CK(cudaGetLastError());
             h->lean_finished = true;
             return WFSA_OK;
         }
-        k_fold_finish6<<<(std::max(h->n_edges, 1) + 7) / 8, 256, 0, st>>>(P);      // one warp per edge
+        launch_dep(k_fold_finish6, dim3((std::max(h->n_edges, 1) + 7) / 8), dim3(256), 0, st, h->pdl_now, P);      // one warp per edge
         h->launches++;
         CK(cudaGetLastError());
         h->lean_finished = !h->comm;
@@ -981,6 +998,7 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
         CK(h->d_krwords.upload(sc.rwords, h->stream)); CK(h->d_krgoff.upload(sc.rgoff, h->stream));
         CK(h->d_krgrows.upload(sc.rgrows, h->stream)); CK(h->d_krW.upload(sc.typeW, h->stream));
         h->pull = getenv("WFSA_PULL") != nullptr;        // off by default: measured slower
+        h->pdl = getenv("WFSA_NO_PDL") == nullptr;       // programmatic dependent launches between the three kernels of an evaluation
         h->n_pchunks = (int64_t)sc.pcarc.size();
         CK(h->d_pv.alloc(std::max<size_t>((size_t)sc.n_pv, 1))); CK(h->d_pvoff.upload(sc.pvoff, h->stream));
         CK(h->d_pcoff.upload(sc.pcoff, h->stream)); CK(h->d_pidx.upload(sc.pidx, h->stream)); CK(h->d_pcarc.upload(sc.pcarc, h->stream));
@@ -1348,9 +1366,18 @@ extern "C" int wfsa_dev_allreduce_f64(wfsa_dev* h, double* values, int n, int op
 extern "C" int wfsa_dev_timer_begin(wfsa_dev* h)
 {
     if (!h) return WFSA_ERR_INVALID;
-    h->timing = true; h->kev_used = 0; h->sev_used = 0;
+    h->timing = true; h->kev_used = 0; h->sev_used = 0; h->timing_detail = true;
     CK(cudaEventRecord(h->ev_begin, h->stream));
     return WFSA_OK;
+}
+
+// Like timer_begin, but only the event pair around each whole evaluation is recorded: no events between the kernels
+// of an evaluation, so they keep their dependent launches (timer_kernel_ms / split / phase then report nothing).
+extern "C" int wfsa_dev_timer_begin_steps(wfsa_dev* h)
+{
+    const int rc = wfsa_dev_timer_begin(h);
+    if (rc == WFSA_OK) h->timing_detail = false;
+    return rc;
 }
 
 extern "C" int wfsa_dev_timer_end(wfsa_dev* h, float* ms)
