@@ -250,6 +250,8 @@ def test_segmented_objective_without_per_string_pass(medium):
     r = rec.astype(bool)
     p = low.p[:len(rec)]
     rng = np.random.RandomState(3)
+    with pytest.raises(W.WfsaError):                    # nothing has been evaluated for this parameter map yet
+        dev.eval_fetch()
     for x in (rng.normal(-1.0, 0.5, size=n), rng.normal(-12.0, 3.0, size=n)):
         dev.upload_x(x)
         dev.eval_launch()

@@ -176,6 +176,7 @@ struct wfsa_dev {
     DevBuf<long long> d_llpart;             // bridge part of the log-likelihood: per-CTA partials of the weight kernel
     int llpart_n = 0;
     bool pdl = true, pdl_now = false, timing_detail = true;     // programmatic dependent launches on the lean segmented path
+    bool evaluated = false;                 // an evaluation has been launched since set_param_map
     bool ks_done = false;                   // ks_strings has run for the last evaluation (it runs on demand)
     DevBuf<long long> d_pv; DevBuf<int64_t> d_pvoff, d_pcoff; DevBuf<int32_t> d_pidx, d_pcarc; int64_t n_pchunks = 0; bool pull = false;
 };
@@ -1058,6 +1059,7 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
         CK(h->d_out.alloc((size_t)n + 2));
     }
     h->n = n;
+    h->evaluated = false;
     CK(cudaStreamSynchronize(h->stream));
     if (h->comm) { const int rc = setup_peer_allreduce(h); if (rc != WFSA_OK) return rc; }
     return WFSA_OK;
@@ -1163,6 +1165,7 @@ extern "C" int wfsa_dev_eval_launch(wfsa_dev* h)
     }
     const int rc = eval_launch_body(h);
     if (s1) cudaEventRecord(s1, h->stream);
+    if (rc == WFSA_OK) h->evaluated = true;
     return rc;
 }
 
@@ -1207,6 +1210,7 @@ extern "C" int wfsa_dev_eval_fetch(wfsa_dev* h, double* loglik, double* logq, do
 {
     if (!h) return WFSA_ERR_INVALID;
     if (h->n < 0) return set_err(h, WFSA_ERR_STATE, "fetch before set_param_map");
+    if (!h->evaluated) return set_err(h, WFSA_ERR_STATE, "fetch before an evaluation was launched for this parameter map");
     CK(cudaMemcpyAsync(h->h_out, h->d_out.p, ((size_t)h->n + 2) * 8, cudaMemcpyDeviceToHost, h->stream));
     if (logq && h->kernel == 6 && h->ks_groups > 0) {
         if (!h->ks_done) {                       // per-string log q of the segmented path, from the lq of the last evaluation
