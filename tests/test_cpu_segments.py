@@ -178,6 +178,17 @@ def check(low, trimmed, x, n_slots=16):
         assert abs(v - olq[s]) <= 1e-12 * max(1.0, abs(olq[s])), (s, v, olq[s])
     st = seg["stats"]
     assert st[0] == np.count_nonzero(seg["typeW"]) and st[5] == len(handled) and st[0] <= st[1]
+    # The objective without a per-string pass (kr_regions + the bridge partials of k_prep6):
+    #   sum_s p_s log q_s = sum_arc c[arc] * log w[arc] + sum_types W_type * lq_type,  c = const_acc / fx_scale
+    c = seg["const_acc"].astype(np.float64) / FX
+    with np.errstate(divide="ignore"):
+        ll_bridges = float(sum(c[a] * np.log(aw[a]) for a in np.nonzero(c)[0]))
+    Wt = seg["typeW"]
+    ll_regions = float(sum(Wt[i] * lq[i] for i in np.nonzero(Wt)[0]))
+    ll_strings = float(sum(low.p[s_] * olq[s_] for s_ in handled))
+    n_bridge_terms = max(int(st[4]), 1)                     # every bridge adds p_s rounded to the 2^-40 quantum of the test
+    assert abs(ll_bridges + ll_regions - ll_strings) <= 1e-11 * max(1.0, abs(ll_strings)) + n_bridge_terms * 2.0 ** -40 * 20, \
+        (ll_bridges, ll_regions, ll_strings)
     # expected edge counts of the handled strings only
     ee = np.zeros(low.n_trans + low.n_emis)
     np.add.at(ee, tid, acc)
