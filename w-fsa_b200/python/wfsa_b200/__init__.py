@@ -121,7 +121,7 @@ def lib():
         L.wfsa_dev_create.argtypes = [C.POINTER(FsaDesc), C.POINTER(CorpusDesc), C.POINTER(DevOptions), C.POINTER(C.c_void_p)]
         L.wfsa_dev_structure.argtypes = [C.c_void_p, U8P, F64P, U8P]
         L.wfsa_dev_set_param_map.argtypes = [C.c_void_p, I32P, C.c_int32, U8P]
-        L.wfsa_dev_eval.argtypes = [C.c_void_p, F64P, F64P, F64P, F64P]
+        L.wfsa_dev_eval.argtypes = [C.c_void_p, C.c_void_p, F64P, C.c_void_p, C.c_void_p]     # raw addresses: cheaper to marshal per call
         L.wfsa_dev_upload_x.argtypes = [C.c_void_p, F64P]
         L.wfsa_dev_eval_launch.argtypes = [C.c_void_p]
         L.wfsa_dev_eval_fetch.argtypes = [C.c_void_p, F64P, F64P, F64P]
@@ -335,11 +335,12 @@ class Device:
         self.n = n
 
     def eval(self, x, want_logq=True):
-        x = np.ascontiguousarray(x, dtype=np.float64)
+        if not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous):
+            x = np.ascontiguousarray(x, dtype=np.float64)
         ll = C.c_double()
-        grad = np.zeros(max(self.n, 1))
+        grad = np.empty(max(self.n, 1))
         logq = np.zeros(max(self.n_strings, 1)) if want_logq else None
-        self._ck(self.L.wfsa_dev_eval(self.h, _p(x, F64P), C.byref(ll), _p(logq, F64P), _p(grad, F64P)))
+        self._ck(self.L.wfsa_dev_eval(self.h, x.ctypes.data, C.byref(ll), logq.ctypes.data if want_logq else None, grad.ctypes.data))
         return ll.value, (logq[:self.n_strings] if want_logq else None), grad[:self.n]
 
     def upload_x(self, x):
