@@ -7,10 +7,13 @@
 // so one evaluation (Learner::ComputeModeledProbs + ComputeObjective + ComputeGrad,
 // /root/reference/src/Learner.cpp:515-553, src/QuasiNewtonLearner.cpp:93-125) becomes
 //   KR  kr_regions : forward-backward over every distinct region TYPE once (thread per type):
-//                    lq[type] = log q_type,  acc[arc] += W_type * posterior   (64-bit fixed-point REDs)
+//                    lq[type] = log q_type,  acc[arc] += W_type * posterior   (64-bit fixed-point REDs),
+//                    loglik += W_type * lq[type]
+// The bridges need no per-string work: with c[arc] = sum_s p_s * (times arc is a bridge of s), computed when the
+// lattices are compiled, their part of the gradient is the constant c and their part of the log-likelihood is
+// sum_arc c[arc] * log w[arc] (k_prep6).  Only a caller that wants log q_s of every string runs
 //   KS  ks_strings : thread per string: log q_s = sum of log w over its bridge arcs (16-bit ids, table in
-//                    shared memory) + sum of lq[type] over its regions; loglik += p_s log q_s
-// and the bridges' part of the gradient is a constant computed when the lattices are compiled.
+//                    shared memory) + sum of lq[type] over its regions.
 #pragma once
 #include "kernels.cuh"
 
@@ -362,7 +365,7 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
 // paths that contain arc pcarc[c] into that arc's accumulator -- one warp per chunk (at most kPullChunk entries:
 // coalesced index reads, gathers from the L2-resident pv, integer shuffle sum, ONE RED).  It replaces one RED per
 // (type, path, edge) -- 7 M per evaluation for config 4, issued at the LSU lane rate inside the latency-bound region
-// kernel -- and runs on the side stream next to ks_strings.
+// kernel.  Measured slower than the REDs; kept behind WFSA_PULL=1.
 __global__ void __launch_bounds__(256) k_pull_paths(long long n_chunks, const int64_t* __restrict__ pcoff, const int32_t* __restrict__ pcarc,
                                                     const int32_t* __restrict__ pidx, const long long* __restrict__ pv,
                                                     unsigned long long* acc)
@@ -393,15 +396,7 @@ struct KSParams {
     double* logq;                         // [n_sgroups*16*32] log q_s in group order
     long long n_sgroups;
     unsigned int* counter;
-    unsigned long long* red;              // red[0] fixed-point loglik, red[1] non-finite strings
-    double ll_scale;
     int n_arcs;
-    // single-GPU finish of [loglik, bad] by the last CTA (the gradient part is folded by k_fold_finish6, which runs
-    // next to this kernel on a second stream: it only depends on the region kernel)
-    int finish_ll;
-    double inv_ll;
-    double* out;
-    unsigned int* done;                   // CTAs that have finished; the last one resets it
 };
 
 // KS: one CTA of 16 warps per super-group of 16 groups, one warp per group, one thread per string.
@@ -423,8 +418,6 @@ __global__ void __launch_bounds__(kKsWarps * 32, 2) ks_strings(const KSParams P)
     for (int i = tid; i < P.n_arcs + 16; i += kKsWarps * 32) tab[i] = i < P.n_arcs ? P.logaw[i] : 0.0;
     if (tid == 0) s_next[0] = (long long)atomicAdd(P.counter, 1u);
     __syncthreads();
-    long long ll_fx = 0;
-    unsigned long long bad = 0;
     int par = 0;
     for (long long sg = s_next[0]; sg < P.n_sgroups;) {
         if (tid == 0) s_next[par ^ 1] = (long long)atomicAdd(P.counter, 1u);   // the next super-group, fetched early
@@ -464,32 +457,10 @@ __global__ void __launch_bounds__(kKsWarps * 32, 2) ks_strings(const KSParams P)
             }
         }
         const double lqs = (s0 + s1) + (r + ((v0 + v1) + (v2 + v3)));
-        if (ps != 0.0) {
-            P.logq[g * 32 + lane] = lqs;
-            if (isfinite(lqs)) ll_fx += __double2ll_rn(ps * lqs * P.ll_scale);
-            else bad++;
-        }
+        if (ps != 0.0) P.logq[g * 32 + lane] = lqs;
         __syncthreads();
         par ^= 1;
         sg = s_next[par];
-    }
-    for (int o = 16; o; o >>= 1) { ll_fx += __shfl_xor_sync(FULL, ll_fx, o); bad += __shfl_xor_sync(FULL, bad, o); }
-    if (lane == 0 && P.red) {                                  // red == nullptr: per-string log q only (the usual case)
-        if (ll_fx) atomicAdd(P.red, (unsigned long long)ll_fx);
-        if (bad) atomicAdd(P.red + 1, bad);
-    }
-    if (P.finish_ll) {                                         // the last CTA to finish writes [loglik, bad]
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            if (atomicAdd(P.done, 1u) == gridDim.x - 1) {
-                __threadfence();
-                const unsigned long long r0 = atomicAdd(P.red, 0ull), r1 = atomicAdd(P.red + 1, 0ull);
-                P.out[0] = r1 > 0 ? -INFINITY : (double)(long long)r0 * P.inv_ll;
-                P.out[1] = (double)r1;
-                *P.done = 0u;
-            }
-        }
     }
 }
 

@@ -170,7 +170,6 @@ struct wfsa_dev {
     size_t kev_used = 0; bool timing = false;
     std::vector<cudaEvent_t> kev_mid;           // segmented path: between kr_regions and ks_strings
     cudaEvent_t mid_now = nullptr;
-    DevBuf<unsigned int> d_done;
     DevBuf<unsigned char> d_flush; int flush_byte = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sev; size_t sev_used = 0;      // per-evaluation event pairs (timer)
     DevBuf<long long> d_llpart;             // bridge part of the log-likelihood: per-CTA partials of the weight kernel
@@ -240,7 +239,7 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     if (h->ev_end) cudaEventDestroy(h->ev_end);
     for (auto& e : h->kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto& e : h->kev_mid) cudaEventDestroy(e);
-    h->d_done.release(); h->d_llpart.release(); h->d_flush.release();
+    h->d_llpart.release(); h->d_flush.release();
     for (auto& e : h->sev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } h->d_pv.release(); h->d_pvoff.release(); h->d_pcoff.release(); h->d_pidx.release(); h->d_pcarc.release();
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -374,8 +373,6 @@ static int setup_kl(wfsa_dev* h)
     CK(h->d_klaw.alloc(A.n_arcs)); CK(h->d_klacc.alloc((size_t)A.n_arcs * h->replicas)); CK(h->d_klconst.alloc(A.n_arcs));
     CK(h->d_klcounter.alloc(2));
     CK(h->d_llpart.alloc(2 * (size_t)((std::max(h->larcs.n_arcs, 1) + 255) / 256)));
-    CK(h->d_done.alloc(1));
-    CK(cudaMemsetAsync(h->d_done.p, 0, 4, h->stream));      // every finishing ks_strings launch counts it up to the grid size and resets it
     if (h->kernel == 6) {
         CK(h->d_klogaw.alloc(A.n_arcs));
         {   // arcs of every edge (transition edges, then emission edges) for the gather in k_fold_finish6
@@ -1216,8 +1213,8 @@ extern "C" int wfsa_dev_eval_fetch(wfsa_dev* h, double* loglik, double* logq, do
         if (!h->ks_done) {                       // per-string log q of the segmented path, from the lq of the last evaluation
             KSParams S{};
             S.logaw = h->d_klogaw.p; S.words = h->d_kswords.p; S.sgoff = h->d_ksgoff.p; S.gref = h->d_ksgref.p; S.lq = h->d_krlq.p;
-            S.p = h->d_ksp.p; S.logq = h->d_kslogq.p; S.n_sgroups = h->ks_groups; S.counter = h->d_klcounter.p + 1; S.red = nullptr;
-            S.ll_scale = 1.0; S.n_arcs = h->larcs.n_arcs; S.finish_ll = 0; S.inv_ll = 1.0; S.out = h->d_out.p; S.done = h->d_done.p;
+            S.p = h->d_ksp.p; S.logq = h->d_kslogq.p; S.n_sgroups = h->ks_groups; S.counter = h->d_klcounter.p + 1;
+            S.n_arcs = h->larcs.n_arcs;
             CK(cudaMemsetAsync(h->d_klcounter.p + 1, 0, 4, h->stream));
             ks_strings<<<h->ks_grid, h->ks_block, h->ks_smem, h->stream>>>(S);
             h->launches++;
