@@ -69,7 +69,7 @@ typedef struct {
     int32_t device;              /* CUDA device ordinal                                       */
     int32_t force_kernel;        /* 0 auto, 1 warp-per-string, 2 CTA-per-string, 3 generic,
                                     4 thread-per-string (table walk), 5 thread-per-string (compiled lattices),
-                                    6 segmented compiled lattices (region types + per-string sums) */
+                                    6 segmented compiled lattices (bridges folded into constants + region types) */
     int32_t accum_mode;          /* 0 auto, 1 shared-memory accumulators, 2 global (L2) REDs  */
     int32_t reserved;
 } wfsa_dev_options;
@@ -100,7 +100,10 @@ int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32_t n, const
  * src/HessianLearner.cpp:565-597):
  *   loglik = sum_s p_s log q_s   (KL = plogp - loglik),   grad_i = -sum_s p_s E_s[count_i].
  * With a communicator attached both are the sums over ALL ranks.  logq (may be NULL) receives
- * log q_s of this shard's strings, -inf/NaN-free only for recognised strings (others: -inf). */
+ * log q_s of this shard's strings, -inf/NaN-free only for recognised strings (others: -inf).
+ * logq is the reference's protected intermediate (inc/Learner.h:95), not needed for the objective or the
+ * gradient: with NULL the segmented path skips its per-string pass altogether (it runs on demand, also from a
+ * later wfsa_dev_eval_fetch with a logq buffer, for the evaluation launched last). */
 int wfsa_dev_eval(wfsa_dev* h, const double* x, double* loglik, double* logq, double* grad);
 
 /* Same evaluation with x already resident (last uploaded x); results stay on the device.
@@ -126,8 +129,9 @@ typedef struct {
 int wfsa_dev_set_path_blocks(wfsa_dev* h, const wfsa_path_blocks* blocks);
 int wfsa_dev_hessian(wfsa_dev* h, const double* x, double* Hf /* n*n */, double* rmin /* or NULL */);
 
-/* Multi-GPU: one handle per process/GPU; results of eval/structure/hessian are all-reduced
- * (ncclAllReduce, exact integer sums, so any rank count gives bitwise identical results). */
+/* Multi-GPU: one handle per process/GPU; results of eval/structure/hessian are all-reduced as exact integer
+ * sums, so every rank holds the same bits (the evaluation through an all-reduce over NVLink peer memory fused
+ * into its last kernel, with ncclAllReduce as the fall-back; structure and hessian through ncclAllReduce). */
 #define WFSA_UNIQUE_ID_BYTES 128
 int wfsa_dev_comm_unique_id(void* id_out /* WFSA_UNIQUE_ID_BYTES */);
 int wfsa_dev_comm_init(wfsa_dev* h, const void* id, int rank, int nranks);

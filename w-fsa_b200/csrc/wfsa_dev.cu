@@ -168,7 +168,7 @@ struct wfsa_dev {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kev;
     size_t kev_used = 0; bool timing = false;
-    std::vector<cudaEvent_t> kev_mid;           // segmented path: between kr_regions and ks_strings
+    std::vector<cudaEvent_t> kev_mid;           // segmented path: behind kr_regions (what follows inside the bracket: overflow strings)
     cudaEvent_t mid_now = nullptr;
     DevBuf<unsigned char> d_flush; int flush_byte = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sev; size_t sev_used = 0;      // per-evaluation event pairs (timer)
@@ -735,7 +735,7 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
     const HostFsa& F = h->fsa;
     cudaStream_t st = h->stream;
     const int unit = (mode == MODE_STRUCT) ? 1 : 0;
-    // segmented path without overflow strings: one prep launch, KR, KS, one fold(+finish) launch
+    // segmented path without overflow strings: one prep launch, KR, one fold(+all-reduce)+finish launch
     const bool lean6 = kernel == 6 && mode == MODE_EVAL && clear && fold && (kernel2 == 0 || n_order2 == 0);
     if (lean6) {
         Prep6Params P{};
