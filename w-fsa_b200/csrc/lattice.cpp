@@ -540,6 +540,13 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
                               double fx_scale, SegmentedCorpus& out)
 {
     const auto t_begin = std::chrono::steady_clock::now();
+    const bool report = getenv("WFSA_COMPILE_TIMES") != nullptr;        // phase times of this function to stderr
+    auto t_last = t_begin;
+    auto lap = [&](const char* what) {
+        const auto now = std::chrono::steady_clock::now();
+        if (report) fprintf(stderr, "[segmented compile] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     out = SegmentedCorpus();
     const size_t n = ids.size();
     out.const_acc.assign(A.n_arcs, 0);
@@ -589,6 +596,7 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
     }
     for (int t = 0; t < T; ++t)
         for (int a = 0; a < A.n_arcs; ++a) out.const_acc[a] += loc[t].cacc[a];
+    lap("per-string compilation");
     // ---- 2. merge identical regions into types, strings visited in `ids` order (deterministic weights)
     struct Type { int t; int64_t beg; int32_t len; double W; };
     std::vector<Type> types;
@@ -630,6 +638,7 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
     }
     out.n_strings = (int64_t)ok.size();
     out.n_types = (int64_t)types.size();
+    lap("type merging");
     // ---- 3. KR layout: types by class, sorted by content.  Class key (descending = roughly by cost):
     //   DAG form, big   : 3<<24 | rows          rows = padded stream length (multiple of 16), groups may mix rows
     //   DAG form, small : 2<<24 | rows          rows = 4, 8, 12, 16 bare edge words
@@ -699,6 +708,7 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
         }
         out.typeW[slot] = Y.W;
     }
+    lap("region layout");
     // ---- 3b. pull form: where every arc finds the path values it has to add up
     {
         out.pvoff.assign((size_t)n_rg, -1);
@@ -730,6 +740,7 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
                 out.pcoff.push_back(std::min(cnt[a + 1], b + kPullChunk));
             }
     }
+    lap("pull-form CSR");
     // ---- 4. KS layout: strings by bridge count, longest first; the bridges of the 16 strings of a half-warp are
     //         scheduled so that the 16 table reads of one shared-memory phase fall into 16 different bank pairs
     const int32_t dummy_type = (int32_t)(n_rg * 32);
@@ -775,6 +786,7 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
         schedule(0);
         for (auto& x : th) x.join();
     }
+    lap("bridge scheduling");
     // super-groups of kKsSuper groups (the warps of one CTA), chunk-interleaved:
     //   word (sg, chunk c, group-in-super w, row j, lane l) at sgoff[sg] + (((c*kKsSuper + w)*kKsChunkRows + j)*32 + l
     // so that the warps of a CTA, walking their groups chunk by chunk, read one contiguous region together
@@ -835,6 +847,7 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
         fill(0);
         for (auto& x : th) x.join();
     }
+    lap("per-string layout fill");
     out.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
 }
 
