@@ -171,6 +171,7 @@ struct wfsa_dev {
     std::vector<cudaEvent_t> kev_mid;           // segmented path: behind kr_regions (what follows inside the bracket: overflow strings)
     cudaEvent_t mid_now = nullptr;
     DevBuf<unsigned char> d_flush; int flush_byte = 0;
+    DevBuf<unsigned long long> d_bar;          // rank barrier without peer memory: a one-word ncclAllReduce
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sev; size_t sev_used = 0;      // per-evaluation event pairs (timer)
     DevBuf<long long> d_llpart;             // bridge part of the log-likelihood: per-CTA partials of the weight kernel
     int llpart_n = 0;
@@ -239,7 +240,7 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     if (h->ev_end) cudaEventDestroy(h->ev_end);
     for (auto& e : h->kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto& e : h->kev_mid) cudaEventDestroy(e);
-    h->d_llpart.release(); h->d_flush.release();
+    h->d_llpart.release(); h->d_flush.release(); h->d_bar.release();
     for (auto& e : h->sev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } h->d_pv.release(); h->d_pvoff.release(); h->d_pcoff.release(); h->d_pidx.release(); h->d_pcarc.release();
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1470,8 +1471,8 @@ extern "C" int wfsa_dev_rank_barrier(wfsa_dev* h)
         CK(cudaGetLastError());
         return WFSA_OK;
     }
-    if (!h->d_flush.p) CK(h->d_flush.alloc(64));
-    return nccl_allreduce(h, h->d_flush.p, 1, ncclUint64, ncclSum);
+    if (!h->d_bar.p) { CK(h->d_bar.alloc(1)); CK(cudaMemsetAsync(h->d_bar.p, 0, 8, h->stream)); }
+    return nccl_allreduce(h, h->d_bar.p, 1, ncclUint64, ncclSum);
 }
 
 extern "C" int wfsa_dev_timer_split_ms(wfsa_dev* h, float* first_ms, float* second_ms)
