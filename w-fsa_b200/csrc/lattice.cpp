@@ -535,9 +535,46 @@ struct BridgeScheduler {
     }
 };
 
+namespace {
+// what one compile thread produced for its strings (strings i = t, t+T, ... on thread t)
+struct SegLocal {
+    std::vector<uint16_t> bridges; std::vector<int64_t> boff;      // bridges of string j at [boff[j], boff[j+1])
+    std::vector<uint32_t> rwords;                                   // region words
+    std::vector<int64_t> rbeg; std::vector<int32_t> rlen;           // per region
+    std::vector<uint64_t> rhash;
+    std::vector<int64_t> sreg;                                      // regions of string j at [sreg[j], sreg[j+1])
+    std::vector<int8_t> status;
+    std::vector<long long> cacc;
+};
+}  // namespace
+
+// Everything the per-string layout (phase 4) needs from the region phases; kept alive by the job object so that the
+// layout can be built later, on another thread, or not at all.
+struct SegmentedStringsJob::State {
+    std::vector<SegLocal> loc;
+    int T = 1, n_arcs = 0;
+    std::vector<int64_t> ok;
+    std::vector<std::vector<int32_t>> reg_type;
+    std::vector<int32_t> type_slot;
+    int64_t n_rg = 0;
+    std::vector<int32_t> ids;
+    const double* p = nullptr;
+};
+SegmentedStringsJob::SegmentedStringsJob() : st(new State) {}
+SegmentedStringsJob::~SegmentedStringsJob() { delete st; }
+
 void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint8_t* alive, const int32_t* tokens,
                               const int64_t* offs, const double* p, const std::vector<int32_t>& ids, int n_slots,
                               double fx_scale, SegmentedCorpus& out)
+{
+    std::shared_ptr<SegmentedStringsJob> job = compile_corpus_regions(f, A, alive, tokens, offs, p, ids, n_slots, fx_scale, out);
+    job->run(out);
+}
+
+std::shared_ptr<SegmentedStringsJob> compile_corpus_regions(const HostFsa& f, const LatticeArcs& A, const uint8_t* alive,
+                                                            const int32_t* tokens, const int64_t* offs, const double* p,
+                                                            const std::vector<int32_t>& ids, int n_slots, double fx_scale,
+                                                            SegmentedCorpus& out)
 {
     const auto t_begin = std::chrono::steady_clock::now();
     const bool report = getenv("WFSA_COMPILE_TIMES") != nullptr;        // phase times of this function to stderr
@@ -553,15 +590,7 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
     unsigned hw = std::thread::hardware_concurrency();
     const int T = (int)std::max<size_t>(1, std::min<size_t>({(size_t)(hw ? hw : 4), (size_t)64, n / 256 + 1}));
     // ---- 1. per-string compilation, strings i = t, t+T, ... on thread t
-    struct Local {
-        std::vector<uint16_t> bridges; std::vector<int64_t> boff;      // bridges of string j at [boff[j], boff[j+1])
-        std::vector<uint32_t> rwords;                                   // region words
-        std::vector<int64_t> rbeg; std::vector<int32_t> rlen;           // per region
-        std::vector<uint64_t> rhash;
-        std::vector<int64_t> sreg;                                      // regions of string j at [sreg[j], sreg[j+1])
-        std::vector<int8_t> status;
-        std::vector<long long> cacc;
-    };
+    using Local = SegLocal;
     std::vector<Local> loc(T);
     auto work = [&](int t) {
         Local& L = loc[t];
@@ -741,8 +770,36 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
             }
     }
     lap("pull-form CSR");
-    // ---- 4. KS layout: strings by bridge count, longest first; the bridges of the 16 strings of a half-warp are
-    //         scheduled so that the 16 table reads of one shared-memory phase fall into 16 different bank pairs
+    out.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    auto job = std::make_shared<SegmentedStringsJob>();
+    SegmentedStringsJob::State& S = *job->st;
+    S.loc = std::move(loc); S.T = T; S.n_arcs = A.n_arcs; S.ok = std::move(ok); S.reg_type = std::move(reg_type);
+    S.type_slot = std::move(type_slot); S.n_rg = n_rg; S.ids = ids; S.p = p;
+    return job;
+}
+
+// ---- 4. KS layout: strings by bridge count, longest first; the bridges of the 16 strings of a half-warp are
+//         scheduled so that the 16 table reads of one shared-memory phase fall into 16 different bank pairs
+void SegmentedStringsJob::run(SegmentedCorpus& out)
+{
+    const auto t_begin = std::chrono::steady_clock::now();
+    const bool report = getenv("WFSA_COMPILE_TIMES") != nullptr;
+    auto t_last = t_begin;
+    auto lap = [&](const char* what) {
+        const auto now = std::chrono::steady_clock::now();
+        if (report) fprintf(stderr, "[segmented compile] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
+    using Local = SegLocal;
+    std::vector<Local>& loc = st->loc;
+    const int T = st->T;
+    std::vector<int64_t>& ok = st->ok;
+    const std::vector<std::vector<int32_t>>& reg_type = st->reg_type;
+    const std::vector<int32_t>& type_slot = st->type_slot;
+    const int64_t n_rg = st->n_rg;
+    const std::vector<int32_t>& ids = st->ids;
+    const double* p = st->p;
+    const struct { int n_arcs; } A = {st->n_arcs};
     const int32_t dummy_type = (int32_t)(n_rg * 32);
     auto nbr = [&](int64_t i) { const Local& L = loc[i % T]; return (int)(L.boff[i / T + 1] - L.boff[i / T]); };
     auto nref = [&](int64_t i) { const Local& L = loc[i % T]; return (int)(L.sreg[i / T + 1] - L.sreg[i / T]); };
@@ -848,7 +905,7 @@ void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint
         for (auto& x : th) x.join();
     }
     lap("per-string layout fill");
-    out.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    out.host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
 }
 
 }  // namespace wfsa

@@ -28,6 +28,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <memory>
 #include <vector>
 #include "layout.hpp"
 
@@ -156,5 +157,23 @@ struct SegmentedCorpus {
 void compile_corpus_segmented(const HostFsa& f, const LatticeArcs& A, const uint8_t* arc_alive, const int32_t* tokens,
                               const int64_t* offs, const double* p, const std::vector<int32_t>& ids, int n_slots,
                               double fx_scale, SegmentedCorpus& out);
+
+// The same in two steps.  compile_corpus_regions fills everything an objective+gradient evaluation needs (region types,
+// constants, overflow/rejected lists, statistics) and returns a job that builds the per-string layout (swords, sgoff,
+// sgref, ksid, kp: only read when log q of every string is asked for) when run() is called -- later, on another thread,
+// or never.  `p` must stay valid until then; `out` of run() may be another object than the one of the first step.
+struct SegmentedStringsJob {
+    struct State;
+    State* st;
+    SegmentedStringsJob();
+    ~SegmentedStringsJob();
+    SegmentedStringsJob(const SegmentedStringsJob&) = delete;
+    SegmentedStringsJob& operator=(const SegmentedStringsJob&) = delete;
+    void run(SegmentedCorpus& out);
+};
+std::shared_ptr<SegmentedStringsJob> compile_corpus_regions(const HostFsa& f, const LatticeArcs& A, const uint8_t* arc_alive,
+                                                            const int32_t* tokens, const int64_t* offs, const double* p,
+                                                            const std::vector<int32_t>& ids, int n_slots, double fx_scale,
+                                                            SegmentedCorpus& out);
 
 }  // namespace wfsa

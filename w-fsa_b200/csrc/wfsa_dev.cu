@@ -15,7 +15,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/wfsa_dev.h"
@@ -133,6 +135,12 @@ struct wfsa_dev {
     int64_t kr_groups = 0, ks_groups = 0, seg_types = 0, seg_instances = 0, seg_region_edges = 0, seg_type_edges = 0,
             seg_bridges = 0, seg_words = 0;
     double seg_host_ms = 0;
+    // the per-string layout of the segmented path (only ks_strings reads it) is built on a background thread started by
+    // set_param_map and uploaded by ensure_ks() when log q of every string is asked for the first time
+    std::thread ks_thread;
+    std::shared_ptr<SegmentedStringsJob> ks_job;
+    std::unique_ptr<SegmentedCorpus> ks_sc;
+    bool ks_failed = false;
     DevBuf<uint32_t> d_krwords, d_kswords;
     DevBuf<int64_t> d_krgoff, d_ksgoff;
     DevBuf<int32_t> d_krgrows, d_ksgref, d_kssid, d_eoff, d_earc;
@@ -208,6 +216,7 @@ extern "C" const char* wfsa_dev_last_error(const wfsa_dev* h) { return h ? h->er
 extern "C" void wfsa_dev_destroy(wfsa_dev* h)
 {
     if (!h) return;
+    if (h->ks_thread.joinable()) h->ks_thread.join();
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (int r = 0; r < 8; ++r) if (h->peer_ptrs[r] && r != h->rank) cudaIpcCloseMemHandle(h->peer_ptrs[r]);
@@ -974,9 +983,20 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
         std::vector<uint8_t> alive((size_t)A.n_arcs);
         for (int a = 0; a < A.n_arcs; ++a)
             alive[a] = ttp[A.arc_tid[a]] != -2 && (A.arc_eid[a] < 0 || etp[A.arc_eid[a]] != -2);
+        if (h->ks_thread.joinable()) h->ks_thread.join();       // the layout job of a previous parameter map
+        h->ks_job.reset(); h->ks_sc.reset(); h->ks_failed = false;
         SegmentedCorpus sc;
-        compile_corpus_segmented(h->fsa, A, alive.data(), h->h_tokens.data(), h->h_offs.data(), h->h_p.data(), order, h->kl_K,
-                                 std::ldexp(1.0, (int)h->fx_log2), sc);
+        h->ks_job = compile_corpus_regions(h->fsa, A, alive.data(), h->h_tokens.data(), h->h_offs.data(), h->h_p.data(), order, h->kl_K,
+                                           std::ldexp(1.0, (int)h->fx_log2), sc);
+        h->ks_sc.reset(new SegmentedCorpus());
+        {
+            std::shared_ptr<SegmentedStringsJob> job = h->ks_job;
+            SegmentedCorpus* dst = h->ks_sc.get();
+            bool* failed = &h->ks_failed;
+            h->ks_thread = std::thread([job, dst, failed] {
+                try { job->run(*dst); } catch (...) { *failed = true; }
+            });
+        }
         order_w = sc.overflow;
         order_w.insert(order_w.end(), sc.rejected.begin(), sc.rejected.end());
         h->n_active = (int64_t)order.size() - (int64_t)order_w.size(); h->n_active_w = (int64_t)order_w.size();
@@ -989,10 +1009,10 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
             while (stride > 1 && std::__gcd(stride, rest) != 1) --stride;
             h->kr_stride = std::max<int64_t>(stride, 1);
         }
-        h->kr_groups = (int64_t)sc.rgrows.size(); h->ks_groups = (int64_t)sc.sgoff.size() - 1;      // KS counts super-groups
+        h->kr_groups = (int64_t)sc.rgrows.size(); h->ks_groups = 0;                                 // KS: set by ensure_ks()
         h->seg_types = sc.n_types; h->seg_instances = sc.n_region_instances; h->seg_region_edges = sc.n_region_edges;
         h->seg_type_edges = sc.n_type_edges; h->seg_bridges = sc.n_bridge; h->seg_host_ms = sc.host_ms;
-        h->seg_words = (int64_t)sc.rwords.size() + (int64_t)sc.swords.size();
+        h->seg_words = (int64_t)sc.rwords.size();               // + the per-string words once they are built
         h->kl_max_words = sc.max_big_rows;
         CK(h->d_krwords.upload(sc.rwords, h->stream)); CK(h->d_krgoff.upload(sc.rgoff, h->stream));
         CK(h->d_krgrows.upload(sc.rgrows, h->stream)); CK(h->d_krW.upload(sc.typeW, h->stream));
@@ -1003,10 +1023,6 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
         CK(h->d_pcoff.upload(sc.pcoff, h->stream)); CK(h->d_pidx.upload(sc.pidx, h->stream)); CK(h->d_pcarc.upload(sc.pcarc, h->stream));
         CK(h->d_krlq.alloc((size_t)h->kr_groups * 32 + 1));
         CK(cudaMemsetAsync(h->d_krlq.p, 0, h->d_krlq.n * 8, h->stream));
-        CK(h->d_kswords.upload(sc.swords, h->stream)); CK(h->d_ksgoff.upload(sc.sgoff, h->stream));
-        CK(h->d_ksgref.upload(sc.sgref, h->stream)); CK(h->d_kssid.upload(sc.ksid, h->stream));
-        CK(h->d_ksp.upload(sc.kp, h->stream));
-        CK(h->d_kslogq.alloc(std::max<size_t>(sc.kp.size(), 1)));
         std::vector<unsigned long long> cacc(sc.const_acc.begin(), sc.const_acc.end());
         CK(cudaMemcpyAsync(h->d_klconst.p, cacc.data(), cacc.size() * 8, cudaMemcpyHostToDevice, h->stream));
         if (!order_w.empty()) CK(cudaMemcpyAsync(h->d_order_w.p, order_w.data(), order_w.size() * 4, cudaMemcpyHostToDevice, h->stream));
@@ -1204,12 +1220,33 @@ extern "C" int wfsa_dev_sync(wfsa_dev* h)
     return WFSA_OK;
 }
 
+// Waits for the per-string layout job of the current parameter map (if any) and uploads its arrays.
+static int ensure_ks(wfsa_dev* h)
+{
+    if (!h->ks_sc) return WFSA_OK;
+    CK(cudaSetDevice(h->device));
+    if (h->ks_thread.joinable()) h->ks_thread.join();
+    std::unique_ptr<SegmentedCorpus> sc = std::move(h->ks_sc);
+    h->ks_job.reset();
+    if (h->ks_failed) return set_err(h, WFSA_ERR_NOMEM, "segmented path: building the per-string layout failed");
+    CK(h->d_kswords.upload(sc->swords, h->stream)); CK(h->d_ksgoff.upload(sc->sgoff, h->stream));
+    CK(h->d_ksgref.upload(sc->sgref, h->stream)); CK(h->d_kssid.upload(sc->ksid, h->stream));
+    CK(h->d_ksp.upload(sc->kp, h->stream));
+    CK(h->d_kslogq.alloc(std::max<size_t>(sc->kp.size(), 1)));
+    CK(cudaStreamSynchronize(h->stream));                        // the host vectors go away with sc
+    h->ks_groups = (int64_t)sc->sgoff.size() - 1;               // KS counts super-groups
+    h->seg_words += (int64_t)sc->swords.size();
+    h->seg_host_ms += sc->host_ms;
+    return WFSA_OK;
+}
+
 extern "C" int wfsa_dev_eval_fetch(wfsa_dev* h, double* loglik, double* logq, double* grad)
 {
     if (!h) return WFSA_ERR_INVALID;
     if (h->n < 0) return set_err(h, WFSA_ERR_STATE, "fetch before set_param_map");
     if (!h->evaluated) return set_err(h, WFSA_ERR_STATE, "fetch before an evaluation was launched for this parameter map");
     CK(cudaMemcpyAsync(h->h_out, h->d_out.p, ((size_t)h->n + 2) * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (logq && h->kernel == 6) { const int rc = ensure_ks(h); if (rc != WFSA_OK) return rc; }
     if (logq && h->kernel == 6 && h->ks_groups > 0) {
         if (!h->ks_done) {                       // per-string log q of the segmented path, from the lq of the last evaluation
             KSParams S{};
@@ -1627,6 +1664,7 @@ extern "C" int wfsa_dev_get_info(wfsa_dev* h, wfsa_dev_info* info)
         info->n_overflow_strings = h->n_active_w; info->pool_slots = h->kl_K;
     }
     if (h->kernel == 6) {
+        { const int rc = ensure_ks(h); if (rc != WFSA_OK) return rc; }     // word counts and compile time include the per-string layout
         info->n_arcs = h->larcs.n_arcs;
         info->lattice_words = h->seg_words; info->lattice_edges = h->seg_bridges + h->seg_region_edges;
         info->lattice_bridge_edges = h->seg_bridges; info->n_overflow_strings = h->n_active_w; info->pool_slots = h->kl_K;
