@@ -60,6 +60,8 @@ void build_lattice_arcs(const HostFsa& f, const GenericLayout& g, LatticeArcs& A
         const int i = fill[key[a]]++;
         A.ent_arc[i] = a; A.ent_dst[i] = dst[a]; A.ent_eid[i] = A.arc_eid[a];
     }
+    A.ent_pack.resize(n_ent);
+    for (int i = 0; i < n_ent; ++i) A.ent_pack[i] = (uint64_t)(uint32_t)A.ent_arc[i] | (uint64_t)(uint32_t)A.ent_dst[i] << 32;
 }
 
 // Forward reachability + co-reachability of one string's lattice.  On return S.esrc/edst/earc hold every
@@ -123,6 +125,45 @@ static int build_and_trim(const HostFsa& f, const LatticeArcs& A, const uint8_t*
         }
     };
     // ---- forward reachability, nodes processed in a topological order
+    if (A.layered) {
+        // Every emission is one token long: the nodes of position pos + 1 are created, in order, while those of pos are
+        // processed, so a position is an index range of the node array (no buckets), and an entry is one packed load.
+        // Same node and edge order as the general loop below.
+        S.npos.push_back(0); S.nstate.push_back(f.start);
+        S.node_of[(size_t)f.start] = 0;
+        int lo = 0, hi = 1;
+        for (int pos = 0; pos <= len; ++pos) {
+            int32_t* next_of = pos < len ? S.node_of.data() + (size_t)(pos + 1) * NSt : nullptr;     // not touched at pos == len (c < 0)
+            const int c = pos < len ? tok[pos] : -1;
+            for (int n = lo; n < hi; ++n) {
+                const int u = S.nstate[n];
+                if (c >= 0 && c < NS) {
+                    const size_t r = (size_t)u * (NS + 1) + c;
+                    for (int i = A.row[r]; i < A.row[r + 1]; ++i) {
+                        const uint64_t pk = A.ent_pack[i];
+                        const int a = (int)(uint32_t)pk, dstate = (int)(pk >> 32);
+                        if (alive && !alive[a]) continue;
+                        int32_t& slot = next_of[dstate];
+                        if (slot < 0) {
+                            slot = (int32_t)S.npos.size();
+                            S.npos.push_back(pos + 1); S.nstate.push_back(dstate);
+                        }
+                        S.esrc.push_back(n); S.edst.push_back(slot); S.earc.push_back(a);
+                    }
+                }
+                if (pos == len && A.final_arc[u] >= 0 && (!alive || alive[A.final_arc[u]])) {
+                    if (end_node < 0) {
+                        end_node = (int)S.npos.size();
+                        S.npos.push_back(len + 1); S.nstate.push_back(f.end);
+                    }
+                    S.esrc.push_back(n); S.edst.push_back(end_node); S.earc.push_back(A.final_arc[u]);
+                }
+            }
+            lo = hi;
+            hi = (int)S.npos.size();
+            if (lo == hi) break;                                  // nothing reaches the next position
+        }
+    } else {
     get_node(0, f.start);
     for (int pos = 0; pos <= len; ++pos) {
         std::vector<int32_t>& B = S.bucket[pos];
@@ -141,10 +182,11 @@ static int build_and_trim(const HostFsa& f, const LatticeArcs& A, const uint8_t*
             }
         }
     }
+    for (int pos = 0; pos <= len; ++pos) S.bucket[pos].clear();
+    }
     const int n_nodes = (int)S.npos.size(), n_e = (int)S.esrc.size();
     // reset the scratch index for the next string
     for (int n = 0; n < n_nodes; ++n) if (S.npos[n] <= len) S.node_of[(size_t)S.npos[n] * NSt + S.nstate[n]] = -1;
-    for (int pos = 0; pos <= len; ++pos) S.bucket[pos].clear();
     if (end_node < 0) return -1;
     // ---- co-reachability (edges are ordered by source in topological order => reverse sweep)
     S.coreach.assign(n_nodes, 0);

@@ -47,6 +47,7 @@ struct LatticeArcs {
     int n_sym = 0, n_states = 0;
     std::vector<int32_t> row;                  // [n_states*(n_sym+1) + 1]
     std::vector<int32_t> ent_arc, ent_dst, ent_eid;
+    std::vector<uint64_t> ent_pack;            // ent_arc | ent_dst << 32: one load per entry in the layered fast path
     std::vector<int32_t> final_arc;            // [n_states] arc id of u -> end, or -1
     std::vector<int32_t> eps_rank;             // [n_states] position in GenericLayout::eps_order
     bool has_eps = false, layered = false;     // layered: every emission is exactly one token long
