@@ -727,14 +727,35 @@ std::shared_ptr<SegmentedStringsJob> compile_corpus_regions(const HostFsa& f, co
     auto rows_of_class = [](int c) { return (c >> 24) == 1 ? ((c >> 8) & 0xff) * (c & 0xff) : (c & 0xffffff); };
     std::vector<int32_t> order(types.size()), tcls(types.size());
     for (size_t i = 0; i < types.size(); ++i) { order[i] = (int32_t)i; tcls[i] = class_of(types[i]); }
-    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+    auto type_less = [&](int32_t a, int32_t b) {
         if (tcls[a] != tcls[b]) return tcls[a] > tcls[b];
         const Type &X = types[a], &Y = types[b];
         const uint32_t* wa = loc[X.t].rwords.data() + X.beg; const uint32_t* wb = loc[Y.t].rwords.data() + Y.beg;
         const int32_t m = std::min(X.len, Y.len);
         for (int32_t k = 0; k < m; ++k) if (wa[k] != wb[k]) return (wa[k] & 0x7fffu) != (wb[k] & 0x7fffu) ? (wa[k] & 0x7fffu) < (wb[k] & 0x7fffu) : wa[k] < wb[k];
         return X.len < Y.len;
-    });
+    };
+    {
+        // types are pairwise different, so the order is total: chunks sorted on the compile threads and merged pairwise
+        // give the same permutation as one std::sort
+        const int parts = order.size() >= 4096 ? std::min(T, 16) : 1;
+        std::vector<size_t> cut(parts + 1);
+        for (int k = 0; k <= parts; ++k) cut[k] = order.size() * (size_t)k / parts;
+        {
+            std::vector<std::thread> th;
+            for (int k = 1; k < parts; ++k) th.emplace_back([&, k] { std::sort(order.begin() + cut[k], order.begin() + cut[k + 1], type_less); });
+            std::sort(order.begin() + cut[0], order.begin() + cut[1], type_less);
+            for (auto& x : th) x.join();
+        }
+        for (int width = 1; width < parts; width *= 2) {
+            std::vector<std::thread> th;
+            for (int k = 0; k + width < parts; k += 2 * width) {
+                const size_t lo = cut[k], mid = cut[k + width], hi = cut[std::min(k + 2 * width, parts)];
+                th.emplace_back([&, lo, mid, hi] { std::inplace_merge(order.begin() + lo, order.begin() + mid, order.begin() + hi, type_less); });
+            }
+            for (auto& x : th) x.join();
+        }
+    }
     std::vector<int32_t> type_slot(types.size(), -1);                     // type -> g*32 + lane
     out.rgoff.assign(1, 0);
     {
