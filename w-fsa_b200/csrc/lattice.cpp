@@ -587,6 +587,7 @@ struct SegLocal {
     std::vector<int64_t> sreg;                                      // regions of string j at [sreg[j], sreg[j+1])
     std::vector<int8_t> status;
     std::vector<long long> cacc;
+    int64_t region_edges = 0;                                       // EDGE words over all regions of the thread's accepted strings
 };
 }  // namespace
 
@@ -652,6 +653,7 @@ std::shared_ptr<SegmentedStringsJob> compile_corpus_regions(const HostFsa& f, co
                     const int b = seg.roff[r], e = seg.roff[r + 1];
                     L.rbeg.push_back((int64_t)L.rwords.size()); L.rlen.push_back(e - b);
                     L.rhash.push_back(fnv1a(seg.rwords.data() + b, (size_t)(e - b)));
+                    for (int k = b; k < e; ++k) L.region_edges += (seg.rwords[k] >> 31);
                     L.rwords.insert(L.rwords.end(), seg.rwords.begin() + b, seg.rwords.begin() + e);
                 }
             }
@@ -704,9 +706,9 @@ std::shared_ptr<SegmentedStringsJob> compile_corpus_regions(const HostFsa& f, co
             types[ty].W += ps;
             reg_type[i % T][r] = ty;
             out.n_region_instances++;
-            for (int32_t k = 0; k < len; ++k) out.n_region_edges += (w[k] >> 31);
         }
     }
+    for (int t = 0; t < T; ++t) out.n_region_edges += loc[t].region_edges;
     out.n_strings = (int64_t)ok.size();
     out.n_types = (int64_t)types.size();
     lap("type merging");
