@@ -671,12 +671,11 @@ std::shared_ptr<SegmentedStringsJob> compile_corpus_regions(const HostFsa& f, co
         for (int a = 0; a < A.n_arcs; ++a) out.const_acc[a] += loc[t].cacc[a];
     lap("per-string compilation");
     // ---- 2. merge identical regions into types, strings visited in `ids` order (deterministic weights)
+    // Partitioned by hash: partition k (one thread) merges the regions whose hash falls into it, walking ALL accepted
+    // strings in `ids` order, so every type still sums the p_s of its instances in that order and keeps the first
+    // instance as its representative: the result does not depend on the number of threads.
     struct Type { int t; int64_t beg; int32_t len; double W; };
-    std::vector<Type> types;
-    std::vector<int32_t> bucket_head((size_t)1 << 20, -1);               // open hashing on the low hash bits
-    std::vector<int32_t> next_in_bucket;
-    std::vector<uint64_t> thash;
-    std::vector<std::vector<int32_t>> reg_type(T);                        // type of every region, per thread
+    std::vector<std::vector<int32_t>> reg_type(T);                        // type of every region, per compile thread
     for (int t = 0; t < T; ++t) reg_type[t].resize(loc[t].rbeg.size());
     std::vector<int64_t> ok;                                              // indices into ids
     for (size_t i = 0; i < n; ++i) {
@@ -686,27 +685,62 @@ std::shared_ptr<SegmentedStringsJob> compile_corpus_regions(const HostFsa& f, co
         if (st < 0) { out.overflow.push_back(ids[i]); continue; }
         if (st == 0) { out.rejected.push_back(ids[i]); continue; }
         ok.push_back((int64_t)i);
-        const double ps = p[ids[i]];
         out.n_bridge += L.boff[j + 1] - L.boff[j];
-        for (int64_t r = L.sreg[j]; r < L.sreg[j + 1]; ++r) {
-            const uint64_t h = L.rhash[r];
-            const uint32_t* w = L.rwords.data() + L.rbeg[r];
-            const int32_t len = L.rlen[r];
-            int32_t& head = bucket_head[h & (bucket_head.size() - 1)];
-            int32_t ty = head;
-            for (; ty >= 0; ty = next_in_bucket[ty]) {
-                const Type& Y = types[ty];
-                if (thash[ty] == h && Y.len == len && !std::memcmp(loc[Y.t].rwords.data() + Y.beg, w, (size_t)len * 4)) break;
+        out.n_region_instances += L.sreg[j + 1] - L.sreg[j];
+    }
+    const int K = std::max(1, std::min(T, 32));
+    auto part_of = [K](uint64_t h) { return (int)((h >> 40) % (uint64_t)K); };
+    std::vector<std::vector<Type>> ptypes(K);
+    auto merge_part = [&](int k) {
+        std::vector<Type>& types = ptypes[k];
+        std::vector<int32_t> bucket_head((size_t)1 << 18, -1);            // open hashing on the low hash bits
+        std::vector<int32_t> next_in_bucket;
+        std::vector<uint64_t> thash;
+        for (const int64_t i : ok) {
+            const Local& L = loc[i % T];
+            const size_t j = (size_t)(i / T);
+            const double ps = p[ids[i]];
+            for (int64_t r = L.sreg[j]; r < L.sreg[j + 1]; ++r) {
+                const uint64_t h = L.rhash[r];
+                if (part_of(h) != k) continue;
+                const uint32_t* w = L.rwords.data() + L.rbeg[r];
+                const int32_t len = L.rlen[r];
+                int32_t& head = bucket_head[h & (bucket_head.size() - 1)];
+                int32_t ty = head;
+                for (; ty >= 0; ty = next_in_bucket[ty]) {
+                    const Type& Y = types[ty];
+                    if (thash[ty] == h && Y.len == len && !std::memcmp(loc[Y.t].rwords.data() + Y.beg, w, (size_t)len * 4)) break;
+                }
+                if (ty < 0) {
+                    ty = (int32_t)types.size();
+                    types.push_back(Type{(int)(i % T), L.rbeg[r], len, 0.0});
+                    thash.push_back(h); next_in_bucket.push_back(head); head = ty;
+                }
+                types[ty].W += ps;
+                reg_type[i % T][r] = ty;                                  // index inside the partition; made global below
             }
-            if (ty < 0) {
-                ty = (int32_t)types.size();
-                types.push_back(Type{(int)(i % T), L.rbeg[r], len, 0.0});
-                thash.push_back(h); next_in_bucket.push_back(head); head = ty;
-            }
-            types[ty].W += ps;
-            reg_type[i % T][r] = ty;
-            out.n_region_instances++;
         }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int k = 1; k < K; ++k) th.emplace_back(merge_part, k);
+        merge_part(0);
+        for (auto& x : th) x.join();
+    }
+    std::vector<int32_t> pbase(K + 1, 0);
+    for (int k = 0; k < K; ++k) pbase[k + 1] = pbase[k] + (int32_t)ptypes[k].size();
+    std::vector<Type> types;
+    types.reserve((size_t)pbase[K]);
+    for (int k = 0; k < K; ++k) { types.insert(types.end(), ptypes[k].begin(), ptypes[k].end()); std::vector<Type>().swap(ptypes[k]); }
+    {
+        auto globalise = [&](int t) {                                     // regions of rejected strings hold a meaningless 0: harmless
+            const Local& L = loc[t];
+            for (size_t r = 0; r < reg_type[t].size(); ++r) reg_type[t][r] += pbase[part_of(L.rhash[r])];
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(globalise, t);
+        globalise(0);
+        for (auto& x : th) x.join();
     }
     for (int t = 0; t < T; ++t) out.n_region_edges += loc[t].region_edges;
     out.n_strings = (int64_t)ok.size();
