@@ -762,7 +762,16 @@ std::shared_ptr<SegmentedStringsJob> compile_corpus_regions(const HostFsa& f, co
     };
     auto rows_of_class = [](int c) { return (c >> 24) == 1 ? ((c >> 8) & 0xff) * (c & 0xff) : (c & 0xffffff); };
     std::vector<int32_t> order(types.size()), tcls(types.size());
-    for (size_t i = 0; i < types.size(); ++i) { order[i] = (int32_t)i; tcls[i] = class_of(types[i]); }
+    {
+        auto classify = [&](int t) {
+            const size_t i0 = types.size() * (size_t)t / T, i1 = types.size() * (size_t)(t + 1) / T;
+            for (size_t i = i0; i < i1; ++i) { order[i] = (int32_t)i; tcls[i] = class_of(types[i]); }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(classify, t);
+        classify(0);
+        for (auto& x : th) x.join();
+    }
     auto type_less = [&](int32_t a, int32_t b) {
         if (tcls[a] != tcls[b]) return tcls[a] > tcls[b];
         const Type &X = types[a], &Y = types[b];
@@ -814,27 +823,54 @@ std::shared_ptr<SegmentedStringsJob> compile_corpus_regions(const HostFsa& f, co
     const int64_t n_rg = (int64_t)out.rgrows.size();
     out.rwords.assign((size_t)out.rgoff[n_rg] + 32, 0u);
     out.typeW.assign((size_t)n_rg * 32, 0.0);
-    for (int64_t g = 0; g < n_rg; ++g)
-        if (out.rgrows[g] & 0x10000) {                                    // path form: every unused cell reads the zero-weight arc
-            uint32_t* dst = out.rwords.data() + out.rgoff[g];
-            const int64_t cells = out.rgoff[g + 1] - out.rgoff[g];
-            for (int64_t k = 0; k < cells; ++k) dst[k] = (uint32_t)A.n_arcs;
+    {
+        // filled on the compile threads: thread t takes a contiguous range of groups (padding cells) and of the sorted
+        // type order (words of the types: different lanes of a group never share a word)
+        std::vector<int64_t> edges_of(T, 0);
+        auto fill_regions = [&](int t) {
+            const int64_t g0 = n_rg * t / T, g1 = n_rg * (t + 1) / T;
+            for (int64_t g = g0; g < g1; ++g)
+                if (out.rgrows[g] & 0x10000) {                            // path form: every unused cell reads the zero-weight arc
+                    uint32_t* dst = out.rwords.data() + out.rgoff[g];
+                    const int64_t cells = out.rgoff[g + 1] - out.rgoff[g];
+                    for (int64_t k = 0; k < cells; ++k) dst[k] = (uint32_t)A.n_arcs;
+                }
+        };
+        auto fill_types = [&](int t) {
+            const size_t i0 = order.size() * (size_t)t / T, i1 = order.size() * (size_t)(t + 1) / T;
+            int64_t ne = 0;
+            for (size_t i = i0; i < i1; ++i) {
+                const size_t ty = (size_t)order[i];
+                const Type& Y = types[ty];
+                const int32_t slot = type_slot[ty];
+                const int64_t g = slot >> 5; const int l = slot & 31;
+                const uint32_t* w = loc[Y.t].rwords.data() + Y.beg;
+                uint32_t* dst = out.rwords.data() + out.rgoff[g] + l;
+                if (!(w[0] >> 31)) {
+                    const int P = (int)((w[0] >> 8) & 0xff), L = (int)(w[0] & 0xff), PP = pad_paths(P);
+                    for (int el = 0; el < L; ++el)
+                        for (int q = 0; q < P; ++q) dst[(size_t)(el * PP + q) * 32] = w[1 + el * P + q] & 0x7fffu;
+                    ne += (int64_t)P * L;
+                } else {
+                    for (int32_t k = 0; k < Y.len; ++k) { dst[(size_t)k * 32] = w[k]; ne += (w[k] >> 31); }
+                }
+                out.typeW[slot] = Y.W;
+            }
+            edges_of[t] = ne;
+        };
+        {
+            std::vector<std::thread> th;
+            for (int t = 1; t < T; ++t) th.emplace_back(fill_regions, t);
+            fill_regions(0);
+            for (auto& x : th) x.join();
         }
-    for (size_t ty = 0; ty < types.size(); ++ty) {
-        const Type& Y = types[ty];
-        const int32_t slot = type_slot[ty];
-        const int64_t g = slot >> 5; const int l = slot & 31;
-        const uint32_t* w = loc[Y.t].rwords.data() + Y.beg;
-        uint32_t* dst = out.rwords.data() + out.rgoff[g] + l;
-        if (!(w[0] >> 31)) {
-            const int P = (int)((w[0] >> 8) & 0xff), L = (int)(w[0] & 0xff), PP = pad_paths(P);
-            for (int el = 0; el < L; ++el)
-                for (int q = 0; q < P; ++q) dst[(size_t)(el * PP + q) * 32] = w[1 + el * P + q] & 0x7fffu;
-            out.n_type_edges += (int64_t)P * L;
-        } else {
-            for (int32_t k = 0; k < Y.len; ++k) { dst[(size_t)k * 32] = w[k]; out.n_type_edges += (w[k] >> 31); }
+        {
+            std::vector<std::thread> th;
+            for (int t = 1; t < T; ++t) th.emplace_back(fill_types, t);
+            fill_types(0);
+            for (auto& x : th) x.join();
         }
-        out.typeW[slot] = Y.W;
+        for (int t = 0; t < T; ++t) out.n_type_edges += edges_of[t];
     }
     lap("region layout");
     // ---- 3b. pull form: where every arc finds the path values it has to add up
