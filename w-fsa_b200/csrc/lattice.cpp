@@ -128,12 +128,13 @@ static int build_and_trim(const HostFsa& f, const LatticeArcs& A, const uint8_t*
     if (A.layered) {
         // Every emission is one token long: the nodes of position pos + 1 are created, in order, while those of pos are
         // processed, so a position is an index range of the node array (no buckets), and an entry is one packed load.
-        // Same node and edge order as the general loop below.
+        // Same node and edge order as the general loop below.  The state -> node index is needed for one position at
+        // a time only: it is the first n_states entries of node_of (1 KB for config 4, cache resident), cleared again
+        // after every position.
         S.npos.push_back(0); S.nstate.push_back(f.start);
-        S.node_of[(size_t)f.start] = 0;
+        int32_t* const next_of = S.node_of.data();
         int lo = 0, hi = 1;
         for (int pos = 0; pos <= len; ++pos) {
-            int32_t* next_of = pos < len ? S.node_of.data() + (size_t)(pos + 1) * NSt : nullptr;     // not touched at pos == len (c < 0)
             const int c = pos < len ? tok[pos] : -1;
             for (int n = lo; n < hi; ++n) {
                 const int u = S.nstate[n];
@@ -161,6 +162,7 @@ static int build_and_trim(const HostFsa& f, const LatticeArcs& A, const uint8_t*
             }
             lo = hi;
             hi = (int)S.npos.size();
+            for (int m = lo; m < hi; ++m) next_of[S.nstate[m]] = -1;
             if (lo == hi) break;                                  // nothing reaches the next position
         }
     } else {
@@ -183,10 +185,10 @@ static int build_and_trim(const HostFsa& f, const LatticeArcs& A, const uint8_t*
         }
     }
     for (int pos = 0; pos <= len; ++pos) S.bucket[pos].clear();
+    // reset the scratch index for the next string
+    for (size_t n = 0; n < S.npos.size(); ++n) if (S.npos[n] <= len) S.node_of[(size_t)S.npos[n] * NSt + S.nstate[n]] = -1;
     }
     const int n_nodes = (int)S.npos.size(), n_e = (int)S.esrc.size();
-    // reset the scratch index for the next string
-    for (int n = 0; n < n_nodes; ++n) if (S.npos[n] <= len) S.node_of[(size_t)S.npos[n] * NSt + S.nstate[n]] = -1;
     if (end_node < 0) return -1;
     // ---- co-reachability (edges are ordered by source in topological order => reverse sweep)
     S.coreach.assign(n_nodes, 0);
