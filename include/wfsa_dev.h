@@ -159,6 +159,9 @@ int wfsa_dev_timer_step_ms(wfsa_dev* h, float* ms, int64_t* steps);
 /* The same evaluations split into three phases (sums, ms): [0] start of the evaluation -> dominant kernel (weights,
  * resets), [1] the dominant kernel(s), [2] from there to the end (fold, collective, conversion). */
 int wfsa_dev_timer_phase_ms(wfsa_dev* h, float* out3);
+/* Segmented path, single-launch evaluation (k_eval6): nanoseconds CTA 0 spent in [arc weights, region types, grid barrier,
+ * fold + exchange + conversion] (globaltimer stamps inside the kernel), summed over the evaluations since the last reset. */
+int wfsa_dev_eval6_phases(wfsa_dev* h, double* out4, int reset);
 /* Benchmark helper: a barrier over the ranks of the communicator, executed on the evaluation stream (through peer
  * memory when the peer all-reduce is in use, else a one-word ncclAllReduce).  Collective.  No-op without a communicator. */
 int wfsa_dev_rank_barrier(wfsa_dev* h);

@@ -48,7 +48,7 @@ def region_fwdbwd(col, aw, big):
             assert w == 0, "padding must be zero"
     if not big:
         q = pool[last]
-    assert n_edges >= 2 and (big == (n_edges > 16))
+    assert n_edges >= 2
     beta = np.full(16, np.nan)
     beta[last] = 1.0
     post = {}
@@ -103,7 +103,7 @@ def interpret(seg, aw, n_arcs):
                 n_path_types += 1
             continue
         rows = desc
-        assert rows in (4, 8, 12, 16) or (rows >= 32 and rows % 16 == 0)
+        assert rows >= 16 and rows % 16 == 0       # every DAG-form region uses the stream format (CHECK every 16th word, FIN last)
         block = seg["rwords"][rgoff[g]:rgoff[g] + rows * 32].reshape(rows, 32)
         for l in range(32):
             col = block[:, l]
@@ -114,7 +114,7 @@ def interpret(seg, aw, n_arcs):
             assert key not in seen, "identical regions must be merged into one type"
             seen.add(key)
             assert W_[g * 32 + l] > 0.0
-            lq[g * 32 + l], post = region_fwdbwd(col, aw, rows > 16)
+            lq[g * 32 + l], post = region_fwdbwd(col, aw, True)
             for arc, v in post.items():
                 acc[arc] += W_[g * 32 + l] * v
             n_dag_types += 1
@@ -228,7 +228,7 @@ def test_config4_shape_bridges_regions_and_type_merging():
     seg_d, ee_d, _, _, handled_d = check(low, trimmed, x, n_slots=16 | 64)
     assert interpret.counts[0] == 0 and len(handled_d) == 600
     dag_rows = seg_d["rgrows"]
-    assert (dag_rows > 16).any() and (dag_rows <= 16).any(), "expected small and big DAG regions"
+    assert (dag_rows > 16).any() and (dag_rows <= 16).any(), "expected DAG regions of one and of several 16-word blocks"
     assert np.allclose(ee_d, oee, rtol=1e-10, atol=1e-9)
     assert np.allclose(ee, oee, rtol=1e-10, atol=1e-9)
     # a pool of 2 slots cannot hold an ambiguous region: such strings are reported, never mis-compiled

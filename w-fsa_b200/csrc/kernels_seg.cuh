@@ -48,6 +48,14 @@ struct KRParams {
     int n_llpart;
 };
 
+// 64-bit add without a return value, spelled as `red` so that ptxas emits REDG in every kernel: in a kernel that also
+// holds a grid barrier (k_eval6) it keeps atomicAdd() with an unused result as ATOMG, whose lanes travel the return path
+// (measured: 0 RED sectors in ncu, region phase 95 us instead of 55 us).
+__device__ __forceinline__ void red_add64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
 // W * log q of one region type into the thread's fixed-point sum (W = 0: a padding lane)
 __device__ __forceinline__ void kr_loglik(const KRParams& P, double W, bool ok, double lq, long long& ll)
 {
@@ -67,8 +75,8 @@ __device__ __forceinline__ void red_uniform(unsigned long long* acc_g, int key, 
     if (__all_sync(FULL, key == k0)) {
 #pragma unroll
         for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        if (lane == 0 && key >= 0 && v) atomicAdd(acc_g + key, (unsigned long long)v);
-    } else if (key >= 0 && v) atomicAdd(acc_g + key, (unsigned long long)v);
+        if (lane == 0 && key >= 0 && v) red_add64(acc_g + key, (unsigned long long)v);
+    } else if (key >= 0 && v) red_add64(acc_g + key, (unsigned long long)v);
 }
 
 // One small region per thread, NE <= 16 word rows (bare EDGE words).  The x values of the forward sweep stay in
@@ -135,7 +143,7 @@ __device__ __forceinline__ void kr_small(const KRParams& P, const double* aw, do
                 v = __double2ll_rn(xs[b * 8 + j] * bd * sc);
             }
             if (ACC == ACC_GLOBAL && b * 8 + j < 2) red_uniform(acc_g, key, v, lane);
-            else if (ACC != ACC_NONE) { if (v) atomicAdd(acc_g + key, (unsigned long long)v); }
+            else if (ACC != ACC_NONE) { if (v) red_add64(acc_g + key, (unsigned long long)v); }
         }
     }
 }
@@ -187,19 +195,20 @@ __device__ __forceinline__ void kr_paths(const KRParams& P, const double* aw, in
 #pragma unroll
         for (int p = 0; p < PP; ++p) {
             if (ACC == ACC_GLOBAL && l == 0 && p < 2) red_uniform(acc_g, v[p] ? (int)a[p] : -1, v[p], lane);
-            else if (v[p]) atomicAdd(acc_g + a[p], (unsigned long long)v[p]);
+            else if (v[p]) red_add64(acc_g + a[p], (unsigned long long)v[p]);
         }
     }
 }
 
-// One big region per thread: the KL stream loop (CHECK words rescale, x values on a per-warp stack).
-template <int ACC>
-__device__ __forceinline__ void kr_big(const KRParams& P, const double* aw, double* pool, int NT, long long g, int lane,
-                                       double* xs, unsigned long long* acc_g, long long& ll)
+// One big region per thread: the KL stream loop (CHECK words rescale, x values on a stack).  STAGED = false: words
+// streamed from HBM (wp = P.words + goff[g] + lane), stack in HBM (one slab per warp).  STAGED = true (k_eval6): the
+// caller copied the nw word rows of the group to shared memory (wp) and the stack lives there as well, so that the serial
+// chain of a region (up to ~100 dependent steps, twice) runs at shared-memory latency.
+template <int ACC, bool STAGED>
+__device__ __forceinline__ void kr_big_t(const KRParams& P, const double* aw, double* pool, int NT, long long g, int lane,
+                                         const uint32_t* wp, int nw, double* xs, unsigned long long* acc_g, long long& ll)
 {
-    const long long o = P.goff[g];
-    const int nw = (int)((P.goff[g + 1] - o) >> 5);
-    const uint32_t* wp = P.words + o + lane;
+    auto ldw = [&](int i) { return STAGED ? wp[(size_t)i * 32] : __ldcs(wp + (size_t)i * 32); };
     const double W = P.typeW[g * 32 + lane];
     pool[0] = 1.0;
     int E = 0, EQ = 0;
@@ -208,7 +217,7 @@ __device__ __forceinline__ void kr_big(const KRParams& P, const double* aw, doub
     for (int i0 = 0; i0 < nw; i0 += 8) {
         uint32_t w[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w[j] = __ldcs(wp + (size_t)(i0 + j) * 32);
+        for (int j = 0; j < 8; ++j) w[j] = ldw(i0 + j);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const uint32_t wj = w[j];
@@ -250,7 +259,7 @@ __device__ __forceinline__ void kr_big(const KRParams& P, const double* aw, doub
         uint32_t w[8];
         double xv[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w[j] = __ldcs(wp + (size_t)(i0 + j) * 32);
+        for (int j = 0; j < 8; ++j) w[j] = ldw(i0 + j);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const bool chk = (j == 7 && (i0 & 8));
@@ -286,10 +295,18 @@ __device__ __forceinline__ void kr_big(const KRParams& P, const double* aw, doub
                 } else if (wj & kLFin) {
                     pool[(wj & 15) * NT] = 1.0;
                 }
-                if (ACC != ACC_NONE && v) atomicAdd(acc_g + key, (unsigned long long)v);
+                if (ACC != ACC_NONE && v) red_add64(acc_g + key, (unsigned long long)v);
             }
         }
     }
+}
+
+template <int ACC>
+__device__ __forceinline__ void kr_big(const KRParams& P, const double* aw, double* pool, int NT, long long g, int lane,
+                                       double* xs, unsigned long long* acc_g, long long& ll)
+{
+    const long long o = P.goff[g];
+    kr_big_t<ACC, false>(P, aw, pool, NT, g, lane, P.words + o + lane, (int)((P.goff[g + 1] - o) >> 5), xs, acc_g, ll);
 }
 
 template <int ACC, int MAXNT>

@@ -104,7 +104,9 @@ void compile_corpus(const HostFsa& f, const LatticeArcs& A, const uint8_t* arc_a
 // Region words: EDGE words as above with region-local slots.  Regions of at most kSegSmallMax edges
 // are stored as bare EDGE words (the exit node is the dst of the last edge); larger regions use the
 // full stream format above (CHECK every kCheckEvery-th word, FIN last) so that they can be rescaled.
-constexpr int kSegSmallMax = 16;          // edges of a "small" region (unrolled in registers on the device)
+constexpr int kSegSmallMax = 0;           // edges of a "small" region (bare EDGE words).  0: every DAG-form region uses the stream format --
+                                          // path form takes nearly all small regions, and one code path on the device beats a second,
+                                          // rarely executed one (cold instruction fetches cost more than the padding rows)
 constexpr int kSegMaxPaths = 8;           // path form: a region with at most this many paths ...
 constexpr int kSegMaxPathLen = 16;        // ... all of one length, at most this many edges
 constexpr int kPullChunk = 128;           // list entries one warp of k_pull_paths sums (four per lane)
