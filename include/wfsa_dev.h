@@ -184,7 +184,9 @@ typedef struct {
     /* compiled-lattice kernel (5): stream words incl. padding, lattice edges, edges whose posterior is
        exactly 1 (folded into constant accumulators), strings handed to the secondary kernel, pool size */
     int64_t lattice_words, lattice_edges, lattice_bridge_edges, n_overflow_strings;
-    int32_t pool_slots, reserved;
+    int32_t pool_slots;
+    int32_t eval_path;           /* bit 0: objective+gradient in ONE launch (k_eval6); bit 1: ranks combined through NVLink peer
+                                    memory inside that launch; bit 2: ranks combined by ncclAllReduce; bit 3: strings on the secondary kernel */
     /* segmented kernels (6): distinct region types, region instances over all strings, edges of all
        instances / of the distinct types (what one evaluation walks), host milliseconds of the compile */
     int64_t seg_types, seg_region_instances, seg_region_edges, seg_type_edges;
@@ -213,8 +215,7 @@ int wfsa_lattice_stats(const wfsa_fsa_desc* fsa, const wfsa_corpus_desc* corpus,
  * (1..16), plus 64 to keep every region in DAG form (no path lists).
  * which: 0 rwords(u32) 1 rgoff(i64) 2 rgrows(i32) 3 typeW(f64) 4 swords(u32) 5 sgoff(i64) 6 sgref(i32)
  *        7 ksid(i32) 8 kp(f64) 9 overflow(i32) 10 rejected(i32) 11 const_acc(i64)
- *        12 stats(i64): types, region instances, instance edges, type edges, bridges, strings, host microseconds
- *        13 pvoff(i64) 14 pidx(i32) 15 pcoff(i64) 16 pcarc(i32): pull form of the path-form gradient */
+ *        12 stats(i64): types, region instances, instance edges, type edges, bridges, strings, host microseconds */
 typedef struct wfsa_segmented wfsa_segmented;
 int wfsa_segmented_compile(const wfsa_fsa_desc* fsa, const wfsa_corpus_desc* corpus, const int32_t* trimmed,
                            int32_t n_slots, double fx_scale, wfsa_segmented** out);

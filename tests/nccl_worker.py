@@ -25,6 +25,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     kernel = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    variant = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # e.g. 4 << 16: four pool slots, so that some strings overflow to the secondary kernel
     model = synth.make_model(256, 64, 8, 4, seed=11)
     low = model.lowered()
     offs, toks, w = model.corpus(6000, 32, 128, seed=12)
@@ -39,14 +40,28 @@ def main():
         assert W.lib().wfsa_dev_comm_unique_id(uid.ctypes.data_as(W.C.c_void_p)) == 0
     t = torch.from_numpy(uid).cuda()
     dist.broadcast(t, 0)
-    dev = W.Device(low, device=local, force_kernel=kernel, first=a, count=b - a)
+    dev = W.Device(low, device=local, force_kernel=kernel, accum_variant=variant, first=a, count=b - a)
     dev.comm_init(t.cpu().numpy().tobytes(), rank, world)
     rec, pc, used = dev.structure()                      # `used` is combined over all ranks
     params = np.concatenate([low.trans_param, low.emis_param])
     trimmed, n, _ = O.trim(low, np.array([r < 0 or used[r] for r in params]))
     dev.set_param_map(trimmed, n, rec)
+    # several evaluations in a row (the exchange alternates between two packet buffers by epoch), through the host-buffer
+    # call (one graph launch on the single-launch path) and through upload / launch / fetch
+    for k in range(4):
+        xk = np.random.RandomState(100 + k).normal(-1.0, 0.4, size=n)
+        llk, _, gk = dev.eval(xk, want_logq=False)
+        dev.upload_x(xk)
+        dev.eval_launch()
+        llr, gr = dev.eval_fetch()
+        assert llk == llr and np.array_equal(gk, gr), "host-buffer call and resident evaluation differ"
+        mk = torch.from_numpy(np.concatenate([[llk], gk])).cuda()
+        rk = mk.clone()
+        dist.broadcast(rk, 0)
+        assert torch.equal(mk.view(torch.int64), rk.view(torch.int64)), "ranks disagree (evaluation %d)" % k
     x = np.random.RandomState(3).normal(-1.2, 0.6, size=n)
     ll, logq, grad = dev.eval(x)
+    path = dev.info()["eval_path"]
     dev.close()
 
     # every rank holds the same bits
@@ -55,7 +70,7 @@ def main():
     dist.broadcast(ref, 0)
     assert torch.equal(mine.view(torch.int64), ref.view(torch.int64)), "ranks disagree"
     if rank == 0:
-        one = W.Device(low, device=local, force_kernel=kernel)
+        one = W.Device(low, device=local, force_kernel=kernel, accum_variant=variant)
         one_kernel = one.info()["kernel"]
         rec1, pc1, used1 = one.structure()
         assert np.array_equal(used1, used) and np.array_equal(rec1[a:b], rec)
@@ -74,7 +89,7 @@ def main():
         _, olq, oee = O.dp_eval(low, ltw, lew)
         r = rec1.astype(bool)
         assert abs(ll - float(np.sum(low.p[r] * olq[r]))) <= 1e-10 * abs(ll)
-        print("nccl_worker ok: world=%d kernel=%d loglik=%.15g" % (world, kernel, ll), flush=True)
+        print("nccl_worker ok: world=%d kernel=%d eval_path=%d loglik=%.15g" % (world, kernel, path, ll), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

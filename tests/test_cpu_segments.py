@@ -72,9 +72,6 @@ def interpret(seg, aw, n_arcs):
     acc = seg["const_acc"].astype(np.float64) / FX
     seen = set()
     n_path_types = n_dag_types = 0
-    assert len(seg["pvoff"]) == n_rg
-    n_pv = int(sum(((int(d) >> 8) & 0xff) * 32 for d in rgrows if int(d) & 0x10000))
-    pv = np.zeros(n_pv)
     for g in range(n_rg):
         desc = int(rgrows[g])
         if desc & 0x10000:                                   # path form: PP paths (zero-weight padding) of L edges
@@ -96,10 +93,10 @@ def interpret(seg, aw, n_arcs):
                 assert real.sum() >= 2 and ((block[:, :, l] == n_arcs).all(axis=0) | real).all()
                 q = r.sum()
                 lq[g * 32 + l] = np.log(q)
-                # pull form: the value of path p is stored at pv[pvoff[g] + p*32 + lane]; the arcs gather it below
-                assert seg["pvoff"][g] >= 0
+                # every edge of path p receives the posterior r_p / q (one RED per (path, edge) on the device)
                 for p_ in np.where(real)[0]:
-                    pv[seg["pvoff"][g] + p_ * 32 + l] = W_[g * 32 + l] * r[p_] / q
+                    for a_ in block[:, p_, l]:
+                        acc[a_] += W_[g * 32 + l] * r[p_] / q
                 n_path_types += 1
             continue
         rows = desc
@@ -119,12 +116,6 @@ def interpret(seg, aw, n_arcs):
                 acc[arc] += W_[g * 32 + l] * v
             n_dag_types += 1
     interpret.counts = (n_path_types, n_dag_types)
-    # k_pull_paths: chunk c adds pv[pidx[pcoff[c]:pcoff[c+1]]] into the accumulator of arc pcarc[c]
-    pidx, pcoff, pcarc = seg["pidx"], seg["pcoff"], seg["pcarc"]
-    assert len(pcoff) == len(pcarc) + 1 and (len(pidx) == pcoff[-1] if len(pcarc) else len(pidx) == 0)
-    for c in range(len(pcarc)):
-        assert 0 < pcoff[c + 1] - pcoff[c] <= 128 and 0 <= pcarc[c] < n_arcs
-        acc[pcarc[c]] += pv[pidx[pcoff[c]:pcoff[c + 1]]].sum()
     sgoff, sgref, ksid, kp = seg["sgoff"], seg["sgref"], seg["ksid"], seg["kp"]
     logq = {}
     with np.errstate(divide="ignore"):

@@ -398,8 +398,8 @@ def test_full_size_config4_properties():
     dev.close()
 
 
-@pytest.mark.parametrize("kernel", [0, 1])
-def test_two_ranks_nccl(kernel):
+@pytest.mark.parametrize("kernel,variant", [(0, 0), (1, 0), (0, 4 << 16)])
+def test_two_ranks_nccl(kernel, variant):
     """Two processes, two GPUs, the library's own ncclAllReduce of exact integers (tests/nccl_worker.py):
     identical bits on every rank and equal to the single-device evaluation.  Skipped on a one-GPU box
     (tests/test_cpu_multirank.py covers the sharding and the integer all-reduce on gloo)."""
@@ -411,7 +411,7 @@ def test_two_ranks_nccl(kernel):
         pytest.skip("needs two GPUs")
     here = os.path.dirname(os.path.abspath(__file__))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(29600 + kernel), os.path.join(here, "nccl_worker.py"), str(kernel)]
+           "--master-port", str(29600 + kernel + (7 if variant else 0)), os.path.join(here, "nccl_worker.py"), str(kernel), str(variant)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "nccl_worker ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 

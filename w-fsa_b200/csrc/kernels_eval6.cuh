@@ -115,7 +115,7 @@ __device__ __forceinline__ void e6_paths_long(const KRParams& P, const double* a
     long long v[PP];
 #pragma unroll
     for (int p = 0; p < PP; ++p) v[p] = __double2ll_rn(r[p] * sc);
-    if (P.pv) return;                                          // timing experiment (debug bit 3): no REDs from long path-form types
+    if (P.no_long_reds) return;                                          // timing experiment (debug bit 3): no REDs from long path-form types
     for (int l0 = 0; l0 < L; l0 += LB) {
         uint32_t a[LB * PP];
 #pragma unroll
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
     // ---- P1: region types -------------------------------------------------------------------------------------
     KRParams R{};
     R.words = P.words; R.goff = P.goff; R.typeW = P.typeW; R.lq = P.lq; R.xs = P.xs; R.xs_rows = P.xs_rows;
-    R.fx_scale = P.fx_scale; R.ll_scale = ll_scale; R.red = P.red; R.n_arcs = P.n_arcs; R.pv = (P.debug & 8) ? reinterpret_cast<long long*>(8) : nullptr;
+    R.fx_scale = P.fx_scale; R.ll_scale = ll_scale; R.red = P.red; R.n_arcs = P.n_arcs; R.no_long_reds = (P.debug & 8) ? 1 : 0;
     unsigned int* const counter = P.ctl + par;
     unsigned long long* const acc_g = P.acc + (size_t)par * acc_words + (size_t)(blockIdx.x % P.replicas) * (size_t)P.n_arcs;
     const long long gwarp = (long long)blockIdx.x * (NT / 32) + warp;

@@ -33,12 +33,7 @@ struct KRParams {
     unsigned long long* acc;              // [replicas][n_arcs]
     double fx_scale;
     int n_arcs, replicas;
-    // pull form of the path-form gradient (lattice.hpp): the value of path p of the type at (g, lane) is stored at
-    // pv[pvoff[g] + p*32 + lane] and gathered per arc by k_pull_paths; pv == nullptr: one RED per (type, path, edge)
-    long long* pv;
-    const int64_t* __restrict__ pvoff;
-    long long n_first;                    // scheduler: tickets [0, n_first) map to the groups in order (the big DAG regions),
-    long long stride;                     // the others to n_first + ((ticket - n_first) * stride) % (n_groups - n_first)
+    int no_long_reds;                     // timing experiment of k_eval6 (debug bit 3): long path-form types skip their REDs
     // log-likelihood: sum_s p_s log q_s = sum_types W_type * lq_type + sum_arcs (bridge count of the arc) * log w[arc].
     // The first sum is accumulated here (fixed point, one RED per CTA), the second one arrives as per-CTA partials of
     // the weight kernel in llpart[n_llpart][2] = (value, non-finite terms) and is added by CTA 0.
@@ -79,75 +74,6 @@ __device__ __forceinline__ void red_uniform(unsigned long long* acc_g, int key, 
     } else if (key >= 0 && v) red_add64(acc_g + key, (unsigned long long)v);
 }
 
-// One small region per thread, NE <= 16 word rows (bare EDGE words).  The x values of the forward sweep stay in
-// registers; the words are held in registers for NE <= 8 and re-read (L1) by the backward sweep otherwise.
-template <int NE, int ACC>
-__device__ __forceinline__ void kr_small(const KRParams& P, const double* aw, double* pool, int NT, long long g, long long off, int lane,
-                                         unsigned long long* acc_g, long long& ll)
-{
-    constexpr int NB = (NE + 7) / 8;                          // batches of up to 8 words
-    const uint32_t* wp = P.words + off + lane;
-    const double W = P.typeW[g * 32 + lane];
-    double xs[NE];
-    uint32_t w[8];
-    pool[0] = 1.0;                                            // the entry node owns slot 0
-    int last = 0;
-    bool any = false;
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) if (b * 8 + j < NE) w[j] = __ldcs(wp + (size_t)(b * 8 + j) * 32);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (b * 8 + j >= NE) continue;
-            const uint32_t wj = w[j];
-            if (wj & kLEdge) {
-                const int src = (wj >> 19) & 15, dst = (wj >> 23) & 15, arc = wj & 0x7fff;
-                const double xv = pool[src * NT] * aw[arc];
-                xs[b * 8 + j] = xv;
-                double* pd = pool + dst * NT;
-                *pd = (wj & kLFirstIn) ? xv : *pd + xv;
-                last = dst;
-                any = true;
-            }
-        }
-    }
-    const double q = pool[last * NT];
-    const bool ok = any && q > 0.0 && isfinite(q);
-    if (any) {
-        const double lq = ok ? log(q) : -INFINITY;
-        P.lq[g * 32 + lane] = lq;
-        kr_loglik(P, W, ok, lq, ll);
-    }
-    const double sc = ok ? W * P.fx_scale / q : 0.0;
-    pool[last * NT] = 1.0;
-#pragma unroll
-    for (int b = NB - 1; b >= 0; --b) {
-        if (NB > 1) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) if (b * 8 + j < NE) w[j] = __ldg(wp + (size_t)(b * 8 + j) * 32);
-        }
-#pragma unroll
-        for (int j = 7; j >= 0; --j) {
-            if (b * 8 + j >= NE) continue;
-            const uint32_t wj = w[j];
-            int key = -1;
-            long long v = 0;
-            if (wj & kLEdge) {
-                const int src = (wj >> 19) & 15, dst = (wj >> 23) & 15, arc = wj & 0x7fff;
-                const double bd = pool[dst * NT];
-                const double c = aw[arc] * bd;
-                double* psrc = pool + src * NT;
-                *psrc = (wj & kLLastOut) ? c : *psrc + c;
-                key = arc;
-                v = __double2ll_rn(xs[b * 8 + j] * bd * sc);
-            }
-            if (ACC == ACC_GLOBAL && b * 8 + j < 2) red_uniform(acc_g, key, v, lane);
-            else if (ACC != ACC_NONE) { if (v) red_add64(acc_g + key, (unsigned long long)v); }
-        }
-    }
-}
-
 // One region in PATH FORM per thread: PP paths (padded with zero-weight paths) of L edges each, arc of edge l of
 // path p at row l*PP + p.  q = sum_p prod_l w[arc]; every edge of path p gets the posterior r_p / q.  Registers
 // only: PP independent multiply chains, no pool, no flags (the reference's P.x / exp / M algebra,
@@ -182,12 +108,6 @@ __device__ __forceinline__ void kr_paths(const KRParams& P, const double* aw, in
     long long v[PP];
 #pragma unroll
     for (int p = 0; p < PP; ++p) v[p] = __double2ll_rn(r[p] * sc);
-    if (ACC == ACC_GLOBAL && P.pv) {                           // pull form: PP coalesced stores instead of PP*L REDs
-        long long* dst = P.pv + P.pvoff[g] + lane;
-#pragma unroll
-        for (int p = 0; p < PP; ++p) dst[p * 32] = v[p];
-        return;
-    }
     for (int l = 0; l < L; ++l) {
         uint32_t a[PP];
 #pragma unroll
@@ -316,30 +236,19 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
     double* aw = reinterpret_cast<double*>(smem);             // [n_arcs + 1]; the last entry is the zero weight of padding
     double* pool = aw + P.n_arcs + 1 + tid;                   // slot s of this thread at pool[s*NT]
-    // programmatic dependent launch (when the host asked for it; no-ops otherwise): this grid may start while the
-    // weight kernel drains, and lets the fold kernel's CTAs be set up while it runs itself
-    cudaGridDependencySynchronize();
-    cudaTriggerProgrammaticLaunchCompletion();
     for (int i = tid; i <= P.n_arcs; i += NT) aw[i] = i < P.n_arcs ? P.aw[i] : 0.0;
     __syncthreads();
     const long long gwarp = ((long long)blockIdx.x * NT + tid) >> 5;
     double* const xs = P.xs + (size_t)gwarp * P.xs_rows * 32 + lane;
     unsigned long long* const acc_g = P.acc + (size_t)(blockIdx.x % P.replicas) * (size_t)P.n_arcs;
-    // groups are sorted by cost (big regions first, then 16, 12, 8, 4 rows) and handed out dynamically, one at a
-    // time; the id of the next group is requested while the current one is processed.  Measured alternatives, all
-    // slower: static round-robin (87 us against 58 us), two requests in flight (76 us), four groups per atomic (135 us)
-    // Tickets from the scheduler can be mapped to groups with a stride (P.stride > 1), so that concurrently running
-    // warps work on regions far apart in the sorted order; the big DAG regions (one long dependency chain per
-    // thread) keep their place at the front.  Measured on config 4: no gain over the sorted order (stride 1) here,
-    // although a split-off path-form kernel went from 82 us to 54 us with it (L2 atomics serialise per address).
-    const long long n_rest = P.n_groups - P.n_first;
-    auto group_of = [&](long long t) { return t < P.n_first || t >= P.n_groups ? t : P.n_first + ((t - P.n_first) * P.stride) % n_rest; };
+    // groups are sorted by cost (DAG regions first, then path form by paths and length) and handed out dynamically, one
+    // at a time; the id of the next group is requested while the current one is processed
     long long g = 0, ll = 0;
-    if (lane == 0) g = group_of((long long)atomicAdd(P.counter, 1u));
+    if (lane == 0) g = (long long)atomicAdd(P.counter, 1u);
     g = __shfl_sync(FULL, g, 0);
     while (g < P.n_groups) {
         long long gn = 0;
-        if (lane == 0) gn = group_of((long long)atomicAdd(P.counter, 1u));
+        if (lane == 0) gn = (long long)atomicAdd(P.counter, 1u);
         const int rows = P.grows[g];
         const long long off = P.goff[g];
         if (rows & 0x10000) {                                  // path form: paths << 8 | length
@@ -351,13 +260,7 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
                 case 6: kr_paths<6, ACC>(P, aw, L, g, off, lane, acc_g, ll); break;
                 default: kr_paths<8, ACC>(P, aw, L, g, off, lane, acc_g, ll); break;
             }
-        } else switch (rows) {
-            case 4: kr_small<4, ACC>(P, aw, pool, NT, g, off, lane, acc_g, ll); break;
-            case 8: kr_small<8, ACC>(P, aw, pool, NT, g, off, lane, acc_g, ll); break;
-            case 12: kr_small<12, ACC>(P, aw, pool, NT, g, off, lane, acc_g, ll); break;
-            case 16: kr_small<16, ACC>(P, aw, pool, NT, g, off, lane, acc_g, ll); break;
-            default: kr_big<ACC>(P, aw, pool, NT, g, lane, xs, acc_g, ll); break;
-        }
+        } else kr_big<ACC>(P, aw, pool, NT, g, lane, xs, acc_g, ll);
         g = __shfl_sync(FULL, gn, 0);
     }
     // the CTA's share of the log-likelihood: integer sums (exact, order independent), one RED per CTA
@@ -376,30 +279,6 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
         if (s) atomicAdd(P.red, (unsigned long long)s);
         if (nf) atomicAdd(P.red + 1, nf);
     }
-}
-
-// Pull form of the path-form gradient: chunk c adds the values pv[pidx[i]], i in [pcoff[c], pcoff[c+1]), of the
-// paths that contain arc pcarc[c] into that arc's accumulator -- one warp per chunk (at most kPullChunk entries:
-// coalesced index reads, gathers from the L2-resident pv, integer shuffle sum, ONE RED).  It replaces one RED per
-// (type, path, edge) -- 7 M per evaluation for config 4, issued at the LSU lane rate inside the latency-bound region
-// kernel.  Measured slower than the REDs; kept behind WFSA_PULL=1.
-__global__ void __launch_bounds__(256) k_pull_paths(long long n_chunks, const int64_t* __restrict__ pcoff, const int32_t* __restrict__ pcarc,
-                                                    const int32_t* __restrict__ pidx, const long long* __restrict__ pv,
-                                                    unsigned long long* acc)
-{
-    const int lane = threadIdx.x & 31;
-    const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (c >= n_chunks) return;
-    const long long b = pcoff[c], e = pcoff[c + 1];              // at most kPullChunkD = 128 entries: four per lane,
-    int id[4];                                                   // all index loads, then all gathers, in flight together
-#pragma unroll
-    for (int k = 0; k < 4; ++k) id[k] = b + lane + 32 * k < e ? pidx[b + lane + 32 * k] : -1;
-    long long s = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) if (id[k] >= 0) s += pv[id[k]];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-    if (lane == 0 && s) atomicAdd(acc + pcarc[c], (unsigned long long)s);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -538,240 +417,6 @@ __global__ void __launch_bounds__(256) k_arc_weights_log(int n_arcs, const int32
     bridge_loglik_partial(i < n_arcs ? const_acc[i] : 0ull, l, inv_fx, ll_scale, llpart);
 }
 
-
-// One launch in front of an evaluation of the segmented path: arc weights from x, accumulators reset
-// (replica 0 starts from the constant bridge part), reduction cells, scheduler counters and the output cleared.
-struct Prep6Params {
-    int n_arcs, replicas, n_red, n_out;
-    const int32_t* __restrict__ arc_tid; const int32_t* __restrict__ arc_eid;
-    const int32_t* __restrict__ trans_tp; const int32_t* __restrict__ emis_tp;
-    const double* __restrict__ x;
-    const unsigned long long* __restrict__ const_acc;
-    double* aw; double* logaw;
-    unsigned long long* acc; unsigned long long* red;
-    unsigned int* counters;            // [2]
-    double* out;
-    double inv_fx, ll_scale;
-    long long* llpart;                 // [ceil(n_arcs / blockDim.x)][2]
-};
-__global__ void __launch_bounds__(256) k_prep6(const Prep6Params P)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    cudaTriggerProgrammaticLaunchCompletion();                 // kr_regions may be set up now (it waits for this grid to finish)
-    if (blockIdx.x * blockDim.x < P.n_arcs) {                  // CTA uniform
-        double l = 0.0;
-        if (i < P.n_arcs) {
-            l = logweight_of(P.trans_tp[P.arc_tid[i]], P.x, 0) + (P.arc_eid[i] < 0 ? 0.0 : logweight_of(P.emis_tp[P.arc_eid[i]], P.x, 0));
-            P.logaw[i] = l;
-            P.aw[i] = exp(l);
-        }
-        bridge_loglik_partial(i < P.n_arcs ? P.const_acc[i] : 0ull, l, P.inv_fx, P.ll_scale, P.llpart);
-    }
-    if (i < P.n_arcs * P.replicas) P.acc[i] = i < P.n_arcs ? P.const_acc[i] : 0ull;
-    if (i < P.n_red) P.red[i] = 0ull;
-    if (i < P.n_out) P.out[i] = 0.0;
-    if (i < 2) P.counters[i] = 0u;
-}
-
-// One launch behind it: per-arc accumulators (all replicas) -> per-edge sums (a gather over the arcs of the
-// edge, fixed order, integer adds) -> and, without a communicator, straight to [loglik, bad, grad].
-struct Fin6Params {
-    int n_edges, n_arcs, replicas, n, finish;      // finish: bit 0 = write grad, bit 1 = write [loglik, bad] as well
-    const int32_t* __restrict__ e_off;      // [n_edges+1] arcs of every edge (transition edges, then emission edges)
-    const int32_t* __restrict__ e_arc;
-    const unsigned long long* __restrict__ acc;
-    unsigned long long* red;
-    const int32_t* __restrict__ edge_tp;
-    double inv_fx, inv_ll;
-    double* out;
-};
-// Sum of the (arc, replica) cells of one edge, by one warp.  The arc ids of the edge are read once (one per lane)
-// and handed out with shuffles, so the cell loads do not wait for an index load each, and four of them are in flight
-// per lane: an emission edge has ~8 arcs x 16 replicas = 128 cells, which took four dependent round trips (5-10 us,
-// the longest thing in the kernel) when every iteration loaded its own arc id first.
-__device__ __forceinline__ unsigned long long fold_edge(const Fin6Params& F, int e, int lane)
-{
-    const int k0 = F.e_off[e], na = F.e_off[e + 1] - k0;
-    int first = lane < min(32, na) ? F.e_arc[k0 + lane] : 0;   // index loads do not depend on the region kernel ...
-    cudaGridDependencySynchronize();                           // ... the accumulator cells do (no-op without PDL)
-    unsigned long long s = 0;
-    for (int b = 0; b < na; b += 32) {
-        const int nb = min(32, na - b);
-        const int mine = b == 0 ? first : (lane < nb ? F.e_arc[k0 + b + lane] : 0);
-        const int cells = nb * F.replicas;
-        for (int c0 = 0; c0 < cells; c0 += 128) {
-            unsigned long long v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = c0 + j * 32 + lane;
-                const int a = __shfl_sync(FULL, mine, min(c / F.replicas, nb - 1));
-                v[j] = c < cells ? F.acc[(size_t)(c % F.replicas) * F.n_arcs + a] : 0ull;
-            }
-            s += (v[0] + v[1]) + (v[2] + v[3]);
-        }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-    return s;
-}
-
-__global__ void __launch_bounds__(256) k_fold_finish6(const Fin6Params P)
-{
-    // one warp per edge: its lanes share the (arc, replica) cells of the edge, then a shuffle sum (integers)
-    const int lane = threadIdx.x & 31;
-    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (e == 0 && lane == 0 && (P.finish & 2)) {
-        cudaGridDependencySynchronize();
-        const double bad = (double)P.red[1];
-        P.out[0] = bad > 0 ? -INFINITY : (double)(long long)P.red[0] * P.inv_ll;
-        P.out[1] = bad;
-    }
-    if (e >= P.n_edges) return;
-    unsigned long long s = fold_edge(P, e, lane);              // (waits for kr_regions inside, after the index loads)
-    if (lane == 0) {
-        s += P.red[2 + e];
-        P.red[2 + e] = s;
-        if (P.finish & 1) {
-            const int tp = P.edge_tp[e];
-            if (tp >= 0 && tp < P.n) P.out[2 + tp] = -(double)(long long)s * P.inv_fx;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// One-shot all-reduce of the evaluation result over NVLink peer memory, fused with the finish step.
-// The payload ([loglik, bad, per-edge accumulators]: ~27 KB of exact 64-bit integers for config 4) is far too small
-// for ncclAllReduce to be anything but latency: here every rank WRITES its payload into its slot of every peer's
-// buffer (plain stores through NVLink / NVSwitch into IPC-mapped memory), publishes an epoch flag behind a system
-// fence, waits for the other ranks' flags, sums the slots in rank order (so every rank gets the same bits) and
-// converts to [loglik, bad, grad] -- one single-CTA launch instead of a collective plus two small kernels.
-// Buffers are double buffered by epoch parity; a rank cannot be two epochs ahead of a peer because it needs that
-// peer's contribution to finish the epoch in between.  The wait is bounded (~2 s): out[1] = NaN on time-out.
-// Layout of a rank's buffer (uint64 words): data[2][nranks][words] then flags[2][nranks].
-// ------------------------------------------------------------------------------------------
-struct PeerParams {
-    unsigned long long* peers[8];          // IPC-mapped base of every rank's buffer (own entry = local pointer)
-    int nranks, rank, words, n_edges, n, rearm;
-    unsigned long long epoch;              // 1, 2, ...
-    unsigned long long* red;               // in: this rank's payload; out: the sums
-    const int32_t* __restrict__ edge_tp;
-    double inv_fx, inv_ll;
-    double* out;
-};
-
-__global__ void __launch_bounds__(1024, 1) k_peer_allreduce_finish(const PeerParams P)
-{
-    const int tid = threadIdx.x, ph = (int)(P.epoch & 1ull);
-    const size_t slot = ((size_t)ph * P.nranks + P.rank) * P.words;
-    const size_t flag0 = (size_t)2 * P.nranks * P.words + (size_t)ph * P.nranks;
-    for (int i = tid; i < P.words; i += blockDim.x) {
-        const unsigned long long v = P.red[i];
-        for (int r = 0; r < P.nranks; ++r) P.peers[r][slot + i] = v;
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < P.nranks) *reinterpret_cast<volatile unsigned long long*>(P.peers[tid] + flag0 + P.rank) = P.epoch;
-    __shared__ int s_timeout;
-    if (tid == 0) s_timeout = 0;
-    __syncthreads();
-    if (tid < P.nranks) {
-        const volatile unsigned long long* f = P.peers[P.rank] + flag0 + tid;
-        const long long t0 = clock64();
-        while (*f != P.epoch)
-            if (clock64() - t0 > 4000000000ll) { s_timeout = 1; break; }
-        __threadfence_system();
-    }
-    __syncthreads();
-    const unsigned long long* mine = P.peers[P.rank] + (size_t)ph * P.nranks * P.words;
-    for (int i = tid; i < P.words; i += blockDim.x) {
-        unsigned long long sum = 0;
-        for (int r = 0; r < P.nranks; ++r) sum += *reinterpret_cast<const volatile unsigned long long*>(mine + (size_t)r * P.words + i);
-        if (i >= 2) {
-            P.red[i] = sum;
-            const int e = i - 2;
-            if (e < P.n_edges) { const int tp = P.edge_tp[e]; if (tp >= 0 && tp < P.n) P.out[2 + tp] = -(double)(long long)sum * P.inv_fx; }
-        } else P.red[i] = P.rearm ? 0ull : sum;
-        if (i == 0) {
-            unsigned long long bad = 0;
-            for (int r = 0; r < P.nranks; ++r) bad += *reinterpret_cast<const volatile unsigned long long*>(mine + (size_t)r * P.words + 1);
-            P.out[0] = bad > 0 ? -INFINITY : (double)(long long)sum * P.inv_ll;
-            P.out[1] = s_timeout ? NAN : (double)bad;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Fold + all-reduce + finish in ONE launch (the lean segmented path with a communicator).
-// One warp per payload word w (0 = loglik, 1 = non-finite terms, 2 + e = accumulator of edge e):
-//   1. the local value: red[w] for w < 2, else the gather over the (arc, replica) cells of the edge (k_fold_finish6);
-//   2. lane r < nranks sends it to rank r as two self-validating 8-byte packets {32 data bits, 32-bit epoch}
-//      (plain stores into the peer's IPC-mapped buffer; an aligned 8-byte store is a single transaction, so a packet
-//      whose upper half equals the epoch is complete -- no fence, no separate flag, no second round trip);
-//   3. lane r polls the two packets rank r sent for this word into the local buffer, the lanes add up with shuffles
-//      (integers: every rank gets the same bits) and lane 0 converts to out[].
-// Packets of epoch e live in buffer e & 1; a rank cannot start epoch e + 2 before every peer has finished reading
-// epoch e, because it needs their packets of epoch e + 1 first.  All CTAs of the grid are resident (host checks), so
-// no warp waits for a warp of its own GPU.  The wait is bounded (~2 s): out[1] = NaN on time-out.
-// Layout (uint64 words, relative to ll_off): pk[parity][sender rank][word][2].
-struct FoldPeerParams {
-    Fin6Params F;
-    unsigned long long* peers[8];
-    size_t ll_off;
-    int nranks, rank, words;
-    unsigned int flag;                     // low 32 bits of the epoch; epochs start at 1
-    int parity;
-};
-
-__device__ __forceinline__ unsigned long long ll_exchange(const FoldPeerParams& P, int w, unsigned long long s, int lane, bool& timeout)
-{
-    unsigned long long v = 0;
-    if (lane < P.nranks) {
-        volatile unsigned long long* dst = P.peers[lane] + P.ll_off + (((size_t)P.parity * P.nranks + P.rank) * P.words + w) * 2;
-        const unsigned long long fl = (unsigned long long)P.flag << 32;
-        dst[0] = (s & 0xffffffffull) | fl;
-        dst[1] = (s >> 32) | fl;
-        const volatile unsigned long long* src = P.peers[P.rank] + P.ll_off + (((size_t)P.parity * P.nranks + lane) * P.words + w) * 2;
-        const long long t0 = clock64();
-        unsigned long long a = src[0], b = src[1];
-        while ((unsigned int)(a >> 32) != P.flag || (unsigned int)(b >> 32) != P.flag) {
-            if (clock64() - t0 > 4000000000ll) { timeout = true; break; }
-            a = src[0]; b = src[1];
-        }
-        v = (a & 0xffffffffull) | (b << 32);
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-
-__global__ void __launch_bounds__(256) k_fold_allreduce_finish6(const FoldPeerParams P)
-{
-    const Fin6Params& F = P.F;
-    const int lane = threadIdx.x & 31;
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= P.words || w == 1) return;                        // warp 0 takes words 0 and 1
-    bool timeout = false;
-    if (w == 0) {
-        cudaGridDependencySynchronize();
-        const unsigned long long ll = ll_exchange(P, 0, F.red[0], lane, timeout);       // (two round trips for this one warp:
-        const unsigned long long bad = ll_exchange(P, 1, F.red[1], lane, timeout);      //  it has no gather to do before them)
-        const bool any_to = __any_sync(FULL, timeout);
-        if (lane == 0) {
-            F.out[0] = bad > 0 ? -INFINITY : (double)(long long)ll * F.inv_ll;
-            if (any_to) F.out[1] = NAN; else if (bad) F.out[1] = (double)bad;      // out[] was cleared by k_prep6; NaN wins
-        }
-        return;
-    }
-    const int e = w - 2;
-    const unsigned long long s = fold_edge(F, e, lane);
-    const unsigned long long sum = ll_exchange(P, w, s, lane, timeout);
-    if (__any_sync(FULL, timeout)) { if (lane == 0) F.out[1] = NAN; return; }
-    if (lane == 0) {
-        F.red[w] = sum;
-        const int tp = F.edge_tp[e];
-        if (tp >= 0 && tp < F.n) F.out[2 + tp] = -(double)(long long)sum * F.inv_fx;
-    }
-}
 
 // Device-side barrier over the ranks of the communicator through peer memory (benchmark helper: it lines the ranks
 // up between two timed evaluations).  One warp: lane r tells rank r "rank `rank` reached epoch e", then waits for

@@ -875,38 +875,6 @@ std::shared_ptr<SegmentedStringsJob> compile_corpus_regions(const HostFsa& f, co
         for (int t = 0; t < T; ++t) out.n_type_edges += edges_of[t];
     }
     lap("region layout");
-    // ---- 3b. pull form: where every arc finds the path values it has to add up
-    {
-        out.pvoff.assign((size_t)n_rg, -1);
-        for (int64_t g = 0; g < n_rg; ++g)
-            if (out.rgrows[g] & 0x10000) { out.pvoff[g] = out.n_pv; out.n_pv += (int64_t)((out.rgrows[g] >> 8) & 0xff) * 32; }
-        std::vector<int64_t> cnt((size_t)A.n_arcs + 1, 0);
-        auto visit = [&](auto&& f) {
-            for (int64_t g = 0; g < n_rg; ++g) {
-                if (!(out.rgrows[g] & 0x10000)) continue;
-                const int PP = (out.rgrows[g] >> 8) & 0xff, L = out.rgrows[g] & 0xff;
-                const uint32_t* base = out.rwords.data() + out.rgoff[g];
-                for (int q = 0; q < PP; ++q)
-                    for (int l = 0; l < 32; ++l)
-                        for (int el = 0; el < L; ++el) {
-                            const uint32_t a = base[(size_t)(el * PP + q) * 32 + l];
-                            if ((int)a < A.n_arcs) f((int)a, out.pvoff[g] + (int64_t)q * 32 + l);
-                        }
-            }
-        };
-        visit([&](int a, int64_t) { cnt[a + 1]++; });
-        for (int a = 0; a < A.n_arcs; ++a) cnt[a + 1] += cnt[a];
-        out.pidx.resize((size_t)cnt[A.n_arcs]);
-        std::vector<int64_t> fillp(cnt.begin(), cnt.end() - 1);
-        visit([&](int a, int64_t pv) { out.pidx[(size_t)fillp[a]++] = (int32_t)pv; });
-        out.pcoff.assign(1, 0);
-        for (int a = 0; a < A.n_arcs; ++a)
-            for (int64_t b = cnt[a]; b < cnt[a + 1]; b += kPullChunk) {
-                out.pcarc.push_back(a);
-                out.pcoff.push_back(std::min(cnt[a + 1], b + kPullChunk));
-            }
-    }
-    lap("pull-form CSR");
     out.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     auto job = std::make_shared<SegmentedStringsJob>();
     SegmentedStringsJob::State& S = *job->st;

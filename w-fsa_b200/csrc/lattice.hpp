@@ -109,7 +109,6 @@ constexpr int kSegSmallMax = 0;           // edges of a "small" region (bare EDG
                                           // rarely executed one (cold instruction fetches cost more than the padding rows)
 constexpr int kSegMaxPaths = 8;           // path form: a region with at most this many paths ...
 constexpr int kSegMaxPathLen = 16;        // ... all of one length, at most this many edges
-constexpr int kPullChunk = 128;           // list entries one warp of k_pull_paths sums (four per lane)
 constexpr int kKsSuper = 16;              // groups (warps) per super-group of the KS layout
 constexpr int kKsChunkRows = 8;           // rows per interleaving chunk of the KS layout
 constexpr int kSegSmallStep = 4;          // small regions are padded to 4, 8, 12 or 16 word rows
@@ -131,15 +130,6 @@ struct SegmentedCorpus {
     std::vector<int32_t> rgrows;               // [n_rgroups]
     std::vector<double> typeW;                 // [n_rgroups*32] sum of p_s over the instances (0 = padding lane)
     int64_t n_types = 0, n_region_instances = 0, n_region_edges = 0, n_type_edges = 0, max_big_rows = 0;
-    // PULL form of the gradient of the path-form types: kr_regions stores the value v of path p of the type at
-    // (g, lane) into pv[pvoff[g] + p*32 + lane]; every arc then GATHERS the values of the paths it lies on
-    // (k_pull_paths) instead of receiving one RED per (type, path, edge).  The lists are cut into chunks of at most
-    // kPullChunk entries: chunk c adds pv[pidx[pcoff[c] .. pcoff[c+1])] into the accumulator of arc pcarc[c].
-    std::vector<int64_t> pvoff;                // [n_rgroups] or -1 for a DAG-form group
-    int64_t n_pv = 0;
-    std::vector<int32_t> pidx;                 // [sum of path lengths]
-    std::vector<int64_t> pcoff;                // [n_chunks+1]
-    std::vector<int32_t> pcarc;                // [n_chunks]
     // KS: strings in groups of 32 (one warp), longest first; string position kpos = g*32 + l.  kKsSuper groups
     // form a super-group (one CTA); its words are chunk-interleaved:
     //   word (super-group sg, chunk c, group w in sg, row j in chunk, lane l)

@@ -132,7 +132,7 @@ struct wfsa_dev {
     DevBuf<unsigned long long> d_klacc, d_klconst;
     // segmented compiled lattices (KR + KS, kernel 6)
     size_t ks_smem = 0; int ks_grid = 0, ks_block = 512, ks_ctas = 2;
-    int64_t kr_big_groups = 0, kr_stride = 1;   // scheduler ticket -> group map of kr_regions
+    int64_t kr_big_groups = 0;                  // DAG-form groups (they sort first)
     int64_t kr_groups = 0, ks_groups = 0, seg_types = 0, seg_instances = 0, seg_region_edges = 0, seg_type_edges = 0,
             seg_bridges = 0, seg_words = 0;
     double seg_host_ms = 0;
@@ -170,8 +170,8 @@ struct wfsa_dev {
     int hb_fx_log2 = 40;
     // comm
     ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
-    // one-shot all-reduce over NVLink peer memory (k_peer_allreduce_finish); falls back to NCCL when it cannot be set up
-    bool peer_ok = false; unsigned long long peer_epoch = 0, peer_ll_epoch = 0; int peer_words = 0; size_t peer_ll_off = 0, peer_bar_off = 0; int fold_peer_ctas = 0; unsigned long long peer_bar_epoch = 0;
+    // NVLink peer memory for the exchange inside k_eval6 (and the rank barrier of the benchmark); without it ncclAllReduce
+    bool peer_ok = false; int peer_words = 0; size_t peer_ll_off = 0, peer_bar_off = 0; unsigned long long peer_bar_epoch = 0;
     unsigned long long* peer_local = nullptr; unsigned long long* peer_ptrs[8] = {nullptr};
     // timing
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -184,10 +184,9 @@ struct wfsa_dev {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sev; size_t sev_used = 0;      // per-evaluation event pairs (timer)
     DevBuf<long long> d_llpart;             // bridge part of the log-likelihood: per-CTA partials of the weight kernel
     int llpart_n = 0;
-    bool pdl = true, pdl_now = false, timing_detail = true;     // programmatic dependent launches on the lean segmented path
+    bool timing_detail = true;
     bool evaluated = false;                 // an evaluation has been launched since set_param_map
     bool ks_done = false;                   // ks_strings has run for the last evaluation (it runs on demand)
-    DevBuf<long long> d_pv; DevBuf<int64_t> d_pvoff, d_pcoff; DevBuf<int32_t> d_pidx, d_pcarc; int64_t n_pchunks = 0; bool pull = false;
     // single-launch evaluation of the segmented path (k_eval6, kernels_eval6.cuh)
     DevBuf<unsigned int> d_e6ctl;           // [0..1] tickets, [2] barrier arrivals, [3] epoch
     DevBuf<unsigned long long> d_e6acc, d_e6red, d_e6stamps;
@@ -260,7 +259,7 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     for (auto& e : h->kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto& e : h->kev_mid) cudaEventDestroy(e);
     h->d_llpart.release(); h->d_flush.release(); h->d_flush_sink.release(); h->d_bar.release();
-    for (auto& e : h->sev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } h->d_pv.release(); h->d_pvoff.release(); h->d_pcoff.release(); h->d_pidx.release(); h->d_pcarc.release();
+    for (auto& e : h->sev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     h->d_e6ctl.release(); h->d_e6acc.release(); h->d_e6red.release(); h->d_e6stamps.release(); h->d_arc_tp.release(); h->d_e6cls.release();
     if (h->e6_exec) cudaGraphExecDestroy(h->e6_exec);
     if (h->e6_graph) cudaGraphDestroy(h->e6_graph);
@@ -631,20 +630,6 @@ static int upload_transposed_tokens(wfsa_dev* h, const std::vector<int32_t>& ord
     return WFSA_OK;
 }
 
-// Launch with the programmatic-stream-serialization attribute: the grid may be set up (and run up to its
-// cudaGridDependencySynchronize()) while the previous kernel in the stream drains.  pdl = false: a plain launch.
-template <class Kern, class Params>
-static void launch_dep(Kern kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, const Params& params)
-{
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kernel, params);
-}
-
 static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, const EvalOutD& O)
 {
     const HostFsa& F = h->fsa;
@@ -652,20 +637,16 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
     cudaStream_t st = h->stream;
     if (C.n_order <= 0) return;
     if (kernel == 6) {
-        if (!h->lean_now) cudaMemsetAsync(h->d_klcounter.p, 0, 8, st);
+        // (the general path: evaluations with overflow strings, or without the single-launch kernel)
+        cudaMemsetAsync(h->d_klcounter.p, 0, 8, st);
         if (h->kr_groups > 0) {
             KRParams P{};
             P.aw = h->d_klaw.p; P.words = h->d_krwords.p; P.goff = h->d_krgoff.p; P.grows = h->d_krgrows.p; P.typeW = h->d_krW.p;
             P.lq = h->d_krlq.p; P.n_groups = h->kr_groups; P.xs = h->d_klxs.p; P.xs_rows = (size_t)std::max<int64_t>(h->kl_max_words, 1);
             P.counter = h->d_klcounter.p; P.acc = h->d_klacc.p; P.fx_scale = O.fx_scale; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas;
-            P.n_first = h->kr_big_groups; P.stride = h->kr_stride;
             P.ll_scale = O.ll_scale; P.red = O.red; P.llpart = h->d_llpart.p; P.n_llpart = h->llpart_n;
-            P.pv = (h->lean_now && h->pull && h->n_pchunks > 0) ? h->d_pv.p : nullptr; P.pvoff = h->d_pvoff.p;
-            if (h->opt.reserved & 2) kr_regions<ACC_NONE, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // timing experiment
-            else if (h->opt.reserved & 1) kr_regions<ACC_SMEM_CAS, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // plain REDs
-            else if (h->kl_block <= 512) launch_dep(kr_regions<ACC_GLOBAL, 512>, dim3(h->kl_grid), dim3(h->kl_block), h->kl_smem, st, h->pdl_now, P);
-            else if (h->kl_block <= 768) kr_regions<ACC_GLOBAL, 768><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
-            else kr_regions<ACC_GLOBAL, 1024><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
+            if (h->opt.reserved & 2) kr_regions<ACC_NONE, 512><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // timing experiment
+            else kr_regions<ACC_GLOBAL, 512><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
             h->launches++;
         }
         if (h->mid_now) cudaEventRecord(h->mid_now, st);
@@ -675,11 +656,6 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
         h->ks_done = false;
         if (h->kr_groups == 0 && h->larcs.n_arcs > 0) {          // no region at all (unique paths): the bridge part on its own
             k_add_llpart<<<1, 32, 0, st>>>(h->d_llpart.p, h->llpart_n, O.red);
-            h->launches++;
-        }
-        if (h->lean_now && h->pull && h->n_pchunks > 0) {       // experiment: per-arc gather of the stored path values
-            k_pull_paths<<<(unsigned)((h->n_pchunks + 7) / 8), 256, 0, st>>>(h->n_pchunks, h->d_pcoff.p, h->d_pcarc.p, h->d_pidx.p,
-                                                                             h->d_pv.p, h->d_klacc.p);
             h->launches++;
         }
     } else if (kernel == 5) {
@@ -772,7 +748,9 @@ static void fill_eval6_params(wfsa_dev* h, Eval6Params& P)
     P = Eval6Params{};
     P.words = h->d_krwords.p; P.goff = h->d_krgoff.p; P.grows = h->d_krgrows.p; P.typeW = h->d_krW.p; P.lq = h->d_krlq.p;
     P.n_groups = h->kr_groups; P.n_big = h->kr_big_groups; P.cls = h->d_e6cls.p; P.n_cls = h->e6_ncls;
-    P.static_pct = getenv("WFSA_E6_STATIC") ? std::min(100, std::max(0, atoi(getenv("WFSA_E6_STATIC")))) : 85;
+    // static share of the regular groups: 70 % measured best for the full corpus; none when CTAs are dedicated to their big
+    // groups first (a CTA that starts late cannot give its static share away)
+    P.static_pct = getenv("WFSA_E6_STATIC") ? std::min(100, std::max(0, atoi(getenv("WFSA_E6_STATIC")))) : 70;
     P.xs = h->d_klxs.p; P.xs_rows = (size_t)std::max<int64_t>(h->kl_max_words, 1);
     P.arc_tp = h->d_arc_tp.p; P.x = h->d_x.p; P.n = h->n; P.n_arcs = h->larcs.n_arcs;
     P.direct_exp = (size_t)h->n > (size_t)h->kl_block * h->kl_K ? 1 : 0;
@@ -786,6 +764,7 @@ static void fill_eval6_params(wfsa_dev* h, Eval6Params& P)
     P.debug = getenv("WFSA_E6_DEBUG") ? atoi(getenv("WFSA_E6_DEBUG")) : 0;
     P.pool_slots = h->kl_K; P.big_slots = h->e6_big_slots; P.big_rows = h->e6_big_rows;
     P.big_dedicate = (h->kr_big_groups > 0 && h->kr_big_groups * 4 <= h->kl_grid && !getenv("WFSA_E6_NO_DEDICATE")) ? 1 : 0;
+    if (P.big_dedicate && !getenv("WFSA_E6_STATIC")) P.static_pct = 0;
 }
 
 static cudaError_t launch_eval6(wfsa_dev* h, cudaStream_t st, bool count = true)
@@ -797,7 +776,7 @@ static cudaError_t launch_eval6(wfsa_dev* h, cudaStream_t st, bool count = true)
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative;             // all CTAs resident: the grid barrier and the exchange rely on it
     at[0].val.cooperative = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.attrs = at; cfg.numAttrs = getenv("WFSA_E6_PLAIN_LAUNCH") ? 0 : 1;
     cudaError_t e;
     if (h->kl_block == 512) e = cudaLaunchKernelEx(&cfg, k_eval6<512>, P);
     else if (h->kl_block == 384) e = cudaLaunchKernelEx(&cfg, k_eval6<384>, P);
@@ -844,18 +823,7 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
         return WFSA_OK;
     }
     if (mode == MODE_EVAL) h->e6_used = false;
-    if (lean6) {
-        Prep6Params P{};
-        P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas; P.n_red = (int)h->d_red.n; P.n_out = (int)h->d_out.n;
-        P.arc_tid = h->d_kl_arc_tid.p; P.arc_eid = h->d_kl_arc_eid.p; P.trans_tp = h->d_trans_tp.p; P.emis_tp = h->d_emis_tp.p;
-        P.x = h->d_x.p; P.const_acc = h->d_klconst.p; P.aw = h->d_klaw.p; P.logaw = h->d_klogaw.p; P.acc = h->d_klacc.p;
-        P.red = h->d_red.p; P.counters = h->d_klcounter.p; P.out = h->d_out.p;
-        P.inv_fx = std::ldexp(1.0, -(int)h->fx_log2); P.ll_scale = std::ldexp(1.0, (int)h->ll_log2); P.llpart = h->d_llpart.p;
-        const int total = std::max({P.n_arcs * P.replicas, P.n_red, P.n_out, 2});
-        k_prep6<<<(total + 255) / 256, 256, 0, st>>>(P);
-        h->llpart_n = (P.n_arcs + 255) / 256;
-        h->launches++;
-    } else if (clear) {
+    if (clear) {
         CK(cudaMemsetAsync(h->d_red.p, 0, h->d_red.n * 8, st));
         if (h->fast.ok) CK(cudaMemsetAsync(h->d_acc.p, 0, h->d_acc.n * 8, st));
         const int n_slots = h->fast.ok ? h->fast.n_slots : 0;
@@ -906,42 +874,12 @@ static int launch_pipeline(wfsa_dev* h, int mode, int kernel, const int32_t* d_o
         if (h->kev_used < h->kev.size()) { e0 = h->kev[h->kev_used].first; e1 = h->kev[h->kev_used].second; h->mid_now = h->kev_mid[h->kev_used]; h->kev_used++; }
     }
     if (e0) cudaEventRecord(e0, st);
-    h->lean_now = lean6;
-    // dependent launches only when no event sits between the kernels (an event record serialises the stream)
-    h->pdl_now = lean6 && !e0 && h->pdl;
+    h->lean_now = false;
     launch_main(h, kernel, mode, CorpusD{h->d_tokens.p, h->d_offs.p, h->d_p.p, d_order, n_order}, O);
     if (kernel2) launch_main(h, kernel2, mode, CorpusD{h->d_tokens.p, h->d_offs.p, h->d_p.p, d_order2, n_order2}, O);
     if (e1) cudaEventRecord(e1, st);
     h->mid_now = nullptr;
     CK(cudaGetLastError());
-    if (lean6) {
-        Fin6Params P{};
-        P.n_edges = h->n_edges; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas; P.n = h->n; P.finish = h->comm ? 0 : 3;
-        P.e_off = h->d_eoff.p; P.e_arc = h->d_earc.p; P.acc = h->d_klacc.p; P.red = h->d_red.p; P.edge_tp = h->d_edge_tp.p;
-        P.inv_fx = std::ldexp(1.0, -(int)h->fx_log2); P.inv_ll = std::ldexp(1.0, -(int)h->ll_log2); P.out = h->d_out.p;
-        const int words = 2 + h->n_edges;
-        const int grid_f = (words + 7) / 8;
-        if (h->comm && h->peer_ok && h->peer_words == words && grid_f <= h->fold_peer_ctas && !getenv("WFSA_PEER_SINGLE_CTA")) {
-            // fold, all-reduce over peer memory and conversion in one launch; its warps wait for the peers' packets,
-            // so the whole grid must be resident (fold_peer_ctas: occupancy x SMs)
-            FoldPeerParams Q{};
-            Q.F = P;
-            for (int r = 0; r < h->nranks; ++r) Q.peers[r] = h->peer_ptrs[r];
-            Q.ll_off = h->peer_ll_off; Q.nranks = h->nranks; Q.rank = h->rank; Q.words = words;
-            ++h->peer_ll_epoch;
-            Q.flag = (unsigned int)(h->peer_ll_epoch % 0xfffffffeull) + 1u; Q.parity = (int)(h->peer_ll_epoch & 1ull);
-            launch_dep(k_fold_allreduce_finish6, dim3(grid_f), dim3(256), 0, st, h->pdl_now, Q);
-            h->launches++;
-            CK(cudaGetLastError());
-            h->lean_finished = true;
-            return WFSA_OK;
-        }
-        launch_dep(k_fold_finish6, dim3((std::max(h->n_edges, 1) + 7) / 8), dim3(256), 0, st, h->pdl_now, P);      // one warp per edge
-        h->launches++;
-        CK(cudaGetLastError());
-        h->lean_finished = !h->comm;
-        return WFSA_OK;
-    }
     h->lean_finished = false;
     if (fold && (kernel == 5 || kernel == 6)) {
         const int na = h->larcs.n_arcs;
@@ -1099,13 +1037,6 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
         h->n_active = (int64_t)order.size() - (int64_t)order_w.size(); h->n_active_w = (int64_t)order_w.size();
         h->kr_big_groups = 0;
         for (int32_t r : sc.rgrows) if (!(r & 0x10000) && r > kSegSmallMax) h->kr_big_groups++;      // big DAG classes sort first
-        {
-            const int64_t rest = (int64_t)sc.rgrows.size() - h->kr_big_groups;
-            int64_t stride = getenv("WFSA_KR_STRIDE") ? atoll(getenv("WFSA_KR_STRIDE")) : 1;     // tuning knob; 1 = sorted order (measured best)
-            stride = rest > 1 ? stride % rest : 1;
-            while (stride > 1 && std::__gcd(stride, rest) != 1) --stride;
-            h->kr_stride = std::max<int64_t>(stride, 1);
-        }
         h->kr_groups = (int64_t)sc.rgrows.size(); h->ks_groups = 0;                                 // KS: set by ensure_ks()
         h->seg_types = sc.n_types; h->seg_instances = sc.n_region_instances; h->seg_region_edges = sc.n_region_edges;
         h->seg_type_edges = sc.n_type_edges; h->seg_bridges = sc.n_bridge; h->seg_host_ms = sc.host_ms;
@@ -1113,11 +1044,6 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
         h->kl_max_words = sc.max_big_rows;
         CK(h->d_krwords.upload(sc.rwords, h->stream)); CK(h->d_krgoff.upload(sc.rgoff, h->stream));
         CK(h->d_krgrows.upload(sc.rgrows, h->stream)); CK(h->d_krW.upload(sc.typeW, h->stream));
-        h->pull = getenv("WFSA_PULL") != nullptr;        // off by default: measured slower
-        h->pdl = getenv("WFSA_NO_PDL") == nullptr;       // programmatic dependent launches between the three kernels of an evaluation
-        h->n_pchunks = (int64_t)sc.pcarc.size();
-        CK(h->d_pv.alloc(std::max<size_t>((size_t)sc.n_pv, 1))); CK(h->d_pvoff.upload(sc.pvoff, h->stream));
-        CK(h->d_pcoff.upload(sc.pcoff, h->stream)); CK(h->d_pidx.upload(sc.pidx, h->stream)); CK(h->d_pcarc.upload(sc.pcarc, h->stream));
         CK(h->d_krlq.alloc((size_t)h->kr_groups * 32 + 1));
         CK(cudaMemsetAsync(h->d_krlq.p, 0, h->d_krlq.n * 8, h->stream));
         std::vector<unsigned long long> cacc(sc.const_acc.begin(), sc.const_acc.end());
@@ -1272,8 +1198,8 @@ static int setup_peer_allreduce(wfsa_dev* h)
     const int words = (int)h->d_red.n;
     if (h->peer_local && h->peer_words == words) { h->peer_ok = true; return WFSA_OK; }
     if (h->peer_local) return WFSA_OK;                       // sized for another parameter map: keep NCCL (rare)
-    // [data of the single-CTA kernel: 2 x nranks x words][its flags: 2 x nranks][packets of the fused kernel: 2 x nranks x words x 2]
-    h->peer_ll_off = (size_t)2 * h->nranks * words + (size_t)2 * h->nranks;
+    // [packets of k_eval6: 2 parities x nranks senders x words x 2][words of k_peer_barrier: 2 x nranks]
+    h->peer_ll_off = 0;
     h->peer_bar_off = h->peer_ll_off + (size_t)4 * h->nranks * words;       // then the words of k_peer_barrier: 2 x nranks
     const size_t total = h->peer_bar_off + (size_t)2 * h->nranks;
     unsigned long long ok = 1;
@@ -1316,12 +1242,7 @@ static int setup_peer_allreduce(wfsa_dev* h)
     CK(cudaMemcpyAsync(&bad, d_flag, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->peer_words = words;
-    h->peer_epoch = 0; h->peer_ll_epoch = 0; h->peer_bar_epoch = 0;
-    {
-        int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fold_allreduce_finish6, 256, 0) != cudaSuccess) { nb = 0; cudaGetLastError(); }
-        h->fold_peer_ctas = nb * h->sm_count;
-    }
+    h->peer_bar_epoch = 0;
     h->peer_ok = bad == 0;
     return WFSA_OK;
 }
@@ -1352,21 +1273,9 @@ static int eval_launch_body(wfsa_dev* h)
                              h->kernel >= 4 ? h->secondary : 0, h->d_order_w.p, h->n_active_w, true, true);
     if (rc != WFSA_OK) return rc;
     if (h->lean_finished) return WFSA_OK;          // k_fold_finish6 already wrote [loglik, bad, grad]
-    if (h->comm && h->peer_ok) {
-        PeerParams P{};
-        for (int r = 0; r < h->nranks; ++r) P.peers[r] = h->peer_ptrs[r];
-        P.nranks = h->nranks; P.rank = h->rank; P.words = h->peer_words; P.n_edges = h->n_edges; P.n = h->n; P.rearm = 0;
-        P.epoch = ++h->peer_epoch; P.red = h->d_red.p; P.edge_tp = h->d_edge_tp.p;
-        P.inv_fx = std::ldexp(1.0, -(int)h->fx_log2); P.inv_ll = std::ldexp(1.0, -(int)h->ll_log2); P.out = h->d_out.p;
-        if (!h->lean_now) CK(cudaMemsetAsync(h->d_out.p, 0, h->d_out.n * 8, h->stream));
-        k_peer_allreduce_finish<<<1, 1024, 0, h->stream>>>(P);
-        h->launches++;
-        CK(cudaGetLastError());
-        return WFSA_OK;
-    }
     rc = nccl_allreduce(h, h->d_red.p, h->d_red.n, ncclUint64, ncclSum);
     if (rc != WFSA_OK) return rc;
-    if (!h->lean_now) CK(cudaMemsetAsync(h->d_out.p, 0, h->d_out.n * 8, h->stream));   // k_prep6 already cleared it
+    CK(cudaMemsetAsync(h->d_out.p, 0, h->d_out.n * 8, h->stream));
     const int total = std::max(h->n_edges, 1);
     k_finish_eval<<<(total + 255) / 256, 256, 0, h->stream>>>(h->n_edges, h->n, h->d_red.p, h->d_edge_tp.p,
                                                              std::ldexp(1.0, -(int)h->fx_log2), std::ldexp(1.0, -(int)h->ll_log2), h->d_out.p);
@@ -1877,7 +1786,7 @@ extern "C" int wfsa_segmented_get(const wfsa_segmented* s, int which, const void
     switch (which) {
         SEG_ARR(0, c.rwords) SEG_ARR(1, c.rgoff) SEG_ARR(2, c.rgrows) SEG_ARR(3, c.typeW) SEG_ARR(4, c.swords) SEG_ARR(5, c.sgoff)
         SEG_ARR(6, c.sgref) SEG_ARR(7, c.ksid) SEG_ARR(8, c.kp) SEG_ARR(9, c.overflow) SEG_ARR(10, c.rejected) SEG_ARR(11, c.const_acc)
-        SEG_ARR(12, s->stats) SEG_ARR(13, c.pvoff) SEG_ARR(14, c.pidx) SEG_ARR(15, c.pcoff) SEG_ARR(16, c.pcarc)
+        SEG_ARR(12, s->stats)
         default: return WFSA_ERR_INVALID;
     }
 #undef SEG_ARR
@@ -1914,5 +1823,9 @@ extern "C" int wfsa_dev_get_info(wfsa_dev* h, wfsa_dev_info* info)
     }
     info->n_active_strings = h->n_active + h->n_active_w; info->table_bytes = (int64_t)h->table_bytes;
     info->kernels_launched = h->launches; info->fixed_point_scale_log2 = h->fx_log2;
+    {
+        const bool single = h->kernel == 6 && h->e6_ok && !h->any_overflow && h->n >= 0;
+        info->eval_path = (single ? 1 : 0) | (single && h->comm ? 2 : 0) | (!single && h->comm ? 4 : 0) | (h->any_overflow ? 8 : 0);
+    }
     return WFSA_OK;
 }

@@ -57,7 +57,7 @@ class DevInfo(C.Structure):
                 ("n_tokens", C.c_int64), ("n_active_tokens", C.c_int64), ("smem_bytes", C.c_int64),
                 ("table_bytes", C.c_int64), ("kernels_launched", C.c_int64), ("fixed_point_scale_log2", C.c_double),
                 ("lattice_words", C.c_int64), ("lattice_edges", C.c_int64), ("lattice_bridge_edges", C.c_int64),
-                ("n_overflow_strings", C.c_int64), ("pool_slots", C.c_int32), ("reserved", C.c_int32),
+                ("n_overflow_strings", C.c_int64), ("pool_slots", C.c_int32), ("eval_path", C.c_int32),
                 ("seg_types", C.c_int64), ("seg_region_instances", C.c_int64), ("seg_region_edges", C.c_int64),
                 ("seg_type_edges", C.c_int64), ("seg_host_ms", C.c_double)]
 
@@ -155,8 +155,7 @@ def lib():
 
 _SEG_ARRAYS = [("rwords", np.uint32), ("rgoff", np.int64), ("rgrows", np.int32), ("typeW", np.float64), ("swords", np.uint32),
                ("sgoff", np.int64), ("sgref", np.int32), ("ksid", np.int32), ("kp", np.float64), ("overflow", np.int32),
-               ("rejected", np.int32), ("const_acc", np.int64), ("stats", np.int64), ("pvoff", np.int64), ("pidx", np.int32),
-               ("pcoff", np.int64), ("pcarc", np.int32)]
+               ("rejected", np.int32), ("const_acc", np.int64), ("stats", np.int64)]
 
 
 def segmented_compile(lowered, trimmed=None, n_slots=16, fx_scale=1.0):
