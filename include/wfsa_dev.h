@@ -215,7 +215,9 @@ int wfsa_lattice_stats(const wfsa_fsa_desc* fsa, const wfsa_corpus_desc* corpus,
  * (1..16), plus 64 to keep every region in DAG form (no path lists).
  * which: 0 rwords(u32) 1 rgoff(i64) 2 rgrows(i32) 3 typeW(f64) 4 swords(u32) 5 sgoff(i64) 6 sgref(i32)
  *        7 ksid(i32) 8 kp(f64) 9 overflow(i32) 10 rejected(i32) 11 const_acc(i64)
- *        12 stats(i64): types, region instances, instance edges, type edges, bridges, strings, host microseconds */
+ *        12 stats(i64): types, region instances, instance edges, type edges, bridges, strings, host microseconds
+ *        13 path_off(i64) 14 col_off(i64) 15 val_off(i64) 16 cols(i32) 17 counts(f64) 18 p(f64) 19 type slot(i32): the path blocks
+ *           wfsa_dev_hessian derives from the region types (layout of wfsa_path_blocks, p = weight of the type) */
 typedef struct wfsa_segmented wfsa_segmented;
 int wfsa_segmented_compile(const wfsa_fsa_desc* fsa, const wfsa_corpus_desc* corpus, const int32_t* trimmed,
                            int32_t n_slots, double fx_scale, wfsa_segmented** out);

@@ -238,3 +238,40 @@ def test_trimmed_arcs_are_removed_from_segments():
     seg, _, _, olq, handled = check(low, trimmed, x)
     for s in range(80):
         assert (s in handled) == bool(np.isfinite(olq[s]))
+
+
+def _hessian_from_blocks(seg, x, n):
+    """numpy restatement of k5_hessian over the path blocks the library derives from the region types."""
+    H = np.zeros((n, n))
+    po, co, vo = seg["hb_path_off"], seg["hb_col_off"], seg["hb_val_off"]
+    for b in range(len(seg["hb_p"])):
+        c = seg["hb_cols"][co[b]:co[b + 1]]
+        M = seg["hb_counts"][vo[b]:vo[b + 1]].reshape(po[b + 1] - po[b], len(c))
+        s = M @ x[c]
+        r = np.exp(s - s.max()); r /= r.sum()
+        g = M.T @ r
+        H[np.ix_(c, c)] += seg["hb_p"][b] * (np.outer(g, g) - M.T @ (r[:, None] * M))
+    return H
+
+
+@pytest.mark.parametrize("case", good_cases(("fixtures", "random")), ids=lambda c: c["name"])
+def test_hessian_blocks_from_region_types(case):
+    """H_f = -sum_types W_type Cov_type(c_j, c_k): the path blocks built from the compiled region types (no enumeration per
+    string; wfsa_dev.cu make_type_blocks) against the enumeration of every path of every string, which is what
+    HessianLearner::ComputeHf does (/root/reference/src/HessianLearner.cpp:498-547; restated in oracle/wfsa_oracle.c)."""
+    d = W.parse(case["fsa_text"], case["corpus_text"])
+    low = W.Lowered(d)
+    zt, ze = np.zeros(low.n_trans), np.zeros(low.n_emis)
+    _, _, ee0 = O.dp_eval(low, zt, ze, want_counts=True)
+    trimmed, n, _ = O.trim(low, ee0 > 0)
+    if n == 0:
+        pytest.skip("no parameters")
+    x = np.random.RandomState(8).normal(-1.0, 0.7, size=n)
+    seg = W.segmented_compile(low, trimmed, n_slots=16, fx_scale=FX)
+    assert len(seg["overflow"]) == 0
+    H = _hessian_from_blocks(seg, x, n)
+    ltw, lew = low.edge_logweights(x, trimmed)
+    params = np.concatenate([low.trans_param, low.emis_param])
+    edge_param = np.array([trimmed[r] if r >= 0 and trimmed[r] >= 0 else -1 for r in params], dtype=np.int32)
+    Href = O.enum_hessian(low, ltw, lew, edge_param, n)
+    assert np.allclose(H, Href, rtol=1e-10, atol=1e-13), np.abs(H - Href).max()

@@ -416,6 +416,73 @@ def test_two_ranks_nccl(kernel, variant):
     assert r.returncode == 0 and "nccl_worker ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+def _device_hessian(dev, x, n):
+    import ctypes as C
+    H = np.zeros((n, n)); rmin = C.c_double()
+    xx = np.ascontiguousarray(x, dtype=np.float64)
+    dev._ck(dev.L.wfsa_dev_hessian(dev.h, W._p(xx, W.F64P), W._p(H, W.F64P), C.byref(rmin)))
+    return H, rmin.value
+
+
+def test_hessian_from_region_types_matches_enumeration(medium):
+    """H_f with NO path enumeration per string: the segmented backend takes the blocks of the contraction from its
+    compiled region types (Cov adds over the independent regions of a string, wfsa_dev.cu build_type_blocks).
+    Checked against the CPU enumeration of every path of every string (HessianLearner::ComputeHf,
+    /root/reference/src/HessianLearner.cpp:498-547, restated in oracle/wfsa_oracle.c), 1e-9 per entry."""
+    model, low = medium
+    dev, rec, pc, trimmed, n = build_device(low, force_kernel=6)
+    assert dev.info()["kernel"] == 6
+    x = np.random.RandomState(21).normal(-1.0, 0.5, size=n)
+    H, rmin = _device_hessian(dev, x, n)
+    dev.close()
+    ltw, lew = low.edge_logweights(x, trimmed)
+    params = np.concatenate([low.trans_param, low.emis_param])
+    edge_param = np.array([trimmed[r] if r >= 0 else -1 for r in params], dtype=np.int32)
+    edge_param[edge_param < 0] = -1
+    keep = np.where(rec > 0)[0]
+    sub = type(low).__new__(type(low)); sub.__dict__.update(low.__dict__)
+    offs = np.concatenate([[0], np.cumsum((low.offsets[1:] - low.offsets[:-1])[keep])])
+    toks = np.concatenate([low.tokens[low.offsets[i]:low.offsets[i + 1]] for i in keep])
+    sub.set_tokens(offs, toks, low.p[keep])
+    Href = O.enum_hessian(sub, ltw, lew, edge_param, n, max_paths=20000000)
+    assert np.allclose(H, H.T, rtol=0, atol=1e-15)
+    ok, err = vec_tol_ok(H.reshape(-1), Href.reshape(-1), rtol=1e-9)
+    assert ok, err
+    assert 0.0 < rmin <= 0.5
+
+
+def test_hessian_at_scale_without_path_enumeration():
+    """100 000 config-4-shaped strings (about 1.5 M paths): the host enumeration of round 1 refused corpora beyond
+    4e6 paths; the type-derived blocks have no such limit.  Properties: symmetric, negative semi-definite
+    (H_f = -sum_s p_s Cov_s), rows of a constraint group sum to zero against the group's indicator ... and additive:
+    the sum of H_f over two halves of the corpus equals H_f of the whole."""
+    model = synth.make_model(256, 64, 8, 4, seed=1234)
+    low = model.lowered()
+    offs, toks, w = model.corpus(100000, 32, 128, seed=77)
+    low.set_tokens(offs, toks, w / w.sum())
+    dev, rec, pc, trimmed, n = build_device(low)
+    assert dev.info()["kernel"] == 6 and pc.sum() > 1.0e6
+    x = np.random.RandomState(5).normal(-1.0, 0.3, size=n)
+    H, rmin = _device_hessian(dev, x, n)
+    dev.close()
+    assert np.isfinite(H).all() and np.abs(H - H.T).max() <= 1e-15 and 0.0 < rmin < 1e-3
+    rng = np.random.RandomState(6)
+    for _ in range(5):
+        v = rng.normal(size=n)
+        assert v @ H @ v <= 1e-12
+    half = 50000
+    Hs = np.zeros_like(H)
+    for first, count in ((0, half), (half, 100000 - half)):
+        d2 = W.Device(low, first=first, count=count)
+        d2.structure()
+        d2.set_param_map(trimmed, n, None)
+        Hh, _ = _device_hessian(d2, x, n)
+        d2.close()
+        Hs += Hh
+    # every block adds its entries rounded to the fixed-point quantum of H (2^-52 here): absolute error ~ blocks x quantum
+    assert np.allclose(Hs, H, rtol=1e-9, atol=1e-13), np.abs(Hs - H).max()
+
+
 def test_hessian_contraction_random_blocks():
     """K5 (FP64 tensor-core contraction) on random dense path blocks against numpy."""
     rng = np.random.RandomState(9)

@@ -1454,6 +1454,8 @@ struct HessParams {
     double* rmin;                    // [1] smallest path posterior (atomicMin on bits)
     int n;
     double fx_scale;
+    const int32_t* __restrict__ blk_slot;   // blocks = region types: type slot of block b, or nullptr
+    double* slot_lrmin;              // [type slots] log of the smallest path posterior of the type
 };
 
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b)
@@ -1496,6 +1498,7 @@ __global__ void __launch_bounds__(256) k5_hessian(const HessParams P)
 #pragma unroll
         for (int o = 16; o; o >>= 1) rm = fmin(rm, __shfl_xor_sync(FULL, rm, o));
         if (lane == 0 && P.rmin) atomicMin(reinterpret_cast<unsigned long long*>(P.rmin), (unsigned long long)__double_as_longlong(rm));
+        if (lane == 0 && P.blk_slot) P.slot_lrmin[P.blk_slot[b]] = log(rm);
         __syncwarp();
         // 8x8 output tiles; DMMA fragment layout (m8n8k4): A[row=lane/4][k=lane%4],
         // B[k=lane%4][col=lane/4], C[row=lane/4][col=2*(lane%4)+{0,1}]
@@ -1548,6 +1551,19 @@ __global__ void __launch_bounds__(256) k5_hessian(const HessParams P)
         }
         __syncwarp();
     }
+}
+
+// rmin = exp(min over the strings of the summed log rmin of their regions); one CTA
+__global__ void k_min_exp(long long n, const double* __restrict__ v, double* out)
+{
+    __shared__ double s_m[32];
+    double m = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) m = fmin(m, v[i]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmin(m, __shfl_xor_sync(FULL, m, o));
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) { for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmin(m, s_m[w]); *out = exp(m); }
 }
 
 __global__ void k_fx_to_double(size_t n, const unsigned long long* __restrict__ in, double inv, double* out)

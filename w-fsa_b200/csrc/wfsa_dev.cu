@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <map>
 #include <memory>
 #include <string>
 #include <thread>
@@ -167,6 +168,11 @@ struct wfsa_dev {
     DevBuf<double> d_hb_counts, d_hb_p, d_hb_r, d_H, d_rmin;
     DevBuf<unsigned long long> d_Hfx;
     int64_t hb_blocks = -1, hb_paths = 0;
+    // H_f from the compiled region types (no path enumeration per string): host copy of the KR arrays, kept by set_param_map
+    std::vector<uint32_t> hrw; std::vector<int64_t> hrgoff; std::vector<int32_t> hrgrows; std::vector<double> hrW;
+    std::vector<int32_t> h_ttp, h_etp;
+    bool hb_from_types = false, hb_user = false;
+    DevBuf<int32_t> d_hb_slot; DevBuf<double> d_type_lrmin, d_zero_logaw, d_rmin_part;
     int hb_fx_log2 = 40;
     // comm
     ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
@@ -1088,6 +1094,11 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
             if (e != cudaSuccess) return set_err(h, WFSA_ERR_NOMEM, "segmented kernel: cannot allocate the per-warp x stacks");
         }
         CK(cudaStreamSynchronize(h->stream));
+        // the region types stay on the host as well: wfsa_dev_hessian derives its path blocks from them
+        h->hrw = std::move(sc.rwords); h->hrgoff = std::move(sc.rgoff); h->hrgrows = std::move(sc.rgrows); h->hrW = std::move(sc.typeW);
+        h->h_ttp = ttp; h->h_etp = etp;
+        if (!h->hb_user) h->hb_blocks = -1;
+        h->hb_from_types = false;
     }
     if (h->kernel == 5) {
         // compile the trimmed lattice of every participating string (structure is independent of x)
@@ -1398,6 +1409,40 @@ extern "C" int wfsa_dev_eval(wfsa_dev* h, const double* x, double* loglik, doubl
 }
 
 // ---------------------------------------------------------------------------------------------
+// uploads validated path blocks and fixes the fixed-point scale of H (collective when a communicator is attached)
+static int upload_path_blocks(wfsa_dev* h, const std::vector<int64_t>& po, const std::vector<int64_t>& co, const std::vector<int64_t>& vo,
+                              const std::vector<int32_t>& cols, const std::vector<double>& counts, const std::vector<double>& p,
+                              const std::vector<int32_t>* slots, unsigned long long local_error)
+{
+    const int64_t nb = (int64_t)p.size();
+    CK(h->d_hb_path_off.upload(po, h->stream)); CK(h->d_hb_col_off.upload(co, h->stream)); CK(h->d_hb_val_off.upload(vo, h->stream));
+    CK(h->d_hb_cols.upload(cols, h->stream)); CK(h->d_hb_counts.upload(counts, h->stream)); CK(h->d_hb_p.upload(p, h->stream));
+    if (slots) CK(h->d_hb_slot.upload(*slots, h->stream)); else h->d_hb_slot.release();
+    CK(h->d_hb_r.alloc(std::max<int64_t>(po[nb], 1)));
+    CK(h->d_Hfx.alloc(std::max<size_t>((size_t)h->n * h->n, 1)));
+    CK(h->d_H.alloc(std::max<size_t>((size_t)h->n * h->n, 1)));
+    CK(h->d_rmin.alloc(1));
+    CK(cudaStreamSynchronize(h->stream));
+    // fixed-point scale of H: |H_jk| <= sum_s p_s * cmax^2 <= cmax^2 (p sums to <= 1 over all ranks)
+    double cmax = 1.0;
+    for (double c : counts) cmax = std::max(cmax, std::fabs(c));
+    long long v[2] = {(long long)std::ceil(cmax * cmax) + 1, (long long)local_error};
+    if (h->comm) {         // every rank must see a failure of any rank BEFORE the all-reduce of H (a rank that returned early would leave the others waiting)
+        long long* d = reinterpret_cast<long long*>(h->d_red.p);
+        CK(cudaMemcpyAsync(d, v, 16, cudaMemcpyHostToDevice, h->stream));
+        int rc = nccl_allreduce(h, d, 2, ncclInt64, ncclMax);
+        if (rc != WFSA_OK) return rc;
+        CK(cudaMemcpyAsync(v, d, 16, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (v[1]) return set_err(h, WFSA_ERR_LIMIT, local_error ? h->err : "H_f blocks: another rank could not build its path blocks");
+    int bits = 1;
+    while ((1ll << bits) <= v[0] && bits < 50) ++bits;
+    h->hb_fx_log2 = 61 - bits;
+    h->hb_blocks = nb; h->hb_paths = po[nb];
+    return WFSA_OK;
+}
+
 extern "C" int wfsa_dev_set_path_blocks(wfsa_dev* h, const wfsa_path_blocks* b)
 {
     if (!h || !b || b->n_blocks < 0) return set_err(h, WFSA_ERR_INVALID, "set_path_blocks: bad arguments");
@@ -1412,36 +1457,140 @@ extern "C" int wfsa_dev_set_path_blocks(wfsa_dev* h, const wfsa_path_blocks* b)
     std::vector<int32_t> cols(b->cols, b->cols + co[nb]);
     for (int32_t c : cols) if (c < 0 || c >= h->n) return set_err(h, WFSA_ERR_INVALID, "set_path_blocks: column out of range");
     std::vector<double> counts(b->counts, b->counts + vo[nb]), p(b->p, b->p + nb);
-    CK(h->d_hb_path_off.upload(po, h->stream)); CK(h->d_hb_col_off.upload(co, h->stream)); CK(h->d_hb_val_off.upload(vo, h->stream));
-    CK(h->d_hb_cols.upload(cols, h->stream)); CK(h->d_hb_counts.upload(counts, h->stream)); CK(h->d_hb_p.upload(p, h->stream));
-    CK(h->d_hb_r.alloc(std::max<int64_t>(po[nb], 1)));
-    CK(h->d_Hfx.alloc(std::max<size_t>((size_t)h->n * h->n, 1)));
-    CK(h->d_H.alloc(std::max<size_t>((size_t)h->n * h->n, 1)));
-    CK(h->d_rmin.alloc(1));
-    CK(cudaStreamSynchronize(h->stream));
-    // fixed-point scale of H: |H_jk| <= sum_s p_s * cmax^2 <= cmax^2 (p sums to <= 1 over all ranks)
-    double cmax = 1.0;
-    for (double c : counts) cmax = std::max(cmax, std::fabs(c));
-    long long bound = (long long)std::ceil(cmax * cmax) + 1;
-    if (h->comm) {
-        long long* d = reinterpret_cast<long long*>(h->d_red.p);
-        CK(cudaMemcpyAsync(d, &bound, 8, cudaMemcpyHostToDevice, h->stream));
-        int rc = nccl_allreduce(h, d, 1, ncclInt64, ncclMax);
-        if (rc != WFSA_OK) return rc;
-        CK(cudaMemcpyAsync(&bound, d, 8, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-    }
-    int bits = 1;
-    while ((1ll << bits) <= bound && bits < 50) ++bits;
-    h->hb_fx_log2 = 61 - bits;
-    h->hb_blocks = nb; h->hb_paths = po[nb];
-    return WFSA_OK;
+    h->hb_user = true; h->hb_from_types = false;
+    return upload_path_blocks(h, po, co, vo, cols, counts, p, nullptr, 0);
 }
+
+// H_f without enumerating the paths of any STRING.  Counts add over the segments of a string and the segments are
+// independent given the string, so Cov_s(c_j, c_k) = sum over the REGIONS of s of Cov_region(c_j, c_k) (bridges have
+// no variance), and with the type weights W = sum of p_s over the instances
+//     H_f = - sum_types W_type * Cov_type(c_j, c_k):
+// the blocks of k5_hessian are the distinct region types of the compiled corpus.  Path-form types are their own path
+// list; the paths of a DAG-form type are enumerated from its words (a region, not a string: bounded by max_paths).
+// Replaces the per-string BFS of Learner::BuildPaths feeding HessianLearner::ComputeHf (src/HessianLearner.cpp:498-547).
+struct TypeBlocks {
+    std::vector<int64_t> po{0}, co{0}, vo{0};
+    std::vector<int32_t> cols, slots;
+    std::vector<double> counts, bp;
+    std::string fail;
+};
+
+static void make_type_blocks(const LatticeArcs& A, const std::vector<int32_t>& ttp, const std::vector<int32_t>& etp,
+                             const std::vector<uint32_t>& rw, const std::vector<int64_t>& rgoff, const std::vector<int32_t>& rgrows,
+                             const std::vector<double>& typeW, TypeBlocks& B)
+{
+    const int64_t n_rg = (int64_t)rgrows.size();
+    const size_t max_paths = 1u << 20;
+    std::vector<std::vector<int32_t>> paths;              // arcs of every path of the current type
+    auto emit = [&](int64_t slot, double W) {
+        std::map<int, int> colset;
+        std::vector<std::map<int, double>> hist(paths.size());
+        for (size_t q = 0; q < paths.size(); ++q)
+            for (int32_t a : paths[q]) {
+                const int tp = ttp[A.arc_tid[a]], ep = A.arc_eid[a] < 0 ? -1 : etp[A.arc_eid[a]];
+                if (tp >= 0) { hist[q][tp] += 1.0; colset[tp] = 0; }
+                if (ep >= 0) { hist[q][ep] += 1.0; colset[ep] = 0; }
+            }
+        std::vector<int> keep;                             // columns whose count differs between the paths (src/HessianLearner.cpp:409-443)
+        for (const auto& kv : colset) {
+            const int j = kv.first;
+            auto f0 = hist[0].find(j);
+            const double c0 = f0 == hist[0].end() ? 0.0 : f0->second;
+            bool same = true;
+            for (const auto& hq : hist) { auto f = hq.find(j); if ((f == hq.end() ? 0.0 : f->second) != c0) { same = false; break; } }
+            if (!same) keep.push_back(j);
+        }
+        for (int j : keep) B.cols.push_back(j);
+        for (const auto& hq : hist)
+            for (int j : keep) { auto f = hq.find(j); B.counts.push_back(f == hq.end() ? 0.0 : f->second); }
+        B.po.push_back(B.po.back() + (int64_t)paths.size());
+        B.co.push_back((int64_t)B.cols.size());
+        B.vo.push_back((int64_t)B.counts.size());
+        B.bp.push_back(W);
+        B.slots.push_back((int32_t)slot);
+    };
+    for (int64_t g = 0; g < n_rg && B.fail.empty(); ++g) {
+        const int code = rgrows[g];
+        const uint32_t* base = rw.data() + rgoff[g];
+        for (int l = 0; l < 32 && B.fail.empty(); ++l) {
+            const double W = typeW[(size_t)g * 32 + l];
+            if (!(W > 0.0)) continue;
+            paths.clear();
+            if (code & 0x10000) {
+                const int PP = (code >> 8) & 0xff, L = code & 0xff;
+                for (int q = 0; q < PP; ++q) {
+                    std::vector<int32_t> pa;
+                    bool real = true;
+                    for (int el = 0; el < L; ++el) {
+                        const uint32_t a = base[(size_t)(el * PP + q) * 32 + l];
+                        if ((int)a >= A.n_arcs) { real = false; break; }
+                        pa.push_back((int32_t)a);
+                    }
+                    if (real) paths.push_back(std::move(pa));
+                }
+            } else {
+                // DAG form: rebuild the nodes from the slot life times, then walk every path from the entry to the FIN node
+                const int rows = (int)((rgoff[g + 1] - rgoff[g]) >> 5);
+                std::vector<int> node_of(16, -1);
+                std::vector<std::vector<std::pair<int, int32_t>>> out;      // node -> (dst node, arc)
+                auto new_node = [&]() { out.emplace_back(); return (int)out.size() - 1; };
+                const int entry_node = node_of[0] = new_node();          // (slot 0 may be taken by a later node)
+                int exit_node = -1;
+                for (int i = 0; i < rows; ++i) {
+                    const uint32_t w = base[(size_t)i * 32 + l];
+                    if ((i & (kCheckEvery - 1)) == kCheckEvery - 1) continue;               // CHECK word
+                    if (w & kLatEdge) {
+                        const int src = (w >> kLatSrcShift) & 15, dst = (w >> kLatDstShift) & 15;
+                        if (w & kLatFirstIn) node_of[dst] = new_node();
+                        out[node_of[src]].push_back({node_of[dst], (int32_t)(w & 0x7fff)});
+                    } else if (w & kLatFin) exit_node = node_of[w & 15];
+                }
+                if (exit_node < 0) { B.fail = "H_f blocks: a DAG-form region type has no FIN word"; break; }
+                std::vector<std::pair<int, size_t>> stack{{entry_node, 0}};
+                std::vector<int32_t> cur;
+                while (!stack.empty()) {
+                    auto& top = stack.back();
+                    if (top.first == exit_node) {
+                        paths.push_back(cur);
+                        if (paths.size() > max_paths) { B.fail = "H_f blocks: a region type has more than 2^20 paths"; break; }
+                        stack.pop_back(); if (!cur.empty()) cur.pop_back();
+                        continue;
+                    }
+                    if (top.second >= out[top.first].size()) { stack.pop_back(); if (!cur.empty()) cur.pop_back(); continue; }
+                    const auto ed = out[top.first][top.second++];
+                    cur.push_back(ed.second);
+                    stack.push_back({ed.first, 0});
+                }
+            }
+            if (B.fail.empty() && paths.size() >= 2) emit(g * 32 + l, W);
+        }
+    }
+}
+
+static int build_type_blocks(wfsa_dev* h)
+{
+    TypeBlocks B;
+    make_type_blocks(h->larcs, h->h_ttp, h->h_etp, h->hrw, h->hrgoff, h->hrgrows, h->hrW, B);
+    if (!B.fail.empty()) h->err = B.fail;
+    CK(h->d_type_lrmin.alloc(h->hrgrows.size() * 32 + 1));
+    CK(cudaMemsetAsync(h->d_type_lrmin.p, 0, h->d_type_lrmin.n * 8, h->stream));
+    const int rc = upload_path_blocks(h, B.po, B.co, B.vo, B.cols, B.counts, B.bp, &B.slots, B.fail.empty() ? 0 : 1);
+    if (rc == WFSA_OK) h->hb_from_types = true;
+    return rc;
+}
+
+static int ensure_ks(wfsa_dev* h);
 
 extern "C" int wfsa_dev_hessian(wfsa_dev* h, const double* x, double* Hf, double* rmin)
 {
     if (!h || !Hf) return set_err(h, WFSA_ERR_INVALID, "hessian: bad arguments");
-    if (h->hb_blocks < 0) return set_err(h, WFSA_ERR_STATE, "hessian before set_path_blocks");
+    if (h->n < 0) return set_err(h, WFSA_ERR_STATE, "hessian before set_param_map");
+    if (h->hb_blocks < 0) {
+        if (h->kernel != 6) return set_err(h, WFSA_ERR_STATE, "hessian before set_path_blocks");
+        CK(cudaSetDevice(h->device));
+        const int rc = build_type_blocks(h);              // the segmented path derives the blocks from its region types
+        if (rc != WFSA_OK) return rc;
+    }
     int rc = wfsa_dev_upload_x(h, x);
     if (rc != WFSA_OK) return rc;
     const size_t nn = (size_t)h->n * h->n;
@@ -1454,6 +1603,7 @@ extern "C" int wfsa_dev_hessian(wfsa_dev* h, const double* x, double* Hf, double
         P.n_blocks = h->hb_blocks; P.path_off = h->d_hb_path_off.p; P.col_off = h->d_hb_col_off.p; P.cols = h->d_hb_cols.p;
         P.val_off = h->d_hb_val_off.p; P.counts = h->d_hb_counts.p; P.p = h->d_hb_p.p; P.x = h->d_x.p; P.r_scratch = h->d_hb_r.p;
         P.H_fx = h->d_Hfx.p; P.rmin = h->d_rmin.p; P.n = h->n; P.fx_scale = fx;
+        P.blk_slot = h->hb_from_types ? h->d_hb_slot.p : nullptr; P.slot_lrmin = h->hb_from_types ? h->d_type_lrmin.p : nullptr;
         const int warps_per_block = 8;
         const int64_t blocks = std::min<int64_t>((h->hb_blocks + warps_per_block - 1) / warps_per_block, (int64_t)h->sm_count * 8);
         k5_hessian<<<(int)std::max<int64_t>(blocks, 1), warps_per_block * 32, 0, h->stream>>>(P);
@@ -1467,10 +1617,32 @@ extern "C" int wfsa_dev_hessian(wfsa_dev* h, const double* x, double* Hf, double
         CK(cudaMemcpyAsync(Hf, h->d_H.p, nn * 8, cudaMemcpyDeviceToHost, h->stream));
     }
     double rm = INFINITY;
+    if (rmin && h->hb_from_types) {
+        // The smallest path posterior of a STRING (the rmin column of the reference, src/HessianLearner.cpp:315) is the
+        // product over its regions of their smallest path posteriors: ks_strings adds log rmin_type over the regions of
+        // every string (zero table for the bridges), a reduction takes the minimum.
+        rc = ensure_ks(h);
+        if (rc != WFSA_OK) return rc;
+        if (h->ks_groups > 0) {
+            if (h->d_zero_logaw.n < (size_t)h->larcs.n_arcs + 16) { CK(h->d_zero_logaw.alloc((size_t)h->larcs.n_arcs + 16)); CK(cudaMemsetAsync(h->d_zero_logaw.p, 0, h->d_zero_logaw.n * 8, h->stream)); }
+            KSParams S{};
+            S.logaw = h->d_zero_logaw.p; S.words = h->d_kswords.p; S.sgoff = h->d_ksgoff.p; S.gref = h->d_ksgref.p; S.lq = h->d_type_lrmin.p;
+            S.p = h->d_ksp.p; S.logq = h->d_kslogq.p; S.n_sgroups = h->ks_groups; S.counter = h->d_klcounter.p + 1; S.n_arcs = h->larcs.n_arcs;
+            CK(cudaMemsetAsync(h->d_klcounter.p + 1, 0, 4, h->stream));
+            CK(cudaMemsetAsync(h->d_kslogq.p, 0, h->d_kslogq.n * 8, h->stream));
+            ks_strings<<<h->ks_grid, h->ks_block, h->ks_smem, h->stream>>>(S);
+            k_min_exp<<<1, 1024, 0, h->stream>>>((long long)h->d_kslogq.n, h->d_kslogq.p, h->d_rmin.p);
+            h->launches += 2;
+            h->ks_done = false;                           // the per-string buffer no longer holds log q
+        }
+    }
     CK(cudaMemcpyAsync(&rm, h->d_rmin.p, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
-    if (rmin) *rmin = rm;
+    if (rmin) {
+        if (h->comm) { rm = -rm; const int r2 = wfsa_dev_allreduce_f64(h, &rm, 1, 1); if (r2 != WFSA_OK) return r2; rm = -rm; }
+        *rmin = rm;
+    }
     return WFSA_OK;
 }
 
@@ -1743,6 +1915,7 @@ struct wfsa_segmented {
     SegmentedCorpus sc;
     LatticeArcs arcs;
     std::vector<int64_t> stats;
+    TypeBlocks blocks;                          // what wfsa_dev_hessian derives from the region types
 };
 
 extern "C" int wfsa_segmented_compile(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* cd, const int32_t* trimmed,
@@ -1774,6 +1947,13 @@ extern "C" int wfsa_segmented_compile(const wfsa_fsa_desc* fd, const wfsa_corpus
     compile_corpus_segmented(f, A, alive.data(), cd->tokens, cd->offsets, cd->p, ids, n_slots, fx_scale, s->sc);
     s->stats = {s->sc.n_types, s->sc.n_region_instances, s->sc.n_region_edges, s->sc.n_type_edges, s->sc.n_bridge, s->sc.n_strings,
                 (int64_t)(s->sc.host_ms * 1000.0)};
+    {   // H_f blocks in the numbering of `trimmed` (raw parameter ids when trimmed is NULL)
+        std::vector<int32_t> ttp(f.n_trans()), etp(f.n_emis());
+        for (int t = 0; t < f.n_trans(); ++t) ttp[t] = f.trans_param[t] < 0 ? -1 : (trimmed ? trimmed[f.trans_param[t]] : f.trans_param[t]);
+        for (int e = 0; e < f.n_emis(); ++e) etp[e] = f.emis_param[e] < 0 ? -1 : (trimmed ? trimmed[f.emis_param[e]] : f.emis_param[e]);
+        make_type_blocks(A, ttp, etp, s->sc.rwords, s->sc.rgoff, s->sc.rgrows, s->sc.typeW, s->blocks);
+        if (!s->blocks.fail.empty()) { g_create_error = s->blocks.fail; delete s; return WFSA_ERR_LIMIT; }
+    }
     *out = s;
     return WFSA_OK;
 }
@@ -1786,7 +1966,8 @@ extern "C" int wfsa_segmented_get(const wfsa_segmented* s, int which, const void
     switch (which) {
         SEG_ARR(0, c.rwords) SEG_ARR(1, c.rgoff) SEG_ARR(2, c.rgrows) SEG_ARR(3, c.typeW) SEG_ARR(4, c.swords) SEG_ARR(5, c.sgoff)
         SEG_ARR(6, c.sgref) SEG_ARR(7, c.ksid) SEG_ARR(8, c.kp) SEG_ARR(9, c.overflow) SEG_ARR(10, c.rejected) SEG_ARR(11, c.const_acc)
-        SEG_ARR(12, s->stats)
+        SEG_ARR(12, s->stats) SEG_ARR(13, s->blocks.po) SEG_ARR(14, s->blocks.co) SEG_ARR(15, s->blocks.vo) SEG_ARR(16, s->blocks.cols)
+        SEG_ARR(17, s->blocks.counts) SEG_ARR(18, s->blocks.bp) SEG_ARR(19, s->blocks.slots)
         default: return WFSA_ERR_INVALID;
     }
 #undef SEG_ARR

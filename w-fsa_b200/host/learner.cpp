@@ -253,7 +253,11 @@ void Learner::BuildPathBlocks()
     const double limit = 4e6;
     double total = 0;
     for (size_t s = 0; s < shard_words.size(); ++s) if (recognised[s] && path_counts[s] > 1.0) total += path_counts[s];
-    if (total > limit) throw LearnerError("too many paths to enumerate for the H_f blocks");
+    {   // with several ranks every rank must fail together: wfsa_dev_set_path_blocks below is collective
+        double too_many = total > limit ? 1.0 : 0.0;
+        if (opts.nranks > 1) check(wfsa_dev_allreduce_f64(dev, &too_many, 1, 1), "wfsa_dev_allreduce_f64");
+        if (too_many > 0.0) throw LearnerError("too many paths to enumerate for the H_f blocks");
+    }
     for (size_t s = 0; s < shard_words.size(); ++s) {
         if (!recognised[s] || !(path_counts[s] > 1.0)) continue;
         const std::string& w = shard_words[s];
@@ -322,9 +326,16 @@ void Learner::ComputeHfDense(std::vector<double>& Hf, double* rmin)
     const int n = GetNumberOfParameters();
     Hf.assign((size_t)n * n, 0.0);
     if (HasUniquePaths()) { if (rmin) *rmin = 0.0; return; }
-    BuildPathBlocks();
     double rm = 0.0;
-    check(wfsa_dev_hessian(dev, _x.data(), Hf.data(), &rm), "wfsa_dev_hessian");
+    // The segmented backend derives the blocks of the contraction from its compiled region types (no path enumeration per
+    // string); backends without a compiled form answer WFSA_ERR_STATE until they are given the blocks of the host
+    // enumeration (route A: fixtures and small corpora only).
+    int rc = wfsa_dev_hessian(dev, _x.data(), Hf.data(), &rm);
+    if (rc == WFSA_ERR_STATE && !have_blocks) {
+        BuildPathBlocks();
+        rc = wfsa_dev_hessian(dev, _x.data(), Hf.data(), &rm);
+    }
+    check(rc, "wfsa_dev_hessian");
     if (rmin) *rmin = std::isfinite(rm) ? rm : 1.0;
 }
 
@@ -435,7 +446,6 @@ void HessianLearner::InitCallback(int flags)           // src/HessianLearner.cpp
     if (flags & 2) Renormalize();
     if (flags & 4) InitSlackVariables();
     include_Hf = (flags & 8) != 0;
-    if (include_Hf && !HasUniquePaths()) BuildPathBlocks();
     degenerate = false;
     factored = false;
 }
