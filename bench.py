@@ -408,7 +408,7 @@ def run_ours(args, rank, world, local):
         # the segmented path does not write log q_s unless asked (not asked here), so those 8 B are not counted
         alg_bytes = 4.0 * my_tokens + (12.0 if info["kernel"] == 6 else 20.0) * n_local_strings + 8.0 * n + float(info["table_bytes"])
         a_lat = None
-        if info["kernel"] == 2:
+        if info["kernel"] in (2, 7):
             # CTA-per-string kernel: the alpha lattice of a string does not fit on chip; SURVEY 8(d) charges 16 B per
             # live alpha entry (8 B written by the forward sweep, 8 B read back).  The kernel keeps one entry per
             # candidate state of the position's symbol (exactly max_candidates for the synthetic config 5).
@@ -424,7 +424,8 @@ def run_ours(args, rank, world, local):
             except Exception:
                 traffic = None
         single = bool(info["eval_path"] & 1)
-        kname = {1: "k2_fwdbwd", 2: "k3_fwdbwd", 3: "kg_fwdbwd", 4: "kt_fwdbwd", 5: "kl_fwdbwd", 6: "k_eval6" if single else "kr_regions"}[info["kernel"]]
+        kname = {1: "k2_fwdbwd", 2: "k3_fwdbwd", 3: "kg_fwdbwd", 4: "kt_fwdbwd", 5: "kl_fwdbwd", 6: "k_eval6" if single else "kr_regions",
+                 7: "k7_fwd + k7_bwd (one launch each per position)"}[info["kernel"]]
         collective = "none"
         if world > 1:
             collective = ("exchange of [loglik, per-edge sums] (exact 64-bit integers) through NVLink peer memory inside the evaluation kernel"
@@ -439,6 +440,8 @@ def run_ours(args, rank, world, local):
                        "strings_per_gpu": n_local_strings, "symbols_per_gpu": my_tokens, "symbols_total": tok_total, "parameters": n,
                        "kernel": {1: "K2 warp-per-string", 2: "K3 CTA-per-string", 3: "generic", 4: "KT thread-per-string (+ warp-per-string for overflow strings)",
                                   5: "KL thread-per-string over compiled lattices (+ warp-per-string for overflow strings)",
+                                  7: "K7 position-synchronous, pair-batched: all strings of a batch advance one position per launch, grouped by symbol pair; "
+                                     "alpha lattice of the batch resident in HBM (%d batch(es))" % info["pool_slots"],
                                   6: "segmented compiled lattices: forward-backward over the distinct region types (thread per type), "
                                      + ("weights, region types, grid barrier, fold and rank exchange in ONE persistent launch (k_eval6); " if single else "kr_regions + fold kernels; ")
                                      + "bridge edges are folded into constants when the corpus is compiled; log q per string (ks_strings) only on request"}[info["kernel"]],
@@ -455,7 +458,7 @@ def run_ours(args, rank, world, local):
                        "collective": collective,
                        "seeds": {"automaton": cfg["seed"], "strings": 1235}},
             # one-time cost per parameter map, outside the metric: structural pass on the device + corpus compile on the host cores
-            "setup": {"structure_plus_set_param_map_s": setup_s, "corpus_compile_host_ms": info["seg_host_ms"] if info["kernel"] == 6 else None},
+            "setup": {"structure_plus_set_param_map_s": setup_s, "corpus_compile_host_ms": info["seg_host_ms"] if info["kernel"] in (6, 7) else None},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "dram_frac": (traffic / (k_ms * 1e-3) / 1e9 / peak) if traffic else None,
                          "peak_source": peak_src, "kernel": kname,

@@ -69,7 +69,8 @@ typedef struct {
     int32_t device;              /* CUDA device ordinal                                       */
     int32_t force_kernel;        /* 0 auto, 1 warp-per-string, 2 CTA-per-string, 3 generic,
                                     4 thread-per-string (table walk), 5 thread-per-string (compiled lattices),
-                                    6 segmented compiled lattices (bridges folded into constants + region types) */
+                                    6 segmented compiled lattices (bridges folded into constants + region types),
+                                    7 position-synchronous, pair-batched (dense automata: more than 32 states emit one symbol) */
     int32_t accum_mode;          /* 0 auto, 1 shared-memory accumulators, 2 global (L2) REDs  */
     int32_t reserved;
 } wfsa_dev_options;
@@ -172,7 +173,8 @@ int wfsa_dev_l2_flush(wfsa_dev* h);
 typedef struct {
     int32_t kernel;              /* 1 warp-per-string, 2 CTA-per-string, 3 generic, 4 thread-per-string
                                     (table walk), 5 thread-per-string over compiled lattices,
-                                    6 segmented compiled lattices (kr_regions + ks_strings)        */
+                                    6 segmented compiled lattices (k_eval6 / kr_regions + ks_strings),
+                                    7 position-synchronous pair-batched kernels (k7_fwd / k7_bwd)     */
     int32_t accum_mode;          /* 1 shared, 2 global                                          */
     int32_t n_trans, n_emis, n_arcs, n_slots;
     int32_t max_candidates;      /* max over symbols of states emitting it                      */

@@ -56,6 +56,16 @@ def test_structure_objective_gradient_hessian(case):
     s.close()
 
 
+# Hessian-optimiser runs whose KKT matrix is singular along a non-identifiable direction (the optimum is a set, not a point):
+# the Newton step along the null space is rounding noise shaped by the linear solver's pivoting, so the WEIGHTS of these
+# runs are compared to 1e-5 / 1e-3 only; every printed column is still compared tightly.  Every other run: 1e-6 (north_star).
+SINGULAR_KKT = {
+    "talk.wfsa+talk.corpus",   # the reference's own optimum differs between its two optimisers: weights are not identifiable
+    "random00",                # measured: the only other runs that leave 1e-6 (3 of 117 runs); both random automata have a state
+    "random34",                # whose emissions never disambiguate two transitions, i.e. a flat direction of the objective
+}
+
+
 def _runs():
     out = []
     for case in good_cases():
@@ -83,7 +93,8 @@ def test_optimisation_trajectory(case, run):
     # solver's pivoting makes of rounding noise (MKL DSS, the oracle's stand-in and our Bunch-Kaufman all
     # differ), so weights are compared to 1e-3 / 1e-5 relative while every printed column (KL, graderr,
     # g_min, g_max, lambda_min, inertia, rmin) is still compared tightly at every epoch.
-    xtol = dict(rtol=1e-5, atol=1e-3) if hess else dict(rtol=1e-6, atol=1e-6)
+    singular = hess and case["name"] in SINGULAR_KKT
+    xtol = dict(rtol=1e-5, atol=1e-3) if singular else dict(rtol=1e-6, atol=1e-6)
     ref_rows = run["trajectory"]
     n_cmp = len(ref_rows) - (1 if run["error"] else 0)       # the row that made the reference stop is not compared
     halted = False
@@ -195,7 +206,7 @@ def medium():
     return model, low
 
 
-@pytest.mark.parametrize("kernel,accum,variant", [(6, 0, 0), (6, 0, 4 << 16), (5, 0, 0), (5, 0, 4 << 16), (5, 0, 4), (4, 0, 0), (4, 0, 4 << 16), (1, 1, 0), (1, 1, 1), (1, 2, 0), (2, 0, 0), (3, 0, 0)])
+@pytest.mark.parametrize("kernel,accum,variant", [(6, 0, 0), (6, 0, 4 << 16), (5, 0, 0), (5, 0, 4 << 16), (5, 0, 4), (4, 0, 0), (4, 0, 4 << 16), (1, 1, 0), (1, 1, 1), (1, 2, 0), (2, 0, 0), (7, 0, 0), (3, 0, 0)])
 def test_kernels_match_cpu_oracle(medium, kernel, accum, variant):
     model, low = medium
     count = 3000 if kernel != 3 else 300          # the generic kernel is the slow, dense one
@@ -349,21 +360,65 @@ def test_long_strings_need_rescaling():
         dev.close()
 
 
-def test_config5_shape_cta_kernel():
-    """Down-scaled config 5 (dense: more than 32 states emit a symbol -> CTA-per-string kernel)."""
+@pytest.mark.parametrize("kernel", [2, 7])
+def test_config5_shape_dense_kernels(kernel):
+    """Down-scaled config 5 (dense: more than 32 states emit a symbol): CTA-per-string kernel K3 and the
+    position-synchronous pair-batched kernel K7, each against the CPU forward-backward; K7 runs K3's sums in K3's order, so the two agree to the last bits."""
     model = synth.make_model(512, 64, 16, 8, seed=31)       # 64 states per symbol
     low = model.lowered()
     offs, toks, w = model.corpus(400, 16, 48, seed=32)
+    toks = toks.copy()
+    toks[offs[7] + 3] = -1                                  # one string with an unknown symbol
     low.set_tokens(offs, toks, w / w.sum())
-    dev, rec, pc, trimmed, n = build_device(low)
-    assert dev.info()["kernel"] == 2 and rec.all()
+    dev, rec, pc, trimmed, n = build_device(low, force_kernel=kernel)
+    assert dev.info()["kernel"] == kernel and rec.sum() == 399
     x = np.random.RandomState(6).normal(-1.0, 0.4, size=n)
+    ll, logq, grad = dev.eval(x)
+    ltw, lew = low.edge_logweights(x, trimmed)
+    _, olq, oee = O.dp_eval(low, ltw, lew)
+    r = rec.astype(bool)
+    assert np.allclose(logq[r], olq[r], rtol=1e-12) and np.isneginf(logq[~r]).all()
+    ok, err = vec_tol_ok(grad, oracle_grad(low, trimmed, n, oee), 1e-9)
+    assert ok, err
+    assert abs(ll - float(np.dot(low.p[r], olq[r]))) <= 1e-11 * abs(ll)
+    if kernel == 7:
+        d3 = W.Device(low, force_kernel=2)
+        d3.structure()
+        d3.set_param_map(trimmed, n, rec)
+        ll3, logq3, grad3 = d3.eval(x)
+        d3.close()
+        # (identical sums in identical order, except the association of one product in the posterior of the final
+        #  transitions: equal to the last bits, not bitwise)
+        assert np.allclose(grad3, grad, rtol=1e-13, atol=0) and np.allclose(logq3[r], logq[r], rtol=1e-15)
+    dev.close()
+
+
+def test_config5_true_shape_parity():
+    """BASELINE config 5 at its named shape (4096 states / 256 symbols, 64 successors, 16 emissions: ~256 states per symbol,
+    4.2 M combined arcs): 300 strings through the batched kernel K7 against the CPU forward-backward, with a small
+    lattice budget so that the corpus is cut into several batches, and long strings so that the power-of-two
+    rescaling is exercised."""
+    import os
+    model = synth.make_model(4096, 256, 64, 16, seed=4321)
+    low = model.lowered()
+    offs, toks, w = model.corpus(300, 32, 128, seed=41)
+    low.set_tokens(offs, toks, w / w.sum())
+    os.environ["WFSA_K7_ROWS"] = "9000"
+    try:
+        dev, rec, pc, trimmed, n = build_device(low, force_kernel=7)     # (the default for this shape from 200 000 strings on)
+    finally:
+        os.environ.pop("WFSA_K7_ROWS", None)
+    info = dev.info()
+    assert info["kernel"] == 7 and rec.all() and info["pool_slots"] >= 2     # (pool_slots reports the number of batches)
+    x = np.random.RandomState(8).normal(-3.0, 1.0, size=n)                  # small weights: alpha underflows without rescaling
     ll, logq, grad = dev.eval(x)
     ltw, lew = low.edge_logweights(x, trimmed)
     _, olq, oee = O.dp_eval(low, ltw, lew)
     assert np.allclose(logq, olq, rtol=1e-12)
     ok, err = vec_tol_ok(grad, oracle_grad(low, trimmed, n, oee), 1e-9)
     assert ok, err
+    ll2, _, grad2 = dev.eval(x, want_logq=False)
+    assert ll2 == ll and np.array_equal(grad2, grad), "run-to-run bitwise determinism"
     dev.close()
 
 

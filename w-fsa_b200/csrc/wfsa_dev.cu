@@ -25,6 +25,7 @@
 #include "kernels.cuh"
 #include "kernels_seg.cuh"
 #include "kernels_eval6.cuh"
+#include "kernels_k7.cuh"
 #include "layout.hpp"
 #include "lattice.hpp"
 
@@ -193,6 +194,18 @@ struct wfsa_dev {
     bool timing_detail = true;
     bool evaluated = false;                 // an evaluation has been launched since set_param_map
     bool ks_done = false;                   // ks_strings has run for the last evaluation (it runs on demand)
+    // K7: position-synchronous, pair-batched forward-backward for dense automata (kernels_k7.cuh)
+    struct K7Batch {
+        int NB = 0, Tmax = 0;
+        std::vector<int> n_t;                   // [Tmax + 1] strings longer than t
+        std::vector<size_t> row_off;            // [Tmax + 1] lattice rows (= perm entries) before step t
+        std::vector<size_t> desc_off;           // [Tmax + 1]
+        DevBuf<K7Desc> d_desc; DevBuf<int32_t> d_perm, d_sid, d_last;
+    };
+    std::vector<K7Batch> k7;
+    int k7_V = 0; size_t k7_rows = 0, k7_nb = 0;
+    DevBuf<double> d_k7lat, d_k7bt, d_k7scale; DevBuf<int> d_k7exp, d_k7EQ, d_k7F;
+    double k7_host_ms = 0;
     // single-launch evaluation of the segmented path (k_eval6, kernels_eval6.cuh)
     DevBuf<unsigned int> d_e6ctl;           // [0..1] tickets, [2] barrier arrivals, [3] epoch
     DevBuf<unsigned long long> d_e6acc, d_e6red, d_e6stamps;
@@ -477,6 +490,12 @@ static int choose_launch(wfsa_dev* h)
         h->secondary = h->fast.warp_ok ? 1 : 2;
         rc = setup_kt(h);
         if (rc == WFSA_OK) rc = h->secondary == 1 ? setup_k2(h) : setup_k3(h);
+    } else if (h->kernel == 7) {
+        h->secondary = 2; h->skernel = 2;                  // structural pass and strings with unknown symbols: CTA-per-string kernel
+        h->k7_V = (h->fast.max_cand + 31) / 32 * 32;
+        cudaFuncSetAttribute(k7_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kK7Chunk * h->k7_V * 8);
+        cudaFuncSetAttribute(k7_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kK7Chunk * h->k7_V * 8);
+        rc = setup_k3(h);
     } else if (h->kernel == 1) rc = setup_k2(h);
     else if (h->kernel == 2) rc = setup_k3(h);
     else rc = setup_generic(h);
@@ -528,13 +547,14 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
     if (kernel == 0) {
         int nt = 0; size_t sm = 0; int K = (h->opt.reserved >> 16) & 0xff; if (K == 0) K = 8;
         if (kl_possible(h, kLatMaxSlots, 0, nt, sm)) kernel = h->larcs.n_arcs < 65520 ? 6 : 5;
-        else kernel = !h->fast.ok ? 3 : (kt_possible(h, K, nt, sm) ? 4 : (h->fast.warp_ok ? 1 : 2));
+        else kernel = !h->fast.ok ? 3 : (kt_possible(h, K, nt, sm) ? 4 : (h->fast.warp_ok ? 1 : (((h->fast.max_cand + 31) / 32 * 32 <= 512 && cd && cd->n_strings >= 200000) ? 7 : 2)));     // K7 pays off once ~3 strings share a symbol pair per position
     }
     if (kernel == 6 && h->larcs.n_arcs >= 65520) { h->err = "forced segmented kernel but the automaton has 65520 or more combined arcs"; return bail(WFSA_ERR_INVALID); }
     if (kernel == 5 || kernel == 6) { int nt = 0; size_t sm = 0; if (!kl_possible(h, kLatMaxSlots, 0, nt, sm)) { h->err = "forced compiled-lattice kernel but the arc weights do not fit shared memory"; return bail(WFSA_ERR_INVALID); } }
-    if ((kernel == 1 || kernel == 2 || kernel == 4) && !h->fast.ok) { h->err = "forced fast kernel but emissions are not all one token long"; return bail(WFSA_ERR_INVALID); }
+    if (kernel == 7 && h->fast.ok && (h->fast.max_cand + 31) / 32 * 32 > 512) { h->err = "forced batched kernel but more than 512 states emit one symbol"; return bail(WFSA_ERR_INVALID); }
+    if ((kernel == 1 || kernel == 2 || kernel == 4 || kernel == 7) && !h->fast.ok) { h->err = "forced fast kernel but emissions are not all one token long"; return bail(WFSA_ERR_INVALID); }
     if (kernel == 1 && !h->fast.warp_ok) { h->err = "forced warp-per-string kernel but more than 32 states emit one symbol"; return bail(WFSA_ERR_INVALID); }
-    if (kernel < 1 || kernel > 6) { h->err = "force_kernel out of range"; return bail(WFSA_ERR_INVALID); }
+    if (kernel < 1 || kernel > 7) { h->err = "force_kernel out of range"; return bail(WFSA_ERR_INVALID); }
     h->kernel = kernel;
 
     // ---- corpus shard
@@ -711,6 +731,58 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
             else k2_fwdbwd<MODE_EVAL, ACC_SMEM_SPLIT, 1><<<h->grid, h->block, h->smem_bytes, st>>>(P);
         }
         h->launches++;
+    } else if (kernel == 7) {
+        FastTablesD T{};
+        T.cand_off = h->d_cand_off.p; T.slot_state = h->d_slot_state.p;
+        T.frow = h->d_frow.p; T.fent = h->d_fent.p; T.brow = h->d_brow.p; T.bent = h->d_bent.p;
+        T.n_sym = F.n_sym; T.n_states = F.n_states; T.n_arcs = L.n_arcs; T.n_slots = L.n_slots;
+        T.start_state = F.start; T.start_final_tid = L.start_final_tid;
+        const EvalWeightsD Wt{h->d_tw.p, h->d_sw.p, h->d_fw.p};
+        const int V = h->k7_V;
+        const size_t smem = (size_t)kK7Chunk * V * 8;
+        double* const lat = h->d_k7lat.p;
+        double* const bt[2] = {h->d_k7bt.p, h->d_k7bt.p + h->k7_nb * (size_t)V};
+        for (auto& B : h->k7) {
+            K7FinParams Fn{};
+            Fn.T = T; Fn.W = Wt; Fn.O = O; Fn.sid = B.d_sid.p; Fn.last_tok = B.d_last.p; Fn.p = h->d_p.p;
+            Fn.scale = h->d_k7scale.p; Fn.EQ = h->d_k7EQ.p; Fn.F = h->d_k7F.p; Fn.V = V;
+            K7Params P{};
+            P.T = T; P.W = Wt; P.O = O; P.V = V; P.F = h->d_k7F.p; P.EQ = h->d_k7EQ.p; P.scale = h->d_k7scale.p;
+            for (int t = 0; t < B.Tmax; ++t) {                 // forward: every string of the batch advances one position
+                P.desc = B.d_desc.p + B.desc_off[t]; P.perm = B.d_perm.p + B.row_off[t];
+                P.src = t ? lat + B.row_off[t - 1] * V : nullptr; P.dst = lat + B.row_off[t] * V;
+                P.exp_src = t ? h->d_k7exp.p + B.row_off[t - 1] : nullptr; P.exp_dst = h->d_k7exp.p + B.row_off[t];
+                P.rescale = (t & (kRescaleEvery - 1)) == kRescaleEvery - 1;
+                const unsigned nd = (unsigned)(B.desc_off[t + 1] - B.desc_off[t]);
+                if (nd) { k7_fwd<<<nd, V, smem, st>>>(P); h->launches++; }
+                if (B.n_t[t + 1] < B.n_t[t]) {                 // strings that end here: q, log q, p_s / q_s
+                    Fn.r0 = B.n_t[t + 1]; Fn.r1 = B.n_t[t]; Fn.lat = lat + B.row_off[t] * V; Fn.exp_t = h->d_k7exp.p + B.row_off[t];
+                    k7_finish_q<<<(Fn.r1 - Fn.r0 + 7) / 8, 256, 0, st>>>(Fn);
+                    h->launches++;
+                }
+            }
+            for (int t = B.Tmax - 1; t >= 0; --t) {             // backward
+                if (B.n_t[t + 1] < B.n_t[t]) {
+                    Fn.r0 = B.n_t[t + 1]; Fn.r1 = B.n_t[t]; Fn.lat = lat + B.row_off[t] * V; Fn.exp_t = h->d_k7exp.p + B.row_off[t];
+                    Fn.bt = bt[t & 1];
+                    k7_finish_beta<<<(Fn.r1 - Fn.r0 + 7) / 8, 256, 0, st>>>(Fn);
+                    h->launches++;
+                }
+                if (t + 1 < B.Tmax && B.n_t[t + 1] > 0) {
+                    P.desc = B.d_desc.p + B.desc_off[t + 1]; P.perm = B.d_perm.p + B.row_off[t + 1];
+                    P.src = bt[(t + 1) & 1]; P.dst = bt[t & 1]; P.lat = lat + B.row_off[t] * V; P.exp_t = h->d_k7exp.p + B.row_off[t];
+                    P.rescale = (t & (kRescaleEvery - 1)) == 0;
+                    const unsigned nd = (unsigned)(B.desc_off[t + 2] - B.desc_off[t + 1]);
+                    if (nd) { k7_bwd<<<nd, V, smem, st>>>(P); h->launches++; }
+                }
+            }
+            {                                                  // the arcs out of the start state (descriptors of step 0: cp = START)
+                P.desc = B.d_desc.p + B.desc_off[0]; P.perm = B.d_perm.p + B.row_off[0];
+                P.src = bt[0]; P.dst = nullptr; P.lat = nullptr; P.exp_t = nullptr; P.rescale = 0;
+                const unsigned nd = (unsigned)(B.desc_off[1] - B.desc_off[0]);
+                if (nd) { k7_bwd<<<nd, V, smem, st>>>(P); h->launches++; }
+            }
+        }
     } else if (kernel == 2) {
         K3Params P{};
         FastTablesD T{};
@@ -1099,6 +1171,99 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
         h->h_ttp = ttp; h->h_etp = etp;
         if (!h->hb_user) h->hb_blocks = -1;
         h->hb_from_types = false;
+    }
+    if (h->kernel == 7) {
+        // K7: batches of strings (longest first) whose alpha lattices fit the device memory; per batch and position the
+        // strings grouped by the symbol pair (c_{t-1}, c_t), in chunks of kK7Chunk
+        const auto t_begin = std::chrono::steady_clock::now();
+        const int A = F.n_sym, V = h->k7_V;
+        std::vector<int32_t> good;
+        for (int32_t s : order) {
+            bool ok = true;
+            for (int64_t i = h->h_offs[s]; i < h->h_offs[s + 1]; ++i) if ((unsigned)h->h_tokens[i] >= (unsigned)A) { ok = false; break; }
+            if (h->h_offs[s + 1] == h->h_offs[s]) ok = false;                    // the empty string: the CTA-per-string kernel knows how
+            (ok ? good : order_w).push_back(s);
+        }
+        h->n_active = (int64_t)good.size(); h->n_active_w = (int64_t)order_w.size();
+        if (!order_w.empty()) CK(cudaMemcpyAsync(h->d_order_w.p, order_w.data(), order_w.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        h->k7.clear();
+        h->d_k7lat.release(); h->d_k7bt.release(); h->d_k7exp.release(); h->d_k7scale.release(); h->d_k7EQ.release(); h->d_k7F.release();
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        // per lattice row: V doubles + one exponent + one permutation entry; keep a third of the free memory for everything else
+        size_t budget_rows = (size_t)((double)free_b * 0.6) / ((size_t)V * 8 + 8);
+        if (getenv("WFSA_K7_ROWS")) budget_rows = (size_t)atoll(getenv("WFSA_K7_ROWS"));
+        size_t i0 = 0;
+        size_t max_rows = 0, max_nb = 0;
+        while (i0 < good.size()) {
+            size_t rows = 0, i1 = i0;
+            while (i1 < good.size()) {
+                const size_t len = (size_t)(h->h_offs[good[i1] + 1] - h->h_offs[good[i1]]);
+                if (i1 > i0 && rows + len > budget_rows) break;
+                rows += len; ++i1;
+            }
+            h->k7.emplace_back();
+            wfsa_dev::K7Batch& B = h->k7.back();
+            B.NB = (int)(i1 - i0);
+            B.Tmax = (int)(h->h_offs[good[i0] + 1] - h->h_offs[good[i0]]);
+            B.n_t.assign((size_t)B.Tmax + 2, 0);
+            for (size_t i = i0; i < i1; ++i) B.n_t[(size_t)(h->h_offs[good[i] + 1] - h->h_offs[good[i]]) - 1]++;     // strings whose last position is t
+            for (int t = B.Tmax - 1; t >= 0; --t) B.n_t[t] += B.n_t[t + 1];                                      // -> strings longer than t
+            B.row_off.assign((size_t)B.Tmax + 1, 0);
+            for (int t = 0; t < B.Tmax; ++t) B.row_off[t + 1] = B.row_off[t] + (size_t)B.n_t[t];
+            std::vector<int32_t> perm(rows), sid((size_t)B.NB), last((size_t)B.NB);
+            for (int r = 0; r < B.NB; ++r) { sid[r] = good[i0 + r]; last[r] = h->h_tokens[h->h_offs[sid[r] + 1] - 1]; }
+            // counting sort of the strings of every step by their pair key, steps dealt out to the host threads
+            std::vector<std::vector<K7Desc>> step_desc((size_t)B.Tmax);
+            unsigned hw = std::thread::hardware_concurrency();
+            const int NT = (int)std::max(1u, std::min(hw ? hw : 4u, 32u));
+            auto work = [&](int tid) {
+                std::vector<int32_t> cnt((size_t)(A + 1) * A + 1);
+                for (int t = tid; t < B.Tmax; t += NT) {
+                    std::fill(cnt.begin(), cnt.end(), 0);
+                    const int n = B.n_t[t];
+                    auto key_of = [&](int r) {
+                        const int64_t o = h->h_offs[sid[r]];
+                        return (t ? h->h_tokens[o + t - 1] : A) * A + h->h_tokens[o + t];
+                    };
+                    for (int r = 0; r < n; ++r) cnt[(size_t)key_of(r) + 1]++;
+                    std::vector<K7Desc>& D = step_desc[t];
+                    int run = 0;
+                    for (size_t k = 0; k + 1 < cnt.size(); ++k) {
+                        const int c = cnt[k + 1];
+                        for (int b = 0; b < c; b += kK7Chunk) D.push_back(K7Desc{(int)(k / A), (int)(k % A), run + b, std::min(kK7Chunk, c - b)});
+                        cnt[k + 1] = run; run += c;                                       // becomes the write cursor of key k
+                    }
+                    int32_t* out = perm.data() + B.row_off[t];
+                    for (int r = 0; r < n; ++r) out[cnt[(size_t)key_of(r) + 1]++] = r;
+                }
+            };
+            {
+                std::vector<std::thread> th;
+                for (int k = 1; k < NT; ++k) th.emplace_back(work, k);
+                work(0);
+                for (auto& x : th) x.join();
+            }
+            B.desc_off.assign((size_t)B.Tmax + 1, 0);
+            for (int t = 0; t < B.Tmax; ++t) B.desc_off[t + 1] = B.desc_off[t] + step_desc[t].size();
+            std::vector<K7Desc> desc(B.desc_off[B.Tmax]);
+            for (int t = 0; t < B.Tmax; ++t) std::copy(step_desc[t].begin(), step_desc[t].end(), desc.begin() + B.desc_off[t]);
+            CK(B.d_desc.upload(desc, h->stream)); CK(B.d_perm.upload(perm, h->stream));
+            CK(B.d_sid.upload(sid, h->stream)); CK(B.d_last.upload(last, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            max_rows = std::max(max_rows, rows); max_nb = std::max(max_nb, (size_t)B.NB);
+            i0 = i1;
+        }
+        h->k7_rows = max_rows; h->k7_nb = max_nb;
+        if (max_rows) {
+            if (h->d_k7lat.alloc(max_rows * (size_t)V) != cudaSuccess || h->d_k7exp.alloc(max_rows) != cudaSuccess ||
+                h->d_k7bt.alloc(2 * max_nb * (size_t)V) != cudaSuccess || h->d_k7scale.alloc(max_nb) != cudaSuccess ||
+                h->d_k7EQ.alloc(max_nb) != cudaSuccess || h->d_k7F.alloc(max_nb) != cudaSuccess) {
+                cudaGetLastError();
+                return set_err(h, WFSA_ERR_NOMEM, "batched kernel: cannot allocate the alpha lattice of a batch");
+            }
+        }
+        h->k7_host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     }
     if (h->kernel == 5) {
         // compile the trimmed lattice of every participating string (structure is independent of x)
@@ -1986,9 +2151,11 @@ extern "C" int wfsa_dev_get_info(wfsa_dev* h, wfsa_dev_info* info)
     info->sm_count = h->sm_count;
     info->grid = h->kernel >= 5 ? h->kl_grid : (h->kernel == 4 ? h->kt_grid : (h->kernel == 2 ? (h->k3w ? h->k3w_grid : h->k3_grid) : h->grid));
     info->block = h->kernel >= 5 ? h->kl_block : (h->kernel == 4 ? h->kt_block : (h->kernel == 2 ? (h->k3w ? h->k3w_block : h->k3_block) : (h->kernel == 3 ? 128 : h->block)));
+    if (h->kernel == 7) { info->grid = 0; info->block = h->k7_V; }
     info->n_strings = h->n_strings; info->n_tokens = h->n_tokens;
     info->n_active_tokens = h->n_active_tokens;
     info->smem_bytes = (int64_t)(h->kernel >= 5 ? h->kl_smem : (h->kernel == 4 ? h->kt_smem : (h->kernel == 2 ? (h->k3w ? h->k3w_smem : h->k3_smem) : h->smem_bytes)));
+    if (h->kernel == 7) { info->smem_bytes = (int64_t)kK7Chunk * h->k7_V * 8; info->seg_host_ms = h->k7_host_ms; info->lattice_words = (int64_t)h->k7_rows * h->k7_V * 2; info->pool_slots = (int32_t)h->k7.size(); }
     if (h->kernel == 5) {
         info->n_arcs = h->larcs.n_arcs;
         info->lattice_words = h->kl_words; info->lattice_edges = h->kl_edges; info->lattice_bridge_edges = h->kl_bridge_edges;
