@@ -35,7 +35,8 @@ for cfg in configs:
     steps = 20
     dev.timer_begin_steps()
     for _ in range(steps):
-        dev.l2_flush()
+        if not cfg.get("no_flush"):
+            dev.l2_flush()
         dev.eval_launch()
     dev.timer_end()
     ms, k = dev.timer_step_ms()

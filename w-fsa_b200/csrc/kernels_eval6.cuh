@@ -46,7 +46,10 @@ struct Eval6Params {
     int replicas;
     double fx_scale, inv_fx;
     unsigned long long* red;                    // [2] fixed-point loglik, non-finite terms; zero between evaluations
-    unsigned int* ctl;                          // [0..1] ticket counters, [2] barrier arrivals (monotonic), [3] epoch (starts at 1)
+    unsigned int* ctl;                          // [0..1] ticket counters, [2] barrier arrivals (monotonic), [3] epoch (starts at 1),
+                                                // [4] CTAs of host-buffer launches that have finished (monotonic)
+    unsigned int* done_flag;                    // host-mapped word that receives the count of host-buffer launches when the whole grid has written `out`
+                                                // (the host-buffer call polls it instead of waiting for a D2H copy and a stream sync), or nullptr
     // fold
     int n_edges;
     const int32_t* __restrict__ e_off; const int32_t* __restrict__ e_arc; const int32_t* __restrict__ edge_tp;
@@ -210,6 +213,9 @@ __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
     const bool prof = P.stamps && blockIdx.x == 0 && tid == 0;
     unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
     if (prof) { t0 = e6_timer(); if (P.debug) P.stamps[6] = t0; }
+    const bool tline = (P.debug & 16) && tid == 0;
+    unsigned long long tl0 = 0, tl1 = 0, tl2 = 0, tl3 = 0;
+    if (tline) tl0 = e6_timer();
     // Big DAG groups are dealt out statically: big group b to warp b / gridDim.x of CTA b % gridDim.x (see P1).  Warp w
     // owns staging area w behind the pool (if w < big_slots); the words of its first big group are on their way to it
     // before anything else happens.
@@ -285,6 +291,7 @@ __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
     }
     __syncthreads();                                           // weights complete; exp(x) scratch is free: the pool starts here
     if (prof) t1 = e6_timer();
+    if (tline) tl1 = e6_timer();
     // ---- P1: region types -------------------------------------------------------------------------------------
     KRParams R{};
     R.words = P.words; R.goff = P.goff; R.typeW = P.typeW; R.lq = P.lq; R.xs = P.xs; R.xs_rows = P.xs_rows;
@@ -379,6 +386,7 @@ __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
     if (lane == 0) { s_part[warp][0] = ll; s_part[warp][1] = (long long)nf; }
     __syncthreads();
     if (prof) t2 = e6_timer();
+    if (tline) tl2 = e6_timer();
     // ---- P2: grid barrier -------------------------------------------------------------------------------------
     if (tid == 0) {
         long long s = 0, f = 0;
@@ -393,6 +401,7 @@ __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
     }
     __syncthreads();
     if (prof) t3 = e6_timer();
+    if (tline) tl3 = e6_timer();
     // ---- P3: fold, exchange, conversion ---------------------------------------------------------------------------
     if (blockIdx.x == 0 && tid == 0) P.ctl[3] = epoch + 1u;    // every CTA has read the epoch (it passed the barrier)
     const unsigned long long* const acc_all = P.acc + (size_t)par * acc_words;
@@ -429,9 +438,23 @@ __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
         if (blockIdx.x == 0 && tid == 0) P.ctl[par ^ 1] = 0u;
     }
     if (__any_sync(FULL, timeout) && lane == 0) P.out[2 + P.n] = (double)epoch;
+    if (P.done_flag) {                                         // `out` is host memory here: tell the host when every CTA is through
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            // ctl[4] counts the CTAs of host-buffer launches only; launches are stream ordered, so a multiple of the grid
+            // size means the last CTA of THIS launch.  The word written is the number of host-buffer launches so far.
+            const unsigned int arrived = atomicAdd(P.ctl + 4, 1u) + 1u;
+            if (arrived % gridDim.x == 0u) { *reinterpret_cast<volatile unsigned int*>(P.done_flag) = arrived / gridDim.x; __threadfence_system(); }
+        }
+    }
     if (prof) {
         const unsigned long long t4 = e6_timer();
         P.stamps[0] += t1 - t0; P.stamps[1] += t2 - t1; P.stamps[2] += t3 - t2; P.stamps[3] += t4 - t3;
+    }
+    if (P.stamps && (P.debug & 16) && tid == 0) {              // timeline of the last launch: [start, weights, regions, barrier, end] of every CTA
+        unsigned long long* tl = P.stamps + 8 + (size_t)blockIdx.x * 8;
+        tl[0] = tl0; tl[1] = tl1; tl[2] = tl2; tl[3] = tl3; tl[4] = e6_timer();
     }
 }
 

@@ -214,6 +214,10 @@ struct wfsa_dev {
     int e6_ncls = 0, e6_big_slots = 0, e6_big_rows = 0; size_t e6_smem = 0;
     bool e6_ok = false, any_overflow = false, e6_used = false, comm_failed = false;
     cudaGraph_t e6_graph = nullptr; cudaGraphExec_t e6_exec = nullptr; bool e6_graph_tried = false;
+    // host-buffer call: the graph's kernel writes [loglik, bad, grad, time-out epoch] and a completion word straight into mapped pinned memory
+    double* hm_out = nullptr; double* hm_out_dev = nullptr; unsigned int* hm_flag = nullptr; unsigned int* hm_flag_dev = nullptr; size_t hm_n = 0;
+    bool out_on_host = false;               // the results of the last evaluation are in h_out only (graph path)
+    unsigned int hm_runs = 0;               // host-buffer launches of k_eval6 since the control words were last reset
     cudaEvent_t ev_x = nullptr; bool x_in_flight = false;
 };
 
@@ -283,6 +287,8 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     if (h->e6_exec) cudaGraphExecDestroy(h->e6_exec);
     if (h->e6_graph) cudaGraphDestroy(h->e6_graph);
     if (h->ev_x) cudaEventDestroy(h->ev_x);
+    if (h->hm_out) cudaFreeHost(h->hm_out);
+    if (h->hm_flag) cudaFreeHost(h->hm_flag);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -432,10 +438,10 @@ static int setup_kl(wfsa_dev* h)
             CK(h->d_eoff.upload(off, h->stream)); CK(h->d_earc.upload(arc, h->stream));
         }
         {   // single-launch evaluation: control words (tickets, barrier arrivals, epoch = 1), reduction cells, phase stamps
-            const std::vector<unsigned int> ctl = {0u, 0u, 0u, 1u};
+            const std::vector<unsigned int> ctl = {0u, 0u, 0u, 1u, 0u, 0u, 0u, 0u};
             CK(h->d_e6ctl.upload(ctl, h->stream));
             CK(h->d_e6red.alloc(2)); CK(cudaMemsetAsync(h->d_e6red.p, 0, 16, h->stream));
-            CK(h->d_e6stamps.alloc(8)); CK(cudaMemsetAsync(h->d_e6stamps.p, 0, 64, h->stream));
+            CK(h->d_e6stamps.alloc(8 + 8 * 1024)); CK(cudaMemsetAsync(h->d_e6stamps.p, 0, (8 + 8 * 1024) * 8, h->stream));
             cudaFuncSetAttribute(k_eval6<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);
             cudaFuncSetAttribute(k_eval6<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);
             cudaFuncSetAttribute(k_eval6<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);
@@ -845,10 +851,11 @@ static void fill_eval6_params(wfsa_dev* h, Eval6Params& P)
     if (P.big_dedicate && !getenv("WFSA_E6_STATIC")) P.static_pct = 0;
 }
 
-static cudaError_t launch_eval6(wfsa_dev* h, cudaStream_t st, bool count = true)
+static cudaError_t launch_eval6(wfsa_dev* h, cudaStream_t st, bool count = true, bool to_host = false)
 {
     Eval6Params P;
     fill_eval6_params(h, P);
+    if (to_host) { P.out = h->hm_out_dev; P.done_flag = h->hm_flag_dev; }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(h->kl_grid); cfg.blockDim = dim3(h->kl_block); cfg.dynamicSmemBytes = h->e6_smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -1437,6 +1444,7 @@ extern "C" int wfsa_dev_eval_launch(wfsa_dev* h)
         }
         if (h->sev_used < h->sev.size()) { cudaEventRecord(h->sev[h->sev_used].first, h->stream); s1 = h->sev[h->sev_used].second; h->sev_used++; }
     }
+    h->out_on_host = false;
     const int rc = eval_launch_body(h);
     if (s1) cudaEventRecord(s1, h->stream);
     if (rc == WFSA_OK) h->evaluated = true;
@@ -1506,7 +1514,7 @@ extern "C" int wfsa_dev_eval_fetch(wfsa_dev* h, double* loglik, double* logq, do
     if (!h) return WFSA_ERR_INVALID;
     if (h->n < 0) return set_err(h, WFSA_ERR_STATE, "fetch before set_param_map");
     if (!h->evaluated) return set_err(h, WFSA_ERR_STATE, "fetch before an evaluation was launched for this parameter map");
-    CK(cudaMemcpyAsync(h->h_out, h->d_out.p, ((size_t)h->n + 3) * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (!h->out_on_host) CK(cudaMemcpyAsync(h->h_out, h->d_out.p, ((size_t)h->n + 3) * 8, cudaMemcpyDeviceToHost, h->stream));
     if (logq && h->kernel == 6) { const int rc = ensure_ks(h); if (rc != WFSA_OK) return rc; }
     if (logq && h->kernel == 6 && h->ks_groups > 0) {
         if (!h->ks_done) {                       // per-string log q of the segmented path, from the lq of the last evaluation
@@ -1533,17 +1541,31 @@ extern "C" int wfsa_dev_eval_fetch(wfsa_dev* h, double* loglik, double* logq, do
     return finish_fetch(h, loglik, grad);
 }
 
-// H2D x -> k_eval6 -> D2H [loglik, grad] captured once per parameter map; every node's parameters are constant
+// H2D x -> k_eval6 captured once per parameter map; every node's parameters are constant.  The kernel of this graph writes
+// [loglik, bad, grad] and, when the last CTA is through, a completion word straight into mapped pinned host memory: the
+// host polls that word instead of paying for a D2H copy node and the wake-up of cudaStreamSynchronize.
 static bool eval6_graph(wfsa_dev* h)
 {
     if (h->e6_exec) return true;
     if (h->e6_graph_tried || getenv("WFSA_NO_GRAPH")) return false;
     h->e6_graph_tried = true;
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return false;
+    const size_t words = (size_t)h->n + 3;
+    if (h->hm_n != words) {
+        if (h->hm_out) cudaFreeHost(h->hm_out);
+        if (h->hm_flag) cudaFreeHost(h->hm_flag);
+        h->hm_out = nullptr; h->hm_flag = nullptr; h->hm_n = 0;
+        if (cudaHostAlloc(&h->hm_out, words * 8, cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostAlloc(&h->hm_flag, 64, cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer(&h->hm_out_dev, h->hm_out, 0) != cudaSuccess ||
+            cudaHostGetDevicePointer(&h->hm_flag_dev, h->hm_flag, 0) != cudaSuccess) { cudaGetLastError(); return false; }
+        std::memset(h->hm_out, 0, words * 8);
+        *h->hm_flag = 0u;
+        h->hm_n = words;
+    }
     if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
     cudaMemcpyAsync(h->d_x.p, h->h_x, ((size_t)h->n + 1) * 8, cudaMemcpyHostToDevice, h->stream);
-    launch_eval6(h, h->stream, false);
-    cudaMemcpyAsync(h->h_out, h->d_out.p, ((size_t)h->n + 3) * 8, cudaMemcpyDeviceToHost, h->stream);
+    launch_eval6(h, h->stream, false, true);
     cudaGraph_t g = nullptr;
     if (cudaStreamEndCapture(h->stream, &g) != cudaSuccess || !g) { cudaGetLastError(); return false; }
     cudaGraphExec_t ex = nullptr;
@@ -1560,9 +1582,19 @@ extern "C" int wfsa_dev_eval(wfsa_dev* h, const double* x, double* loglik, doubl
         if (eval6_graph(h)) {
             const int rc = stage_x(h, x);
             if (rc != WFSA_OK) return rc;
+            const unsigned int epoch = ++h->hm_runs;
             CK(cudaGraphLaunch(h->e6_exec, h->stream));
             h->launches++; h->e6_used = true; h->evaluated = true; h->ks_done = false; h->lean_now = true; h->lean_finished = true;
-            CK(cudaStreamSynchronize(h->stream));
+            // wait for the completion word of this epoch; every now and then ask the stream whether it failed instead
+            volatile unsigned int* flag = h->hm_flag;
+            for (unsigned long long spin = 1; *flag != epoch; ++spin)
+                if ((spin & 0xfffffull) == 0) {
+                    const cudaError_t q = cudaStreamQuery(h->stream);
+                    if (q != cudaErrorNotReady) { if (q != cudaSuccess) CK(q); if (*flag != epoch) { cudaGetLastError(); return set_err(h, WFSA_ERR_CUDA, "k_eval6 finished without its completion word"); } }
+                }
+            std::memcpy(h->h_out, h->hm_out, ((size_t)h->n + 3) * 8);
+            // (the same values are NOT in d_out: a later wfsa_dev_eval_fetch copies them back up first)
+            h->out_on_host = true;
             return finish_fetch(h, loglik, grad);
         }
     }
@@ -1870,6 +1902,19 @@ extern "C" int wfsa_dev_eval6_phases(wfsa_dev* h, double* out4, int reset)
     if (getenv("WFSA_E6_DEBUG"))
         fprintf(stderr, "[k_eval6 debug] longest group %.2f us (rows code 0x%x), latest end of the region phase %.2f us after the start of CTA 0, longest wait for staged words %.2f us\n",
                 (double)(v[4] >> 32) * 1e-3, (unsigned)(v[4] & 0xffffffffu), (double)v[5] * 1e-3, (double)v[7] * 1e-3);
+    if (getenv("WFSA_E6_DEBUG") && (atoi(getenv("WFSA_E6_DEBUG")) & 16) && h->kl_grid <= 1024) {
+        // per-CTA timeline of the last launch: when each phase ended, relative to the earliest CTA start
+        std::vector<unsigned long long> tl((size_t)h->kl_grid * 8);
+        CK(cudaMemcpy(tl.data(), h->d_e6stamps.p + 8, tl.size() * 8, cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull;
+        for (int b = 0; b < h->kl_grid; ++b) t0 = std::min(t0, tl[(size_t)b * 8]);
+        const char* nm[5] = {"start", "weights done", "regions done", "barrier passed", "end"};
+        for (int k = 0; k < 5; ++k) {
+            double mn = 1e30, mx = 0, sum = 0; int amx = 0;
+            for (int b = 0; b < h->kl_grid; ++b) { const double d = (double)(tl[(size_t)b * 8 + k] - t0) * 1e-3; if (d < mn) mn = d; if (d > mx) { mx = d; amx = b; } sum += d; }
+            fprintf(stderr, "[k_eval6 timeline] %-14s min %7.2f  mean %7.2f  max %7.2f us (CTA %d)\n", nm[k], mn, sum / h->kl_grid, mx, amx);
+        }
+    }
     for (int i = 0; i < 4; ++i) out4[i] = (double)v[i];
     return WFSA_OK;
 }
