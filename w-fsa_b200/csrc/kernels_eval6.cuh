@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
     __shared__ long long s_part[NT / 32][2];
     __shared__ unsigned int s_ticket;                         // next entry of this CTA's static share of the regular groups
     __shared__ int s_bigleft;                                 // warps of this CTA still busy with big DAG groups
+    __shared__ double s_trash[NT];                            // where the lanes without an edge store (kr_big_t)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* aw = reinterpret_cast<double*>(smem);             // [n_arcs + 1]; the last entry is the zero weight of padding
     double* pool = aw + P.n_arcs + 1 + tid;                   // slot s of this thread at pool[s*NT]
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
                     if (P.debug && lane == 0) atomicMax(P.stamps + 7, e6_timer() - tg0);
                 }
                 // (one instance: generic loads serve the staging area and HBM alike)
-                if (!(P.debug & 4)) kr_big_t<ACC_GLOBAL, true>(R, aw, pool, NT, g, lane, staged ? sw : P.words + off + lane, nw, staged ? sxs : xs, acc_g, ll);
+                if (!(P.debug & 4)) kr_big_t<ACC_GLOBAL, true>(R, aw, pool, NT, g, lane, staged ? sw : P.words + off + lane, nw, staged ? sxs : xs, acc_g, ll, &s_trash[tid]);
                 __syncwarp();
             }
         }

@@ -23,7 +23,12 @@ namespace wfsa {
 constexpr int kK7Chunk = 16;                 // strings of one pair per CTA (alpha tile in shared memory)
 constexpr int kK7Reg = 8;                    // table entries of a thread kept in registers (more: re-read)
 
-struct K7Desc { int cp, c, start, cnt; };    // strings perm[start .. start+cnt) of this step sit on the pair (cp, c); cp = n_sym at position 0
+constexpr int kK7Planes = 8;                 // in-/out-edges of a candidate kept in the pair planes (more: read through the row word)
+constexpr uint32_t kK7Sent = 0xfffffc00u;    // padding entry of a plane: transition field all ones, slot 0
+
+// strings perm[start .. start+cnt) of this step sit on the pair (cp, c); cp = n_sym at position 0.  c0c / c0p: first slot of
+// the candidates of c / cp; kf / kb: planes of the pair that hold entries (forward / backward tables)
+struct K7Desc { int cp, c, start, cnt, c0c, c0p, kf, kb; };
 
 struct K7Params {
     FastTablesD T;
@@ -41,7 +46,42 @@ struct K7Params {
     const int* __restrict__ EQ;              // bwd: exponent of q [r]
     const double* __restrict__ scale;        // bwd: p_s / q_s [r]
     int V, rescale;
+    // Pair planes (k7_build_planes): everything thread j needs for the pair (cp, c), laid out so that the threads of a CTA
+    // read consecutive words -- entry k of candidate j at pe[(key * kK7Planes + k) * V + j], its row word (start << 8 | count
+    // in the fent / bent table) at pr[key * V + j], key = cp * n_sym + c.  One round trip instead of the chain
+    // cand_off -> slot_state -> row -> entries of the per-state tables.
+    const uint32_t* __restrict__ pe;
+    const uint32_t* __restrict__ pr;
 };
+
+// Pair planes of one direction.  fwd: thread j = candidate j of c, row (state, cp) of the in-edge table; bwd: thread j =
+// candidate j of cp, row (state, c) of the out-edge table.  One CTA of V threads per key; kmax[key] = planes in use.
+__global__ void k7_build_planes(const FastTablesD T, int V, int fwd, uint32_t* pe, uint32_t* pr, int* kmax)
+{
+    __shared__ int s_max;
+    const int A = T.n_sym, j = threadIdx.x;
+    const size_t key = blockIdx.x;
+    const int cp = (int)(key / A), c = (int)(key % A);
+    if (j == 0) s_max = 0;
+    __syncthreads();
+    uint32_t row = 0;
+    const uint32_t* ent = fwd ? T.fent : T.bent;
+    if (fwd || cp < A) {
+        const int sym = fwd ? c : cp;
+        const uint32_t c0 = T.cand_off[sym], n = T.cand_off[sym + 1] - c0;
+        if ((uint32_t)j < n) {
+            const uint32_t st = T.slot_state[c0 + j];
+            row = fwd ? T.frow[(size_t)st * (A + 1) + cp] : T.brow[(size_t)st * A + c];
+        }
+    }
+    const int cnt = row & ((1u << kRowCntBitsD) - 1);
+    const uint32_t st = row >> kRowCntBitsD;
+    pr[key * V + j] = row;
+    for (int k = 0; k < kK7Planes; ++k) pe[(key * kK7Planes + k) * V + j] = k < cnt ? ent[st + k] : kK7Sent;
+    if (cnt) atomicMax(&s_max, min(cnt, kK7Planes));
+    __syncthreads();
+    if (j == 0) kmax[key] = s_max;
+}
 
 // the largest biased exponent of one value per thread over the CTA (-1: all zero)
 __device__ __forceinline__ int k7_block_emax(double a, int* s_red, int nwarps, int warp, int lane)
@@ -279,6 +319,183 @@ __global__ void __launch_bounds__(512, 2) k7_bwd(const K7Params P)
 #pragma unroll
         for (int k = 0; k < kK7Reg; ++k) if (lacc[k]) atomicAdd(P.O.acc_global + st + k, (unsigned long long)lacc[k]);
     }
+}
+
+
+// ---- the same two steps on the pair planes ------------------------------------------------------------------------------
+// What changed against k7_fwd / k7_bwd (same arithmetic, same order of every sum): the table entries of thread j come from
+// the pair planes in ONE coalesced round trip; the alpha / beta rows of the chunk go to shared memory with cp.async while
+// the weights are gathered; shared-memory addresses are byte offsets computed once; the exponent check of a rescale step
+// takes one pass over the chunk and a fix-up pass for the (rare) strings that leave the band, instead of two block barriers
+// per string; the alpha_t values of the backward step are fetched four strings ahead.
+
+__device__ __forceinline__ void k7_cp_async8(void* smem_dst, const void* gsrc)
+{
+    const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ double k7_lds(const char* base, unsigned int off)
+{
+    return *reinterpret_cast<const double*>(base + off);
+}
+
+__global__ void __launch_bounds__(512, 2) k7_fwd2(const K7Params P)
+{
+    extern __shared__ double k7_tile[];                     // [kK7Chunk][V]
+    __shared__ int s_r[kK7Chunk], s_E[kK7Chunk], s_emax[kK7Chunk];
+    const FastTablesD& T = P.T;
+    const int V = P.V, j = threadIdx.x, lane = j & 31, A = T.n_sym;
+    const K7Desc d = P.desc[blockIdx.x];
+    const size_t key = (size_t)d.cp * A + d.c;
+    if (j < d.cnt) { s_r[j] = P.perm[d.start + j]; s_emax[j] = -1; }
+    uint32_t ent[kK7Planes];
+#pragma unroll
+    for (int k = 0; k < kK7Planes; ++k) ent[k] = k < d.kf ? P.pe[(key * kK7Planes + k) * V + j] : kK7Sent;
+    const uint32_t row = P.pr[key * V + j];
+    const double swj = P.W.sw[min(d.c0c + j, T.n_slots - 1)];
+    __syncthreads();
+    if (d.cp == A) {
+        for (int i = 0; i < d.cnt; ++i) k7_tile[i * V + j] = j == 0 ? 1.0 : 0.0;
+    } else {
+        for (int i = 0; i < d.cnt; ++i) k7_cp_async8(k7_tile + i * V + j, P.src + (size_t)s_r[i] * V + j);
+    }
+    if (j < d.cnt) s_E[j] = d.cp == A ? 0 : P.exp_src[s_r[j]];
+    double w[kK7Planes];
+    unsigned int off[kK7Planes];
+#pragma unroll
+    for (int k = 0; k < kK7Planes; ++k) {
+        w[k] = (ent[k] >> kSlotBitsD) != (kK7Sent >> kSlotBitsD) ? P.W.tw[ent[k] >> kSlotBitsD] : 0.0;
+        off[k] = (ent[k] & ((1u << kSlotBitsD) - 1)) * 8u;
+    }
+    const int cnt = row & ((1u << kRowCntBitsD) - 1);
+    const uint32_t st = row >> kRowCntBitsD;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    const char* tile = reinterpret_cast<const char*>(k7_tile);
+    const unsigned int rowb = (unsigned int)V * 8u;
+    for (int i = 0; i < d.cnt; ++i) {
+        const char* sv = tile + (unsigned int)i * rowb;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < kK7Planes; ++k) s = fma(w[k], k7_lds(sv, off[k]), s);
+        for (int k = kK7Planes; k < cnt; ++k) {
+            const uint32_t e = T.fent[st + k];
+            s = fma(P.W.tw[e >> kSlotBitsD], k7_lds(sv, (e & ((1u << kSlotBitsD) - 1)) * 8u), s);
+        }
+        const double v = s * swj;
+        if (P.rescale) {
+            const int wmax = __reduce_max_sync(FULL, v != 0.0 ? biased_exp(v) : -1);
+            if (lane == 0 && wmax >= 0) atomicMax(&s_emax[i], wmax);
+        }
+        P.dst[(size_t)s_r[i] * V + j] = v;
+    }
+    if (P.rescale) {
+        __syncthreads();
+        for (int i = 0; i < d.cnt; ++i) {
+            const int emax = s_emax[i];
+            if (emax >= 0 && (emax < 1023 - kRescaleBand || emax > 1023 + kRescaleBand)) {
+                double* q = P.dst + (size_t)s_r[i] * V + j;
+                *q = scalbn(*q, 1023 - emax);                 // this thread's own store of the loop above
+                if (j == i) s_E[i] -= 1023 - emax;
+            }
+        }
+    }
+    if (j < d.cnt) P.exp_dst[s_r[j]] = s_E[j];
+}
+
+__global__ void __launch_bounds__(512, 2) k7_bwd2(const K7Params P)
+{
+    extern __shared__ double k7_tile[];
+    __shared__ int s_r[kK7Chunk], s_emax[kK7Chunk];
+    __shared__ double s_sc[kK7Chunk];                        // p_s / q_s * 2^k * 2^(E_t + F_{t+1} - EQ) per string
+    const FastTablesD& T = P.T;
+    const int V = P.V, j = threadIdx.x, lane = j & 31, A = T.n_sym;
+    const K7Desc d = P.desc[blockIdx.x];                     // (cp < n_sym: the step out of the start state runs k7_bwd)
+    const size_t key = (size_t)d.cp * A + d.c;
+    if (j < d.cnt) { s_r[j] = P.perm[d.start + j]; s_emax[j] = -1; }
+    uint32_t ent[kK7Planes];
+#pragma unroll
+    for (int k = 0; k < kK7Planes; ++k) ent[k] = k < d.kb ? P.pe[(key * kK7Planes + k) * V + j] : kK7Sent;
+    const uint32_t row = P.pr[key * V + j];
+    const double swj = P.W.sw[min(d.c0p + j, T.n_slots - 1)];
+    __syncthreads();
+    for (int i = 0; i < d.cnt; ++i) k7_cp_async8(k7_tile + i * V + j, P.src + (size_t)s_r[i] * V + j);
+    constexpr int PF = 2;                                    // strings whose alpha_t value is fetched ahead
+    double aln[PF];
+#pragma unroll
+    for (int ii = 0; ii < PF; ++ii) aln[ii] = ii < d.cnt ? P.lat[(size_t)s_r[ii] * V + j] : 0.0;
+    if (j < d.cnt) {
+        const int r = s_r[j];
+        const int de = P.exp_t[r] + P.F[r] - P.EQ[r];
+        double sc = P.scale[r] * P.O.fx_scale;
+        if (de != 0) sc = scalbn(sc, de);
+        s_sc[j] = sc;
+    }
+    double w[kK7Planes];
+    unsigned int off2[kK7Planes / 2];                        // two 16-bit byte offsets per register
+#pragma unroll
+    for (int k = 0; k < kK7Planes; ++k) w[k] = (ent[k] >> kSlotBitsD) != (kK7Sent >> kSlotBitsD) ? P.W.tw[ent[k] >> kSlotBitsD] : 0.0;
+#pragma unroll
+    for (int k = 0; k < kK7Planes; k += 2)
+        off2[k / 2] = ((ent[k] & ((1u << kSlotBitsD) - 1)) * 8u) | (((ent[k + 1] & ((1u << kSlotBitsD) - 1)) * 8u) << 16);
+    const int cnt = row & ((1u << kRowCntBitsD) - 1);
+    const uint32_t st = row >> kRowCntBitsD;
+    long long lacc[kK7Planes];
+#pragma unroll
+    for (int k = 0; k < kK7Planes; ++k) lacc[k] = 0;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    const char* tile = reinterpret_cast<const char*>(k7_tile);
+    const unsigned int rowb = (unsigned int)V * 8u;
+    for (int i0 = 0; i0 < d.cnt; i0 += PF) {
+        double al[PF];
+#pragma unroll
+        for (int ii = 0; ii < PF; ++ii) al[ii] = aln[ii];
+#pragma unroll
+        for (int ii = 0; ii < PF; ++ii) if (i0 + PF + ii < d.cnt) aln[ii] = P.lat[(size_t)s_r[i0 + PF + ii] * V + j];
+#pragma unroll
+        for (int ii = 0; ii < PF; ++ii) {
+            const int i = i0 + ii;
+            if (i >= d.cnt) break;
+            double bt = 0.0;
+            if (al[ii] != 0.0) {
+                const double sc = s_sc[i];
+                const char* sv = tile + (unsigned int)i * rowb;
+                double b = 0.0;
+#pragma unroll
+                for (int k = 0; k < kK7Planes; ++k) {
+                    const double term = w[k] * k7_lds(sv, (k & 1) ? off2[k / 2] >> 16 : off2[k / 2] & 0xffffu);
+                    b += term;
+                    lacc[k] += __double2ll_rn(al[ii] * term * sc);
+                }
+                for (int k = kK7Planes; k < cnt; ++k) {
+                    const uint32_t e = T.bent[st + k];
+                    const double term = P.W.tw[e >> kSlotBitsD] * k7_lds(sv, (e & ((1u << kSlotBitsD) - 1)) * 8u);
+                    b += term;
+                    if (term != 0.0) { const long long v = __double2ll_rn(al[ii] * term * sc); if (v) atomicAdd(P.O.acc_global + st + k, (unsigned long long)v); }
+                }
+                bt = b * swj;
+            }
+            if (P.rescale) {
+                const int wmax = __reduce_max_sync(FULL, bt != 0.0 ? biased_exp(bt) : -1);
+                if (lane == 0 && wmax >= 0) atomicMax(&s_emax[i], wmax);
+            }
+            P.dst[(size_t)s_r[i] * V + j] = bt;
+        }
+    }
+    if (P.rescale) {
+        __syncthreads();
+        for (int i = 0; i < d.cnt; ++i) {
+            const int emax = s_emax[i];
+            if (emax >= 0 && (emax < 1023 - kRescaleBand || emax > 1023 + kRescaleBand)) {
+                double* q = P.dst + (size_t)s_r[i] * V + j;
+                *q = scalbn(*q, 1023 - emax);
+                if (j == i) P.F[s_r[i]] -= 1023 - emax;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kK7Planes; ++k) if (lacc[k]) atomicAdd(P.O.acc_global + st + k, (unsigned long long)lacc[k]);
 }
 
 }  // namespace wfsa

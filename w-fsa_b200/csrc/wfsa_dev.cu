@@ -206,6 +206,10 @@ struct wfsa_dev {
     int k7_V = 0; size_t k7_rows = 0, k7_nb = 0;
     DevBuf<double> d_k7lat, d_k7bt, d_k7scale; DevBuf<int> d_k7exp, d_k7EQ, d_k7F;
     double k7_host_ms = 0;
+    // pair planes of K7 (k7_build_planes): entries and row words per (symbol pair, candidate), forward and backward tables
+    DevBuf<uint32_t> d_k7pef, d_k7prf, d_k7peb, d_k7prb;
+    std::vector<int> k7_kf, k7_kb;             // planes in use per pair key
+    bool k7_planes = false;
     // single-launch evaluation of the segmented path (k_eval6, kernels_eval6.cuh)
     DevBuf<unsigned int> d_e6ctl;           // [0..1] tickets, [2] barrier arrivals, [3] epoch
     DevBuf<unsigned long long> d_e6acc, d_e6red, d_e6stamps;
@@ -269,6 +273,7 @@ extern "C" void wfsa_dev_destroy(wfsa_dev* h)
     h->d_ksgref.release(); h->d_kssid.release(); h->d_krW.release(); h->d_krlq.release(); h->d_ksp.release();
     h->d_kslogq.release(); h->d_klogaw.release(); h->d_eoff.release(); h->d_earc.release();
     for (auto* b : u32) b->release();
+    h->d_k7pef.release(); h->d_k7prf.release(); h->d_k7peb.release(); h->d_k7prb.release();
     DevBuf<double>* f64[] = {&h->d_p, &h->d_x, &h->d_tw, &h->d_sw, &h->d_fw, &h->d_ltw, &h->d_lew, &h->d_logq, &h->d_pathcnt,
                              &h->d_out, &h->d_k3lat, &h->d_gscratch, &h->d_aw, &h->d_hb_counts, &h->d_hb_p, &h->d_hb_r, &h->d_H, &h->d_rmin};
     for (auto* b : f64) b->release();
@@ -396,13 +401,48 @@ static bool kl_possible(const wfsa_dev* h, int K, int want_nt, int& nt, size_t& 
 {
     const LatticeArcs& A = h->larcs;
     if (A.n_arcs <= 0 || A.n_arcs >= (1 << kLatArcBits)) return false;
-    const size_t tab = ((size_t)A.n_arcs + 1) * 8, max_smem = 227 * 1024 - 4096;     // + the zero weight of padding (kr_regions); k_eval6 has 3 KB of static shared memory
+    const size_t tab = ((size_t)A.n_arcs + 1) * 8, max_smem = 227 * 1024 - 9216;     // + the zero weight of padding (kr_regions); k_eval6 has 7 KB of static shared memory, kr_regions up to 8
     if (tab + (size_t)128 * K * 8 > max_smem) return false;
     nt = (int)((max_smem - tab) / ((size_t)K * 8) / 32) * 32;
     nt = std::min(nt, 1024);
     if (want_nt > 0) nt = std::min(nt, want_nt);
     smem = tab + (size_t)nt * K * 8;
     return nt >= 128;
+}
+
+// K7 pair planes: built on the device from the per-state tables (structure only, once per handle).  If they do not fit
+// (alphabets far beyond config 5), K7 keeps walking the per-state tables (k7_fwd / k7_bwd).
+static int setup_k7_planes(wfsa_dev* h)
+{
+    h->k7_planes = false;
+    if (getenv("WFSA_K7_NO_PLANES")) return WFSA_OK;
+    const FastLayout& L = h->fast;
+    const size_t A = (size_t)L.n_sym, V = (size_t)h->k7_V, n_keys = (A + 1) * A;
+    const size_t words = n_keys * V * (kK7Planes + 1);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return WFSA_OK; }
+    if (2 * words * 4 > free_b / 8) return WFSA_OK;
+    DevBuf<int> d_kmax;
+    if (h->d_k7pef.alloc(n_keys * V * kK7Planes) != cudaSuccess || h->d_k7prf.alloc(n_keys * V) != cudaSuccess ||
+        h->d_k7peb.alloc(n_keys * V * kK7Planes) != cudaSuccess || h->d_k7prb.alloc(n_keys * V) != cudaSuccess ||
+        d_kmax.alloc(2 * n_keys) != cudaSuccess) {
+        cudaGetLastError();
+        h->d_k7pef.release(); h->d_k7prf.release(); h->d_k7peb.release(); h->d_k7prb.release(); d_kmax.release();
+        return WFSA_OK;
+    }
+    FastTablesD T{};
+    T.cand_off = h->d_cand_off.p; T.slot_state = h->d_slot_state.p;
+    T.frow = h->d_frow.p; T.fent = h->d_fent.p; T.brow = h->d_brow.p; T.bent = h->d_bent.p;
+    T.n_sym = L.n_sym; T.n_states = h->fsa.n_states; T.n_arcs = L.n_arcs; T.n_slots = L.n_slots;
+    k7_build_planes<<<(unsigned)n_keys, (unsigned)V, 0, h->stream>>>(T, (int)V, 1, h->d_k7pef.p, h->d_k7prf.p, d_kmax.p);
+    k7_build_planes<<<(unsigned)n_keys, (unsigned)V, 0, h->stream>>>(T, (int)V, 0, h->d_k7peb.p, h->d_k7prb.p, d_kmax.p + n_keys);
+    h->k7_kf.assign(n_keys, 0); h->k7_kb.assign(n_keys, 0);
+    CK(cudaMemcpyAsync(h->k7_kf.data(), d_kmax.p, n_keys * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->k7_kb.data(), d_kmax.p + n_keys, n_keys * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    d_kmax.release();
+    h->k7_planes = true;
+    return WFSA_OK;
 }
 
 static int setup_kl(wfsa_dev* h)
@@ -442,20 +482,20 @@ static int setup_kl(wfsa_dev* h)
             CK(h->d_e6ctl.upload(ctl, h->stream));
             CK(h->d_e6red.alloc(2)); CK(cudaMemsetAsync(h->d_e6red.p, 0, 16, h->stream));
             CK(h->d_e6stamps.alloc(8 + 8 * 1024)); CK(cudaMemsetAsync(h->d_e6stamps.p, 0, (8 + 8 * 1024) * 8, h->stream));
-            cudaFuncSetAttribute(k_eval6<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);
-            cudaFuncSetAttribute(k_eval6<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);
-            cudaFuncSetAttribute(k_eval6<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);
-            cudaFuncSetAttribute(k_eval6<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);
+            cudaFuncSetAttribute(k_eval6<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);
+            cudaFuncSetAttribute(k_eval6<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);
+            cudaFuncSetAttribute(k_eval6<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);
+            cudaFuncSetAttribute(k_eval6<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);
         }
         h->ks_smem = ((size_t)A.n_arcs + 16) * 8;
         h->ks_block = kKsWarps * 32;
         h->ks_ctas = h->ks_smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
         h->ks_grid = h->sm_count * h->ks_ctas;
-        cudaFuncSetAttribute(kr_regions<ACC_GLOBAL, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(kr_regions<ACC_GLOBAL, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(kr_regions<ACC_GLOBAL, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(kr_regions<ACC_SMEM_CAS, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(kr_regions<ACC_NONE, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(kr_regions<ACC_GLOBAL, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192 - 1024);
+        cudaFuncSetAttribute(kr_regions<ACC_GLOBAL, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192 - 1024);
+        cudaFuncSetAttribute(kr_regions<ACC_GLOBAL, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192 - 1024);
+        cudaFuncSetAttribute(kr_regions<ACC_SMEM_CAS, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192 - 1024);
+        cudaFuncSetAttribute(kr_regions<ACC_NONE, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192 - 1024);
         cudaFuncSetAttribute(ks_strings, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ks_smem);   // it also has static shared memory
     }
     cudaFuncSetAttribute(kl_fwdbwd<ACC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -501,7 +541,12 @@ static int choose_launch(wfsa_dev* h)
         h->k7_V = (h->fast.max_cand + 31) / 32 * 32;
         cudaFuncSetAttribute(k7_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kK7Chunk * h->k7_V * 8);
         cudaFuncSetAttribute(k7_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kK7Chunk * h->k7_V * 8);
+        cudaFuncSetAttribute(k7_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, kK7Chunk * h->k7_V * 8);
+        cudaFuncSetAttribute(k7_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, kK7Chunk * h->k7_V * 8);
+        cudaFuncSetAttribute(k7_fwd2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k7_bwd2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         rc = setup_k3(h);
+        if (rc == WFSA_OK) rc = setup_k7_planes(h);
     } else if (h->kernel == 1) rc = setup_k2(h);
     else if (h->kernel == 2) rc = setup_k3(h);
     else rc = setup_generic(h);
@@ -760,7 +805,11 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
                 P.exp_src = t ? h->d_k7exp.p + B.row_off[t - 1] : nullptr; P.exp_dst = h->d_k7exp.p + B.row_off[t];
                 P.rescale = (t & (kRescaleEvery - 1)) == kRescaleEvery - 1;
                 const unsigned nd = (unsigned)(B.desc_off[t + 1] - B.desc_off[t]);
-                if (nd) { k7_fwd<<<nd, V, smem, st>>>(P); h->launches++; }
+                if (nd) {
+                    if (h->k7_planes) { P.pe = h->d_k7pef.p; P.pr = h->d_k7prf.p; k7_fwd2<<<nd, V, smem, st>>>(P); }
+                    else k7_fwd<<<nd, V, smem, st>>>(P);
+                    h->launches++;
+                }
                 if (B.n_t[t + 1] < B.n_t[t]) {                 // strings that end here: q, log q, p_s / q_s
                     Fn.r0 = B.n_t[t + 1]; Fn.r1 = B.n_t[t]; Fn.lat = lat + B.row_off[t] * V; Fn.exp_t = h->d_k7exp.p + B.row_off[t];
                     k7_finish_q<<<(Fn.r1 - Fn.r0 + 7) / 8, 256, 0, st>>>(Fn);
@@ -779,7 +828,11 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
                     P.src = bt[(t + 1) & 1]; P.dst = bt[t & 1]; P.lat = lat + B.row_off[t] * V; P.exp_t = h->d_k7exp.p + B.row_off[t];
                     P.rescale = (t & (kRescaleEvery - 1)) == 0;
                     const unsigned nd = (unsigned)(B.desc_off[t + 2] - B.desc_off[t + 1]);
-                    if (nd) { k7_bwd<<<nd, V, smem, st>>>(P); h->launches++; }
+                    if (nd) {
+                        if (h->k7_planes) { P.pe = h->d_k7peb.p; P.pr = h->d_k7prb.p; k7_bwd2<<<nd, V, smem, st>>>(P); }
+                        else k7_bwd<<<nd, V, smem, st>>>(P);
+                        h->launches++;
+                    }
                 }
             }
             {                                                  // the arcs out of the start state (descriptors of step 0: cp = START)
@@ -1150,7 +1203,7 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
             h->e6_ok = regular && cls.size() <= (size_t)kE6MaxCls && (h->kl_block == 512 || h->kl_block == 384 || h->kl_block == 256 || h->kl_block == 128) && h->kr_groups < (int64_t)0x7fffffff && !getenv("WFSA_EVAL6_OFF");
             if (cls.empty()) cls.push_back(Eval6Cls{0, 4, 0});
             {   // staging areas for the big DAG groups in the shared memory the tables and the pool leave free
-                const size_t room = (size_t)(227 * 1024 - 4096) - h->kl_smem;
+                const size_t room = (size_t)(227 * 1024 - 8192) - h->kl_smem;
                 int rows = (int)std::max<int64_t>(sc.max_big_rows, 0);
                 if (rows > 0 && (size_t)rows * 384 > room) rows = (int)(room / 384 / 16) * 16;      // larger groups stay in HBM
                 h->e6_big_rows = rows;
@@ -1238,7 +1291,12 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
                     int run = 0;
                     for (size_t k = 0; k + 1 < cnt.size(); ++k) {
                         const int c = cnt[k + 1];
-                        for (int b = 0; b < c; b += kK7Chunk) D.push_back(K7Desc{(int)(k / A), (int)(k % A), run + b, std::min(kK7Chunk, c - b)});
+                        if (c > 0) {
+                            const int cp = (int)(k / A), cc = (int)(k % A);
+                            const int kf = h->k7_planes ? h->k7_kf[k] : 0, kb = h->k7_planes ? h->k7_kb[k] : 0;
+                            for (int b = 0; b < c; b += kK7Chunk)
+                                D.push_back(K7Desc{cp, cc, run + b, std::min(kK7Chunk, c - b), (int)h->fast.cand_off[cc], (int)h->fast.cand_off[cp], kf, kb});
+                        }
                         cnt[k + 1] = run; run += c;                                       // becomes the write cursor of key k
                     }
                     int32_t* out = perm.data() + B.row_off[t];
