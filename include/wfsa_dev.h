@@ -87,7 +87,9 @@ int wfsa_dev_create(const wfsa_fsa_desc* fsa, const wfsa_corpus_desc* corpus,
  * (src/Learner.cpp:276-348 driving inc/Recognize.h:62-96).  recognised[s] = 1 iff the string
  * has an accepting path; path_count[s] = number of accepting paths (a double; the DP counts,
  * it does not enumerate); param_used[i] = 1 iff raw parameter i lies on an accepting path of
- * some string of this shard (feeds Learner::Trim, :350-425).  Any pointer may be NULL. */
+ * some string of this shard (feeds Learner::Trim, :350-425).  Any pointer may be NULL.
+ * The pass reuses the evaluation's string-order buffers: a parameter map set earlier is void
+ * afterwards (evaluations return WFSA_ERR_STATE until wfsa_dev_set_param_map is called again). */
 int wfsa_dev_structure(wfsa_dev* h, uint8_t* recognised, double* path_count, uint8_t* param_used);
 
 /* trimmed[i] for every raw parameter: -2 unused (weight exp(-inf)=0), -1 pinned (weight 1),

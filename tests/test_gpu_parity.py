@@ -471,6 +471,39 @@ def test_two_ranks_nccl(kernel, variant):
     assert r.returncode == 0 and "nccl_worker ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+@pytest.mark.parametrize("optimizer,init", [("QuasiNewton", 7), ("Hessian", 15)])
+def test_cli_two_gpus_same_table(optimizer, init, tmp_path):
+    """`wfsa --gpus 2` (one forked process per GPU, the training loop of /root/reference/src/main.cpp:271-304 on every
+    rank, sums over the ranks inside the backend) prints the same optimisation table and writes the same weights as one
+    GPU.  Skipped on a one-GPU box."""
+    import os
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    exe = os.path.join(root, "w-fsa_b200", "_build", "wfsa")
+    fsa = tmp_path / "talk.wfsa"; corpus = tmp_path / "talk.corpus"
+    fsa.write_text("\n^\n$\n^  0\n^ TALK_N 0 TALK_V 0\nTALK_V talk 0\nTALK_V TENSE 0\nTALK_N talk 0\nTALK_N PLUR 0\nPLUR  0 s 0\nPLUR $ 0\nTENSE  0 s 0 ed 0\nTENSE $ 0\n")
+    corpus.write_text("\ntalk 1\ntalks 2\ntalked 1\ntalking 1\ntalkings 1\n")
+    outs = []
+    for gpus in (1, 2):
+        r = subprocess.run([exe, "-a", str(fsa), "-c", str(corpus), "-opt", optimizer, "-i", str(init), "-e", "6", "--full", "--gpus", str(gpus)],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-3000:]
+        table = [ln.split() for ln in r.stderr.splitlines() if ln[:2].isdigit() or ln[:1].isdigit() and "\t" in ln]
+        assert len(table) >= 3, r.stderr[-3000:]
+        outs.append((table, r.stdout))
+    (t1, w1), (t2, w2) = outs
+    assert len(t1) == len(t2)
+    for a, b in zip(t1, t2):
+        assert np.allclose([float(v) for v in a], [float(v) for v in b], rtol=1e-6, atol=1e-9), (a, b)
+    n1 = [float(v) for ln in w1.splitlines() for v in ln.split() if v.replace(".", "").replace("-", "").replace("e", "").replace("+", "").isdigit()]
+    n2 = [float(v) for ln in w2.splitlines() for v in ln.split() if v.replace(".", "").replace("-", "").replace("e", "").replace("+", "").isdigit()]
+    assert len(n1) == len(n2) and len(n1) > 0 and np.allclose(n1, n2, rtol=1e-6, atol=1e-9)
+
+
 def _device_hessian(dev, x, n):
     import ctypes as C
     H = np.zeros((n, n)); rmin = C.c_double()

@@ -90,6 +90,10 @@ __device__ __forceinline__ void e6_paths_long(const KRParams& P, const double* a
 {
     constexpr int LB = 24 / PP;
     const uint32_t* wp = P.words + off + lane;
+    // more than one batch: ask for all rows of the group now (one 128-byte row per lane and round), so that the later
+    // batches find them in the L2 instead of paying a DRAM round trip each (an 8 x 16 group took 26 us: twelve batches)
+    if (L > LB)
+        for (int i = lane; i < L * PP; i += 32) asm volatile("prefetch.global.L2 [%0];" :: "l"(P.words + off + (size_t)i * 32));
     const double W = P.typeW[g * 32 + lane];
     double r[PP];
 #pragma unroll
@@ -312,11 +316,19 @@ __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
     // which evens out the tail.  One global counter for all 18.7 k groups of config 4 was the limit of the whole phase:
     // same-address atomics retire at ~3 ns each in the L2, i.e. 55 us, and the profile showed the warps waiting for
     // their next ticket (the SHFL behind the atomic) more than for anything else.
+    // With dedicated CTAs (few big groups, each alone on its SM until it is done) the static share is dealt out among the
+    // other CTAs only: a dedicated CTA starts on the regular groups late and takes what the ticket counter has left.
     const long long n_rest = P.n_groups - P.n_big;
-    const long long n_stat = P.n_big + n_rest * P.static_pct / 100 / (long long)gridDim.x * (long long)gridDim.x;
+    const int n_ded = P.big_dedicate ? (int)(P.n_big < (long long)gridDim.x ? P.n_big : (long long)gridDim.x) : 0;
+    const int n_free = (int)gridDim.x - n_ded;
+    const bool ded = (int)blockIdx.x < n_ded;
+    const long long n_stat = n_free > 0 ? P.n_big + n_rest * P.static_pct / 100 / (long long)n_free * (long long)n_free : P.n_big;
     auto fetch = [&]() -> long long {                          // lane 0 only
-        const long long gs = P.n_big + (long long)blockIdx.x + (long long)atomicAdd(&s_ticket, 1u) * gridDim.x;
-        return gs < n_stat ? gs : n_stat + (long long)atomicAdd(counter, 1u);
+        if (!ded) {
+            const long long gs = P.n_big + (long long)((int)blockIdx.x - n_ded) + (long long)atomicAdd(&s_ticket, 1u) * n_free;
+            if (gs < n_stat) return gs;
+        }
+        return n_stat + (long long)atomicAdd(counter, 1u);
     };
     unsigned long long dbg_max = 0;
     long long big = big0;

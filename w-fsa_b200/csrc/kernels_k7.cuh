@@ -339,7 +339,8 @@ __device__ __forceinline__ double k7_lds(const char* base, unsigned int off)
     return *reinterpret_cast<const double*>(base + off);
 }
 
-__global__ void __launch_bounds__(512, 2) k7_fwd2(const K7Params P)
+template <int MAXV, int MINB>
+__global__ void __launch_bounds__(MAXV, MINB) k7_fwd2(const K7Params P)
 {
     extern __shared__ double k7_tile[];                     // [kK7Chunk][V]
     __shared__ int s_r[kK7Chunk], s_E[kK7Chunk], s_emax[kK7Chunk];
@@ -403,7 +404,8 @@ __global__ void __launch_bounds__(512, 2) k7_fwd2(const K7Params P)
     if (j < d.cnt) P.exp_dst[s_r[j]] = s_E[j];
 }
 
-__global__ void __launch_bounds__(512, 2) k7_bwd2(const K7Params P)
+template <int MAXV, int MINB>
+__global__ void __launch_bounds__(MAXV, MINB) k7_bwd2(const K7Params P)
 {
     extern __shared__ double k7_tile[];
     __shared__ int s_r[kK7Chunk], s_emax[kK7Chunk];

@@ -222,6 +222,7 @@ struct wfsa_dev {
     double* hm_out = nullptr; double* hm_out_dev = nullptr; unsigned int* hm_flag = nullptr; unsigned int* hm_flag_dev = nullptr; size_t hm_n = 0;
     bool out_on_host = false;               // the results of the last evaluation are in h_out only (graph path)
     unsigned int hm_runs = 0;               // host-buffer launches of k_eval6 since the control words were last reset
+    double e2e_ns[4] = {0, 0, 0, 0}; long long e2e_calls = 0;   // WFSA_E2E_DEBUG: host time of the host-buffer call [stage x, graph launch, wait, copy out]
     cudaEvent_t ev_x = nullptr; bool x_in_flight = false;
 };
 
@@ -541,10 +542,13 @@ static int choose_launch(wfsa_dev* h)
         h->k7_V = (h->fast.max_cand + 31) / 32 * 32;
         cudaFuncSetAttribute(k7_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kK7Chunk * h->k7_V * 8);
         cudaFuncSetAttribute(k7_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kK7Chunk * h->k7_V * 8);
-        cudaFuncSetAttribute(k7_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, kK7Chunk * h->k7_V * 8);
-        cudaFuncSetAttribute(k7_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, kK7Chunk * h->k7_V * 8);
-        cudaFuncSetAttribute(k7_fwd2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k7_bwd2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        {   // up to 320 candidates per symbol (config 5): four forward / three backward CTAs per SM; else two of up to 512 threads
+            auto prep = [&](auto kern) {
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kK7Chunk * h->k7_V * 8);
+                cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            };
+            prep(k7_fwd2<320, 4>); prep(k7_fwd2<512, 2>); prep(k7_bwd2<320, 3>); prep(k7_bwd2<512, 2>);
+        }
         rc = setup_k3(h);
         if (rc == WFSA_OK) rc = setup_k7_planes(h);
     } else if (h->kernel == 1) rc = setup_k2(h);
@@ -806,7 +810,10 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
                 P.rescale = (t & (kRescaleEvery - 1)) == kRescaleEvery - 1;
                 const unsigned nd = (unsigned)(B.desc_off[t + 1] - B.desc_off[t]);
                 if (nd) {
-                    if (h->k7_planes) { P.pe = h->d_k7pef.p; P.pr = h->d_k7prf.p; k7_fwd2<<<nd, V, smem, st>>>(P); }
+                    if (h->k7_planes) {
+                        P.pe = h->d_k7pef.p; P.pr = h->d_k7prf.p;
+                        if (V <= 320) k7_fwd2<320, 4><<<nd, V, smem, st>>>(P); else k7_fwd2<512, 2><<<nd, V, smem, st>>>(P);
+                    }
                     else k7_fwd<<<nd, V, smem, st>>>(P);
                     h->launches++;
                 }
@@ -829,7 +836,10 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
                     P.rescale = (t & (kRescaleEvery - 1)) == 0;
                     const unsigned nd = (unsigned)(B.desc_off[t + 2] - B.desc_off[t + 1]);
                     if (nd) {
-                        if (h->k7_planes) { P.pe = h->d_k7peb.p; P.pr = h->d_k7prb.p; k7_bwd2<<<nd, V, smem, st>>>(P); }
+                        if (h->k7_planes) {
+                            P.pe = h->d_k7peb.p; P.pr = h->d_k7prb.p;
+                            if (V <= 320) k7_bwd2<320, 3><<<nd, V, smem, st>>>(P); else k7_bwd2<512, 2><<<nd, V, smem, st>>>(P);
+                        }
                         else k7_bwd<<<nd, V, smem, st>>>(P);
                         h->launches++;
                     }
@@ -901,7 +911,9 @@ static void fill_eval6_params(wfsa_dev* h, Eval6Params& P)
     P.debug = getenv("WFSA_E6_DEBUG") ? atoi(getenv("WFSA_E6_DEBUG")) : 0;
     P.pool_slots = h->kl_K; P.big_slots = h->e6_big_slots; P.big_rows = h->e6_big_rows;
     P.big_dedicate = (h->kr_big_groups > 0 && h->kr_big_groups * 4 <= h->kl_grid && !getenv("WFSA_E6_NO_DEDICATE")) ? 1 : 0;
-    if (P.big_dedicate && !getenv("WFSA_E6_STATIC")) P.static_pct = 0;
+    // dedicated CTAs: the shard is small (a few regular groups per warp): everything static among the free CTAs; one global
+    // ticket counter for ~3.5 k groups costs ~3 ns per ticket in the L2, i.e. ~10 us of a ~14 us phase
+    if (P.big_dedicate && !getenv("WFSA_E6_STATIC")) P.static_pct = 100;
 }
 
 static cudaError_t launch_eval6(wfsa_dev* h, cudaStream_t st, bool count = true, bool to_host = false)
@@ -1041,6 +1053,9 @@ extern "C" int wfsa_dev_structure(wfsa_dev* h, uint8_t* recognised, double* path
 {
     if (!h) return WFSA_ERR_INVALID;
     CK(cudaSetDevice(h->device));
+    // the structural pass reuses the string-order buffers of the evaluation: a parameter map set earlier is void after it
+    // (wfsa_dev_eval returns WFSA_ERR_STATE until wfsa_dev_set_param_map is called again)
+    h->n = -1; h->evaluated = false;
     CK(cudaMemcpyAsync(h->d_order.p, h->h_order_all.data(), (size_t)h->n_strings * 4, cudaMemcpyHostToDevice, h->stream));
     std::vector<double> pc((size_t)h->n_strings);
     h->h_overflow.assign((size_t)h->n_strings, 0);
@@ -1403,11 +1418,27 @@ static int stage_x(wfsa_dev* h, const double* x)
     // the staging buffer is reused by every call: wait for the copy of the previous one before overwriting it
     if (h->x_in_flight) { CK(cudaEventSynchronize(h->ev_x)); h->x_in_flight = false; }
     // fixed-point scale of loglik: |sum_s p_s log q_s| <= max steps * (2 max|x| + log(fan-out))
-    double mx = 0.0; bool finite = true;
-    for (int i = 0; i < h->n; ++i) {
-        const double v = x[i];
-        h->h_x[i] = v;
-        if (!std::isfinite(v)) finite = false; else mx = std::max(mx, std::fabs(v));
+    // (one pass the compiler can vectorise: max of |x| with NaN mapped to +inf, so `finite` falls out of the maximum)
+    double mx = 0.0;
+    {
+        const int n = h->n;
+        double* __restrict__ dst = h->h_x;
+        double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+        int i = 0;
+        for (; i + 4 <= n; i += 4) {
+            const double a = x[i], b = x[i + 1], c = x[i + 2], d = x[i + 3];
+            dst[i] = a; dst[i + 1] = b; dst[i + 2] = c; dst[i + 3] = d;
+            const double fa = a == a ? std::fabs(a) : HUGE_VAL, fb = b == b ? std::fabs(b) : HUGE_VAL;
+            const double fc = c == c ? std::fabs(c) : HUGE_VAL, fd = d == d ? std::fabs(d) : HUGE_VAL;
+            m0 = fa > m0 ? fa : m0; m1 = fb > m1 ? fb : m1; m2 = fc > m2 ? fc : m2; m3 = fd > m3 ? fd : m3;
+        }
+        for (; i < n; ++i) { const double a = x[i]; dst[i] = a; const double fa = a == a ? std::fabs(a) : HUGE_VAL; m0 = fa > m0 ? fa : m0; }
+        mx = std::max(std::max(m0, m1), std::max(m2, m3));
+    }
+    const bool finite = mx < HUGE_VAL;
+    if (!finite) {                                             // the largest finite |x| sets the scale, as before
+        mx = 0.0;
+        for (int i = 0; i < h->n; ++i) if (std::isfinite(x[i])) mx = std::max(mx, std::fabs(x[i]));
     }
     const double B = (double)h->step_bound * (2.0 * mx + std::log((double)h->n_edges + 2.0)) + 1.0;
     int bits = 1;
@@ -1555,8 +1586,16 @@ static int ensure_ks(wfsa_dev* h)
 }
 
 // the results of the evaluation are in h_out: error checks, then copies into the caller's buffers
-static int finish_fetch(wfsa_dev* h, double* loglik, double* grad)
+static int finish_fetch(wfsa_dev* h, double* loglik, double* grad, const double* src = nullptr)
 {
+    if (src) {                                                 // results in mapped memory: one pass fills the caller's buffers and h_out
+        h->h_out[0] = src[0]; h->h_out[1] = src[1]; h->h_out[h->n + 2] = src[h->n + 2];
+        double* __restrict__ keep = h->h_out + 2;
+        const double* __restrict__ g = src + 2;
+        if (grad) for (int i = 0; i < h->n; ++i) { const double v = g[i]; keep[i] = v; grad[i] = v; }
+        else std::memcpy(keep, g, (size_t)h->n * 8);
+        grad = nullptr;
+    }
     if (h->comm && (std::isnan(h->h_out[1]) || h->h_out[h->n + 2] != 0.0)) {
         // the ranks no longer agree on the epoch of the exchange: later evaluations of this handle fail as well
         h->comm_failed = true;
@@ -1638,10 +1677,14 @@ extern "C" int wfsa_dev_eval(wfsa_dev* h, const double* x, double* loglik, doubl
         // the lean segmented path as one graph launch
         CK(cudaSetDevice(h->device));
         if (eval6_graph(h)) {
+            static const bool e2e_dbg = getenv("WFSA_E2E_DEBUG") != nullptr;
+            const auto tp0 = std::chrono::steady_clock::now();
             const int rc = stage_x(h, x);
             if (rc != WFSA_OK) return rc;
+            const auto tp1 = std::chrono::steady_clock::now();
             const unsigned int epoch = ++h->hm_runs;
             CK(cudaGraphLaunch(h->e6_exec, h->stream));
+            const auto tp2 = std::chrono::steady_clock::now();
             h->launches++; h->e6_used = true; h->evaluated = true; h->ks_done = false; h->lean_now = true; h->lean_finished = true;
             // wait for the completion word of this epoch; every now and then ask the stream whether it failed instead
             volatile unsigned int* flag = h->hm_flag;
@@ -1650,10 +1693,21 @@ extern "C" int wfsa_dev_eval(wfsa_dev* h, const double* x, double* loglik, doubl
                     const cudaError_t q = cudaStreamQuery(h->stream);
                     if (q != cudaErrorNotReady) { if (q != cudaSuccess) CK(q); if (*flag != epoch) { cudaGetLastError(); return set_err(h, WFSA_ERR_CUDA, "k_eval6 finished without its completion word"); } }
                 }
-            std::memcpy(h->h_out, h->hm_out, ((size_t)h->n + 3) * 8);
-            // (the same values are NOT in d_out: a later wfsa_dev_eval_fetch copies them back up first)
+            const auto tp3 = std::chrono::steady_clock::now();
+            // (the same values are NOT in d_out: a later wfsa_dev_eval_fetch finds them in h_out)
             h->out_on_host = true;
-            return finish_fetch(h, loglik, grad);
+            const int frc = finish_fetch(h, loglik, grad, h->hm_out);
+            if (e2e_dbg) {
+                const auto tp4 = std::chrono::steady_clock::now();
+                auto ns = [](auto a, auto b) { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count(); };
+                h->e2e_ns[0] += ns(tp0, tp1); h->e2e_ns[1] += ns(tp1, tp2); h->e2e_ns[2] += ns(tp2, tp3); h->e2e_ns[3] += ns(tp3, tp4);
+                if (++h->e2e_calls % 20 == 0) {
+                    fprintf(stderr, "[wfsa_dev_eval] host us per call over the last 20: stage x %.2f, graph launch %.2f, wait for the completion word %.2f, copy out %.2f\n",
+                            h->e2e_ns[0] / 2e4, h->e2e_ns[1] / 2e4, h->e2e_ns[2] / 2e4, h->e2e_ns[3] / 2e4);
+                    h->e2e_ns[0] = h->e2e_ns[1] = h->e2e_ns[2] = h->e2e_ns[3] = 0;
+                }
+            }
+            return frc;
         }
     }
     int rc = wfsa_dev_upload_x(h, x);
@@ -1971,6 +2025,12 @@ extern "C" int wfsa_dev_eval6_phases(wfsa_dev* h, double* out4, int reset)
             double mn = 1e30, mx = 0, sum = 0; int amx = 0;
             for (int b = 0; b < h->kl_grid; ++b) { const double d = (double)(tl[(size_t)b * 8 + k] - t0) * 1e-3; if (d < mn) mn = d; if (d > mx) { mx = d; amx = b; } sum += d; }
             fprintf(stderr, "[k_eval6 timeline] %-14s min %7.2f  mean %7.2f  max %7.2f us (CTA %d)\n", nm[k], mn, sum / h->kl_grid, mx, amx);
+        }
+        if (atoi(getenv("WFSA_E6_DEBUG")) & 32) {             // every CTA: time from the grid barrier to its end (fold + exchange)
+            std::string line = "[k_eval6 timeline] rank " + std::to_string(h->rank) + " fold+exchange us per CTA:";
+            char buf[32];
+            for (int b = 0; b < h->kl_grid; ++b) { snprintf(buf, sizeof buf, " %.1f", (double)(tl[(size_t)b * 8 + 4] - tl[(size_t)b * 8 + 3]) * 1e-3); line += buf; }
+            fprintf(stderr, "%s\n", line.c_str());
         }
     }
     for (int i = 0; i < 4; ++i) out4[i] = (double)v[i];

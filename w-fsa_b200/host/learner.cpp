@@ -500,8 +500,45 @@ void HessianLearner::OptimizationStep(double eta, bool)  // src/HessianLearner.c
     const int n = GetNumberOfParameters(), N = GetNumberOfAugmentedParameters();
     ComputeRhs();
     ComputeObjective();
-    H.assign((size_t)N * N, 0.0);
     rmin = 0.0;
+    diag_solved = false;
+    if (!include_Hf) {
+        // Without H_f the KKT matrix is [D B; B^T 0] with D = diag(e^x_i lambda_c(i)) and one entry e^x_i per row of B
+        // (every parameter sits in exactly one constraint, src/HessianLearner.cpp:622-639): the Schur complement
+        // B^T D^-1 B on the multipliers is DIAGONAL, S_jj = sum_{i in j} e^x_i / lambda_j.  Solve and inertia in O(n)
+        // instead of a dense (n+k)^3 factorisation (the reference hands the same sparse matrix to MKL DSS, :100-113);
+        // inertia by Haynsworth: In(K) = In(D) + In(-S).  A zero pivot falls through to the dense path below.
+        const int k = N - n;
+        const double* lambda = _x.data() + n;
+        std::vector<double> S(k, 0.0), t(k, 0.0);
+        bool ok = true;
+        int pos = 0, neg = 0;
+        for (int i = 0; i < n && ok; ++i) {
+            const double d = expx[i] * lambda[Ccol[i]];
+            if (d == 0.0 || !std::isfinite(d)) { ok = false; break; }
+            (d > 0 ? pos : neg)++;
+            S[Ccol[i]] += expx[i] * expx[i] / d;
+            t[Ccol[i]] += expx[i] * rhs[i] / d;
+        }
+        for (int j = 0; j < k && ok; ++j) { if (S[j] == 0.0 || !std::isfinite(S[j])) ok = false; else (S[j] < 0 ? pos : neg)++; }
+        if (ok) {
+            aux.assign(N, 0.0);
+            for (int j = 0; j < k; ++j) aux[n + j] = (t[j] - rhs[n + j]) / S[j];
+            for (int i = 0; i < n; ++i) aux[i] = (rhs[i] - expx[i] * aux[n + Ccol[i]]) / (expx[i] * lambda[Ccol[i]]);
+            diag_solved = true; diag_pos = pos; diag_neg = neg;
+            lambda_min = *std::min_element(_x.begin() + n, _x.end());
+            factored = true;
+        }
+    }
+    if (diag_solved) {
+        if (std::find_if(aux.begin(), aux.end(), [](double v) { return !std::isfinite(v); }) != aux.end()) diag_solved = false;
+    }
+    if (diag_solved) {
+        for (int i = 0; i < n; ++i) _x[i] -= eta * aux[i];
+        LambdaUpdate(aux.data() + n, _x.data() + n, eta, exponential_lambda);
+        return;
+    }
+    H.assign((size_t)N * N, 0.0);
     if (include_Hf) {
         ComputeHfDense(Hf, &rmin);
         for (int i = 0; i < n; ++i)
@@ -542,7 +579,8 @@ std::vector<double> HessianLearner::GetOptimizationInfo()
     error = std::max(std::max(result[1], std::fabs(result[2])), std::fabs(result[3]));
     if (!degenerate && factored) {
         int pos, neg, zero;
-        solver.Inertia(pos, neg, zero);
+        if (diag_solved) { pos = diag_pos; neg = diag_neg; }
+        else solver.Inertia(pos, neg, zero);
         result[4] = pos; result[5] = neg;
     }
     result[6] = lambda_min;

@@ -163,6 +163,7 @@ private:
     SymIndefinite solver;
     double error = 0, lambda_min = 0, rmin = 0;
     bool include_Hf = false, degenerate = false, exponential_lambda = false, factored = false;
+    bool diag_solved = false; int diag_pos = 0, diag_neg = 0;     // Newton step taken through the diagonal Schur complement (no H_f)
 };
 
 }  // namespace wfsa

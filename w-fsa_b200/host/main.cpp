@@ -3,7 +3,9 @@
 // Same options, same stderr/stdout protocol and exit codes as the reference executable
 // (/root/reference/src/main.cpp:68-106 options, :121-347 flow).  Not carried over: the MKL
 // micro-benchmarks (-testt/-testn), -t (MKL threads) and the -m path-matrix cache -- a DP
-// backend has no P/M matrices to cache.  -r only orders the -p/-pr path listing (BFS/DFS).  Added: --device N, --full (dump weights with 17 digits).
+// backend has no P/M matrices to cache.  -r only orders the -p/-pr path listing (BFS/DFS).  Added: --device N, --full (dump weights with 17 digits),
+// --gpus N: one process per GPU (forked before anything touches CUDA), corpus cut into N ranges of equal symbol count, the
+// same optimiser loop on every rank with loglik / gradient / H_f summed over the ranks inside the backend; rank 0 reports.
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -16,6 +18,11 @@
 #include <string>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include "../../include/wfsa_dev.h"
 #include "fsa.hpp"
 #include "learner.hpp"
 
@@ -88,14 +95,15 @@ static void usage()
         "  -x, --initx, --initial     reads initial x vector from stdin\n"
         "  -i, --init FLAGS           1 uniform, 2 normalize, 4 init multipliers, 8 use H_f,\n"
         "                             16 reorder (no-op: dense solve), 32 exponential multipliers\n"
-        "  --device N                 CUDA device ordinal (0)\n"
+        "  --device N                 CUDA device ordinal (0); with --gpus the first of N consecutive devices\n"
+        "  --gpus N                   shard the corpus over N GPUs of this node (one process per GPU, 1)\n"
         "  --full                     dump weights with 17 significant digits\n";
 }
 
 int main(int argc, const char* argv[])
 {
     std::string automaton_filename, corpus_filename, output_filename, optimizer = "Hessian";
-    int epochs = 20, initflags = 0, device = 0;
+    int epochs = 20, initflags = 0, device = 0, gpus = 1;
     bool normalize = false, print = false, print_recognize = false, suppress = false, evaluate = false, initx = false, full = false;
     int recognize = 0;
     double eta = 1.0, tolerance = 1e-6;
@@ -127,25 +135,68 @@ int main(int argc, const char* argv[])
         else if (is(a, {"-x", "--initx", "--initial"})) initx = true;
         else if (is(a, {"-i", "--init"})) initflags = atoi(next());
         else if (is(a, {"--device"})) device = atoi(next());
+        else if (is(a, {"--gpus"})) { gpus = atoi(next()); if (gpus < 1 || gpus > 8) { std::cerr << "--gpus must be between 1 and 8" << std::endl; return 1; } }
         else if (is(a, {"--full"})) full = true;
         else if (is(a, {"-m", "--matrices", "--matrix"})) { next(); std::cerr << "-m is not supported: the DP backend has no path matrices to cache" << std::endl; return 1; }
         else { std::cerr << "Unknown argument \"" << a << "\"!" << std::endl; return 1; }
     }
+    // --gpus N: fork the other ranks before CUDA is touched.  Rank 0 (this process) creates the communicator id and hands
+    // it to every child through a pipe; the children run the same program with their output discarded (their errors still
+    // reach the terminal) and rank 0 reports; -x values are read once, before the fork.
+    int rank = 0;
+    std::vector<pid_t> children;
+    std::vector<double> stdin_x;
+    unsigned char unique_id[WFSA_UNIQUE_ID_BYTES] = {0};
+    int err_fd = 2;
+    if (gpus > 1) {
+        if (initx) { double v; while (std::cin >> v) stdin_x.push_back(v); }
+        std::vector<int> wr;
+        for (int r = 1; r < gpus; ++r) {
+            int fd[2];
+            if (pipe(fd) != 0) { perror("pipe"); return 1; }
+            const pid_t pid = fork();
+            if (pid < 0) { perror("fork"); return 1; }
+            if (pid == 0) {
+                rank = r;
+                close(fd[1]);
+                for (int w : wr) close(w);
+                size_t got = 0;
+                while (got < sizeof unique_id) { const ssize_t k = read(fd[0], unique_id + got, sizeof unique_id - got); if (k <= 0) return 1; got += (size_t)k; }
+                close(fd[0]);
+                err_fd = dup(2);
+                const int nul = open("/dev/null", O_WRONLY);
+                if (nul >= 0) { dup2(nul, 1); dup2(nul, 2); close(nul); }
+                children.clear();
+                break;
+            }
+            close(fd[0]);
+            wr.push_back(fd[1]);
+            children.push_back(pid);
+        }
+        if (rank == 0) {
+            if (wfsa_dev_comm_unique_id(unique_id) != 0) { std::cerr << "--gpus: cannot create the communicator id (libnccl.so.2 not found?)" << std::endl; for (int w : wr) close(w); return 1; }
+            for (int w : wr) { if (write(w, unique_id, sizeof unique_id) != (ssize_t)sizeof unique_id) { perror("write"); return 1; } close(w); }
+        }
+    }
+    auto finish = [&](int rc) {                       // rank 0 collects the exit codes of the other ranks
+        for (pid_t c : children) { int st = 0; if (waitpid(c, &st, 0) < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) rc = rc ? rc : 1; }
+        return rc;
+    };
     try {
         Fsa fsa;
         std::unique_ptr<Learner> learner(optimizer == "Hessian" ? (Learner*)(new HessianLearner()) : (Learner*)(new QuasiNewtonLearner()));
-        BackendOptions bo; bo.device = device;
+        BackendOptions bo; bo.device = device + rank; bo.rank = rank; bo.nranks = gpus; bo.unique_id = gpus > 1 ? unique_id : nullptr;
         learner->SetBackend(bo);
         std::cerr << "Corpus: "; std::cerr.flush();
         Corpus corpus;
         if (FILE* f = fopen(corpus_filename.c_str(), "r")) { corpus.Read(f); fclose(f); }
-        else { std::cerr << "\nUnable to open \"" << corpus_filename << "\"!" << std::endl; return 1; }
+        else { std::cerr << "\nUnable to open \"" << corpus_filename << "\"!" << std::endl; return finish(1); }
         std::cerr << "\n\tsize: " << corpus.size() << "\n\tsum: " << corpus.Sum();
         corpus.Renormalize();
         std::cerr << ", renormalized to " << corpus.Sum() << std::endl;
         std::cerr << "Automaton: "; std::cerr.flush();
         if (FILE* f = fopen(automaton_filename.c_str(), "r")) { fsa.Read(f); fclose(f); }
-        else { std::cerr << "\nUnable to open \"" << automaton_filename << "\"!" << std::endl; return 1; }
+        else { std::cerr << "\nUnable to open \"" << automaton_filename << "\"!" << std::endl; return finish(1); }
         std::cerr << "\n\tstates: " << fsa.GetNumberOfStates() << "\n\ttransitions: " << fsa.GetNumberOfTransitions()
                   << "\n\temissions: " << fsa.GetNumberOfEmissions() << "\n\tparameters: " << fsa.GetNumberOfParameters()
                   << "\n\tconstraints: " << fsa.GetNumberOfConstraints() << "\n\tfree parameters: " << fsa.GetNumberOfFreeParameters() << std::endl;
@@ -157,11 +208,14 @@ int main(int argc, const char* argv[])
                   << "\n\tunique paths: " << (learner->HasUniquePaths() ? "true" : "false")
                   << "\nAfter trimming:\n\tparameters: " << learner->GetNumberOfParameters()
                   << "\n\tconstraints: " << learner->GetNumberOfConstraints() << std::endl;
-        if (learner->GetNumberOfParameters() == 0) { std::cerr << "Empty automaton!" << std::endl; return 1; }
-        if (learner->GetNumberOfStrings() == 0) { std::cerr << "Automaton cannot generate any of the strings!" << std::endl; return 1; }
+        if (learner->GetNumberOfParameters() == 0) { std::cerr << "Empty automaton!" << std::endl; return finish(1); }
+        if (learner->GetNumberOfStrings() == 0) { std::cerr << "Automaton cannot generate any of the strings!" << std::endl; return finish(1); }
         learner->Finalize();
         std::cerr << "Initialize ... "; std::cerr.flush();
-        if (initx) {
+        if (initx && gpus > 1) {
+            if ((int)stdin_x.size() < learner->GetNumberOfParameters()) throw MyError("Cannot read initial x value!");
+            learner->Init(initflags, stdin_x.data());
+        } else if (initx) {
             std::vector<double> x;
             while (std::cin && (int)x.size() < learner->GetNumberOfParameters()) { x.emplace_back(); std::cin >> x.back(); }
             if (!std::cin) throw MyError("Cannot read initial x value!");
@@ -194,7 +248,7 @@ int main(int argc, const char* argv[])
             for (double x : results) std::cerr << ' ' << x;
             std::cerr << std::endl;
         }
-        if (!suppress) {
+        if (!suppress && rank == 0) {
             FILE* outf = output_filename.empty() ? stdout : fopen(output_filename.c_str(), "w");
             if (!outf) throw MyError("Unable to open output file \"" + output_filename + "\" for writing!");
             learner->RewriteWeights(fsa);
@@ -203,8 +257,9 @@ int main(int argc, const char* argv[])
             if (outf != stdout) fclose(outf);
         }
     } catch (std::exception& e) {
-        fprintf(stderr, "%s\n", e.what());
-        return 1;
+        if (rank == 0) fprintf(stderr, "%s\n", e.what());
+        else dprintf(err_fd, "[rank %d] %s\n", rank, e.what());
+        return finish(1);
     }
-    return 0;
+    return finish(0);
 }
