@@ -423,10 +423,10 @@ def test_config5_true_shape_parity():
 
 
 def test_full_size_config4_properties():
-    """BASELINE config 4 at full size (1M strings, ~80M tokens): too big for the oracle, so check
-    size-independent identities: every position emits exactly one symbol and takes exactly one
-    transition (+1 into the end state), run-to-run bitwise determinism, and a 20k-string sample
-    against the oracle."""
+    """BASELINE config 4 at full size (1M strings, ~80M tokens): size-independent identities (every position emits exactly
+    one symbol and takes exactly one transition, +1 into the end state), run-to-run bitwise determinism, a 20k-string
+    sample of log q, and -- at a random x -- log q of every string, the log-likelihood and the whole gradient against the
+    CPU forward-backward over the full corpus."""
     model = synth.make_model(256, 64, 8, 4, seed=1234)
     low = model.lowered()
     offs, toks, w = model.corpus(1000000, 32, 128, seed=1235)
@@ -450,7 +450,54 @@ def test_full_size_config4_properties():
     ltw, lew = low.edge_logweights(x, trimmed)
     _, olq, _ = O.dp_eval(low, ltw, lew, first=500000, count=20000, want_grad=False)
     assert np.allclose(logq[500000:520000], olq, rtol=1e-12)
+    # ... and the whole evaluation at a random x against the CPU forward-backward over ALL 1M strings (the oracle takes a
+    # few seconds on the host cores): log q of every string, the log-likelihood and every gradient component, 1e-9
+    x = np.random.RandomState(3).normal(-1.0, 0.3, size=n)
+    ll, logq, grad = dev.eval(x)
+    ltw, lew = low.edge_logweights(x, trimmed)
+    _, olq, oee = O.dp_eval(low, ltw, lew, nthreads=O.max_threads())
+    assert np.allclose(logq, olq, rtol=1e-11)
+    assert abs(ll - float(np.dot(p, olq))) <= 1e-11 * abs(ll)
+    ok, err = vec_tol_ok(grad, oracle_grad(low, trimmed, n, oee), 1e-9)
+    assert ok, err
     dev.close()
+
+
+def test_pool_overflow_at_scale():
+    """100 000 config-4 strings with FOUR pool slots per region instead of sixteen: every string with a region that
+    needs more goes to the warp-per-string kernel (the cliff of DESIGN.md section 5).  Results must not change; the
+    time of the mixed evaluation is printed next to the all-segmented one so that the cost of the cliff is on record."""
+    import time
+    model = synth.make_model(256, 64, 8, 4, seed=1234)
+    low = model.lowered()
+    offs, toks, w = model.corpus(100000, 32, 128, seed=55)
+    low.set_tokens(offs, toks, w / w.sum())
+    out = {}
+    for name, variant in (("16 slots", 0), ("4 slots", 4 << 16)):
+        dev, rec, pc, trimmed, n = build_device(low, accum_variant=variant)
+        info = dev.info()
+        assert info["kernel"] == 6 and rec.all()
+        x = np.random.RandomState(9).normal(-1.0, 0.3, size=n)
+        dev.eval(x, want_logq=False)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ll, _, grad = dev.eval(x, want_logq=False)
+        ms = (time.perf_counter() - t0) / 5 * 1e3
+        _, logq, _ = dev.eval(x)
+        out[name] = (ll, logq, grad, info["n_overflow_strings"], ms)
+        dev.close()
+    assert out["16 slots"][3] == 0 and out["4 slots"][3] > 100
+    print("\npool overflow at scale: %d of 100000 strings on the warp-per-string kernel, %.3f ms per evaluation against %.3f ms"
+          % (out["4 slots"][3], out["4 slots"][4], out["16 slots"][4]))
+    ltw, lew = low.edge_logweights(x, trimmed)
+    _, olq, oee = O.dp_eval(low, ltw, lew, nthreads=O.max_threads())
+    og = oracle_grad(low, trimmed, n, oee)
+    for name in out:
+        ll, logq, grad = out[name][:3]
+        assert np.allclose(logq, olq, rtol=1e-11), name
+        assert abs(ll - float(np.dot(low.p, olq))) <= 1e-11 * abs(ll), name
+        ok, err = vec_tol_ok(grad, og, 1e-9)
+        assert ok, (name, err)
 
 
 @pytest.mark.parametrize("kernel,variant", [(0, 0), (1, 0), (0, 4 << 16)])

@@ -970,229 +970,6 @@ __global__ void __launch_bounds__(1024, 1) k3_fwdbwd(const K3Params P)
 }
 
 // ------------------------------------------------------------------------------------------
-// K3W: the same dense candidate-vector recursion as K3, but one WARP per string: the candidates of a position are
-// dealt out to the lanes (candidate j on lane j % 32), alpha / beta~ live in a per-warp slice of shared memory,
-// and there is no block-wide barrier or reduction -- only __syncwarp and warp shuffles.  K3 keeps a whole CTA in
-// lock step on a chain of dependent table look-ups per position (5 us per position for config 5); here 32 warps
-// per SM walk 32 strings independently and hide each other's latency.  Lattice and per-position exponents go to a
-// per-warp slab in global memory.
-// ------------------------------------------------------------------------------------------
-struct K3WParams {
-    FastTablesD T;
-    EvalWeightsD W;
-    CorpusD C;
-    EvalOutD O;
-    double* lattice;           // [warps][max_len][nt]
-    int* lat_exp;              // [warps][max_len]
-    int max_len, nt;           // nt = candidates per position rounded up to a multiple of 32
-};
-
-template <int MODE>
-__global__ void __launch_bounds__(1024, 1) k3w_fwdbwd(const K3WParams P)
-{
-    extern __shared__ unsigned long long smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, nt = P.nt;
-    double* va = reinterpret_cast<double*>(smem) + (size_t)warp * 2 * nt;     // [2][nt] alpha or beta~ of this warp
-    const FastTablesD& T = P.T;
-    const int A = T.n_sym;
-    const long long gw = (long long)blockIdx.x * nwarps + warp, GW = (long long)gridDim.x * nwarps;
-    double* lat = P.lattice + (size_t)gw * P.max_len * nt;
-    int* lexp = P.lat_exp + (size_t)gw * P.max_len;
-    long long ll_fx = 0;
-    unsigned long long bad = 0;
-
-    for (long long it = gw; it < P.C.n_order; it += GW) {
-        const int sid = P.C.order[it];
-        const long long off = P.C.offs[sid];
-        const int len = (int)(P.C.offs[sid + 1] - off);
-        const double ps = P.C.p[sid];
-        const int32_t* tok = P.C.tokens + off;
-        __syncwarp();
-        if (len == 0) {
-            if (lane == 0) {
-                const double q = T.start_final_tid >= 0 ? P.W.tw[T.start_final_tid] : 0.0;
-                if (MODE == MODE_STRUCT) {
-                    P.O.path_count[sid] = q;
-                    if (q != 0.0) atomicAdd(P.O.red + 2 + T.start_final_tid, 1ull);
-                } else {
-                    const double lq = log(q);
-                    if (P.O.logq) P.O.logq[sid] = lq;
-                    if (q > 0.0 && isfinite(lq)) {
-                        ll_fx += __double2ll_rn(ps * lq * P.O.ll_scale);
-                        atomicAdd(P.O.red + 2 + T.start_final_tid, (unsigned long long)__double2ll_rn(ps * P.O.fx_scale));
-                    } else bad++;
-                }
-            }
-            continue;
-        }
-        // ---------------- forward ----------------
-        int cur = 0, E = 0, cprev = A;
-        bool dead = false;
-        for (int j = lane; j < nt; j += 32) va[j] = (j == 0) ? 1.0 : 0.0;       // START pseudo position: slot 0 = start state
-        __syncwarp();
-        uint32_t c0 = 0, ncand = 0;
-        for (int t = 0; t < len; ++t) {
-            const int c = tok[t];
-            if ((unsigned)c >= (unsigned)A) { dead = true; break; }
-            c0 = T.cand_off[c]; ncand = T.cand_off[c + 1] - c0;
-            const double* src = va + cur * nt;
-            double* dst = va + (cur ^ 1) * nt;
-            int e = -1;
-            for (uint32_t j = lane; j < (uint32_t)nt; j += 32) {
-                double alpha = 0.0;
-                if (j < ncand) {
-                    const uint32_t slot = c0 + j;
-                    const uint32_t row = T.frow[(size_t)T.slot_state[slot] * (A + 1) + cprev];
-                    const int cnt = row & ((1u << kRowCntBitsD) - 1);
-                    const uint32_t st = row >> kRowCntBitsD;
-                    double s = 0.0;
-                    for (int k = 0; k < cnt; ++k) {
-                        const uint32_t ent = T.fent[st + k];
-                        s = fma(P.W.tw[ent >> kSlotBitsD], src[ent & ((1u << kSlotBitsD) - 1)], s);
-                    }
-                    alpha = s * P.W.sw[slot];
-                }
-                dst[j] = alpha;
-                if (alpha != 0.0) e = max(e, biased_exp(alpha));
-            }
-            const int emax = __reduce_max_sync(FULL, e);
-            if (emax < 0) { dead = true; break; }
-            __syncwarp();
-            if ((t & (kRescaleEvery - 1)) == kRescaleEvery - 1 && (emax < 1023 - kRescaleBand || emax > 1023 + kRescaleBand)) {
-                const int shift = 1023 - emax;
-                for (int j = lane; j < nt; j += 32) dst[j] = scalbn(dst[j], shift);
-                E -= shift;
-                __syncwarp();
-            }
-            double* lt = lat + (size_t)t * nt;
-            for (int j = lane; j < nt; j += 32) lt[j] = dst[j];
-            if (lane == 0) lexp[t] = E;
-            cur ^= 1;
-            cprev = c;
-        }
-        double qh = 0.0;
-        if (!dead) {
-            const double* a = va + cur * nt;
-            double part = 0.0;
-            for (uint32_t j = lane; j < ncand; j += 32) part = fma(a[j], P.W.fw[c0 + j], part);
-            qh = warp_sum(part);
-        }
-        if (dead || !(qh > 0.0) || !isfinite(qh)) {
-            if (lane == 0) {
-                if (MODE == MODE_STRUCT) P.O.path_count[sid] = 0.0;
-                else { if (P.O.logq) P.O.logq[sid] = -INFINITY; bad++; }
-            }
-            continue;
-        }
-        const int EQ = E;
-        if (lane == 0) {
-            if (MODE == MODE_STRUCT) P.O.path_count[sid] = scalbn(qh, EQ);
-            else {
-                const double lq = log(qh) + (double)EQ * 0.69314718055994530942;
-                if (P.O.logq) P.O.logq[sid] = lq;
-                ll_fx += __double2ll_rn(ps * lq * P.O.ll_scale);
-            }
-        }
-        // ---------------- backward ----------------
-        const double invq = 1.0 / qh;
-        int F = 0, cnext = tok[len - 1];
-        {   // last position: posterior of the final transitions, beta~ = a(v,end) * b(v,c)
-            const double* a = va + cur * nt;
-            double* b = va + (cur ^ 1) * nt;
-            for (uint32_t j = lane; j < (uint32_t)nt; j += 32) {
-                double bt = 0.0;
-                if (j < ncand) {
-                    const uint32_t slot = c0 + j;
-                    const double al = a[j], fin = al != 0.0 ? P.W.fw[slot] : 0.0;
-                    if (al != 0.0 && fin != 0.0) {
-                        const uint32_t fst = T.slot_state[slot];
-                        if (MODE == MODE_STRUCT) atomicAdd(P.O.acc_global + T.n_arcs + fst, 1ull);
-                        else atomicAdd(P.O.acc_global + T.n_arcs + fst, (unsigned long long)__double2ll_rn(al * fin * invq * ps * P.O.fx_scale));
-                        bt = fin * P.W.sw[slot];
-                    }
-                }
-                b[j] = bt;
-            }
-            cur ^= 1;
-            __syncwarp();
-        }
-        for (int t = len - 2; t >= 0; --t) {
-            const int c = tok[t];
-            const uint32_t cc0 = T.cand_off[c], nc = T.cand_off[c + 1] - cc0;
-            const double* al_t = lat + (size_t)t * nt;
-            const int d = lexp[t] + F - EQ;
-            double sc = invq * ps * P.O.fx_scale;
-            if (d != 0) sc = scalbn(sc, d);
-            const double* src = va + cur * nt;
-            double* dst = va + (cur ^ 1) * nt;
-            int e = -1;
-            for (uint32_t j = lane; j < (uint32_t)nt; j += 32) {
-                double bt = 0.0;
-                const double al = j < nc ? al_t[j] : 0.0;
-                if (al != 0.0) {
-                    const uint32_t slot = cc0 + j;
-                    const uint32_t row = T.brow[(size_t)T.slot_state[slot] * A + cnext];
-                    const int cnt = row & ((1u << kRowCntBitsD) - 1);
-                    const uint32_t st = row >> kRowCntBitsD;
-                    double b = 0.0;
-                    for (int k = 0; k < cnt; ++k) {
-                        const uint32_t ent = T.bent[st + k];
-                        const double term = P.W.tw[ent >> kSlotBitsD] * src[ent & ((1u << kSlotBitsD) - 1)];
-                        b += term;
-                        if (term != 0.0) {
-                            if (MODE == MODE_STRUCT) atomicAdd(P.O.acc_global + st + k, 1ull);
-                            else {
-                                const long long v = __double2ll_rn(al * term * sc);
-                                if (v) atomicAdd(P.O.acc_global + st + k, (unsigned long long)v);
-                            }
-                        }
-                    }
-                    bt = b * P.W.sw[slot];
-                }
-                dst[j] = bt;
-                if (bt != 0.0) e = max(e, biased_exp(bt));
-            }
-            __syncwarp();
-            if ((t & (kRescaleEvery - 1)) == 0) {
-                const int emax = __reduce_max_sync(FULL, e);
-                if (emax >= 0 && (emax < 1023 - kRescaleBand || emax > 1023 + kRescaleBand)) {
-                    const int shift = 1023 - emax;
-                    for (int j = lane; j < nt; j += 32) dst[j] = scalbn(dst[j], shift);
-                    F -= shift;
-                    __syncwarp();
-                }
-            }
-            cur ^= 1;
-            cnext = c;
-        }
-        {   // arcs out of the start state
-            const uint32_t row = T.brow[(size_t)T.start_state * A + cnext];
-            const int cnt = row & ((1u << kRowCntBitsD) - 1);
-            const uint32_t st = row >> kRowCntBitsD;
-            const int d = F - EQ;
-            double sc = invq * ps * P.O.fx_scale;
-            if (d != 0) sc = scalbn(sc, d);
-            const double* src = va + cur * nt;
-            for (int k = lane; k < cnt; k += 32) {
-                const uint32_t ent = T.bent[st + k];
-                const double term = P.W.tw[ent >> kSlotBitsD] * src[ent & ((1u << kSlotBitsD) - 1)];
-                if (term != 0.0) {
-                    if (MODE == MODE_STRUCT) atomicAdd(P.O.acc_global + st + k, 1ull);
-                    else {
-                        const long long v = __double2ll_rn(term * sc);
-                        if (v) atomicAdd(P.O.acc_global + st + k, (unsigned long long)v);
-                    }
-                }
-            }
-        }
-    }
-    for (int o = 16; o; o >>= 1) { ll_fx += __shfl_xor_sync(FULL, ll_fx, o); bad += __shfl_xor_sync(FULL, bad, o); }
-    if (lane == 0) {
-        if (ll_fx) atomicAdd(P.O.red, (unsigned long long)ll_fx);
-        if (bad) atomicAdd(P.O.red + 1, bad);
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 // Generic path: emissions of any length (0, 1, 2, ... tokens), one thread per string, dense
 // log-domain lattice (len+1) x n_states in global scratch.  Correct for every automaton the

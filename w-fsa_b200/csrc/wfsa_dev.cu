@@ -118,7 +118,7 @@ struct wfsa_dev {
     int grid = 0, block = 0, stack_cap = 0, n_acc_smem = 0;      // warp-per-string (K2) launch
     size_t smem_bytes = 0, glstack_words = 0, table_bytes = 0;
     int k3_grid = 0, k3_block = 0; size_t k3_smem = 0;
-    bool k3w = false; int k3w_grid = 0, k3w_block = 0, k3w_nt = 0; size_t k3w_smem = 0;   // warp-per-string variant of K3            // CTA-per-string (K3) launch
+            // CTA-per-string (K3) launch
     int kt_grid = 0, kt_block = 0, kt_K = 0; size_t kt_smem = 0, kt_lat_words = 0;   // thread-per-string (KT)
     int secondary = 0;                                            // kernel that takes KT's / KL's overflow strings
     int skernel = 0;                                              // kernel of the structural pass
@@ -343,26 +343,6 @@ static int setup_k3(wfsa_dev* h)
     h->k3_block = nt;
     h->k3_grid = h->sm_count * std::max(1, std::min(4, 1024 / nt));
     h->k3_smem = (size_t)(2 * nt + 32) * 8 + 40 * 4;
-    // K3W (WFSA_K3_WARP=1): one warp per string, 2*nt doubles of shared memory per warp, a lattice slab per warp in global memory
-    h->k3w = getenv("WFSA_K3_WARP") != nullptr;     // off by default: measured no faster than the CTA kernel
-    if (h->k3w) {
-        const size_t per_warp = (size_t)2 * nt * 8;
-        int warps = (int)std::min<size_t>(32, (size_t)(220 * 1024) / per_warp);
-        if (warps < 1) h->k3w = false;
-        else {
-            h->k3w_nt = nt; h->k3w_block = warps * 32; h->k3w_smem = per_warp * warps;
-            const size_t slab = (size_t)std::max(h->max_len, 1) * nt * 8;                 // bytes per warp
-            const size_t budget = (size_t)4 << 30;
-            int grid = h->sm_count;
-            while (grid > 1 && (size_t)grid * warps * slab > budget) grid = (grid + 1) / 2;
-            h->k3w_grid = grid;
-            CK(h->d_k3lat.alloc((size_t)grid * warps * std::max(h->max_len, 1) * nt));
-            CK(h->d_k3exp.alloc((size_t)grid * warps * std::max(h->max_len, 1)));
-            cudaFuncSetAttribute(k3w_fwdbwd<MODE_EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            cudaFuncSetAttribute(k3w_fwdbwd<MODE_STRUCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            return WFSA_OK;
-        }
-    }
     CK(h->d_k3lat.alloc((size_t)h->k3_grid * std::max(h->max_len, 1) * nt));
     CK(h->d_k3exp.alloc((size_t)h->k3_grid * std::max(h->max_len, 1)));
     return WFSA_OK;
@@ -859,15 +839,6 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
         T.frow = h->d_frow.p; T.fent = h->d_fent.p; T.brow = h->d_brow.p; T.bent = h->d_bent.p;
         T.n_sym = F.n_sym; T.n_states = F.n_states; T.n_arcs = L.n_arcs; T.n_slots = L.n_slots;
         T.start_state = F.start; T.start_final_tid = L.start_final_tid;
-        if (h->k3w) {
-            K3WParams Q{};
-            Q.T = T; Q.W = EvalWeightsD{h->d_tw.p, h->d_sw.p, h->d_fw.p}; Q.C = C; Q.O = O;
-            Q.lattice = h->d_k3lat.p; Q.lat_exp = h->d_k3exp.p; Q.max_len = std::max(h->max_len, 1); Q.nt = h->k3w_nt;
-            if (mode == MODE_STRUCT) k3w_fwdbwd<MODE_STRUCT><<<h->k3w_grid, h->k3w_block, h->k3w_smem, st>>>(Q);
-            else k3w_fwdbwd<MODE_EVAL><<<h->k3w_grid, h->k3w_block, h->k3w_smem, st>>>(Q);
-            h->launches++;
-            return;
-        }
         P.T = T; P.W = EvalWeightsD{h->d_tw.p, h->d_sw.p, h->d_fw.p}; P.C = C; P.O = O;
         P.lattice = h->d_k3lat.p; P.lat_exp = h->d_k3exp.p; P.max_len = std::max(h->max_len, 1);
         if (mode == MODE_STRUCT) k3_fwdbwd<MODE_STRUCT><<<h->k3_grid, h->k3_block, h->k3_smem, st>>>(P);
@@ -2312,12 +2283,12 @@ extern "C" int wfsa_dev_get_info(wfsa_dev* h, wfsa_dev_info* info)
     info->n_arcs = h->fast.ok ? h->fast.n_arcs : 0; info->n_slots = h->fast.ok ? h->fast.n_slots : 0;
     info->max_candidates = h->fast.ok ? h->fast.max_cand : 0;
     info->sm_count = h->sm_count;
-    info->grid = h->kernel >= 5 ? h->kl_grid : (h->kernel == 4 ? h->kt_grid : (h->kernel == 2 ? (h->k3w ? h->k3w_grid : h->k3_grid) : h->grid));
-    info->block = h->kernel >= 5 ? h->kl_block : (h->kernel == 4 ? h->kt_block : (h->kernel == 2 ? (h->k3w ? h->k3w_block : h->k3_block) : (h->kernel == 3 ? 128 : h->block)));
+    info->grid = h->kernel >= 5 ? h->kl_grid : (h->kernel == 4 ? h->kt_grid : (h->kernel == 2 ? h->k3_grid : h->grid));
+    info->block = h->kernel >= 5 ? h->kl_block : (h->kernel == 4 ? h->kt_block : (h->kernel == 2 ? h->k3_block : (h->kernel == 3 ? 128 : h->block)));
     if (h->kernel == 7) { info->grid = 0; info->block = h->k7_V; }
     info->n_strings = h->n_strings; info->n_tokens = h->n_tokens;
     info->n_active_tokens = h->n_active_tokens;
-    info->smem_bytes = (int64_t)(h->kernel >= 5 ? h->kl_smem : (h->kernel == 4 ? h->kt_smem : (h->kernel == 2 ? (h->k3w ? h->k3w_smem : h->k3_smem) : h->smem_bytes)));
+    info->smem_bytes = (int64_t)(h->kernel >= 5 ? h->kl_smem : (h->kernel == 4 ? h->kt_smem : (h->kernel == 2 ? h->k3_smem : h->smem_bytes)));
     if (h->kernel == 7) { info->smem_bytes = (int64_t)kK7Chunk * h->k7_V * 8; info->seg_host_ms = h->k7_host_ms; info->lattice_words = (int64_t)h->k7_rows * h->k7_V * 2; info->pool_slots = (int32_t)h->k7.size(); }
     if (h->kernel == 5) {
         info->n_arcs = h->larcs.n_arcs;
