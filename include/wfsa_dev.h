@@ -130,7 +130,7 @@ typedef struct {
     const double*  p;            /* [n_blocks] p_s of the block's string                         */
 } wfsa_path_blocks;
 int wfsa_dev_set_path_blocks(wfsa_dev* h, const wfsa_path_blocks* blocks);
-int wfsa_dev_hessian(wfsa_dev* h, const double* x, double* Hf /* n*n */, double* rmin /* or NULL */);
+int wfsa_dev_hessian(wfsa_dev* h, const double* x, double* Hf /* n*n, or NULL: only rmin is computed */, double* rmin /* or NULL */);
 
 /* Multi-GPU: one handle per process/GPU; results of eval/structure/hessian are all-reduced as exact integer
  * sums, so every rank holds the same bits (the evaluation through an all-reduce over NVLink peer memory fused

@@ -1277,6 +1277,7 @@ __global__ void __launch_bounds__(256) k5_hessian(const HessParams P)
         if (lane == 0 && P.rmin) atomicMin(reinterpret_cast<unsigned long long*>(P.rmin), (unsigned long long)__double_as_longlong(rm));
         if (lane == 0 && P.blk_slot) P.slot_lrmin[P.blk_slot[b]] = log(rm);
         __syncwarp();
+        if (!P.H_fx) continue;                                 // rmin only (QuasiNewtonLearner's diagnostic column)
         // 8x8 output tiles; DMMA fragment layout (m8n8k4): A[row=lane/4][k=lane%4],
         // B[k=lane%4][col=lane/4], C[row=lane/4][col=2*(lane%4)+{0,1}]
         const int gi = lane >> 2, ti = lane & 3;

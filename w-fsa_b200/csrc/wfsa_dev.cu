@@ -1863,7 +1863,7 @@ static int ensure_ks(wfsa_dev* h);
 
 extern "C" int wfsa_dev_hessian(wfsa_dev* h, const double* x, double* Hf, double* rmin)
 {
-    if (!h || !Hf) return set_err(h, WFSA_ERR_INVALID, "hessian: bad arguments");
+    if (!h || (!Hf && !rmin)) return set_err(h, WFSA_ERR_INVALID, "hessian: bad arguments");
     if (h->n < 0) return set_err(h, WFSA_ERR_STATE, "hessian before set_param_map");
     if (h->hb_blocks < 0) {
         if (h->kernel != 6) return set_err(h, WFSA_ERR_STATE, "hessian before set_path_blocks");
@@ -1873,8 +1873,8 @@ extern "C" int wfsa_dev_hessian(wfsa_dev* h, const double* x, double* Hf, double
     }
     int rc = wfsa_dev_upload_x(h, x);
     if (rc != WFSA_OK) return rc;
-    const size_t nn = (size_t)h->n * h->n;
-    CK(cudaMemsetAsync(h->d_Hfx.p, 0, std::max<size_t>(nn, 1) * 8, h->stream));
+    const size_t nn = Hf ? (size_t)h->n * h->n : 0;          // Hf == NULL: only rmin is wanted, nothing of H is touched
+    if (Hf) CK(cudaMemsetAsync(h->d_Hfx.p, 0, std::max<size_t>(nn, 1) * 8, h->stream));
     const double inf = INFINITY;
     CK(cudaMemcpyAsync(h->d_rmin.p, &inf, 8, cudaMemcpyHostToDevice, h->stream));
     const double fx = std::ldexp(1.0, h->hb_fx_log2);
@@ -1882,15 +1882,14 @@ extern "C" int wfsa_dev_hessian(wfsa_dev* h, const double* x, double* Hf, double
         HessParams P{};
         P.n_blocks = h->hb_blocks; P.path_off = h->d_hb_path_off.p; P.col_off = h->d_hb_col_off.p; P.cols = h->d_hb_cols.p;
         P.val_off = h->d_hb_val_off.p; P.counts = h->d_hb_counts.p; P.p = h->d_hb_p.p; P.x = h->d_x.p; P.r_scratch = h->d_hb_r.p;
-        P.H_fx = h->d_Hfx.p; P.rmin = h->d_rmin.p; P.n = h->n; P.fx_scale = fx;
+        P.H_fx = Hf ? h->d_Hfx.p : nullptr; P.rmin = h->d_rmin.p; P.n = h->n; P.fx_scale = fx;
         P.blk_slot = h->hb_from_types ? h->d_hb_slot.p : nullptr; P.slot_lrmin = h->hb_from_types ? h->d_type_lrmin.p : nullptr;
         const int warps_per_block = 8;
         const int64_t blocks = std::min<int64_t>((h->hb_blocks + warps_per_block - 1) / warps_per_block, (int64_t)h->sm_count * 8);
         k5_hessian<<<(int)std::max<int64_t>(blocks, 1), warps_per_block * 32, 0, h->stream>>>(P);
         h->launches++;
     }
-    rc = nccl_allreduce(h, h->d_Hfx.p, nn, ncclUint64, ncclSum);
-    if (rc != WFSA_OK) return rc;
+    if (Hf) { rc = nccl_allreduce(h, h->d_Hfx.p, nn, ncclUint64, ncclSum); if (rc != WFSA_OK) return rc; }
     if (nn) {
         k_fx_to_double<<<(unsigned)((nn + 255) / 256), 256, 0, h->stream>>>(nn, h->d_Hfx.p, 1.0 / fx, h->d_H.p);
         h->launches++;

@@ -396,6 +396,7 @@ void QuasiNewtonLearner::OptimizationStep(double eta, bool)     // src/QuasiNewt
     ComputeG();
     ComputeGrad();
     ComputeObjective();
+    rmin = ComputeRmin();                                  // relative_path_probs of this evaluation, src/QuasiNewtonLearner.cpp:80-84
     aux.assign(n, 0.0);
     for (int i = 0; i < n; ++i) { aux[i] = expx[i] * lambda[Ccol[i]]; rhs[i] = grad[i] + aux[i]; }
     grad_error = 0.0;
@@ -418,14 +419,29 @@ std::string QuasiNewtonLearner::GetOptimizationHeader() const
 
 std::vector<double> QuasiNewtonLearner::GetOptimizationInfo()
 {
-    // rmin / argmin (smallest path posterior) are path-level diagnostics with no DP analogue:
-    // reported as 0, as the reference does for unique paths (src/QuasiNewtonLearner.cpp:68-86)
-    return {GetKLDistance(), grad_error, g_min, g_max, lambda_min, 0.0, 0.0};
+    // rmin = smallest path posterior (src/QuasiNewtonLearner.cpp:80-84); its argmin is a path index of the reference's
+    // enumeration order, which a DP backend does not have: reported as 0
+    return {GetKLDistance(), grad_error, g_min, g_max, lambda_min, rmin, 0.0};
 }
 
 bool QuasiNewtonLearner::HaltCondition(double tol)
 {
     return grad_error <= tol && std::fabs(g_min) <= tol && std::fabs(g_max) <= tol;
+}
+
+// smallest path posterior over all strings at the current x (the rmin column of both optimisers): the H_f entry point of the
+// backend without its matrix
+double Learner::ComputeRmin()
+{
+    if (HasUniquePaths()) return 0.0;
+    double rm = 0.0;
+    int rc = wfsa_dev_hessian(dev, _x.data(), nullptr, &rm);
+    if (rc == WFSA_ERR_STATE && !have_blocks) {
+        BuildPathBlocks();
+        rc = wfsa_dev_hessian(dev, _x.data(), nullptr, &rm);
+    }
+    check(rc, "wfsa_dev_hessian");
+    return std::isfinite(rm) ? rm : 1.0;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -80,6 +80,7 @@ public:
     const LoweredFsa& Lowered() const { return lowered; }
     // dense H_f (n x n, row major) at the current x; builds the path blocks on first use
     void ComputeHfDense(std::vector<double>& Hf, double* rmin = nullptr);
+    double ComputeRmin();
 
 protected:
     virtual void FinalizeCallback() {}
@@ -134,7 +135,7 @@ protected:
     void ComputeLambdaNext(std::vector<double>& result);
 private:
     std::vector<double> grad, expx, lambda, g, rhs, aux;
-    double grad_error = 0, lambda_min = 0, g_min = 0, g_max = 0;
+    double grad_error = 0, lambda_min = 0, g_min = 0, g_max = 0, rmin = 0;
     bool exponential_lambda = false;
 };
 
