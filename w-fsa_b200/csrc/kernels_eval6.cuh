@@ -371,8 +371,10 @@ __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
                     __syncwarp();
                     if (P.debug && lane == 0) atomicMax(P.stamps + 7, e6_timer() - tg0);
                 }
-                // (one instance: generic loads serve the staging area and HBM alike)
-                if (!(P.debug & 4)) kr_big_t<ACC_GLOBAL, true>(R, aw, pool, NT, g, lane, staged ? sw : P.words + off + lane, nw, staged ? sxs : xs, acc_g, ll, &s_trash[tid]);
+                if (!(P.debug & 4)) {
+                    if (staged) kr_big_t<ACC_GLOBAL, true>(R, aw, pool, NT, g, lane, sw, nw, sxs, acc_g, ll, &s_trash[tid]);
+                    else kr_big_t<ACC_GLOBAL, false>(R, aw, pool, NT, g, lane, P.words + off + lane, nw, xs, acc_g, ll, &s_trash[tid]);
+                }
                 __syncwarp();
             }
         }

@@ -143,7 +143,24 @@ __device__ __forceinline__ void kr_big_t(const KRParams& P, const double* aw, do
     // rounded inside the backward chain and parked in the x stack; a third loop without dependencies issues the REDs.
     // Measured before (45 instructions with four branches per step): ~300 cycles per step, the 96-row group of a
     // 125 k-string shard alone took 31 us of a 37 us region phase.
-    auto ldw = [&](int i) { return STAGED ? wp[(size_t)i * 32] : __ldcs(wp + (size_t)i * 32); };
+    // STAGED: words and x stack are in shared memory; address them as such (a generic store to the shared window sits in the
+    // same in-order LSU queue as the chain's LDS/STS and takes longer to resolve)
+    const unsigned int wp_sa = STAGED ? (unsigned int)__cvta_generic_to_shared(wp) : 0u;
+    const unsigned int xs_sa = STAGED ? (unsigned int)__cvta_generic_to_shared(xs) : 0u;
+    auto ldw = [&](int i) -> uint32_t {
+        if (STAGED) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(wp_sa + (unsigned int)i * 128u)); return v; }
+        return __ldcs(wp + (size_t)i * 32);
+    };
+    auto xs_ld = [&](int i) -> long long {
+        if (STAGED) { long long v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(xs_sa + (unsigned int)i * 256u)); return v; }
+        return reinterpret_cast<const long long*>(xs)[(size_t)i * 32];
+    };
+    auto xs_st = [&](int i, long long v) {
+        // (no memory clobber: the x stack is touched by these volatile statements only, which keep their order among themselves;
+        //  a clobber would pin the chain's pool accesses around every store)
+        if (STAGED) asm volatile("st.shared.b64 [%0], %1;" :: "r"(xs_sa + (unsigned int)i * 256u), "l"(v));
+        else reinterpret_cast<long long*>(xs)[(size_t)i * 32] = v;
+    };
     const double W = P.typeW[g * 32 + lane];
     pool[0] = 1.0;
     int E = 0, EQ = 0;
@@ -155,25 +172,34 @@ __device__ __forceinline__ void kr_big_t(const KRParams& P, const double* aw, do
         for (int j = 0; j < 8; ++j) w[j] = ldw(i0 + j);
         const bool has_chk = (i0 & 8) != 0;                   // word 7 of every second batch is a CHECK word (same index in all lanes)
         if (has_chk) w[7] = 0u;
+        // decode first (addresses and weights of the eight steps are independent of the chain), then the chain itself:
+        // per step  LDS node -> DMUL -> DADD -> select -> STS  and nothing else
+        const double* ps[8]; double* pd[8]; double wv[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const uint32_t wj = w[j];
             const bool edge = (wj & kLEdge) != 0;
-            const bool fin = !edge && (wj & kLFin) != 0;
             const int src = edge ? (wj >> 19) & 15 : (wj & 15), arc = edge ? (int)(wj & 0x7fff) : 0;
-            double* pd = edge ? pool + ((wj >> 23) & 15) * NT : trash;
-            const double a = pool[src * NT];                  // (FIN: the value of the exit node)
-            const double xv = a * aw[arc];
-            const double sum = *pd + xv;
-            *pd = (wj & kLFirstIn) ? xv : sum;
-            xs[(size_t)(i0 + j) * 32] = xv;
+            ps[j] = pool + src * NT;                          // (FIN: the exit node)
+            pd[j] = edge ? pool + ((wj >> 23) & 15) * NT : trash;
+            wv[j] = aw[arc];
             any |= edge;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t wj = w[j];
+            const bool fin = (wj & (kLEdge | kLFin)) == kLFin;
+            const double a = *ps[j];
+            const double xv = a * wv[j];
+            const double sum = *pd[j] + xv;
+            *pd[j] = (wj & kLFirstIn) ? xv : sum;
+            xs_st(i0 + j, __double_as_longlong(xv));
             qh = fin ? a : qh;
             EQ = fin ? E : EQ;
         }
         if (has_chk) {
             const uint32_t m0 = ldw(i0 + 7) & 0xffffu;
-            reinterpret_cast<long long*>(xs)[(size_t)(i0 + 7) * 32] = E;
+            xs_st(i0 + 7, (long long)E);
             if (m0) {
                 int emax = 0;
                 for (uint32_t m = m0; m; m &= m - 1) emax = max(emax, pool_exp(pool + (__ffs(m) - 1) * NT));
@@ -198,7 +224,7 @@ __device__ __forceinline__ void kr_big_t(const KRParams& P, const double* aw, do
         uint32_t w[8];
         double xv[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { w[j] = ldw(i0 + j); xv[j] = xs[(size_t)(i0 + j) * 32]; }
+        for (int j = 0; j < 8; ++j) { w[j] = ldw(i0 + j); xv[j] = __longlong_as_double(xs_ld(i0 + j)); }
         const bool has_chk = (i0 & 8) != 0;
         if (has_chk) {
             const uint32_t m0 = w[7] & 0xffffu;
@@ -215,21 +241,27 @@ __device__ __forceinline__ void kr_big_t(const KRParams& P, const double* aw, do
             }
             w[7] = 0u;
         }
+        const double* pdst[8]; double* psrc[8]; double wv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t wj = w[j];
+            const bool edge = (wj & kLEdge) != 0;
+            const int slot = edge ? (wj >> 19) & 15 : (wj & 15), arc = edge ? (int)(wj & 0x7fff) : 0;   // (FIN: the exit node, beta = 1)
+            pdst[j] = pool + ((wj >> 23) & 15) * NT;
+            psrc[j] = (wj & (kLEdge | kLFin)) ? pool + slot * NT : trash;
+            wv[j] = aw[arc];
+        }
 #pragma unroll
         for (int j = 7; j >= 0; --j) {
             const uint32_t wj = w[j];
             const bool edge = (wj & kLEdge) != 0;
-            const bool fin = !edge && (wj & kLFin) != 0;
-            const int dst = (wj >> 23) & 15, arc = edge ? (int)(wj & 0x7fff) : 0;
-            const int slot = edge ? (wj >> 19) & 15 : (wj & 15);                                       // (FIN: the exit node, beta = 1)
-            double* const pslot = pool + slot * NT;
-            double* psrc = (wj & (kLEdge | kLFin)) ? pslot : trash;
-            const double bd = pool[dst * NT];
-            const double c = aw[arc] * bd;
-            const double sum = *psrc + c;
-            *psrc = fin ? 1.0 : ((wj & kLLastOut) ? c : sum);
+            const bool fin = (wj & (kLEdge | kLFin)) == kLFin;
+            const double bd = *pdst[j];
+            const double c = wv[j] * bd;
+            const double sum = *psrc[j] + c;
+            *psrc[j] = fin ? 1.0 : ((wj & kLLastOut) ? c : sum);
             const long long v = __double2ll_rn(xv[j] * bd * sc);
-            reinterpret_cast<long long*>(xs)[(size_t)(i0 + j) * 32] = (edge && ok) ? v : 0ll;
+            xs_st(i0 + j, (edge && ok) ? v : 0ll);
         }
     }
     if (ACC == ACC_NONE) return;
@@ -237,7 +269,7 @@ __device__ __forceinline__ void kr_big_t(const KRParams& P, const double* aw, do
         uint32_t w[8];
         long long v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { w[j] = ldw(i0 + j); v[j] = reinterpret_cast<const long long*>(xs)[(size_t)(i0 + j) * 32]; }
+        for (int j = 0; j < 8; ++j) { w[j] = ldw(i0 + j); v[j] = xs_ld(i0 + j); }
 #pragma unroll
         for (int j = 0; j < 8; ++j) if (v[j]) red_add64(acc_g + (w[j] & 0x7fff), (unsigned long long)v[j]);
     }
