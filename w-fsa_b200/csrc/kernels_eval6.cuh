@@ -344,6 +344,7 @@ __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
         big += (long long)gridDim.x * (NT / 32);
         if (big >= P.n_big && lane == 0) gn = fetch();
         int rows; long long off;
+        if ((P.debug & 64) && g >= P.n_big) { g = big < P.n_big ? big : __shfl_sync(FULL, gn, 0); continue; }   // profiling: big groups only
         if (g < P.n_big) { rows = P.grows[g]; off = P.goff[g]; }
         else {
             int ci = 0;                                        // last class with first <= g
