@@ -131,9 +131,16 @@ def run_reference(args, rank, world):
                 subprocess.run([ref_bin, "-a", fa, "-c", fc, "-opt", "QuasiNewton", "-i", "7", "-e", str(epochs), "-tol", "0", "-s"],
                                check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
                 return time.perf_counter() - t
-            t0 = run(0)                       # load + path enumeration (Learner::BuildFrom), one-time
-            t1 = run(warm + steps)
-        per_step = max(t1 - t0, 1e-9) / (warm + steps)
+            # a step is timed as the difference of two whole runs, so the run with the steps must be long against the
+            # jitter of the 8 s one-time part: at least 20 epochs, the one-time part as the smaller of two runs, and four
+            # times the epochs if the difference still drowns
+            epochs = max(warm + steps, 20)
+            t0 = min(run(0), run(0))          # load + path enumeration (Learner::BuildFrom), one-time
+            t1 = run(epochs)
+            if t1 - t0 < 0.05 * t0:
+                epochs *= 4
+                t1 = run(epochs)
+        per_step = max(t1 - t0, 1e-6) / epochs
         tokens = int(offs[-1])
         kind, cores = "reference", 1
         sample = "%d strings (%d symbols) of config 4; one-time path enumeration %.1f s excluded" % (n, tokens, t0)

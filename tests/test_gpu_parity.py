@@ -465,6 +465,30 @@ def test_full_size_config4_properties():
     dev.close()
 
 
+@pytest.mark.parametrize("n_states,expect_segmented", [(512, True), (1024, False), (2048, False)])
+def test_automata_around_the_arc_limits(n_states, expect_segmented):
+    """The cliffs of DESIGN.md section 5: the segmented path needs the arc weights in shared memory and 15-bit arc ids.
+    512 states (16.9 k combined arcs, 135 KB of weights) still take it; 1024 and 2048 states (33.8 k / 67.6 k arcs) leave
+    it for whatever the library picks instead.  Whatever runs, the results are the oracle's."""
+    model = synth.make_model(n_states, 64, 8, 4, seed=77)
+    low = model.lowered()
+    offs, toks, w = model.corpus(20000, 32, 128, seed=78)
+    low.set_tokens(offs, toks, w / w.sum())
+    dev, rec, pc, trimmed, n = build_device(low)
+    info = dev.info()
+    assert rec.all() and (info["kernel"] == 6) == expect_segmented, info["kernel"]
+    x = np.random.RandomState(4).normal(-1.0, 0.3, size=n)
+    ll, logq, grad = dev.eval(x)
+    ltw, lew = low.edge_logweights(x, trimmed)
+    _, olq, oee = O.dp_eval(low, ltw, lew, nthreads=O.max_threads())
+    assert np.allclose(logq, olq, rtol=1e-11)
+    assert abs(ll - float(np.dot(low.p, olq))) <= 1e-11 * abs(ll)
+    ok, err = vec_tol_ok(grad, oracle_grad(low, trimmed, n, oee), 1e-9)
+    assert ok, (info["kernel"], err)
+    print("\n%d states, %d combined arcs: kernel %d" % (n_states, info["n_arcs"], info["kernel"]))
+    dev.close()
+
+
 def test_pool_overflow_at_scale():
     """100 000 config-4 strings with FOUR pool slots per region instead of sixteen: every string with a region that
     needs more goes to the warp-per-string kernel (the cliff of DESIGN.md section 5).  Results must not change; the

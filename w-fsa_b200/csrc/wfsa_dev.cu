@@ -435,7 +435,7 @@ static int setup_kl(wfsa_dev* h)
     if (want_nt == 0 && h->kernel == 6) want_nt = 512;       // measured: 16 warps leave the L1 to the register spills
     if (!kl_possible(h, K, want_nt, nt, smem))
         return set_err(h, WFSA_ERR_LIMIT, "compiled-lattice kernel: the arc weights do not fit shared memory");
-    if (h->kernel == 6 && want_nt == 512) {                 // k_eval6 is compiled for 512, 256 and 128 threads
+    if (h->kernel == 6 && (want_nt == 512 || nt > 512)) {   // k_eval6 is compiled for 512, 256 and 128 threads, kr_regions for up to 512
         nt = nt >= 512 ? 512 : (nt >= 256 ? 256 : 128);
         smem = ((size_t)h->larcs.n_arcs + 1) * 8 + (size_t)nt * K * 8;
     }
@@ -472,11 +472,8 @@ static int setup_kl(wfsa_dev* h)
         h->ks_block = kKsWarps * 32;
         h->ks_ctas = h->ks_smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
         h->ks_grid = h->sm_count * h->ks_ctas;
-        cudaFuncSetAttribute(kr_regions<ACC_GLOBAL, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192 - 1024);
-        cudaFuncSetAttribute(kr_regions<ACC_GLOBAL, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192 - 1024);
         cudaFuncSetAttribute(kr_regions<ACC_GLOBAL, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192 - 1024);
-        cudaFuncSetAttribute(kr_regions<ACC_SMEM_CAS, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192 - 1024);
-        cudaFuncSetAttribute(kr_regions<ACC_NONE, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192 - 1024);
+        cudaFuncSetAttribute(kr_regions<ACC_NONE, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192 - 1024);
         cudaFuncSetAttribute(ks_strings, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ks_smem);   // it also has static shared memory
     }
     cudaFuncSetAttribute(kl_fwdbwd<ACC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
