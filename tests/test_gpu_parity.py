@@ -151,6 +151,44 @@ def test_evaluation_result_line():
     s.close()
 
 
+def _eval_runs():
+    out = []
+    cases = {c["name"]: c for c in load_cases("fixtures") + load_cases("random")}
+    for r in load_cases("eval"):
+        if r["returncode"] == 0 and r["name"] in cases and r["optimizer"] == "Hessian":      # (QuasiNewton prints an empty Result line)
+            out.append(pytest.param(cases[r["name"]], r, id="%s-%s-i%d" % (r["name"], r["optimizer"], r["flags"])))
+    return out
+
+
+@pytest.mark.parametrize("case,run", _eval_runs())
+def test_evaluation_result_line_all_cases(case, run):
+    """The `-eval` Result line (src/main.cpp:306-323; HessianLearner::GetOptimizationResult, src/HessianLearner.cpp:349-372:
+    KL, -log common support, log model volume, log auxiliary volume, log det of the Hessian, log det of the auxiliary Hessian,
+    free parameters, auxiliary parameters; QuasiNewtonLearner prints an empty line) after the reference's own run
+    `-opt O -i F -e E -tol T -n -eval`, for every fixture and every random automaton the reference accepts
+    (tests/golden/eval.json, written by oracle/make_golden_eval.py from the unmodified reference build)."""
+    s = W.Session(case["fsa_text"], case["corpus_text"], run["optimizer"])
+    s.init(run["flags"])
+    for _ in range(run["epochs"]):
+        s.step(1.0)
+        if s.halt(run["tol"]):
+            break
+    s.renormalize()
+    r = s.result()
+    ref = [fnum(v) for v in run["result"]]
+    assert len(r) == 8 and len(ref) == 8
+    for i in (0, 1, 2, 3, 5, 6, 7):
+        assert math.isclose(r[i], ref[i], rel_tol=1e-6, abs_tol=1e-8), (i, r[i], ref[i])
+    # r[4], the log-determinant of the n x n Hessian in the weights (src/HessianLearner.cpp:219-260), is +inf for a non-positive
+    # determinant (src/Utils.cpp:349-351).  It is compared when both sides call it positive: at the stopping tolerance of the
+    # run (1e-6 on the gradient) it agrees to ~1e-3.  Where the Hessian has an eigenvalue at rounding level (non-identifiable
+    # directions) the SIGN of the determinant is noise of the factorisation, and one side may print inf: 2 of the 77 runs
+    # (random11 -i 7, random24 -i 31), both with |log det| of the other side far from zero.
+    if math.isfinite(ref[4]) and math.isfinite(r[4]) and case["name"] not in SINGULAR_KKT:
+        assert math.isclose(r[4], ref[4], rel_tol=2e-3, abs_tol=2e-3), (r[4], ref[4])
+    s.close()
+
+
 @pytest.mark.parametrize("case", [c for c in load_cases("fixtures") + load_cases("random") if c.get("degenerate")],
                          ids=lambda c: c["name"])
 def test_degenerate_inputs(case):
