@@ -131,3 +131,28 @@ def test_path_listing_matches_reference_binary(fsa, corpus, order):
     want = sorted(ln for ln in subprocess.run([ref] + args, capture_output=True, text=True).stderr.splitlines() if " -> " in ln)
     got = sorted(ln for ln in subprocess.run([ours] + args, capture_output=True, text=True).stderr.splitlines() if " -> " in ln)
     assert want and got == want
+
+
+def test_cli_gpus_option_without_a_device(tmp_path):
+    """`wfsa --gpus N` forks one process per GPU before anything touches CUDA and hands the communicator id down a pipe.
+    Without a device every rank must fail loudly (no CPU fallback), rank 0 must collect the children and return 1, and
+    out-of-range values must be refused before any fork."""
+    import os
+    import subprocess
+    exe = os.path.join(ROOT, "w-fsa_b200", "_build", "wfsa")
+    fsa = tmp_path / "t.wfsa"; corpus = tmp_path / "t.corpus"
+    fsa.write_text("\n^\n$\n^  0\n^ A 0\nA a 0\nA A 0 $ 0\n")
+    corpus.write_text("\na 1\naa 2\n")
+    r = subprocess.run([exe, "-a", str(fsa), "-c", str(corpus), "--gpus", "9"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "--gpus must be between 1 and 8" in r.stderr
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present (tests/test_gpu_parity.py::test_cli_two_gpus_same_table covers the working path)")
+    r = subprocess.run([exe, "-a", str(fsa), "-c", str(corpus), "-opt", "QuasiNewton", "-i", "7", "-e", "2", "--gpus", "2"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1
+    assert "no CPU fallback" in r.stderr or "libnccl" in r.stderr or "communicator" in r.stderr, r.stderr[-2000:]
