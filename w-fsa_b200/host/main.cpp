@@ -19,6 +19,8 @@
 #include <vector>
 
 #include <fcntl.h>
+#include <signal.h>
+#include <sys/prctl.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
@@ -72,6 +74,25 @@ static void print_paths(const Fsa& fsa, const Corpus& corpus, bool bfs)
             }
             for (auto it = found.rbegin(); it != found.rend(); ++it) work.push_back(std::move(*it));
         }
+    }
+}
+
+// --gpus: the ranks meet in collectives (communicator set-up, all-reduces).  A rank that dies would leave the others waiting
+// there for ever, so rank 0 ends the whole run as soon as a child ends with an error, and the children end with their parent.
+static volatile sig_atomic_t g_children_left = 0;
+static pid_t g_child_pids[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+static void on_child(int)
+{
+    int st = 0;
+    pid_t p;
+    while ((p = waitpid(-1, &st, WNOHANG)) > 0) {
+        if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) {
+            static const char msg[] = "wfsa: a rank ended with an error; stopping the other ranks\n";
+            if (write(2, msg, sizeof msg - 1) < 0) {}
+            for (pid_t c : g_child_pids) if (c > 0 && c != p) kill(c, SIGTERM);      // only the ranks this process forked
+            _exit(1);
+        }
+        --g_children_left;
     }
 }
 
@@ -150,6 +171,10 @@ int main(int argc, const char* argv[])
     int err_fd = 2;
     if (gpus > 1) {
         if (initx) { double v; while (std::cin >> v) stdin_x.push_back(v); }
+        g_children_left = gpus - 1;
+        struct sigaction sa{};
+        sa.sa_handler = on_child; sa.sa_flags = SA_RESTART | SA_NOCLDSTOP;
+        sigaction(SIGCHLD, &sa, nullptr);
         std::vector<int> wr;
         for (int r = 1; r < gpus; ++r) {
             int fd[2];
@@ -158,6 +183,8 @@ int main(int argc, const char* argv[])
             if (pid < 0) { perror("fork"); return 1; }
             if (pid == 0) {
                 rank = r;
+                prctl(PR_SET_PDEATHSIG, SIGTERM);        // do not outlive rank 0
+                signal(SIGCHLD, SIG_DFL);
                 close(fd[1]);
                 for (int w : wr) close(w);
                 size_t got = 0;
@@ -172,14 +199,21 @@ int main(int argc, const char* argv[])
             close(fd[0]);
             wr.push_back(fd[1]);
             children.push_back(pid);
+            g_child_pids[r] = pid;
         }
         if (rank == 0) {
             if (wfsa_dev_comm_unique_id(unique_id) != 0) { std::cerr << "--gpus: cannot create the communicator id (libnccl.so.2 not found?)" << std::endl; for (int w : wr) close(w); return 1; }
             for (int w : wr) { if (write(w, unique_id, sizeof unique_id) != (ssize_t)sizeof unique_id) { perror("write"); return 1; } close(w); }
         }
     }
-    auto finish = [&](int rc) {                       // rank 0 collects the exit codes of the other ranks
-        for (pid_t c : children) { int st = 0; if (waitpid(c, &st, 0) < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) rc = rc ? rc : 1; }
+    auto finish = [&](int rc) {                       // rank 0 waits for the other ranks (a failing one ends the run in on_child)
+        if (rank == 0 && !children.empty()) {
+            sigset_t block, old;
+            sigemptyset(&block); sigaddset(&block, SIGCHLD);
+            sigprocmask(SIG_BLOCK, &block, &old);
+            while (g_children_left > 0) sigsuspend(&old);
+            sigprocmask(SIG_SETMASK, &old, nullptr);
+        }
         return rc;
     };
     try {
