@@ -23,7 +23,7 @@ def compile_string(low, trimmed, toks, n_slots=16):
     cap = 64 + 40 * (len(toks) + 2) * 16
     words = np.zeros(cap, dtype=np.uint32)
     nw, na = C.c_int64(), C.c_int32()
-    acap = 1 << 15
+    acap = 1 << 16
     tid, eid = np.zeros(acap, dtype=np.int32), np.zeros(acap, dtype=np.int32)
     t = np.ascontiguousarray(toks, dtype=np.int32)
     tr = None if trimmed is None else np.ascontiguousarray(trimmed, dtype=np.int32)
@@ -50,7 +50,7 @@ def interpret(words, aw):
                     assert np.isfinite(pool[s]), "live slot without a value"
             continue
         if w & EDGE:
-            src, dst, arc = (w >> 19) & 15, (w >> 23) & 15, w & 0x7fff
+            src, dst, arc = (w >> 19) & 15, (w >> 23) & 15, w & 0xffff
             assert src != dst and np.isfinite(pool[src])
             x = pool[src] * aw[arc]
             xs[i] = x
@@ -69,7 +69,7 @@ def interpret(words, aw):
                     assert np.isfinite(pool[s]), "live slot without a beta"
             continue
         if w & EDGE:
-            src, dst, arc = (w >> 19) & 15, (w >> 23) & 15, w & 0x7fff
+            src, dst, arc = (w >> 19) & 15, (w >> 23) & 15, w & 0xffff
             bd = pool[dst]
             c = aw[arc] * bd
             pool[src] = c if w & LAST_OUT else pool[src] + c
@@ -155,6 +155,6 @@ def test_trimmed_arcs_are_removed():
             assert nw == 0
         else:
             aw = np.exp(ltw[tid] + np.where(eid >= 0, lew[np.maximum(eid, 0)], 0.0))
-            assert np.all(np.isfinite(aw[words[(words >> 31) == 1] & 0x7fff]))
+            assert np.all(np.isfinite(aw[words[(words >> 31) == 1] & 0xffff]))
             lq, _ = interpret(words, aw)
             assert abs(lq - olq[s]) <= 1e-12 * max(1.0, abs(olq[s]))

@@ -31,7 +31,7 @@ def region_fwdbwd(col, aw, big):
                     assert np.isfinite(pool[s]), "live slot without a value"
             continue
         if w & EDGE:
-            src, dst, arc = (w >> 19) & 15, (w >> 23) & 15, w & 0x7fff
+            src, dst, arc = (w >> 19) & 15, (w >> 23) & 15, w & 0xffff
             assert src != dst and np.isfinite(pool[src])
             assert bool(w & FIRST_IN) == (not np.isfinite(pool[dst])), "first_in flag must match slot liveness"
             xs[i] = pool[src] * aw[arc]
@@ -56,7 +56,7 @@ def region_fwdbwd(col, aw, big):
         w = int(col[i])
         if (big and i % 16 == 15) or not (w & EDGE):
             continue
-        src, dst, arc = (w >> 19) & 15, (w >> 23) & 15, w & 0x7fff
+        src, dst, arc = (w >> 19) & 15, (w >> 23) & 15, w & 0xffff
         c = aw[arc] * beta[dst]
         beta[src] = c if w & LAST_OUT else beta[src] + c
         post[arc] = post.get(arc, 0.0) + xs[i] * beta[dst] / q

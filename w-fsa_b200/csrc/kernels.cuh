@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(1024, 1) kl_fwdbwd(const KLParams P)
                         }
                     }
                 } else if (wj & kLEdge) {
-                    const int src = (wj >> 19) & 15, dst = (wj >> 23) & 15, arc = wj & 0x7fff;
+                    const int src = (wj >> 19) & 15, dst = (wj >> 23) & 15, arc = wj & 0xffff;
                     const double xv = pool[src * NT] * aw[arc];
                     if (!(wj & kLBridge)) xs[(size_t)(i0 + j) * 32] = xv;
                     double* pd = pool + dst * NT;
@@ -735,7 +735,7 @@ __global__ void __launch_bounds__(1024, 1) kl_fwdbwd(const KLParams P)
                         sc = scalbn(sc0, Et + F - EQ);
                     }
                 } else if (wj & kLEdge) {
-                    const int src = (wj >> 19) & 15, dst = (wj >> 23) & 15, arc = wj & 0x7fff;
+                    const int src = (wj >> 19) & 15, dst = (wj >> 23) & 15, arc = wj & 0xffff;
                     const double bd = pool[dst * NT];
                     const double c = aw[arc] * bd;
                     double* psrc = pool + src * NT;

@@ -41,6 +41,8 @@ struct Eval6Params {
     const int2* __restrict__ arc_tp;            // per arc: trimmed parameter of its transition / emission; -1 weight 1, -2 weight 0
     const double* __restrict__ x;               // [n + 1]: x, then log2 of the fixed-point scale of loglik
     int n, n_arcs, direct_exp;                  // direct_exp: exp per arc (x does not fit the scratch area)
+    double* aw_g;                               // AWG instance: [n_arcs + 1] arc weights in HBM/L2 (they do not fit shared memory); every CTA
+                                                // writes the whole table (identical values) before it reads any of it
     const unsigned long long* __restrict__ const_acc;
     unsigned long long* acc;                    // [2][replicas][n_arcs]
     int replicas;
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(256) k_arc_logw(int n_arcs, const int2* __rest
     logaw[i] = (tp.x == -2 || tp.y == -2) ? -INFINITY : (tp.x >= 0 ? x[tp.x] : 0.0) + (tp.y >= 0 ? x[tp.y] : 0.0);
 }
 
-template <int NT>
+template <int NT, bool AWG = false>
 __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
 {
     extern __shared__ unsigned long long smem[];
@@ -212,9 +214,10 @@ __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
     __shared__ int s_bigleft;                                 // warps of this CTA still busy with big DAG groups
     __shared__ double s_trash[NT];                            // where the lanes without an edge store (kr_big_t)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* aw = reinterpret_cast<double*>(smem);             // [n_arcs + 1]; the last entry is the zero weight of padding
-    double* pool = aw + P.n_arcs + 1 + tid;                   // slot s of this thread at pool[s*NT]
-    double* ex = aw + P.n_arcs + 1;                           // exp(x), in the pool area until the weights are built
+    double* aw = AWG ? P.aw_g : reinterpret_cast<double*>(smem);   // [n_arcs + 1]; the last entry is the zero weight of padding
+    double* const sbase = AWG ? reinterpret_cast<double*>(smem) : aw + P.n_arcs + 1;    // shared memory behind the weight table
+    double* pool = sbase + tid;                               // slot s of this thread at pool[s*NT]
+    double* ex = sbase;                                       // exp(x), in the pool area until the weights are built
     const bool prof = P.stamps && blockIdx.x == 0 && tid == 0;
     unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
     if (prof) { t0 = e6_timer(); if (P.debug) P.stamps[6] = t0; }
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
     // owns staging area w behind the pool (if w < big_slots); the words of its first big group are on their way to it
     // before anything else happens.
     const long long big0 = (long long)blockIdx.x + (long long)warp * gridDim.x;
-    double* const sxs = aw + P.n_arcs + 1 + (size_t)P.pool_slots * NT + (size_t)warp * P.big_rows * 48 + lane;    // [rows][32] doubles
+    double* const sxs = sbase + (size_t)P.pool_slots * NT + (size_t)warp * P.big_rows * 48 + lane;    // [rows][32] doubles
     uint32_t* const sw = reinterpret_cast<uint32_t*>(sxs - lane + (size_t)P.big_rows * 32) + lane;                 // [rows][32] words
     auto stage_big = [&](long long g) {                        // true: the rows of group g are being copied to the staging area
         const long long off = P.goff[g];
@@ -294,6 +297,7 @@ __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
             aw[i] = w;                                         // i == n_arcs: the zero weight of padding
         }
     }
+    if (AWG) __threadfence();                                  // (the table is in global memory: this CTA's copy is complete before any of its threads reads it)
     __syncthreads();                                           // weights complete; exp(x) scratch is free: the pool starts here
     if (prof) t1 = e6_timer();
     if (tline) tl1 = e6_timer();

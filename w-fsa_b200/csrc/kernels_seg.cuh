@@ -179,7 +179,7 @@ __device__ __forceinline__ void kr_big_t(const KRParams& P, const double* aw, do
         for (int j = 0; j < 8; ++j) {
             const uint32_t wj = w[j];
             const bool edge = (wj & kLEdge) != 0;
-            const int src = edge ? (wj >> 19) & 15 : (wj & 15), arc = edge ? (int)(wj & 0x7fff) : 0;
+            const int src = edge ? (wj >> 19) & 15 : (wj & 15), arc = edge ? (int)(wj & 0xffff) : 0;
             ps[j] = pool + src * NT;                          // (FIN: the exit node)
             pd[j] = edge ? pool + ((wj >> 23) & 15) * NT : trash;
             wv[j] = aw[arc];
@@ -246,7 +246,7 @@ __device__ __forceinline__ void kr_big_t(const KRParams& P, const double* aw, do
         for (int j = 0; j < 8; ++j) {
             const uint32_t wj = w[j];
             const bool edge = (wj & kLEdge) != 0;
-            const int slot = edge ? (wj >> 19) & 15 : (wj & 15), arc = edge ? (int)(wj & 0x7fff) : 0;   // (FIN: the exit node, beta = 1)
+            const int slot = edge ? (wj >> 19) & 15 : (wj & 15), arc = edge ? (int)(wj & 0xffff) : 0;   // (FIN: the exit node, beta = 1)
             pdst[j] = pool + ((wj >> 23) & 15) * NT;
             psrc[j] = (wj & (kLEdge | kLFin)) ? pool + slot * NT : trash;
             wv[j] = aw[arc];
@@ -271,7 +271,7 @@ __device__ __forceinline__ void kr_big_t(const KRParams& P, const double* aw, do
 #pragma unroll
         for (int j = 0; j < 8; ++j) { w[j] = ldw(i0 + j); v[j] = xs_ld(i0 + j); }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) if (v[j]) red_add64(acc_g + (w[j] & 0x7fff), (unsigned long long)v[j]);
+        for (int j = 0; j < 8; ++j) if (v[j]) red_add64(acc_g + (w[j] & 0xffff), (unsigned long long)v[j]);
     }
 }
 
@@ -283,15 +283,17 @@ __device__ __forceinline__ void kr_big(const KRParams& P, const double* aw, doub
     kr_big_t<ACC, false>(P, aw, pool, NT, g, lane, P.words + o + lane, (int)((P.goff[g + 1] - o) >> 5), xs, acc_g, ll, trash);
 }
 
-template <int ACC, int MAXNT>
+template <int ACC, int MAXNT, bool AWG = false>
 __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
 {
     extern __shared__ unsigned long long smem[];
     __shared__ double s_trash[MAXNT];                         // where the lanes without an edge store (kr_big_t)
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
-    double* aw = reinterpret_cast<double*>(smem);             // [n_arcs + 1]; the last entry is the zero weight of padding
-    double* pool = aw + P.n_arcs + 1 + tid;                   // slot s of this thread at pool[s*NT]
-    for (int i = tid; i <= P.n_arcs; i += NT) aw[i] = i < P.n_arcs ? P.aw[i] : 0.0;
+    // [n_arcs + 1] arc weights, the last entry the zero weight of padding: a copy in shared memory, or (AWG: the table does not
+    // fit) P.aw itself, which then has the zero entry behind it
+    const double* aw = AWG ? P.aw : reinterpret_cast<const double*>(smem);
+    double* pool = (AWG ? reinterpret_cast<double*>(smem) : reinterpret_cast<double*>(smem) + P.n_arcs + 1) + tid;   // slot s of this thread at pool[s*NT]
+    if (!AWG) { double* t = reinterpret_cast<double*>(smem); for (int i = tid; i <= P.n_arcs; i += NT) t[i] = i < P.n_arcs ? P.aw[i] : 0.0; }
     __syncthreads();
     const long long gwarp = ((long long)blockIdx.x * NT + tid) >> 5;
     double* const xs = P.xs + (size_t)gwarp * P.xs_rows * 32 + lane;
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__(MAXNT, 1) kr_regions(const KRParams P)
 #pragma unroll
     for (int o = 16; o; o >>= 1) ll += __shfl_xor_sync(FULL, ll, o);
     __syncthreads();                                           // the pool is free now
-    long long* part = reinterpret_cast<long long*>(aw + P.n_arcs + 1);
+    long long* part = reinterpret_cast<long long*>(pool - tid);
     if (lane == 0) part[tid >> 5] = ll;
     __syncthreads();
     if (tid == 0) {
@@ -360,13 +362,15 @@ struct KSParams {
 // slower than this register double buffer (the limit was DRAM burst locality, not bytes in flight).
 constexpr int kKsRows = 8, kKsWarps = 16;      // = kKsChunkRows, kKsSuper of lattice.hpp
 
+// AWG: the table does not fit shared memory and is read from HBM/L2 (P.logaw has n_arcs + 16 entries, the last 16 zero)
+template <bool AWG = false>
 __global__ void __launch_bounds__(kKsWarps * 32, 2) ks_strings(const KSParams P)
 {
     extern __shared__ __align__(128) unsigned long long smem[];
     __shared__ long long s_next[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* tab = reinterpret_cast<double*>(smem);            // [n_arcs + 16]; ids n_arcs.. (padding, one per bank pair) -> 0
-    for (int i = tid; i < P.n_arcs + 16; i += kKsWarps * 32) tab[i] = i < P.n_arcs ? P.logaw[i] : 0.0;
+    const double* tab = AWG ? P.logaw : reinterpret_cast<const double*>(smem);   // [n_arcs + 16]; ids n_arcs.. (padding, one per bank pair) -> 0
+    if (!AWG) { double* t = reinterpret_cast<double*>(smem); for (int i = tid; i < P.n_arcs + 16; i += kKsWarps * 32) t[i] = i < P.n_arcs ? P.logaw[i] : 0.0; }
     if (tid == 0) s_next[0] = (long long)atomicAdd(P.counter, 1u);
     __syncthreads();
     int par = 0;

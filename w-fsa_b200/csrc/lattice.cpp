@@ -779,7 +779,7 @@ std::shared_ptr<SegmentedStringsJob> compile_corpus_regions(const HostFsa& f, co
         const Type &X = types[a], &Y = types[b];
         const uint32_t* wa = loc[X.t].rwords.data() + X.beg; const uint32_t* wb = loc[Y.t].rwords.data() + Y.beg;
         const int32_t m = std::min(X.len, Y.len);
-        for (int32_t k = 0; k < m; ++k) if (wa[k] != wb[k]) return (wa[k] & 0x7fffu) != (wb[k] & 0x7fffu) ? (wa[k] & 0x7fffu) < (wb[k] & 0x7fffu) : wa[k] < wb[k];
+        for (int32_t k = 0; k < m; ++k) if (wa[k] != wb[k]) return (wa[k] & 0xffffu) != (wb[k] & 0xffffu) ? (wa[k] & 0xffffu) < (wb[k] & 0xffffu) : wa[k] < wb[k];
         return X.len < Y.len;
     };
     {
@@ -851,7 +851,7 @@ std::shared_ptr<SegmentedStringsJob> compile_corpus_regions(const HostFsa& f, co
                 if (!(w[0] >> 31)) {
                     const int P = (int)((w[0] >> 8) & 0xff), L = (int)(w[0] & 0xff), PP = pad_paths(P);
                     for (int el = 0; el < L; ++el)
-                        for (int q = 0; q < P; ++q) dst[(size_t)(el * PP + q) * 32] = w[1 + el * P + q] & 0x7fffu;
+                        for (int q = 0; q < P; ++q) dst[(size_t)(el * PP + q) * 32] = w[1 + el * P + q] & 0xffffu;
                     ne += (int64_t)P * L;
                 } else {
                     for (int32_t k = 0; k < Y.len; ++k) { dst[(size_t)k * 32] = w[k]; ne += (w[k] >> 31); }

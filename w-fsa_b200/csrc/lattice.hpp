@@ -36,7 +36,7 @@ namespace wfsa {
 
 constexpr uint32_t kLatEdge = 1u << 31, kLatFin = 1u << 30, kLatFirstIn = 1u << 29, kLatLastOut = 1u << 28,
                    kLatBridge = 1u << 27;
-constexpr int kLatDstShift = 23, kLatSrcShift = 19, kLatArcBits = 15, kLatMaxSlots = 16;
+constexpr int kLatDstShift = 23, kLatSrcShift = 19, kLatArcBits = 16, kLatMaxSlots = 16;
 constexpr int kCheckEvery = 16;           // words between CHECK words (power of two, multiple of the kernel's chunk)
 
 // combined arcs of an automaton: (transition, emission of its target) pairs and final transitions

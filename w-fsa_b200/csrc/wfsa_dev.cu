@@ -125,6 +125,7 @@ struct wfsa_dev {
     // compiled-lattice thread-per-string kernel (KL)
     LatticeArcs larcs;
     int kl_grid = 0, kl_block = 0, kl_K = 0; size_t kl_smem = 0;
+    bool awg = false;                         // segmented path with the arc weights in HBM/L2 (they do not fit shared memory)
     bool kl_bridges = true;
     int64_t kl_groups = 0, kl_words = 0, kl_edges = 0, kl_bridge_edges = 0, kl_max_words = 0;
     DevBuf<uint32_t> d_klwords, d_klcounter;
@@ -378,12 +379,19 @@ static int setup_kt(wfsa_dev* h)
 }
 
 // compiled-lattice kernel: per-arc weights + kLatMaxSlots pool doubles per thread must fit 227 KB
-static bool kl_possible(const wfsa_dev* h, int K, int want_nt, int& nt, size_t& smem)
+// `awg` (may be null = not allowed): set when the table does not fit but the pool alone does -- the segmented kernels then read
+// the weights from HBM/L2 (their AWG instances); the thread-per-string kernel 5 has no such form
+static bool kl_possible(const wfsa_dev* h, int K, int want_nt, int& nt, size_t& smem, bool* awg = nullptr)
 {
     const LatticeArcs& A = h->larcs;
+    if (awg) *awg = false;
     if (A.n_arcs <= 0 || A.n_arcs >= (1 << kLatArcBits)) return false;
-    const size_t tab = ((size_t)A.n_arcs + 1) * 8, max_smem = 227 * 1024 - 9216;     // + the zero weight of padding (kr_regions); k_eval6 has 7 KB of static shared memory, kr_regions up to 8
-    if (tab + (size_t)128 * K * 8 > max_smem) return false;
+    size_t tab = ((size_t)A.n_arcs + 1) * 8;
+    const size_t max_smem = 227 * 1024 - 9216;     // + the zero weight of padding (kr_regions); k_eval6 has 7 KB of static shared memory, kr_regions up to 8
+    if (tab + (size_t)128 * K * 8 > max_smem) {
+        if (!awg) return false;
+        *awg = true; tab = 0;
+    }
     nt = (int)((max_smem - tab) / ((size_t)K * 8) / 32) * 32;
     nt = std::min(nt, 1024);
     if (want_nt > 0) nt = std::min(nt, want_nt);
@@ -433,21 +441,23 @@ static int setup_kl(wfsa_dev* h)
     int nt = 0; size_t smem = 0;
     int want_nt = ((h->opt.reserved >> 24) & 0x7f) * 32;
     if (want_nt == 0 && h->kernel == 6) want_nt = 512;       // measured: 16 warps leave the L1 to the register spills
-    if (!kl_possible(h, K, want_nt, nt, smem))
+    bool awg = false;
+    if (!kl_possible(h, K, want_nt, nt, smem, h->kernel == 6 ? &awg : nullptr))
         return set_err(h, WFSA_ERR_LIMIT, "compiled-lattice kernel: the arc weights do not fit shared memory");
-    if (h->kernel == 6 && (want_nt == 512 || nt > 512)) {   // k_eval6 is compiled for 512, 256 and 128 threads, kr_regions for up to 512
-        nt = nt >= 512 ? 512 : (nt >= 256 ? 256 : 128);
-        smem = ((size_t)h->larcs.n_arcs + 1) * 8 + (size_t)nt * K * 8;
+    h->awg = awg;
+    if (h->kernel == 6 && (want_nt == 512 || nt > 512 || awg)) {   // k_eval6 is compiled for 512, 256 and 128 threads (AWG: 512), kr_regions for up to 512
+        nt = awg ? 512 : (nt >= 512 ? 512 : (nt >= 256 ? 256 : 128));
+        smem = (awg ? 0 : ((size_t)h->larcs.n_arcs + 1) * 8) + (size_t)nt * K * 8;
     }
     h->kl_K = K; h->kl_block = nt; h->kl_grid = h->sm_count; h->kl_smem = smem;
     h->kl_bridges = !(h->opt.reserved & 4);
     const LatticeArcs& A = h->larcs;
     CK(h->d_kl_arc_tid.upload(A.arc_tid, h->stream)); CK(h->d_kl_arc_eid.upload(A.arc_eid, h->stream));
-    CK(h->d_klaw.alloc(A.n_arcs)); CK(h->d_klacc.alloc((size_t)A.n_arcs * h->replicas)); CK(h->d_klconst.alloc(A.n_arcs));
+    CK(h->d_klaw.alloc((size_t)A.n_arcs + 1)); CK(cudaMemsetAsync(h->d_klaw.p, 0, ((size_t)A.n_arcs + 1) * 8, h->stream)); CK(h->d_klacc.alloc((size_t)A.n_arcs * h->replicas)); CK(h->d_klconst.alloc(A.n_arcs));
     CK(h->d_klcounter.alloc(2));
     CK(h->d_llpart.alloc(2 * (size_t)((std::max(h->larcs.n_arcs, 1) + 255) / 256)));
     if (h->kernel == 6) {
-        CK(h->d_klogaw.alloc(A.n_arcs));
+        CK(h->d_klogaw.alloc((size_t)A.n_arcs + 16)); CK(cudaMemsetAsync(h->d_klogaw.p, 0, ((size_t)A.n_arcs + 16) * 8, h->stream));   // (+ the zero entries of the padding ids)
         {   // arcs of every edge (transition edges, then emission edges) for the gather in k_fold_finish6
             const int nt = h->fsa.n_trans(), ne = nt + h->fsa.n_emis();
             std::vector<int32_t> off((size_t)ne + 1, 0), arc;
@@ -468,13 +478,15 @@ static int setup_kl(wfsa_dev* h)
             cudaFuncSetAttribute(k_eval6<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);
             cudaFuncSetAttribute(k_eval6<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);
         }
-        h->ks_smem = ((size_t)A.n_arcs + 16) * 8;
+        h->ks_smem = h->awg ? 0 : ((size_t)A.n_arcs + 16) * 8;
         h->ks_block = kKsWarps * 32;
         h->ks_ctas = h->ks_smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
         h->ks_grid = h->sm_count * h->ks_ctas;
+        cudaFuncSetAttribute(k_eval6<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);
         cudaFuncSetAttribute(kr_regions<ACC_GLOBAL, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192 - 1024);
         cudaFuncSetAttribute(kr_regions<ACC_NONE, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192 - 1024);
-        cudaFuncSetAttribute(ks_strings, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ks_smem);   // it also has static shared memory
+        cudaFuncSetAttribute(kr_regions<ACC_GLOBAL, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192 - 1024);
+        cudaFuncSetAttribute(ks_strings<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ks_smem);   // it also has static shared memory
     }
     cudaFuncSetAttribute(kl_fwdbwd<ACC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(kl_fwdbwd<ACC_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -578,11 +590,13 @@ extern "C" int wfsa_dev_create(const wfsa_fsa_desc* fd, const wfsa_corpus_desc* 
     int kernel = h->opt.force_kernel;
     if (kernel == 0) {
         int nt = 0; size_t sm = 0; int K = (h->opt.reserved >> 16) & 0xff; if (K == 0) K = 8;
+        bool awg = false;
         if (kl_possible(h, kLatMaxSlots, 0, nt, sm)) kernel = h->larcs.n_arcs < 65520 ? 6 : 5;
+        else if (h->larcs.n_arcs < 65520 && kl_possible(h, kLatMaxSlots, 0, nt, sm, &awg)) kernel = 6;      // weights in HBM/L2 (16-bit arc ids still fit)
         else kernel = !h->fast.ok ? 3 : (kt_possible(h, K, nt, sm) ? 4 : (h->fast.warp_ok ? 1 : (((h->fast.max_cand + 31) / 32 * 32 <= 512 && cd && cd->n_strings >= 200000) ? 7 : 2)));     // K7 pays off once ~3 strings share a symbol pair per position
     }
     if (kernel == 6 && h->larcs.n_arcs >= 65520) { h->err = "forced segmented kernel but the automaton has 65520 or more combined arcs"; return bail(WFSA_ERR_INVALID); }
-    if (kernel == 5 || kernel == 6) { int nt = 0; size_t sm = 0; if (!kl_possible(h, kLatMaxSlots, 0, nt, sm)) { h->err = "forced compiled-lattice kernel but the arc weights do not fit shared memory"; return bail(WFSA_ERR_INVALID); } }
+    if (kernel == 5 || kernel == 6) { int nt = 0; size_t sm = 0; bool awg = false; if (!kl_possible(h, kLatMaxSlots, 0, nt, sm, kernel == 6 ? &awg : nullptr)) { h->err = "forced compiled-lattice kernel but the arc weights do not fit shared memory"; return bail(WFSA_ERR_INVALID); } }
     if (kernel == 7 && h->fast.ok && (h->fast.max_cand + 31) / 32 * 32 > 512) { h->err = "forced batched kernel but more than 512 states emit one symbol"; return bail(WFSA_ERR_INVALID); }
     if ((kernel == 1 || kernel == 2 || kernel == 4 || kernel == 7) && !h->fast.ok) { h->err = "forced fast kernel but emissions are not all one token long"; return bail(WFSA_ERR_INVALID); }
     if (kernel == 1 && !h->fast.warp_ok) { h->err = "forced warp-per-string kernel but more than 32 states emit one symbol"; return bail(WFSA_ERR_INVALID); }
@@ -703,7 +717,8 @@ static void launch_main(wfsa_dev* h, int kernel, int mode, const CorpusD& C, con
             P.lq = h->d_krlq.p; P.n_groups = h->kr_groups; P.xs = h->d_klxs.p; P.xs_rows = (size_t)std::max<int64_t>(h->kl_max_words, 1);
             P.counter = h->d_klcounter.p; P.acc = h->d_klacc.p; P.fx_scale = O.fx_scale; P.n_arcs = h->larcs.n_arcs; P.replicas = h->replicas;
             P.ll_scale = O.ll_scale; P.red = O.red; P.llpart = h->d_llpart.p; P.n_llpart = h->llpart_n;
-            if (h->opt.reserved & 2) kr_regions<ACC_NONE, 512><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // timing experiment
+            if (h->awg) kr_regions<ACC_GLOBAL, 512, true><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);       // weights read from HBM/L2
+            else if (h->opt.reserved & 2) kr_regions<ACC_NONE, 512><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);   // timing experiment
             else kr_regions<ACC_GLOBAL, 512><<<h->kl_grid, h->kl_block, h->kl_smem, st>>>(P);
             h->launches++;
         }
@@ -869,6 +884,7 @@ static void fill_eval6_params(wfsa_dev* h, Eval6Params& P)
     P.xs = h->d_klxs.p; P.xs_rows = (size_t)std::max<int64_t>(h->kl_max_words, 1);
     P.arc_tp = h->d_arc_tp.p; P.x = h->d_x.p; P.n = h->n; P.n_arcs = h->larcs.n_arcs;
     P.direct_exp = (size_t)h->n > (size_t)h->kl_block * h->kl_K ? 1 : 0;
+    P.aw_g = h->d_klaw.p;
     P.const_acc = h->d_klconst.p; P.acc = h->d_e6acc.p; P.replicas = h->replicas;
     P.fx_scale = std::ldexp(1.0, (int)h->fx_log2); P.inv_fx = std::ldexp(1.0, -(int)h->fx_log2);
     P.red = h->d_e6red.p; P.ctl = h->d_e6ctl.p;
@@ -896,7 +912,8 @@ static cudaError_t launch_eval6(wfsa_dev* h, cudaStream_t st, bool count = true,
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = getenv("WFSA_E6_PLAIN_LAUNCH") ? 0 : 1;
     cudaError_t e;
-    if (h->kl_block == 512) e = cudaLaunchKernelEx(&cfg, k_eval6<512>, P);
+    if (h->awg) e = cudaLaunchKernelEx(&cfg, k_eval6<512, true>, P);
+    else if (h->kl_block == 512) e = cudaLaunchKernelEx(&cfg, k_eval6<512>, P);
     else if (h->kl_block == 384) e = cudaLaunchKernelEx(&cfg, k_eval6<384>, P);
     else if (h->kl_block == 256) e = cudaLaunchKernelEx(&cfg, k_eval6<256>, P);
     else e = cudaLaunchKernelEx(&cfg, k_eval6<128>, P);
@@ -1592,7 +1609,7 @@ extern "C" int wfsa_dev_eval_fetch(wfsa_dev* h, double* loglik, double* logq, do
                 k_arc_logw<<<(h->larcs.n_arcs + 255) / 256, 256, 0, h->stream>>>(h->larcs.n_arcs, h->d_arc_tp.p, h->d_x.p, h->d_klogaw.p);
                 h->launches++;
             }
-            ks_strings<<<h->ks_grid, h->ks_block, h->ks_smem, h->stream>>>(S);
+            if (h->awg) ks_strings<true><<<h->ks_grid, h->ks_block, 0, h->stream>>>(S); else ks_strings<false><<<h->ks_grid, h->ks_block, h->ks_smem, h->stream>>>(S);
             h->launches++;
             h->ks_done = true;
         }
@@ -1819,7 +1836,7 @@ static void make_type_blocks(const LatticeArcs& A, const std::vector<int32_t>& t
                     if (w & kLatEdge) {
                         const int src = (w >> kLatSrcShift) & 15, dst = (w >> kLatDstShift) & 15;
                         if (w & kLatFirstIn) node_of[dst] = new_node();
-                        out[node_of[src]].push_back({node_of[dst], (int32_t)(w & 0x7fff)});
+                        out[node_of[src]].push_back({node_of[dst], (int32_t)(w & 0xffff)});
                     } else if (w & kLatFin) exit_node = node_of[w & 15];
                 }
                 if (exit_node < 0) { B.fail = "H_f blocks: a DAG-form region type has no FIN word"; break; }
@@ -1906,7 +1923,7 @@ extern "C" int wfsa_dev_hessian(wfsa_dev* h, const double* x, double* Hf, double
             S.p = h->d_ksp.p; S.logq = h->d_kslogq.p; S.n_sgroups = h->ks_groups; S.counter = h->d_klcounter.p + 1; S.n_arcs = h->larcs.n_arcs;
             CK(cudaMemsetAsync(h->d_klcounter.p + 1, 0, 4, h->stream));
             CK(cudaMemsetAsync(h->d_kslogq.p, 0, h->d_kslogq.n * 8, h->stream));
-            ks_strings<<<h->ks_grid, h->ks_block, h->ks_smem, h->stream>>>(S);
+            if (h->awg) ks_strings<true><<<h->ks_grid, h->ks_block, 0, h->stream>>>(S); else ks_strings<false><<<h->ks_grid, h->ks_block, h->ks_smem, h->stream>>>(S);
             k_min_exp<<<1, 1024, 0, h->stream>>>((long long)h->d_kslogq.n, h->d_kslogq.p, h->d_rmin.p);
             h->launches += 2;
             h->ks_done = false;                           // the per-string buffer no longer holds log q
