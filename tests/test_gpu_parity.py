@@ -503,19 +503,21 @@ def test_full_size_config4_properties():
     dev.close()
 
 
-@pytest.mark.parametrize("n_states,expect_segmented", [(512, True), (1024, True), (2048, False)])
-def test_automata_around_the_arc_limits(n_states, expect_segmented):
+@pytest.mark.parametrize("n_states,expect_segmented,variant", [(512, True, 0), (1024, True, 0), (1024, True, 4 << 16), (2048, False, 0)])
+def test_automata_around_the_arc_limits(n_states, expect_segmented, variant):
     """The limits of DESIGN.md section 5.  512 states (16.9 k combined arcs, 135 KB of weights): the segmented path with the
     weights in shared memory.  1024 states (32.8 k arcs, 262 KB of weights): the same kernels reading the weights from HBM/L2
     (their AWG instances).  2048 states (65.6 k arcs): beyond the 16-bit arc ids of the compiled form, whatever the library picks
-    instead.  Whatever runs, the results are the oracle's."""
+    instead.  Whatever runs, the results are the oracle's.  (Variant 4 << 16: four pool slots, so that some strings overflow and
+    the evaluation takes the general pipeline -- kr_regions with the weights in HBM -- instead of the single-launch kernel.)"""
     model = synth.make_model(n_states, 64, 8, 4, seed=77)
     low = model.lowered()
     offs, toks, w = model.corpus(20000, 32, 128, seed=78)
     low.set_tokens(offs, toks, w / w.sum())
-    dev, rec, pc, trimmed, n = build_device(low)
+    dev, rec, pc, trimmed, n = build_device(low, accum_variant=variant)
     info = dev.info()
     assert rec.all() and (info["kernel"] == 6) == expect_segmented, info["kernel"]
+    assert (info["n_overflow_strings"] > 0) == (variant != 0)
     x = np.random.RandomState(4).normal(-1.0, 0.3, size=n)
     ll, logq, grad = dev.eval(x)
     ltw, lew = low.edge_logweights(x, trimmed)
