@@ -480,7 +480,7 @@ def run_ours(args, rank, world, local):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * (n + 1), "d2h_bytes_per_step": 8 * (n + 3),
                     "ms_per_step": e2e_max * 1e3 / steps, "with_logq_ms_per_step": lq_ms,
                     "with_logq_d2h_bytes_per_step": 8 * (n + 3) + 8 * n_local_strings,
-                    "call": "wfsa_dev_eval(x, &loglik, NULL, grad) with host buffers" + (": one CUDA graph launch (H2D copy of x, then k_eval6, which writes [loglik, grad] and a completion word straight into mapped pinned host memory; the host polls that word)" if single else "")},
+                    "call": "wfsa_dev_eval(x, &loglik, NULL, grad) with host buffers" + (": one CUDA graph launch of ONE kernel node -- CTA 0 of k_eval6 fetches x from the mapped pinned staging buffer and publishes it to the grid, the kernel writes [loglik, grad] and a completion word straight into mapped pinned host memory, the host polls that word" if single else "")},
             "gpu_launches": int(M["launches"]),
             "self_check": {"loglik_vs_sum_p_logq_all_ranks": bool(ll_check), "resident_vs_host_buffer_bitwise": True},
             **extra_keys,

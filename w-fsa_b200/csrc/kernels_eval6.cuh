@@ -39,7 +39,9 @@ struct Eval6Params {
     double* xs; size_t xs_rows;
     // weights
     const int2* __restrict__ arc_tp;            // per arc: trimmed parameter of its transition / emission; -1 weight 1, -2 weight 0
-    const double* __restrict__ x;               // [n + 1]: x, then log2 of the fixed-point scale of loglik
+    const double* x;                            // [n + 1]: x, then log2 of the fixed-point scale of loglik
+    const double* x_host; double* x_w;          // host-buffer call: x waits in mapped pinned host memory (x_host); CTA 0 copies it to
+                                                // x_w (= x) and publishes the epoch in ctl[5], the other CTAs wait for that word
     int n, n_arcs, direct_exp;                  // direct_exp: exp per arc (x does not fit the scratch area)
     double* aw_g;                               // AWG instance: [n_arcs + 1] arc weights in HBM/L2 (they do not fit shared memory); every CTA
                                                 // writes the whole table (identical values) before it reads any of it
@@ -49,7 +51,7 @@ struct Eval6Params {
     double fx_scale, inv_fx;
     unsigned long long* red;                    // [2] fixed-point loglik, non-finite terms; zero between evaluations
     unsigned int* ctl;                          // [0..1] ticket counters, [2] barrier arrivals (monotonic), [3] epoch (starts at 1),
-                                                // [4] CTAs of host-buffer launches that have finished (monotonic)
+                                                // [4] CTAs of host-buffer launches that have finished (monotonic), [5] epoch whose x has been fetched from the host
     unsigned int* done_flag;                    // host-mapped word that receives the count of host-buffer launches when the whole grid has written `out`
                                                 // (the host-buffer call polls it instead of waiting for a D2H copy and a stream sync), or nullptr
     // fold
@@ -258,6 +260,23 @@ __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
     const unsigned long long bc = bi < P.n_arcs ? P.const_acc[bi] : 0ull;
     const int2 btp = bi < P.n_arcs ? P.arc_tp[bi] : make_int2(-2, -2);
     for (int i = tid; i < P.n_cls; i += NT) s_cls[i] = P.cls[i];
+    if (P.x_host) {                                            // (uniform over the grid)
+        if (blockIdx.x == 0) {
+            for (int i0 = tid; i0 <= P.n; i0 += 8 * NT) {                          // eight loads per thread in flight: a PCIe round trip per batch
+                double hv[8];                                                       // (one load per iteration was measured: 10.5 us for 27 KB)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) hv[j] = i0 + j * NT <= P.n ? __ldcv(P.x_host + i0 + j * NT) : 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (i0 + j * NT <= P.n) P.x_w[i0 + j * NT] = hv[j];
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(P.ctl + 5), "r"(epoch) : "memory");
+        } else {
+            if (tid == 0) while (e6_ld_acquire(P.ctl + 5) != epoch) { }
+            __syncthreads();
+        }
+    }
     if (!P.direct_exp)
         for (int i0 = tid; i0 < P.n; i0 += 8 * NT) {
             double xv[8];

@@ -113,7 +113,8 @@ struct wfsa_dev {
     DevBuf<double> d_gscratch;
     long long g_batch = 0;
     double* h_out = nullptr;                   // pinned [2 + n]
-    double* h_x = nullptr;                     // pinned [n]
+    double* h_x = nullptr;                     // pinned and mapped [n + 1]
+    double* h_x_dev = nullptr;                 // device address of h_x (the host-buffer call lets the kernel fetch x itself)
     double fx_log2 = 0, ll_log2 = 44;
     int grid = 0, block = 0, stack_cap = 0, n_acc_smem = 0;      // warp-per-string (K2) launch
     size_t smem_bytes = 0, glstack_words = 0, table_bytes = 0;
@@ -900,11 +901,12 @@ static void fill_eval6_params(wfsa_dev* h, Eval6Params& P)
     if (P.big_dedicate && !getenv("WFSA_E6_STATIC")) P.static_pct = 100;
 }
 
-static cudaError_t launch_eval6(wfsa_dev* h, cudaStream_t st, bool count = true, bool to_host = false)
+static cudaError_t launch_eval6(wfsa_dev* h, cudaStream_t st, bool count = true, bool to_host = false, bool x_from_host = false)
 {
     Eval6Params P;
     fill_eval6_params(h, P);
     if (to_host) { P.out = h->hm_out_dev; P.done_flag = h->hm_flag_dev; }
+    if (x_from_host) { P.x_host = h->h_x_dev; P.x_w = h->d_x.p; }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(h->kl_grid); cfg.blockDim = dim3(h->kl_block); cfg.dynamicSmemBytes = h->e6_smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -1364,7 +1366,9 @@ extern "C" int wfsa_dev_set_param_map(wfsa_dev* h, const int32_t* trimmed, int32
         if (h->h_x) cudaFreeHost(h->h_x);
         h->h_out = nullptr; h->h_x = nullptr;
         CK(cudaMallocHost(&h->h_out, ((size_t)n + 3) * 8));      // [loglik, non-finite terms, grad[n], epoch of a timed-out exchange]
-        CK(cudaMallocHost(&h->h_x, ((size_t)n + 1) * 8));        // [x[n], log2 of the fixed-point scale of loglik]
+        CK(cudaHostAlloc(&h->h_x, ((size_t)n + 1) * 8, cudaHostAllocMapped));        // [x[n], log2 of the fixed-point scale of loglik]
+        h->h_x_dev = nullptr;
+        if (cudaHostGetDevicePointer(&h->h_x_dev, h->h_x, 0) != cudaSuccess) { cudaGetLastError(); h->h_x_dev = nullptr; }
         CK(h->d_x.alloc((size_t)n + 1));
         CK(h->d_out.alloc((size_t)n + 3));
     }
@@ -1646,8 +1650,12 @@ static bool eval6_graph(wfsa_dev* h)
         h->hm_n = words;
     }
     if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
-    cudaMemcpyAsync(h->d_x.p, h->h_x, ((size_t)h->n + 1) * 8, cudaMemcpyHostToDevice, h->stream);
-    launch_eval6(h, h->stream, false, true);
+    // x: CTA 0 of the kernel fetches it from the mapped staging buffer and publishes it to the other CTAs (k_eval6, P.x_host).
+    // A copy node in front of the kernel cost 12.5 us per call (measured: the DMA set-up and the dependency between the two
+    // nodes), the fetch inside the kernel ~3 us.  (WFSA_E2E_COPY_NODE=1 brings the copy node back.)
+    const bool copy_node = !h->h_x_dev || getenv("WFSA_E2E_COPY_NODE");
+    if (copy_node) cudaMemcpyAsync(h->d_x.p, h->h_x, ((size_t)h->n + 1) * 8, cudaMemcpyHostToDevice, h->stream);
+    launch_eval6(h, h->stream, false, true, !copy_node);
     cudaGraph_t g = nullptr;
     if (cudaStreamEndCapture(h->stream, &g) != cudaSuccess || !g) { cudaGetLastError(); return false; }
     cudaGraphExec_t ex = nullptr;
