@@ -15,8 +15,9 @@
 //       exchanged through NVLink peer memory as self-validating packets (ll_exchange, kernels_seg.cuh) and the warp
 //       converts the total to grad[i]; one warp does the same for [loglik, non-finite terms].
 // Everything an evaluation needs that changes from call to call lives in device memory (x, the fixed-point scale of
-// the log-likelihood behind x, the epoch in ctl[3]), so the launch parameters are constant per parameter map and the
-// sequence  H2D x -> k_eval6 -> D2H [loglik, grad]  is replayed as a CUDA graph by wfsa_dev_eval.
+// the log-likelihood behind x, the epoch in ctl[3]), so the launch parameters are constant per parameter map and
+// wfsa_dev_eval replays the launch as a CUDA graph of this one kernel: with host buffers CTA 0 fetches x from mapped pinned
+// memory (x_host) and the results go straight into mapped pinned memory as well (out, done_flag) -- no copy nodes.
 #pragma once
 #include "kernels_seg.cuh"
 
