@@ -52,7 +52,8 @@ struct Eval6Params {
     double fx_scale, inv_fx;
     unsigned long long* red;                    // [2] fixed-point loglik, non-finite terms; zero between evaluations
     unsigned int* ctl;                          // [0..1] ticket counters, [2] barrier arrivals (monotonic), [3] epoch (starts at 1),
-                                                // [4] CTAs of host-buffer launches that have finished (monotonic), [5] epoch whose x has been fetched from the host
+                                                // [4] CTAs of the current host-buffer launch that are through, [5] epoch whose x has been fetched from the host,
+                                                // [6] host-buffer launches completed
     unsigned int* done_flag;                    // host-mapped word that receives the count of host-buffer launches when the whole grid has written `out`
                                                 // (the host-buffer call polls it instead of waiting for a D2H copy and a stream sync), or nullptr
     // fold
@@ -482,10 +483,16 @@ __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
         __syncthreads();
         if (tid == 0) {
             __threadfence_system();
-            // ctl[4] counts the CTAs of host-buffer launches only; launches are stream ordered, so a multiple of the grid
-            // size means the last CTA of THIS launch.  The word written is the number of host-buffer launches so far.
+            // ctl[4] counts the CTAs of THIS host-buffer launch that are through (launches are stream ordered); the last one
+            // re-arms it and writes the number of host-buffer launches so far (ctl[6], wraps like the host's counter)
             const unsigned int arrived = atomicAdd(P.ctl + 4, 1u) + 1u;
-            if (arrived % gridDim.x == 0u) { *reinterpret_cast<volatile unsigned int*>(P.done_flag) = arrived / gridDim.x; __threadfence_system(); }
+            if (arrived == gridDim.x) {
+                P.ctl[4] = 0u;
+                const unsigned int done = P.ctl[6] + 1u;
+                P.ctl[6] = done;
+                *reinterpret_cast<volatile unsigned int*>(P.done_flag) = done;
+                __threadfence_system();
+            }
         }
     }
     if (prof) {

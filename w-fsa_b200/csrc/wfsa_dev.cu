@@ -1675,16 +1675,17 @@ extern "C" int wfsa_dev_eval(wfsa_dev* h, const double* x, double* loglik, doubl
             const int rc = stage_x(h, x);
             if (rc != WFSA_OK) return rc;
             const auto tp1 = std::chrono::steady_clock::now();
-            const unsigned int epoch = ++h->hm_runs;
+            const unsigned int before = *reinterpret_cast<volatile unsigned int*>(h->hm_flag);   // the kernel writes a new count when it is through
+            ++h->hm_runs;
             CK(cudaGraphLaunch(h->e6_exec, h->stream));
             const auto tp2 = std::chrono::steady_clock::now();
             h->launches++; h->e6_used = true; h->evaluated = true; h->ks_done = false; h->lean_now = true; h->lean_finished = true;
             // wait for the completion word of this epoch; every now and then ask the stream whether it failed instead
             volatile unsigned int* flag = h->hm_flag;
-            for (unsigned long long spin = 1; *flag != epoch; ++spin)
+            for (unsigned long long spin = 1; *flag == before; ++spin)
                 if ((spin & 0xfffffull) == 0) {
                     const cudaError_t q = cudaStreamQuery(h->stream);
-                    if (q != cudaErrorNotReady) { if (q != cudaSuccess) CK(q); if (*flag != epoch) { cudaGetLastError(); return set_err(h, WFSA_ERR_CUDA, "k_eval6 finished without its completion word"); } }
+                    if (q != cudaErrorNotReady) { if (q != cudaSuccess) CK(q); if (*flag == before) { cudaGetLastError(); return set_err(h, WFSA_ERR_CUDA, "k_eval6 finished without its completion word"); } }
                 }
             const auto tp3 = std::chrono::steady_clock::now();
             // (the same values are NOT in d_out: a later wfsa_dev_eval_fetch finds them in h_out)
