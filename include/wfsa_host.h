@@ -22,6 +22,14 @@ int wfsa_host_parse(const char* fsa_text, size_t fsa_len, const char* corpus_tex
                     const char** json_out);
 const char* wfsa_host_last_error(void);
 
+/* Host-only (no device): the Newton system of HessianLearner without H_f, [D B; B^T 0] [dx; dl] = rhs with
+ * D = diag(expx_i * lambda[ccol_i]) and B[i, ccol_i] = expx_i (src/HessianLearner.cpp:622-639), solved twice -- through its
+ * diagonal Schur complement (what the optimiser does, O(n)) and through the dense Bunch-Kaufman factorisation that stands
+ * where the reference calls MKL DSS (:100-113).  sol_schur / sol_dense: [n + k]; inertia4 = {+, - of the Schur path, +, - of
+ * the dense path}.  Returns 0, or 1 when the Schur path meets a zero pivot (sol_schur untouched). */
+int wfsa_host_kkt_solve(int32_t n, int32_t k, const double* expx, const double* lambda, const int32_t* ccol, const double* rhs,
+                        double* sol_schur, double* sol_dense, int32_t* inertia4);
+
 typedef struct wfsa_session wfsa_session;
 typedef struct {
     int32_t device, force_kernel, accum_mode, accum_variant;

@@ -156,3 +156,42 @@ def test_cli_gpus_option_without_a_device(tmp_path):
                        capture_output=True, text=True, timeout=120)
     assert r.returncode == 1
     assert any(m in r.stderr for m in ("no CPU fallback", "libnccl", "communicator", "a rank ended with an error")), r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_kkt_diagonal_schur_complement_against_dense_factorisation(seed):
+    """The Newton system of HessianLearner without H_f, [D B; B^T 0] (src/HessianLearner.cpp:622-639; the reference hands it
+    to MKL DSS, :100-113): the O(n) solve through the diagonal Schur complement that the optimiser uses must give the
+    solution and the inertia of the dense Bunch-Kaufman factorisation -- multipliers of both signs, groups of 1..9
+    parameters."""
+    import ctypes as C
+    rng = np.random.RandomState(seed)
+    k = 40 + 10 * seed
+    sizes = rng.randint(1, 10, size=k)
+    ccol = np.repeat(np.arange(k), sizes).astype(np.int32)
+    n = len(ccol)
+    expx = np.exp(rng.normal(-1.0, 1.0, size=n))
+    lam = rng.normal(0.0, 1.0, size=k)
+    lam[np.abs(lam) < 0.05] = 0.3
+    rhs = rng.normal(size=n + k)
+    s1, s2 = np.zeros(n + k), np.zeros(n + k)
+    inertia = np.zeros(4, dtype=np.int32)
+    L = W.lib()
+    L.wfsa_host_kkt_solve.argtypes = [C.c_int32, C.c_int32, W.F64P, W.F64P, W.I32P, W.F64P, W.F64P, W.F64P, W.I32P]
+    rc = L.wfsa_host_kkt_solve(n, k, W._p(expx, W.F64P), W._p(lam, W.F64P), W._p(ccol, W.I32P), W._p(rhs, W.F64P),
+                               W._p(s1, W.F64P), W._p(s2, W.F64P), W._p(inertia, W.I32P))
+    assert rc == 0
+    K = np.zeros((n + k, n + k))
+    K[np.arange(n), np.arange(n)] = expx * lam[ccol]
+    K[np.arange(n), n + ccol] = expx
+    K[n + ccol, np.arange(n)] = expx
+    ref = np.linalg.solve(K, rhs)
+    assert np.allclose(s1, ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    assert np.allclose(s2, ref, rtol=1e-8, atol=1e-8 * np.abs(ref).max())
+    ev = np.linalg.eigvalsh(K)
+    assert (inertia[0], inertia[1]) == (int((ev > 0).sum()), int((ev < 0).sum())) == (inertia[2], inertia[3])
+    # a multiplier that is exactly zero: the Schur path declines (the optimiser then factorises densely)
+    lam[3] = 0.0
+    rc = L.wfsa_host_kkt_solve(n, k, W._p(expx, W.F64P), W._p(lam, W.F64P), W._p(ccol, W.I32P), W._p(rhs, W.F64P),
+                               W._p(s1, W.F64P), W._p(s2, W.F64P), W._p(inertia, W.I32P))
+    assert rc == 1

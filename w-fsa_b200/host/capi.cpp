@@ -57,6 +57,29 @@ static void describe_fsa(std::ostringstream& o, const Fsa& fsa, const std::vecto
     o << ']';
 }
 
+extern "C" int wfsa_host_kkt_solve(int32_t n, int32_t k, const double* expx, const double* lambda, const int32_t* ccol, const double* rhs,
+                                   double* sol_schur, double* sol_dense, int32_t* inertia4)
+{
+    const int N = n + k;
+    std::vector<double> H((size_t)N * N, 0.0), sol;
+    for (int i = 0; i < n; ++i) {                      // HessianLearner::ComputeHg
+        H[(size_t)i * N + i] += expx[i] * lambda[ccol[i]];
+        H[(size_t)i * N + n + ccol[i]] += expx[i];
+        H[(size_t)(n + ccol[i]) * N + i] += expx[i];
+    }
+    SymIndefinite solver;
+    solver.Factor(N, H);
+    solver.Solve(rhs, sol_dense);
+    int pos = 0, neg = 0, zero = 0;
+    solver.Inertia(pos, neg, zero);
+    inertia4[2] = pos; inertia4[3] = neg;
+    int sp = 0, sn = 0;
+    if (!SolveDiagonalKKT(n, k, expx, lambda, ccol, rhs, sol, sp, sn)) { inertia4[0] = inertia4[1] = -1; return 1; }
+    std::copy(sol.begin(), sol.end(), sol_schur);
+    inertia4[0] = sp; inertia4[1] = sn;
+    return 0;
+}
+
 extern "C" const char* wfsa_host_last_error(void) { return g_err.c_str(); }
 
 extern "C" int wfsa_host_parse(const char* fsa_text, size_t fsa_len, const char* corpus_text, size_t corpus_len, const char** json_out)

@@ -511,6 +511,30 @@ void HessianLearner::ComputeHg()                        // src/HessianLearner.cp
     }
 }
 
+// Newton system of the optimiser WITHOUT H_f:  [D B; B^T 0] [dx; dl] = [r_x; r_l]  with D = diag(e^x_i lambda_c(i)) and one entry
+// e^x_i per row of B (every parameter sits in exactly one constraint, src/HessianLearner.cpp:622-639).  The Schur complement
+// B^T D^-1 B on the multipliers is DIAGONAL, S_jj = sum_{i in j} e^x_i / lambda_j: solve and inertia in O(n) instead of a dense
+// (n+k)^3 factorisation (the reference hands the same sparse matrix to MKL DSS, :100-113); inertia by Haynsworth,
+// In(K) = In(D) + In(-S).  Returns false on a zero or non-finite pivot (the caller falls back to the dense factorisation).
+bool SolveDiagonalKKT(int n, int k, const double* expx, const double* lambda, const int* Ccol, const double* rhs,
+                      std::vector<double>& sol, int& pos, int& neg)
+{
+    std::vector<double> S(k, 0.0), t(k, 0.0);
+    pos = neg = 0;
+    for (int i = 0; i < n; ++i) {
+        const double d = expx[i] * lambda[Ccol[i]];
+        if (d == 0.0 || !std::isfinite(d)) return false;
+        (d > 0 ? pos : neg)++;
+        S[Ccol[i]] += expx[i] * expx[i] / d;
+        t[Ccol[i]] += expx[i] * rhs[i] / d;
+    }
+    for (int j = 0; j < k; ++j) { if (S[j] == 0.0 || !std::isfinite(S[j])) return false; (S[j] < 0 ? pos : neg)++; }
+    sol.assign((size_t)n + k, 0.0);
+    for (int j = 0; j < k; ++j) sol[n + j] = (t[j] - rhs[n + j]) / S[j];
+    for (int i = 0; i < n; ++i) sol[i] = (rhs[i] - expx[i] * sol[n + Ccol[i]]) / (expx[i] * lambda[Ccol[i]]);
+    return true;
+}
+
 void HessianLearner::OptimizationStep(double eta, bool)  // src/HessianLearner.cpp:63-130
 {
     const int n = GetNumberOfParameters(), N = GetNumberOfAugmentedParameters();
@@ -519,28 +543,8 @@ void HessianLearner::OptimizationStep(double eta, bool)  // src/HessianLearner.c
     rmin = 0.0;
     diag_solved = false;
     if (!include_Hf) {
-        // Without H_f the KKT matrix is [D B; B^T 0] with D = diag(e^x_i lambda_c(i)) and one entry e^x_i per row of B
-        // (every parameter sits in exactly one constraint, src/HessianLearner.cpp:622-639): the Schur complement
-        // B^T D^-1 B on the multipliers is DIAGONAL, S_jj = sum_{i in j} e^x_i / lambda_j.  Solve and inertia in O(n)
-        // instead of a dense (n+k)^3 factorisation (the reference hands the same sparse matrix to MKL DSS, :100-113);
-        // inertia by Haynsworth: In(K) = In(D) + In(-S).  A zero pivot falls through to the dense path below.
-        const int k = N - n;
-        const double* lambda = _x.data() + n;
-        std::vector<double> S(k, 0.0), t(k, 0.0);
-        bool ok = true;
         int pos = 0, neg = 0;
-        for (int i = 0; i < n && ok; ++i) {
-            const double d = expx[i] * lambda[Ccol[i]];
-            if (d == 0.0 || !std::isfinite(d)) { ok = false; break; }
-            (d > 0 ? pos : neg)++;
-            S[Ccol[i]] += expx[i] * expx[i] / d;
-            t[Ccol[i]] += expx[i] * rhs[i] / d;
-        }
-        for (int j = 0; j < k && ok; ++j) { if (S[j] == 0.0 || !std::isfinite(S[j])) ok = false; else (S[j] < 0 ? pos : neg)++; }
-        if (ok) {
-            aux.assign(N, 0.0);
-            for (int j = 0; j < k; ++j) aux[n + j] = (t[j] - rhs[n + j]) / S[j];
-            for (int i = 0; i < n; ++i) aux[i] = (rhs[i] - expx[i] * aux[n + Ccol[i]]) / (expx[i] * lambda[Ccol[i]]);
+        if (SolveDiagonalKKT(n, N - n, expx.data(), _x.data() + n, Ccol.data(), rhs.data(), aux, pos, neg)) {
             diag_solved = true; diag_pos = pos; diag_neg = neg;
             lambda_min = *std::min_element(_x.begin() + n, _x.end());
             factored = true;

@@ -27,6 +27,8 @@ struct BackendOptions {
     const void* unique_id = nullptr;     // WFSA_UNIQUE_ID_BYTES, required when nranks > 1
 };
 
+bool SolveDiagonalKKT(int n, int k, const double* expx, const double* lambda, const int* Ccol, const double* rhs,
+                      std::vector<double>& sol, int& pos, int& neg);
 double LogFactorial(size_t d);
 double LogSimplexVolume(size_t d);
 double mxlogx(double x);

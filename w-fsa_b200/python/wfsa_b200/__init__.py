@@ -24,7 +24,7 @@ DEV_SYMBOLS = [
     "wfsa_segmented_free",
 ]
 HOST_SYMBOLS = [
-    "wfsa_host_parse", "wfsa_host_last_error", "wfsa_session_create", "wfsa_session_destroy", "wfsa_session_error",
+    "wfsa_host_parse", "wfsa_host_last_error", "wfsa_host_kkt_solve", "wfsa_session_create", "wfsa_session_destroy", "wfsa_session_error",
     "wfsa_session_describe", "wfsa_session_n", "wfsa_session_k", "wfsa_session_n_recognised_local", "wfsa_session_init",
     "wfsa_session_eval", "wfsa_session_hessian", "wfsa_session_step", "wfsa_session_halt", "wfsa_session_get_x",
     "wfsa_session_renormalize", "wfsa_session_result", "wfsa_session_dump", "wfsa_session_backend",
