@@ -1,10 +1,64 @@
 // w-fsa_b200/host/ldlt.cpp -- see ldlt.hpp.  Unblocked Bunch-Kaufman on the lower triangle.
 #include "ldlt.hpp"
 
+#include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <functional>
+#include <thread>
 #include <utility>
 
 namespace wfsa {
+
+namespace {
+// The trailing update of a pivot step touches every column right of the pivot and nothing else of the matrix: columns are
+// dealt out cyclically to a team of host threads that lives for one factorisation and meets at a spinning barrier twice per
+// step (the pivot search and the row/column interchanges stay with the calling thread).  Every element sees the same
+// operations in the same order as in the serial loop: the factor is bit-identical for any team size.
+class ColumnTeam {
+public:
+    explicit ColumnTeam(int threads) : n_(threads)
+    {
+        for (int t = 1; t < n_; ++t) pool_.emplace_back([this, t] { worker(t); });
+    }
+    ~ColumnTeam()
+    {
+        stop_ = true;
+        gen_.fetch_add(1, std::memory_order_release);
+        for (auto& th : pool_) th.join();
+    }
+    int size() const { return n_; }
+    // runs job(t, size) on every member (t = 0 on the caller) and returns when all are done
+    void run(const std::function<void(int, int)>& job)
+    {
+        if (n_ == 1) { job(0, 1); return; }
+        job_ = &job;
+        done_.store(0, std::memory_order_relaxed);
+        gen_.fetch_add(1, std::memory_order_release);
+        job(0, n_);
+        while (done_.load(std::memory_order_acquire) != n_ - 1) { }
+    }
+private:
+    void worker(int t)
+    {
+        unsigned seen = 0;
+        for (;;) {
+            unsigned g;
+            while ((g = gen_.load(std::memory_order_acquire)) == seen) { }
+            seen = g;
+            if (stop_) return;
+            (*job_)(t, n_);
+            done_.fetch_add(1, std::memory_order_release);
+        }
+    }
+    int n_;
+    std::vector<std::thread> pool_;
+    std::atomic<unsigned> gen_{0};
+    std::atomic<int> done_{0};
+    const std::function<void(int, int)>* job_ = nullptr;
+    bool stop_ = false;
+};
+}  // namespace
 
 void SymIndefinite::Factor(int n, const std::vector<double>& a)
 {
@@ -14,6 +68,11 @@ void SymIndefinite::Factor(int n, const std::vector<double>& a)
         for (int j = 0; j <= i; ++j) at(i, j) = a[(size_t)i * n + j];
     piv_.assign(n, 0);
     const double alpha = (1.0 + std::sqrt(17.0)) / 8.0;
+    // (an unblocked factorisation streams the trailing matrix once per step: n^3/6 doubles of memory traffic -- 76 GB for the
+    //  3 849 x 3 849 KKT matrix of config 4 -- so it is worth a team from a few hundred rows on)
+    unsigned hw = std::thread::hardware_concurrency();
+    ColumnTeam team(n >= 512 ? (int)std::max(1u, std::min(hw ? hw : 1u, 32u)) : 1);
+    const int serial_below = 256;                            // columns left: not worth waking the team
     int k = 0;
     while (k < n) {
         int kstep = 1, kp = k;
@@ -42,10 +101,13 @@ void SymIndefinite::Factor(int n, const std::vector<double>& a)
             if (kstep == 1) {
                 if (k < n - 1) {
                     const double r1 = 1.0 / at(k, k);
-                    for (int j = k + 1; j < n; ++j) {
-                        const double f = r1 * at(j, k);
-                        if (f != 0.0) for (int i = j; i < n; ++i) at(i, j) -= at(i, k) * f;
-                    }
+                    auto update = [&](int t, int T) {
+                        for (int j = k + 1 + t; j < n; j += T) {
+                            const double f = r1 * at(j, k);
+                            if (f != 0.0) for (int i = j; i < n; ++i) at(i, j) -= at(i, k) * f;
+                        }
+                    };
+                    if (n - k > serial_below && team.size() > 1) team.run(update); else update(0, 1);
                     for (int i = k + 1; i < n; ++i) at(i, k) *= r1;
                 }
             } else if (k < n - 2) {
@@ -53,13 +115,21 @@ void SymIndefinite::Factor(int n, const std::vector<double>& a)
                 const double d11 = at(k + 1, k + 1) / d21, d22 = at(k, k) / d21;
                 const double t = 1.0 / (d11 * d22 - 1.0);
                 d21 = t / d21;
+                // (the serial loop overwrites at(j, k) and at(j, k+1) with the multipliers as it goes and later columns read the
+                //  ORIGINAL entries of their own row j only, so the team first updates the columns, then stores the multipliers)
+                std::vector<double> wks((size_t)n, 0.0), wkp1s((size_t)n, 0.0);
                 for (int j = k + 2; j < n; ++j) {
-                    const double wk = d21 * (d11 * at(j, k) - at(j, k + 1));
-                    const double wkp1 = d21 * (d22 * at(j, k + 1) - at(j, k));
-                    for (int i = j; i < n; ++i) at(i, j) -= at(i, k) * wk + at(i, k + 1) * wkp1;
-                    at(j, k) = wk;
-                    at(j, k + 1) = wkp1;
+                    wks[j] = d21 * (d11 * at(j, k) - at(j, k + 1));
+                    wkp1s[j] = d21 * (d22 * at(j, k + 1) - at(j, k));
                 }
+                auto update = [&](int t, int T) {
+                    for (int j = k + 2 + t; j < n; j += T) {
+                        const double wk = wks[j], wkp1 = wkp1s[j];
+                        for (int i = j; i < n; ++i) at(i, j) -= at(i, k) * wk + at(i, k + 1) * wkp1;
+                    }
+                };
+                if (n - k > serial_below && team.size() > 1) team.run(update); else update(0, 1);
+                for (int j = k + 2; j < n; ++j) { at(j, k) = wks[j]; at(j, k + 1) = wkp1s[j]; }
             }
         }
         if (kstep == 1) piv_[k] = kp;
