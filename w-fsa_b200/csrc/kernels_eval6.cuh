@@ -358,6 +358,22 @@ __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
     unsigned long long dbg_max = 0;
     long long big = big0;
     long long g = 0;
+    // A dedicated CTA (few big groups: this CTA's only one is group blockIdx.x on warp 0, the other warps wait for it) walks
+    // the two chains of the group on two warps: warp 0 forward, warp 1 backward (kernels_seg.cuh, kr_big_fwd2 / _bwd2 / _red2).
+    bool two = false;
+    int two_nw = 0;
+    if (P.big_dedicate && warp < 2 && (long long)blockIdx.x < P.n_big && P.big_slots >= 2 && !(P.debug & (4 | 128))) {
+        two_nw = (int)((P.goff[blockIdx.x + 1] - P.goff[blockIdx.x]) >> 5);
+        two = two_nw <= P.big_rows && !(P.grows[blockIdx.x] & 0x10000);
+    }
+    if (two && warp == 1) {
+        double* const xs0 = sxs - (size_t)P.big_rows * 48;                                  // warp 0's staging area
+        const unsigned int w0_sa = (unsigned int)__cvta_generic_to_shared(reinterpret_cast<uint32_t*>(xs0 - lane + (size_t)P.big_rows * 32) + lane);
+        asm volatile("bar.sync 1, 64;" ::: "memory");                                        // warp 0 has the words in place
+        kr_big_bwd2(aw, (unsigned int)__cvta_generic_to_shared(pool), (unsigned int)NT * 8u, (unsigned int)__cvta_generic_to_shared(&s_trash[tid]),
+                    w0_sa, two_nw, (unsigned int)__cvta_generic_to_shared(sxs));
+        asm volatile("bar.sync 1, 64;" ::: "memory");                                        // the y stack is complete
+    }
     if (big >= P.n_big) {
         while (*reinterpret_cast<volatile int*>(&s_bigleft) > 0) __nanosleep(500);
         if (lane == 0) g = fetch();
@@ -397,7 +413,24 @@ __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
                     __syncwarp();
                     if (P.debug && lane == 0) atomicMax(P.stamps + 7, e6_timer() - tg0);
                 }
-                if (!(P.debug & 4)) {
+                if (two && warp == 0 && g == big0) {
+                    // (stage_big succeeded for this group: two == the same conditions)
+                    const unsigned int wp_sa = (unsigned int)__cvta_generic_to_shared(sw), xs_sa = (unsigned int)__cvta_generic_to_shared(sxs);
+                    const unsigned int ys_sa = (unsigned int)__cvta_generic_to_shared(sxs + (size_t)P.big_rows * 48);      // warp 1's x-stack area
+                    asm volatile("bar.sync 1, 64;" ::: "memory");
+                    double qh; int EQ; bool any;
+                    kr_big_fwd2(aw, (unsigned int)__cvta_generic_to_shared(pool), (unsigned int)NT * 8u, (unsigned int)__cvta_generic_to_shared(&s_trash[tid]),
+                                wp_sa, nw, xs_sa, qh, EQ, any);
+                    const double W = R.typeW[g * 32 + lane];
+                    const bool ok = any && qh > 0.0 && isfinite(qh);
+                    if (any) {
+                        const double lq = ok ? log(qh) + (double)EQ * 0.69314718055994530942 : -INFINITY;
+                        R.lq[g * 32 + lane] = lq;
+                        kr_loglik(R, W, ok, lq, ll);
+                    }
+                    asm volatile("bar.sync 1, 64;" ::: "memory");
+                    kr_big_red2(wp_sa, nw, xs_sa, ys_sa, ok, ok ? W * R.fx_scale / qh : 0.0, EQ, acc_g);
+                } else if (!(P.debug & 4)) {
                     if (staged) kr_big_t<ACC_GLOBAL, true>(R, aw, pool, NT, g, lane, sw, nw, sxs, acc_g, ll, &s_trash[tid]);
                     else kr_big_t<ACC_GLOBAL, false>(R, aw, pool, NT, g, lane, P.words + off + lane, nw, xs, acc_g, ll, &s_trash[tid]);
                 }

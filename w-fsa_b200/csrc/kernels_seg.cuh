@@ -275,6 +275,143 @@ __device__ __forceinline__ void kr_big_t(const KRParams& P, const double* aw, do
     }
 }
 
+// ---- one big DAG group on TWO warps (k_eval6, a staged group on a dedicated CTA) ---------------------------------------
+// The chain of a region costs a lone warp ~4 cycles per instruction whatever is done about its dependencies (interleaving
+// the forward with the backward chain in one instruction stream was measured twice: slower).  But the two chains are
+// independent until the posteriors -- alpha needs the weights only, beta as well -- so they can run on two warps, i.e. two
+// schedulers: warp 0 walks the words forward (x stack: alpha_src * w per edge, E at the CHECK words), warp 1 backward on its own
+// pool (y stack: beta_dst per edge, F at the CHECK words), and warp 0 then forms (x * y) * sc in the order and with the scale
+// factors of kr_big_t -- bitwise the same posteriors -- and issues the REDs.  All addresses are shared-memory byte addresses of
+// the calling lane's column: wp_sa words [rows][32] u32, xs_sa / ys_sa stacks [rows][32] f64, pool at stride NT doubles.
+__device__ __forceinline__ double bg_lds(unsigned int a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void bg_sts(unsigned int a, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v)); }
+__device__ __forceinline__ uint32_t bg_ldw(unsigned int wp_sa, int i) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(wp_sa + (unsigned int)i * 128u)); return v; }
+__device__ __forceinline__ void bg_st64(unsigned int base, int i, long long v) { asm volatile("st.shared.b64 [%0], %1;" :: "r"(base + (unsigned int)i * 256u), "l"(v)); }
+__device__ __forceinline__ long long bg_ld64(unsigned int base, int i) { long long v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(base + (unsigned int)i * 256u)); return v; }
+__device__ __forceinline__ int bg_exp(unsigned int a) { int hi; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(a + 4u)); return (hi >> 20) & 0x7ff; }
+
+// forward chain; returns q (its exponent in EQ) and whether the lane holds a region at all
+__device__ __forceinline__ void kr_big_fwd2(const double* aw, unsigned int p_sa, unsigned int ps, unsigned int tr_sa, unsigned int wp_sa, int nw,
+                                            unsigned int xs_sa, double& qh, int& EQ, bool& any)
+{
+    bg_sts(p_sa, 1.0);
+    int E = 0;
+    EQ = 0; qh = 0.0; any = false;
+    for (int i0 = 0; i0 < nw; i0 += 8) {
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = bg_ldw(wp_sa, i0 + j);
+        const bool chk = (i0 & 8) != 0;
+        const uint32_t m0 = chk ? w[7] & 0xffffu : 0u;
+        if (chk) w[7] = 0u;
+        unsigned int fs[8], fd[8];
+        double fw[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t wj = w[j];
+            const bool edge = (wj & kLEdge) != 0;
+            fs[j] = p_sa + (edge ? (wj >> 19) & 15u : (wj & 15u)) * ps;
+            fd[j] = edge ? p_sa + ((wj >> 23) & 15u) * ps : tr_sa;
+            fw[j] = aw[edge ? (wj & 0xffffu) : 0u];
+            any |= edge;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t wj = w[j];
+            const bool fin = (wj & (kLEdge | kLFin)) == kLFin;
+            const double a = bg_lds(fs[j]);
+            const double xv = a * fw[j];
+            const double old = bg_lds(fd[j]);
+            bg_sts(fd[j], (wj & kLFirstIn) ? xv : old + xv);
+            bg_st64(xs_sa, i0 + j, __double_as_longlong(xv));
+            qh = fin ? a : qh;
+            EQ = fin ? E : EQ;
+        }
+        if (chk) {
+            bg_st64(xs_sa, i0 + 7, (long long)E);
+            if (m0) {
+                int emax = 0;
+                for (uint32_t m = m0; m; m &= m - 1) emax = max(emax, bg_exp(p_sa + (unsigned int)(__ffs(m) - 1) * ps));
+                if (emax != 0 && (emax < 1023 - kLBand || emax > 1023 + kLBand)) {
+                    const int shift = 1023 - emax;
+                    for (uint32_t m = m0; m; m &= m - 1) { const unsigned int a = p_sa + (unsigned int)(__ffs(m) - 1) * ps; bg_sts(a, scalbn(bg_lds(a), shift)); }
+                    E -= shift;
+                }
+            }
+        }
+    }
+}
+
+// backward chain on the caller's own pool: beta of the target node of every edge to the y stack, F to the CHECK slots
+__device__ __forceinline__ void kr_big_bwd2(const double* aw, unsigned int p_sa, unsigned int ps, unsigned int tr_sa, unsigned int wp_sa, int nw,
+                                            unsigned int ys_sa)
+{
+    int F = 0;
+    for (int i0 = nw - 8; i0 >= 0; i0 -= 8) {
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = bg_ldw(wp_sa, i0 + j);
+        const bool chk = (i0 & 8) != 0;
+        if (chk) {                                             // the CHECK word comes first in backward order
+            const uint32_t m0 = w[7] & 0xffffu;
+            if (m0) {
+                int emax = 0;
+                for (uint32_t m = m0; m; m &= m - 1) emax = max(emax, bg_exp(p_sa + (unsigned int)(__ffs(m) - 1) * ps));
+                if (emax != 0 && (emax < 1023 - kLBand || emax > 1023 + kLBand)) {
+                    const int shift = 1023 - emax;
+                    for (uint32_t m = m0; m; m &= m - 1) { const unsigned int a = p_sa + (unsigned int)(__ffs(m) - 1) * ps; bg_sts(a, scalbn(bg_lds(a), shift)); }
+                    F -= shift;
+                }
+            }
+            bg_st64(ys_sa, i0 + 7, (long long)F);
+            w[7] = 0u;
+        }
+        unsigned int bd_[8], bs[8];
+        double bw[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t wj = w[j];
+            const bool edge = (wj & kLEdge) != 0;
+            bd_[j] = p_sa + ((wj >> 23) & 15u) * ps;
+            bs[j] = (wj & (kLEdge | kLFin)) ? p_sa + (edge ? (wj >> 19) & 15u : (wj & 15u)) * ps : tr_sa;
+            bw[j] = aw[edge ? (wj & 0xffffu) : 0u];
+        }
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+            const uint32_t wj = w[j];
+            const bool fin = (wj & (kLEdge | kLFin)) == kLFin;
+            const double bd = bg_lds(bd_[j]);
+            const double c = bw[j] * bd;
+            const double old = bg_lds(bs[j]);
+            bg_sts(bs[j], fin ? 1.0 : ((wj & kLLastOut) ? c : old + c));
+            if (!(j == 7 && chk)) bg_st64(ys_sa, i0 + j, __double_as_longlong(bd));
+        }
+    }
+}
+
+// posteriors (x * y) * sc and their REDs; sc follows the CHECK words exactly as in kr_big_t
+__device__ __forceinline__ void kr_big_red2(unsigned int wp_sa, int nw, unsigned int xs_sa, unsigned int ys_sa, bool ok, double sc0, int EQ,
+                                            unsigned long long* acc_g)
+{
+    double sc = sc0;
+    for (int i0 = nw - 8; i0 >= 0; i0 -= 8) {
+        uint32_t w[8];
+        long long x[8], y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { w[j] = bg_ldw(wp_sa, i0 + j); x[j] = bg_ld64(xs_sa, i0 + j); y[j] = bg_ld64(ys_sa, i0 + j); }
+        if (i0 & 8) {
+            if (w[7] & 0xffffu) sc = scalbn(sc0, (int)x[7] + (int)y[7] - EQ);
+            w[7] = 0u;
+        }
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+            if (!(w[j] & kLEdge) || !ok) continue;
+            const long long v = __double2ll_rn(__longlong_as_double(x[j]) * __longlong_as_double(y[j]) * sc);
+            if (v) red_add64(acc_g + (w[j] & 0xffff), (unsigned long long)v);
+        }
+    }
+}
+
 template <int ACC>
 __device__ __forceinline__ void kr_big(const KRParams& P, const double* aw, double* pool, int NT, long long g, int lane,
                                        double* xs, unsigned long long* acc_g, long long& ll, double* trash)
