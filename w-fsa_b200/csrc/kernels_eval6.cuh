@@ -358,11 +358,12 @@ __global__ void __launch_bounds__(NT, 1) k_eval6(const Eval6Params P)
     unsigned long long dbg_max = 0;
     long long big = big0;
     long long g = 0;
-    // A dedicated CTA (few big groups: this CTA's only one is group blockIdx.x on warp 0, the other warps wait for it) walks
-    // the two chains of the group on two warps: warp 0 forward, warp 1 backward (kernels_seg.cuh, kr_big_fwd2 / _bwd2 / _red2).
+    // At most one big group per CTA (n_big <= grid: group blockIdx.x on warp 0): the CTA walks the two chains of the group on
+    // two warps, warp 0 forward, warp 1 backward (kernels_seg.cuh, kr_big_fwd2 / _bwd2 / _red2); warp 1 joins the regular groups
+    // afterwards.
     bool two = false;
     int two_nw = 0;
-    if (P.big_dedicate && warp < 2 && (long long)blockIdx.x < P.n_big && P.big_slots >= 2 && !(P.debug & (4 | 128))) {
+    if (P.n_big <= (long long)gridDim.x && warp < 2 && (long long)blockIdx.x < P.n_big && P.big_slots >= 2 && !(P.debug & (4 | 128))) {
         two_nw = (int)((P.goff[blockIdx.x + 1] - P.goff[blockIdx.x]) >> 5);
         two = two_nw <= P.big_rows && !(P.grows[blockIdx.x] & 0x10000);
     }
