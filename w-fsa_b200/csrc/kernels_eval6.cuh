@@ -9,7 +9,9 @@
 //       ticket counter of the NEXT evaluation (two of each, used alternately);
 //   P1  region types, 32 to a warp, handed out by a ticket counter (kr_regions' loop).  Path-form types of the common
 //       shapes are fully unrolled: all rows of a group are loaded in one round trip and stay in registers for the REDs;
-//       group descriptors of the regular classes come from a class table in shared memory, not from HBM;
+//       group descriptors of the regular classes come from a class table in shared memory, not from HBM; big DAG groups are
+//       staged in shared memory and, when a CTA owns one, walked by two warps (forward chain on warp 0, backward chain on
+//       warp 1, kernels_seg.cuh kr_big_fwd2 / _bwd2 / _red2);
 //   P2  grid barrier (arrival counter in HBM);
 //   P3  fold: one warp per edge gathers the (arc, replica) cells of the edge; with several ranks the per-edge sums are
 //       exchanged through NVLink peer memory as self-validating packets (ll_exchange, kernels_seg.cuh) and the warp
