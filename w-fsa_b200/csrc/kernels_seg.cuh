@@ -124,13 +124,6 @@ __device__ __forceinline__ void kr_paths(const KRParams& P, const double* aw, in
 // streamed from HBM (wp = P.words + goff[g] + lane), stack in HBM (one slab per warp).  STAGED = true (k_eval6): the
 // caller copied the nw word rows of the group to shared memory (wp) and the stack lives there as well, so that the serial
 // chain of a region (up to ~100 dependent steps, twice) runs at shared-memory latency.
-// 64-bit add of a possibly zero value: predicated inside the instruction, so that the caller's loop body stays one
-// basic block (a branch per step kept ptxas from overlapping the steps of the serial chain below)
-__device__ __forceinline__ void red_add64_nz(unsigned long long* p, long long v)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s64 p, %1, 0;\n\t@p red.relaxed.gpu.global.add.u64 [%0], %1;\n\t}" :: "l"(p), "l"(v) : "memory");
-}
-
 template <int ACC, bool STAGED>
 __device__ __forceinline__ void kr_big_t(const KRParams& P, const double* aw, double* pool, int NT, long long g, int lane,
                                          const uint32_t* wp, int nw, double* xs, unsigned long long* acc_g, long long& ll, double* trash)
