@@ -895,7 +895,8 @@ static void fill_eval6_params(wfsa_dev* h, Eval6Params& P)
     P.stamps = h->d_e6stamps.p;
     P.debug = getenv("WFSA_E6_DEBUG") ? atoi(getenv("WFSA_E6_DEBUG")) : 0;
     P.pool_slots = h->kl_K; P.big_slots = h->e6_big_slots; P.big_rows = h->e6_big_rows;
-    P.big_dedicate = (h->kr_big_groups > 0 && h->kr_big_groups * 4 <= h->kl_grid && !getenv("WFSA_E6_NO_DEDICATE")) ? 1 : 0;
+    const int ded_div = getenv("WFSA_E6_DED_DIV") ? std::max(1, atoi(getenv("WFSA_E6_DED_DIV"))) : 4;      // dedicate CTAs up to grid / 4 big groups
+    P.big_dedicate = (h->kr_big_groups > 0 && h->kr_big_groups * ded_div <= h->kl_grid && !getenv("WFSA_E6_NO_DEDICATE")) ? 1 : 0;
     // dedicated CTAs: the shard is small (a few regular groups per warp): everything static among the free CTAs; one global
     // ticket counter for ~3.5 k groups costs ~3 ns per ticket in the L2, i.e. ~10 us of a ~14 us phase
     if (P.big_dedicate && !getenv("WFSA_E6_STATIC")) P.static_pct = 100;
